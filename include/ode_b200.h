@@ -1,0 +1,231 @@
+/* ode_b200.h -- C ABI of libode_b200.so: the B200 (sm_100a) implementation of
+ * ODE.jl's Runge-Kutta / Rosenbrock integration hot path.
+ *
+ * The reference (SciML/ODE.jl v2.15.0, pure Julia) has no FFI layer; the
+ * boundary this ABI replaces is the call of the drivers
+ *     oderk_adapt   src/runge_kutta.jl:232-369   (ode21/ode23/ode45_fe/ode45_dp/ode45/ode78, :218-224)
+ *     oderk_fixed   src/runge_kutta.jl:176-212   (ode1/ode2_midpoint/ode2_heun/ode4, :165-168)
+ *     ode23s        src/ODE.jl:252-361
+ * made by the `odeXX(F, y0, tspan; reltol, abstol, minstep, maxstep, initstep,
+ * points)` front-ends and by `solve(prob, alg)` (src/common.jl:93-100).
+ * A Julia closure cannot run on the device, so `F` crosses the ABI as a
+ * registered right-hand-side id plus a parameter vector.
+ *
+ * Conventions
+ *  - plain C, no C++/torch types; every entry point returns 0 on success or a
+ *    negative ODE_B200_E_* code and never unwinds; ode_b200_last_error() gives a
+ *    thread-local message.
+ *  - the caller owns every buffer it passes for the duration of the call; the
+ *    library owns device memory and the opaque handles it returns.
+ *  - all arithmetic is IEEE binary64 with no fused multiply-add in the solver
+ *    arithmetic and the reference's association order; `^` and `log10` are the
+ *    deterministic ones of ode_b200_detmath.h.
+ *  - there is no CPU fallback: without a usable CUDA device every solve entry
+ *    point fails with ODE_B200_E_NO_DEVICE.
+ */
+#ifndef ODE_B200_H
+#define ODE_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define ODE_B200_ABI_VERSION 1
+
+/* ---- methods: one per reference tableau / driver ------------------------- */
+typedef enum {
+  ODE_B200_M_FEULER = 0,   /* ode1           bt_feuler   src/runge_kutta.jl:66  */
+  ODE_B200_M_MIDPOINT = 1, /* ode2_midpoint  bt_midpoint :71 */
+  ODE_B200_M_HEUN = 2,     /* ode2_heun      bt_heun     :77 */
+  ODE_B200_M_RK4 = 3,      /* ode4           bt_rk4      :83 */
+  ODE_B200_M_RK21 = 4,     /* ode21          bt_rk21     :93 */
+  ODE_B200_M_RK23 = 5,     /* ode23          bt_rk23     :101 */
+  ODE_B200_M_RK45_FE = 6,  /* ode45_fe       bt_rk45     :112 */
+  ODE_B200_M_DOPRI5 = 7,   /* ode45 = ode45_dp  bt_dopri5 :124 */
+  ODE_B200_M_FEH78 = 8,    /* ode78          bt_feh78    :140 */
+  ODE_B200_M_ODE23S = 9,   /* ode23s         src/ODE.jl:252 */
+  ODE_B200_M_COUNT = 10
+} ode_b200_method;
+
+/* ---- registered right-hand sides F(t, y; params) ------------------------- */
+typedef enum {
+  ODE_B200_RHS_LINEAR = 0,    /* dof 1: a*u              params {a}   (README.md:19, test/runtests.jl:54) */
+  ODE_B200_RHS_CONST = 1,     /* dof 1: c                params {c}   (test/runtests.jl:40) */
+  ODE_B200_RHS_TIMELIN = 2,   /* dof 1: c*t              params {c}   (test/runtests.jl:47) */
+  ODE_B200_RHS_ROTATION = 3,  /* dof 2: [-y2, y1]                     (test/runtests.jl:67) */
+  ODE_B200_RHS_LORENZ = 4,    /* dof 3: params {sigma, rho, beta}     (examples/Lorenz_Attractor.ipynb) */
+  ODE_B200_RHS_VDP = 5,       /* dof 2: [y2, mu*((1-y1*y1)*y2) - y1]  params {mu} */
+  ODE_B200_RHS_ROBERTSON = 6, /* dof 3: params {k1, k2, k3}           (test/runtests.jl:81-87) */
+  ODE_B200_RHS_KEPLER = 7,    /* dof 4: planar two-body, mu = 1 */
+  ODE_B200_RHS_REACTION_DIFFUSION = 8, /* dof N: kappa*((u[i-1]-2u[i])+u[i+1]) + (r*u[i])*(1-u[i]), periodic; params {kappa, r} */
+  ODE_B200_RHS_COUNT = 9
+} ode_b200_rhs;
+
+/* `points` keyword (src/runge_kutta.jl:238,283-290); FINAL is an ensemble-only
+ * extension that skips all intermediate output. */
+typedef enum {
+  ODE_B200_POINTS_ALL = 0,
+  ODE_B200_POINTS_SPECIFIED = 1,
+  ODE_B200_POINTS_FINAL = 2
+} ode_b200_points;
+
+/* per-trajectory status */
+typedef enum {
+  ODE_B200_ST_OK = 0,
+  ODE_B200_ST_MINSTEP = 1,   /* "Warning: dt < minstep.  Stopping." src/runge_kutta.jl:358-360; truncated result */
+  ODE_B200_ST_MAXSTEPS = 2,  /* max_steps guard hit (the reference would keep looping) */
+  ODE_B200_ST_NONFINITE = 3, /* dt became NaN/Inf (the reference would loop forever) */
+  ODE_B200_ST_SINGULAR = 4,  /* ode23s: zero pivot in W = I - h*d*J (Julia raises SingularException) */
+  ODE_B200_ST_OVERFLOW = 5   /* points buffer too small; n_points holds the required count */
+} ode_b200_status;
+
+/* error codes */
+#define ODE_B200_OK 0
+#define ODE_B200_E_INVALID (-1)      /* bad argument */
+#define ODE_B200_E_ZERO_SPAN (-2)    /* "Zero time span"             src/ODE.jl:88 */
+#define ODE_B200_E_INITSTEP (-3)     /* "initstep has wrong sign."   src/runge_kutta.jl:294 */
+#define ODE_B200_E_POINTS (-4)       /* "Unrecognized option points" src/runge_kutta.jl:289 */
+#define ODE_B200_E_NOT_ADAPTIVE (-5) /* "Can only use this solver with an adaptive RK Butcher table" :249 */
+#define ODE_B200_E_NO_DEVICE (-6)    /* no CUDA device / driver */
+#define ODE_B200_E_CUDA (-7)         /* CUDA runtime error, see last_error */
+#define ODE_B200_E_UNSUPPORTED (-8)  /* rhs/method/dof combination not compiled */
+#define ODE_B200_E_NOMEM (-9)
+
+/* Options.  The host shim fills the reference's defaults
+ * (reltol 1e-5, abstol 1e-8, minstep span/1e18, maxstep span/2.5, initstep 0,
+ * points ALL: src/runge_kutta.jl:233-239, src/ODE.jl:253-259). */
+typedef struct {
+  int32_t method;    /* ode_b200_method */
+  int32_t rhs;       /* ode_b200_rhs */
+  int32_t dof;       /* state length per trajectory (N for the large system) */
+  int32_t n_params;  /* parameters per trajectory */
+  int32_t params_stride; /* 0: one shared parameter vector; else doubles between trajectories */
+  int32_t points;    /* ode_b200_points */
+  int32_t jacobian;  /* ode23s: 0 = forward-difference fdjacobian (reference default), 1 = analytic functor */
+  int32_t device;    /* CUDA device ordinal */
+  int64_t max_steps; /* guard on step attempts per trajectory; <=0 -> 100000000 */
+  double reltol, abstol, minstep, maxstep, initstep;
+  int32_t mathmode;  /* 0 = detmath pow/log10 (only mode of the library); the oracle also accepts 1 = libm */
+  int32_t reserved[7];
+} ode_b200_opts;
+
+/* Ensemble I/O.  Host arrays are row-major [trajectory][...]; NULL outputs are
+ * skipped.  `tspan` is shared by all trajectories (tspan[0] = start,
+ * tspan[n_tspan-1] = end, interior entries are output points). */
+typedef struct {
+  int64_t n_traj;
+  const double* y0;     /* [n_traj][dof] */
+  const double* params; /* [n_traj][n_params] or [n_params] when params_stride == 0 */
+  const double* tspan;  /* [n_tspan] */
+  int32_t n_tspan;
+  int32_t pad0;
+  double* t_final;      /* [n_traj]  last output time (tout[end]) */
+  double* y_final;      /* [n_traj][dof]  yout[end] */
+  int32_t* n_accept;    /* [n_traj] */
+  int32_t* n_reject;    /* [n_traj] */
+  int32_t* n_rhs;       /* [n_traj] RHS evaluations */
+  int32_t* status;      /* [n_traj] ode_b200_status */
+  /* points output (ALL / SPECIFIED): tout, yout per trajectory, capacity pts_cap points each */
+  double* pts_t;        /* [n_traj][pts_cap] */
+  double* pts_y;        /* [n_traj][pts_cap][dof] */
+  int32_t* pts_n;       /* [n_traj] points written (required count on overflow) */
+  int64_t pts_cap;
+  /* optional attempt trace of ONE trajectory: rows (t, dt, err, accepted) */
+  int64_t trace_traj;   /* trajectory index, -1 = none */
+  double* trace;        /* [trace_cap][4] */
+  int64_t trace_cap;
+  int64_t* trace_n;     /* attempts recorded */
+} ode_b200_ensemble_io;
+
+/* ---- library info --------------------------------------------------------- */
+int ode_b200_version(void);                 /* ODE_B200_ABI_VERSION */
+const char* ode_b200_last_error(void);      /* thread-local, never NULL */
+int ode_b200_device_count(void);            /* CUDA devices visible, 0 if none */
+int ode_b200_rhs_id(const char* name);      /* "lorenz" -> id, <0 unknown */
+int ode_b200_method_id(const char* name);   /* "ode45" -> id, <0 unknown */
+int ode_b200_rhs_dof(int rhs);              /* fixed dof of a registered rhs, 0 = variable */
+int ode_b200_rhs_nparams(int rhs);
+int ode_b200_method_stages(int method);     /* S of the tableau (src/runge_kutta.jl:66-157), 3 for ode23s */
+int ode_b200_method_is_adaptive(int method);/* isadaptive, src/runge_kutta.jl:58 */
+int ode_b200_method_is_fsal(int method);    /* isFSAL, src/runge_kutta.jl:62 */
+/* Tableau entry as the reference converts it (Rational -> Float64, src/ODE.jl:163).
+ * which: 0 = a[i][j], 1 = b[i][j] (i = 0 stepping row, 1 error row), 2 = c[i]. */
+double ode_b200_tableau(int method, int which, int i, int j);
+
+/* ---- ensembles of small systems (one trajectory per thread) -------------- */
+/* Replaces n_traj independent calls of oderk_adapt / oderk_fixed / ode23s.
+ * Host buffers; H2D, kernel and D2H happen inside the call. */
+int ode_b200_solve_ensemble(const ode_b200_opts* opts, const ode_b200_ensemble_io* io);
+/* Same, but every pointer in `io` is a device pointer on opts->device (tspan
+ * included); work is enqueued on `stream` (a cudaStream_t, NULL = default
+ * stream) and the call returns without synchronising. */
+int ode_b200_solve_ensemble_dev(const ode_b200_opts* opts, const ode_b200_ensemble_io* io, void* stream);
+/* Milliseconds the last ensemble kernel of this thread took (CUDA events on its stream). */
+double ode_b200_last_kernel_ms(void);
+/* Number of kernel launches issued by this thread since the last reset. */
+int64_t ode_b200_launch_count(int reset);
+
+/* ---- one system, reference return contract (tout, yout) ------------------ */
+typedef struct ode_b200_result ode_b200_result;
+/* Replaces one call of odeXX(F, y0, tspan; ...): result holds tout/yout with
+ * the reference's length rules (src/runge_kutta.jl:321-340, src/ODE.jl:329-345). */
+int ode_b200_solve_single(const ode_b200_opts* opts, const double* y0, const double* params,
+                          const double* tspan, int32_t n_tspan, ode_b200_result** out);
+int64_t ode_b200_result_len(const ode_b200_result* r);
+int32_t ode_b200_result_dof(const ode_b200_result* r);
+int32_t ode_b200_result_status(const ode_b200_result* r);
+int64_t ode_b200_result_counts(const ode_b200_result* r, int which); /* 0 accepted, 1 rejected, 2 rhs calls */
+int ode_b200_result_copy(const ode_b200_result* r, double* tout, double* yout /*[len][dof]*/);
+void ode_b200_result_free(ode_b200_result* r);
+
+/* ---- one large method-of-lines system (fused stage kernels, HBM-bound) ---- */
+typedef struct {
+  int64_t n_accept, n_reject, n_rhs;
+  int32_t status;
+  int32_t pad;
+  double t_final;
+  double kernel_ms; /* device time of the whole integration loop */
+} ode_b200_large_stats;
+
+/* Replaces one call of oderk_adapt on a dof = N state with the registered
+ * stencil RHS.  Host buffers in/out, one GPU.  trace (optional): rows
+ * (t, dt, err, accepted) per attempt. */
+int ode_b200_solve_large(const ode_b200_opts* opts, int64_t n, const double* y0, const double* params,
+                         double t0, double tend, double* y_out, ode_b200_large_stats* stats,
+                         double* trace, int64_t trace_cap, int64_t* trace_n);
+
+/* Slab session for the domain-decomposed path: every rank owns n_local
+ * contiguous points of an n_global periodic grid plus ghost cells; between the
+ * two halves of an attempt the host exchanges `xchg_send` (ODE_B200_XCHG_DOUBLES
+ * doubles per rank) with an all-gather into `xchg_recv` ([world][XCHG]).
+ * All pointers are device pointers; work is enqueued on `stream`. */
+#define ODE_B200_XCHG_DOUBLES 32
+typedef struct ode_b200_slab ode_b200_slab;
+int ode_b200_slab_create(const ode_b200_opts* opts, int64_t n_local, int64_t n_global, int32_t rank,
+                         int32_t world, const double* params, double t0, double tend, void* stream,
+                         ode_b200_slab** out);
+int ode_b200_slab_set_state(ode_b200_slab* s, const double* y_local_dev); /* [n_local] device */
+int ode_b200_slab_get_state(ode_b200_slab* s, double* y_local_dev);
+/* hinit (src/ODE.jl:85-112) in three phases, each followed by an exchange */
+int ode_b200_slab_init_phase(ode_b200_slab* s, int phase, double* xchg_send, const double* xchg_recv);
+/* one attempt: stages + local error partials -> xchg_send */
+int ode_b200_slab_attempt(ode_b200_slab* s, double* xchg_send);
+/* controller: reduce gathered partials, accept/reject, new dt, ghost refresh */
+int ode_b200_slab_control(ode_b200_slab* s, const double* xchg_recv);
+/* copy the control block {done, status, n_accept, n_reject, t, dt, err} to host (synchronises stream) */
+int ode_b200_slab_poll(ode_b200_slab* s, double* ctl_out /*[8]*/);
+void ode_b200_slab_free(ode_b200_slab* s);
+
+/* ---- measurement hooks ---------------------------------------------------- */
+/* Register-resident DFMA/DADD/DMUL chain microbenchmark: returns FP64
+ * instructions per second of the given kind (0 = DFMA, 1 = DADD+DMUL mix) on
+ * opts device, <0 on error.  Used as the ensemble roofline denominator
+ * (SURVEY.md F10). */
+double ode_b200_fp64_peak(int device, int kind);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* ODE_B200_H */

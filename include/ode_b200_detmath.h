@@ -1,0 +1,215 @@
+/* ode_b200_detmath.h -- deterministic pow / log10 shared by host and device.
+ *
+ * Why this exists: the reference's step controllers call Base `^` and `log10`
+ * (/root/reference src/runge_kutta.jl:436 `(1/err)^(1/(order+1))`,
+ * src/ODE.jl:107-108 `10^(-(2+log10(..))/(p+1))`, src/ODE.jl:357
+ * `(delta/err)^(1/3)`).  Julia's, glibc's and CUDA's libm differ at the ulp
+ * level, and one ulp in `newdt` is enough to make a CUDA kernel and a CPU
+ * checker diverge bit-wise.  This header is a single implementation built only
+ * from IEEE-754 binary64 add/mul/fma (all correctly rounded on x86-64 and on
+ * sm_100a) plus integer bit manipulation and two small tables, so the very same
+ * bits come out on the CPU and on the GPU.  Its results are within
+ * 0.5 ulp + ~2^-15 ulp of the exact value in the domain the solvers use
+ * (|y*log(x)| < 64), i.e. they equal the correctly rounded result except in
+ * rare near-tie cases (checked against mpmath in tests/test_detmath.py).
+ *
+ * Technique (standard, table-driven): log via an exact fma reduction
+ * r = z*invc - 1 with an 8-bit invc and a 128-entry log(c) table kept as
+ * hi + lo, a degree-10 Taylor tail, result carried as a double-double; exp via
+ * k = round(x*128/ln2), an exact hi reduction, a 128-entry 2^(j/128) table and a
+ * final compensated `th + th*q + ...` so there is one effective rounding.
+ *
+ * Compile flags that matter: device code with -fmad=false, host code with
+ * -ffp-contract=off, so that nothing except the explicit dm_fma calls fuses.
+ */
+#ifndef ODE_B200_DETMATH_H
+#define ODE_B200_DETMATH_H
+
+#include <stdint.h>
+#include <string.h>
+#include <math.h>
+
+#include "ode_b200_detmath_tables.h"
+
+#if defined(__CUDACC__)
+#define DM_HD __host__ __device__ __forceinline__
+#else
+#define DM_HD static inline
+#endif
+
+/* ---- tables: one host copy, one device copy (same bits) ------------------ */
+#define DM_X3(a, b, c) a, b, c,
+#define DM_X2(a, b) a, b,
+static const double dm_logtab_h[128 * 3] = {DM_LOG_TABLE(DM_X3)};
+static const double dm_exptab_h[128 * 2] = {DM_EXP_TABLE(DM_X2)};
+#if defined(__CUDACC__)
+static __device__ const double dm_logtab_d[128 * 3] = {DM_LOG_TABLE(DM_X3)};
+static __device__ const double dm_exptab_d[128 * 2] = {DM_EXP_TABLE(DM_X2)};
+#endif
+
+#if defined(__CUDA_ARCH__)
+#define DM_LOGTAB(i) dm_logtab_d[(i)]
+#define DM_EXPTAB(i) dm_exptab_d[(i)]
+#else
+#define DM_LOGTAB(i) dm_logtab_h[(i)]
+#define DM_EXPTAB(i) dm_exptab_h[(i)]
+#endif
+
+DM_HD uint64_t dm_bits(double x) {
+#if defined(__CUDA_ARCH__)
+  return (uint64_t)__double_as_longlong(x);
+#else
+  uint64_t u;
+  memcpy(&u, &x, 8);
+  return u;
+#endif
+}
+DM_HD double dm_from_bits(uint64_t u) {
+#if defined(__CUDA_ARCH__)
+  return __longlong_as_double((long long)u);
+#else
+  double x;
+  memcpy(&x, &u, 8);
+  return x;
+#endif
+}
+DM_HD double dm_fma(double a, double b, double c) {
+#if defined(__CUDA_ARCH__)
+  return __fma_rn(a, b, c);
+#else
+  return __builtin_fma(a, b, c);
+#endif
+}
+
+typedef struct {
+  double hi, lo;
+} dm_dd;
+
+/* s + e = a + b exactly (Knuth two-sum, no magnitude precondition). */
+DM_HD dm_dd dm_two_sum(double a, double b) {
+  dm_dd r;
+  double s = a + b;
+  double bb = s - a;
+  double e = (a - (s - bb)) + (b - bb);
+  r.hi = s;
+  r.lo = e;
+  return r;
+}
+
+/* log(x) as a double-double for finite normal-or-subnormal x > 0. */
+DM_HD dm_dd dm_log_dd(double x) {
+  uint64_t ix = dm_bits(x);
+  int64_t kadj = 0;
+  if (ix < 0x0010000000000000ULL) { /* subnormal: scale by 2^52 (exact) */
+    x = x * 4503599627370496.0;
+    ix = dm_bits(x);
+    kadj = -52;
+  }
+  const uint64_t OFF = 0x3FE6A00000000000ULL; /* 181/256 */
+  uint64_t tmp = ix - OFF;
+  int i = (int)((tmp >> 45) & 127);
+  int64_t k = ((int64_t)tmp >> 52) + kadj;
+  uint64_t iz = ix - (tmp & 0xFFF0000000000000ULL);
+  double z = dm_from_bits(iz);
+  double kd = (double)k;
+  double invc = DM_LOGTAB(3 * i), logc = DM_LOGTAB(3 * i + 1), logct = DM_LOGTAB(3 * i + 2);
+
+  double r = dm_fma(z, invc, -1.0);         /* exact */
+  double t1 = dm_fma(kd, DM_LN2_HI, logc);  /* exact: both on the 2^-42 grid */
+  dm_dd a = dm_two_sum(t1, r);              /* t1 + r */
+  double r2 = r * r;
+  double r2e = dm_fma(r, r, -r2);           /* r*r = r2 + r2e */
+  dm_dd b = dm_two_sum(a.hi, -0.5 * r2);    /* ... - r^2/2 */
+  /* r^3/3 - r^4/4 + ... + r^9/9 - r^10/10 */
+  double p = -0.1;
+  p = dm_fma(p, r, 0x1.c71c71c71c71cp-4);   /* 1/9 */
+  p = dm_fma(p, r, -0.125);
+  p = dm_fma(p, r, 0x1.2492492492492p-3);   /* 1/7 */
+  p = dm_fma(p, r, -0x1.5555555555555p-3);  /* 1/6 */
+  p = dm_fma(p, r, 0.2);
+  p = dm_fma(p, r, -0.25);
+  p = dm_fma(p, r, 0x1.5555555555555p-2);   /* 1/3 */
+  p = p * (r * r2);
+  double lo = ((a.lo + b.lo) + (-0.5 * r2e)) + dm_fma(kd, DM_LN2_LO, logct);
+  lo = lo + p;
+  dm_dd res;
+  res.hi = b.hi + lo;
+  res.lo = (b.hi - res.hi) + lo; /* fast two-sum: |b.hi| >= |lo| or both tiny */
+  return res;
+}
+
+/* exp(ehi + elo), |ehi| < ~745, |elo| << |ehi|. */
+DM_HD double dm_exp_dd(double ehi, double elo) {
+  if (ehi > 709.782712893384) return (double)INFINITY;
+  if (ehi < -745.2) return 0.0;
+  double zz = ehi * DM_INVLN2N;
+  const double SHIFT = 6755399441055744.0; /* 1.5 * 2^52 */
+  double kd = (zz + SHIFT) - SHIFT;        /* round to nearest integer */
+  int64_t ki = (int64_t)kd;
+  double rh = dm_fma(kd, -DM_LN2N_HI, ehi); /* exact (see header comment) */
+  double rl = dm_fma(kd, -DM_LN2N_LO, elo);
+  dm_dd qq = dm_two_sum(rh, rl);
+  double q = qq.hi, ql = qq.lo;
+  int j = (int)(ki & 127);
+  int64_t e2 = (ki - j) / 128; /* exact: ki - j is a multiple of 128 */
+  double th = DM_EXPTAB(2 * j), tl = DM_EXPTAB(2 * j + 1);
+  /* exp(q) - 1 - q = q^2 (1/2 + q/6 + ... + q^5/5040) */
+  double p = 0x1.a01a01a01a01ap-13;            /* 1/5040 */
+  p = dm_fma(p, q, 0x1.6c16c16c16c17p-10);     /* 1/720 */
+  p = dm_fma(p, q, 0x1.1111111111111p-7);      /* 1/120 */
+  p = dm_fma(p, q, 0x1.5555555555555p-5);      /* 1/24 */
+  p = dm_fma(p, q, 0x1.5555555555555p-3);      /* 1/6 */
+  p = dm_fma(p, q, 0.5);
+  double rest = dm_fma(q * q, p, dm_fma(q, ql, ql));
+  double ph = th * q;
+  double pl = dm_fma(th, q, -ph);
+  double s = th + ph;
+  double e = (th - s) + ph; /* fast two-sum, |th| >= |ph| */
+  double tail = (e + pl) + dm_fma(th, rest, dm_fma(tl, q, tl));
+  double v = s + tail; /* in [1, 2) roughly; scale by 2^e2 */
+  if (e2 >= -1021 && e2 <= 1022) {
+    return v * dm_from_bits((uint64_t)(e2 + 1023) << 52);
+  }
+  /* out-of-range scale: two exact-power-of-two multiplies (deterministic) */
+  if (e2 > 1022) {
+    double f = dm_from_bits((uint64_t)(1022 + 1023) << 52);
+    return (v * f) * dm_from_bits((uint64_t)(e2 - 1022 + 1023) << 52);
+  } else {
+    double f = dm_from_bits((uint64_t)(-1021 + 1023) << 52);
+    int64_t rem = e2 + 1021; /* negative */
+    if (rem < -1021) rem = -1021;
+    return (v * f) * dm_from_bits((uint64_t)(rem + 1023) << 52);
+  }
+}
+
+/* x^y for x >= 0.  Negative x returns NaN (Julia raises DomainError there;
+ * the solvers only ever pass norms and ratios of norms). */
+DM_HD double dm_pow(double x, double y) {
+  if (x != x || y != y) return x + y; /* NaN */
+  if (y == 0.0) return 1.0;
+  if (x < 0.0) return (double)NAN;
+  if (x == 0.0) return y > 0.0 ? 0.0 : (double)INFINITY;
+  if (x == (double)INFINITY) return y > 0.0 ? (double)INFINITY : 0.0;
+  if (x == 1.0) return 1.0;
+  if (y == (double)INFINITY) return x > 1.0 ? (double)INFINITY : 0.0;
+  if (y == -(double)INFINITY) return x > 1.0 ? 0.0 : (double)INFINITY;
+  dm_dd l = dm_log_dd(x);
+  double ehi = y * l.hi;
+  double elo = dm_fma(y, l.lo, dm_fma(y, l.hi, -ehi));
+  return dm_exp_dd(ehi, elo);
+}
+
+/* log10(x) for x >= 0. */
+DM_HD double dm_log10(double x) {
+  if (x != x) return x;
+  if (x < 0.0) return (double)NAN;
+  if (x == 0.0) return -(double)INFINITY;
+  if (x == (double)INFINITY) return x;
+  dm_dd l = dm_log_dd(x);
+  double ph = l.hi * DM_INVLN10_HI;
+  double pe = dm_fma(l.hi, DM_INVLN10_HI, -ph);
+  double t = dm_fma(l.hi, DM_INVLN10_LO, l.lo * DM_INVLN10_HI);
+  return ph + (pe + t);
+}
+
+#endif /* ODE_B200_DETMATH_H */

@@ -1,0 +1,193 @@
+"""The CPU oracle against the reference's own known answers and golden data.
+
+Pins oracle/ode_oracle.cpp (and the independent python restatement) to:
+  * the tableaus extracted from /root/reference/src/runge_kutta.jl:66-157
+    (tests/golden/tableaus.json, made by tools/gen_golden_tableaus.py)
+  * test/runtests.jl:40-70 analytic problems, tolerance 1e-2 (Float64 row of `tols`)
+  * test/runtests.jl:78-96 ROBER refsol, 2e-10
+  * README.md:19-27 linear problem
+"""
+import json
+import math
+import os
+from fractions import Fraction
+
+import numpy as np
+import pytest
+
+from oracle import oracle as O
+from oracle import ode_oracle as P
+
+GOLD = os.path.join(os.path.dirname(__file__), "golden")
+NAME2GOLD = dict(ode1="bt_feuler", ode2_midpoint="bt_midpoint", ode2_heun="bt_heun", ode4="bt_rk4", ode21="bt_rk21",
+                 ode23="bt_rk23", ode45_fe="bt_rk45", ode45="bt_dopri5", ode78="bt_feh78")
+ADAPTIVE = ["ode21", "ode23", "ode45_fe", "ode45", "ode78"]
+FIXED = ["ode1", "ode2_midpoint", "ode2_heun", "ode4"]
+LORENZ = [10.0, 28.0, 8.0 / 3.0]
+
+
+def fr2f(s):
+    f = Fraction(s)
+    return float(f.numerator) / float(f.denominator)
+
+
+@pytest.mark.parametrize("name", sorted(NAME2GOLD))
+def test_tableau_matches_reference_source(name):
+    g = json.load(open(os.path.join(GOLD, "tableaus.json")))[NAME2GOLD[name]]
+    t = O.tableau(name)
+    S = len(g["c"])
+    assert t["S"] == S
+    assert np.array_equal(t["a"], np.array([[fr2f(x) for x in r] for r in g["a"]]))
+    assert np.array_equal(t["b"], np.array([[fr2f(x) for x in r] for r in g["b"]]))
+    assert np.array_equal(t["c"], np.array([fr2f(x) for x in g["c"]]))
+    assert t["order"] == min(g["order"])
+    # consistency assert of the reference constructor (src/runge_kutta.jl:25-27), exactly
+    for i in range(S):
+        assert sum(Fraction(x) for x in g["a"][i]) == Fraction(g["c"][i])
+    # isFSAL (src/runge_kutta.jl:62): only dopri5
+    assert t["fsal"] == (name == "ode45")
+    # the python restatement carries the same rationals
+    pt = P.Tab(name)
+    assert pt.a == t["a"].tolist() and pt.b == t["b"].tolist() and pt.c == t["c"].tolist()
+    assert pt.fsal == t["fsal"]
+
+
+ALL_SOLVERS = FIXED + ADAPTIVE + ["ode23s"]
+
+
+@pytest.mark.parametrize("solver", ALL_SOLVERS)
+def test_reference_analytic_problems(solver):
+    """test/runtests.jl:40-70 with T = Float64, tol = 1e-2."""
+    tol = 1e-2
+    ts = np.arange(0, 11) * 0.1  # T[0:.1:1;]
+    s = O.solve(solver, "const", [0.0], ts, [6.0])
+    assert np.max(np.abs(s.y[:, 0] - 6 * s.t)) < tol
+    ts = np.arange(0, 1001) * 0.001
+    s = O.solve(solver, "timelin", [0.0], ts, [2.0])
+    assert np.max(np.abs(s.y[:, 0] - s.t ** 2)) < tol
+    s = O.solve(solver, "linear", [1.0], ts, [1.0])
+    assert np.max(np.abs(s.y[:, 0] - np.exp(s.t))) < tol
+    if solver != "ode23s":  # ode23s backwards emits no tspan points (src/ODE.jl:332) but still integrates
+        s = O.solve(solver, "linear", [1.0], ts[::-1].copy(), [1.0])
+        assert np.max(np.abs(s.y[:, 0] - np.exp(s.t - 1))) < tol
+    ts = np.arange(0, int(2 * math.pi / 0.001) + 1) * 0.001
+    s = O.solve(solver, "rotation", [1.0, 2.0], ts)
+    ex = np.stack([np.cos(s.t) - 2 * np.sin(s.t), 2 * np.cos(s.t) + np.sin(s.t)], 1)
+    assert np.max(np.abs(s.y - ex)) < tol
+    assert len(s.t) >= len(ts)
+
+
+def test_ode23s_negative_start():
+    """test/runtests.jl:75."""
+    s = O.solve("ode23s", "rotation", [1.0, 2.0], [-5.0, 0.0])
+    assert len(s.t) > 1
+
+
+@pytest.mark.parametrize("mathmode", [0, 1])
+def test_rober_refsol(mathmode):
+    """test/runtests.jl:78-96: ||y(1e11) - refsol||_inf < 2e-10."""
+    s = O.solve("ode23s", "robertson", [1.0, 0.0, 0.0], [0.0, 1e11], [0.04, 3e7, 1e4], abstol=1e-8, reltol=1e-8,
+                maxstep=1e11 / 10, minstep=1e11 / 1e18, mathmode=mathmode)
+    ref = np.array([0.2083340149701255e-07, 0.8333360770334713e-13, 0.9999999791665050])
+    assert np.max(np.abs(s.y[-1] - ref)) < 2e-10
+    assert (s.n_accept, s.n_reject) == (905, 12)  # SURVEY.md appendix C (independent scratch restatement)
+
+
+@pytest.mark.parametrize("mathmode", [0, 1])
+def test_readme_linear(mathmode):
+    """README.md:19-27 through solve(): dtmin = span/1e-9 (src/common.jl:13), dtmax = span/2.5."""
+    s = O.solve("ode45", "linear", [0.5], [0.0, 1.0], [1.01], reltol=1e-8, abstol=1e-8, minstep=1e9, maxstep=0.4,
+                mathmode=mathmode)
+    assert (s.n_accept, s.n_reject, s.n_rhs) == (11, 0, 68)
+    assert len(s.t) == 12 and s.t[-1] == 1.0
+    assert abs(s.y[-1, 0] - 0.5 * math.exp(1.01)) < 5e-9
+    assert s.y[-1, 0] == 1.3728005108017367
+
+
+def _same(cpp, py):
+    assert cpp.n_rhs == py["n_rhs"]
+    if "n_accept" in py:
+        assert cpp.n_accept == py["n_accept"] and cpp.n_reject == py["n_reject"]
+    assert np.array_equal(cpp.t, np.array(py["t"]))
+    assert np.array_equal(cpp.y, np.array(py["y"]), equal_nan=True)
+    if len(py.get("trace", [])):
+        assert np.array_equal(cpp.trace, np.array(py["trace"]))
+
+
+@pytest.mark.parametrize("method", ADAPTIVE)
+def test_cpp_equals_python_bitwise_adaptive(method):
+    """Two independent restatements, libm math: identical bits, step for step."""
+    cases = [("lorenz", [1.0, 1.0, 1.0], [0.0, 0.7, 2.0], LORENZ, {}),
+             ("vdp", [2.0, 0.0], [0.0, 3.0], [5.0], dict(reltol=1e-6)),
+             ("kepler", [0.4, 0.0, 0.0, 2.0], [0.0, 3.0], None, dict(reltol=1e-9, abstol=1e-9)),
+             ("linear", [1.0], [1.0, 0.5, 0.0], [1.0], {})]
+    for rhs, y0, ts, p, kw in cases:
+        if method == "ode21" and rhs == "kepler":
+            kw = dict(reltol=1e-5)
+        for points in ("all", "specified"):
+            c = O.solve(method, rhs, y0, ts, p, trace=True, mathmode=1, points=points, **kw)
+            q = P.solve(method, rhs, y0, ts, p, points=points, **kw)
+            _same(c, q)
+
+
+@pytest.mark.parametrize("method", FIXED)
+def test_cpp_equals_python_bitwise_fixed(method):
+    ts = np.linspace(0, 1, 201)
+    c = O.solve(method, "lorenz", [1.0, 1.0, 1.0], ts, LORENZ)
+    q = P.solve(method, "lorenz", [1.0, 1.0, 1.0], ts, LORENZ)
+    _same(c, q)
+
+
+def test_cpp_equals_python_bitwise_ode23s():
+    c = O.solve("ode23s", "robertson", [1.0, 0.0, 0.0], [0.0, 1.0, 40.0], [0.04, 3e7, 1e4], trace=True, mathmode=1)
+    q = P.solve("ode23s", "robertson", [1.0, 0.0, 0.0], [0.0, 1.0, 40.0], [0.04, 3e7, 1e4])
+    _same(c, q)
+    c = O.solve("ode23s", "vdp", [2.0, 0.0], [0.0, 1.0], [10.0], trace=True, mathmode=1, points="specified")
+    q = P.solve("ode23s", "vdp", [2.0, 0.0], [0.0, 1.0], [10.0], points="specified")
+    _same(c, q)
+
+
+def test_detmath_vs_libm_same_step_sequence():
+    """mathmode 0 (detmath) and 1 (libm) may differ by an ulp in newdt but give the same decisions."""
+    a = O.solve("ode45", "lorenz", [1.0, 1.0, 1.0], [0.0, 2.0], LORENZ, trace=True, mathmode=0)
+    b = O.solve("ode45", "lorenz", [1.0, 1.0, 1.0], [0.0, 2.0], LORENZ, trace=True, mathmode=1)
+    assert (a.n_accept, a.n_reject) == (b.n_accept, b.n_reject)
+    assert np.array_equal(a.trace[:, 3], b.trace[:, 3])
+    np.testing.assert_allclose(a.y[-1], b.y[-1], rtol=1e-10)
+
+
+def test_reference_error_paths():
+    """Zero span (src/ODE.jl:88), wrong-sign initstep (src/runge_kutta.jl:294), minstep stop (:358-360)."""
+    with pytest.raises(RuntimeError):
+        O.solve("ode45", "linear", [1.0], [0.0, 0.0], [1.0])
+    with pytest.raises(RuntimeError):
+        O.solve("ode45", "linear", [1.0], [0.0, 1.0], [1.0], initstep=-0.1)
+    # solve()'s dtmin = span/1e-9 makes the first rejected step stop the integration
+    s = O.solve("ode45", "lorenz", [1.0, 1.0, 1.0], [0.0, 10.0], LORENZ, minstep=1e10)
+    assert s.status == 1 and s.t[-1] < 10.0 and s.n_reject == 0
+
+
+def test_survey_step_counts():
+    """SURVEY.md appendix C (independent scratch restatement made during the survey)."""
+    s = O.solve("ode45", "lorenz", [0.1, 0.0, 0.0], [0.0, 10.0], LORENZ, mathmode=1)
+    assert (s.n_accept, s.n_reject, s.n_rhs) == (248, 1, 1496)
+    for m, exp in (("ode23", (1225, 2, 4908)), ("ode45_fe", (283, 4, 1720)), ("ode78", (106, 4, 1428))):
+        s = O.solve(m, "lorenz", [1.0, 1.0, 1.0], [0.0, 10.0], LORENZ, mathmode=1)
+        assert (s.n_accept, s.n_reject, s.n_rhs) == exp
+    for e, exp in ((0.0, (661, 0)), (0.3, (645, 0)), (0.6, (799, 0)), (0.9, (1221, 1))):
+        y0 = [1 - e, 0.0, 0.0, math.sqrt((1 + e) / (1 - e))]
+        s = O.solve("ode78", "kepler", y0, [0.0, 20 * math.pi], None, reltol=1e-12, abstol=1e-12, mathmode=1)
+        assert (s.n_accept, s.n_reject) == exp
+        en = lambda y: 0.5 * (y[2] ** 2 + y[3] ** 2) - 1 / math.hypot(y[0], y[1])
+        assert abs(en(s.y[-1]) - en(s.y[0])) < 5e-10
+
+
+def test_ensemble_matches_single():
+    rng = np.random.default_rng(7)
+    y0 = np.stack([rng.uniform(-10, 10, 64), rng.uniform(-10, 10, 64), rng.uniform(5, 35, 64)], 1)
+    e = O.solve_ensemble("ode45", "lorenz", y0, [0.0, 1.0], LORENZ)
+    for i in (0, 13, 63):
+        s = O.solve("ode45", "lorenz", y0[i], [0.0, 1.0], LORENZ, points="final")
+        assert np.array_equal(s.y[-1], e["y_final"][i]) and s.n_accept == e["n_accept"][i]
+        s2 = O.solve("ode45", "lorenz", y0[i], [0.0, 1.0], LORENZ, points="all")
+        assert np.array_equal(s2.y[-1], e["y_final"][i]) and s2.t[-1] == e["t_final"][i]

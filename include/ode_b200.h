@@ -224,6 +224,11 @@ void ode_b200_slab_free(ode_b200_slab* s);
  * opts device, <0 on error.  Used as the ensemble roofline denominator
  * (SURVEY.md F10). */
 double ode_b200_fp64_peak(int device, int kind);
+/* Evaluates the device build of ode_b200_detmath.h: out_pow[i] = dm_pow(x[i], y[i]),
+ * out_log10[i] = dm_log10(x[i]) (host pointers).  Lets a caller verify that the
+ * GPU produces the same bits as the host build of the same header. */
+int ode_b200_selftest_detmath(int device, const double* x, const double* y, double* out_pow, double* out_log10,
+                              int64_t n);
 
 #ifdef __cplusplus
 }

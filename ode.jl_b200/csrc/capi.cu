@@ -1,0 +1,493 @@
+// capi.cu -- the C ABI of libode_b200.so (include/ode_b200.h): argument checks
+// with the reference's error behaviour, device memory, launches, result handles.
+//
+// There is no CPU path in this file: every solve entry point needs a CUDA
+// device and fails with ODE_B200_E_NO_DEVICE otherwise.
+#include <cuda_runtime.h>
+
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <new>
+#include <vector>
+
+#include "dispatch.cuh"
+#include "host_util.cuh"
+#include "tableaus.cuh"
+
+namespace odeb200 {
+
+thread_local char g_err[512] = "";
+thread_local double g_last_kernel_ms = 0.0;
+thread_local long long g_launches = 0;
+thread_local cudaEvent_t g_ev0 = nullptr, g_ev1 = nullptr;
+thread_local int g_ev_dev = -1;
+thread_local bool g_ev_pending = false;
+
+int set_err(int code, const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+  return code;
+}
+void note_launch() { g_launches++; }
+
+// ---- per-thread device arena (grow-only) ------------------------------------
+struct Arena {
+  int dev = -1;
+  char* base = nullptr;
+  size_t cap = 0, off = 0;
+  cudaStream_t stream = nullptr;
+  int ensure(int device, size_t bytes) {
+    if (dev != device || cap < bytes) {
+      if (base) {
+        cudaSetDevice(dev);
+        cudaFree(base);
+        base = nullptr;
+        cap = 0;
+      }
+      ODEB200_CUDA(cudaSetDevice(device));
+      size_t want = bytes + (bytes >> 3) + (1 << 20);
+      ODEB200_CUDA(cudaMalloc(&base, want));
+      cap = want;
+      dev = device;
+    }
+    if (!stream) ODEB200_CUDA(cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking));
+    off = 0;
+    return 0;
+  }
+  template <class T>
+  T* take(size_t n) {
+    size_t bytes = (n * sizeof(T) + 255) & ~(size_t)255;
+    T* p = reinterpret_cast<T*>(base + off);
+    off += bytes;
+    return p;
+  }
+};
+thread_local Arena g_arena;
+static size_t pad256(size_t b) { return (b + 255) & ~(size_t)255; }
+
+// ---- names -------------------------------------------------------------------
+struct NameId {
+  const char* name;
+  int id;
+};
+static const NameId kMethods[] = {
+    {"ode1", ODE_B200_M_FEULER},       {"feuler", ODE_B200_M_FEULER},     {"ode2_midpoint", ODE_B200_M_MIDPOINT},
+    {"midpoint", ODE_B200_M_MIDPOINT}, {"ode2_heun", ODE_B200_M_HEUN},    {"heun", ODE_B200_M_HEUN},
+    {"ode4", ODE_B200_M_RK4},          {"rk4", ODE_B200_M_RK4},           {"ode21", ODE_B200_M_RK21},
+    {"rk21", ODE_B200_M_RK21},         {"ode23", ODE_B200_M_RK23},        {"rk23", ODE_B200_M_RK23},
+    {"ode45_fe", ODE_B200_M_RK45_FE},  {"rk45", ODE_B200_M_RK45_FE},      {"ode45", ODE_B200_M_DOPRI5},
+    {"ode45_dp", ODE_B200_M_DOPRI5},   {"dopri5", ODE_B200_M_DOPRI5},     {"ode78", ODE_B200_M_FEH78},
+    {"feh78", ODE_B200_M_FEH78},       {"ode23s", ODE_B200_M_ODE23S}};
+static const NameId kRhs[] = {{"linear", ODE_B200_RHS_LINEAR},
+                              {"const", ODE_B200_RHS_CONST},
+                              {"timelin", ODE_B200_RHS_TIMELIN},
+                              {"rotation", ODE_B200_RHS_ROTATION},
+                              {"lorenz", ODE_B200_RHS_LORENZ},
+                              {"vdp", ODE_B200_RHS_VDP},
+                              {"robertson", ODE_B200_RHS_ROBERTSON},
+                              {"kepler", ODE_B200_RHS_KEPLER},
+                              {"reaction_diffusion", ODE_B200_RHS_REACTION_DIFFUSION}};
+static const int kRhsDof[ODE_B200_RHS_COUNT] = {1, 1, 1, 2, 3, 2, 3, 4, 0};
+static const int kRhsNp[ODE_B200_RHS_COUNT] = {1, 1, 1, 0, 3, 1, 3, 0, 2};
+
+template <class T>
+static double tab_get(int which, int i, int j) {
+  if (i < 0 || j < 0) return NAN;
+  // Rational -> Float64 exactly as the reference converts (src/ODE.jl:163)
+  if (which == 0) return (i < T::S && j < T::S) ? (double)T::A[i][j].n / (double)T::A[i][j].d : NAN;
+  if (which == 1) return (i < T::NB && j < T::S) ? (double)T::B[i][j].n / (double)T::B[i][j].d : NAN;
+  return i < T::S ? (double)T::C[i].n / (double)T::C[i].d : NAN;
+}
+#define ODEB200_TAB_SWITCH(method, X)             \
+  switch (method) {                               \
+    case ODE_B200_M_FEULER: X(TabFEuler);         \
+    case ODE_B200_M_MIDPOINT: X(TabMidpoint);     \
+    case ODE_B200_M_HEUN: X(TabHeun);             \
+    case ODE_B200_M_RK4: X(TabRK4);               \
+    case ODE_B200_M_RK21: X(TabRK21);             \
+    case ODE_B200_M_RK23: X(TabRK23);             \
+    case ODE_B200_M_RK45_FE: X(TabRK45);          \
+    case ODE_B200_M_DOPRI5: X(TabDopri5);         \
+    case ODE_B200_M_FEH78: X(TabFeh78);           \
+    default: break;                               \
+  }
+
+static int device_ok(int dev) {
+  int n = 0;
+  cudaError_t e = cudaGetDeviceCount(&n);
+  if (e != cudaSuccess || n <= 0) {
+    cudaGetLastError();
+    return set_err(ODE_B200_E_NO_DEVICE, "no CUDA device available (%s); libode_b200 has no CPU fallback",
+                   e != cudaSuccess ? cudaGetErrorString(e) : "device count 0");
+  }
+  if (dev < 0 || dev >= n) return set_err(ODE_B200_E_INVALID, "device %d out of range (0..%d)", dev, n - 1);
+  return 0;
+}
+
+// Checks shared by every ensemble entry point; mirrors the reference's errors.
+static int validate(const ode_b200_opts* o, const ode_b200_ensemble_io* io, double t0, double tend) {
+  if (!o || !io) return set_err(ODE_B200_E_INVALID, "null opts/io");
+  if (o->method < 0 || o->method >= ODE_B200_M_COUNT) return set_err(ODE_B200_E_INVALID, "unknown method %d", o->method);
+  if (o->rhs < 0 || o->rhs >= ODE_B200_RHS_COUNT) return set_err(ODE_B200_E_INVALID, "unknown rhs %d", o->rhs);
+  if (o->rhs == ODE_B200_RHS_REACTION_DIFFUSION)
+    return set_err(ODE_B200_E_UNSUPPORTED, "reaction_diffusion is a large-system RHS: use ode_b200_solve_large");
+  if (o->dof != kRhsDof[o->rhs]) return set_err(ODE_B200_E_INVALID, "rhs %d has dof %d, got %d", o->rhs, kRhsDof[o->rhs], o->dof);
+  if (o->n_params < kRhsNp[o->rhs]) return set_err(ODE_B200_E_INVALID, "rhs %d needs %d params, got %d", o->rhs, kRhsNp[o->rhs], o->n_params);
+  if (kRhsNp[o->rhs] > 0 && !io->params) return set_err(ODE_B200_E_INVALID, "params is NULL");
+  if (o->params_stride != 0 && o->params_stride < kRhsNp[o->rhs]) return set_err(ODE_B200_E_INVALID, "params_stride < n_params");
+  if (io->n_traj < 0 || (io->n_traj > 0 && !io->y0)) return set_err(ODE_B200_E_INVALID, "bad n_traj / y0");
+  if (io->n_tspan < 2 || !io->tspan) return set_err(ODE_B200_E_INVALID, "tspan needs at least 2 entries");
+  if (o->points != ODE_B200_POINTS_ALL && o->points != ODE_B200_POINTS_SPECIFIED && o->points != ODE_B200_POINTS_FINAL)
+    return set_err(ODE_B200_E_POINTS, "Unrecognized option points==%d", o->points);  // src/runge_kutta.jl:289
+  if (o->jacobian != 0) return set_err(ODE_B200_E_UNSUPPORTED, "analytic Jacobian functors are not registered yet");
+  const bool fixed = o->method <= ODE_B200_M_RK4;
+  if (!fixed) {
+    double tdir = tend > t0 ? 1.0 : (tend < t0 ? -1.0 : 0.0);
+    if (!(tend == tend) || !(t0 == t0)) return set_err(ODE_B200_E_INVALID, "NaN in tspan");
+    if (tdir == 0.0) return set_err(ODE_B200_E_ZERO_SPAN, "Zero time span");  // src/ODE.jl:88
+    if (o->method != ODE_B200_M_ODE23S && o->initstep != 0.0) {
+      double s = o->initstep > 0 ? 1.0 : (o->initstep < 0 ? -1.0 : 0.0);
+      if (s != tdir) return set_err(ODE_B200_E_INITSTEP, "initstep has wrong sign.");  // src/runge_kutta.jl:294
+    }
+  }
+  if ((io->pts_y || io->pts_t) && (io->pts_cap <= 0 || !io->pts_y || !io->pts_t))
+    return set_err(ODE_B200_E_INVALID, "pts_t, pts_y and pts_cap must be given together");
+  return 0;
+}
+
+static EnsembleKernel pick_kernel(const ode_b200_opts* o, int mode) {
+  switch (o->method) {
+    case ODE_B200_M_RK21: return adapt_kernel_rk21(o->rhs, mode);
+    case ODE_B200_M_RK23: return adapt_kernel_rk23(o->rhs, mode);
+    case ODE_B200_M_RK45_FE: return adapt_kernel_rk45(o->rhs, mode);
+    case ODE_B200_M_DOPRI5: return adapt_kernel_dopri5(o->rhs, mode);
+    case ODE_B200_M_FEH78: return adapt_kernel_feh78(o->rhs, mode);
+    case ODE_B200_M_ODE23S: return ode23s_kernel(o->rhs, mode);
+    default: return fixed_kernel(o->method, o->rhs);
+  }
+}
+
+// Launch on `stream` with device pointers.  `counter` is an 8-byte device word.
+static int launch_ensemble(const ode_b200_opts* o, const ode_b200_ensemble_io* io, unsigned long long* counter,
+                           cudaStream_t stream, bool time_it) {
+  const bool want_points = io->pts_y != nullptr || io->trace != nullptr;
+  const int mode = (want_points && o->points != ODE_B200_POINTS_FINAL) || io->trace ? 1 : 0;
+  EnsembleKernel k = pick_kernel(o, mode);
+  if (!k) return set_err(ODE_B200_E_UNSUPPORTED, "no kernel for method %d / rhs %d", o->method, o->rhs);
+  EnsembleArgs A;
+  memset(&A, 0, sizeof(A));
+  A.n_traj = io->n_traj;
+  A.y0 = io->y0;
+  A.params = io->params;
+  A.tspan = io->tspan;
+  A.n_tspan = io->n_tspan;
+  A.params_stride = o->params_stride;
+  A.points = o->points;
+  A.reltol = o->reltol;
+  A.abstol = o->abstol;
+  A.minstep = o->minstep;
+  A.maxstep = o->maxstep;
+  A.initstep = o->initstep;
+  A.max_steps = o->max_steps > 0 ? o->max_steps : 100000000LL;
+  A.t_final = io->t_final;
+  A.y_final = io->y_final;
+  A.n_accept = io->n_accept;
+  A.n_reject = io->n_reject;
+  A.n_rhs = io->n_rhs;
+  A.status = io->status;
+  A.pts_t = io->pts_t;
+  A.pts_y = io->pts_y;
+  A.pts_n = io->pts_n;
+  A.pts_cap = io->pts_y ? io->pts_cap : 0;
+  A.trace_traj = io->trace ? io->trace_traj : -1;
+  A.trace = io->trace;
+  A.trace_cap = io->trace ? io->trace_cap : 0;
+  A.trace_n = (long long*)io->trace_n;
+  A.work_counter = counter;
+
+  int dev = 0, sms = 0, per_sm = 0;
+  ODEB200_CUDA(cudaGetDevice(&dev));
+  ODEB200_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+  ODEB200_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k, ENS_BLOCK, 0));
+  if (per_sm < 1) per_sm = 1;
+  long long need = (io->n_traj + ENS_BLOCK - 1) / ENS_BLOCK;
+  long long grid = (long long)sms * per_sm;  // persistent: every lane pulls work until the counter runs out
+  if (need < grid) grid = need;
+  if (grid < 1) grid = 1;
+  ODEB200_CUDA(cudaMemsetAsync(counter, 0, sizeof(unsigned long long), stream));
+  if (time_it) {
+    if (g_ev_dev != dev) {
+      if (g_ev0) {
+        cudaEventDestroy(g_ev0);
+        cudaEventDestroy(g_ev1);
+      }
+      ODEB200_CUDA(cudaEventCreate(&g_ev0));
+      ODEB200_CUDA(cudaEventCreate(&g_ev1));
+      g_ev_dev = dev;
+    }
+    ODEB200_CUDA(cudaEventRecord(g_ev0, stream));
+  }
+  k<<<(unsigned)grid, ENS_BLOCK, 0, stream>>>(A);
+  note_launch();
+  ODEB200_CUDA(cudaGetLastError());
+  if (time_it) {
+    ODEB200_CUDA(cudaEventRecord(g_ev1, stream));
+    g_ev_pending = true;
+  }
+  return 0;
+}
+
+}  // namespace odeb200
+
+using namespace odeb200;
+
+extern "C" {
+
+int ode_b200_version(void) { return ODE_B200_ABI_VERSION; }
+const char* ode_b200_last_error(void) { return g_err; }
+int ode_b200_device_count(void) {
+  int n = 0;
+  if (cudaGetDeviceCount(&n) != cudaSuccess) {
+    cudaGetLastError();
+    return 0;
+  }
+  return n;
+}
+int ode_b200_rhs_id(const char* name) {
+  if (name)
+    for (const NameId& e : kRhs)
+      if (!strcmp(e.name, name)) return e.id;
+  return ODE_B200_E_INVALID;
+}
+int ode_b200_method_id(const char* name) {
+  if (name)
+    for (const NameId& e : kMethods)
+      if (!strcmp(e.name, name)) return e.id;
+  return ODE_B200_E_INVALID;
+}
+int ode_b200_rhs_dof(int rhs) { return (rhs >= 0 && rhs < ODE_B200_RHS_COUNT) ? kRhsDof[rhs] : ODE_B200_E_INVALID; }
+int ode_b200_rhs_nparams(int rhs) { return (rhs >= 0 && rhs < ODE_B200_RHS_COUNT) ? kRhsNp[rhs] : ODE_B200_E_INVALID; }
+int ode_b200_method_stages(int method) {
+  if (method == ODE_B200_M_ODE23S) return 3;
+#define X(T) return T::S
+  ODEB200_TAB_SWITCH(method, X)
+#undef X
+  return ODE_B200_E_INVALID;
+}
+int ode_b200_method_is_adaptive(int method) {
+  if (method == ODE_B200_M_ODE23S) return 1;
+#define X(T) return T::NB == 2
+  ODEB200_TAB_SWITCH(method, X)
+#undef X
+  return ODE_B200_E_INVALID;
+}
+int ode_b200_method_is_fsal(int method) {
+  if (method == ODE_B200_M_ODE23S) return 1;  // F0 = F2, src/ODE.jl:351
+#define X(T)                       \
+  {                                \
+    constexpr bool f = T::fsal();  \
+    return f;                      \
+  }
+  ODEB200_TAB_SWITCH(method, X)
+#undef X
+  return ODE_B200_E_INVALID;
+}
+double ode_b200_tableau(int method, int which, int i, int j) {
+#define X(T) return tab_get<T>(which, i, j)
+  ODEB200_TAB_SWITCH(method, X)
+#undef X
+  return NAN;
+}
+
+double ode_b200_last_kernel_ms(void) {
+  if (g_ev_pending) {
+    float ms = 0.f;
+    if (cudaEventSynchronize(g_ev1) == cudaSuccess && cudaEventElapsedTime(&ms, g_ev0, g_ev1) == cudaSuccess)
+      g_last_kernel_ms = ms;
+    g_ev_pending = false;
+  }
+  return g_last_kernel_ms;
+}
+int64_t ode_b200_launch_count(int reset) {
+  long long v = g_launches;
+  if (reset) g_launches = 0;
+  return v;
+}
+
+int ode_b200_solve_ensemble_dev(const ode_b200_opts* opts, const ode_b200_ensemble_io* io, void* stream) {
+  if (!opts || !io) return set_err(ODE_B200_E_INVALID, "null opts/io");
+  int rc = device_ok(opts->device);
+  if (rc) return rc;
+  ODEB200_CUDA(cudaSetDevice(opts->device));
+  // the span is needed on the host for the reference's argument errors
+  double ends[2] = {0, 0};
+  if (io->n_tspan >= 2 && io->tspan) {
+    ODEB200_CUDA(cudaMemcpyAsync(&ends[0], io->tspan, 8, cudaMemcpyDeviceToHost, (cudaStream_t)stream));
+    ODEB200_CUDA(cudaMemcpyAsync(&ends[1], io->tspan + (io->n_tspan - 1), 8, cudaMemcpyDeviceToHost, (cudaStream_t)stream));
+    ODEB200_CUDA(cudaStreamSynchronize((cudaStream_t)stream));
+  }
+  rc = validate(opts, io, ends[0], ends[1]);
+  if (rc) return rc;
+  if (io->n_traj == 0) return 0;
+  static thread_local unsigned long long* counter = nullptr;
+  static thread_local int counter_dev = -1;
+  if (counter_dev != opts->device) {
+    ODEB200_CUDA(cudaMalloc(&counter, 256));
+    counter_dev = opts->device;
+  }
+  return launch_ensemble(opts, io, counter, (cudaStream_t)stream, true);
+}
+
+int ode_b200_solve_ensemble(const ode_b200_opts* opts, const ode_b200_ensemble_io* io) {
+  if (!opts || !io) return set_err(ODE_B200_E_INVALID, "null opts/io");
+  int rc = device_ok(opts->device);
+  if (rc) return rc;
+  if (io->n_tspan < 2 || !io->tspan) return set_err(ODE_B200_E_INVALID, "tspan needs at least 2 entries");
+  rc = validate(opts, io, io->tspan[0], io->tspan[io->n_tspan - 1]);
+  if (rc) return rc;
+  const long long n = io->n_traj;
+  if (n == 0) return 0;
+  const int D = opts->dof;
+  const int np = kRhsNp[opts->rhs];
+  const size_t n_par = np ? (opts->params_stride ? (size_t)n * opts->params_stride : (size_t)np) : 0;
+  const bool pts = io->pts_y != nullptr;
+  size_t bytes = 256 + pad256(n * D * 8) + pad256(n_par * 8) + pad256((size_t)io->n_tspan * 8) + pad256(n * 8) +
+                 pad256(n * D * 8) + 4 * pad256(n * 4);
+  if (pts) bytes += pad256((size_t)n * io->pts_cap * 8) + pad256((size_t)n * io->pts_cap * D * 8) + pad256(n * 4);
+  if (io->trace) bytes += pad256((size_t)io->trace_cap * 32) + 256;
+  rc = g_arena.ensure(opts->device, bytes);
+  if (rc) return rc;
+  cudaStream_t st = g_arena.stream;
+  ode_b200_ensemble_io d = *io;
+  unsigned long long* counter = g_arena.take<unsigned long long>(1);
+  double* dy0 = g_arena.take<double>((size_t)n * D);
+  double* dpar = n_par ? g_arena.take<double>(n_par) : nullptr;
+  double* dts = g_arena.take<double>(io->n_tspan);
+  d.y0 = dy0;
+  d.params = dpar;
+  d.tspan = dts;
+  d.t_final = io->t_final ? g_arena.take<double>(n) : nullptr;
+  d.y_final = io->y_final ? g_arena.take<double>((size_t)n * D) : nullptr;
+  d.n_accept = io->n_accept ? g_arena.take<int>(n) : nullptr;
+  d.n_reject = io->n_reject ? g_arena.take<int>(n) : nullptr;
+  d.n_rhs = io->n_rhs ? g_arena.take<int>(n) : nullptr;
+  d.status = io->status ? g_arena.take<int>(n) : nullptr;
+  if (pts) {
+    d.pts_t = g_arena.take<double>((size_t)n * io->pts_cap);
+    d.pts_y = g_arena.take<double>((size_t)n * io->pts_cap * D);
+    d.pts_n = io->pts_n ? g_arena.take<int>(n) : nullptr;
+  } else {
+    d.pts_t = d.pts_y = nullptr;
+    d.pts_n = nullptr;
+  }
+  long long* dtrace_n = nullptr;
+  if (io->trace) {
+    d.trace = g_arena.take<double>((size_t)io->trace_cap * 4);
+    dtrace_n = g_arena.take<long long>(1);
+    d.trace_n = (int64_t*)dtrace_n;
+    ODEB200_CUDA(cudaMemsetAsync(dtrace_n, 0, 8, st));
+  }
+  ODEB200_CUDA(cudaMemcpyAsync(dy0, io->y0, (size_t)n * D * 8, cudaMemcpyHostToDevice, st));
+  if (n_par) ODEB200_CUDA(cudaMemcpyAsync(dpar, io->params, n_par * 8, cudaMemcpyHostToDevice, st));
+  ODEB200_CUDA(cudaMemcpyAsync(dts, io->tspan, (size_t)io->n_tspan * 8, cudaMemcpyHostToDevice, st));
+  rc = launch_ensemble(opts, &d, counter, st, true);
+  if (rc) return rc;
+  if (io->t_final) ODEB200_CUDA(cudaMemcpyAsync(io->t_final, d.t_final, n * 8, cudaMemcpyDeviceToHost, st));
+  if (io->y_final) ODEB200_CUDA(cudaMemcpyAsync(io->y_final, d.y_final, (size_t)n * D * 8, cudaMemcpyDeviceToHost, st));
+  if (io->n_accept) ODEB200_CUDA(cudaMemcpyAsync(io->n_accept, d.n_accept, n * 4, cudaMemcpyDeviceToHost, st));
+  if (io->n_reject) ODEB200_CUDA(cudaMemcpyAsync(io->n_reject, d.n_reject, n * 4, cudaMemcpyDeviceToHost, st));
+  if (io->n_rhs) ODEB200_CUDA(cudaMemcpyAsync(io->n_rhs, d.n_rhs, n * 4, cudaMemcpyDeviceToHost, st));
+  if (io->status) ODEB200_CUDA(cudaMemcpyAsync(io->status, d.status, n * 4, cudaMemcpyDeviceToHost, st));
+  if (pts) {
+    ODEB200_CUDA(cudaMemcpyAsync(io->pts_t, d.pts_t, (size_t)n * io->pts_cap * 8, cudaMemcpyDeviceToHost, st));
+    ODEB200_CUDA(cudaMemcpyAsync(io->pts_y, d.pts_y, (size_t)n * io->pts_cap * D * 8, cudaMemcpyDeviceToHost, st));
+    if (io->pts_n) ODEB200_CUDA(cudaMemcpyAsync(io->pts_n, d.pts_n, n * 4, cudaMemcpyDeviceToHost, st));
+  }
+  if (io->trace) {
+    ODEB200_CUDA(cudaMemcpyAsync(io->trace, d.trace, (size_t)io->trace_cap * 32, cudaMemcpyDeviceToHost, st));
+    if (io->trace_n) ODEB200_CUDA(cudaMemcpyAsync(io->trace_n, dtrace_n, 8, cudaMemcpyDeviceToHost, st));
+  }
+  ODEB200_CUDA(cudaStreamSynchronize(st));
+  return 0;
+}
+
+// ---- single system with the reference's (tout, yout) contract ----------------
+struct ode_b200_result {
+  int dof = 0;
+  int status = 0;
+  long long nacc = 0, nrej = 0, nrhs = 0;
+  std::vector<double> t, y;
+};
+
+int ode_b200_solve_single(const ode_b200_opts* opts, const double* y0, const double* params, const double* tspan,
+                          int32_t n_tspan, ode_b200_result** out) {
+  if (!opts || !y0 || !tspan || !out) return set_err(ODE_B200_E_INVALID, "null argument");
+  *out = nullptr;
+  if (opts->points == ODE_B200_POINTS_FINAL) return set_err(ODE_B200_E_POINTS, "Unrecognized option points==final");
+  ode_b200_opts o = *opts;
+  o.params_stride = 0;
+  long long cap = n_tspan + 1024;
+  const bool fixed = o.method <= ODE_B200_M_RK4;
+  if (fixed || o.points == ODE_B200_POINTS_SPECIFIED) cap = n_tspan;
+  for (int tries = 0; tries < 8; tries++) {
+    std::vector<double> pt(cap), py((size_t)cap * o.dof), yf(o.dof);
+    double tf = 0;
+    int32_t na = 0, nr = 0, nf = 0, st = 0, pn = 0;
+    ode_b200_ensemble_io io;
+    memset(&io, 0, sizeof(io));
+    io.n_traj = 1;
+    io.y0 = y0;
+    io.params = params;
+    io.tspan = tspan;
+    io.n_tspan = n_tspan;
+    io.t_final = &tf;
+    io.y_final = yf.data();
+    io.n_accept = &na;
+    io.n_reject = &nr;
+    io.n_rhs = &nf;
+    io.status = &st;
+    io.pts_t = pt.data();
+    io.pts_y = py.data();
+    io.pts_n = &pn;
+    io.pts_cap = cap;
+    io.trace_traj = -1;
+    int rc = ode_b200_solve_ensemble(&o, &io);
+    if (rc) return rc;
+    if (st == ODE_B200_ST_OVERFLOW) {  // deterministic: rerun with the reported size
+      cap = (long long)pn + 16;
+      continue;
+    }
+    ode_b200_result* r = new (std::nothrow) ode_b200_result();
+    if (!r) return set_err(ODE_B200_E_NOMEM, "out of memory");
+    r->dof = o.dof;
+    r->status = st;
+    r->nacc = na;
+    r->nrej = nr;
+    r->nrhs = nf;
+    r->t.assign(pt.begin(), pt.begin() + pn);
+    r->y.assign(py.begin(), py.begin() + (size_t)pn * o.dof);
+    *out = r;
+    return 0;
+  }
+  return set_err(ODE_B200_E_NOMEM, "points buffer kept overflowing");
+}
+int64_t ode_b200_result_len(const ode_b200_result* r) { return r ? (int64_t)r->t.size() : 0; }
+int32_t ode_b200_result_dof(const ode_b200_result* r) { return r ? r->dof : 0; }
+int32_t ode_b200_result_status(const ode_b200_result* r) { return r ? r->status : ODE_B200_E_INVALID; }
+int64_t ode_b200_result_counts(const ode_b200_result* r, int which) {
+  if (!r) return 0;
+  return which == 0 ? r->nacc : which == 1 ? r->nrej : r->nrhs;
+}
+int ode_b200_result_copy(const ode_b200_result* r, double* tout, double* yout) {
+  if (!r) return set_err(ODE_B200_E_INVALID, "null result");
+  if (tout) memcpy(tout, r->t.data(), r->t.size() * 8);
+  if (yout) memcpy(yout, r->y.data(), r->y.size() * 8);
+  return 0;
+}
+void ode_b200_result_free(ode_b200_result* r) { delete r; }
+
+}  // extern "C"

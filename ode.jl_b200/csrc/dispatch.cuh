@@ -1,0 +1,39 @@
+// dispatch.cuh -- (method, rhs, mode) -> kernel pointer.  One translation unit per
+// tableau keeps nvcc compile time parallel (see Makefile).
+#pragma once
+#include "common.cuh"
+
+namespace odeb200 {
+
+// mode: 0 = final state + counters only, 1 = tout/yout points + trace
+EnsembleKernel adapt_kernel_rk21(int rhs, int mode);
+EnsembleKernel adapt_kernel_rk23(int rhs, int mode);
+EnsembleKernel adapt_kernel_rk45(int rhs, int mode);
+EnsembleKernel adapt_kernel_dopri5(int rhs, int mode);
+EnsembleKernel adapt_kernel_feh78(int rhs, int mode);
+EnsembleKernel fixed_kernel(int method, int rhs);
+EnsembleKernel ode23s_kernel(int rhs, int mode);
+
+#define ODEB200_RHS_SWITCH(rhs, X)                 \
+  switch (rhs) {                                   \
+    case ODE_B200_RHS_LINEAR: X(RhsLinear);        \
+    case ODE_B200_RHS_CONST: X(RhsConst);          \
+    case ODE_B200_RHS_TIMELIN: X(RhsTimeLin);      \
+    case ODE_B200_RHS_ROTATION: X(RhsRotation);    \
+    case ODE_B200_RHS_LORENZ: X(RhsLorenz);        \
+    case ODE_B200_RHS_VDP: X(RhsVdp);              \
+    case ODE_B200_RHS_ROBERTSON: X(RhsRobertson);  \
+    case ODE_B200_RHS_KEPLER: X(RhsKepler);        \
+    default: return nullptr;                       \
+  }
+
+#define ODEB200_DEFINE_ADAPT(NAME, TAB)                                                        \
+  EnsembleKernel NAME(int rhs, int mode) {                                                     \
+    if (mode) {                                                                                \
+      ODEB200_RHS_SWITCH(rhs, ODEB200_ADAPT_M1_##TAB)                                          \
+    } else {                                                                                   \
+      ODEB200_RHS_SWITCH(rhs, ODEB200_ADAPT_M0_##TAB)                                          \
+    }                                                                                          \
+  }
+
+}  // namespace odeb200

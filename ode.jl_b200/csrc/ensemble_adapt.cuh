@@ -1,0 +1,296 @@
+// ensemble_adapt.cuh -- adaptive embedded Runge-Kutta, one trajectory per thread.
+//
+// Replaces n_traj independent calls of the reference driver
+//   oderk_adapt         /root/reference src/runge_kutta.jl:232-369
+//   rk_embedded_step!   :371-399      calc_next_k!  :444-458
+//   stepsize_hw92!      :401-442      hinit         src/ODE.jl:85-112
+//   hermite_interp!     :479-492
+// with identical arithmetic (binary64, no FMA, reference association order).
+//
+// Mapping to the machine
+//  * state y, k1, the S-1 scaled stages dt*k_s and both b-row accumulators live
+//    in registers; tableau coefficients are compile-time constants (zero entries
+//    drop out of the unrolled loops); tolerances come straight from the
+//    kernel-parameter constant bank.
+//  * dt*k_s is formed once per stage: (dt*k)*a is left-associated in the
+//    reference (:454), so hoisting dt*k is bit-identical and removes
+//    nnz(a) - (S-1) multiplies per attempt.
+//  * the grid is persistent: every lane pulls trajectory indices from a global
+//    counter, so a warp does not idle until its slowest trajectory ends; the
+//    loop body is one step ATTEMPT, common to all lanes, and accept/reject is
+//    a handful of predicated register moves (FSAL) rather than a branch around
+//    the stage loop.
+//  * MODE 0 keeps only final state + counters; MODE 1 adds the reference's
+//    tout/yout contract (points = :all / :specified with Hermite output) and an
+//    optional attempt trace, used by the odeXX front-ends and the parity tests.
+#pragma once
+
+#include "common.cuh"
+#include "rhs.cuh"
+#include "tableaus.cuh"
+
+namespace odeb200 {
+
+template <int D>
+__device__ __forceinline__ void hermite_point(double* out, double tq, double t, double dt, const double (&y0)[D],
+                                              const double (&y1)[D], const double (&f0)[D], const double (&f1)[D]) {
+  double theta = (tq - t) / dt;  // :486
+#pragma unroll
+  for (int i = 0; i < D; i++) {  // :488-489
+    out[i] = ((1.0 - theta) * y0[i] + theta * y1[i]) +
+             (theta * (theta - 1.0)) *
+                 (((1.0 - 2.0 * theta) * (y1[i] - y0[i]) + ((theta - 1.0) * dt) * f0[i]) + (theta * dt) * f1[i]);
+  }
+}
+
+template <class Tab, class Rhs, int MODE>
+__global__ void __launch_bounds__(ENS_BLOCK) ens_adapt_kernel(const EnsembleArgs A) {
+  constexpr int D = Rhs::DOF, S = Tab::S, NPA = RhsNP<Rhs>::value;
+  constexpr bool FSAL = Tab::fsal();
+  constexpr double EXPO = 1.0 / (double)(Tab::ORDER + 1);  // T(1/(order+1)) :436
+  constexpr int NK = S > 1 ? S - 1 : 1;
+
+  const double tstart = A.tspan[0];
+  const double tend = A.tspan[A.n_tspan - 1];
+  const double tdir = jl_sign(tend - tstart);  // src/ODE.jl:87 (zero span rejected on the host)
+  const int nfixed = A.n_tspan;
+
+  long long idx = -1;
+  double y[D], k1[D], p[NPA];
+  double t = 0.0, dt = 0.0;
+  int timeout = 0, nacc = 0, nrej = 0, nrhs = 0;
+  bool islast = false;
+  long long attempts = 0;
+  int iter = 2, iter_fixed = 2, npts = 0;  // 1-based like the reference (:286,:304)
+  long long ntrace = 0;
+
+  while (true) {
+    if (idx < 0) {
+      idx = (long long)atomicAdd(A.work_counter, 1ULL);
+      if (idx >= A.n_traj) break;
+      // ---------------------------------------------------------- init :256-304
+#pragma unroll
+      for (int d = 0; d < D; d++) y[d] = A.y0[idx * D + d];
+#pragma unroll
+      for (int q = 0; q < NPA; q++) p[q] = (q < Rhs::NP) ? A.params[idx * A.params_stride + q] : 0.0;
+      t = tstart;
+      nacc = nrej = 0;
+      attempts = 0;
+      timeout = 0;  // :303
+      iter = 2;
+      iter_fixed = 2;
+      ntrace = 0;
+      // hinit, src/ODE.jl:85-112 (p = order)
+      {
+        double n0 = fabs(y[0]);
+#pragma unroll
+        for (int d = 1; d < D; d++) n0 = normInf_step(n0, fabs(y[d]));
+        double tau = jl_max(A.reltol * n0, A.abstol);  // :89
+        double d0 = n0 / tau;                          // :90
+        Rhs::eval(tstart, y, k1, p);                   // :91  f0 -> ks[1]
+        double n1 = fabs(k1[0]);
+#pragma unroll
+        for (int d = 1; d < D; d++) n1 = normInf_step(n1, fabs(k1[d]));
+        double d1 = n1 / tau;  // :92
+        double h0 = (d0 < 1e-5 || d1 < 1e-5) ? 1e-6 : 0.01 * (d0 / d1);  // :93-97
+        double x1[D], f1[D];
+        double th = tdir * h0;
+#pragma unroll
+        for (int d = 0; d < D; d++) x1[d] = y[d] + th * k1[d];  // :100
+        Rhs::eval(tstart + tdir * h0, x1, f1, p);               // :101
+        double n2 = fabs(f1[0] - k1[0]);
+#pragma unroll
+        for (int d = 1; d < D; d++) n2 = normInf_step(n2, fabs(f1[d] - k1[d]));
+        double d2 = n2 / (tau * h0);  // :103
+        double dm = jl_max(d1, d2);
+        double h1;
+        if (dm <= 1e-15) {
+          h1 = jl_max(1e-6, 1e-3 * h0);  // :105
+        } else {
+          double pw = -(2.0 + dm_log10(dm)) / (double)(Tab::ORDER + 1);  // :107
+          h1 = dm_pow(10.0, pw);                                         // :108
+        }
+        dt = tdir * jl_min(jl_min(100.0 * h0, h1), tdir * (tend - tstart));  // :111
+        nrhs = 2;
+      }
+      if (A.initstep != 0.0) dt = A.initstep;            // :293-295 (sign checked on the host)
+      islast = fabs(t + dt - tend) <= jl_eps(tend);      // :302
+      if (MODE == 1) {
+        if (A.points == ODE_B200_POINTS_ALL) {  // ys[1] = y0, tspan = [tstart] :280,:285
+          if (A.pts_cap > 0) {
+            A.pts_t[idx * A.pts_cap] = tstart;
+#pragma unroll
+            for (int d = 0; d < D; d++) A.pts_y[(idx * A.pts_cap) * D + d] = y[d];
+          }
+          npts = 1;
+        } else if (A.points == ODE_B200_POINTS_SPECIFIED) {
+          for (int i = 0; i < nfixed && i < A.pts_cap; i++) A.pts_t[idx * A.pts_cap + i] = A.tspan[i];
+          if (A.pts_cap > 0) {
+#pragma unroll
+            for (int d = 0; d < D; d++) A.pts_y[(idx * A.pts_cap) * D + d] = y[d];
+          }
+          npts = nfixed;
+        }
+      }
+    }
+
+    // ------------------------------------------------ rk_embedded_step! :371-399
+    attempts++;
+    double ytrial[D], yerr[D], dtk[NK][D], klast[D];
+    constexpr double b10 = Tab::b(0, 0), b20 = Tab::b(1, 0);
+#pragma unroll
+    for (int d = 0; d < D; d++) {  // :384-387
+      ytrial[d] = (b10 != 0.0) ? b10 * k1[d] : 0.0;
+      yerr[d] = (b20 != 0.0) ? b20 * k1[d] : 0.0;
+      dtk[0][d] = dt * k1[d];
+      klast[d] = k1[d];
+    }
+    static_for<S - 1>([&](auto I) {  // :388-394
+      constexpr int s = decltype(I)::value + 1;
+      double ytmp[D], ks[D];
+#pragma unroll
+      for (int d = 0; d < D; d++) ytmp[d] = y[d];  // calc_next_k! :452
+      static_for<s>([&](auto J) {                  // :453-455
+        constexpr int ss = decltype(J)::value;
+        constexpr double a = Tab::a(s, ss);
+        if constexpr (a != 0.0) {
+#pragma unroll
+          for (int d = 0; d < D; d++) ytmp[d] = ytmp[d] + dtk[ss][d] * a;
+        }
+      });
+      constexpr double c = Tab::c(s);
+      Rhs::eval(t + c * dt, ytmp, ks, p);  // :456
+      constexpr double b1 = Tab::b(0, s), b2 = Tab::b(1, s);
+#pragma unroll
+      for (int d = 0; d < D; d++) {  // :390-393
+        if constexpr (b1 != 0.0) ytrial[d] = ytrial[d] + b1 * ks[d];
+        if constexpr (b2 != 0.0) yerr[d] = yerr[d] + b2 * ks[d];
+        if constexpr (s < S - 1) dtk[s][d] = dt * ks[d];
+        if constexpr (s == S - 1) klast[d] = ks[d];
+      }
+    });
+    nrhs += S - 1;
+#pragma unroll
+    for (int d = 0; d < D; d++) {  // :395-398
+      yerr[d] = dt * (ytrial[d] - yerr[d]);
+      ytrial[d] = y[d] + dt * ytrial[d];
+    }
+
+    // ---------------------------------------------------- stepsize_hw92! :401-442
+    bool nanout = false;
+#pragma unroll
+    for (int d = 0; d < D; d++) {  // :430-434
+      nanout = nanout || (ytrial[d] != ytrial[d]);  // isoutofdomain, src/ODE.jl:116
+      double ay = fabs(y[d]), at = fabs(ytrial[d]);
+      yerr[d] = yerr[d] / (A.abstol + ((ay > at) ? ay : at) * A.reltol);  // :433
+    }
+    double err, newdt;
+    if (nanout) {  // :432
+      err = 10.0;
+      newdt = dt * 0.2;
+      timeout = 5;
+    } else {
+      err = norm2_small<D>(yerr);  // :435
+      double nd = jl_min(A.maxstep, (tdir * dt) * jl_max(0.2, 0.8 * dm_pow(1.0 / err, EXPO)));  // :436
+      if (timeout > 0) {  // :437-440
+        nd = jl_min(nd, dt);
+        timeout -= 1;
+      }
+      newdt = tdir * nd;  // :441
+    }
+    const bool accept = err <= 1.0;  // :312
+    if (MODE == 1 && idx == A.trace_traj) {
+      if (ntrace < A.trace_cap) {
+        A.trace[ntrace * 4 + 0] = t;
+        A.trace[ntrace * 4 + 1] = dt;
+        A.trace[ntrace * 4 + 2] = err;
+        A.trace[ntrace * 4 + 3] = accept ? 1.0 : 0.0;
+      }
+      ntrace++;
+    }
+
+    int fin = -1;  // >= 0: trajectory ends with this status
+    bool fin_trial = false;
+    if (accept) {
+      nacc++;
+      double f1[D];
+      if (FSAL) {  // :320
+#pragma unroll
+        for (int d = 0; d < D; d++) f1[d] = klast[d];
+      } else {
+        Rhs::eval(t + dt, ytrial, f1, p);
+        nrhs++;
+      }
+      if (MODE == 1) {
+        double* py = A.pts_y + (idx * A.pts_cap) * D;
+        double* pt = A.pts_t + idx * A.pts_cap;
+        if (A.points == ODE_B200_POINTS_SPECIFIED) {  // :321-326
+          while (iter - 1 < nfixed && (tdir * A.tspan[iter - 1] < tdir * (t + dt) || islast)) {
+            if (iter - 1 < A.pts_cap) hermite_point<D>(py + (long long)(iter - 1) * D, A.tspan[iter - 1], t, dt, y, ytrial, k1, f1);
+            iter++;
+          }
+        } else if (A.points == ODE_B200_POINTS_ALL) {  // :327-340
+          while (iter_fixed - 1 < nfixed && tdir * t < tdir * A.tspan[iter_fixed - 1] &&
+                 tdir * A.tspan[iter_fixed - 1] < tdir * (t + dt)) {
+            if (npts < A.pts_cap) {
+              hermite_point<D>(py + (long long)npts * D, A.tspan[iter_fixed - 1], t, dt, y, ytrial, k1, f1);
+              pt[npts] = A.tspan[iter_fixed - 1];
+            }
+            npts++;
+            iter_fixed++;
+          }
+          if (npts < A.pts_cap) {
+#pragma unroll
+            for (int d = 0; d < D; d++) py[(long long)npts * D + d] = ytrial[d];
+            pt[npts] = t + dt;
+          }
+          npts++;
+        }
+      }
+#pragma unroll
+      for (int d = 0; d < D; d++) k1[d] = f1[d];  // :341
+      if (islast) {                               // :344
+        fin = ODE_B200_ST_OK;
+        fin_trial = true;
+      } else {
+#pragma unroll
+        for (int d = 0; d < D; d++) y[d] = ytrial[d];  // :347
+        t += dt;                                       // :350
+        dt = newdt;                                    // :351
+        if (tdir * (t + dt + dt / 100) >= tdir * tend) {  // :354-357
+          dt = tend - t;
+          islast = true;
+        }
+      }
+    } else if (fabs(newdt) < A.minstep) {  // :358-360
+      fin = ODE_B200_ST_MINSTEP;
+    } else {  // :361-366
+      islast = false;
+      nrej++;
+      dt = newdt;
+      timeout = 5;
+      if (!is_finite(dt)) fin = ODE_B200_ST_NONFINITE;  // the reference would spin forever
+    }
+    if (fin < 0 && attempts >= A.max_steps) fin = ODE_B200_ST_MAXSTEPS;
+
+    if (fin >= 0) {
+      if (MODE == 1 && npts > A.pts_cap && A.pts_y) fin = ODE_B200_ST_OVERFLOW;
+      if (A.t_final) A.t_final[idx] = fin_trial ? t + dt : t;
+      if (A.y_final) {
+#pragma unroll
+        for (int d = 0; d < D; d++) A.y_final[idx * D + d] = fin_trial ? ytrial[d] : y[d];
+      }
+      if (A.n_accept) A.n_accept[idx] = nacc;
+      if (A.n_reject) A.n_reject[idx] = nrej;
+      if (A.n_rhs) A.n_rhs[idx] = nrhs;
+      if (A.status) A.status[idx] = fin;
+      if (MODE == 1) {
+        if (A.pts_n) A.pts_n[idx] = npts;
+        if (idx == A.trace_traj && A.trace_n) *A.trace_n = ntrace;
+      }
+      idx = -1;
+    }
+  }
+}
+
+}  // namespace odeb200

@@ -1,0 +1,311 @@
+// ensemble_ode23s.cuh -- modified Rosenbrock triple, one trajectory per thread.
+//
+// Replaces n_traj calls of ode23s (/root/reference src/ODE.jl:252-361) with the
+// default forward-difference Jacobian fdjacobian (src/ODE.jl:232-243).
+// W = I - h*d*J is factorised per attempt as an in-register LU with partial
+// pivoting (first maximal |entry|, reciprocal-pivot scaling, right-looking
+// update -- the operation order of LAPACK dgetf2 that Julia's `lu` reaches for a
+// tiny matrix) and the three solves follow getrs (row swaps, unit-lower
+// forward sweep, upper back substitution with division).  Row exchanges use
+// compare-and-swap on register rows, so no local-memory indexing appears.
+#pragma once
+
+#include "common.cuh"
+#include "rhs.cuh"
+
+namespace odeb200 {
+
+template <int D>
+struct LuReg {
+  double a[D][D];
+  int piv[D];
+  bool singular;
+
+  __device__ __forceinline__ void factor() {
+    singular = false;
+#pragma unroll
+    for (int j = 0; j < D; j++) {
+      int pr = j;
+      double mx = fabs(a[j][j]);
+#pragma unroll
+      for (int i = j + 1; i < D; i++) {
+        double v = fabs(a[i][j]);
+        if (v > mx) {
+          mx = v;
+          pr = i;
+        }
+      }
+      piv[j] = pr;
+#pragma unroll
+      for (int i = j + 1; i < D; i++) {
+        if (pr == i) {
+#pragma unroll
+          for (int c = 0; c < D; c++) {
+            double tmp = a[j][c];
+            a[j][c] = a[i][c];
+            a[i][c] = tmp;
+          }
+        }
+      }
+      if (a[j][j] == 0.0) {
+        singular = true;
+      } else {
+        double rp = 1.0 / a[j][j];
+#pragma unroll
+        for (int i = j + 1; i < D; i++) a[i][j] = a[i][j] * rp;
+#pragma unroll
+        for (int c = j + 1; c < D; c++) {
+#pragma unroll
+          for (int i = j + 1; i < D; i++) a[i][c] = a[i][c] - a[i][j] * a[j][c];
+        }
+      }
+    }
+  }
+  __device__ __forceinline__ void solve(double (&b)[D]) const {
+#pragma unroll
+    for (int j = 0; j < D; j++) {
+#pragma unroll
+      for (int i = j + 1; i < D; i++) {
+        if (piv[j] == i) {
+          double tmp = b[j];
+          b[j] = b[i];
+          b[i] = tmp;
+        }
+      }
+    }
+#pragma unroll
+    for (int j = 0; j < D; j++) {
+#pragma unroll
+      for (int i = j + 1; i < D; i++) b[i] = b[i] - b[j] * a[i][j];
+    }
+#pragma unroll
+    for (int j = D - 1; j >= 0; j--) {
+      b[j] = b[j] / a[j][j];
+#pragma unroll
+      for (int i = 0; i < j; i++) b[i] = b[i] - b[j] * a[i][j];
+    }
+  }
+};
+
+// fdjacobian, src/ODE.jl:232-243 (recomputes F(t,x), D+1 RHS calls).
+template <class Rhs, int D, int NPA>
+__device__ __forceinline__ void fd_jacobian(double t, const double (&x)[D], const double (&p)[NPA], double (&J)[D][D]) {
+  double ftx[D];
+  Rhs::eval(t, x, ftx, p);  // :233
+#pragma unroll
+  for (int j = 0; j < D; j++) {  // :236
+    double dxj = (x[j] + ((x[j] == 0.0) ? 1.0 : 0.0)) / 100;  // :239
+    double xp[D], fp[D];
+#pragma unroll
+    for (int i = 0; i < D; i++) xp[i] = x[i] + ((i == j) ? dxj : 0.0);
+    Rhs::eval(t, xp, fp, p);
+#pragma unroll
+    for (int i = 0; i < D; i++) J[i][j] = (fp[i] - ftx[i]) / dxj;  // :240
+  }
+}
+
+template <class Rhs, int MODE>
+__global__ void __launch_bounds__(ENS_BLOCK) ens_ode23s_kernel(const EnsembleArgs A) {
+  constexpr int D = Rhs::DOF, NPA = RhsNP<Rhs>::value;
+  const double dd = 1.0 / (2.0 + sqrt(2.0));  // :270
+  const double e32 = 6.0 + sqrt(2.0);         // :271
+  const double tstart = A.tspan[0];
+  const double tfinal = A.tspan[A.n_tspan - 1];
+  const double tdir = jl_sign(tfinal - tstart);
+  const int nfixed = A.n_tspan;
+
+  long long idx = -1;
+  double y[D], F0[D], J[D][D], p[NPA];
+  double t = 0.0, h = 0.0, last_tout = 0.0;
+  int nacc = 0, nrej = 0, nrhs = 0, npts = 0;
+  long long attempts = 0, ntrace = 0;
+
+  while (true) {
+    if (idx < 0) {
+      idx = (long long)atomicAdd(A.work_counter, 1ULL);
+      if (idx >= A.n_traj) break;
+#pragma unroll
+      for (int d = 0; d < D; d++) y[d] = A.y0[idx * D + d];
+#pragma unroll
+      for (int q = 0; q < NPA; q++) p[q] = (q < Rhs::NP) ? A.params[idx * A.params_stride + q] : 0.0;
+      t = tstart;
+      nacc = nrej = nrhs = 0;
+      attempts = 0;
+      ntrace = 0;
+      h = A.initstep;  // :279
+      if (h == 0.0) {  // hinit with p = 3, :282 (src/ODE.jl:85-112)
+        double n0 = fabs(y[0]);
+#pragma unroll
+        for (int d = 1; d < D; d++) n0 = normInf_step(n0, fabs(y[d]));
+        double tau = jl_max(A.reltol * n0, A.abstol);
+        double d0 = n0 / tau;
+        Rhs::eval(tstart, y, F0, p);
+        double n1 = fabs(F0[0]);
+#pragma unroll
+        for (int d = 1; d < D; d++) n1 = normInf_step(n1, fabs(F0[d]));
+        double d1 = n1 / tau;
+        double h0 = (d0 < 1e-5 || d1 < 1e-5) ? 1e-6 : 0.01 * (d0 / d1);
+        double x1[D], f1[D];
+        double th = tdir * h0;
+#pragma unroll
+        for (int d = 0; d < D; d++) x1[d] = y[d] + th * F0[d];
+        Rhs::eval(tstart + tdir * h0, x1, f1, p);
+        double n2 = fabs(f1[0] - F0[0]);
+#pragma unroll
+        for (int d = 1; d < D; d++) n2 = normInf_step(n2, fabs(f1[d] - F0[d]));
+        double d2 = n2 / (tau * h0);
+        double dm = jl_max(d1, d2);
+        double h1;
+        if (dm <= 1e-15) {
+          h1 = jl_max(1e-6, 1e-3 * h0);
+        } else {
+          double pw = -(2.0 + dm_log10(dm)) / 4.0;
+          h1 = dm_pow(10.0, pw);
+        }
+        h = tdir * jl_min(jl_min(100.0 * h0, h1), tdir * (tfinal - tstart));
+        nrhs = 2;
+      } else {  // :284-285
+        Rhs::eval(tstart, y, F0, p);
+        nrhs = 1;
+      }
+      h = tdir * jl_min(fabs(h), A.maxstep);  // :287
+      if (MODE == 1) {                        // tout = [t], yout = [y0] :290-291
+        if (A.pts_cap > 0 && A.pts_y) {
+          A.pts_t[idx * A.pts_cap] = tstart;
+#pragma unroll
+          for (int d = 0; d < D; d++) A.pts_y[(idx * A.pts_cap) * D + d] = y[d];
+        }
+        npts = 1;
+        last_tout = tstart;
+      }
+      fd_jacobian<Rhs, D, NPA>(t, y, p, J);  // :294
+      nrhs += D + 1;
+    }
+
+    int fin = -1;
+    if (!(fabs(t - tfinal) > 0 && A.minstep < fabs(h))) {  // :296
+      fin = (fabs(t - tfinal) > 0) ? ODE_B200_ST_MINSTEP : ODE_B200_ST_OK;
+      if (fin == ODE_B200_ST_MINSTEP && !is_finite(h)) fin = ODE_B200_ST_NONFINITE;
+    } else if (attempts >= A.max_steps) {
+      fin = ODE_B200_ST_MAXSTEPS;
+    } else {
+      attempts++;
+      if (fabs(t - tfinal) < fabs(h)) h = tfinal - t;  // :297-299
+      LuReg<D> W;                                     // :301-310
+      const double hd = h * dd;
+#pragma unroll
+      for (int i = 0; i < D; i++) {
+#pragma unroll
+        for (int j = 0; j < D; j++) {
+          double m = -(hd * J[i][j]);
+          W.a[i][j] = (i == j) ? (m + 1.0) : m;
+        }
+      }
+      W.factor();
+      if (W.singular) {
+        fin = ODE_B200_ST_SINGULAR;
+      } else {
+        double Fa[D], T[D], k1[D], k2[D], k3[D], F1[D], F2[D], ynew[D], tmp[D];
+        Rhs::eval(t + h / 100, y, Fa, p);  // :313
+#pragma unroll
+        for (int i = 0; i < D; i++) T[i] = (hd * (Fa[i] - F0[i])) / (h / 100);
+#pragma unroll
+        for (int i = 0; i < D; i++) k1[i] = F0[i] + T[i];  // :316
+        W.solve(k1);
+        const double hh = 0.5 * h;
+#pragma unroll
+        for (int i = 0; i < D; i++) tmp[i] = y[i] + hh * k1[i];  // :317
+        Rhs::eval(t + 0.5 * h, tmp, F1, p);
+#pragma unroll
+        for (int i = 0; i < D; i++) k2[i] = F1[i] - k1[i];  // :318
+        W.solve(k2);
+#pragma unroll
+        for (int i = 0; i < D; i++) k2[i] = k2[i] + k1[i];
+#pragma unroll
+        for (int i = 0; i < D; i++) ynew[i] = y[i] + h * k2[i];  // :319
+        Rhs::eval(t + h, ynew, F2, p);                           // :320
+#pragma unroll
+        for (int i = 0; i < D; i++) k3[i] = ((F2[i] - e32 * (k2[i] - F1[i])) - 2 * (k1[i] - F0[i])) + T[i];  // :321
+        W.solve(k3);
+        nrhs += 3;
+#pragma unroll
+        for (int i = 0; i < D; i++) tmp[i] = (k1[i] - 2 * k2[i]) + k3[i];
+        const double err = (fabs(h) / 6) * norm2_small<D>(tmp);  // :323
+        const double delta = jl_max(A.reltol * jl_max(norm2_small<D>(y), norm2_small<D>(ynew)), A.abstol);  // :324
+        const bool accept = err <= delta;  // :327
+        if (MODE == 1 && idx == A.trace_traj) {
+          if (ntrace < A.trace_cap) {
+            A.trace[ntrace * 4 + 0] = t;
+            A.trace[ntrace * 4 + 1] = h;
+            A.trace[ntrace * 4 + 2] = err / delta;
+            A.trace[ntrace * 4 + 3] = accept ? 1.0 : 0.0;
+          }
+          ntrace++;
+        }
+        if (accept) {
+          nacc++;
+          if (MODE == 1 && A.points != ODE_B200_POINTS_FINAL) {
+            double* py = A.pts_y + (idx * A.pts_cap) * D;
+            double* pt = A.pts_t + idx * A.pts_cap;
+            for (int q = 0; q < nfixed; q++) {  // :332 tspan points in (t, t+h]
+              const double toi = A.tspan[q];
+              if (toi > t && toi <= t + h) {
+                const double s = (toi - t) / h;  // :334
+                const double den = 1 - 2 * dd;
+                if (npts < A.pts_cap && A.pts_y) {
+                  pt[npts] = toi;
+#pragma unroll
+                  for (int i = 0; i < D; i++)  // :338
+                    py[(long long)npts * D + i] =
+                        y[i] + h * (((k1[i] * s) * (1 - s)) / den + ((k2[i] * s) * (s - 2 * dd)) / den);
+                }
+                npts++;
+                last_tout = toi;
+              }
+            }
+            if (A.points == ODE_B200_POINTS_ALL && last_tout != t + h) {  // :341-345
+              if (npts < A.pts_cap && A.pts_y) {
+                pt[npts] = t + h;
+#pragma unroll
+                for (int i = 0; i < D; i++) py[(long long)npts * D + i] = ynew[i];
+              }
+              npts++;
+              last_tout = t + h;
+            }
+          }
+          t = t + h;  // :348
+#pragma unroll
+          for (int i = 0; i < D; i++) {
+            y[i] = ynew[i];  // :349
+            F0[i] = F2[i];   // :351
+          }
+          fd_jacobian<Rhs, D, NPA>(t, y, p, J);  // :352
+          nrhs += D + 1;
+        } else {
+          nrej++;
+        }
+        h = tdir * jl_min(A.maxstep, (fabs(h) * 0.8) * dm_pow(delta / err, 1.0 / 3));  // :357
+      }
+    }
+
+    if (fin >= 0) {
+      if (MODE == 1 && npts > A.pts_cap && A.pts_y) fin = ODE_B200_ST_OVERFLOW;
+      if (A.t_final) A.t_final[idx] = t;
+      if (A.y_final) {
+#pragma unroll
+        for (int d = 0; d < D; d++) A.y_final[idx * D + d] = y[d];
+      }
+      if (A.n_accept) A.n_accept[idx] = nacc;
+      if (A.n_reject) A.n_reject[idx] = nrej;
+      if (A.n_rhs) A.n_rhs[idx] = nrhs;
+      if (A.status) A.status[idx] = fin;
+      if (MODE == 1) {
+        if (A.pts_n) A.pts_n[idx] = npts;
+        if (idx == A.trace_traj && A.trace_n) *A.trace_n = ntrace;
+      }
+      idx = -1;
+    }
+  }
+}
+
+}  // namespace odeb200

@@ -1,0 +1,18 @@
+// host_util.cuh -- host-side helpers shared by the C ABI translation units.
+#pragma once
+#include <cuda_runtime.h>
+
+namespace odeb200 {
+int set_err(int code, const char* fmt, ...);  // fills the thread-local last_error, returns code
+void note_launch();                           // counts kernel launches (ode_b200_launch_count)
+}  // namespace odeb200
+
+#define ODEB200_CUDA(call)                                                                              \
+  do {                                                                                                  \
+    cudaError_t e__ = (call);                                                                           \
+    if (e__ != cudaSuccess) {                                                                           \
+      cudaGetLastError();                                                                               \
+      return ::odeb200::set_err(ODE_B200_E_CUDA, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e__), \
+                                __FILE__, __LINE__);                                                    \
+    }                                                                                                   \
+  } while (0)

@@ -1,0 +1,8 @@
+// Ensemble kernels for the TabDopri5 tableau (all registered small-system RHS).
+#include "dispatch.cuh"
+#include "ensemble_adapt.cuh"
+namespace odeb200 {
+#define ODEB200_ADAPT_M0_TabDopri5(R) return ens_adapt_kernel<TabDopri5, R, 0>
+#define ODEB200_ADAPT_M1_TabDopri5(R) return ens_adapt_kernel<TabDopri5, R, 1>
+ODEB200_DEFINE_ADAPT(adapt_kernel_dopri5, TabDopri5)
+}  // namespace odeb200

@@ -1,0 +1,8 @@
+// Ensemble kernels for the TabFeh78 tableau (all registered small-system RHS).
+#include "dispatch.cuh"
+#include "ensemble_adapt.cuh"
+namespace odeb200 {
+#define ODEB200_ADAPT_M0_TabFeh78(R) return ens_adapt_kernel<TabFeh78, R, 0>
+#define ODEB200_ADAPT_M1_TabFeh78(R) return ens_adapt_kernel<TabFeh78, R, 1>
+ODEB200_DEFINE_ADAPT(adapt_kernel_feh78, TabFeh78)
+}  // namespace odeb200

@@ -1,0 +1,8 @@
+// Ensemble kernels for the TabRK21 tableau (all registered small-system RHS).
+#include "dispatch.cuh"
+#include "ensemble_adapt.cuh"
+namespace odeb200 {
+#define ODEB200_ADAPT_M0_TabRK21(R) return ens_adapt_kernel<TabRK21, R, 0>
+#define ODEB200_ADAPT_M1_TabRK21(R) return ens_adapt_kernel<TabRK21, R, 1>
+ODEB200_DEFINE_ADAPT(adapt_kernel_rk21, TabRK21)
+}  // namespace odeb200

@@ -1,0 +1,8 @@
+// Ensemble kernels for the TabRK23 tableau (all registered small-system RHS).
+#include "dispatch.cuh"
+#include "ensemble_adapt.cuh"
+namespace odeb200 {
+#define ODEB200_ADAPT_M0_TabRK23(R) return ens_adapt_kernel<TabRK23, R, 0>
+#define ODEB200_ADAPT_M1_TabRK23(R) return ens_adapt_kernel<TabRK23, R, 1>
+ODEB200_DEFINE_ADAPT(adapt_kernel_rk23, TabRK23)
+}  // namespace odeb200

@@ -1,0 +1,8 @@
+// Ensemble kernels for the TabRK45 tableau (all registered small-system RHS).
+#include "dispatch.cuh"
+#include "ensemble_adapt.cuh"
+namespace odeb200 {
+#define ODEB200_ADAPT_M0_TabRK45(R) return ens_adapt_kernel<TabRK45, R, 0>
+#define ODEB200_ADAPT_M1_TabRK45(R) return ens_adapt_kernel<TabRK45, R, 1>
+ODEB200_DEFINE_ADAPT(adapt_kernel_rk45, TabRK45)
+}  // namespace odeb200

@@ -1,0 +1,97 @@
+// rhs.cuh -- registered right-hand sides F(t, y; p) as compiled device functors.
+//
+// A Julia closure cannot cross the C ABI, so `F` is a registered id
+// (include/ode_b200.h ode_b200_rhs) plus a parameter vector.  Each functor states
+// the same expression, in the same association, as the Julia `F` the reference
+// would be given; the CPU oracle states them independently
+// (oracle/ode_oracle.cpp Rhs::operator(), oracle/ode_oracle.py rhs_factory) and
+// the parity tests compare bit for bit.  No FMA contraction (-fmad=false).
+#pragma once
+
+namespace odeb200 {
+
+// f(u,p,t) = a*u            README.md:19 (a = 1.01), test/runtests.jl:54 (a = 1)
+struct RhsLinear {
+  static constexpr int DOF = 1, NP = 1, ID = ODE_B200_RHS_LINEAR;
+  __device__ __forceinline__ static void eval(double, const double (&y)[1], double (&f)[1], const double (&p)[1]) {
+    f[0] = p[0] * y[0];
+  }
+};
+// (t,y) -> T(6)             test/runtests.jl:40
+struct RhsConst {
+  static constexpr int DOF = 1, NP = 1, ID = ODE_B200_RHS_CONST;
+  __device__ __forceinline__ static void eval(double, const double (&)[1], double (&f)[1], const double (&p)[1]) {
+    f[0] = p[0];
+  }
+};
+// (t,y) -> T(2)*t           test/runtests.jl:47
+struct RhsTimeLin {
+  static constexpr int DOF = 1, NP = 1, ID = ODE_B200_RHS_TIMELIN;
+  __device__ __forceinline__ static void eval(double t, const double (&)[1], double (&f)[1], const double (&p)[1]) {
+    f[0] = p[0] * t;
+  }
+};
+// (t,y) -> [-y[2]; y[1]]    test/runtests.jl:67
+struct RhsRotation {
+  static constexpr int DOF = 2, NP = 0, ID = ODE_B200_RHS_ROTATION;
+  __device__ __forceinline__ static void eval(double, const double (&y)[2], double (&f)[2], const double (&)[1]) {
+    f[0] = -y[1];
+    f[1] = y[0];
+  }
+};
+// Lorenz, examples/Lorenz_Attractor.ipynb cell 4: [s*(y-x); x*(r-z)-y; x*y-b*z]
+struct RhsLorenz {
+  static constexpr int DOF = 3, NP = 3, ID = ODE_B200_RHS_LORENZ;
+  __device__ __forceinline__ static void eval(double, const double (&y)[3], double (&f)[3], const double (&p)[3]) {
+    f[0] = p[0] * (y[1] - y[0]);
+    f[1] = y[0] * (p[1] - y[2]) - y[1];
+    f[2] = y[0] * y[1] - p[2] * y[2];
+  }
+};
+// Van der Pol: [y2; mu*((1-y1*y1)*y2) - y1]
+struct RhsVdp {
+  static constexpr int DOF = 2, NP = 1, ID = ODE_B200_RHS_VDP;
+  __device__ __forceinline__ static void eval(double, const double (&y)[2], double (&f)[2], const double (&p)[1]) {
+    f[0] = y[1];
+    f[1] = p[0] * ((1.0 - y[0] * y[0]) * y[1]) - y[0];
+  }
+};
+// Robertson, test/runtests.jl:81-87 (ydot[1], then ydot[3], then ydot[2] = -ydot[1]-ydot[3])
+struct RhsRobertson {
+  static constexpr int DOF = 3, NP = 3, ID = ODE_B200_RHS_ROBERTSON;
+  __device__ __forceinline__ static void eval(double, const double (&y)[3], double (&f)[3], const double (&p)[3]) {
+    double d1 = -p[0] * y[0] + p[2] * y[1] * y[2];
+    double d3 = p[1] * y[1] * y[1];
+    f[0] = d1;
+    f[2] = d3;
+    f[1] = -d1 - d3;
+  }
+};
+// planar Kepler, mu = 1: r2 = x*x+y*y; r3 = r2*sqrt(r2); [vx, vy, -x/r3, -y/r3]
+struct RhsKepler {
+  static constexpr int DOF = 4, NP = 0, ID = ODE_B200_RHS_KEPLER;
+  __device__ __forceinline__ static void eval(double, const double (&y)[4], double (&f)[4], const double (&)[1]) {
+    double r2 = y[0] * y[0] + y[1] * y[1];
+    double r3 = r2 * sqrt(r2);
+    f[0] = y[2];
+    f[1] = y[3];
+    f[2] = -y[0] / r3;
+    f[3] = -y[1] / r3;
+  }
+};
+
+// 1-D reaction-diffusion stencil (large-system regime): point value from the
+// three neighbours, kappa*((um - 2*u) + up) + (r*u)*(1 - u).
+struct RhsReactionDiffusion {
+  static constexpr int NP = 2, RADIUS = 1, ID = ODE_B200_RHS_REACTION_DIFFUSION;
+  __device__ __forceinline__ static double point(double um, double u, double up, double kappa, double r) {
+    return kappa * ((um - 2.0 * u) + up) + (r * u) * (1.0 - u);
+  }
+};
+
+template <class R>
+struct RhsNP {
+  static constexpr int value = R::NP > 0 ? R::NP : 1;
+};
+
+}  // namespace odeb200

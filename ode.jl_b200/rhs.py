@@ -1,0 +1,82 @@
+"""Registered right-hand-side tokens.
+
+A Julia closure (or a Python callable) cannot run on the device, so the `F`
+argument of the odeXX front-ends is a DeviceRHS: a callable object that
+(i) evaluates the registered expression on the host -- handy for reference runs
+and for checking the device functors -- and (ii) names the compiled device
+functor (`rhs id`, parameter vector) that crosses the C ABI.
+"""
+import math
+
+import numpy as np
+
+from ._lib import RHS
+
+_DOF = dict(linear=1, const=1, timelin=1, rotation=2, lorenz=3, vdp=2, robertson=3, kepler=4, reaction_diffusion=0)
+_NP = dict(linear=1, const=1, timelin=1, rotation=0, lorenz=3, vdp=1, robertson=3, kepler=0, reaction_diffusion=2)
+
+
+class DeviceRHS:
+    """`DeviceRHS("lorenz", 10.0, 28.0, 8/3)`; calling it evaluates F(t, y) on the host."""
+
+    def __init__(self, name, *params):
+        if name not in RHS:
+            raise KeyError("unknown right-hand side %r; registered: %s" % (name, ", ".join(sorted(RHS))))
+        if len(params) == 1 and np.ndim(params[0]) >= 1:
+            params = tuple(np.asarray(params[0], dtype=np.float64).ravel().tolist()) if np.ndim(params[0]) == 1 \
+                else (np.asarray(params[0], dtype=np.float64),)
+        self.name = name
+        self.id = RHS[name]
+        self.dof = _DOF[name]
+        self.n_params = _NP[name]
+        self.params = params
+
+    def with_params(self, p):
+        if p is None:
+            return self
+        return DeviceRHS(self.name, *np.atleast_1d(np.asarray(p, dtype=np.float64)).tolist())
+
+    def param_array(self):
+        if self.n_params == 0:
+            return None
+        if len(self.params) == 1 and isinstance(self.params[0], np.ndarray):
+            a = np.ascontiguousarray(self.params[0], dtype=np.float64)
+        else:
+            a = np.asarray(self.params, dtype=np.float64)
+        if a.shape[-1] != self.n_params:
+            raise ValueError("%s takes %d parameters, got %r" % (self.name, self.n_params, a.shape))
+        return a
+
+    def __call__(self, t, y):
+        p = self.params
+        n = self.name
+        scalar = np.ndim(y) == 0
+        v = [float(y)] if scalar else [float(x) for x in y]
+        if n == "linear":
+            f = [p[0] * v[0]]
+        elif n == "const":
+            f = [p[0]]
+        elif n == "timelin":
+            f = [p[0] * t]
+        elif n == "rotation":
+            f = [-v[1], v[0]]
+        elif n == "lorenz":
+            f = [p[0] * (v[1] - v[0]), v[0] * (p[1] - v[2]) - v[1], v[0] * v[1] - p[2] * v[2]]
+        elif n == "vdp":
+            f = [v[1], p[0] * ((1.0 - v[0] * v[0]) * v[1]) - v[0]]
+        elif n == "robertson":
+            d1 = -p[0] * v[0] + p[2] * v[1] * v[2]
+            d3 = p[1] * v[1] * v[1]
+            f = [d1, -d1 - d3, d3]
+        elif n == "kepler":
+            r2 = v[0] * v[0] + v[1] * v[1]
+            r3 = r2 * math.sqrt(r2)
+            f = [v[2], v[3], -v[0] / r3, -v[1] / r3]
+        else:
+            u = np.asarray(v)
+            f = p[0] * ((np.roll(u, 1) - 2.0 * u) + np.roll(u, -1)) + (p[1] * u) * (1.0 - u)
+            return f
+        return f[0] if scalar else np.array(f)
+
+    def __repr__(self):
+        return "DeviceRHS(%r%s)" % (self.name, "".join(", %r" % (x,) for x in self.params))

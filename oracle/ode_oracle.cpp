@@ -752,6 +752,9 @@ void ode23s(const Rhs& F, const MathCtx& M, const Vec& y0, const Vec& tspan, con
     }
     h = tdir * jl_min(o.maxstep, (std::fabs(h) * 0.8) * M.pow(delta / err, 1.0 / 3));  // :357
   }
+  // the reference returns silently when the loop guard fails short of tfinal; report why
+  if (R.status == ODE_B200_ST_OK && std::fabs(t - tfinal) > 0)
+    R.status = std::isfinite(h) ? ODE_B200_ST_MINSTEP : ODE_B200_ST_NONFINITE;
   R.nrhs = F.calls;
   R.t = tout;
   R.y.resize(yout.size() * n);

@@ -507,6 +507,8 @@ def ode23s(F, y0, tspan, reltol=1e-5, abstol=1e-8, minstep=None, maxstep=None, i
         else:
             nrej += 1
         h = tdir * jmin(maxstep, (abs(h) * 0.8) * jpow(delta / err if err != 0 else INF, 1.0 / 3))
+    if status == 0 and abs(t - tfinal) > 0:
+        status = 1 if math.isfinite(h) else 3
     return dict(t=tout, y=yout, n_accept=nacc, n_reject=nrej, n_rhs=F.n, trace=trace, status=status)
 
 

@@ -1,0 +1,237 @@
+"""GPU parity: the CUDA kernels (through the C ABI) against the CPU oracle, bit for bit.
+
+Every comparison here is exact: same accept/reject sequence, same step and RHS
+counts, same final bits.  The oracle runs in mathmode 0 (the shared deterministic
+pow/log10); test_oracle.py ties that to libm and to the reference's known answers.
+"""
+import math
+
+import numpy as np
+import pytest
+
+import ode_jl_b200 as m
+from oracle import oracle as O
+
+pytestmark = pytest.mark.gpu
+
+LORENZ = [10.0, 28.0, 8.0 / 3.0]
+ADAPTIVE = ["ode21", "ode23", "ode45_fe", "ode45", "ode78"]
+FIXED = ["ode1", "ode2_midpoint", "ode2_heun", "ode4"]
+
+
+def lorenz_ics(n, seed=20261019):
+    rng = np.random.default_rng(seed)
+    return np.stack([rng.uniform(-10, 10, n), rng.uniform(-10, 10, n), rng.uniform(5, 35, n)], 1)
+
+
+def assert_same(got, ref, keys=("y_final", "t_final", "n_accept", "n_reject", "n_rhs", "status")):
+    for k in keys:
+        a, b = np.asarray(got[k]), np.asarray(ref[k])
+        if not np.array_equal(a, b, equal_nan=a.dtype.kind == "f"):
+            bad = np.flatnonzero(np.any(np.atleast_2d((a != b).reshape(len(a), -1)), axis=1))
+            raise AssertionError("%s differs on %d of %d trajectories (first %s)" % (k, bad.size, len(a), bad[:5]))
+
+
+def test_device_detmath_equals_host_detmath():
+    import ctypes as C
+    rng = np.random.default_rng(1)
+    n = 200000
+    x = np.exp(rng.uniform(-40, 40, n))
+    x[:8] = [0.0, 1.0, np.inf, 5e-324, 1e-310, 10.0, 2.0, 1e308]
+    y = np.array([0.5, 1 / 3, 0.2, 0.125, -0.7, 3.3])[rng.integers(0, 6, n)]
+    op, ol = np.empty(n), np.empty(n)
+    dp = C.POINTER(C.c_double)
+    c = lambda a: a.ctypes.data_as(dp)
+    m._lib.check(m.lib().ode_b200_selftest_detmath(0, c(x), c(y), c(op), c(ol), n))
+    hp, hl = np.empty(n), np.empty(n)
+    O.lib().oracle_pow_v(c(x), c(y), c(hp), n, 0)
+    O.lib().oracle_log10_v(c(x), c(hl), n, 0)
+    assert np.array_equal(op, hp, equal_nan=True)
+    assert np.array_equal(ol, hl, equal_nan=True)
+
+
+@pytest.mark.parametrize("tend", [2.0, 10.0])
+def test_lorenz_dopri5_ensemble_bit_exact(tend):
+    """Config 2 strict-parity subset: first 4096 trajectories."""
+    y0 = lorenz_ics(4096)
+    got = m.solve_ensemble("ode45", m.DeviceRHS("lorenz", *LORENZ), y0, [0.0, tend])
+    ref = O.solve_ensemble("ode45", "lorenz", y0, [0.0, tend], LORENZ)
+    assert_same(got, ref)
+    assert np.all(got["status"] == 0) and np.all(got["t_final"] == tend)
+
+
+@pytest.mark.parametrize("method", ADAPTIVE)
+def test_all_adaptive_tableaus_bit_exact(method):
+    n = 256
+    y0 = lorenz_ics(n, 5)
+    got = m.solve_ensemble(method, m.DeviceRHS("lorenz", *LORENZ), y0, [0.0, 1.5], reltol=1e-4)
+    ref = O.solve_ensemble(method, "lorenz", y0, [0.0, 1.5], LORENZ, reltol=1e-4)
+    assert_same(got, ref)
+    rng = np.random.default_rng(9)
+    y0 = np.stack([rng.uniform(-2, 2, n), rng.uniform(-2, 2, n)], 1)
+    mu = rng.uniform(0.5, 5.0, (n, 1))
+    got = m.solve_ensemble(method, m.DeviceRHS("vdp", 1.0), y0, [0.0, 4.0], params=mu)
+    ref = O.solve_ensemble(method, "vdp", y0, [0.0, 4.0], mu)
+    assert_same(got, ref)
+    # backward in time on a smooth problem (test/runtests.jl:58)
+    y0 = rng.uniform(0.5, 2.0, (n, 1))
+    got = m.solve_ensemble(method, m.DeviceRHS("linear", 1.0), y0, [1.0, 0.0])
+    ref = O.solve_ensemble(method, "linear", y0, [1.0, 0.0], [1.0])
+    assert_same(got, ref)
+
+
+def test_kepler_feh78_tight_tolerance_bit_exact_and_energy():
+    """Config 3: ode78, tol 1e-12, 10 periods; energy drift check."""
+    rng = np.random.default_rng(20261019)
+    n = 512
+    e = rng.uniform(0, 0.9, n)
+    y0 = np.stack([1 - e, np.zeros(n), np.zeros(n), np.sqrt((1 + e) / (1 - e))], 1)
+    ts = [0.0, 20 * math.pi]
+    got = m.solve_ensemble("ode78", m.DeviceRHS("kepler"), y0, ts, reltol=1e-12, abstol=1e-12)
+    ref = O.solve_ensemble("ode78", "kepler", y0, ts, None, reltol=1e-12, abstol=1e-12)
+    assert_same(got, ref)
+    en = lambda y: 0.5 * (y[:, 2] ** 2 + y[:, 3] ** 2) - 1 / np.hypot(y[:, 0], y[:, 1])
+    assert np.max(np.abs(en(got["y_final"]) - en(y0))) < 2e-9
+
+
+def test_robertson_ode23s_ensemble_bit_exact():
+    """Config 4: per-trajectory rate constants, FD Jacobian, in-register 3x3 LU."""
+    rng = np.random.default_rng(20261019)
+    n = 512
+    k = np.array([0.04, 3e7, 1e4]) * 10 ** rng.uniform(-0.5, 0.5, (n, 3))
+    y0 = np.tile([1.0, 0.0, 0.0], (n, 1))
+    kw = dict(reltol=1e-8, abstol=1e-8)
+    got = m.solve_ensemble("ode23s", m.DeviceRHS("robertson", 0.04, 3e7, 1e4), y0, [0.0, 1e5], params=k, **kw)
+    ref = O.solve_ensemble("ode23s", "robertson", y0, [0.0, 1e5], k, **kw)
+    assert_same(got, ref)
+    assert np.all(np.abs(got["y_final"].sum(1) - 1.0) < 1e-6)
+
+
+def test_rober_kat_on_gpu():
+    """test/runtests.jl:78-96 through the ode23s front-end."""
+    F = m.DeviceRHS("robertson", 0.04, 3e7, 1e4)
+    t, y, st = m.ode23s.stats(F, [1.0, 0.0, 0.0], [0.0, 1e11], abstol=1e-8, reltol=1e-8, maxstep=1e11 / 10,
+                              minstep=1e11 / 1e18)
+    ref = np.array([0.2083340149701255e-07, 0.8333360770334713e-13, 0.9999999791665050])
+    assert np.max(np.abs(y[-1] - ref)) < 2e-10
+    o = O.solve("ode23s", "robertson", [1.0, 0.0, 0.0], [0.0, 1e11], [0.04, 3e7, 1e4], abstol=1e-8, reltol=1e-8,
+                maxstep=1e10, minstep=1e-7)
+    assert np.array_equal(t, o.t) and np.array_equal(y, o.y)
+    assert (st["n_accept"], st["n_reject"], st["n_rhs"]) == (o.n_accept, o.n_reject, o.n_rhs) == (905, 12, 6377)
+
+
+@pytest.mark.parametrize("method", ADAPTIVE + ["ode23s"])
+@pytest.mark.parametrize("points", ["all", "specified"])
+def test_single_system_tout_yout_bit_exact(method, points):
+    """The (tout, yout) contract incl. Hermite / Rosenbrock dense output at interior tspan points."""
+    F = m.DeviceRHS("lorenz", *LORENZ)
+    ts = [0.0, 0.3, 0.31, 1.0, 1.7, 2.0]
+    t, y, st = getattr(m, method).stats(F, [1.0, 1.0, 1.0], ts, points=points)
+    o = O.solve(method, "lorenz", [1.0, 1.0, 1.0], ts, LORENZ, points=points)
+    assert np.array_equal(t, o.t) and np.array_equal(y, o.y)
+    assert (st["n_accept"], st["n_reject"], st["n_rhs"]) == (o.n_accept, o.n_reject, o.n_rhs)
+    if points == "specified" and method != "ode23s":
+        assert np.array_equal(t, ts)
+
+
+@pytest.mark.parametrize("method", ADAPTIVE + ["ode23s"])
+def test_attempt_trace_bit_exact(method):
+    """Accept/reject sequence, dt and err of every attempt of one trajectory."""
+    y0 = lorenz_ics(8, 3)
+    tr = 5
+    got = m.solve_ensemble(method, m.DeviceRHS("lorenz", *LORENZ), y0, [0.0, 3.0], trace_traj=tr)
+    o = O.solve(method, "lorenz", y0[tr], [0.0, 3.0], LORENZ, trace=True)
+    assert got["trace_n"] == len(o.trace)
+    assert np.array_equal(got["trace"], o.trace)
+    assert o.n_reject > 0
+
+
+@pytest.mark.parametrize("method", FIXED)
+def test_fixed_step_bit_exact(method):
+    F = m.DeviceRHS("lorenz", *LORENZ)
+    ts = np.linspace(0.0, 1.0, 201)
+    t, y = getattr(m, method)(F, [1.0, 1.0, 1.0], ts)
+    o = O.solve(method, "lorenz", [1.0, 1.0, 1.0], ts, LORENZ)
+    assert np.array_equal(t, o.t) and np.array_equal(y, o.y)
+    y0 = lorenz_ics(300, 4)
+    got = m.solve_ensemble(method, F, y0, ts)
+    for i in (0, 7, 299):
+        oi = O.solve(method, "lorenz", y0[i], ts, LORENZ)
+        assert np.array_equal(got["y_final"][i], oi.y[-1])
+
+
+ALL = FIXED + ADAPTIVE + ["ode23s"]
+
+
+@pytest.mark.parametrize("solver", ALL)
+def test_reference_runtests_analytic(solver):
+    """test/runtests.jl:40-70 (T = Float64, tol 1e-2) through the odeXX front-ends."""
+    tol = 1e-2
+    f = getattr(m, solver)
+    t, y = f(m.DeviceRHS("const", 6.0), 0.0, np.arange(0, 11) * 0.1)
+    assert np.max(np.abs(y - 6 * t)) < tol and t.dtype == np.float64
+    ts = np.arange(0, 1001) * 0.001
+    t, y = f(m.DeviceRHS("timelin", 2.0), 0.0, ts)
+    assert np.max(np.abs(y - t ** 2)) < tol
+    t, y = f(m.DeviceRHS("linear", 1.0), 1.0, ts)
+    assert np.max(np.abs(y - np.exp(t))) < tol
+    if solver != "ode23s":
+        t, y = f(m.DeviceRHS("linear", 1.0), 1.0, ts[::-1].copy())
+        assert np.max(np.abs(y - np.exp(t - 1))) < tol
+    ts = np.arange(0, int(2 * math.pi / 0.001) + 1) * 0.001
+    t, y = f(m.DeviceRHS("rotation"), [1.0, 2.0], ts)
+    ex = np.stack([np.cos(t) - 2 * np.sin(t), 2 * np.cos(t) + np.sin(t)], 1)
+    assert np.max(np.abs(y - ex)) < tol
+
+
+def test_ode23s_negative_start():
+    """test/runtests.jl:75."""
+    t, y = m.ode23s(m.DeviceRHS("rotation"), [1.0, 2.0], [-5.0, 0.0])
+    assert len(t) > 1
+
+
+def test_readme_solve_common_interface(capsys):
+    """README.md:17-23 / test/common.jl: solve(prob, ode45(), reltol=1e-8, abstol=1e-8)."""
+    prob = m.ODEProblem(m.DeviceRHS("linear", 1.01), 0.5, (0.0, 1.0))
+    sol = m.solve(prob, m.ode45(), reltol=1e-8, abstol=1e-8)
+    assert sol.retcode == "Succss" and len(sol.t) == 12 and sol.t[-1] == 1.0
+    assert sol[-1] == 1.3728005108017367
+    assert abs(sol[-1] - 0.5 * math.exp(1.01)) < 5e-9
+    assert isinstance(float(sol[1]), float)
+    # 2-D array problem keeps its shape (test/common.jl:21-23)
+    prob2 = m.ODEProblem(m.DeviceRHS("rotation"), np.array([[1.0], [2.0]]), (0.0, 1.0))
+    for alg in (m.ode23(), m.ode45(), m.ode78()):
+        s2 = m.solve(prob2, alg, dt=1 / 16, dtmin=np.finfo(float).eps, abstol=1e-6, reltol=1e-3)
+        assert s2[1].shape == (2, 1)
+    # saveat, save_everystep=false -> points=:specified
+    s3 = m.solve(prob, m.ode45(), saveat=[0.25, 0.5], reltol=1e-8, abstol=1e-8)
+    assert list(s3.t) == [0.25, 0.5, 1.0] or list(s3.t) == [0.0, 0.25, 0.5, 1.0]
+
+
+def test_reference_error_behaviour(capsys):
+    F = m.DeviceRHS("linear", 1.0)
+    with pytest.raises(ValueError, match="Zero time span"):
+        m.ode45(F, 1.0, [0.0, 0.0])
+    with pytest.raises(ValueError, match="initstep has wrong sign"):
+        m.ode45(F, 1.0, [0.0, 1.0], initstep=-0.1)
+    with pytest.raises(ValueError, match="Unrecognized option points"):
+        m.ode45(F, 1.0, [0.0, 1.0], points="some")
+    # dt < minstep on the first rejection: warning + truncated solution (src/runge_kutta.jl:358-360)
+    t, y = m.ode45(m.DeviceRHS("lorenz", *LORENZ), [1.0, 1.0, 1.0], [0.0, 10.0], minstep=1e10)
+    assert "Warning: dt < minstep.  Stopping." in capsys.readouterr().out
+    o = O.solve("ode45", "lorenz", [1.0, 1.0, 1.0], [0.0, 10.0], LORENZ, minstep=1e10)
+    assert t[-1] < 10.0 and np.array_equal(t, o.t) and np.array_equal(y, o.y)
+    # max_steps guard instead of the reference's endless loop
+    got = m.solve_ensemble("ode45", m.DeviceRHS("lorenz", *LORENZ), lorenz_ics(4), [0.0, 10.0], max_steps=50)
+    assert np.all(got["status"] == 2) and np.all(got["n_accept"] + got["n_reject"] == 50)
+
+
+def test_empty_and_ragged_ensembles():
+    F = m.DeviceRHS("lorenz", *LORENZ)
+    got = m.solve_ensemble("ode45", F, np.zeros((0, 3)), [0.0, 1.0])
+    assert got["y_final"].shape == (0, 3)
+    for n in (1, 31, 33, 129, 1000):
+        y0 = lorenz_ics(n, n)
+        got = m.solve_ensemble("ode45", F, y0, [0.0, 0.5])
+        ref = O.solve_ensemble("ode45", "lorenz", y0, [0.0, 0.5], LORENZ)
+        assert_same(got, ref)

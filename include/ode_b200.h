@@ -201,21 +201,25 @@ int ode_b200_solve_large(const ode_b200_opts* opts, int64_t n, const double* y0,
  * two halves of an attempt the host exchanges `xchg_send` (ODE_B200_XCHG_DOUBLES
  * doubles per rank) with an all-gather into `xchg_recv` ([world][XCHG]).
  * All pointers are device pointers; work is enqueued on `stream`. */
-#define ODE_B200_XCHG_DOUBLES 32
+#define ODE_B200_XCHG_DOUBLES 96
 typedef struct ode_b200_slab ode_b200_slab;
 int ode_b200_slab_create(const ode_b200_opts* opts, int64_t n_local, int64_t n_global, int32_t rank,
                          int32_t world, const double* params, double t0, double tend, void* stream,
                          ode_b200_slab** out);
 int ode_b200_slab_set_state(ode_b200_slab* s, const double* y_local_dev); /* [n_local] device */
+/* optional attempt trace on the device: rows (t, dt, err, accepted) */
+int ode_b200_slab_set_trace(ode_b200_slab* s, double* trace_dev, int64_t trace_cap);
 int ode_b200_slab_get_state(ode_b200_slab* s, double* y_local_dev);
-/* hinit (src/ODE.jl:85-112) in three phases, each followed by an exchange */
+/* hinit (src/ODE.jl:85-112) in phases 0..3; phases 0, 1 and 2 are each followed by an exchange
+ * (0: y edges; 1: max|y|, max|f0|, f0 edges; 2: max|f1-f0|; 3: dt) */
 int ode_b200_slab_init_phase(ode_b200_slab* s, int phase, double* xchg_send, const double* xchg_recv);
 /* one attempt: stages + local error partials -> xchg_send */
 int ode_b200_slab_attempt(ode_b200_slab* s, double* xchg_send);
 /* controller: reduce gathered partials, accept/reject, new dt, ghost refresh */
 int ode_b200_slab_control(ode_b200_slab* s, const double* xchg_recv);
-/* copy the control block {done, status, n_accept, n_reject, t, dt, err} to host (synchronises stream) */
-int ode_b200_slab_poll(ode_b200_slab* s, double* ctl_out /*[8]*/);
+/* copy the control block to the host (synchronises the stream): ctl_out[12] =
+ * {done, status, n_accept, n_reject, t, dt, err, t_final, n_rhs, attempts, trace_n, ghost width H} */
+int ode_b200_slab_poll(ode_b200_slab* s, double* ctl_out /*[12]*/);
 void ode_b200_slab_free(ode_b200_slab* s);
 
 /* ---- measurement hooks ---------------------------------------------------- */

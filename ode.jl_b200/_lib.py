@@ -8,7 +8,8 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libode_b200.so")
+# ODE_B200_LIB lets a developer point at an experimental build of the same ABI
+LIB_PATH = os.environ.get("ODE_B200_LIB") or os.path.join(_HERE, "libode_b200.so")
 
 # include/ode_b200.h enums
 METHODS = dict(ode1=0, ode2_midpoint=1, ode2_heun=2, ode4=3, ode21=4, ode23=5, ode45_fe=6, ode45_dp=7, ode45=7,
@@ -17,7 +18,7 @@ RHS = dict(linear=0, const=1, timelin=2, rotation=3, lorenz=4, vdp=5, robertson=
 POINTS = {"all": 0, "specified": 1, "final": 2}
 STATUS = {0: "OK", 1: "MINSTEP", 2: "MAXSTEPS", 3: "NONFINITE", 4: "SINGULAR", 5: "OVERFLOW"}
 E_ZERO_SPAN, E_INITSTEP, E_POINTS, E_NOT_ADAPTIVE, E_NO_DEVICE, E_UNSUPPORTED = -2, -3, -4, -5, -6, -8
-XCHG_DOUBLES = 32
+XCHG_DOUBLES = 96
 
 dp = C.POINTER(C.c_double)
 ip = C.POINTER(C.c_int32)
@@ -98,6 +99,7 @@ def lib():
                                        C.c_double, C.c_void_p, C.POINTER(C.c_void_p)]
     L.ode_b200_slab_set_state.argtypes = [C.c_void_p, C.c_void_p]
     L.ode_b200_slab_get_state.argtypes = [C.c_void_p, C.c_void_p]
+    L.ode_b200_slab_set_trace.argtypes = [C.c_void_p, C.c_void_p, C.c_int64]
     L.ode_b200_slab_init_phase.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]
     L.ode_b200_slab_attempt.argtypes = [C.c_void_p, C.c_void_p]
     L.ode_b200_slab_control.argtypes = [C.c_void_p, C.c_void_p]

@@ -43,8 +43,12 @@ __device__ __forceinline__ void hermite_point(double* out, double tq, double t, 
   }
 }
 
+#ifndef ODEB200_ADAPT_MIN_BLOCKS
+#define ODEB200_ADAPT_MIN_BLOCKS 1
+#endif
+
 template <class Tab, class Rhs, int MODE>
-__global__ void __launch_bounds__(ENS_BLOCK) ens_adapt_kernel(const EnsembleArgs A) {
+__global__ void __launch_bounds__(ENS_BLOCK, ODEB200_ADAPT_MIN_BLOCKS) ens_adapt_kernel(const EnsembleArgs A) {
   constexpr int D = Rhs::DOF, S = Tab::S, NPA = RhsNP<Rhs>::value;
   constexpr bool FSAL = Tab::fsal();
   constexpr double EXPO = 1.0 / (double)(Tab::ORDER + 1);  // T(1/(order+1)) :436

@@ -1,27 +1,623 @@
-// large.cu -- single large method-of-lines system (placeholder until the fused
-// stage kernels land; every entry point reports ODE_B200_E_UNSUPPORTED).
+// large.cu -- host side of the large-system regime: slab sessions, the device
+// control kernel, hinit in phases, and the single-GPU convenience call.
+// Kernels: large.cuh (fused attempt) + the small init/control kernels below.
 #include <cuda_runtime.h>
 
-#include "../../include/ode_b200.h"
+#include <cmath>
+#include <cstring>
+#include <new>
+#include <vector>
+
 #include "host_util.cuh"
+#include "large.cuh"
+
+namespace odeb200 {
+
+// ---- control kernel -------------------------------------------------------------
+// stepsize_hw92! :435-441 on the globally reduced sum, the accept/reject branch of
+// oderk_adapt :312-366, and the ghost refresh for the next step.
+__global__ void large_control_kernel(const ControlArgs C) {
+  LargeCtl* ctl = C.ctl;
+  __shared__ int refresh;
+  if (ctl->done) return;
+  if (threadIdx.x == 0) {
+    refresh = 0;
+    dm_dd tot;
+    tot.hi = 0.0;
+    tot.lo = 0.0;
+    double m = 0.0, nf = 0.0;
+    for (int r = 0; r < C.world; r++) {  // fixed rank order on every rank
+      const double* x = C.xrecv + (long long)r * XCHG;
+      dm_dd o;
+      o.hi = x[XS_HI];
+      o.lo = x[XS_LO];
+      tot = dd_add(tot, o);
+      m = normInf_step(m, x[XS_MAX]);
+      nf = fmax(nf, x[XS_NAN]);
+    }
+    const double dt = ctl->dt, tdir = ctl->tdir, t = ctl->t;
+    double err, newdt;
+    int timeout = ctl->timeout;
+    if (nf > 0.0) {  // :432
+      err = 10.0;
+      newdt = dt * 0.2;
+      timeout = 5;
+    } else {
+      // norm(xerr, 2) for a long vector: maxabs shortcut, else sqrt of the exact sum
+      if (m == 0.0 || m != m || !is_finite(m))
+        err = m;
+      else
+        err = sqrt(tot.hi + tot.lo);
+      double nd = jl_min(ctl->maxstep,
+                         (tdir * dt) * jl_max(0.2, 0.8 * dm_pow(1.0 / err, 1.0 / (double)(C.order + 1))));  // :436
+      if (timeout > 0) {
+        nd = jl_min(nd, dt);
+        timeout -= 1;
+      }
+      newdt = tdir * nd;
+    }
+    ctl->attempts += 1;
+    ctl->err = err;
+    ctl->newdt = newdt;
+    const bool accept = err <= 1.0;
+    if (C.trace && ctl->trace_n < ctl->trace_cap) {
+      double* row = C.trace + ctl->trace_n * 4;
+      row[0] = t;
+      row[1] = dt;
+      row[2] = err;
+      row[3] = accept ? 1.0 : 0.0;
+    }
+    ctl->trace_n += 1;
+    ctl->accepted_last = accept ? 1 : 0;
+    if (accept) {
+      ctl->nacc += 1;
+      ctl->par ^= 1;  // y <-> ytrial, k1 <-> k_next  (:341,:347)
+      if (ctl->islast) {
+        ctl->t_final = t + dt;
+        ctl->done = 1;
+        ctl->status = ODE_B200_ST_OK;
+      } else {
+        double tn = t + dt;  // :350
+        double dn = newdt;   // :351
+        int islast = 0;
+        if (tdir * (tn + dn + dn / 100) >= tdir * ctl->tend) {  // :354-357
+          dn = ctl->tend - tn;
+          islast = 1;
+        }
+        ctl->t = tn;
+        ctl->dt = dn;
+        ctl->islast = islast;
+        ctl->t_final = tn;
+        refresh = 1;
+      }
+    } else if (fabs(newdt) < ctl->minstep) {  // :358-360
+      ctl->done = 1;
+      ctl->status = ODE_B200_ST_MINSTEP;
+    } else {  // :361-366
+      ctl->islast = 0;
+      ctl->nrej += 1;
+      ctl->dt = newdt;
+      timeout = 5;
+      if (!is_finite(newdt)) {
+        ctl->done = 1;
+        ctl->status = ODE_B200_ST_NONFINITE;
+      }
+    }
+    ctl->timeout = timeout;
+    if (!ctl->done && ctl->attempts >= ctl->max_steps) {
+      ctl->done = 1;
+      ctl->status = ODE_B200_ST_MAXSTEPS;
+    }
+  }
+  __syncthreads();
+  if (!refresh) return;
+  // ghost cells of the new y and k1 from the neighbours' edges (periodic ring)
+  const int par = ctl->par, H = C.H;
+  const int lr = (C.rank + C.world - 1) % C.world, rr = (C.rank + 1) % C.world;
+  const double* xl = C.xrecv + (long long)lr * XCHG + XS_EDGE;
+  const double* xr = C.xrecv + (long long)rr * XCHG + XS_EDGE;
+  for (int j = threadIdx.x; j < H; j += blockDim.x) {
+    C.Y[par][j] = xl[H + j];
+    C.Y[par][C.n + H + j] = xr[j];
+    C.K[par][j] = xl[3 * H + j];
+    C.K[par][C.n + H + j] = xr[2 * H + j];
+  }
+}
+
+// ---- hinit (src/ODE.jl:85-112) in phases ------------------------------------------
+// pack the H edge values of an interior array into slot `slot` (0: A, 1: B)
+__global__ void pack_edges_kernel(const double* a, double* xsend, long long n, int H, int slot) {
+  int j = threadIdx.x;
+  if (j < H) {
+    xsend[XS_EDGE + 2 * H * slot + j] = a[H + j];
+    xsend[XS_EDGE + 2 * H * slot + H + j] = a[H + (n - H) + j];
+  }
+}
+__global__ void large_ghost_kernel(double* a, const double* xrecv, long long n, int rank, int world, int H, int slot) {
+  const int lr = (rank + world - 1) % world, rr = (rank + 1) % world;
+  const double* xl = xrecv + (long long)lr * XCHG + XS_EDGE + 2 * H * slot;
+  const double* xr = xrecv + (long long)rr * XCHG + XS_EDGE + 2 * H * slot;
+  int j = threadIdx.x;
+  if (j < H) {
+    a[j] = xl[H + j];
+    a[n + H + j] = xr[j];
+  }
+}
+
+template <int T>
+__device__ __forceinline__ double block_max_nanprop(double v, double* sh) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = normInf_step(v, __shfl_down_sync(0xffffffffu, v, o));
+  if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = v;
+  __syncthreads();
+  double r = 0.0;
+  if (threadIdx.x == 0) {
+    r = sh[0];
+    for (int w = 1; w < T / 32; w++) r = normInf_step(r, sh[w]);
+  }
+  __syncthreads();
+  return r;
+}
+
+// phase 1: f0 = F(t0, y) on the interior -> K[par]; partial max|y|, max|f0|
+template <class Rhs>
+__global__ void __launch_bounds__(256) hinit_f0_kernel(const double* y, double* f0, double* part, long long n, int H,
+                                                       double p0, double p1) {
+  __shared__ double sh[8];
+  double my = 0.0, mf = 0.0;
+  for (long long i = blockIdx.x * 256LL + threadIdx.x; i < n; i += (long long)gridDim.x * 256) {
+    const double um = y[H + i - 1], u = y[H + i], up = y[H + i + 1];
+    const double f = Rhs::point(um, u, up, p0, p1);
+    f0[H + i] = f;
+    my = normInf_step(my, fabs(u));
+    mf = normInf_step(mf, fabs(f));
+  }
+  double a = block_max_nanprop<256>(my, sh);
+  double b = block_max_nanprop<256>(mf, sh);
+  if (threadIdx.x == 0) {
+    part[blockIdx.x * 2] = a;
+    part[blockIdx.x * 2 + 1] = b;
+  }
+}
+// phase 2: x1 = y + (tdir*h0)*f0, f1 = F(t0 + tdir*h0, x1); partial max|f1 - f0|
+template <class Rhs>
+__global__ void __launch_bounds__(256) hinit_f1_kernel(const double* y, const double* f0, const LargeCtl* ctl,
+                                                       double* part, long long n, int H, double p0, double p1) {
+  __shared__ double sh[8];
+  const double th = ctl->tdir * ctl->h0;
+  double md = 0.0;
+  for (long long i = blockIdx.x * 256LL + threadIdx.x; i < n; i += (long long)gridDim.x * 256) {
+    const double xm = y[H + i - 1] + th * f0[H + i - 1];
+    const double x = y[H + i] + th * f0[H + i];
+    const double xp = y[H + i + 1] + th * f0[H + i + 1];
+    const double f1 = Rhs::point(xm, x, xp, p0, p1);
+    md = normInf_step(md, fabs(f1 - f0[H + i]));
+  }
+  double a = block_max_nanprop<256>(md, sh);
+  if (threadIdx.x == 0) part[blockIdx.x * 2] = a;
+}
+__global__ void reduce_max_kernel(const double* part, int nblocks, int ncol, double* xsend) {
+  // one warp; NaN-propagating max of each column
+  for (int c = 0; c < ncol; c++) {
+    double v = 0.0;
+    for (int b = threadIdx.x; b < nblocks; b += 32) v = normInf_step(v, part[b * 2 + c]);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v = normInf_step(v, __shfl_down_sync(0xffffffffu, v, o));
+    if (threadIdx.x == 0) xsend[XS_AUX0 + c] = v;
+  }
+}
+// hinit scalar parts: stage 0 after the (max|y|, max|f0|) exchange, stage 1 after max|f1-f0|
+__global__ void hinit_control_kernel(LargeCtl* ctl, const double* xrecv, int world, int stage, int order) {
+  if (threadIdx.x != 0) return;
+  if (stage == 0) {
+    double n0 = 0.0, n1 = 0.0;
+    for (int r = 0; r < world; r++) {
+      n0 = normInf_step(n0, xrecv[(long long)r * XCHG + XS_AUX0]);
+      n1 = normInf_step(n1, xrecv[(long long)r * XCHG + XS_AUX1]);
+    }
+    const double tau = jl_max(ctl->reltol * n0, ctl->abstol);  // :89
+    const double d0 = n0 / tau, d1 = n1 / tau;                 // :90,:92
+    ctl->tau = tau;
+    ctl->d0 = d0;
+    ctl->d1 = d1;
+    ctl->h0 = (d0 < 1e-5 || d1 < 1e-5) ? 1e-6 : 0.01 * (d0 / d1);  // :93-97
+  } else {
+    double n2 = 0.0;
+    for (int r = 0; r < world; r++) n2 = normInf_step(n2, xrecv[(long long)r * XCHG + XS_AUX0]);
+    const double h0 = ctl->h0, tdir = ctl->tdir;
+    const double d2 = n2 / (ctl->tau * h0);  // :103
+    const double dm = jl_max(ctl->d1, d2);
+    double h1;
+    if (dm <= 1e-15)
+      h1 = jl_max(1e-6, 1e-3 * h0);
+    else
+      h1 = dm_pow(10.0, -(2.0 + dm_log10(dm)) / (double)(order + 1));  // :107-108
+    double dt = tdir * jl_min(jl_min(100.0 * h0, h1), tdir * (ctl->tend - ctl->tstart));  // :111
+    if (ctl->initstep != 0.0) dt = ctl->initstep;  // src/runge_kutta.jl:293
+    ctl->dt = dt;
+    ctl->t = ctl->tstart;
+    ctl->islast = (fabs(ctl->t + dt - ctl->tend) <= jl_eps(ctl->tend)) ? 1 : 0;  // :302
+    ctl->timeout = 0;
+    ctl->nrhs = 2;
+    ctl->t_final = ctl->tstart;
+  }
+}
+
+typedef void (*AttemptKernel)(LargeArgs);
+struct MethodInfo {
+  AttemptKernel kernel;
+  int H, VAL, order, S, fsal;
+};
+template <class Tab>
+static MethodInfo method_info() {
+  using Geo = LargeGeom<Tab, RhsReactionDiffusion>;
+  MethodInfo m;
+  m.kernel = large_attempt_kernel<Tab, RhsReactionDiffusion>;
+  m.H = Geo::H;
+  m.VAL = Geo::VAL;
+  m.order = Tab::ORDER;
+  m.S = Tab::S;
+  m.fsal = Geo::FSAL ? 1 : 0;
+  return m;
+}
+static bool pick_method(int method, MethodInfo* out) {
+  switch (method) {
+    case ODE_B200_M_RK21: *out = method_info<TabRK21>(); return true;
+    case ODE_B200_M_RK23: *out = method_info<TabRK23>(); return true;
+    case ODE_B200_M_RK45_FE: *out = method_info<TabRK45>(); return true;
+    case ODE_B200_M_DOPRI5: *out = method_info<TabDopri5>(); return true;
+    case ODE_B200_M_FEH78: *out = method_info<TabFeh78>(); return true;
+    default: return false;
+  }
+}
+
+}  // namespace odeb200
 
 using namespace odeb200;
 
+struct ode_b200_slab {
+  int device = 0, rank = 0, world = 1;
+  long long n = 0, n_global = 0, tiles = 0;
+  MethodInfo mi;
+  cudaStream_t stream = nullptr;
+  double *Y[2] = {nullptr, nullptr}, *K[2] = {nullptr, nullptr};
+  LargeCtl* ctl = nullptr;
+  double *part = nullptr, *ipart = nullptr;
+  double* trace = nullptr;
+  long long trace_cap = 0;
+  double p0 = 0, p1 = 0;
+  int init_blocks = 0;
+  LargeCtl host_ctl;
+};
+
+static int slab_check(ode_b200_slab* s) {
+  if (!s) return set_err(ODE_B200_E_INVALID, "null slab");
+  ODEB200_CUDA(cudaSetDevice(s->device));
+  return 0;
+}
+
 extern "C" {
-int ode_b200_solve_large(const ode_b200_opts*, int64_t, const double*, const double*, double, double, double*,
-                         ode_b200_large_stats*, double*, int64_t, int64_t*) {
-  return set_err(ODE_B200_E_UNSUPPORTED, "large-system path not built yet");
+
+int ode_b200_slab_create(const ode_b200_opts* o, int64_t n_local, int64_t n_global, int32_t rank, int32_t world,
+                         const double* params, double t0, double tend, void* stream, ode_b200_slab** out) {
+  if (!o || !out) return set_err(ODE_B200_E_INVALID, "null argument");
+  *out = nullptr;
+  int cnt = 0;
+  if (cudaGetDeviceCount(&cnt) != cudaSuccess || cnt <= 0) {
+    cudaGetLastError();
+    return set_err(ODE_B200_E_NO_DEVICE, "no CUDA device available; libode_b200 has no CPU fallback");
+  }
+  if (o->device < 0 || o->device >= cnt) return set_err(ODE_B200_E_INVALID, "device %d out of range", o->device);
+  if (o->rhs != ODE_B200_RHS_REACTION_DIFFUSION)
+    return set_err(ODE_B200_E_UNSUPPORTED, "the large-system path takes a registered stencil RHS (reaction_diffusion)");
+  MethodInfo mi;
+  if (!pick_method(o->method, &mi)) {
+    if (o->method >= 0 && o->method <= ODE_B200_M_RK4)
+      return set_err(ODE_B200_E_NOT_ADAPTIVE, "Can only use this solver with an adaptive RK Butcher table");
+    return set_err(ODE_B200_E_UNSUPPORTED, "method %d has no large-system kernel", o->method);
+  }
+  if (!params || o->n_params < 2) return set_err(ODE_B200_E_INVALID, "reaction_diffusion needs params {kappa, r}");
+  if (world < 1 || rank < 0 || rank >= world) return set_err(ODE_B200_E_INVALID, "bad rank/world");
+  if (n_local < 2 * mi.H || n_global < 32 || n_local > n_global)
+    return set_err(ODE_B200_E_INVALID, "slab too small: n_local %lld (needs >= %d), n_global %lld (needs >= 32)",
+                   (long long)n_local, 2 * mi.H, (long long)n_global);
+  if (o->points == ODE_B200_POINTS_SPECIFIED)
+    return set_err(ODE_B200_E_UNSUPPORTED, "points=:specified is not available on the large-system path yet");
+  if (o->points != ODE_B200_POINTS_ALL && o->points != ODE_B200_POINTS_FINAL)
+    return set_err(ODE_B200_E_POINTS, "Unrecognized option points==%d", o->points);
+  if (!(t0 == t0) || !(tend == tend)) return set_err(ODE_B200_E_INVALID, "NaN in tspan");
+  const double tdir = tend > t0 ? 1.0 : (tend < t0 ? -1.0 : 0.0);
+  if (tdir == 0.0) return set_err(ODE_B200_E_ZERO_SPAN, "Zero time span");
+  if (o->initstep != 0.0 && ((o->initstep > 0 ? 1.0 : -1.0) != tdir))
+    return set_err(ODE_B200_E_INITSTEP, "initstep has wrong sign.");
+  ODEB200_CUDA(cudaSetDevice(o->device));
+  ode_b200_slab* s = new (std::nothrow) ode_b200_slab();
+  if (!s) return set_err(ODE_B200_E_NOMEM, "out of memory");
+  s->device = o->device;
+  s->rank = rank;
+  s->world = world;
+  s->n = n_local;
+  s->n_global = n_global;
+  s->mi = mi;
+  s->stream = (cudaStream_t)stream;
+  s->tiles = (n_local + mi.VAL - 1) / mi.VAL;
+  s->p0 = params[0];
+  s->p1 = params[1];
+  const size_t padded = (size_t)(n_local + 2 * mi.H + 8) * sizeof(double);
+  int sms = 0;
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, o->device);
+  s->init_blocks = sms * 8;
+  bool ok = true;
+  for (int i = 0; i < 2 && ok; i++) {
+    ok = ok && cudaMalloc(&s->Y[i], padded) == cudaSuccess;
+    ok = ok && cudaMalloc(&s->K[i], padded) == cudaSuccess;
+  }
+  ok = ok && cudaMalloc(&s->ctl, sizeof(LargeCtl)) == cudaSuccess;
+  ok = ok && cudaMalloc(&s->part, (size_t)s->tiles * 4 * sizeof(double)) == cudaSuccess;
+  ok = ok && cudaMalloc(&s->ipart, (size_t)s->init_blocks * 2 * sizeof(double)) == cudaSuccess;
+  if (!ok) {
+    cudaGetLastError();
+    ode_b200_slab_free(s);
+    return set_err(ODE_B200_E_NOMEM, "cudaMalloc failed for a slab of %lld points", (long long)n_local);
+  }
+  for (int i = 0; i < 2; i++) {
+    cudaMemsetAsync(s->Y[i], 0, padded, s->stream);
+    cudaMemsetAsync(s->K[i], 0, padded, s->stream);
+  }
+  LargeCtl c;
+  memset(&c, 0, sizeof(c));
+  c.tdir = tdir;
+  c.tstart = t0;
+  c.tend = tend;
+  c.t = t0;
+  c.reltol = o->reltol;
+  c.abstol = o->abstol;
+  c.minstep = o->minstep;
+  c.maxstep = o->maxstep;
+  c.initstep = o->initstep;
+  c.max_steps = o->max_steps > 0 ? o->max_steps : 100000000LL;
+  c.order = mi.order;
+  c.t_final = t0;
+  s->host_ctl = c;
+  ODEB200_CUDA(cudaMemcpyAsync(s->ctl, &s->host_ctl, sizeof(LargeCtl), cudaMemcpyHostToDevice, s->stream));
+  ODEB200_CUDA(cudaStreamSynchronize(s->stream));
+  *out = s;
+  return 0;
 }
-int ode_b200_slab_create(const ode_b200_opts*, int64_t, int64_t, int32_t, int32_t, const double*, double, double, void*,
-                         ode_b200_slab** out) {
-  if (out) *out = nullptr;
-  return set_err(ODE_B200_E_UNSUPPORTED, "large-system path not built yet");
+
+int ode_b200_slab_set_trace(ode_b200_slab* s, double* trace_dev, int64_t trace_cap) {
+  int rc = slab_check(s);
+  if (rc) return rc;
+  s->trace = trace_dev;
+  s->trace_cap = trace_cap;
+  long long v[2] = {0, trace_cap};
+  ODEB200_CUDA(cudaMemcpyAsync(&s->ctl->trace_n, v, sizeof(v), cudaMemcpyHostToDevice, s->stream));
+  ODEB200_CUDA(cudaStreamSynchronize(s->stream));
+  return 0;
 }
-int ode_b200_slab_set_state(ode_b200_slab*, const double*) { return set_err(ODE_B200_E_UNSUPPORTED, "not built"); }
-int ode_b200_slab_get_state(ode_b200_slab*, double*) { return set_err(ODE_B200_E_UNSUPPORTED, "not built"); }
-int ode_b200_slab_init_phase(ode_b200_slab*, int, double*, const double*) { return set_err(ODE_B200_E_UNSUPPORTED, "not built"); }
-int ode_b200_slab_attempt(ode_b200_slab*, double*) { return set_err(ODE_B200_E_UNSUPPORTED, "not built"); }
-int ode_b200_slab_control(ode_b200_slab*, const double*) { return set_err(ODE_B200_E_UNSUPPORTED, "not built"); }
-int ode_b200_slab_poll(ode_b200_slab*, double*) { return set_err(ODE_B200_E_UNSUPPORTED, "not built"); }
-void ode_b200_slab_free(ode_b200_slab*) {}
+
+int ode_b200_slab_set_state(ode_b200_slab* s, const double* y_local_dev) {
+  int rc = slab_check(s);
+  if (rc) return rc;
+  ODEB200_CUDA(cudaMemcpyAsync(s->Y[0] + s->mi.H, y_local_dev, (size_t)s->n * 8, cudaMemcpyDeviceToDevice, s->stream));
+  return 0;
 }
+int ode_b200_slab_get_state(ode_b200_slab* s, double* y_local_dev) {
+  int rc = slab_check(s);
+  if (rc) return rc;
+  int par = 0;
+  ODEB200_CUDA(cudaMemcpyAsync(&par, &s->ctl->par, sizeof(int), cudaMemcpyDeviceToHost, s->stream));
+  ODEB200_CUDA(cudaStreamSynchronize(s->stream));
+  ODEB200_CUDA(cudaMemcpyAsync(y_local_dev, s->Y[par & 1] + s->mi.H, (size_t)s->n * 8, cudaMemcpyDeviceToDevice, s->stream));
+  return 0;
+}
+
+// phase 0: pack y edges -> xchg_send            [exchange]
+// phase 1: y ghosts; f0 = F(t0,y) -> k1; max|y|, max|f0|, f0 edges -> xchg_send   [exchange]
+// phase 2: h0; k1 ghosts; f1 = F(t0+tdir*h0, y + tdir*h0*f0); max|f1-f0| -> xchg_send   [exchange]
+// phase 3: dt, islaststep
+int ode_b200_slab_init_phase(ode_b200_slab* s, int phase, double* xsend, const double* xrecv) {
+  int rc = slab_check(s);
+  if (rc) return rc;
+  const int H = s->mi.H;
+  cudaStream_t st = s->stream;
+  switch (phase) {
+    case 0:
+      pack_edges_kernel<<<1, 32, 0, st>>>(s->Y[0], xsend, s->n, H, 0);
+      note_launch();
+      break;
+    case 1:
+      large_ghost_kernel<<<1, 32, 0, st>>>(s->Y[0], xrecv, s->n, s->rank, s->world, H, 0);
+      hinit_f0_kernel<RhsReactionDiffusion><<<s->init_blocks, 256, 0, st>>>(s->Y[0], s->K[0], s->ipart, s->n, H, s->p0, s->p1);
+      reduce_max_kernel<<<1, 32, 0, st>>>(s->ipart, s->init_blocks, 2, xsend);
+      pack_edges_kernel<<<1, 32, 0, st>>>(s->K[0], xsend, s->n, H, 1);
+      for (int i = 0; i < 4; i++) note_launch();
+      break;
+    case 2:
+      hinit_control_kernel<<<1, 32, 0, st>>>(s->ctl, xrecv, s->world, 0, s->mi.order);
+      large_ghost_kernel<<<1, 32, 0, st>>>(s->K[0], xrecv, s->n, s->rank, s->world, H, 1);
+      hinit_f1_kernel<RhsReactionDiffusion><<<s->init_blocks, 256, 0, st>>>(s->Y[0], s->K[0], s->ctl, s->ipart, s->n, H, s->p0, s->p1);
+      reduce_max_kernel<<<1, 32, 0, st>>>(s->ipart, s->init_blocks, 1, xsend);
+      for (int i = 0; i < 4; i++) note_launch();
+      break;
+    case 3:
+      hinit_control_kernel<<<1, 32, 0, st>>>(s->ctl, xrecv, s->world, 1, s->mi.order);
+      note_launch();
+      break;
+    default:
+      return set_err(ODE_B200_E_INVALID, "init phase must be 0..3");
+  }
+  ODEB200_CUDA(cudaGetLastError());
+  return 0;
+}
+
+int ode_b200_slab_attempt(ode_b200_slab* s, double* xsend) {
+  int rc = slab_check(s);
+  if (rc) return rc;
+  LargeArgs A;
+  A.Y[0] = s->Y[0];
+  A.Y[1] = s->Y[1];
+  A.K[0] = s->K[0];
+  A.K[1] = s->K[1];
+  A.ctl = s->ctl;
+  A.part = s->part;
+  A.xsend = xsend;
+  A.n = s->n;
+  A.tiles = s->tiles;
+  A.p0 = s->p0;
+  A.p1 = s->p1;
+  s->mi.kernel<<<(unsigned)s->tiles, LARGE_THREADS, 0, s->stream>>>(A);
+  note_launch();
+  ODEB200_CUDA(cudaGetLastError());
+  return 0;
+}
+
+int ode_b200_slab_control(ode_b200_slab* s, const double* xrecv) {
+  int rc = slab_check(s);
+  if (rc) return rc;
+  ControlArgs C;
+  C.Y[0] = s->Y[0];
+  C.Y[1] = s->Y[1];
+  C.K[0] = s->K[0];
+  C.K[1] = s->K[1];
+  C.ctl = s->ctl;
+  C.xrecv = xrecv;
+  C.trace = s->trace;
+  C.n = s->n;
+  C.rank = s->rank;
+  C.world = s->world;
+  C.H = s->mi.H;
+  C.order = s->mi.order;
+  large_control_kernel<<<1, 32, 0, s->stream>>>(C);
+  note_launch();
+  ODEB200_CUDA(cudaGetLastError());
+  return 0;
+}
+
+// ctl_out: {done, status, n_accept, n_reject, t, dt, err, t_final, n_rhs, attempts, trace_n, ghost H}
+int ode_b200_slab_poll(ode_b200_slab* s, double* ctl_out) {
+  int rc = slab_check(s);
+  if (rc) return rc;
+  ODEB200_CUDA(cudaMemcpyAsync(&s->host_ctl, s->ctl, sizeof(LargeCtl), cudaMemcpyDeviceToHost, s->stream));
+  ODEB200_CUDA(cudaStreamSynchronize(s->stream));
+  const LargeCtl& c = s->host_ctl;
+  if (ctl_out) {
+    ctl_out[0] = c.done;
+    ctl_out[1] = c.status;
+    ctl_out[2] = (double)c.nacc;
+    ctl_out[3] = (double)c.nrej;
+    ctl_out[4] = c.t;
+    ctl_out[5] = c.dt;
+    ctl_out[6] = c.err;
+    ctl_out[7] = c.t_final;
+    // RHS sweeps: 2 in hinit, S-1 per attempt, +1 per accepted step when the tableau is not FSAL
+    ctl_out[8] = (double)(c.nrhs + c.attempts * (s->mi.S - 1) + (s->mi.fsal ? 0 : c.nacc));
+    ctl_out[9] = (double)c.attempts;
+    ctl_out[10] = (double)c.trace_n;
+    ctl_out[11] = (double)s->mi.H;
+  }
+  return 0;
+}
+
+void ode_b200_slab_free(ode_b200_slab* s) {
+  if (!s) return;
+  cudaSetDevice(s->device);
+  for (int i = 0; i < 2; i++) {
+    if (s->Y[i]) cudaFree(s->Y[i]);
+    if (s->K[i]) cudaFree(s->K[i]);
+  }
+  if (s->ctl) cudaFree(s->ctl);
+  if (s->part) cudaFree(s->part);
+  if (s->ipart) cudaFree(s->ipart);
+  delete s;
+}
+
+int ode_b200_solve_large(const ode_b200_opts* o, int64_t n, const double* y0, const double* params, double t0,
+                         double tend, double* y_out, ode_b200_large_stats* stats, double* trace, int64_t trace_cap,
+                         int64_t* trace_n) {
+  if (!o || !y0) return set_err(ODE_B200_E_INVALID, "null argument");
+  int cnt = 0;
+  if (cudaGetDeviceCount(&cnt) != cudaSuccess || cnt <= 0) {
+    cudaGetLastError();
+    return set_err(ODE_B200_E_NO_DEVICE, "no CUDA device available; libode_b200 has no CPU fallback");
+  }
+  if (o->device < 0 || o->device >= cnt) return set_err(ODE_B200_E_INVALID, "device %d out of range", o->device);
+  ODEB200_CUDA(cudaSetDevice(o->device));
+  cudaStream_t st;
+  ODEB200_CUDA(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
+  ode_b200_slab* s = nullptr;
+  int rc = ode_b200_slab_create(o, n, n, 0, 1, params, t0, tend, st, &s);
+  double *dy = nullptr, *xs = nullptr, *xr = nullptr, *dtrace = nullptr;
+  cudaEvent_t e0 = nullptr, e1 = nullptr;
+  double poll[12] = {0};
+#define LARGE_TRY(x)  \
+  do {                \
+    if (!rc) rc = (x); \
+  } while (0)
+#define LARGE_CUDA(x)                                                                          \
+  do {                                                                                         \
+    if (!rc) {                                                                                 \
+      cudaError_t e__ = (x);                                                                   \
+      if (e__ != cudaSuccess) rc = set_err(ODE_B200_E_CUDA, "%s: %s", #x, cudaGetErrorString(e__)); \
+    }                                                                                          \
+  } while (0)
+  LARGE_CUDA(cudaMalloc(&dy, (size_t)n * 8));
+  LARGE_CUDA(cudaMalloc(&xs, XCHG * 8));
+  LARGE_CUDA(cudaMalloc(&xr, XCHG * 8));
+  LARGE_CUDA(cudaMemsetAsync(xs, 0, XCHG * 8, st));
+  if (trace && trace_cap > 0) {
+    LARGE_CUDA(cudaMalloc(&dtrace, (size_t)trace_cap * 32));
+    LARGE_TRY(ode_b200_slab_set_trace(s, dtrace, trace_cap));
+  }
+  LARGE_CUDA(cudaMemcpyAsync(dy, y0, (size_t)n * 8, cudaMemcpyHostToDevice, st));
+  LARGE_TRY(ode_b200_slab_set_state(s, dy));
+  LARGE_CUDA(cudaEventCreate(&e0));
+  LARGE_CUDA(cudaEventCreate(&e1));
+  LARGE_CUDA(cudaEventRecord(e0, st));
+  for (int ph = 0; ph < 4 && !rc; ph++) {
+    LARGE_TRY(ode_b200_slab_init_phase(s, ph, xs, xr));
+    if (ph < 3) LARGE_CUDA(cudaMemcpyAsync(xr, xs, XCHG * 8, cudaMemcpyDeviceToDevice, st));  // world = 1 "all-gather"
+  }
+  while (!rc) {
+    for (int q = 0; q < 4 && !rc; q++) {  // poll the done flag every 4 attempts; extra launches are no-ops
+      LARGE_TRY(ode_b200_slab_attempt(s, xs));
+      LARGE_CUDA(cudaMemcpyAsync(xr, xs, XCHG * 8, cudaMemcpyDeviceToDevice, st));
+      LARGE_TRY(ode_b200_slab_control(s, xr));
+    }
+    LARGE_TRY(ode_b200_slab_poll(s, poll));
+    if (poll[0] != 0.0) break;
+  }
+  LARGE_CUDA(cudaEventRecord(e1, st));
+  LARGE_TRY(ode_b200_slab_get_state(s, dy));
+  if (y_out) LARGE_CUDA(cudaMemcpyAsync(y_out, dy, (size_t)n * 8, cudaMemcpyDeviceToHost, st));
+  if (trace && dtrace) {
+    long long tn = (long long)poll[10];
+    long long m = tn < trace_cap ? tn : trace_cap;
+    LARGE_CUDA(cudaMemcpyAsync(trace, dtrace, (size_t)m * 32, cudaMemcpyDeviceToHost, st));
+    if (trace_n) *trace_n = tn;
+  }
+  LARGE_CUDA(cudaStreamSynchronize(st));
+  if (!rc && stats) {
+    float ms = 0.f;
+    cudaEventElapsedTime(&ms, e0, e1);
+    stats->n_accept = (int64_t)poll[2];
+    stats->n_reject = (int64_t)poll[3];
+    stats->n_rhs = (int64_t)poll[8];
+    stats->status = (int32_t)poll[1];
+    stats->t_final = poll[7];
+    stats->kernel_ms = ms;
+  }
+  if (e0) cudaEventDestroy(e0);
+  if (e1) cudaEventDestroy(e1);
+  if (dy) cudaFree(dy);
+  if (xs) cudaFree(xs);
+  if (xr) cudaFree(xr);
+  if (dtrace) cudaFree(dtrace);
+  ode_b200_slab_free(s);
+  cudaStreamDestroy(st);
+  return rc;
+#undef LARGE_TRY
+#undef LARGE_CUDA
+}
+
+}  // extern "C"

@@ -1,0 +1,380 @@
+// large.cuh -- one large method-of-lines system: a whole embedded-RK step ATTEMPT
+// in one fused kernel.
+//
+// Replaces oderk_adapt (/root/reference src/runge_kutta.jl:232-369) on a
+// dof = N state with a registered 3-point stencil right-hand side, with the
+// reference's arithmetic per grid point (rk_embedded_step! :371-399,
+// calc_next_k! :444-458, the scaling of stepsize_hw92! :430-434).
+//
+// Design (B200): the reference re-streams every earlier stage vector for each
+// stage (33 array passes = 264 B per point per attempt if
+// each stage were its own kernel).  Here all S stages of an attempt run inside
+// one CTA-resident tile:
+//   * a CTA owns W = THREADS*P consecutive points, H ghost points on either side
+//     of its VAL = W - 2H valid points; each thread keeps its P points of y, every
+//     dt*k_s and both b-row accumulators in registers for the whole attempt;
+//   * a stage needs ytmp at i-1, i, i+1: inside a thread these are registers, the
+//     two chunk-edge values cross threads through a double-buffered shared-memory
+//     line (one __syncthreads per stage); the tile edge loses one point of
+//     validity per stage, which is what the H >= S-1 ghost points pay for
+//     (redundant work 2H/W ~ 1.6 %);
+//   * HBM traffic per attempt drops to: read y, k1; write ytrial, k_next
+//     = 4 passes = 32 B per point (8.25x less than stage-per-kernel), with
+//     256-bit aligned vector loads/stores; the kernel becomes FP64-issue bound.
+//   * the scaled error is squared and accumulated in double-double (error-free
+//     products and sums), reduced by warp shuffles, then shared memory, then by
+//     the last CTA to finish (fixed order), so the 2-norm does not depend on the
+//     launch geometry or on the number of GPUs.
+//   * accept/reject, the new dt (deterministic pow) and the y/ytrial, k1/k_next
+//     pointer swap happen in a one-block control kernel on the device; the host
+//     only polls a done flag.
+//
+// Domain decomposition uses the same trick one level up: a rank's slab carries H
+// ghost points per side, refreshed once per ACCEPTED step from the neighbours'
+// edge values that ride in the same small all-gather as the error partials.
+#pragma once
+
+#include "common.cuh"
+#include "rhs.cuh"
+#include "tableaus.cuh"
+
+namespace odeb200 {
+
+constexpr int LARGE_THREADS = 256;
+constexpr int LARGE_P = 4;
+constexpr int XCHG = ODE_B200_XCHG_DOUBLES;
+// xchg slots
+constexpr int XS_HI = 0, XS_LO = 1, XS_MAX = 2, XS_NAN = 3, XS_AUX0 = 4, XS_AUX1 = 5, XS_EDGE = 8;
+
+struct LargeCtl {
+  double t, dt, tdir, tstart, tend;
+  double reltol, abstol, minstep, maxstep, initstep;
+  double err, newdt, t_final;
+  double h0, tau, d0, d1;  // hinit scratch
+  long long attempts, max_steps, nacc, nrej, nrhs;
+  long long trace_n, trace_cap;
+  int par;      // y = Y[par], ytrial = Y[par^1]; k1 = K[par], k_next = K[par^1]
+  int islast, timeout, done, status, accepted_last;
+  unsigned int blocks_done;  // last-CTA-done counter of the attempt kernel
+  int order;
+};
+
+struct LargeArgs {
+  double* Y[2];  // padded [n + 2H]
+  double* K[2];
+  LargeCtl* ctl;
+  double* part;   // [tiles][4]: sumsq hi, lo, maxabs, nanflag
+  double* xsend;  // [XCHG]
+  long long n;    // interior points of this slab
+  long long tiles;
+  double p0, p1;  // stencil parameters
+};
+
+__device__ __forceinline__ dm_dd dd_add(dm_dd a, dm_dd b) {
+  dm_dd s = dm_two_sum(a.hi, b.hi);
+  double lo = (a.lo + b.lo) + s.lo;
+  dm_dd r;
+  r.hi = s.hi + lo;
+  r.lo = (s.hi - r.hi) + lo;
+  return r;
+}
+__device__ __forceinline__ dm_dd dd_add_sq(dm_dd acc, double e) {  // acc + e*e, error-free product
+  double p = e * e;
+  double pe = dm_fma(e, e, -p);
+  dm_dd s = dm_two_sum(acc.hi, p);
+  dm_dd r;
+  r.hi = s.hi;
+  r.lo = acc.lo + (s.lo + pe);
+  return r;
+}
+
+template <int H>
+__device__ __forceinline__ void load4(const double* a, long long q, long long lim, double (&v)[4]) {
+  if (q + 4 <= lim) {
+    const double4 x = *reinterpret_cast<const double4*>(a + q);
+    v[0] = x.x;
+    v[1] = x.y;
+    v[2] = x.z;
+    v[3] = x.w;
+  } else {
+#pragma unroll
+    for (int p = 0; p < 4; p++) v[p] = (q + p < lim) ? a[q + p] : 0.0;
+  }
+}
+
+// ---- the fused attempt ---------------------------------------------------------
+template <class Tab, class Rhs>
+struct LargeGeom {
+  static constexpr int S = Tab::S;
+  static constexpr bool FSAL = Tab::fsal();
+  static constexpr int G = S - 1 + (FSAL ? 0 : 1);  // stencil radius 1 per RHS evaluation
+  static constexpr int H = (G + 3) / 4 * 4;         // ghost width, multiple of 4 for 32-byte alignment
+  static constexpr int W = LARGE_THREADS * LARGE_P;
+  static constexpr int VAL = W - 2 * H;
+};
+
+template <class Tab, class Rhs>
+__global__ void __launch_bounds__(LARGE_THREADS) large_attempt_kernel(const LargeArgs A) {
+  using Geo = LargeGeom<Tab, Rhs>;
+  constexpr int S = Geo::S, H = Geo::H, VAL = Geo::VAL, P = LARGE_P, T = LARGE_THREADS;
+  constexpr bool FSAL = Geo::FSAL;
+  constexpr int NK = S > 1 ? S - 1 : 1;
+  static_assert(P == 4, "vector width");
+
+  __shared__ double eL[2][T], eR[2][T];
+  __shared__ double red[T / 32][4];
+  __shared__ bool is_last;
+
+  LargeCtl* ctl = A.ctl;
+  if (ctl->done) return;
+  const int tid = threadIdx.x;
+  const long long tile = blockIdx.x;
+  const int par = ctl->par;
+  const double dt = ctl->dt, t = ctl->t;
+  const double reltol = ctl->reltol, abstol = ctl->abstol;
+  const double* __restrict__ yA = A.Y[par];
+  const double* __restrict__ kA = A.K[par];
+  double* __restrict__ ytA = A.Y[par ^ 1];
+  double* __restrict__ knA = A.K[par ^ 1];
+  const long long lim = A.n + 2 * H;
+  const long long q0 = tile * VAL + (long long)tid * P;  // padded index of my first point
+
+  double y[P], k1[P];
+  load4<H>(yA, q0, lim, y);
+  load4<H>(kA, q0, lim, k1);
+
+  double ytrial[P], yerr[P], dtk[NK][P], klast[P];
+  constexpr double b10 = Tab::b(0, 0), b20 = Tab::b(1, 0);
+#pragma unroll
+  for (int p = 0; p < P; p++) {
+    ytrial[p] = (b10 != 0.0) ? b10 * k1[p] : 0.0;
+    yerr[p] = (b20 != 0.0) ? b20 * k1[p] : 0.0;
+    dtk[0][p] = dt * k1[p];
+    klast[p] = k1[p];
+  }
+  (void)t;  // the registered stencil RHS is autonomous; t + c*dt is not needed
+
+  static_for<S - 1>([&](auto I) {
+    constexpr int s = decltype(I)::value + 1;
+    constexpr int buf = s & 1;
+    double ytmp[P], ks[P];
+#pragma unroll
+    for (int p = 0; p < P; p++) ytmp[p] = y[p];
+    static_for<s>([&](auto J) {
+      constexpr int ss = decltype(J)::value;
+      constexpr double a = Tab::a(s, ss);
+      if constexpr (a != 0.0) {
+#pragma unroll
+        for (int p = 0; p < P; p++) ytmp[p] = ytmp[p] + dtk[ss][p] * a;  // (dt*k)*a :454
+      }
+    });
+    eL[buf][tid] = ytmp[0];
+    eR[buf][tid] = ytmp[P - 1];
+    __syncthreads();
+    const double left = (tid > 0) ? eR[buf][tid - 1] : ytmp[0];
+    const double right = (tid < T - 1) ? eL[buf][tid + 1] : ytmp[P - 1];
+#pragma unroll
+    for (int p = 0; p < P; p++) {
+      const double um = (p == 0) ? left : ytmp[p - 1];
+      const double up = (p == P - 1) ? right : ytmp[p + 1];
+      ks[p] = Rhs::point(um, ytmp[p], up, A.p0, A.p1);
+    }
+    constexpr double b1 = Tab::b(0, s), b2 = Tab::b(1, s);
+#pragma unroll
+    for (int p = 0; p < P; p++) {
+      if constexpr (b1 != 0.0) ytrial[p] = ytrial[p] + b1 * ks[p];
+      if constexpr (b2 != 0.0) yerr[p] = yerr[p] + b2 * ks[p];
+      if constexpr (s < S - 1) dtk[s][p] = dt * ks[p];
+      if constexpr (s == S - 1) klast[p] = ks[p];
+    }
+  });
+#pragma unroll
+  for (int p = 0; p < P; p++) {  // :395-398
+    yerr[p] = dt * (ytrial[p] - yerr[p]);
+    ytrial[p] = y[p] + dt * ytrial[p];
+  }
+  double knext[P];
+  if constexpr (FSAL) {
+#pragma unroll
+    for (int p = 0; p < P; p++) knext[p] = klast[p];
+  } else {  // f1 = F(t+dt, ytrial) :320, fused as one more stencil sweep
+    constexpr int buf = S & 1;
+    eL[buf][tid] = ytrial[0];
+    eR[buf][tid] = ytrial[P - 1];
+    __syncthreads();
+    const double left = (tid > 0) ? eR[buf][tid - 1] : ytrial[0];
+    const double right = (tid < T - 1) ? eL[buf][tid + 1] : ytrial[P - 1];
+#pragma unroll
+    for (int p = 0; p < P; p++) {
+      const double um = (p == 0) ? left : ytrial[p - 1];
+      const double up = (p == P - 1) ? right : ytrial[p + 1];
+      knext[p] = Rhs::point(um, ytrial[p], up, A.p0, A.p1);
+    }
+  }
+
+  // ---- scaled error (stepsize_hw92! :430-435), valid points only -------------
+  dm_dd acc;
+  acc.hi = 0.0;
+  acc.lo = 0.0;
+  double mx = 0.0;
+  bool anynan = false;
+  const int off0 = tid * P;
+  bool allvalid = true;
+#pragma unroll
+  for (int p = 0; p < P; p++) {
+    const int off = off0 + p;
+    const long long li = q0 + p - H;  // interior index
+    const bool valid = (off >= H) && (off < H + VAL) && (li < A.n);
+    allvalid = allvalid && valid;
+    if (valid) {
+      anynan = anynan || (ytrial[p] != ytrial[p]);
+      const double ay = fabs(y[p]), at = fabs(ytrial[p]);
+      const double e = yerr[p] / (abstol + ((ay > at) ? ay : at) * reltol);  // :433
+      acc = dd_add_sq(acc, e);
+      mx = normInf_step(mx, fabs(e));
+    }
+  }
+  // stores
+  if (allvalid) {
+    *reinterpret_cast<double4*>(ytA + q0) = make_double4(ytrial[0], ytrial[1], ytrial[2], ytrial[3]);
+    *reinterpret_cast<double4*>(knA + q0) = make_double4(knext[0], knext[1], knext[2], knext[3]);
+  } else {
+#pragma unroll
+    for (int p = 0; p < P; p++) {
+      const int off = off0 + p;
+      const long long li = q0 + p - H;
+      if ((off >= H) && (off < H + VAL) && (li < A.n)) {
+        ytA[q0 + p] = ytrial[p];
+        knA[q0 + p] = knext[p];
+      }
+    }
+  }
+  // slab edges ride along with the error partials (ghost refresh on accept)
+#pragma unroll
+  for (int p = 0; p < P; p++) {
+    const int off = off0 + p;
+    const long long li = q0 + p - H;
+    if ((off >= H) && (off < H + VAL) && (li < A.n)) {
+      if (li < H) {
+        A.xsend[XS_EDGE + li] = ytrial[p];
+        A.xsend[XS_EDGE + 2 * H + li] = knext[p];
+      }
+      if (li >= A.n - H) {
+        A.xsend[XS_EDGE + H + (li - (A.n - H))] = ytrial[p];
+        A.xsend[XS_EDGE + 3 * H + (li - (A.n - H))] = knext[p];
+      }
+    }
+  }
+
+  // ---- block reduction: warp shuffles, then shared memory ----------------------
+  double nanf = anynan ? 1.0 : 0.0;
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    dm_dd other;
+    other.hi = __shfl_down_sync(0xffffffffu, acc.hi, o);
+    other.lo = __shfl_down_sync(0xffffffffu, acc.lo, o);
+    acc = dd_add(acc, other);
+    mx = normInf_step(mx, __shfl_down_sync(0xffffffffu, mx, o));
+    nanf = fmax(nanf, __shfl_down_sync(0xffffffffu, nanf, o));
+  }
+  if ((tid & 31) == 0) {
+    red[tid >> 5][0] = acc.hi;
+    red[tid >> 5][1] = acc.lo;
+    red[tid >> 5][2] = mx;
+    red[tid >> 5][3] = nanf;
+  }
+  __syncthreads();
+  if (tid == 0) {
+    dm_dd tot;
+    tot.hi = red[0][0];
+    tot.lo = red[0][1];
+    double m = red[0][2], nf = red[0][3];
+    for (int w = 1; w < T / 32; w++) {
+      dm_dd o;
+      o.hi = red[w][0];
+      o.lo = red[w][1];
+      tot = dd_add(tot, o);
+      m = normInf_step(m, red[w][2]);
+      nf = fmax(nf, red[w][3]);
+    }
+    double* pp = A.part + tile * 4;
+    pp[0] = tot.hi;
+    pp[1] = tot.lo;
+    pp[2] = m;
+    pp[3] = nf;
+    __threadfence();
+    unsigned int done = atomicAdd(&ctl->blocks_done, 1u);
+    is_last = (done == (unsigned int)(gridDim.x - 1));
+  }
+  __syncthreads();
+  if (!is_last) return;
+  // ---- last CTA: reduce all tile partials in a fixed order -> xsend[0..3] -------
+  __threadfence();
+  dm_dd a2;
+  a2.hi = 0.0;
+  a2.lo = 0.0;
+  double m2 = 0.0, n2 = 0.0;
+  for (long long b = tid; b < A.tiles; b += T) {
+    const volatile double* pp = A.part + b * 4;
+    dm_dd o;
+    o.hi = pp[0];
+    o.lo = pp[1];
+    a2 = dd_add(a2, o);
+    m2 = normInf_step(m2, pp[2]);
+    n2 = fmax(n2, pp[3]);
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    dm_dd other;
+    other.hi = __shfl_down_sync(0xffffffffu, a2.hi, o);
+    other.lo = __shfl_down_sync(0xffffffffu, a2.lo, o);
+    a2 = dd_add(a2, other);
+    m2 = normInf_step(m2, __shfl_down_sync(0xffffffffu, m2, o));
+    n2 = fmax(n2, __shfl_down_sync(0xffffffffu, n2, o));
+  }
+  __syncthreads();
+  if ((tid & 31) == 0) {
+    red[tid >> 5][0] = a2.hi;
+    red[tid >> 5][1] = a2.lo;
+    red[tid >> 5][2] = m2;
+    red[tid >> 5][3] = n2;
+  }
+  __syncthreads();
+  if (tid == 0) {
+    dm_dd tot;
+    tot.hi = red[0][0];
+    tot.lo = red[0][1];
+    double m = red[0][2], nf = red[0][3];
+    for (int w = 1; w < T / 32; w++) {
+      dm_dd o;
+      o.hi = red[w][0];
+      o.lo = red[w][1];
+      tot = dd_add(tot, o);
+      m = normInf_step(m, red[w][2]);
+      nf = fmax(nf, red[w][3]);
+    }
+    A.xsend[XS_HI] = tot.hi;
+    A.xsend[XS_LO] = tot.lo;
+    A.xsend[XS_MAX] = m;
+    A.xsend[XS_NAN] = nf;
+    ctl->blocks_done = 0;
+  }
+}
+
+// ---- control: global accept/reject from the gathered partials --------------------
+// One block.  xrecv is [world][XCHG]; every rank runs the same arithmetic on the
+// same data, so all ranks take the same decision and the same new dt.
+struct ControlArgs {
+  double* Y[2];
+  double* K[2];
+  LargeCtl* ctl;
+  const double* xrecv;
+  double* trace;
+  long long n;
+  int rank, world, H, order;
+};
+
+__global__ void large_control_kernel(const ControlArgs C);
+__global__ void large_ghost_kernel(double* a, const double* xrecv, long long n, int rank, int world, int H, int slot);
+
+}  // namespace odeb200

@@ -1,0 +1,178 @@
+"""The large-system regime: one method-of-lines ODE system of N unknowns.
+
+`solve_large` is the single-GPU call with host buffers (ode_b200_solve_large).
+`solve_large_distributed` is the domain-decomposed path: every rank owns a
+contiguous slab of the periodic grid plus ghost cells; per step ATTEMPT there is
+exactly one small all-gather (ODE_B200_XCHG_DOUBLES doubles per rank) that
+carries the double-double error partials, the NaN flag and the slab-edge values
+used to refresh the ghosts when the step is accepted.  Every rank then runs the
+same controller arithmetic on the same gathered data, so the accept/reject
+decision and the new dt are identical everywhere without a broadcast
+(reference semantics: oderk_adapt, /root/reference src/runge_kutta.jl:232-369,
+where the whole state is one Vector in one process).
+
+The host loop (`integrate_slab`) is engine-agnostic: the CUDA engine below is the
+product; the CPU tests inject a stand-in engine to exercise the collective
+plumbing with gloo.
+"""
+import ctypes as C
+
+import numpy as np
+
+from . import _lib
+from ._lib import LargeStats, check, lib, XCHG_DOUBLES
+from .api import make_opts, _alg_name, _raise_like_reference
+from .rhs import DeviceRHS
+
+
+def shard_bounds(n_global, world, rank):
+    """Contiguous slab [lo, hi) of rank `rank`; the first n_global % world ranks get one extra point."""
+    base, rem = divmod(int(n_global), int(world))
+    lo = rank * base + min(rank, rem)
+    return lo, lo + base + (1 if rank < rem else 0)
+
+
+def solve_large(alg, F, y0, tspan, *, trace=False, trace_cap=65536, **kw):
+    """One GPU, host buffers in and out.  Returns dict(y, t_final, n_accept, n_reject, n_rhs, status, kernel_ms[, trace])."""
+    if not isinstance(F, DeviceRHS) or F.name != "reaction_diffusion":
+        raise TypeError("the large-system path takes DeviceRHS('reaction_diffusion', kappa, r)")
+    y0 = np.ascontiguousarray(np.asarray(y0, dtype=np.float64))
+    ts = np.asarray(tspan, dtype=np.float64)
+    kw.setdefault("points", "final")
+    o = make_opts(_alg_name(alg), F, ts, dof=min(y0.size, 2 ** 31 - 1), **kw)
+    p = F.param_array()
+    out = np.empty_like(y0)
+    st = LargeStats()
+    tr = np.zeros((trace_cap, 4)) if trace else None
+    tn = C.c_int64(0)
+    dp = _lib.dp
+    try:
+        check(lib().ode_b200_solve_large(C.byref(o), y0.size, y0.ctypes.data_as(dp), p.ctypes.data_as(dp),
+                                         float(ts[0]), float(ts[-1]), out.ctypes.data_as(dp), C.byref(st),
+                                         tr.ctypes.data_as(dp) if trace else None, trace_cap if trace else 0,
+                                         C.byref(tn)))
+    except _lib.OdeB200Error as e:
+        _raise_like_reference(e)
+    res = dict(y=out, t_final=st.t_final, n_accept=st.n_accept, n_reject=st.n_reject, n_rhs=st.n_rhs,
+               status=st.status, kernel_ms=st.kernel_ms)
+    if trace:
+        res["trace"] = tr[:min(tn.value, trace_cap)]
+    return res
+
+
+class CudaSlabEngine:
+    """A slab session of libode_b200.so (device pointers, caller's CUDA stream)."""
+
+    def __init__(self, alg, F, n_local, n_global, rank, world, tspan, stream_ptr, device=0, **kw):
+        ts = np.asarray(tspan, dtype=np.float64)
+        kw.setdefault("points", "final")
+        self.opts = make_opts(_alg_name(alg), F, ts, dof=min(int(n_global), 2 ** 31 - 1), device=device, **kw)
+        p = F.param_array()
+        self.h = C.c_void_p()
+        self.L = lib()
+        try:
+            check(self.L.ode_b200_slab_create(C.byref(self.opts), int(n_local), int(n_global), int(rank), int(world),
+                                              p.ctypes.data_as(_lib.dp), float(ts[0]), float(ts[-1]),
+                                              C.c_void_p(stream_ptr), C.byref(self.h)))
+        except _lib.OdeB200Error as e:
+            _raise_like_reference(e)
+
+    def set_state(self, dev_ptr):
+        check(self.L.ode_b200_slab_set_state(self.h, C.c_void_p(dev_ptr)))
+
+    def get_state(self, dev_ptr):
+        check(self.L.ode_b200_slab_get_state(self.h, C.c_void_p(dev_ptr)))
+
+    def set_trace(self, dev_ptr, cap):
+        check(self.L.ode_b200_slab_set_trace(self.h, C.c_void_p(dev_ptr), int(cap)))
+
+    def init_phase(self, phase, send_ptr, recv_ptr):
+        check(self.L.ode_b200_slab_init_phase(self.h, phase, C.c_void_p(send_ptr), C.c_void_p(recv_ptr)))
+
+    def attempt(self, send_ptr):
+        check(self.L.ode_b200_slab_attempt(self.h, C.c_void_p(send_ptr)))
+
+    def control(self, recv_ptr):
+        check(self.L.ode_b200_slab_control(self.h, C.c_void_p(recv_ptr)))
+
+    def poll(self):
+        a = np.zeros(12)
+        check(self.L.ode_b200_slab_poll(self.h, a.ctypes.data_as(_lib.dp)))
+        return dict(done=bool(a[0]), status=int(a[1]), n_accept=int(a[2]), n_reject=int(a[3]), t=a[4], dt=a[5],
+                    err=a[6], t_final=a[7], n_rhs=int(a[8]), attempts=int(a[9]), trace_n=int(a[10]), ghost=int(a[11]))
+
+    def close(self):
+        if self.h:
+            self.L.ode_b200_slab_free(self.h)
+            self.h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+def integrate_slab(engine, send, recv, exchange, poll_every=4, max_polls=10 ** 9):
+    """The host loop shared by every rank.
+
+    engine   : slab engine (init_phase / attempt / control / poll)
+    send     : this rank's exchange buffer  [XCHG_DOUBLES]   (object with .data_ptr(), or an int pointer)
+    recv     : gathered buffer              [world, XCHG_DOUBLES]
+    exchange : callable() performing recv <- all_gather(send) in stream order
+    The done flag lives on the device; it is polled every `poll_every` attempts
+    (attempts issued after the end are no-ops on the device).
+    """
+    sp = send.data_ptr() if hasattr(send, "data_ptr") else send
+    rp = recv.data_ptr() if hasattr(recv, "data_ptr") else recv
+    for phase in range(4):
+        engine.init_phase(phase, sp, rp)
+        if phase < 3:
+            exchange()
+    polls = 0
+    while True:
+        for _ in range(poll_every):
+            engine.attempt(sp)
+            exchange()
+            engine.control(rp)
+        ctl = engine.poll()
+        polls += 1
+        if ctl["done"] or polls >= max_polls:
+            return ctl
+
+
+def solve_large_distributed(alg, F, y_local, n_global, tspan, *, group=None, poll_every=4, trace=False,
+                            trace_cap=65536, **kw):
+    """Domain-decomposed solve.  y_local: CUDA float64 torch tensor holding this rank's slab
+    (shard_bounds(n_global, world, rank)); returns (y_local_final tensor, ctl dict[, trace tensor])."""
+    import torch
+    import torch.distributed as dist
+
+    world = dist.get_world_size(group) if dist.is_available() and dist.is_initialized() else 1
+    rank = dist.get_rank(group) if world > 1 else 0
+    dev = y_local.device
+    stream = torch.cuda.current_stream(dev)
+    eng = CudaSlabEngine(alg, F, y_local.numel(), n_global, rank, world, tspan, stream.cuda_stream,
+                         device=dev.index or 0, **kw)
+    send = torch.zeros(XCHG_DOUBLES, dtype=torch.float64, device=dev)
+    recv = torch.zeros(world, XCHG_DOUBLES, dtype=torch.float64, device=dev)
+    tr = None
+    if trace:
+        tr = torch.zeros(trace_cap, 4, dtype=torch.float64, device=dev)
+        eng.set_trace(tr.data_ptr(), trace_cap)
+    if world > 1:
+        def exchange():
+            dist.all_gather_into_tensor(recv.view(-1), send, group=group)
+    else:
+        def exchange():
+            recv.view(-1).copy_(send)
+    y_local = y_local.contiguous()
+    eng.set_state(y_local.data_ptr())
+    ctl = integrate_slab(eng, send, recv, exchange, poll_every=poll_every)
+    out = torch.empty_like(y_local)
+    eng.get_state(out.data_ptr())
+    torch.cuda.current_stream(dev).synchronize()
+    eng.close()
+    if trace:
+        return out, ctl, tr[:min(ctl["trace_n"], trace_cap)]
+    return out, ctl

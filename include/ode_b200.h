@@ -207,6 +207,9 @@ int ode_b200_slab_create(const ode_b200_opts* opts, int64_t n_local, int64_t n_g
                          int32_t world, const double* params, double t0, double tend, void* stream,
                          ode_b200_slab** out);
 int ode_b200_slab_set_state(ode_b200_slab* s, const double* y_local_dev); /* [n_local] device */
+/* re-arm the session for another integration over [t0, tend] with the same options
+ * (the reference is stateless: a restart is a new call); follow with set_state */
+int ode_b200_slab_reset(ode_b200_slab* s, double t0, double tend);
 /* optional attempt trace on the device: rows (t, dt, err, accepted) */
 int ode_b200_slab_set_trace(ode_b200_slab* s, double* trace_dev, int64_t trace_cap);
 int ode_b200_slab_get_state(ode_b200_slab* s, double* y_local_dev);

@@ -99,6 +99,7 @@ def lib():
                                        C.c_double, C.c_void_p, C.POINTER(C.c_void_p)]
     L.ode_b200_slab_set_state.argtypes = [C.c_void_p, C.c_void_p]
     L.ode_b200_slab_get_state.argtypes = [C.c_void_p, C.c_void_p]
+    L.ode_b200_slab_reset.argtypes = [C.c_void_p, C.c_double, C.c_double]
     L.ode_b200_slab_set_trace.argtypes = [C.c_void_p, C.c_void_p, C.c_int64]
     L.ode_b200_slab_init_phase.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]
     L.ode_b200_slab_attempt.argtypes = [C.c_void_p, C.c_void_p]

@@ -113,14 +113,16 @@ __global__ void large_control_kernel(const ControlArgs C) {
   if (!refresh) return;
   // ghost cells of the new y and k1 from the neighbours' edges (periodic ring)
   const int par = ctl->par, H = C.H;
+  double* Yp = par ? C.Y[1] : C.Y[0];
+  double* Kp = par ? C.K[1] : C.K[0];
   const int lr = (C.rank + C.world - 1) % C.world, rr = (C.rank + 1) % C.world;
   const double* xl = C.xrecv + (long long)lr * XCHG + XS_EDGE;
   const double* xr = C.xrecv + (long long)rr * XCHG + XS_EDGE;
   for (int j = threadIdx.x; j < H; j += blockDim.x) {
-    C.Y[par][j] = xl[H + j];
-    C.Y[par][C.n + H + j] = xr[j];
-    C.K[par][j] = xl[3 * H + j];
-    C.K[par][C.n + H + j] = xr[2 * H + j];
+    Yp[j] = xl[H + j];
+    Yp[C.n + H + j] = xr[j];
+    Kp[j] = xl[3 * H + j];
+    Kp[C.n + H + j] = xr[2 * H + j];
   }
 }
 
@@ -382,6 +384,36 @@ int ode_b200_slab_create(const ode_b200_opts* o, int64_t n_local, int64_t n_glob
   ODEB200_CUDA(cudaMemcpyAsync(s->ctl, &s->host_ctl, sizeof(LargeCtl), cudaMemcpyHostToDevice, s->stream));
   ODEB200_CUDA(cudaStreamSynchronize(s->stream));
   *out = s;
+  return 0;
+}
+
+int ode_b200_slab_reset(ode_b200_slab* s, double t0, double tend) {
+  int rc = slab_check(s);
+  if (rc) return rc;
+  if (!(t0 == t0) || !(tend == tend)) return set_err(ODE_B200_E_INVALID, "NaN in tspan");
+  const double tdir = tend > t0 ? 1.0 : (tend < t0 ? -1.0 : 0.0);
+  if (tdir == 0.0) return set_err(ODE_B200_E_ZERO_SPAN, "Zero time span");
+  LargeCtl c = s->host_ctl;
+  const double initstep = c.initstep;
+  if (initstep != 0.0 && ((initstep > 0 ? 1.0 : -1.0) != tdir)) return set_err(ODE_B200_E_INITSTEP, "initstep has wrong sign.");
+  LargeCtl z;
+  memset(&z, 0, sizeof(z));
+  z.tdir = tdir;
+  z.tstart = t0;
+  z.tend = tend;
+  z.t = t0;
+  z.t_final = t0;
+  z.reltol = c.reltol;
+  z.abstol = c.abstol;
+  z.minstep = c.minstep;
+  z.maxstep = c.maxstep;
+  z.initstep = c.initstep;
+  z.max_steps = c.max_steps;
+  z.order = c.order;
+  z.trace_cap = s->trace ? s->trace_cap : 0;
+  s->host_ctl = z;
+  ODEB200_CUDA(cudaMemcpyAsync(s->ctl, &s->host_ctl, sizeof(LargeCtl), cudaMemcpyHostToDevice, s->stream));
+  ODEB200_CUDA(cudaStreamSynchronize(s->stream));  // host_ctl is reused by poll
   return 0;
 }
 

@@ -132,10 +132,11 @@ __global__ void __launch_bounds__(LARGE_THREADS) large_attempt_kernel(const Larg
   const int par = ctl->par;
   const double dt = ctl->dt, t = ctl->t;
   const double reltol = ctl->reltol, abstol = ctl->abstol;
-  const double* __restrict__ yA = A.Y[par];
-  const double* __restrict__ kA = A.K[par];
-  double* __restrict__ ytA = A.Y[par ^ 1];
-  double* __restrict__ knA = A.K[par ^ 1];
+  // (ternaries, not A.Y[par]: a dynamically indexed kernel-parameter array is copied to local memory)
+  const double* __restrict__ yA = par ? A.Y[1] : A.Y[0];
+  const double* __restrict__ kA = par ? A.K[1] : A.K[0];
+  double* __restrict__ ytA = par ? A.Y[0] : A.Y[1];
+  double* __restrict__ knA = par ? A.K[0] : A.K[1];
   const long long lim = A.n + 2 * H;
   const long long q0 = tile * VAL + (long long)tid * P;  // padded index of my first point
 
@@ -314,14 +315,28 @@ __global__ void __launch_bounds__(LARGE_THREADS) large_attempt_kernel(const Larg
   a2.hi = 0.0;
   a2.lo = 0.0;
   double m2 = 0.0, n2 = 0.0;
-  for (long long b = tid; b < A.tiles; b += T) {
-    const volatile double* pp = A.part + b * 4;
-    dm_dd o;
-    o.hi = pp[0];
-    o.lo = pp[1];
-    a2 = dd_add(a2, o);
-    m2 = normInf_step(m2, pp[2]);
-    n2 = fmax(n2, pp[3]);
+  for (long long b0 = tid; b0 < A.tiles; b0 += 4 * T) {  // 4 independent 32-byte L2 loads in flight per thread
+    double4 v[4];
+#pragma unroll
+    for (int u = 0; u < 4; u++) {
+      const long long b = b0 + (long long)u * T;
+      if (b < A.tiles) {
+        const double2 lo2 = __ldcg(reinterpret_cast<const double2*>(A.part + b * 4));
+        const double2 hi2 = __ldcg(reinterpret_cast<const double2*>(A.part + b * 4 + 2));
+        v[u] = make_double4(lo2.x, lo2.y, hi2.x, hi2.y);
+      } else {
+        v[u] = make_double4(0.0, 0.0, 0.0, 0.0);
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < 4; u++) {
+      dm_dd o;
+      o.hi = v[u].x;
+      o.lo = v[u].y;
+      a2 = dd_add(a2, o);
+      m2 = normInf_step(m2, v[u].z);
+      n2 = fmax(n2, v[u].w);
+    }
   }
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) {

@@ -77,6 +77,9 @@ class CudaSlabEngine:
         except _lib.OdeB200Error as e:
             _raise_like_reference(e)
 
+    def reset(self, t0, tend):
+        check(self.L.ode_b200_slab_reset(self.h, float(t0), float(tend)))
+
     def set_state(self, dev_ptr):
         check(self.L.ode_b200_slab_set_state(self.h, C.c_void_p(dev_ptr)))
 
@@ -142,7 +145,7 @@ def integrate_slab(engine, send, recv, exchange, poll_every=4, max_polls=10 ** 9
 
 
 def solve_large_distributed(alg, F, y_local, n_global, tspan, *, group=None, poll_every=4, trace=False,
-                            trace_cap=65536, **kw):
+                            trace_cap=65536, engine=None, keep_engine=False, **kw):
     """Domain-decomposed solve.  y_local: CUDA float64 torch tensor holding this rank's slab
     (shard_bounds(n_global, world, rank)); returns (y_local_final tensor, ctl dict[, trace tensor])."""
     import torch
@@ -152,8 +155,12 @@ def solve_large_distributed(alg, F, y_local, n_global, tspan, *, group=None, pol
     rank = dist.get_rank(group) if world > 1 else 0
     dev = y_local.device
     stream = torch.cuda.current_stream(dev)
-    eng = CudaSlabEngine(alg, F, y_local.numel(), n_global, rank, world, tspan, stream.cuda_stream,
-                         device=dev.index or 0, **kw)
+    if engine is None:
+        eng = CudaSlabEngine(alg, F, y_local.numel(), n_global, rank, world, tspan, stream.cuda_stream,
+                             device=dev.index or 0, **kw)
+    else:  # reuse the device buffers of an earlier call (same slab size, options and stream)
+        eng = engine
+        eng.reset(tspan[0], tspan[-1])
     send = torch.zeros(XCHG_DOUBLES, dtype=torch.float64, device=dev)
     recv = torch.zeros(world, XCHG_DOUBLES, dtype=torch.float64, device=dev)
     tr = None
@@ -172,7 +179,10 @@ def solve_large_distributed(alg, F, y_local, n_global, tspan, *, group=None, pol
     out = torch.empty_like(y_local)
     eng.get_state(out.data_ptr())
     torch.cuda.current_stream(dev).synchronize()
-    eng.close()
+    if keep_engine:
+        ctl["engine"] = eng
+    else:
+        eng.close()
     if trace:
         return out, ctl, tr[:min(ctl["trace_n"], trace_cap)]
     return out, ctl

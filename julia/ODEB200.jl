@@ -1,0 +1,149 @@
+# ODEB200.jl -- Julia host shim over libode_b200.so (include/ode_b200.h).
+#
+# Keeps ODE.jl's surface for the RK / ode23s hot path:
+#     tout, yout = ode45(F, y0, tspan; reltol, abstol, minstep, maxstep, initstep, points)
+#     sol = solve(prob, ode45(); reltol, abstol, saveat, ...)        (see solve_b200 below)
+# with `F` a registered DeviceRHS token instead of a closure (a Julia closure cannot run on the
+# device).  A DeviceRHS is also callable, `F(t, y)`, and evaluates the same expression in Julia,
+# so the unmodified ODE.jl solvers accept it for reference runs.
+#
+# NOTE: written against the C ABI but NOT executed in the build container (Julia is not
+# installed there, SURVEY.md F2).  The Python mirror ode.jl_b200/api.py is the tested twin; the
+# two files marshal the same structs in the same order.
+module ODEB200
+
+using Libdl
+
+const LIB = Ref{String}(get(ENV, "ODE_B200_LIB", joinpath(@__DIR__, "..", "ode.jl_b200", "libode_b200.so")))
+
+# ---- ids (include/ode_b200.h) -------------------------------------------------------------------
+const METHODS = Dict(:ode1=>0, :ode2_midpoint=>1, :ode2_heun=>2, :ode4=>3, :ode21=>4, :ode23=>5,
+                     :ode45_fe=>6, :ode45_dp=>7, :ode45=>7, :ode78=>8, :ode23s=>9)
+const RHS = Dict(:linear=>0, :const=>1, :timelin=>2, :rotation=>3, :lorenz=>4, :vdp=>5,
+                 :robertson=>6, :kepler=>7, :reaction_diffusion=>8)
+const POINTS = Dict(:all=>0, :specified=>1, :final=>2)
+
+struct DeviceRHS{Name}
+    params::Vector{Float64}
+end
+DeviceRHS(name::Symbol, params...) = DeviceRHS{name}(Float64[params...])
+rhs_id(::DeviceRHS{N}) where {N} = RHS[N]
+
+# host evaluation: the same expressions, same association, as csrc/rhs.cuh
+(f::DeviceRHS{:linear})(t, y) = f.params[1]*y
+(f::DeviceRHS{:const})(t, y) = f.params[1]
+(f::DeviceRHS{:timelin})(t, y) = f.params[1]*t
+(f::DeviceRHS{:rotation})(t, y) = [-y[2]; y[1]]
+(f::DeviceRHS{:lorenz})(t, y) = (p = f.params; [p[1]*(y[2]-y[1]); y[1]*(p[2]-y[3])-y[2]; y[1]*y[2]-p[3]*y[3]])
+(f::DeviceRHS{:vdp})(t, y) = [y[2]; f.params[1]*((1.0-y[1]*y[1])*y[2]) - y[1]]
+function (f::DeviceRHS{:robertson})(t, y)
+    p = f.params
+    d1 = -p[1]*y[1] + p[3]*y[2]*y[3]
+    d3 = p[2]*y[2]*y[2]
+    [d1; -d1 - d3; d3]
+end
+function (f::DeviceRHS{:kepler})(t, y)
+    r2 = y[1]*y[1] + y[2]*y[2]; r3 = r2*sqrt(r2)
+    [y[3]; y[4]; -y[1]/r3; -y[2]/r3]
+end
+
+# ---- ode_b200_opts (field order and types as in the header) -----------------------------------------
+struct Opts
+    method::Int32; rhs::Int32; dof::Int32; n_params::Int32
+    params_stride::Int32; points::Int32; jacobian::Int32; device::Int32
+    max_steps::Int64
+    reltol::Float64; abstol::Float64; minstep::Float64; maxstep::Float64; initstep::Float64
+    mathmode::Int32
+    reserved::NTuple{7,Int32}
+end
+
+last_error() = unsafe_string(ccall((:ode_b200_last_error, LIB[]), Cstring, ()))
+
+function check(rc::Integer)
+    rc == 0 && return
+    msg = last_error()
+    rc == -2 && error("Zero time span")                 # src/ODE.jl:88
+    rc == -3 && error("initstep has wrong sign.")       # src/runge_kutta.jl:294
+    rc == -5 && error("Can only use this solver with an adaptive RK Butcher table")  # :249
+    error("libode_b200 error $rc: $msg")
+end
+
+function _solve(method::Symbol, F::DeviceRHS, y0, tspan;
+                reltol = 1.0e-5, abstol = 1.0e-8,
+                minstep = abs(tspan[end] - tspan[1])/1e18,     # src/runge_kutta.jl:235
+                maxstep = abs(tspan[end] - tspan[1])/2.5,      # :236
+                initstep = 0.0, points = :all, device = 0)
+    haskey(POINTS, points) || error("Unrecognized option points==$points")   # :289
+    scalar = !(y0 isa AbstractVector)
+    y = scalar ? Float64[y0] : convert(Vector{Float64}, y0)
+    ts = convert(Vector{Float64}, collect(tspan))
+    o = Ref(Opts(METHODS[method], rhs_id(F), length(y), length(F.params), 0, POINTS[points], 0, device, 0,
+                 reltol, abstol, minstep, maxstep, initstep, 0, ntuple(_ -> Int32(0), 7)))
+    h = Ref{Ptr{Cvoid}}(C_NULL)
+    GC.@preserve y ts F begin
+        check(ccall((:ode_b200_solve_single, LIB[]), Cint,
+                    (Ref{Opts}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Int32, Ref{Ptr{Cvoid}}),
+                    o, y, F.params, ts, length(ts), h))
+    end
+    n = ccall((:ode_b200_result_len, LIB[]), Int64, (Ptr{Cvoid},), h[])
+    tout = Vector{Float64}(undef, n)
+    yflat = Matrix{Float64}(undef, length(y), n)       # column = one output state (row-major [len][dof] in C)
+    check(ccall((:ode_b200_result_copy, LIB[]), Cint, (Ptr{Cvoid}, Ptr{Float64}, Ptr{Float64}), h[], tout, yflat))
+    status = ccall((:ode_b200_result_status, LIB[]), Int32, (Ptr{Cvoid},), h[])
+    ccall((:ode_b200_result_free, LIB[]), Cvoid, (Ptr{Cvoid},), h[])
+    status == 1 && method != :ode23s && println("Warning: dt < minstep.  Stopping.")   # :359
+    yout = scalar ? vec(yflat) : [yflat[:, i] for i in 1:n]
+    return tout, yout
+end
+
+for name in (:ode1, :ode2_midpoint, :ode2_heun, :ode4, :ode21, :ode23, :ode45_fe, :ode45_dp, :ode45, :ode78, :ode23s)
+    @eval $name(F::DeviceRHS, y0, tspan; kw...) = _solve($(QuoteNode(name)), F, y0, tspan; kw...)
+    @eval $name(F, y0, tspan; kw...) =
+        error("libode_b200 takes a registered DeviceRHS; a Julia closure cannot run on the device (no CPU fallback)")
+    @eval export $name
+end
+export DeviceRHS
+
+# ---- ensembles: n independent odeXX calls in one launch --------------------------------------------
+struct EnsembleIO
+    n_traj::Int64; y0::Ptr{Float64}; params::Ptr{Float64}; tspan::Ptr{Float64}; n_tspan::Int32; pad0::Int32
+    t_final::Ptr{Float64}; y_final::Ptr{Float64}; n_accept::Ptr{Int32}; n_reject::Ptr{Int32}; n_rhs::Ptr{Int32}
+    status::Ptr{Int32}; pts_t::Ptr{Float64}; pts_y::Ptr{Float64}; pts_n::Ptr{Int32}; pts_cap::Int64
+    trace_traj::Int64; trace::Ptr{Float64}; trace_cap::Int64; trace_n::Ptr{Int64}
+end
+
+"""solve_ensemble(:ode45, F, Y0, tspan; kw...) with Y0 a dof x n_traj matrix (one trajectory per column)."""
+function solve_ensemble(method::Symbol, F::DeviceRHS, Y0::Matrix{Float64}, tspan;
+                        reltol = 1.0e-5, abstol = 1.0e-8, minstep = abs(tspan[end]-tspan[1])/1e18,
+                        maxstep = abs(tspan[end]-tspan[1])/2.5, initstep = 0.0, device = 0)
+    dof, n = size(Y0)
+    ts = convert(Vector{Float64}, collect(tspan))
+    tf = Vector{Float64}(undef, n); yf = Matrix{Float64}(undef, dof, n)
+    na = Vector{Int32}(undef, n); nr = similar(na); nf = similar(na); st = similar(na)
+    o = Ref(Opts(METHODS[method], rhs_id(F), dof, length(F.params), 0, POINTS[:final], 0, device, 0,
+                 reltol, abstol, minstep, maxstep, initstep, 0, ntuple(_ -> Int32(0), 7)))
+    GC.@preserve Y0 ts F tf yf na nr nf st begin
+        io = Ref(EnsembleIO(n, pointer(Y0), pointer(F.params), pointer(ts), length(ts), 0,
+                            pointer(tf), pointer(yf), pointer(na), pointer(nr), pointer(nf), pointer(st),
+                            C_NULL, C_NULL, C_NULL, 0, -1, C_NULL, 0, C_NULL))
+        check(ccall((:ode_b200_solve_ensemble, LIB[]), Cint, (Ref{Opts}, Ref{EnsembleIO}), o, io))
+    end
+    return (t_final = tf, y_final = yf, n_accept = na, n_reject = nr, n_rhs = nf, status = st)
+end
+
+# ---- common interface: what src/common.jl:1-123 does, minus DiffEqBase types --------------------------
+"""solve_b200(f::DeviceRHS, u0, tspan, alg::Symbol; ...) mirrors ODE.solve's keyword mapping
+(dtmin = span/1e-9 (sic, src/common.jl:13), dtmax = span/2.5, saveat -> Ts, save_everystep -> points)."""
+function solve_b200(f::DeviceRHS, u0, tspan::Tuple, alg::Symbol; saveat = Float64[], reltol = 1e-5, abstol = 1e-8,
+                    save_everystep = isempty(saveat), dtmin = abs(tspan[2]-tspan[1])/1e-9,
+                    dtmax = abs(tspan[2]-tspan[1])/2.5, dt = 0.0)
+    sv = saveat isa Number ? collect(tspan[1]+saveat:saveat:tspan[2]) : collect(Float64, saveat)
+    !isempty(sv) && sv[end] == tspan[2] && pop!(sv)
+    Ts = (!isempty(sv) && sv[1] == tspan[1]) ? unique([sv; tspan[2]]) : unique([tspan[1]; sv; tspan[2]])
+    points = save_everystep ? :all : :specified
+    ts, us = _solve(alg, f, u0 isa AbstractArray ? vec(u0) : u0, Ts; abstol = abstol, reltol = reltol,
+                    maxstep = dtmax, minstep = dtmin, initstep = dt, points = points)
+    return (t = ts, u = us, retcode = :Succss)   # src/common.jl:122
+end
+
+end # module

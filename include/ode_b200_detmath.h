@@ -138,10 +138,16 @@ DM_HD dm_dd dm_log_dd(double x) {
   return res;
 }
 
-/* exp(ehi + elo), |ehi| < ~745, |elo| << |ehi|. */
+/* exp(ehi + elo), |elo| << |ehi|.  The common case |ehi| < 700 is detected with one
+ * integer compare on the high word and scales by a normal power of two. */
 DM_HD double dm_exp_dd(double ehi, double elo) {
-  if (ehi > 709.782712893384) return (double)INFINITY;
-  if (ehi < -745.2) return 0.0;
+  const uint32_t hw = (uint32_t)(dm_bits(ehi) >> 32) & 0x7fffffffu;
+  const int fast = hw < 0x4085E000u; /* |ehi| < 700 */
+  if (!fast) {
+    if (ehi != ehi) return ehi;
+    if (ehi > 709.782712893384) return (double)INFINITY;
+    if (ehi < -745.2) return 0.0;
+  }
   double zz = ehi * DM_INVLN2N;
   const double SHIFT = 6755399441055744.0; /* 1.5 * 2^52 */
   double kd = (zz + SHIFT) - SHIFT;        /* round to nearest integer */
@@ -167,7 +173,7 @@ DM_HD double dm_exp_dd(double ehi, double elo) {
   double e = (th - s) + ph; /* fast two-sum, |th| >= |ph| */
   double tail = (e + pl) + dm_fma(th, rest, dm_fma(tl, q, tl));
   double v = s + tail; /* in [1, 2) roughly; scale by 2^e2 */
-  if (e2 >= -1021 && e2 <= 1022) {
+  if (fast || (e2 >= -1021 && e2 <= 1022)) {
     return v * dm_from_bits((uint64_t)(e2 + 1023) << 52);
   }
   /* out-of-range scale: two exact-power-of-two multiplies (deterministic) */
@@ -183,16 +189,24 @@ DM_HD double dm_exp_dd(double ehi, double elo) {
 }
 
 /* x^y for x >= 0.  Negative x returns NaN (Julia raises DomainError there;
- * the solvers only ever pass norms and ratios of norms). */
+ * the solvers only ever pass norms and ratios of norms).  Positive normal
+ * finite x with finite y -- every controller call -- is recognised with integer
+ * compares only and goes straight to the arithmetic. */
 DM_HD double dm_pow(double x, double y) {
-  if (x != x || y != y) return x + y; /* NaN */
-  if (y == 0.0) return 1.0;
-  if (x < 0.0) return (double)NAN;
-  if (x == 0.0) return y > 0.0 ? 0.0 : (double)INFINITY;
-  if (x == (double)INFINITY) return y > 0.0 ? (double)INFINITY : 0.0;
-  if (x == 1.0) return 1.0;
-  if (y == (double)INFINITY) return x > 1.0 ? (double)INFINITY : 0.0;
-  if (y == -(double)INFINITY) return x > 1.0 ? 0.0 : (double)INFINITY;
+  const uint64_t ix = dm_bits(x);
+  const uint64_t iy = dm_bits(y) & 0x7fffffffffffffffULL;
+  const int xnorm = (ix - 0x0010000000000000ULL) < 0x7fe0000000000000ULL; /* +normal, finite */
+  const int yfin = iy < 0x7ff0000000000000ULL;
+  if (!(xnorm && yfin)) {
+    if (x != x || y != y) return x + y; /* NaN */
+    if (y == 0.0) return 1.0;
+    if (x < 0.0) return (double)NAN;
+    if (x == 0.0) return y > 0.0 ? 0.0 : (double)INFINITY;
+    if (x == (double)INFINITY) return y > 0.0 ? (double)INFINITY : 0.0;
+    if (y == (double)INFINITY) return x == 1.0 ? 1.0 : (x > 1.0 ? (double)INFINITY : 0.0);
+    if (y == -(double)INFINITY) return x == 1.0 ? 1.0 : (x > 1.0 ? 0.0 : (double)INFINITY);
+    /* positive subnormal x, finite y: falls through */
+  }
   dm_dd l = dm_log_dd(x);
   double ehi = y * l.hi;
   double elo = dm_fma(y, l.lo, dm_fma(y, l.hi, -ehi));

@@ -144,6 +144,9 @@ static int validate(const ode_b200_opts* o, const ode_b200_ensemble_io* io, doub
   if (o->points != ODE_B200_POINTS_ALL && o->points != ODE_B200_POINTS_SPECIFIED && o->points != ODE_B200_POINTS_FINAL)
     return set_err(ODE_B200_E_POINTS, "Unrecognized option points==%d", o->points);  // src/runge_kutta.jl:289
   if (o->jacobian != 0) return set_err(ODE_B200_E_UNSUPPORTED, "analytic Jacobian functors are not registered yet");
+  if (!(o->reltol == o->reltol) || !(o->abstol == o->abstol) || !(o->minstep == o->minstep) ||
+      !(o->maxstep == o->maxstep) || !(o->initstep == o->initstep))
+    return set_err(ODE_B200_E_INVALID, "NaN in reltol/abstol/minstep/maxstep/initstep");
   const bool fixed = o->method <= ODE_B200_M_RK4;
   if (!fixed) {
     double tdir = tend > t0 ? 1.0 : (tend < t0 ? -1.0 : 0.0);

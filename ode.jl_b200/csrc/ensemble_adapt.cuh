@@ -43,12 +43,16 @@ __device__ __forceinline__ void hermite_point(double* out, double tq, double t, 
   }
 }
 
-#ifndef ODEB200_ADAPT_MIN_BLOCKS
-#define ODEB200_ADAPT_MIN_BLOCKS 1
-#endif
+// Resident CTAs per SM asked of ptxas.  Measured on Lorenz/dopri5 (profiles/ensemble_lorenz_r1.md):
+// 5 CTAs/SM (<= 102 registers, no spill) beats both the unconstrained allocation (119 registers,
+// 4 CTAs/SM) and tighter bounds that spill.  Larger state x stage products are left unconstrained.
+template <class Tab, class Rhs>
+constexpr int adapt_min_blocks() {
+  return (Rhs::DOF <= 3 && Rhs::DOF * Tab::S <= 21) ? 5 : 1;
+}
 
 template <class Tab, class Rhs, int MODE>
-__global__ void __launch_bounds__(ENS_BLOCK, ODEB200_ADAPT_MIN_BLOCKS) ens_adapt_kernel(const EnsembleArgs A) {
+__global__ void __launch_bounds__(ENS_BLOCK, adapt_min_blocks<Tab, Rhs>()) ens_adapt_kernel(const EnsembleArgs A) {
   constexpr int D = Rhs::DOF, S = Tab::S, NPA = RhsNP<Rhs>::value;
   constexpr bool FSAL = Tab::fsal();
   constexpr double EXPO = 1.0 / (double)(Tab::ORDER + 1);  // T(1/(order+1)) :436
@@ -57,6 +61,7 @@ __global__ void __launch_bounds__(ENS_BLOCK, ODEB200_ADAPT_MIN_BLOCKS) ens_adapt
   const double tstart = A.tspan[0];
   const double tend = A.tspan[A.n_tspan - 1];
   const double tdir = jl_sign(tend - tstart);  // src/ODE.jl:87 (zero span rejected on the host)
+  const bool fwd = tdir > 0.0;                  // x*tdir == (fwd ? x : -x) exactly
   const int nfixed = A.n_tspan;
 
   long long idx = -1;
@@ -195,12 +200,14 @@ __global__ void __launch_bounds__(ENS_BLOCK, ODEB200_ADAPT_MIN_BLOCKS) ens_adapt
       timeout = 5;
     } else {
       err = norm2_small<D>(yerr);  // :435
-      double nd = jl_min(A.maxstep, (tdir * dt) * jl_max(0.2, 0.8 * dm_pow(1.0 / err, EXPO)));  // :436
-      if (timeout > 0) {  // :437-440
-        nd = jl_min(nd, dt);
-        timeout -= 1;
-      }
-      newdt = tdir * nd;  // :441
+      // :436  min(maxstep, tdir*dt*max(facmin, fac*(1/err)^(1/(order+1)))); tdir = +-1 is applied as a
+      // sign (exact), min/max keep Julia's NaN propagation (maxstep, facmin and dt are never NaN here)
+      const double g = 0.8 * dm_pow(1.0 / err, EXPO);
+      double nd = jl_min_nn(A.maxstep, (fwd ? dt : -dt) * jl_max_nn(0.2, g));
+      const double ndt = jl_min_nn(dt, nd);  // :437-440 (signed dt), branch-free
+      nd = (timeout > 0) ? ndt : nd;
+      timeout = (timeout > 0) ? timeout - 1 : 0;
+      newdt = fwd ? nd : -nd;  // :441
     }
     const bool accept = err <= 1.0;  // :312
     if (MODE == 1 && idx == A.trace_traj) {
@@ -261,7 +268,8 @@ __global__ void __launch_bounds__(ENS_BLOCK, ODEB200_ADAPT_MIN_BLOCKS) ens_adapt
         for (int d = 0; d < D; d++) y[d] = ytrial[d];  // :347
         t += dt;                                       // :350
         dt = newdt;                                    // :351
-        if (tdir * (t + dt + dt / 100) >= tdir * tend) {  // :354-357
+        const double tl = t + dt + dt / 100;  // :354-357, tdir*a >= tdir*b as a signed compare
+        if (fwd ? (tl >= tend) : (tl <= tend)) {
           dt = tend - t;
           islast = true;
         }

@@ -37,14 +37,13 @@ struct LuReg {
       }
       piv[j] = pr;
 #pragma unroll
-      for (int i = j + 1; i < D; i++) {
-        if (pr == i) {
+      for (int i = j + 1; i < D; i++) {  // row exchange as selects (keeps the rows in registers)
+        const bool sw = (pr == i);
 #pragma unroll
-          for (int c = 0; c < D; c++) {
-            double tmp = a[j][c];
-            a[j][c] = a[i][c];
-            a[i][c] = tmp;
-          }
+        for (int c = 0; c < D; c++) {
+          const double aj = a[j][c], ai = a[i][c];
+          a[j][c] = sw ? ai : aj;
+          a[i][c] = sw ? aj : ai;
         }
       }
       if (a[j][j] == 0.0) {
@@ -66,11 +65,10 @@ struct LuReg {
     for (int j = 0; j < D; j++) {
 #pragma unroll
       for (int i = j + 1; i < D; i++) {
-        if (piv[j] == i) {
-          double tmp = b[j];
-          b[j] = b[i];
-          b[i] = tmp;
-        }
+        const bool sw = (piv[j] == i);
+        const double bj = b[j], bi = b[i];
+        b[j] = sw ? bi : bj;
+        b[i] = sw ? bj : bi;
       }
     }
 #pragma unroll

@@ -250,6 +250,17 @@ struct MethodInfo {
   AttemptKernel kernel;
   int H, VAL, order, S, fsal;
 };
+static int persistent_grid(AttemptKernel k, int device, long long tiles) {
+  int sms = 0, per_sm = 0;
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device);
+  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k, LARGE_THREADS, 0) != cudaSuccess || per_sm < 1) {
+    cudaGetLastError();
+    per_sm = 1;
+  }
+  long long g = (long long)sms * per_sm;  // one wave of resident CTAs, each loops over its tiles
+  if (g > tiles) g = tiles;
+  return (int)(g < 1 ? 1 : g);
+}
 template <class Tab>
 static MethodInfo method_info() {
   using Geo = LargeGeom<Tab, RhsReactionDiffusion>;
@@ -280,6 +291,7 @@ using namespace odeb200;
 struct ode_b200_slab {
   int device = 0, rank = 0, world = 1;
   long long n = 0, n_global = 0, tiles = 0;
+  int grid = 1;
   MethodInfo mi;
   cudaStream_t stream = nullptr;
   double *Y[2] = {nullptr, nullptr}, *K[2] = {nullptr, nullptr};
@@ -343,6 +355,7 @@ int ode_b200_slab_create(const ode_b200_opts* o, int64_t n_local, int64_t n_glob
   s->mi = mi;
   s->stream = (cudaStream_t)stream;
   s->tiles = (n_local + mi.VAL - 1) / mi.VAL;
+  s->grid = persistent_grid(mi.kernel, o->device, s->tiles);
   s->p0 = params[0];
   s->p1 = params[1];
   const size_t padded = (size_t)(n_local + 2 * mi.H + 8) * sizeof(double);
@@ -355,7 +368,7 @@ int ode_b200_slab_create(const ode_b200_opts* o, int64_t n_local, int64_t n_glob
     ok = ok && cudaMalloc(&s->K[i], padded) == cudaSuccess;
   }
   ok = ok && cudaMalloc(&s->ctl, sizeof(LargeCtl)) == cudaSuccess;
-  ok = ok && cudaMalloc(&s->part, (size_t)s->tiles * 4 * sizeof(double)) == cudaSuccess;
+  ok = ok && cudaMalloc(&s->part, (size_t)s->grid * 4 * sizeof(double)) == cudaSuccess;
   ok = ok && cudaMalloc(&s->ipart, (size_t)s->init_blocks * 2 * sizeof(double)) == cudaSuccess;
   if (!ok) {
     cudaGetLastError();
@@ -498,7 +511,7 @@ int ode_b200_slab_attempt(ode_b200_slab* s, double* xsend) {
   A.tiles = s->tiles;
   A.p0 = s->p0;
   A.p1 = s->p1;
-  s->mi.kernel<<<(unsigned)s->tiles, LARGE_THREADS, 0, s->stream>>>(A);
+  s->mi.kernel<<<(unsigned)s->grid, LARGE_THREADS, 0, s->stream>>>(A);
   note_launch();
   ODEB200_CUDA(cudaGetLastError());
   return 0;

@@ -10,9 +10,12 @@
 // stage (33 array passes = 264 B per point per attempt if
 // each stage were its own kernel).  Here all S stages of an attempt run inside
 // one CTA-resident tile:
-//   * a CTA owns W = THREADS*P consecutive points, H ghost points on either side
+//   * a tile is W = THREADS*P consecutive points, H ghost points on either side
 //     of its VAL = W - 2H valid points; each thread keeps its P points of y, every
 //     dt*k_s and both b-row accumulators in registers for the whole attempt;
+//     CTAs are persistent (grid = SMs x resident CTAs) and request the next
+//     tile's y, k1 before computing the current one, so the tile load latency
+//     hides behind a whole attempt of FP64 work;
 //   * a stage needs ytmp at i-1, i, i+1: inside a thread these are registers, the
 //     two chunk-edge values cross threads through a double-buffered shared-memory
 //     line (one __syncthreads per stage); the tile edge loses one point of
@@ -22,9 +25,10 @@
 //     = 4 passes = 32 B per point (8.25x less than stage-per-kernel), with
 //     256-bit aligned vector loads/stores; the kernel becomes FP64-issue bound.
 //   * the scaled error is squared and accumulated in double-double (error-free
-//     products and sums), reduced by warp shuffles, then shared memory, then by
-//     the last CTA to finish (fixed order), so the 2-norm does not depend on the
-//     launch geometry or on the number of GPUs.
+//     products and sums) per thread across all tiles of its CTA, reduced once per
+//     CTA by warp shuffles and shared memory, then by the last CTA to finish
+//     (fixed order); the sum is exact to ~2^-78, so the rounded 2-norm does not
+//     depend on the launch geometry or on the number of GPUs.
 //   * accept/reject, the new dt (deterministic pow) and the y/ytrial, k1/k_next
 //     pointer swap happen in a one-block control kernel on the device; the host
 //     only polls a done flag.
@@ -40,8 +44,14 @@
 
 namespace odeb200 {
 
-constexpr int LARGE_THREADS = 256;
-constexpr int LARGE_P = 4;
+#ifndef ODEB200_LARGE_THREADS
+#define ODEB200_LARGE_THREADS 128
+#endif
+#ifndef ODEB200_LARGE_P
+#define ODEB200_LARGE_P 4
+#endif
+constexpr int LARGE_THREADS = ODEB200_LARGE_THREADS;  // threads per CTA
+constexpr int LARGE_P = ODEB200_LARGE_P;              // consecutive points per thread (multiple of 4)
 constexpr int XCHG = ODE_B200_XCHG_DOUBLES;
 // xchg slots
 constexpr int XS_HI = 0, XS_LO = 1, XS_MAX = 2, XS_NAN = 3, XS_AUX0 = 4, XS_AUX1 = 5, XS_EDGE = 8;
@@ -88,17 +98,20 @@ __device__ __forceinline__ dm_dd dd_add_sq(dm_dd acc, double e) {  // acc + e*e,
   return r;
 }
 
-template <int H>
-__device__ __forceinline__ void load4(const double* a, long long q, long long lim, double (&v)[4]) {
-  if (q + 4 <= lim) {
-    const double4 x = *reinterpret_cast<const double4*>(a + q);
-    v[0] = x.x;
-    v[1] = x.y;
-    v[2] = x.z;
-    v[3] = x.w;
+template <int P>
+__device__ __forceinline__ void load_chunk(const double* a, long long q, long long lim, double (&v)[P]) {
+  if (q + P <= lim) {
+#pragma unroll
+    for (int c = 0; c < P / 4; c++) {
+      const double4 x = *reinterpret_cast<const double4*>(a + q + 4 * c);
+      v[4 * c + 0] = x.x;
+      v[4 * c + 1] = x.y;
+      v[4 * c + 2] = x.z;
+      v[4 * c + 3] = x.w;
+    }
   } else {
 #pragma unroll
-    for (int p = 0; p < 4; p++) v[p] = (q + p < lim) ? a[q + p] : 0.0;
+    for (int p = 0; p < P; p++) v[p] = (q + p < lim) ? a[q + p] : 0.0;
   }
 }
 
@@ -119,7 +132,7 @@ __global__ void __launch_bounds__(LARGE_THREADS) large_attempt_kernel(const Larg
   constexpr int S = Geo::S, H = Geo::H, VAL = Geo::VAL, P = LARGE_P, T = LARGE_THREADS;
   constexpr bool FSAL = Geo::FSAL;
   constexpr int NK = S > 1 ? S - 1 : 1;
-  static_assert(P == 4, "vector width");
+  static_assert(P % 4 == 0, "256-bit vector accesses");
 
   __shared__ double eL[2][T], eR[2][T];
   __shared__ double red[T / 32][4];
@@ -128,9 +141,8 @@ __global__ void __launch_bounds__(LARGE_THREADS) large_attempt_kernel(const Larg
   LargeCtl* ctl = A.ctl;
   if (ctl->done) return;
   const int tid = threadIdx.x;
-  const long long tile = blockIdx.x;
   const int par = ctl->par;
-  const double dt = ctl->dt, t = ctl->t;
+  const double dt = ctl->dt;
   const double reltol = ctl->reltol, abstol = ctl->abstol;
   // (ternaries, not A.Y[par]: a dynamically indexed kernel-parameter array is copied to local memory)
   const double* __restrict__ yA = par ? A.Y[1] : A.Y[0];
@@ -138,136 +150,164 @@ __global__ void __launch_bounds__(LARGE_THREADS) large_attempt_kernel(const Larg
   double* __restrict__ ytA = par ? A.Y[0] : A.Y[1];
   double* __restrict__ knA = par ? A.K[0] : A.K[1];
   const long long lim = A.n + 2 * H;
-  const long long q0 = tile * VAL + (long long)tid * P;  // padded index of my first point
+  const int off0 = tid * P;
 
-  double y[P], k1[P];
-  load4<H>(yA, q0, lim, y);
-  load4<H>(kA, q0, lim, k1);
-
-  double ytrial[P], yerr[P], dtk[NK][P], klast[P];
-  constexpr double b10 = Tab::b(0, 0), b20 = Tab::b(1, 0);
-#pragma unroll
-  for (int p = 0; p < P; p++) {
-    ytrial[p] = (b10 != 0.0) ? b10 * k1[p] : 0.0;
-    yerr[p] = (b20 != 0.0) ? b20 * k1[p] : 0.0;
-    dtk[0][p] = dt * k1[p];
-    klast[p] = k1[p];
-  }
-  (void)t;  // the registered stencil RHS is autonomous; t + c*dt is not needed
-
-  static_for<S - 1>([&](auto I) {
-    constexpr int s = decltype(I)::value + 1;
-    constexpr int buf = s & 1;
-    double ytmp[P], ks[P];
-#pragma unroll
-    for (int p = 0; p < P; p++) ytmp[p] = y[p];
-    static_for<s>([&](auto J) {
-      constexpr int ss = decltype(J)::value;
-      constexpr double a = Tab::a(s, ss);
-      if constexpr (a != 0.0) {
-#pragma unroll
-        for (int p = 0; p < P; p++) ytmp[p] = ytmp[p] + dtk[ss][p] * a;  // (dt*k)*a :454
-      }
-    });
-    eL[buf][tid] = ytmp[0];
-    eR[buf][tid] = ytmp[P - 1];
-    __syncthreads();
-    const double left = (tid > 0) ? eR[buf][tid - 1] : ytmp[0];
-    const double right = (tid < T - 1) ? eL[buf][tid + 1] : ytmp[P - 1];
-#pragma unroll
-    for (int p = 0; p < P; p++) {
-      const double um = (p == 0) ? left : ytmp[p - 1];
-      const double up = (p == P - 1) ? right : ytmp[p + 1];
-      ks[p] = Rhs::point(um, ytmp[p], up, A.p0, A.p1);
-    }
-    constexpr double b1 = Tab::b(0, s), b2 = Tab::b(1, s);
-#pragma unroll
-    for (int p = 0; p < P; p++) {
-      if constexpr (b1 != 0.0) ytrial[p] = ytrial[p] + b1 * ks[p];
-      if constexpr (b2 != 0.0) yerr[p] = yerr[p] + b2 * ks[p];
-      if constexpr (s < S - 1) dtk[s][p] = dt * ks[p];
-      if constexpr (s == S - 1) klast[p] = ks[p];
-    }
-  });
-#pragma unroll
-  for (int p = 0; p < P; p++) {  // :395-398
-    yerr[p] = dt * (ytrial[p] - yerr[p]);
-    ytrial[p] = y[p] + dt * ytrial[p];
-  }
-  double knext[P];
-  if constexpr (FSAL) {
-#pragma unroll
-    for (int p = 0; p < P; p++) knext[p] = klast[p];
-  } else {  // f1 = F(t+dt, ytrial) :320, fused as one more stencil sweep
-    constexpr int buf = S & 1;
-    eL[buf][tid] = ytrial[0];
-    eR[buf][tid] = ytrial[P - 1];
-    __syncthreads();
-    const double left = (tid > 0) ? eR[buf][tid - 1] : ytrial[0];
-    const double right = (tid < T - 1) ? eL[buf][tid + 1] : ytrial[P - 1];
-#pragma unroll
-    for (int p = 0; p < P; p++) {
-      const double um = (p == 0) ? left : ytrial[p - 1];
-      const double up = (p == P - 1) ? right : ytrial[p + 1];
-      knext[p] = Rhs::point(um, ytrial[p], up, A.p0, A.p1);
-    }
-  }
-
-  // ---- scaled error (stepsize_hw92! :430-435), valid points only -------------
+  // running per-thread error partials over all tiles of this (persistent) CTA
   dm_dd acc;
   acc.hi = 0.0;
   acc.lo = 0.0;
   double mx = 0.0;
   bool anynan = false;
-  const int off0 = tid * P;
-  bool allvalid = true;
-#pragma unroll
-  for (int p = 0; p < P; p++) {
-    const int off = off0 + p;
-    const long long li = q0 + p - H;  // interior index
-    const bool valid = (off >= H) && (off < H + VAL) && (li < A.n);
-    allvalid = allvalid && valid;
-    if (valid) {
-      anynan = anynan || (ytrial[p] != ytrial[p]);
-      const double ay = fabs(y[p]), at = fabs(ytrial[p]);
-      const double e = yerr[p] / (abstol + ((ay > at) ? ay : at) * reltol);  // :433
-      acc = dd_add_sq(acc, e);
-      mx = normInf_step(mx, fabs(e));
-    }
+  int xc = 0;  // exchange counter: shared-memory line parity alternates across stages AND tiles
+
+  // software prefetch: the next tile's y, k1 are requested before the current tile is computed
+  double yN[P], kN[P];
+  long long tile = blockIdx.x;
+  if (tile < A.tiles) {
+    load_chunk<P>(yA, tile * VAL + off0, lim, yN);
+    load_chunk<P>(kA, tile * VAL + off0, lim, kN);
   }
-  // stores
-  if (allvalid) {
-    *reinterpret_cast<double4*>(ytA + q0) = make_double4(ytrial[0], ytrial[1], ytrial[2], ytrial[3]);
-    *reinterpret_cast<double4*>(knA + q0) = make_double4(knext[0], knext[1], knext[2], knext[3]);
-  } else {
+  for (; tile < A.tiles; tile += gridDim.x) {
+    const long long q0 = tile * VAL + off0;  // padded index of my first point
+    double y[P], k1[P];
+#pragma unroll
+    for (int p = 0; p < P; p++) {
+      y[p] = yN[p];
+      k1[p] = kN[p];
+    }
+    const long long nxt = tile + gridDim.x;
+    if (nxt < A.tiles) {
+      load_chunk<P>(yA, nxt * VAL + off0, lim, yN);
+      load_chunk<P>(kA, nxt * VAL + off0, lim, kN);
+    }
+
+    double ytrial[P], yerr[P], dtk[NK][P], klast[P];
+    constexpr double b10 = Tab::b(0, 0), b20 = Tab::b(1, 0);
+#pragma unroll
+    for (int p = 0; p < P; p++) {
+      ytrial[p] = (b10 != 0.0) ? b10 * k1[p] : 0.0;
+      yerr[p] = (b20 != 0.0) ? b20 * k1[p] : 0.0;
+      dtk[0][p] = dt * k1[p];
+      klast[p] = k1[p];
+    }
+    // (the registered stencil RHS is autonomous; t + c*dt is not needed)
+    static_for<S - 1>([&](auto I) {
+      constexpr int s = decltype(I)::value + 1;
+      double ytmp[P], ks[P];
+#pragma unroll
+      for (int p = 0; p < P; p++) ytmp[p] = y[p];
+      static_for<s>([&](auto J) {
+        constexpr int ss = decltype(J)::value;
+        constexpr double a = Tab::a(s, ss);
+        if constexpr (a != 0.0) {
+#pragma unroll
+          for (int p = 0; p < P; p++) ytmp[p] = ytmp[p] + dtk[ss][p] * a;  // (dt*k)*a :454
+        }
+      });
+      const int buf = xc & 1;
+      xc++;
+      eL[buf][tid] = ytmp[0];
+      eR[buf][tid] = ytmp[P - 1];
+      __syncthreads();
+      const double left = (tid > 0) ? eR[buf][tid - 1] : ytmp[0];
+      const double right = (tid < T - 1) ? eL[buf][tid + 1] : ytmp[P - 1];
+#pragma unroll
+      for (int p = 0; p < P; p++) {
+        const double um = (p == 0) ? left : ytmp[p - 1];
+        const double up = (p == P - 1) ? right : ytmp[p + 1];
+        ks[p] = Rhs::point(um, ytmp[p], up, A.p0, A.p1);
+      }
+      constexpr double b1 = Tab::b(0, s), b2 = Tab::b(1, s);
+#pragma unroll
+      for (int p = 0; p < P; p++) {
+        if constexpr (b1 != 0.0) ytrial[p] = ytrial[p] + b1 * ks[p];
+        if constexpr (b2 != 0.0) yerr[p] = yerr[p] + b2 * ks[p];
+        if constexpr (s < S - 1) dtk[s][p] = dt * ks[p];
+        if constexpr (s == S - 1) klast[p] = ks[p];
+      }
+    });
+#pragma unroll
+    for (int p = 0; p < P; p++) {  // :395-398
+      yerr[p] = dt * (ytrial[p] - yerr[p]);
+      ytrial[p] = y[p] + dt * ytrial[p];
+    }
+    double knext[P];
+    if constexpr (FSAL) {
+#pragma unroll
+      for (int p = 0; p < P; p++) knext[p] = klast[p];
+    } else {  // f1 = F(t+dt, ytrial) :320, fused as one more stencil sweep
+      const int buf = xc & 1;
+      xc++;
+      eL[buf][tid] = ytrial[0];
+      eR[buf][tid] = ytrial[P - 1];
+      __syncthreads();
+      const double left = (tid > 0) ? eR[buf][tid - 1] : ytrial[0];
+      const double right = (tid < T - 1) ? eL[buf][tid + 1] : ytrial[P - 1];
+#pragma unroll
+      for (int p = 0; p < P; p++) {
+        const double um = (p == 0) ? left : ytrial[p - 1];
+        const double up = (p == P - 1) ? right : ytrial[p + 1];
+        knext[p] = Rhs::point(um, ytrial[p], up, A.p0, A.p1);
+      }
+    }
+
+    // ---- scaled error (stepsize_hw92! :430-435), valid points only -------------
+    bool allvalid = true;
 #pragma unroll
     for (int p = 0; p < P; p++) {
       const int off = off0 + p;
-      const long long li = q0 + p - H;
-      if ((off >= H) && (off < H + VAL) && (li < A.n)) {
-        ytA[q0 + p] = ytrial[p];
-        knA[q0 + p] = knext[p];
+      const long long li = q0 + p - H;  // interior index
+      const bool valid = (off >= H) && (off < H + VAL) && (li < A.n);
+      allvalid = allvalid && valid;
+      if (valid) {
+        anynan = anynan || (ytrial[p] != ytrial[p]);
+        const double ay = fabs(y[p]), at = fabs(ytrial[p]);
+        const double e = yerr[p] / (abstol + ((ay > at) ? ay : at) * reltol);  // :433
+        acc = dd_add_sq(acc, e);
+        mx = normInf_step(mx, fabs(e));
       }
     }
-  }
-  // slab edges ride along with the error partials (ghost refresh on accept)
+    // stores
+    if (allvalid) {
 #pragma unroll
-  for (int p = 0; p < P; p++) {
-    const int off = off0 + p;
-    const long long li = q0 + p - H;
-    if ((off >= H) && (off < H + VAL) && (li < A.n)) {
-      if (li < H) {
-        A.xsend[XS_EDGE + li] = ytrial[p];
-        A.xsend[XS_EDGE + 2 * H + li] = knext[p];
+      for (int c = 0; c < P / 4; c++) {
+        *reinterpret_cast<double4*>(ytA + q0 + 4 * c) =
+            make_double4(ytrial[4 * c], ytrial[4 * c + 1], ytrial[4 * c + 2], ytrial[4 * c + 3]);
+        *reinterpret_cast<double4*>(knA + q0 + 4 * c) =
+            make_double4(knext[4 * c], knext[4 * c + 1], knext[4 * c + 2], knext[4 * c + 3]);
       }
-      if (li >= A.n - H) {
-        A.xsend[XS_EDGE + H + (li - (A.n - H))] = ytrial[p];
-        A.xsend[XS_EDGE + 3 * H + (li - (A.n - H))] = knext[p];
+    } else {
+#pragma unroll
+      for (int p = 0; p < P; p++) {
+        const int off = off0 + p;
+        const long long li = q0 + p - H;
+        if ((off >= H) && (off < H + VAL) && (li < A.n)) {
+          ytA[q0 + p] = ytrial[p];
+          knA[q0 + p] = knext[p];
+        }
+      }
+    }
+    // slab edges ride along with the error partials (ghost refresh on accept)
+    if (tile == 0 || q0 + P + VAL >= A.n) {  // only the first tile and the last two can touch an edge
+#pragma unroll
+      for (int p = 0; p < P; p++) {
+        const int off = off0 + p;
+        const long long li = q0 + p - H;
+        if ((off >= H) && (off < H + VAL) && (li < A.n)) {
+          if (li < H) {
+            A.xsend[XS_EDGE + li] = ytrial[p];
+            A.xsend[XS_EDGE + 2 * H + li] = knext[p];
+          }
+          if (li >= A.n - H) {
+            A.xsend[XS_EDGE + H + (li - (A.n - H))] = ytrial[p];
+            A.xsend[XS_EDGE + 3 * H + (li - (A.n - H))] = knext[p];
+          }
+        }
       }
     }
   }
 
-  // ---- block reduction: warp shuffles, then shared memory ----------------------
+  // ---- one block reduction per CTA: warp shuffles, then shared memory --------------
   double nanf = anynan ? 1.0 : 0.0;
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) {
@@ -278,6 +318,7 @@ __global__ void __launch_bounds__(LARGE_THREADS) large_attempt_kernel(const Larg
     mx = normInf_step(mx, __shfl_down_sync(0xffffffffu, mx, o));
     nanf = fmax(nanf, __shfl_down_sync(0xffffffffu, nanf, o));
   }
+  __syncthreads();  // all exchanges of the tile loop are complete before `red` is reused
   if ((tid & 31) == 0) {
     red[tid >> 5][0] = acc.hi;
     red[tid >> 5][1] = acc.lo;
@@ -298,7 +339,7 @@ __global__ void __launch_bounds__(LARGE_THREADS) large_attempt_kernel(const Larg
       m = normInf_step(m, red[w][2]);
       nf = fmax(nf, red[w][3]);
     }
-    double* pp = A.part + tile * 4;
+    double* pp = A.part + (long long)blockIdx.x * 4;
     pp[0] = tot.hi;
     pp[1] = tot.lo;
     pp[2] = m;
@@ -309,34 +350,21 @@ __global__ void __launch_bounds__(LARGE_THREADS) large_attempt_kernel(const Larg
   }
   __syncthreads();
   if (!is_last) return;
-  // ---- last CTA: reduce all tile partials in a fixed order -> xsend[0..3] -------
+  // ---- last CTA: reduce the per-CTA partials in a fixed order -> xsend[0..3] ----------
   __threadfence();
   dm_dd a2;
   a2.hi = 0.0;
   a2.lo = 0.0;
   double m2 = 0.0, n2 = 0.0;
-  for (long long b0 = tid; b0 < A.tiles; b0 += 4 * T) {  // 4 independent 32-byte L2 loads in flight per thread
-    double4 v[4];
-#pragma unroll
-    for (int u = 0; u < 4; u++) {
-      const long long b = b0 + (long long)u * T;
-      if (b < A.tiles) {
-        const double2 lo2 = __ldcg(reinterpret_cast<const double2*>(A.part + b * 4));
-        const double2 hi2 = __ldcg(reinterpret_cast<const double2*>(A.part + b * 4 + 2));
-        v[u] = make_double4(lo2.x, lo2.y, hi2.x, hi2.y);
-      } else {
-        v[u] = make_double4(0.0, 0.0, 0.0, 0.0);
-      }
-    }
-#pragma unroll
-    for (int u = 0; u < 4; u++) {
-      dm_dd o;
-      o.hi = v[u].x;
-      o.lo = v[u].y;
-      a2 = dd_add(a2, o);
-      m2 = normInf_step(m2, v[u].z);
-      n2 = fmax(n2, v[u].w);
-    }
+  for (int b = tid; b < (int)gridDim.x; b += T) {
+    const double2 lo2 = __ldcg(reinterpret_cast<const double2*>(A.part + (long long)b * 4));
+    const double2 hi2 = __ldcg(reinterpret_cast<const double2*>(A.part + (long long)b * 4 + 2));
+    dm_dd o;
+    o.hi = lo2.x;
+    o.lo = lo2.y;
+    a2 = dd_add(a2, o);
+    m2 = normInf_step(m2, hi2.x);
+    n2 = fmax(n2, hi2.y);
   }
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) {

@@ -235,3 +235,17 @@ def test_empty_and_ragged_ensembles():
         got = m.solve_ensemble("ode45", F, y0, [0.0, 0.5])
         ref = O.solve_ensemble("ode45", "lorenz", y0, [0.0, 0.5], LORENZ)
         assert_same(got, ref)
+
+
+def test_chunked_host_path_matches_oracle_at_chunk_boundaries():
+    """>= 262144 trajectories take the 4-chunk, two-stream pipeline inside ode_b200_solve_ensemble;
+    results must not depend on the chunking (checked against the oracle around every chunk boundary)."""
+    n = 4 * 65536 + 17
+    y0 = lorenz_ics(n, 77)
+    got = m.solve_ensemble("ode45", m.DeviceRHS("lorenz", *LORENZ), y0, [0.0, 1.0])
+    assert np.all(got["status"] == 0) and np.all(got["t_final"] == 1.0)
+    idx = np.unique(np.concatenate([np.arange(0, 64)] + [np.arange(n * c // 4 - 32, n * c // 4 + 32) for c in (1, 2, 3)]
+                                   + [np.arange(n - 64, n)]))
+    ref = O.solve_ensemble("ode45", "lorenz", y0[idx], [0.0, 1.0], LORENZ)
+    for k in ("y_final", "t_final", "n_accept", "n_reject", "n_rhs", "status"):
+        assert np.array_equal(got[k][idx], ref[k]), k

@@ -46,7 +46,10 @@ typedef enum {
   ODE_B200_M_DOPRI5 = 7,   /* ode45 = ode45_dp  bt_dopri5 :124 */
   ODE_B200_M_FEH78 = 8,    /* ode78          bt_feh78    :140 */
   ODE_B200_M_ODE23S = 9,   /* ode23s         src/ODE.jl:252 */
-  ODE_B200_M_COUNT = 10
+  ODE_B200_M_ODE4S_S = 10, /* ode4s = ode4s_s  oderosenbrock with Shampine coefficients, src/ODE.jl:366-438 */
+  ODE_B200_M_ODE4S_KR = 11,/* ode4s_kr         oderosenbrock with Kaps-Rentrop coefficients, src/ODE.jl:408-419 */
+  ODE_B200_M_ODE4MS = 12,  /* ode4ms           Adams-Bashforth order 4, ode_ms src/ODE.jl:175-212 */
+  ODE_B200_M_COUNT = 13
 } ode_b200_method;
 
 /* ---- registered right-hand sides F(t, y; params) ------------------------- */
@@ -103,7 +106,8 @@ typedef struct {
   int32_t n_params;  /* parameters per trajectory */
   int32_t params_stride; /* 0: one shared parameter vector; else doubles between trajectories */
   int32_t points;    /* ode_b200_points */
-  int32_t jacobian;  /* ode23s: 0 = forward-difference fdjacobian (reference default), 1 = analytic functor */
+  int32_t jacobian;  /* ode23s / ode4s: 0 = forward-difference fdjacobian (reference default, src/ODE.jl:232-243),
+                        1 = the registered analytic Jacobian of the rhs (the `jacobian = G(t,y)` keyword) */
   int32_t device;    /* CUDA device ordinal */
   int64_t max_steps; /* guard on step attempts per trajectory; <=0 -> 100000000 */
   double reltol, abstol, minstep, maxstep, initstep;

@@ -14,6 +14,7 @@ from ._lib import Opts, EnsembleIO, METHODS, POINTS, check, lib
 from .rhs import DeviceRHS
 
 _FIXED = ("ode1", "ode2_midpoint", "ode2_heun", "ode4")
+_ROSENBROCK_FIXED = ("ode4s", "ode4s_s", "ode4s_kr")  # oderosenbrock(...; jacobian=nothing, kwargs...), src/ODE.jl:366
 
 
 def _vp(a):
@@ -36,8 +37,12 @@ def make_opts(method, F, tspan, *, reltol=1e-5, abstol=1e-8, minstep=None, maxst
                         "libode_b200 has no CPU fallback), got %r" % type(F).__name__)
     if norm is not None:
         raise NotImplementedError("only the default norm (LinearAlgebra.norm) is compiled into the kernels")
-    if jacobian is not None:
-        raise NotImplementedError("user Jacobians are not registered; ode23s uses the reference's fdjacobian")
+    # `jacobian = G(t,y)` (src/ODE.jl:254,262-267): a host closure cannot run on the device, so the
+    # keyword selects the REGISTERED analytic Jacobian of F (jacobian=True); None/False keeps fdjacobian.
+    if jacobian not in (None, False, True, 0, 1):
+        raise TypeError("jacobian must be None/False (fdjacobian) or True (the registered analytic Jacobian of F)")
+    if jacobian and method not in ("ode23s",) + _ROSENBROCK_FIXED:
+        raise TypeError("%s does not take a jacobian keyword" % method)
     span = abs(float(tspan[-1]) - float(tspan[0]))
     o = Opts()
     o.method = METHODS[method]
@@ -46,7 +51,7 @@ def make_opts(method, F, tspan, *, reltol=1e-5, abstol=1e-8, minstep=None, maxst
     o.n_params = F.n_params
     o.params_stride = int(params_stride)
     o.points = _points(points)
-    o.jacobian = 0
+    o.jacobian = 1 if jacobian else 0
     o.device = int(device)
     o.max_steps = int(max_steps)
     o.reltol = float(reltol)
@@ -99,6 +104,12 @@ def _solve_single(name, F, y0, tspan, _stats=False, **kw):
         if kw and not scalar:
             raise TypeError("%s on a vector y0 takes no keyword arguments (reference: oderk_fixed)" % name)
         kw = {}
+    elif name in _ROSENBROCK_FIXED:
+        kw = {"jacobian": kw.get("jacobian")}  # the other keywords are swallowed by kwargs... (src/ODE.jl:366)
+        if name == "ode4s":
+            kw = {}  # ode4s(F, x0, tspan; jacobian=nothing, kwargs...) passes jacobian=nothing on (src/ODE.jl:437-438)
+    elif name == "ode4ms":
+        kw = {}  # ode_ms(F, x0, tspan, order; kwargs...) ignores keywords (src/ODE.jl:175,212)
     o = make_opts(name, F, ts, **kw)
     if y.size != o.dof:
         raise ValueError("%r has %d components, y0 has %d" % (F, o.dof, y.size))
@@ -139,6 +150,10 @@ ode45_dp = Solver("ode45_dp")
 ode45 = Solver("ode45")  # Dormand-Prince by default, src/runge_kutta.jl:223
 ode78 = Solver("ode78")
 ode23s = Solver("ode23s")
+ode4s_s = Solver("ode4s_s")    # Shampine coefficients, src/ODE.jl:433
+ode4s_kr = Solver("ode4s_kr")  # Kaps-Rentrop coefficients, src/ODE.jl:419
+ode4s = Solver("ode4s")        # = ode4s_s with jacobian=nothing, src/ODE.jl:437
+ode4ms = Solver("ode4ms")      # Adams-Bashforth order 4, src/ODE.jl:212
 
 
 def _alg_name(alg):

@@ -45,8 +45,6 @@ def solve(prob, alg, *, verbose=True, save_timeseries=None, saveat=(), reltol=1e
           save_everystep=None, dense=None, save_start=None, callback=None, dtmin=None, dtmax=None,
           timeseries_errors=True, dense_errors=False, dt=0.0, norm=None, **kwargs):
     name = _alg_name(alg)
-    if name in ("ode4ms", "ode4s"):
-        raise NotImplementedError("%s is outside the RK/ode23s hot path (SURVEY.md section 8f)" % name)
     if name not in ALGORITHMS:
         raise TypeError("%r is not an ODEjlAlgorithm" % (alg,))
     if not isinstance(prob.f, DeviceRHS):

@@ -88,7 +88,8 @@ static const NameId kMethods[] = {
     {"rk21", ODE_B200_M_RK21},         {"ode23", ODE_B200_M_RK23},        {"rk23", ODE_B200_M_RK23},
     {"ode45_fe", ODE_B200_M_RK45_FE},  {"rk45", ODE_B200_M_RK45_FE},      {"ode45", ODE_B200_M_DOPRI5},
     {"ode45_dp", ODE_B200_M_DOPRI5},   {"dopri5", ODE_B200_M_DOPRI5},     {"ode78", ODE_B200_M_FEH78},
-    {"feh78", ODE_B200_M_FEH78},       {"ode23s", ODE_B200_M_ODE23S}};
+    {"feh78", ODE_B200_M_FEH78},       {"ode23s", ODE_B200_M_ODE23S},     {"ode4s", ODE_B200_M_ODE4S_S},
+    {"ode4s_s", ODE_B200_M_ODE4S_S},   {"ode4s_kr", ODE_B200_M_ODE4S_KR}, {"ode4ms", ODE_B200_M_ODE4MS}};
 static const NameId kRhs[] = {{"linear", ODE_B200_RHS_LINEAR},
                               {"const", ODE_B200_RHS_CONST},
                               {"timelin", ODE_B200_RHS_TIMELIN},
@@ -123,6 +124,11 @@ static double tab_get(int which, int i, int j) {
     default: break;                               \
   }
 
+static bool is_fixed_step(int method) {
+  return method <= ODE_B200_M_RK4 || method == ODE_B200_M_ODE4S_S || method == ODE_B200_M_ODE4S_KR ||
+         method == ODE_B200_M_ODE4MS;
+}
+
 static int device_ok(int dev) {
   int n = 0;
   cudaError_t e = cudaGetDeviceCount(&n);
@@ -150,11 +156,11 @@ static int validate(const ode_b200_opts* o, const ode_b200_ensemble_io* io, doub
   if (io->n_tspan < 2 || !io->tspan) return set_err(ODE_B200_E_INVALID, "tspan needs at least 2 entries");
   if (o->points != ODE_B200_POINTS_ALL && o->points != ODE_B200_POINTS_SPECIFIED && o->points != ODE_B200_POINTS_FINAL)
     return set_err(ODE_B200_E_POINTS, "Unrecognized option points==%d", o->points);  // src/runge_kutta.jl:289
-  if (o->jacobian != 0) return set_err(ODE_B200_E_UNSUPPORTED, "analytic Jacobian functors are not registered yet");
+  if (o->jacobian != 0 && o->jacobian != 1) return set_err(ODE_B200_E_INVALID, "jacobian must be 0 (fdjacobian) or 1 (analytic)");
   if (!(o->reltol == o->reltol) || !(o->abstol == o->abstol) || !(o->minstep == o->minstep) ||
       !(o->maxstep == o->maxstep) || !(o->initstep == o->initstep))
     return set_err(ODE_B200_E_INVALID, "NaN in reltol/abstol/minstep/maxstep/initstep");
-  const bool fixed = o->method <= ODE_B200_M_RK4;
+  const bool fixed = is_fixed_step(o->method);
   if (!fixed) {
     double tdir = tend > t0 ? 1.0 : (tend < t0 ? -1.0 : 0.0);
     if (!(tend == tend) || !(t0 == t0)) return set_err(ODE_B200_E_INVALID, "NaN in tspan");
@@ -176,7 +182,10 @@ static EnsembleKernel pick_kernel(const ode_b200_opts* o, int mode) {
     case ODE_B200_M_RK45_FE: return adapt_kernel_rk45(o->rhs, mode);
     case ODE_B200_M_DOPRI5: return adapt_kernel_dopri5(o->rhs, mode);
     case ODE_B200_M_FEH78: return adapt_kernel_feh78(o->rhs, mode);
-    case ODE_B200_M_ODE23S: return ode23s_kernel(o->rhs, mode);
+    case ODE_B200_M_ODE23S: return ode23s_kernel(o->rhs, mode, o->jacobian);
+    case ODE_B200_M_ODE4S_S:
+    case ODE_B200_M_ODE4S_KR: return rosenbrock_kernel(o->method, o->rhs, o->jacobian);
+    case ODE_B200_M_ODE4MS: return ms4_kernel(o->rhs);
     default: return fixed_kernel(o->method, o->rhs);
   }
 }
@@ -283,6 +292,7 @@ int ode_b200_rhs_dof(int rhs) { return (rhs >= 0 && rhs < ODE_B200_RHS_COUNT) ? 
 int ode_b200_rhs_nparams(int rhs) { return (rhs >= 0 && rhs < ODE_B200_RHS_COUNT) ? kRhsNp[rhs] : ODE_B200_E_INVALID; }
 int ode_b200_method_stages(int method) {
   if (method == ODE_B200_M_ODE23S) return 3;
+  if (method == ODE_B200_M_ODE4S_S || method == ODE_B200_M_ODE4S_KR || method == ODE_B200_M_ODE4MS) return 4;
 #define X(T) return T::S
   ODEB200_TAB_SWITCH(method, X)
 #undef X
@@ -290,12 +300,14 @@ int ode_b200_method_stages(int method) {
 }
 int ode_b200_method_is_adaptive(int method) {
   if (method == ODE_B200_M_ODE23S) return 1;
+  if (method == ODE_B200_M_ODE4S_S || method == ODE_B200_M_ODE4S_KR || method == ODE_B200_M_ODE4MS) return 0;
 #define X(T) return T::NB == 2
   ODEB200_TAB_SWITCH(method, X)
 #undef X
   return ODE_B200_E_INVALID;
 }
 int ode_b200_method_is_fsal(int method) {
+  if (method == ODE_B200_M_ODE4S_S || method == ODE_B200_M_ODE4S_KR || method == ODE_B200_M_ODE4MS) return 0;
   if (method == ODE_B200_M_ODE23S) return 1;  // F0 = F2, src/ODE.jl:351
 #define X(T)                       \
   {                                \
@@ -493,7 +505,7 @@ int ode_b200_solve_single(const ode_b200_opts* opts, const double* y0, const dou
   ode_b200_opts o = *opts;
   o.params_stride = 0;
   long long cap = n_tspan + 1024;
-  const bool fixed = o.method <= ODE_B200_M_RK4;
+  const bool fixed = is_fixed_step(o.method);
   if (fixed || o.points == ODE_B200_POINTS_SPECIFIED) cap = n_tspan;
   for (int tries = 0; tries < 8; tries++) {
     std::vector<double> pt(cap), py((size_t)cap * o.dof), yf(o.dof);

@@ -12,7 +12,9 @@ EnsembleKernel adapt_kernel_rk45(int rhs, int mode);
 EnsembleKernel adapt_kernel_dopri5(int rhs, int mode);
 EnsembleKernel adapt_kernel_feh78(int rhs, int mode);
 EnsembleKernel fixed_kernel(int method, int rhs);
-EnsembleKernel ode23s_kernel(int rhs, int mode);
+EnsembleKernel ode23s_kernel(int rhs, int mode, int jac);  // jac: 0 fdjacobian, 1 analytic functor
+EnsembleKernel rosenbrock_kernel(int method, int rhs, int jac);
+EnsembleKernel ms4_kernel(int rhs);
 
 #define ODEB200_RHS_SWITCH(rhs, X)                 \
   switch (rhs) {                                   \

@@ -102,7 +102,18 @@ __device__ __forceinline__ void fd_jacobian(double t, const double (&x)[D], cons
   }
 }
 
-template <class Rhs, int MODE>
+// jac = jacobian(t, y): the registered analytic functor (JAC = 1) or fdjacobian (JAC = 0), :262-267
+template <class Rhs, int JAC, int D, int NPA>
+__device__ __forceinline__ int eval_jacobian(double t, const double (&x)[D], const double (&p)[NPA], double (&J)[D][D]) {
+  if (JAC) {
+    Rhs::jac(t, x, J, p);
+    return 0;
+  }
+  fd_jacobian<Rhs, D, NPA>(t, x, p, J);
+  return D + 1;
+}
+
+template <class Rhs, int MODE, int JAC>
 __global__ void __launch_bounds__(ENS_BLOCK) ens_ode23s_kernel(const EnsembleArgs A) {
   constexpr int D = Rhs::DOF, NPA = RhsNP<Rhs>::value;
   const double dd = 1.0 / (2.0 + sqrt(2.0));  // :270
@@ -176,8 +187,7 @@ __global__ void __launch_bounds__(ENS_BLOCK) ens_ode23s_kernel(const EnsembleArg
         npts = 1;
         last_tout = tstart;
       }
-      fd_jacobian<Rhs, D, NPA>(t, y, p, J);  // :294
-      nrhs += D + 1;
+      nrhs += eval_jacobian<Rhs, JAC, D, NPA>(t, y, p, J);  // :294
     }
 
     int fin = -1;
@@ -277,8 +287,7 @@ __global__ void __launch_bounds__(ENS_BLOCK) ens_ode23s_kernel(const EnsembleArg
             y[i] = ynew[i];  // :349
             F0[i] = F2[i];   // :351
           }
-          fd_jacobian<Rhs, D, NPA>(t, y, p, J);  // :352
-          nrhs += D + 1;
+          nrhs += eval_jacobian<Rhs, JAC, D, NPA>(t, y, p, J);  // :352
         } else {
           nrej++;
         }

@@ -6,6 +6,8 @@
 // would be given; the CPU oracle states them independently
 // (oracle/ode_oracle.cpp Rhs::operator(), oracle/ode_oracle.py rhs_factory) and
 // the parity tests compare bit for bit.  No FMA contraction (-fmad=false).
+// `jac` is the registered analytic Jacobian dF/dy -- what a user would pass as the
+// `jacobian = G(t,y)` keyword of ode23s / ode4s (src/ODE.jl:262-263, :368-369).
 #pragma once
 
 namespace odeb200 {
@@ -16,12 +18,18 @@ struct RhsLinear {
   __device__ __forceinline__ static void eval(double, const double (&y)[1], double (&f)[1], const double (&p)[1]) {
     f[0] = p[0] * y[0];
   }
+  __device__ __forceinline__ static void jac(double, const double (&)[1], double (&J)[1][1], const double (&p)[1]) {
+    J[0][0] = p[0];
+  }
 };
 // (t,y) -> T(6)             test/runtests.jl:40
 struct RhsConst {
   static constexpr int DOF = 1, NP = 1, ID = ODE_B200_RHS_CONST;
   __device__ __forceinline__ static void eval(double, const double (&)[1], double (&f)[1], const double (&p)[1]) {
     f[0] = p[0];
+  }
+  __device__ __forceinline__ static void jac(double, const double (&)[1], double (&J)[1][1], const double (&)[1]) {
+    J[0][0] = 0.0;
   }
 };
 // (t,y) -> T(2)*t           test/runtests.jl:47
@@ -30,6 +38,9 @@ struct RhsTimeLin {
   __device__ __forceinline__ static void eval(double t, const double (&)[1], double (&f)[1], const double (&p)[1]) {
     f[0] = p[0] * t;
   }
+  __device__ __forceinline__ static void jac(double, const double (&)[1], double (&J)[1][1], const double (&)[1]) {
+    J[0][0] = 0.0;
+  }
 };
 // (t,y) -> [-y[2]; y[1]]    test/runtests.jl:67
 struct RhsRotation {
@@ -37,6 +48,12 @@ struct RhsRotation {
   __device__ __forceinline__ static void eval(double, const double (&y)[2], double (&f)[2], const double (&)[1]) {
     f[0] = -y[1];
     f[1] = y[0];
+  }
+  __device__ __forceinline__ static void jac(double, const double (&)[2], double (&J)[2][2], const double (&)[1]) {
+    J[0][0] = 0.0;
+    J[0][1] = -1.0;
+    J[1][0] = 1.0;
+    J[1][1] = 0.0;
   }
 };
 // Lorenz, examples/Lorenz_Attractor.ipynb cell 4: [s*(y-x); x*(r-z)-y; x*y-b*z]
@@ -47,6 +64,17 @@ struct RhsLorenz {
     f[1] = y[0] * (p[1] - y[2]) - y[1];
     f[2] = y[0] * y[1] - p[2] * y[2];
   }
+  __device__ __forceinline__ static void jac(double, const double (&y)[3], double (&J)[3][3], const double (&p)[3]) {
+    J[0][0] = -p[0];
+    J[0][1] = p[0];
+    J[0][2] = 0.0;
+    J[1][0] = p[1] - y[2];
+    J[1][1] = -1.0;
+    J[1][2] = -y[0];
+    J[2][0] = y[1];
+    J[2][1] = y[0];
+    J[2][2] = -p[2];
+  }
 };
 // Van der Pol: [y2; mu*((1-y1*y1)*y2) - y1]
 struct RhsVdp {
@@ -54,6 +82,12 @@ struct RhsVdp {
   __device__ __forceinline__ static void eval(double, const double (&y)[2], double (&f)[2], const double (&p)[1]) {
     f[0] = y[1];
     f[1] = p[0] * ((1.0 - y[0] * y[0]) * y[1]) - y[0];
+  }
+  __device__ __forceinline__ static void jac(double, const double (&y)[2], double (&J)[2][2], const double (&p)[1]) {
+    J[0][0] = 0.0;
+    J[0][1] = 1.0;
+    J[1][0] = p[0] * ((-2.0 * y[0]) * y[1]) - 1.0;
+    J[1][1] = p[0] * (1.0 - y[0] * y[0]);
   }
 };
 // Robertson, test/runtests.jl:81-87 (ydot[1], then ydot[3], then ydot[2] = -ydot[1]-ydot[3])
@@ -66,6 +100,18 @@ struct RhsRobertson {
     f[2] = d3;
     f[1] = -d1 - d3;
   }
+  __device__ __forceinline__ static void jac(double, const double (&y)[3], double (&J)[3][3], const double (&p)[3]) {
+    const double a = p[2] * y[2], b = p[2] * y[1], c = (2.0 * p[1]) * y[1];
+    J[0][0] = -p[0];
+    J[0][1] = a;
+    J[0][2] = b;
+    J[1][0] = p[0];
+    J[1][1] = -a - c;
+    J[1][2] = -b;
+    J[2][0] = 0.0;
+    J[2][1] = c;
+    J[2][2] = 0.0;
+  }
 };
 // planar Kepler, mu = 1: r2 = x*x+y*y; r3 = r2*sqrt(r2); [vx, vy, -x/r3, -y/r3]
 struct RhsKepler {
@@ -77,6 +123,22 @@ struct RhsKepler {
     f[1] = y[3];
     f[2] = -y[0] / r3;
     f[3] = -y[1] / r3;
+  }
+  __device__ __forceinline__ static void jac(double, const double (&y)[4], double (&J)[4][4], const double (&)[1]) {
+    const double x = y[0], yy = y[1];
+    const double r2 = x * x + yy * yy;
+    const double r3 = r2 * sqrt(r2), r5 = r3 * r2;
+#pragma unroll
+    for (int i = 0; i < 4; i++) {
+#pragma unroll
+      for (int j = 0; j < 4; j++) J[i][j] = 0.0;
+    }
+    J[0][2] = 1.0;
+    J[1][3] = 1.0;
+    J[2][0] = (3.0 * x) * x / r5 - 1.0 / r3;
+    J[2][1] = (3.0 * x) * yy / r5;
+    J[3][0] = (3.0 * x) * yy / r5;
+    J[3][1] = (3.0 * yy) * yy / r5 - 1.0 / r3;
   }
 };
 

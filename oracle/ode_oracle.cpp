@@ -299,6 +299,46 @@ struct Rhs {
   }
 };
 
+// Registered analytic Jacobians dF/dy (row-major n x n): what a user would pass as
+// `jacobian = G(t,y)` (src/ODE.jl:262-263, :368-369).  Entry expressions are this
+// repo's definition; the CUDA functors state the same expressions.
+bool rhs_jacobian(const Rhs& F, double t, const double* y, double* J) {
+  const double* p = F.p;
+  switch (F.id) {
+    case ODE_B200_RHS_LINEAR: J[0] = p[0]; return true;
+    case ODE_B200_RHS_CONST: J[0] = 0.0; return true;
+    case ODE_B200_RHS_TIMELIN: J[0] = 0.0; return true;
+    case ODE_B200_RHS_ROTATION: J[0] = 0.0; J[1] = -1.0; J[2] = 1.0; J[3] = 0.0; return true;
+    case ODE_B200_RHS_LORENZ:
+      J[0] = -p[0]; J[1] = p[0]; J[2] = 0.0;
+      J[3] = p[1] - y[2]; J[4] = -1.0; J[5] = -y[0];
+      J[6] = y[1]; J[7] = y[0]; J[8] = -p[2];
+      return true;
+    case ODE_B200_RHS_VDP:
+      J[0] = 0.0; J[1] = 1.0;
+      J[2] = p[0] * ((-2.0 * y[0]) * y[1]) - 1.0; J[3] = p[0] * (1.0 - y[0] * y[0]);
+      return true;
+    case ODE_B200_RHS_ROBERTSON: {
+      const double a = p[2] * y[2], b = p[2] * y[1], c = (2.0 * p[1]) * y[1];
+      J[0] = -p[0]; J[1] = a; J[2] = b;
+      J[3] = p[0]; J[4] = -a - c; J[5] = -b;
+      J[6] = 0.0; J[7] = c; J[8] = 0.0;
+      return true;
+    }
+    case ODE_B200_RHS_KEPLER: {
+      const double x = y[0], yy = y[1];
+      const double r2 = x * x + yy * yy;
+      const double r3 = r2 * std::sqrt(r2), r5 = r3 * r2;
+      for (int i = 0; i < 16; i++) J[i] = 0.0;
+      J[2] = 1.0; J[7] = 1.0;
+      J[8] = (3.0 * x) * x / r5 - 1.0 / r3; J[9] = (3.0 * x) * yy / r5;
+      J[12] = (3.0 * x) * yy / r5; J[13] = (3.0 * yy) * yy / r5 - 1.0 / r3;
+      return true;
+    }
+    default: return false;
+  }
+}
+
 // ------------------------------------------------------------- result record
 struct Result {
   int dof = 0;
@@ -315,6 +355,7 @@ struct Opt {
   int points;
   int64_t max_steps;
   bool want_trace;
+  int jacobian = 0;  // 0: fdjacobian, 1: registered analytic Jacobian
 };
 
 // hinit, src/ODE.jl:85-112.  Returns signed h; sets tdir and f0.
@@ -667,7 +708,15 @@ void ode23s(const Rhs& F, const MathCtx& M, const Vec& y0, const Vec& tspan, con
   tout.push_back(t);  // :290-291
   yout.push_back(y);
   Vec J;
-  fdjacobian(F, y, t, J);  // :294
+  auto jac = [&](const Vec& yy, double tt) {  // :262-267
+    if (o.jacobian) {
+      J.assign(n * n, 0.0);
+      rhs_jacobian(F, tt, yy.data(), J.data());
+    } else {
+      fdjacobian(F, yy, tt, J);
+    }
+  };
+  jac(y, t);  // :294
   Vec Fa(n), T(n), k1(n), k2(n), k3(n), F1(n), F2(n), ynew(n), tmp(n);
   int64_t attempts = 0;
   while (std::fabs(t - tfinal) > 0 && o.minstep < std::fabs(h)) {  // :296
@@ -746,7 +795,7 @@ void ode23s(const Rhs& F, const MathCtx& M, const Vec& y0, const Vec& tspan, con
       t = t + h;  // :348-352
       y = ynew;
       F0 = F2;
-      fdjacobian(F, y, t, J);
+      jac(y, t);
     } else {
       R.nrej++;
     }
@@ -762,15 +811,125 @@ void ode23s(const Rhs& F, const MathCtx& M, const Vec& y0, const Vec& tspan, con
     for (int64_t k = 0; k < n; k++) R.y[i * n + k] = yout[i][k];
 }
 
+// oderosenbrock, src/ODE.jl:366-404, coefficients :408-431.
+struct RosCoef {
+  double gamma, a[4][4], b[4], c[4][4];
+};
+const RosCoef& ros_coef(int method) {
+  static const RosCoef kr = {0.231,
+                             {{0, 0, 0, 0}, {2, 0, 0, 0}, {4.452470820736, 4.16352878860, 0, 0}, {4.452470820736, 4.16352878860, 0, 0}},
+                             {3.95750374663, 4.62489238836, 0.617477263873, 1.28261294568},
+                             {{0, 0, 0, 0}, {-5.07167533877, 0, 0, 0}, {6.02015272865, 0.1597500684673, 0, 0},
+                              {-1.856343618677, -8.50538085819, -2.08407513602, 0}}};
+  static const RosCoef sh = {0.5,
+                             {{0, 0, 0, 0}, {2, 0, 0, 0}, {48.0 / 25, 6.0 / 25, 0, 0}, {48.0 / 25, 6.0 / 25, 0, 0}},
+                             {19.0 / 9, 1.0 / 2, 25.0 / 108, 125.0 / 108},
+                             {{0, 0, 0, 0}, {-8, 0, 0, 0}, {372.0 / 25, 12.0 / 5, 0, 0}, {-112.0 / 125, -54.0 / 125, -2.0 / 5, 0}}};
+  return method == ODE_B200_M_ODE4S_KR ? kr : sh;
+}
+void oderosenbrock(const Rhs& F, int method, const Vec& x0, const Vec& tspan, const Opt& o, Result& R) {
+  const RosCoef& k = ros_coef(method);
+  const int64_t n = (int64_t)x0.size(), nt = (int64_t)tspan.size();
+  R.dof = (int)n;
+  std::vector<Vec> x(nt, Vec(n, 0.0));
+  x[0] = x0;
+  Vec J, f(n), arg(n), dx(n), dF(n);
+  Vec g[4];
+  for (int64_t st = 0; st + 1 < nt; st++) {  // :379
+    const double ts = tspan[st], hs = tspan[st + 1] - tspan[st];
+    const Vec& xs = x[st];
+    if (o.jacobian) {  // :383
+      J.assign(n * n, 0.0);
+      rhs_jacobian(F, ts, xs.data(), J.data());
+    } else {
+      fdjacobian(F, xs, ts, J);
+    }
+    LU W;  // :385  jac = I/(gamma*hs) - dFdx   (every `jac \ v` re-factorises the same matrix)
+    W.n = n;
+    W.a.resize(n * n);
+    const double lam = 1.0 / (k.gamma * hs);
+    for (int64_t i = 0; i < n; i++)
+      for (int64_t j = 0; j < n; j++) W.a[i * n + j] = (i == j) ? (-J[i * n + j] + lam) : -J[i * n + j];
+    lu_factor(W);
+    if (W.singular) {  // Julia raises SingularException; report the truncated solution instead
+      R.status = ODE_B200_ST_SINGULAR;
+      R.t.assign(tspan.begin(), tspan.begin() + st + 1);
+      R.y.resize((st + 1) * n);
+      for (int64_t i = 0; i <= st; i++)
+        for (int64_t d = 0; d < n; d++) R.y[i * n + d] = x[i][d];
+      R.nrhs = F.calls;
+      return;
+    }
+    F(ts + k.b[0] * hs, xs.data(), f.data());  // :388
+    g[0] = f;
+    lu_solve(W, g[0]);
+    for (int64_t d = 0; d < n; d++) x[st + 1][d] = xs[d] + k.b[0] * g[0][d];  // :389
+    for (int i = 1; i < 4; i++) {  // :391
+      for (int64_t d = 0; d < n; d++) {
+        dx[d] = 0.0;
+        dF[d] = 0.0;
+      }
+      for (int j = 0; j < i; j++)  // :394-397
+        for (int64_t d = 0; d < n; d++) {
+          dx[d] += k.a[i][j] * g[j][d];
+          dF[d] += k.c[i][j] * g[j][d];
+        }
+      for (int64_t d = 0; d < n; d++) arg[d] = xs[d] + dx[d];
+      F(ts + k.b[i] * hs, arg.data(), f.data());  // :398
+      g[i].resize(n);
+      for (int64_t d = 0; d < n; d++) g[i][d] = f[d] + dF[d] / hs;
+      lu_solve(W, g[i]);
+      for (int64_t d = 0; d < n; d++) x[st + 1][d] += k.b[i] * g[i][d];  // :399
+    }
+    R.nacc++;
+  }
+  R.nrhs = F.calls;
+  R.t = tspan;
+  R.y.resize(nt * n);
+  for (int64_t i = 0; i < nt; i++)
+    for (int64_t d = 0; d < n; d++) R.y[i * n + d] = x[i][d];
+}
+
+// ode_ms with order 4 (ode4ms), src/ODE.jl:175-212, coefficients :440-443.
+void ode4ms(const Rhs& F, const Vec& x0, const Vec& tspan, Result& R) {
+  static const double b[4][4] = {{1, 0, 0, 0},
+                                 {-1.0 / 2, 3.0 / 2, 0, 0},
+                                 {5.0 / 12, -4.0 / 3, 23.0 / 12, 0},
+                                 {-9.0 / 24, 37.0 / 24, -59.0 / 24, 55.0 / 24}};
+  const int order = 4;
+  const int64_t n = (int64_t)x0.size(), nt = (int64_t)tspan.size();
+  R.dof = (int)n;
+  std::vector<Vec> x(nt, Vec(n, 0.0)), xdot(nt, Vec(n, 0.0));
+  x[0] = x0;
+  for (int64_t i = 0; i + 1 < nt; i++) {  // :198 (0-based i; the reference's i is i+1)
+    const double h = tspan[i + 1] - tspan[i];
+    const int so = (int)std::min<int64_t>(i + 1, order);  // :200
+    F(tspan[i], x[i].data(), xdot[i].data());            // :201
+    x[i + 1] = x[i];                                      // :203
+    for (int j = 0; j < so; j++)                          // :204-206
+      for (int64_t d = 0; d < n; d++) x[i + 1][d] += h * b[so - 1][j] * xdot[i - (so - 1) + j][d];
+  }
+  R.nacc = nt - 1;
+  R.nrhs = F.calls;
+  R.t = tspan;
+  R.y.resize(nt * n);
+  for (int64_t i = 0; i < nt; i++)
+    for (int64_t d = 0; d < n; d++) R.y[i * n + d] = x[i][d];
+}
+
 void solve_one(const ode_b200_opts* op, const double* y0, const double* params, const double* tspan, int n_tspan,
                bool want_trace, Result& R) {
   Rhs F{op->rhs, op->dof, params};
   MathCtx M{op->mathmode};
   Opt o{op->reltol, op->abstol, op->minstep, op->maxstep, op->initstep, op->points,
-        op->max_steps > 0 ? op->max_steps : 100000000, want_trace};
+        op->max_steps > 0 ? op->max_steps : 100000000, want_trace, op->jacobian};
   Vec y(y0, y0 + op->dof), ts(tspan, tspan + n_tspan);
   if (op->method == ODE_B200_M_ODE23S) {
     ode23s(F, M, y, ts, o, R);
+  } else if (op->method == ODE_B200_M_ODE4S_S || op->method == ODE_B200_M_ODE4S_KR) {
+    oderosenbrock(F, op->method, y, ts, o, R);
+  } else if (op->method == ODE_B200_M_ODE4MS) {
+    ode4ms(F, y, ts, R);
   } else {
     Tab bt = make_tab(op->method);
     if (bt.S == 0) {

@@ -435,8 +435,9 @@ def lu_solve(lu, b):
 
 
 def ode23s(F, y0, tspan, reltol=1e-5, abstol=1e-8, minstep=None, maxstep=None, initstep=0.0, points="all",
-           max_steps=10 ** 8):
+           max_steps=10 ** 8, jac=None):
     F = Counted(F)
+    jacf = (lambda yy, tt: jac(tt, yy)) if jac is not None else (lambda yy, tt: fdjacobian(F, yy, tt))
     tspan = [float(x) for x in tspan]
     span = abs(tspan[-1] - tspan[0])
     minstep = span / 1e18 if minstep is None else minstep
@@ -456,7 +457,7 @@ def ode23s(F, y0, tspan, reltol=1e-5, abstol=1e-8, minstep=None, maxstep=None, i
     h = tdir * jmin(abs(h), maxstep)
     tout = [t]
     yout = [list(y)]
-    J = fdjacobian(F, y, t)
+    J = jacf(y, t)
     nacc = nrej = 0
     trace = []
     attempts = 0
@@ -503,7 +504,7 @@ def ode23s(F, y0, tspan, reltol=1e-5, abstol=1e-8, minstep=None, maxstep=None, i
             t = t + h
             y = ynew
             F0 = F2
-            J = fdjacobian(F, y, t)
+            J = jacf(y, t)
         else:
             nrej += 1
         h = tdir * jmin(maxstep, (abs(h) * 0.8) * jpow(delta / err if err != 0 else INF, 1.0 / 3))
@@ -512,10 +513,109 @@ def ode23s(F, y0, tspan, reltol=1e-5, abstol=1e-8, minstep=None, maxstep=None, i
     return dict(t=tout, y=yout, n_accept=nacc, n_reject=nrej, n_rhs=F.n, trace=trace, status=status)
 
 
-def solve(method, rhs, y0, tspan, params=None, **kw):
+# -- registered analytic Jacobians (same entry expressions as the C++ oracle) ----------
+def jac_factory(name, p):
+    if name == "linear":
+        return lambda t, y: [[p[0]]]
+    if name in ("const", "timelin"):
+        return lambda t, y: [[0.0]]
+    if name == "rotation":
+        return lambda t, y: [[0.0, -1.0], [1.0, 0.0]]
+    if name == "lorenz":
+        return lambda t, y: [[-p[0], p[0], 0.0], [p[1] - y[2], -1.0, -y[0]], [y[1], y[0], -p[2]]]
+    if name == "vdp":
+        return lambda t, y: [[0.0, 1.0], [p[0] * ((-2.0 * y[0]) * y[1]) - 1.0, p[0] * (1.0 - y[0] * y[0])]]
+    if name == "robertson":
+        def J(t, y):
+            a, b, c = p[2] * y[2], p[2] * y[1], (2.0 * p[1]) * y[1]
+            return [[-p[0], a, b], [p[0], -a - c, -b], [0.0, c, 0.0]]
+        return J
+    if name == "kepler":
+        def J(t, y):
+            x, yy = y[0], y[1]
+            r2 = x * x + yy * yy
+            r3 = r2 * math.sqrt(r2)
+            r5 = r3 * r2
+            return [[0.0, 0.0, 1.0, 0.0], [0.0, 0.0, 0.0, 1.0],
+                    [(3.0 * x) * x / r5 - 1.0 / r3, (3.0 * x) * yy / r5, 0.0, 0.0],
+                    [(3.0 * x) * yy / r5, (3.0 * yy) * yy / r5 - 1.0 / r3, 0.0, 0.0]]
+        return J
+    raise KeyError(name)
+
+
+ROS = {
+    "ode4s_kr": (0.231,
+                 [[0, 0, 0, 0], [2, 0, 0, 0], [4.452470820736, 4.16352878860, 0, 0], [4.452470820736, 4.16352878860, 0, 0]],
+                 [3.95750374663, 4.62489238836, 0.617477263873, 1.28261294568],
+                 [[0, 0, 0, 0], [-5.07167533877, 0, 0, 0], [6.02015272865, 0.1597500684673, 0, 0],
+                  [-1.856343618677, -8.50538085819, -2.08407513602, 0]]),
+    "ode4s_s": (0.5,
+                [[0, 0, 0, 0], [2, 0, 0, 0], [48 / 25, 6 / 25, 0, 0], [48 / 25, 6 / 25, 0, 0]],
+                [19 / 9, 1 / 2, 25 / 108, 125 / 108],
+                [[0, 0, 0, 0], [-8, 0, 0, 0], [372 / 25, 12 / 5, 0, 0], [-112 / 125, -54 / 125, -2 / 5, 0]]),
+}
+ROS["ode4s"] = ROS["ode4s_s"]
+
+
+def oderosenbrock(F, x0, tspan, method, jac=None):
+    """src/ODE.jl:366-404."""
+    gamma, a, b, c = ROS[method]
+    F = Counted(F)
+    tspan = [float(v) for v in tspan]
+    xs_all = [[float(v) for v in x0]]
+    n = len(x0)
+    for st in range(len(tspan) - 1):
+        ts, hs = tspan[st], tspan[st + 1] - tspan[st]
+        xs = xs_all[st]
+        J = jac(ts, xs) if jac is not None else fdjacobian(F, xs, ts)
+        lam = 1.0 / (gamma * hs)
+        W = [[(-J[i][j] + lam) if i == j else -J[i][j] for j in range(n)] for i in range(n)]
+        lu = lu_factor(W)
+        g = [lu_solve(lu, F(ts + b[0] * hs, xs))]
+        xn = [xs[d] + b[0] * g[0][d] for d in range(n)]
+        for i in range(1, 4):
+            dx = [0.0] * n
+            dF = [0.0] * n
+            for j in range(i):
+                for d in range(n):
+                    dx[d] += a[i][j] * g[j][d]
+                    dF[d] += c[i][j] * g[j][d]
+            f = F(ts + b[i] * hs, [xs[d] + dx[d] for d in range(n)])
+            g.append(lu_solve(lu, [f[d] + dF[d] / hs for d in range(n)]))
+            for d in range(n):
+                xn[d] += b[i] * g[i][d]
+        xs_all.append(xn)
+    return dict(t=tspan, y=xs_all, n_rhs=F.n)
+
+
+def ode4ms(F, x0, tspan):
+    """ode_ms with order 4, src/ODE.jl:175-212."""
+    b = [[1, 0, 0, 0], [-1 / 2, 3 / 2, 0, 0], [5 / 12, -4 / 3, 23 / 12, 0], [-9 / 24, 37 / 24, -59 / 24, 55 / 24]]
+    F = Counted(F)
+    tspan = [float(v) for v in tspan]
+    x = [[float(v) for v in x0]]
+    xdot = []
+    for i in range(len(tspan) - 1):
+        h = tspan[i + 1] - tspan[i]
+        so = min(i + 1, 4)
+        xdot.append(F(tspan[i], x[i]))
+        xn = list(x[i])
+        for j in range(so):
+            xd = xdot[i - (so - 1) + j]
+            for d in range(len(xn)):
+                xn[d] += h * b[so - 1][j] * xd[d]
+        x.append(xn)
+    return dict(t=tspan, y=x, n_rhs=F.n)
+
+
+def solve(method, rhs, y0, tspan, params=None, jacobian=0, **kw):
     F = rhs_factory(rhs, params)
+    if method in ROS:
+        return oderosenbrock(F, y0, tspan, method, jac_factory(rhs, params) if jacobian else None)
+    if method == "ode4ms":
+        return ode4ms(F, y0, tspan)
     if method == "ode23s":
-        return ode23s(F, y0, tspan, **kw)
+        return ode23s(F, y0, tspan, jac=jac_factory(rhs, params) if jacobian else None, **kw)
     if Tab(method).adaptive:
         return oderk_adapt(F, y0, tspan, method, **kw)
     return oderk_fixed(F, y0, tspan, method)

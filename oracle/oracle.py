@@ -16,7 +16,7 @@ _SO = os.path.join(_HERE, "libode_oracle.so")
 # ids, as include/ode_b200.h
 METHODS = dict(ode1=0, feuler=0, ode2_midpoint=1, midpoint=1, ode2_heun=2, heun=2, ode4=3, rk4=3,
                ode21=4, rk21=4, ode23=5, rk23=5, ode45_fe=6, rk45=6, ode45=7, ode45_dp=7, dopri5=7,
-               ode78=8, feh78=8, ode23s=9)
+               ode78=8, feh78=8, ode23s=9, ode4s=10, ode4s_s=10, ode4s_kr=11, ode4ms=12)
 RHS = dict(linear=0, const=1, timelin=2, rotation=3, lorenz=4, vdp=5, robertson=6, kepler=7,
            reaction_diffusion=8)
 POINTS = dict(all=0, specified=1, final=2)
@@ -94,7 +94,7 @@ def _ip(a):
 
 
 def make_opts(method, rhs, dof, params, tspan, *, reltol=1e-5, abstol=1e-8, minstep=None, maxstep=None, initstep=0.0,
-              points="all", mathmode=0, max_steps=0, params_stride=0):
+              points="all", mathmode=0, max_steps=0, params_stride=0, jacobian=0):
     """Options with the reference's defaults (src/runge_kutta.jl:233-239)."""
     span = abs(float(tspan[-1]) - float(tspan[0]))
     o = Opts()
@@ -104,7 +104,7 @@ def make_opts(method, rhs, dof, params, tspan, *, reltol=1e-5, abstol=1e-8, mins
     o.n_params = 0 if params is None else int(np.asarray(params).shape[-1])
     o.params_stride = int(params_stride)
     o.points = POINTS[points] if isinstance(points, str) else int(points)
-    o.jacobian = 0
+    o.jacobian = int(jacobian)
     o.device = 0
     o.max_steps = int(max_steps)
     o.reltol = float(reltol)

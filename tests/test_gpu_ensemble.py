@@ -160,7 +160,7 @@ def test_fixed_step_bit_exact(method):
         assert np.array_equal(got["y_final"][i], oi.y[-1])
 
 
-ALL = FIXED + ADAPTIVE + ["ode23s"]
+ALL = FIXED + ["ode4ms"] + ADAPTIVE + ["ode4s_s", "ode4s_kr", "ode4s", "ode23s"]
 
 
 @pytest.mark.parametrize("solver", ALL)
@@ -249,3 +249,46 @@ def test_chunked_host_path_matches_oracle_at_chunk_boundaries():
     ref = O.solve_ensemble("ode45", "lorenz", y0[idx], [0.0, 1.0], LORENZ)
     for k in ("y_final", "t_final", "n_accept", "n_reject", "n_rhs", "status"):
         assert np.array_equal(got[k][idx], ref[k]), k
+
+
+@pytest.mark.parametrize("method", ["ode4s_s", "ode4s_kr", "ode4ms"])
+@pytest.mark.parametrize("jacobian", [False, True])
+def test_rosenbrock_fixed_and_adams_bashforth_bit_exact(method, jacobian):
+    """oderosenbrock (src/ODE.jl:366-438) and ode4ms (:175-212) on the tspan grid, all points."""
+    if method == "ode4ms" and jacobian:
+        pytest.skip("no Jacobian in Adams-Bashforth")
+    ts = np.linspace(0.0, 1.0, 101)
+    kw = dict(jacobian=True) if jacobian else {}
+    for rhs, y0, p in (("lorenz", [1.0, 1.0, 1.0], LORENZ), ("kepler", [0.4, 0.0, 0.0, 2.0], []), ("vdp", [2.0, 0.0], [5.0])):
+        t, y, st = getattr(m, method).stats(m.DeviceRHS(rhs, *p), y0, ts, **kw)
+        o = O.solve(method, rhs, y0, ts, p if p else None, jacobian=int(jacobian))
+        assert np.array_equal(t, o.t) and np.array_equal(y, o.y) and st["n_rhs"] == o.n_rhs
+    n = 300
+    y0 = lorenz_ics(n, 8)
+    got = m.solve_ensemble(method, m.DeviceRHS("lorenz", *LORENZ), y0, ts, **kw)
+    ref = O.solve_ensemble(method, "lorenz", y0, ts, LORENZ, jacobian=int(jacobian))
+    assert_same(got, ref)
+
+
+def test_ode23s_analytic_jacobian_bit_exact():
+    rng = np.random.default_rng(4)
+    n = 256
+    k = np.array([0.04, 3e7, 1e4]) * 10 ** rng.uniform(-0.5, 0.5, (n, 3))
+    y0 = np.tile([1.0, 0.0, 0.0], (n, 1))
+    kw = dict(reltol=1e-8, abstol=1e-8)
+    got = m.solve_ensemble("ode23s", m.DeviceRHS("robertson", 0.04, 3e7, 1e4), y0, [0.0, 1e4], params=k, jacobian=True, **kw)
+    ref = O.solve_ensemble("ode23s", "robertson", y0, [0.0, 1e4], k, jacobian=1, **kw)
+    assert_same(got, ref)
+    fd = m.solve_ensemble("ode23s", m.DeviceRHS("robertson", 0.04, 3e7, 1e4), y0, [0.0, 1e4], params=k, **kw)
+    assert np.all(got["n_rhs"] < fd["n_rhs"])  # no dof+1 RHS calls per accepted step
+    t, y = m.ode23s(m.DeviceRHS("vdp", 10.0), [2.0, 0.0], [0.0, 1.0, 3.0], jacobian=True)
+    o = O.solve("ode23s", "vdp", [2.0, 0.0], [0.0, 1.0, 3.0], [10.0], jacobian=1)
+    assert np.array_equal(t, o.t) and np.array_equal(y, o.y)
+
+
+def test_solve_common_interface_ode4s_ode4ms():
+    """test/common.jl:8: algs = [ode23(), ode45(), ode78(), ode4(), ode4ms(), ode4s()]."""
+    prob = m.ODEProblem(m.DeviceRHS("linear", 1.01), 0.5, (0.0, 1.0))
+    for alg in (m.ode4(), m.ode4ms(), m.ode4s()):
+        sol = m.solve(prob, alg, dt=1 / 16, abstol=1e-6, reltol=1e-3)
+        assert sol.retcode == "Succss" and isinstance(float(sol[1]), float)

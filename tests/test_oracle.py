@@ -52,7 +52,7 @@ def test_tableau_matches_reference_source(name):
     assert pt.fsal == t["fsal"]
 
 
-ALL_SOLVERS = FIXED + ADAPTIVE + ["ode23s"]
+ALL_SOLVERS = FIXED + ["ode4ms"] + ADAPTIVE + ["ode4s_s", "ode4s_kr", "ode23s"]  # test/runtests.jl:5-25 minus ode5ms
 
 
 @pytest.mark.parametrize("solver", ALL_SOLVERS)
@@ -191,3 +191,42 @@ def test_ensemble_matches_single():
         assert np.array_equal(s.y[-1], e["y_final"][i]) and s.n_accept == e["n_accept"][i]
         s2 = O.solve("ode45", "lorenz", y0[i], [0.0, 1.0], LORENZ, points="all")
         assert np.array_equal(s2.y[-1], e["y_final"][i]) and s2.t[-1] == e["t_final"][i]
+
+
+@pytest.mark.parametrize("method", ["ode4s_s", "ode4s_kr", "ode4ms"])
+@pytest.mark.parametrize("jacobian", [0, 1])
+def test_cpp_equals_python_bitwise_rosenbrock_and_multistep(method, jacobian):
+    """oderosenbrock (src/ODE.jl:366-404) and ode_ms order 4 (:175-212): C++ and Python restatements agree bit for bit."""
+    if method == "ode4ms" and jacobian:
+        pytest.skip("no Jacobian in Adams-Bashforth")
+    ts = np.linspace(0, 1, 101)
+    for rhs, y0, p in (("lorenz", [1.0, 1.0, 1.0], LORENZ), ("kepler", [0.4, 0.0, 0.0, 2.0], None),
+                       ("vdp", [2.0, 0.0], [5.0]), ("linear", [1.0], [1.0])):
+        c = O.solve(method, rhs, y0, ts, p, jacobian=jacobian)
+        q = P.solve(method, rhs, y0, ts, p, jacobian=jacobian)
+        assert np.array_equal(c.y, np.array(q["y"])) and c.n_rhs == q["n_rhs"]
+
+
+def test_ode23s_analytic_jacobian_cpp_equals_python_and_rober():
+    """The `jacobian = G(t,y)` keyword (src/ODE.jl:262-267) with the registered analytic Jacobian."""
+    c = O.solve("ode23s", "robertson", [1.0, 0.0, 0.0], [0.0, 40.0], [0.04, 3e7, 1e4], jacobian=1, mathmode=1, trace=True)
+    q = P.solve("ode23s", "robertson", [1.0, 0.0, 0.0], [0.0, 40.0], [0.04, 3e7, 1e4], jacobian=1)
+    _same(c, q)
+    s = O.solve("ode23s", "robertson", [1.0, 0.0, 0.0], [0.0, 1e11], [0.04, 3e7, 1e4], abstol=1e-8, reltol=1e-8,
+                maxstep=1e10, minstep=1e-7, jacobian=1)
+    ref = np.array([0.2083340149701255e-07, 0.8333360770334713e-13, 0.9999999791665050])
+    assert np.max(np.abs(s.y[-1] - ref)) < 2e-10
+
+
+def test_analytic_jacobians_match_finite_differences():
+    rng = np.random.default_rng(5)
+    for rhs, p, d in (("lorenz", LORENZ, 3), ("vdp", [3.0], 2), ("robertson", [0.04, 3e7, 1e4], 3), ("kepler", None, 4),
+                      ("rotation", None, 2), ("linear", [1.01], 1)):
+        y = rng.uniform(0.2, 1.5, d)
+        J = np.array(P.jac_factory(rhs, p)(0.0, list(y)))
+        F = P.rhs_factory(rhs, p)
+        for j in range(d):
+            e = np.zeros(d)
+            e[j] = 1e-6 * max(1.0, abs(y[j]))
+            fd = (np.array(F(0.0, list(y + e))) - np.array(F(0.0, list(y - e)))) / (2 * e[j])
+            assert np.allclose(J[:, j], fd, rtol=1e-5, atol=1e-4 * max(1.0, np.abs(J).max()))

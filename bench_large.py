@@ -85,10 +85,11 @@ def run_large(args, rank, local_rank, world):
 
     e2e = None
     if world == 1:
-        yh = y0.cpu().pin_memory().numpy()  # pinned host buffer for the H2D leg
-        m.solve_large("ode45", F, yh, tspan)
+        yh = y0.cpu().pin_memory().numpy()  # pinned host buffers for both legs
+        outh = torch.empty(n_local, dtype=torch.float64).pin_memory().numpy()
+        m.solve_large("ode45", F, yh, tspan, out=outh)
         t0 = time.perf_counter()
-        r = m.solve_large("ode45", F, yh, tspan)
+        r = m.solve_large("ode45", F, yh, tspan, out=outh)
         e2e_s = time.perf_counter() - t0
         assert np.array_equal(r["y"], y.cpu().numpy())
         e2e = {"value": (r["n_accept"] + r["n_reject"]) / e2e_s, "unit": "steps/s", "h2d_bytes_per_step": yh.nbytes,

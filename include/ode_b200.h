@@ -200,6 +200,13 @@ int ode_b200_solve_large(const ode_b200_opts* opts, int64_t n, const double* y0,
                          double t0, double tend, double* y_out, ode_b200_large_stats* stats,
                          double* trace, int64_t trace_cap, int64_t* trace_n);
 
+/* Same with the reference's points = :specified contract (src/runge_kutta.jl:321-326): pts_y is
+ * [n_tspan][n]; row 0 is y0, the other rows are 3rd-order Hermite values (hermite_interp!, :479-492)
+ * at tspan[i], the last row at tspan[end]. */
+int ode_b200_solve_large_points(const ode_b200_opts* opts, int64_t n, const double* y0, const double* params,
+                                const double* tspan, int32_t n_tspan, double* pts_y, ode_b200_large_stats* stats,
+                                double* trace, int64_t trace_cap, int64_t* trace_n);
+
 /* Slab session for the domain-decomposed path: every rank owns n_local
  * contiguous points of an n_global periodic grid plus ghost cells; between the
  * two halves of an attempt the host exchanges `xchg_send` (ODE_B200_XCHG_DOUBLES
@@ -214,6 +221,9 @@ int ode_b200_slab_set_state(ode_b200_slab* s, const double* y_local_dev); /* [n_
 /* re-arm the session for another integration over [t0, tend] with the same options
  * (the reference is stateless: a restart is a new call); follow with set_state */
 int ode_b200_slab_reset(ode_b200_slab* s, double t0, double tend);
+/* points = :specified output: tspan (host, n_tspan entries) and a device buffer [n_tspan][n_local];
+ * call before set_state (which writes row 0 = y0).  NULL disables. */
+int ode_b200_slab_set_output(ode_b200_slab* s, const double* tspan_host, int32_t n_tspan, double* out_dev);
 /* optional attempt trace on the device: rows (t, dt, err, accepted) */
 int ode_b200_slab_set_trace(ode_b200_slab* s, double* trace_dev, int64_t trace_cap);
 int ode_b200_slab_get_state(ode_b200_slab* s, double* y_local_dev);

@@ -63,6 +63,12 @@ def lib():
     global _lib
     if _lib is not None:
         return _lib
+    if not os.path.exists(LIB_PATH) and not os.environ.get("ODE_B200_LIB"):
+        # compile the CUDA library in-tree if a toolchain is present (nvcc cross-compiles without a GPU)
+        import shutil
+        import subprocess
+        if shutil.which("nvcc") and shutil.which("make"):
+            subprocess.call(["make", "-C", os.path.join(_HERE, "csrc"), "-j", str(min(16, os.cpu_count() or 1)), "-s"])
     if not os.path.exists(LIB_PATH):
         raise ImportError("%s not found: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
                           "or `make -C ode.jl_b200/csrc`; there is no CPU fallback" % LIB_PATH)
@@ -95,6 +101,9 @@ def lib():
     L.ode_b200_result_free.restype = None
     L.ode_b200_solve_large.argtypes = [C.POINTER(Opts), C.c_int64, dp, dp, C.c_double, C.c_double, dp,
                                        C.POINTER(LargeStats), dp, C.c_int64, lp]
+    L.ode_b200_solve_large_points.argtypes = [C.POINTER(Opts), C.c_int64, dp, dp, dp, C.c_int32, dp,
+                                              C.POINTER(LargeStats), dp, C.c_int64, lp]
+    L.ode_b200_slab_set_output.argtypes = [C.c_void_p, dp, C.c_int32, C.c_void_p]
     L.ode_b200_slab_create.argtypes = [C.POINTER(Opts), C.c_int64, C.c_int64, C.c_int32, C.c_int32, dp, C.c_double,
                                        C.c_double, C.c_void_p, C.POINTER(C.c_void_p)]
     L.ode_b200_slab_set_state.argtypes = [C.c_void_p, C.c_void_p]

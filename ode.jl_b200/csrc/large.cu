@@ -69,8 +69,20 @@ __global__ void large_control_kernel(const ControlArgs C) {
     }
     ctl->trace_n += 1;
     ctl->accepted_last = accept ? 1 : 0;
+    ctl->out_lo = ctl->out_hi = 0;
     if (accept) {
       ctl->nacc += 1;
+      if (C.tq) {  // :321-326  output at all new times which are < t+dt (all remaining ones on the last step)
+        int it = ctl->out_iter;  // 1-based index into tspan, like the reference's `iter`
+        const int lo = it - 1;
+        while (it - 1 < C.n_tq && (tdir * C.tq[it - 1] < tdir * (t + dt) || ctl->islast)) it++;
+        ctl->out_lo = lo;
+        ctl->out_hi = it - 1;
+        ctl->out_iter = it;
+        ctl->out_t = t;
+        ctl->out_dt = dt;
+        ctl->out_par = ctl->par;  // y, k1 of the step start live in Y/K[out_par]; ytrial, f1 in the other pair
+      }
       ctl->par ^= 1;  // y <-> ytrial, k1 <-> k_next  (:341,:347)
       if (ctl->islast) {
         ctl->t_final = t + dt;
@@ -123,6 +135,30 @@ __global__ void large_control_kernel(const ControlArgs C) {
     Yp[C.n + H + j] = xr[j];
     Kp[j] = xl[3 * H + j];
     Kp[C.n + H + j] = xr[2 * H + j];
+  }
+}
+
+// hermite_interp! (src/runge_kutta.jl:479-492) for the tspan rows the control kernel selected.
+__global__ void __launch_bounds__(256) large_hermite_kernel(double* const Y0, double* const Y1, double* const K0,
+                                                            double* const K1, const LargeCtl* ctl, const double* tq,
+                                                            double* out, long long n, int H) {
+  const int lo = ctl->out_lo, hi = ctl->out_hi;
+  if (hi <= lo) return;
+  const int par = ctl->out_par;
+  const double* y0 = (par ? Y1 : Y0) + H;
+  const double* y1 = (par ? Y0 : Y1) + H;
+  const double* f0 = (par ? K1 : K0) + H;
+  const double* f1 = (par ? K0 : K1) + H;
+  const double t = ctl->out_t, dt = ctl->out_dt;
+  for (int q = lo; q < hi; q++) {
+    const double theta = (tq[q] - t) / dt;  // :486
+    double* o = out + (long long)q * n;
+    for (long long i = blockIdx.x * 256LL + threadIdx.x; i < n; i += (long long)gridDim.x * 256) {
+      const double a = y0[i], b = y1[i];
+      o[i] = ((1.0 - theta) * a + theta * b) +
+             (theta * (theta - 1.0)) *
+                 (((1.0 - 2.0 * theta) * (b - a) + ((theta - 1.0) * dt) * f0[i]) + (theta * dt) * f1[i]);  // :488-489
+    }
   }
 }
 
@@ -242,6 +278,8 @@ __global__ void hinit_control_kernel(LargeCtl* ctl, const double* xrecv, int wor
     ctl->timeout = 0;
     ctl->nrhs = 2;
     ctl->t_final = ctl->tstart;
+    ctl->out_iter = 2;  // :304
+    ctl->out_lo = ctl->out_hi = 0;
   }
 }
 
@@ -299,6 +337,9 @@ struct ode_b200_slab {
   double *part = nullptr, *ipart = nullptr;
   double* trace = nullptr;
   long long trace_cap = 0;
+  double* tq = nullptr;   // device copy of tspan for points = :specified
+  int n_tq = 0;
+  double* out = nullptr;  // [n_tq][n] device, caller owned
   double p0 = 0, p1 = 0;
   int init_blocks = 0;
   LargeCtl host_ctl;
@@ -335,9 +376,7 @@ int ode_b200_slab_create(const ode_b200_opts* o, int64_t n_local, int64_t n_glob
   if (n_local < 2 * mi.H || n_global < 32 || n_local > n_global)
     return set_err(ODE_B200_E_INVALID, "slab too small: n_local %lld (needs >= %d), n_global %lld (needs >= 32)",
                    (long long)n_local, 2 * mi.H, (long long)n_global);
-  if (o->points == ODE_B200_POINTS_SPECIFIED)
-    return set_err(ODE_B200_E_UNSUPPORTED, "points=:specified is not available on the large-system path yet");
-  if (o->points != ODE_B200_POINTS_ALL && o->points != ODE_B200_POINTS_FINAL)
+  if (o->points != ODE_B200_POINTS_ALL && o->points != ODE_B200_POINTS_FINAL && o->points != ODE_B200_POINTS_SPECIFIED)
     return set_err(ODE_B200_E_POINTS, "Unrecognized option points==%d", o->points);
   if (!(t0 == t0) || !(tend == tend)) return set_err(ODE_B200_E_INVALID, "NaN in tspan");
   const double tdir = tend > t0 ? 1.0 : (tend < t0 ? -1.0 : 0.0);
@@ -445,6 +484,26 @@ int ode_b200_slab_set_state(ode_b200_slab* s, const double* y_local_dev) {
   int rc = slab_check(s);
   if (rc) return rc;
   ODEB200_CUDA(cudaMemcpyAsync(s->Y[0] + s->mi.H, y_local_dev, (size_t)s->n * 8, cudaMemcpyDeviceToDevice, s->stream));
+  if (s->out)  // ys[1] = y0, src/runge_kutta.jl:280
+    ODEB200_CUDA(cudaMemcpyAsync(s->out, y_local_dev, (size_t)s->n * 8, cudaMemcpyDeviceToDevice, s->stream));
+  return 0;
+}
+
+int ode_b200_slab_set_output(ode_b200_slab* s, const double* tspan_host, int32_t n_tspan, double* out_dev) {
+  int rc = slab_check(s);
+  if (rc) return rc;
+  if (s->tq) {
+    cudaFree(s->tq);
+    s->tq = nullptr;
+  }
+  s->n_tq = 0;
+  s->out = nullptr;
+  if (!tspan_host || n_tspan < 2 || !out_dev) return 0;  // output disabled
+  ODEB200_CUDA(cudaMalloc(&s->tq, (size_t)n_tspan * 8));
+  ODEB200_CUDA(cudaMemcpyAsync(s->tq, tspan_host, (size_t)n_tspan * 8, cudaMemcpyHostToDevice, s->stream));
+  ODEB200_CUDA(cudaStreamSynchronize(s->stream));
+  s->n_tq = n_tspan;
+  s->out = out_dev;
   return 0;
 }
 int ode_b200_slab_get_state(ode_b200_slab* s, double* y_local_dev) {
@@ -533,8 +592,15 @@ int ode_b200_slab_control(ode_b200_slab* s, const double* xrecv) {
   C.world = s->world;
   C.H = s->mi.H;
   C.order = s->mi.order;
+  C.tq = s->out ? s->tq : nullptr;
+  C.n_tq = s->n_tq;
   large_control_kernel<<<1, 32, 0, s->stream>>>(C);
   note_launch();
+  if (s->out) {  // before the next attempt overwrites the step-start arrays
+    large_hermite_kernel<<<s->init_blocks, 256, 0, s->stream>>>(s->Y[0], s->Y[1], s->K[0], s->K[1], s->ctl, s->tq,
+                                                                 s->out, s->n, s->mi.H);
+    note_launch();
+  }
   ODEB200_CUDA(cudaGetLastError());
   return 0;
 }
@@ -574,13 +640,33 @@ void ode_b200_slab_free(ode_b200_slab* s) {
   if (s->ctl) cudaFree(s->ctl);
   if (s->part) cudaFree(s->part);
   if (s->ipart) cudaFree(s->ipart);
+  if (s->tq) cudaFree(s->tq);
   delete s;
 }
+
+static int solve_large_impl(const ode_b200_opts* o, int64_t n, const double* y0, const double* params,
+                            const double* tspan, int32_t n_tspan, double* y_out, double* pts_out,
+                            ode_b200_large_stats* stats, double* trace, int64_t trace_cap, int64_t* trace_n);
 
 int ode_b200_solve_large(const ode_b200_opts* o, int64_t n, const double* y0, const double* params, double t0,
                          double tend, double* y_out, ode_b200_large_stats* stats, double* trace, int64_t trace_cap,
                          int64_t* trace_n) {
+  const double ts[2] = {t0, tend};
+  return solve_large_impl(o, n, y0, params, ts, 2, y_out, nullptr, stats, trace, trace_cap, trace_n);
+}
+
+int ode_b200_solve_large_points(const ode_b200_opts* o, int64_t n, const double* y0, const double* params,
+                                const double* tspan, int32_t n_tspan, double* pts_y, ode_b200_large_stats* stats,
+                                double* trace, int64_t trace_cap, int64_t* trace_n) {
+  if (!tspan || n_tspan < 2 || !pts_y) return set_err(ODE_B200_E_INVALID, "tspan (>= 2 entries) and pts_y are required");
+  return solve_large_impl(o, n, y0, params, tspan, n_tspan, nullptr, pts_y, stats, trace, trace_cap, trace_n);
+}
+
+static int solve_large_impl(const ode_b200_opts* o, int64_t n, const double* y0, const double* params,
+                            const double* tspan, int32_t n_tspan, double* y_out, double* pts_out,
+                            ode_b200_large_stats* stats, double* trace, int64_t trace_cap, int64_t* trace_n) {
   if (!o || !y0) return set_err(ODE_B200_E_INVALID, "null argument");
+  const double t0 = tspan[0], tend = tspan[n_tspan - 1];
   int cnt = 0;
   if (cudaGetDeviceCount(&cnt) != cudaSuccess || cnt <= 0) {
     cudaGetLastError();
@@ -592,7 +678,7 @@ int ode_b200_solve_large(const ode_b200_opts* o, int64_t n, const double* y0, co
   ODEB200_CUDA(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
   ode_b200_slab* s = nullptr;
   int rc = ode_b200_slab_create(o, n, n, 0, 1, params, t0, tend, st, &s);
-  double *dy = nullptr, *xs = nullptr, *xr = nullptr, *dtrace = nullptr;
+  double *dy = nullptr, *xs = nullptr, *xr = nullptr, *dtrace = nullptr, *dpts = nullptr;
   cudaEvent_t e0 = nullptr, e1 = nullptr;
   double poll[12] = {0};
 #define LARGE_TRY(x)  \
@@ -613,6 +699,10 @@ int ode_b200_solve_large(const ode_b200_opts* o, int64_t n, const double* y0, co
   if (trace && trace_cap > 0) {
     LARGE_CUDA(cudaMalloc(&dtrace, (size_t)trace_cap * 32));
     LARGE_TRY(ode_b200_slab_set_trace(s, dtrace, trace_cap));
+  }
+  if (pts_out) {
+    LARGE_CUDA(cudaMalloc(&dpts, (size_t)n_tspan * n * 8));
+    LARGE_TRY(ode_b200_slab_set_output(s, tspan, n_tspan, dpts));
   }
   LARGE_CUDA(cudaMemcpyAsync(dy, y0, (size_t)n * 8, cudaMemcpyHostToDevice, st));
   LARGE_TRY(ode_b200_slab_set_state(s, dy));
@@ -635,6 +725,7 @@ int ode_b200_solve_large(const ode_b200_opts* o, int64_t n, const double* y0, co
   LARGE_CUDA(cudaEventRecord(e1, st));
   LARGE_TRY(ode_b200_slab_get_state(s, dy));
   if (y_out) LARGE_CUDA(cudaMemcpyAsync(y_out, dy, (size_t)n * 8, cudaMemcpyDeviceToHost, st));
+  if (pts_out && dpts) LARGE_CUDA(cudaMemcpyAsync(pts_out, dpts, (size_t)n_tspan * n * 8, cudaMemcpyDeviceToHost, st));
   if (trace && dtrace) {
     long long tn = (long long)poll[10];
     long long m = tn < trace_cap ? tn : trace_cap;
@@ -658,6 +749,7 @@ int ode_b200_solve_large(const ode_b200_opts* o, int64_t n, const double* y0, co
   if (xs) cudaFree(xs);
   if (xr) cudaFree(xr);
   if (dtrace) cudaFree(dtrace);
+  if (dpts) cudaFree(dpts);
   ode_b200_slab_free(s);
   cudaStreamDestroy(st);
   return rc;

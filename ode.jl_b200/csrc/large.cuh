@@ -67,6 +67,10 @@ struct LargeCtl {
   int islast, timeout, done, status, accepted_last;
   unsigned int blocks_done;  // last-CTA-done counter of the attempt kernel
   int order;
+  // points = :specified (src/runge_kutta.jl:321-326): tspan rows [out_lo, out_hi) are to be
+  // Hermite-interpolated over the step (out_t, out_t + out_dt) that was just accepted
+  int out_iter, out_lo, out_hi, out_par;
+  double out_t, out_dt;
 };
 
 struct LargeArgs {
@@ -413,8 +417,9 @@ struct ControlArgs {
   LargeCtl* ctl;
   const double* xrecv;
   double* trace;
+  const double* tq;  // output times (the reference's tspan), device; nullptr = no points output
   long long n;
-  int rank, world, H, order;
+  int rank, world, H, order, n_tq;
 };
 
 __global__ void large_control_kernel(const ControlArgs C);

@@ -32,8 +32,9 @@ def shard_bounds(n_global, world, rank):
     return lo, lo + base + (1 if rank < rem else 0)
 
 
-def solve_large(alg, F, y0, tspan, *, trace=False, trace_cap=65536, **kw):
-    """One GPU, host buffers in and out.  Returns dict(y, t_final, n_accept, n_reject, n_rhs, status, kernel_ms[, trace])."""
+def solve_large(alg, F, y0, tspan, *, trace=False, trace_cap=65536, out=None, **kw):
+    """One GPU, host buffers in and out.  Returns dict(y, t_final, n_accept, n_reject, n_rhs, status, kernel_ms[, trace]).
+    `out` (optional) is a caller-owned float64 array for the final state, e.g. pinned memory."""
     if not isinstance(F, DeviceRHS) or F.name != "reaction_diffusion":
         raise TypeError("the large-system path takes DeviceRHS('reaction_diffusion', kappa, r)")
     y0 = np.ascontiguousarray(np.asarray(y0, dtype=np.float64))
@@ -41,19 +42,32 @@ def solve_large(alg, F, y0, tspan, *, trace=False, trace_cap=65536, **kw):
     kw.setdefault("points", "final")
     o = make_opts(_alg_name(alg), F, ts, dof=min(y0.size, 2 ** 31 - 1), **kw)
     p = F.param_array()
-    out = np.empty_like(y0)
+    if out is None:
+        out = np.empty_like(y0)
+    elif out.dtype != np.float64 or out.size != y0.size or not out.flags.c_contiguous:
+        raise ValueError("out must be a C-contiguous float64 array of y0's size")
     st = LargeStats()
     tr = np.zeros((trace_cap, 4)) if trace else None
     tn = C.c_int64(0)
     dp = _lib.dp
+    specified = o.points == _lib.POINTS["specified"]
     try:
-        check(lib().ode_b200_solve_large(C.byref(o), y0.size, y0.ctypes.data_as(dp), p.ctypes.data_as(dp),
-                                         float(ts[0]), float(ts[-1]), out.ctypes.data_as(dp), C.byref(st),
-                                         tr.ctypes.data_as(dp) if trace else None, trace_cap if trace else 0,
-                                         C.byref(tn)))
+        if specified:  # tout = tspan, yout[i] = Hermite value at tspan[i] (src/runge_kutta.jl:321-326)
+            ts = np.ascontiguousarray(ts)
+            pts = np.empty((ts.size, y0.size))
+            check(lib().ode_b200_solve_large_points(C.byref(o), y0.size, y0.ctypes.data_as(dp), p.ctypes.data_as(dp),
+                                                    ts.ctypes.data_as(dp), ts.size, pts.ctypes.data_as(dp),
+                                                    C.byref(st), tr.ctypes.data_as(dp) if trace else None,
+                                                    trace_cap if trace else 0, C.byref(tn)))
+            out = pts
+        else:
+            check(lib().ode_b200_solve_large(C.byref(o), y0.size, y0.ctypes.data_as(dp), p.ctypes.data_as(dp),
+                                             float(ts[0]), float(ts[-1]), out.ctypes.data_as(dp), C.byref(st),
+                                             tr.ctypes.data_as(dp) if trace else None, trace_cap if trace else 0,
+                                             C.byref(tn)))
     except _lib.OdeB200Error as e:
         _raise_like_reference(e)
-    res = dict(y=out, t_final=st.t_final, n_accept=st.n_accept, n_reject=st.n_reject, n_rhs=st.n_rhs,
+    res = dict(y=out, t=ts if specified else None, t_final=st.t_final, n_accept=st.n_accept, n_reject=st.n_reject, n_rhs=st.n_rhs,
                status=st.status, kernel_ms=st.kernel_ms)
     if trace:
         res["trace"] = tr[:min(tn.value, trace_cap)]
@@ -85,6 +99,11 @@ class CudaSlabEngine:
 
     def get_state(self, dev_ptr):
         check(self.L.ode_b200_slab_get_state(self.h, C.c_void_p(dev_ptr)))
+
+    def set_output(self, tspan, out_dev_ptr):
+        """points=:specified rows [len(tspan), n_local] into a device buffer; call before set_state."""
+        ts = np.ascontiguousarray(np.asarray(tspan, dtype=np.float64))
+        check(self.L.ode_b200_slab_set_output(self.h, ts.ctypes.data_as(_lib.dp), ts.size, C.c_void_p(out_dev_ptr)))
 
     def set_trace(self, dev_ptr, cap):
         check(self.L.ode_b200_slab_set_trace(self.h, C.c_void_p(dev_ptr), int(cap)))

@@ -150,3 +150,17 @@ def test_large_error_paths():
         m.solve_large("ode45", F, u0(8), [0.0, 1.0])
     got = m.solve_large("ode45", F, u0(4096), [0.0, 20.0], max_steps=7)
     assert got["status"] == 2 and got["n_accept"] + got["n_reject"] == 7
+
+
+@pytest.mark.parametrize("method", ["ode45", "ode23"])
+def test_large_points_specified_bit_exact(method):
+    """points=:specified on the large system: Hermite rows at interior tspan points (src/runge_kutta.jl:321-326,479-492)."""
+    n = 6000
+    y0 = u0(n)
+    ts = [0.0, 0.013, 0.5, 0.51, 3.0, 7.5, 10.0]
+    got = m.solve_large(method, m.DeviceRHS("reaction_diffusion", *RD), y0, ts, points="specified", trace=True)
+    ref = O.solve(method, "reaction_diffusion", y0, ts, RD, trace=True, points="specified")
+    assert got["y"].shape == (len(ts), n)
+    assert np.array_equal(got["trace"], ref.trace)
+    assert np.array_equal(got["y"], ref.y)
+    assert np.array_equal(got["t"], ref.t)

@@ -18,7 +18,8 @@ const LIB = Ref{String}(get(ENV, "ODE_B200_LIB", joinpath(@__DIR__, "..", "ode.j
 
 # ---- ids (include/ode_b200.h) -------------------------------------------------------------------
 const METHODS = Dict(:ode1=>0, :ode2_midpoint=>1, :ode2_heun=>2, :ode4=>3, :ode21=>4, :ode23=>5,
-                     :ode45_fe=>6, :ode45_dp=>7, :ode45=>7, :ode78=>8, :ode23s=>9)
+                     :ode45_fe=>6, :ode45_dp=>7, :ode45=>7, :ode78=>8, :ode23s=>9,
+                     :ode4s=>10, :ode4s_s=>10, :ode4s_kr=>11, :ode4ms=>12)
 const RHS = Dict(:linear=>0, :const=>1, :timelin=>2, :rotation=>3, :lorenz=>4, :vdp=>5,
                  :robertson=>6, :kepler=>7, :reaction_diffusion=>8)
 const POINTS = Dict(:all=>0, :specified=>1, :final=>2)
@@ -72,12 +73,14 @@ function _solve(method::Symbol, F::DeviceRHS, y0, tspan;
                 reltol = 1.0e-5, abstol = 1.0e-8,
                 minstep = abs(tspan[end] - tspan[1])/1e18,     # src/runge_kutta.jl:235
                 maxstep = abs(tspan[end] - tspan[1])/2.5,      # :236
-                initstep = 0.0, points = :all, device = 0)
+                initstep = 0.0, points = :all, jacobian = nothing, device = 0)
     haskey(POINTS, points) || error("Unrecognized option points==$points")   # :289
     scalar = !(y0 isa AbstractVector)
     y = scalar ? Float64[y0] : convert(Vector{Float64}, y0)
     ts = convert(Vector{Float64}, collect(tspan))
-    o = Ref(Opts(METHODS[method], rhs_id(F), length(y), length(F.params), 0, POINTS[points], 0, device, 0,
+    # jacobian = true selects the registered analytic Jacobian of F (a closure cannot run on the device)
+    o = Ref(Opts(METHODS[method], rhs_id(F), length(y), length(F.params), 0, POINTS[points],
+                 jacobian === true ? 1 : 0, device, 0,
                  reltol, abstol, minstep, maxstep, initstep, 0, ntuple(_ -> Int32(0), 7)))
     h = Ref{Ptr{Cvoid}}(C_NULL)
     GC.@preserve y ts F begin
@@ -96,7 +99,8 @@ function _solve(method::Symbol, F::DeviceRHS, y0, tspan;
     return tout, yout
 end
 
-for name in (:ode1, :ode2_midpoint, :ode2_heun, :ode4, :ode21, :ode23, :ode45_fe, :ode45_dp, :ode45, :ode78, :ode23s)
+for name in (:ode1, :ode2_midpoint, :ode2_heun, :ode4, :ode21, :ode23, :ode45_fe, :ode45_dp, :ode45, :ode78, :ode23s,
+             :ode4s, :ode4s_s, :ode4s_kr, :ode4ms)
     @eval $name(F::DeviceRHS, y0, tspan; kw...) = _solve($(QuoteNode(name)), F, y0, tspan; kw...)
     @eval $name(F, y0, tspan; kw...) =
         error("libode_b200 takes a registered DeviceRHS; a Julia closure cannot run on the device (no CPU fallback)")

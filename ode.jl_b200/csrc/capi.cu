@@ -175,13 +175,15 @@ static int validate(const ode_b200_opts* o, const ode_b200_ensemble_io* io, doub
   return 0;
 }
 
-static EnsembleKernel pick_kernel(const ode_b200_opts* o, int mode) {
+static bool is_adaptive_rk(int method) { return method >= ODE_B200_M_RK21 && method <= ODE_B200_M_FEH78; }
+
+static EnsembleKernel pick_kernel(const ode_b200_opts* o, int mode, int literal = 0) {
   switch (o->method) {
-    case ODE_B200_M_RK21: return adapt_kernel_rk21(o->rhs, mode);
-    case ODE_B200_M_RK23: return adapt_kernel_rk23(o->rhs, mode);
-    case ODE_B200_M_RK45_FE: return adapt_kernel_rk45(o->rhs, mode);
-    case ODE_B200_M_DOPRI5: return adapt_kernel_dopri5(o->rhs, mode);
-    case ODE_B200_M_FEH78: return adapt_kernel_feh78(o->rhs, mode);
+    case ODE_B200_M_RK21: return adapt_kernel_rk21(o->rhs, mode, literal);
+    case ODE_B200_M_RK23: return adapt_kernel_rk23(o->rhs, mode, literal);
+    case ODE_B200_M_RK45_FE: return adapt_kernel_rk45(o->rhs, mode, literal);
+    case ODE_B200_M_DOPRI5: return adapt_kernel_dopri5(o->rhs, mode, literal);
+    case ODE_B200_M_FEH78: return adapt_kernel_feh78(o->rhs, mode, literal);
     case ODE_B200_M_ODE23S: return ode23s_kernel(o->rhs, mode, o->jacobian);
     case ODE_B200_M_ODE4S_S:
     case ODE_B200_M_ODE4S_KR: return rosenbrock_kernel(o->method, o->rhs, o->jacobian);
@@ -190,7 +192,9 @@ static EnsembleKernel pick_kernel(const ode_b200_opts* o, int mode) {
   }
 }
 
-// Launch on `stream` with device pointers.  `counter` is an 8-byte device word.
+// Launch on `stream` with device pointers.  `counter` points at 32 bytes of device scratch: the work
+// counter of the fast pass, the redo count, and the work counter of the literal pass.  io->status must
+// be non-null for the adaptive RK methods (the two passes communicate through it).
 static int launch_ensemble(const ode_b200_opts* o, const ode_b200_ensemble_io* io, unsigned long long* counter,
                            cudaStream_t stream, bool time_it) {
   const bool want_points = io->pts_y != nullptr || io->trace != nullptr;
@@ -227,6 +231,9 @@ static int launch_ensemble(const ode_b200_opts* o, const ode_b200_ensemble_io* i
   A.trace_cap = io->trace ? io->trace_cap : 0;
   A.trace_n = (long long*)io->trace_n;
   A.work_counter = counter;
+  A.redo_count = reinterpret_cast<int*>(counter + 1);
+  const bool two_pass = is_adaptive_rk(o->method);
+  if (two_pass && !A.status) return set_err(ODE_B200_E_INVALID, "internal: adaptive RK launch without a status buffer");
 
   int dev = 0, sms = 0, per_sm = 0;
   ODEB200_CUDA(cudaGetDevice(&dev));
@@ -237,7 +244,7 @@ static int launch_ensemble(const ode_b200_opts* o, const ode_b200_ensemble_io* i
   long long grid = (long long)sms * per_sm;  // persistent: every lane pulls work until the counter runs out
   if (need < grid) grid = need;
   if (grid < 1) grid = 1;
-  ODEB200_CUDA(cudaMemsetAsync(counter, 0, sizeof(unsigned long long), stream));
+  ODEB200_CUDA(cudaMemsetAsync(counter, 0, 4 * sizeof(unsigned long long), stream));
   if (time_it) {
     if (g_ev_dev != dev) {
       if (g_ev0) {
@@ -253,6 +260,21 @@ static int launch_ensemble(const ode_b200_opts* o, const ode_b200_ensemble_io* i
   k<<<(unsigned)grid, ENS_BLOCK, 0, stream>>>(A);
   note_launch();
   ODEB200_CUDA(cudaGetLastError());
+  if (two_pass) {
+    // literal pass: re-integrates the trajectories the fast pass marked ODE_B200_ST_REDO (non-finite trial
+    // state or error), multiplying every tableau coefficient like the reference; returns at once if none.
+    EnsembleKernel kl = pick_kernel(o, mode, 1);
+    if (!kl) return set_err(ODE_B200_E_UNSUPPORTED, "no literal kernel for method %d / rhs %d", o->method, o->rhs);
+    int per_sm_l = 1;
+    ODEB200_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm_l, kl, ENS_BLOCK, 0));
+    long long grid_l = (long long)sms * (per_sm_l < 1 ? 1 : per_sm_l);
+    if (need < grid_l) grid_l = need;
+    if (grid_l < 1) grid_l = 1;
+    A.work_counter = counter + 2;
+    kl<<<(unsigned)grid_l, ENS_BLOCK, 0, stream>>>(A);
+    note_launch();
+    ODEB200_CUDA(cudaGetLastError());
+  }
   if (time_it) {
     ODEB200_CUDA(cudaEventRecord(g_ev1, stream));
     g_ev_pending = true;
@@ -357,11 +379,24 @@ int ode_b200_solve_ensemble_dev(const ode_b200_opts* opts, const ode_b200_ensemb
   if (io->n_traj == 0) return 0;
   static thread_local unsigned long long* counter = nullptr;
   static thread_local int counter_dev = -1;
+  static thread_local int* status_scratch = nullptr;
+  static thread_local long long status_cap = 0;
   if (counter_dev != opts->device) {
     ODEB200_CUDA(cudaMalloc(&counter, 256));
     counter_dev = opts->device;
+    status_scratch = nullptr;
+    status_cap = 0;
   }
-  return launch_ensemble(opts, io, counter, (cudaStream_t)stream, true);
+  ode_b200_ensemble_io d = *io;
+  if (!d.status && is_adaptive_rk(opts->method)) {  // the fast and literal passes talk through `status`
+    if (status_cap < io->n_traj) {
+      if (status_scratch) cudaFree(status_scratch);
+      ODEB200_CUDA(cudaMalloc(&status_scratch, (size_t)io->n_traj * sizeof(int)));
+      status_cap = io->n_traj;
+    }
+    d.status = status_scratch;
+  }
+  return launch_ensemble(opts, &d, counter, (cudaStream_t)stream, true);
 }
 
 int ode_b200_solve_ensemble(const ode_b200_opts* opts, const ode_b200_ensemble_io* io) {
@@ -397,7 +432,7 @@ int ode_b200_solve_ensemble(const ode_b200_opts* opts, const ode_b200_ensemble_i
   d.n_accept = io->n_accept ? g_arena.take<int>(n) : nullptr;
   d.n_reject = io->n_reject ? g_arena.take<int>(n) : nullptr;
   d.n_rhs = io->n_rhs ? g_arena.take<int>(n) : nullptr;
-  d.status = io->status ? g_arena.take<int>(n) : nullptr;
+  d.status = g_arena.take<int>(n);  // always: the fast and literal adaptive-RK passes talk through it
   if (pts) {
     d.pts_t = g_arena.take<double>((size_t)n * io->pts_cap);
     d.pts_y = g_arena.take<double>((size_t)n * io->pts_cap * D);
@@ -413,19 +448,18 @@ int ode_b200_solve_ensemble(const ode_b200_opts* opts, const ode_b200_ensemble_i
     d.trace_n = (int64_t*)dtrace_n;
     ODEB200_CUDA(cudaMemsetAsync(dtrace_n, 0, 8, st));
   }
-  // Large final-state ensembles are cut into chunks of 65536 trajectories on two streams, so the H2D
-  // of one chunk and the D2H of another overlap a running kernel, and (a chunk's persistent grid
-  // being smaller than the GPU) the lane-starved tail of one kernel overlaps the next kernel's
-  // start.  Measured on the 2^20-trajectory Lorenz run: 1 chunk 12.99 ms, 2: 12.68, 4: 13.33,
-  // 16: 12.46 ms end to end.  Results do not depend on the chunking; ODE_B200_CHUNKS overrides.
+  // Optional chunk pipeline (ODE_B200_CHUNKS=k): the ensemble is cut into k chunks on two streams so the
+  // H2D of one chunk and the D2H of another overlap a running kernel.  Off by default: measured on B200 it
+  // only pays for very large, cheap-per-trajectory ensembles (2^20 Lorenz/ode45: 12.99 ms -> 12.46 ms with
+  // 16 chunks) and costs 6-200 % elsewhere, because every chunk's persistent kernel has its own
+  // lane-starved tail.  Results do not depend on the chunking.
   int n_chunks = 1;
-  if (!pts && !io->trace && n >= 4 * 65536) n_chunks = (int)((n + 65535) / 65536 > 64 ? 64 : (n + 65535) / 65536);
   if (const char* e = getenv("ODE_B200_CHUNKS")) {
     int v = atoi(e);
     if (v >= 1 && v <= 64 && !pts && !io->trace && n >= v) n_chunks = v;
   }
   unsigned long long* counters = counter;
-  if (n_chunks > 1) counters = g_arena.take<unsigned long long>(32 * n_chunks);  // 256 B apart
+  if (n_chunks > 1) counters = g_arena.take<unsigned long long>(32 * n_chunks);  // 256 B apart, 32 B used each
   if (n_par && !opts->params_stride) ODEB200_CUDA(cudaMemcpyAsync(dpar, io->params, n_par * 8, cudaMemcpyHostToDevice, st));
   ODEB200_CUDA(cudaMemcpyAsync(dts, io->tspan, (size_t)io->n_tspan * 8, cudaMemcpyHostToDevice, st));
   if (g_ev_dev != opts->device) {
@@ -437,7 +471,9 @@ int ode_b200_solve_ensemble(const ode_b200_opts* opts, const ode_b200_ensemble_i
     ODEB200_CUDA(cudaEventCreate(&g_ev1));
     g_ev_dev = opts->device;
   }
-  ODEB200_CUDA(cudaEventRecord(g_ev0, st));
+  // ode_b200_last_kernel_ms: kernel only when there is a single chunk, else the device span of the
+  // whole chunk pipeline (copies included)
+  if (n_chunks > 1) ODEB200_CUDA(cudaEventRecord(g_ev0, st));
   ODEB200_CUDA(cudaEventRecord(g_arena.ev_in, st));
   ODEB200_CUDA(cudaStreamWaitEvent(g_arena.stream2, g_arena.ev_in, 0));
   for (int c = 0; c < n_chunks; c++) {
@@ -463,8 +499,10 @@ int ode_b200_solve_ensemble(const ode_b200_opts* opts, const ode_b200_ensemble_i
       dc.pts_y = d.pts_y + lo * io->pts_cap * D;
       if (d.pts_n) dc.pts_n = d.pts_n + lo;
     }
+    if (n_chunks == 1) ODEB200_CUDA(cudaEventRecord(g_ev0, cs));
     rc = launch_ensemble(opts, &dc, n_chunks > 1 ? counters + 32 * c : counter, cs, false);
     if (rc) return rc;
+    if (n_chunks == 1) ODEB200_CUDA(cudaEventRecord(g_ev1, cs));
     if (io->t_final) ODEB200_CUDA(cudaMemcpyAsync(io->t_final + lo, dc.t_final, m * 8, cudaMemcpyDeviceToHost, cs));
     if (io->y_final) ODEB200_CUDA(cudaMemcpyAsync(io->y_final + lo * D, dc.y_final, (size_t)m * D * 8, cudaMemcpyDeviceToHost, cs));
     if (io->n_accept) ODEB200_CUDA(cudaMemcpyAsync(io->n_accept + lo, dc.n_accept, m * 4, cudaMemcpyDeviceToHost, cs));
@@ -474,7 +512,7 @@ int ode_b200_solve_ensemble(const ode_b200_opts* opts, const ode_b200_ensemble_i
   }
   ODEB200_CUDA(cudaEventRecord(g_arena.ev_done2, g_arena.stream2));
   ODEB200_CUDA(cudaStreamWaitEvent(st, g_arena.ev_done2, 0));
-  ODEB200_CUDA(cudaEventRecord(g_ev1, st));
+  if (n_chunks > 1) ODEB200_CUDA(cudaEventRecord(g_ev1, st));
   g_ev_pending = true;
   if (pts) {
     ODEB200_CUDA(cudaMemcpyAsync(io->pts_t, d.pts_t, (size_t)n * io->pts_cap * 8, cudaMemcpyDeviceToHost, st));

@@ -6,11 +6,12 @@
 namespace odeb200 {
 
 // mode: 0 = final state + counters only, 1 = tout/yout points + trace
-EnsembleKernel adapt_kernel_rk21(int rhs, int mode);
-EnsembleKernel adapt_kernel_rk23(int rhs, int mode);
-EnsembleKernel adapt_kernel_rk45(int rhs, int mode);
-EnsembleKernel adapt_kernel_dopri5(int rhs, int mode);
-EnsembleKernel adapt_kernel_feh78(int rhs, int mode);
+// literal: 0 = fast pass (zero coefficients dropped, marks non-finite trajectories), 1 = literal redo pass
+EnsembleKernel adapt_kernel_rk21(int rhs, int mode, int literal);
+EnsembleKernel adapt_kernel_rk23(int rhs, int mode, int literal);
+EnsembleKernel adapt_kernel_rk45(int rhs, int mode, int literal);
+EnsembleKernel adapt_kernel_dopri5(int rhs, int mode, int literal);
+EnsembleKernel adapt_kernel_feh78(int rhs, int mode, int literal);
 EnsembleKernel fixed_kernel(int method, int rhs);
 EnsembleKernel ode23s_kernel(int rhs, int mode, int jac);  // jac: 0 fdjacobian, 1 analytic functor
 EnsembleKernel rosenbrock_kernel(int method, int rhs, int jac);
@@ -30,7 +31,14 @@ EnsembleKernel ms4_kernel(int rhs);
   }
 
 #define ODEB200_DEFINE_ADAPT(NAME, TAB)                                                        \
-  EnsembleKernel NAME(int rhs, int mode) {                                                     \
+  EnsembleKernel NAME(int rhs, int mode, int literal) {                                        \
+    if (literal) {                                                                             \
+      if (mode) {                                                                              \
+        ODEB200_RHS_SWITCH(rhs, ODEB200_ADAPT_M1L_##TAB)                                       \
+      } else {                                                                                 \
+        ODEB200_RHS_SWITCH(rhs, ODEB200_ADAPT_M0L_##TAB)                                       \
+      }                                                                                        \
+    }                                                                                          \
     if (mode) {                                                                                \
       ODEB200_RHS_SWITCH(rhs, ODEB200_ADAPT_M1_##TAB)                                          \
     } else {                                                                                   \

@@ -20,6 +20,13 @@
 //    loop body is one step ATTEMPT, common to all lanes, and accept/reject is
 //    a handful of predicated register moves (FSAL) rather than a branch around
 //    the stage loop.
+//  * zero tableau coefficients are dropped at compile time.  That is bit-identical to the reference
+//    (which multiplies them, :385-392,454) as long as every stage is finite; with a non-finite stage
+//    the reference forms Inf*0 = NaN.  The fast kernel therefore only DETECTS a non-finite trial
+//    state / scaled error (integer tests), marks the trajectory ODE_B200_ST_REDO and drops it; a
+//    second launch of the LITERAL instantiation (every coefficient multiplied, zeros included)
+//    re-integrates just those trajectories from t0, so blow-ups follow the reference's path
+//    (NaN guard -> dt/5 -> ... -> minstep stop) exactly, at no cost to the hot loop.
 //  * MODE 0 keeps only final state + counters; MODE 1 adds the reference's
 //    tout/yout contract (points = :all / :specified with Hermite output) and an
 //    optional attempt trace, used by the odeXX front-ends and the parity tests.
@@ -51,8 +58,9 @@ constexpr int adapt_min_blocks() {
   return (Rhs::DOF <= 3 && Rhs::DOF * Tab::S <= 21) ? 5 : 1;
 }
 
-template <class Tab, class Rhs, int MODE>
-__global__ void __launch_bounds__(ENS_BLOCK, adapt_min_blocks<Tab, Rhs>()) ens_adapt_kernel(const EnsembleArgs A) {
+template <class Tab, class Rhs, int MODE, bool LITERAL>
+__global__ void __launch_bounds__(ENS_BLOCK, LITERAL ? 1 : adapt_min_blocks<Tab, Rhs>()) ens_adapt_kernel(const EnsembleArgs A) {
+  if (LITERAL && *A.redo_count == 0) return;  // nothing was marked by the fast pass
   constexpr int D = Rhs::DOF, S = Tab::S, NPA = RhsNP<Rhs>::value;
   constexpr bool FSAL = Tab::fsal();
   constexpr double EXPO = 1.0 / (double)(Tab::ORDER + 1);  // T(1/(order+1)) :436
@@ -77,6 +85,10 @@ __global__ void __launch_bounds__(ENS_BLOCK, adapt_min_blocks<Tab, Rhs>()) ens_a
     if (idx < 0) {
       idx = (long long)atomicAdd(A.work_counter, 1ULL);
       if (idx >= A.n_traj) break;
+      if (LITERAL && A.status[idx] != ODE_B200_ST_REDO) {  // the literal pass redoes marked trajectories only
+        idx = -1;
+        continue;
+      }
       // ---------------------------------------------------------- init :256-304
 #pragma unroll
       for (int d = 0; d < D; d++) y[d] = A.y0[idx * D + d];
@@ -149,8 +161,8 @@ __global__ void __launch_bounds__(ENS_BLOCK, adapt_min_blocks<Tab, Rhs>()) ens_a
     constexpr double b10 = Tab::b(0, 0), b20 = Tab::b(1, 0);
 #pragma unroll
     for (int d = 0; d < D; d++) {  // :384-387
-      ytrial[d] = (b10 != 0.0) ? b10 * k1[d] : 0.0;
-      yerr[d] = (b20 != 0.0) ? b20 * k1[d] : 0.0;
+      ytrial[d] = LITERAL ? (0.0 + b10 * k1[d]) : ((b10 != 0.0) ? b10 * k1[d] : 0.0);
+      yerr[d] = LITERAL ? (0.0 + b20 * k1[d]) : ((b20 != 0.0) ? b20 * k1[d] : 0.0);
       dtk[0][d] = dt * k1[d];
       klast[d] = k1[d];
     }
@@ -162,7 +174,7 @@ __global__ void __launch_bounds__(ENS_BLOCK, adapt_min_blocks<Tab, Rhs>()) ens_a
       static_for<s>([&](auto J) {                  // :453-455
         constexpr int ss = decltype(J)::value;
         constexpr double a = Tab::a(s, ss);
-        if constexpr (a != 0.0) {
+        if constexpr (a != 0.0 || LITERAL) {
 #pragma unroll
           for (int d = 0; d < D; d++) ytmp[d] = ytmp[d] + dtk[ss][d] * a;
         }
@@ -172,8 +184,8 @@ __global__ void __launch_bounds__(ENS_BLOCK, adapt_min_blocks<Tab, Rhs>()) ens_a
       constexpr double b1 = Tab::b(0, s), b2 = Tab::b(1, s);
 #pragma unroll
       for (int d = 0; d < D; d++) {  // :390-393
-        if constexpr (b1 != 0.0) ytrial[d] = ytrial[d] + b1 * ks[d];
-        if constexpr (b2 != 0.0) yerr[d] = yerr[d] + b2 * ks[d];
+        if constexpr (b1 != 0.0 || LITERAL) ytrial[d] = ytrial[d] + b1 * ks[d];
+        if constexpr (b2 != 0.0 || LITERAL) yerr[d] = yerr[d] + b2 * ks[d];
         if constexpr (s < S - 1) dtk[s][d] = dt * ks[d];
         if constexpr (s == S - 1) klast[d] = ks[d];
       }
@@ -186,12 +198,24 @@ __global__ void __launch_bounds__(ENS_BLOCK, adapt_min_blocks<Tab, Rhs>()) ens_a
     }
 
     // ---------------------------------------------------- stepsize_hw92! :401-442
-    bool nanout = false;
+    bool nanout = false, weird = false;
 #pragma unroll
     for (int d = 0; d < D; d++) {  // :430-434
-      nanout = nanout || (ytrial[d] != ytrial[d]);  // isoutofdomain, src/ODE.jl:116
       double ay = fabs(y[d]), at = fabs(ytrial[d]);
-      yerr[d] = yerr[d] / (A.abstol + ((ay > at) ? ay : at) * A.reltol);  // :433
+      if (LITERAL) {
+        nanout = nanout || (ytrial[d] != ytrial[d]);  // isoutofdomain, src/ODE.jl:116
+        yerr[d] = yerr[d] / (A.abstol + jl_max(ay, at) * A.reltol);  // :433
+      } else {
+        weird = weird || !is_finite(ytrial[d]);
+        yerr[d] = yerr[d] / (A.abstol + ((ay > at) ? ay : at) * A.reltol);  // :433
+        weird = weird || !is_finite(yerr[d]);
+      }
+    }
+    if (!LITERAL && weird) {  // hand the trajectory to the literal pass (see header)
+      A.status[idx] = ODE_B200_ST_REDO;
+      atomicAdd(A.redo_count, 1);
+      idx = -1;
+      continue;
     }
     double err, newdt;
     if (nanout) {  // :432

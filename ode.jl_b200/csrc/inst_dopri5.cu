@@ -2,7 +2,9 @@
 #include "dispatch.cuh"
 #include "ensemble_adapt.cuh"
 namespace odeb200 {
-#define ODEB200_ADAPT_M0_TabDopri5(R) return ens_adapt_kernel<TabDopri5, R, 0>
-#define ODEB200_ADAPT_M1_TabDopri5(R) return ens_adapt_kernel<TabDopri5, R, 1>
+#define ODEB200_ADAPT_M0_TabDopri5(R) return ens_adapt_kernel<TabDopri5, R, 0, false>
+#define ODEB200_ADAPT_M1_TabDopri5(R) return ens_adapt_kernel<TabDopri5, R, 1, false>
+#define ODEB200_ADAPT_M0L_TabDopri5(R) return ens_adapt_kernel<TabDopri5, R, 0, true>
+#define ODEB200_ADAPT_M1L_TabDopri5(R) return ens_adapt_kernel<TabDopri5, R, 1, true>
 ODEB200_DEFINE_ADAPT(adapt_kernel_dopri5, TabDopri5)
 }  // namespace odeb200

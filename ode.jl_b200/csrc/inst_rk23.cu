@@ -2,7 +2,9 @@
 #include "dispatch.cuh"
 #include "ensemble_adapt.cuh"
 namespace odeb200 {
-#define ODEB200_ADAPT_M0_TabRK23(R) return ens_adapt_kernel<TabRK23, R, 0>
-#define ODEB200_ADAPT_M1_TabRK23(R) return ens_adapt_kernel<TabRK23, R, 1>
+#define ODEB200_ADAPT_M0_TabRK23(R) return ens_adapt_kernel<TabRK23, R, 0, false>
+#define ODEB200_ADAPT_M1_TabRK23(R) return ens_adapt_kernel<TabRK23, R, 1, false>
+#define ODEB200_ADAPT_M0L_TabRK23(R) return ens_adapt_kernel<TabRK23, R, 0, true>
+#define ODEB200_ADAPT_M1L_TabRK23(R) return ens_adapt_kernel<TabRK23, R, 1, true>
 ODEB200_DEFINE_ADAPT(adapt_kernel_rk23, TabRK23)
 }  // namespace odeb200

@@ -237,10 +237,11 @@ def test_empty_and_ragged_ensembles():
         assert_same(got, ref)
 
 
-def test_chunked_host_path_matches_oracle_at_chunk_boundaries():
-    """>= 262144 trajectories take the 4-chunk, two-stream pipeline inside ode_b200_solve_ensemble;
-    results must not depend on the chunking (checked against the oracle around every chunk boundary)."""
-    n = 4 * 65536 + 17
+def test_chunked_host_path_matches_oracle_at_chunk_boundaries(monkeypatch):
+    """ODE_B200_CHUNKS=4 turns on the two-stream chunk pipeline inside ode_b200_solve_ensemble; results must
+    not depend on the chunking (checked against the oracle around every chunk boundary)."""
+    monkeypatch.setenv("ODE_B200_CHUNKS", "4")
+    n = 4 * 16384 + 17
     y0 = lorenz_ics(n, 77)
     got = m.solve_ensemble("ode45", m.DeviceRHS("lorenz", *LORENZ), y0, [0.0, 1.0])
     assert np.all(got["status"] == 0) and np.all(got["t_final"] == 1.0)
@@ -292,3 +293,47 @@ def test_solve_common_interface_ode4s_ode4ms():
     for alg in (m.ode4(), m.ode4ms(), m.ode4s()):
         sol = m.solve(prob, alg, dt=1 / 16, abstol=1e-6, reltol=1e-3)
         assert sol.retcode == "Succss" and isinstance(float(sol[1]), float)
+
+
+def test_nan_inf_and_blowup_paths_match_oracle(capsys):
+    """isoutofdomain / NaN guard (src/runge_kutta.jl:432), minstep stop (:358-360) and the non-finite-dt guard:
+    trajectories with NaN / Inf / overflowing states inside an otherwise healthy ensemble."""
+    y0 = lorenz_ics(64, 21)
+    y0[3, 1] = np.nan
+    y0[10, 0] = np.inf
+    y0[20] = [1e200, -1e200, 1e200]
+    F = m.DeviceRHS("lorenz", *LORENZ)
+    for method in ("ode45", "ode23", "ode78"):
+        got = m.solve_ensemble(method, F, y0, [0.0, 1.0], max_steps=5000)
+        ref = O.solve_ensemble(method, "lorenz", y0, [0.0, 1.0], LORENZ, max_steps=5000)
+        assert_same(got, ref, keys=("n_accept", "n_reject", "n_rhs", "status", "t_final"))
+        ok = got["status"] == 0
+        assert np.array_equal(got["y_final"][ok], ref["y_final"][ok]) and ok.sum() >= 61
+        assert set(got["status"][[3, 10, 20]]) <= {1, 2, 3}
+    # exponential growth to overflow: y' = 1e3 y on [0, 10]
+    got = m.solve_ensemble("ode45", m.DeviceRHS("linear", 1e3), np.array([[1.0], [2.0]]), [0.0, 10.0], max_steps=100000)
+    ref = O.solve_ensemble("ode45", "linear", np.array([[1.0], [2.0]]), [0.0, 10.0], [1e3], max_steps=100000)
+    assert_same(got, ref, keys=("n_accept", "n_reject", "status", "t_final"))
+    assert np.array_equal(got["y_final"], ref["y_final"], equal_nan=True)
+    # ode23s with a NaN start: the loop guard `minstep < abs(h)` is false for NaN h (src/ODE.jl:296)
+    got = m.solve_ensemble("ode23s", F, y0[:8], [0.0, 0.5], max_steps=2000)
+    ref = O.solve_ensemble("ode23s", "lorenz", y0[:8], [0.0, 0.5], LORENZ, max_steps=2000)
+    assert_same(got, ref, keys=("n_accept", "n_reject", "n_rhs", "status"))
+
+
+def test_many_output_points_per_trajectory():
+    """points=:specified with thousands of save points per trajectory."""
+    ts = np.linspace(0.0, 2.0, 2001)
+    y0 = lorenz_ics(16, 2)
+    got = m.solve_ensemble("ode45", m.DeviceRHS("lorenz", *LORENZ), y0, ts, points="specified")
+    assert got["pts_y"].shape == (16, 2001, 3) and np.all(got["pts_n"] == 2001)
+    for i in (0, 7, 15):
+        o = O.solve("ode45", "lorenz", y0[i], ts, LORENZ, points="specified")
+        assert np.array_equal(got["pts_y"][i], o.y) and np.array_equal(got["pts_t"][i], o.t)
+    got = m.solve_ensemble("ode45", m.DeviceRHS("lorenz", *LORENZ), y0, ts, points="all", pts_cap=4096)
+    for i in (3, 12):
+        o = O.solve("ode45", "lorenz", y0[i], ts, LORENZ, points="all")
+        k = got["pts_n"][i]
+        assert k == len(o.t) and np.array_equal(got["pts_y"][i, :k], o.y) and np.array_equal(got["pts_t"][i, :k], o.t)
+    small = m.solve_ensemble("ode45", m.DeviceRHS("lorenz", *LORENZ), y0, ts, points="all", pts_cap=100)
+    assert np.all(small["status"] == 5) and np.array_equal(small["pts_n"], got["pts_n"])  # overflow reports the need

@@ -164,3 +164,32 @@ def test_large_points_specified_bit_exact(method):
     assert np.array_equal(got["trace"], ref.trace)
     assert np.array_equal(got["y"], ref.y)
     assert np.array_equal(got["t"], ref.t)
+
+
+def test_large_nan_state_and_backward_direction():
+    """NaN / overflow in the state (src/runge_kutta.jl:432,358) and backward integration over a short span on a
+    smooth state (test/runtests.jl:58 analogue)."""
+    n = 4096
+    F = m.DeviceRHS("reaction_diffusion", *RD)
+    # (1) NaN in u0: hinit already yields dt = NaN; one rejected attempt, then the non-finite-dt guard
+    y0 = u0(n)
+    y0[1234] = np.nan
+    got = m.solve_large("ode45", F, y0, [0.0, 1.0], trace=True, max_steps=400)
+    ref = O.solve("ode45", "reaction_diffusion", y0, [0.0, 1.0], RD, trace=True, points="final", max_steps=400)
+    assert got["status"] == ref.status == 3 and (got["n_accept"], got["n_reject"]) == (ref.n_accept, ref.n_reject)
+    assert np.array_equal(got["trace"], ref.trace, equal_nan=True)
+    # (2) an overflowing point with a forced finite first step: every attempt trips the NaN guard, dt shrinks by 5
+    #     per attempt (err = 10, timeout = 5) until |dt| < minstep stops the integration with a truncated result
+    y0 = u0(n)
+    y0[77] = 1e160
+    kw = dict(initstep=0.1, minstep=1e-9)
+    got = m.solve_large("ode45", F, y0, [0.0, 1.0], trace=True, **kw)
+    ref = O.solve("ode45", "reaction_diffusion", y0, [0.0, 1.0], RD, trace=True, points="final", **kw)
+    assert got["status"] == ref.status == 1 and got["n_accept"] == ref.n_accept == 0 and got["n_reject"] == ref.n_reject > 5
+    assert np.array_equal(got["trace"], ref.trace, equal_nan=True) and np.all(got["trace"][:, 2] == 10.0)
+    assert got["t_final"] == 0.0 and np.array_equal(got["y"], y0)
+    # (3) backward
+    y0 = 0.5 + 0.001 * np.sin(2 * np.pi * np.arange(n) / n)
+    got = m.solve_large("ode45", m.DeviceRHS("reaction_diffusion", 1e-3, 1.0), y0, [0.5, 0.0], trace=True)
+    ref = O.solve("ode45", "reaction_diffusion", y0, [0.5, 0.0], [1e-3, 1.0], trace=True, points="final")
+    assert np.array_equal(got["trace"], ref.trace) and np.array_equal(got["y"], ref.y[-1]) and got["t_final"] == 0.0

@@ -5,6 +5,8 @@ import math
 import os
 import sys
 
+os.environ.setdefault("ODE_B200_CHUNKS", "1")  # one launch per call, so kernel_ms is the kernel alone
+
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np
 import ode_jl_b200 as m

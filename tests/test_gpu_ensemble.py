@@ -337,3 +337,48 @@ def test_many_output_points_per_trajectory():
         assert k == len(o.t) and np.array_equal(got["pts_y"][i, :k], o.y) and np.array_equal(got["pts_t"][i, :k], o.t)
     small = m.solve_ensemble("ode45", m.DeviceRHS("lorenz", *LORENZ), y0, ts, points="all", pts_cap=100)
     assert np.all(small["status"] == 5) and np.array_equal(small["pts_n"], got["pts_n"])  # overflow reports the need
+
+
+def test_full_size_lorenz_ensemble_properties():
+    """BASELINE config 2 at full size (2^20 trajectories): size-independent checks.
+    (a) a random sample of 2048 trajectories equals the oracle bit for bit;
+    (b) permuting the ensemble permutes the results (trajectories are independent of the dynamic scheduling);
+    (c) every trajectory ends exactly at tend with status OK."""
+    n = 1 << 20
+    y0 = lorenz_ics(n)
+    F = m.DeviceRHS("lorenz", *LORENZ)
+    got = m.solve_ensemble("ode45", F, y0, [0.0, 10.0])
+    assert np.all(got["status"] == 0) and np.all(got["t_final"] == 10.0)
+    rng = np.random.default_rng(1)
+    idx = rng.choice(n, 2048, replace=False)
+    ref = O.solve_ensemble("ode45", "lorenz", y0[idx], [0.0, 10.0], LORENZ)
+    for k in ("y_final", "n_accept", "n_reject", "n_rhs"):
+        assert np.array_equal(got[k][idx], ref[k]), k
+    perm = rng.permutation(n)
+    got2 = m.solve_ensemble("ode45", F, y0[perm], [0.0, 10.0])
+    for k in ("y_final", "n_accept", "n_reject"):
+        assert np.array_equal(got2[k], got[k][perm]), k
+    att = int(got["n_accept"].sum() + got["n_reject"].sum())
+    assert att == 381568754  # the bench's workload: attempts per 2^20-trajectory pass (seed 20261019)
+
+
+def test_full_size_kepler_and_robertson_invariants():
+    """BASELINE configs 3 and 4 at full size (2^18): conserved quantities."""
+    rng = np.random.default_rng(20261019)
+    n = 1 << 18
+    e = rng.uniform(0, 0.9, n)
+    y0 = np.stack([1 - e, np.zeros(n), np.zeros(n), np.sqrt((1 + e) / (1 - e))], 1)
+    got = m.solve_ensemble("ode78", m.DeviceRHS("kepler"), y0, [0.0, 20 * math.pi], reltol=1e-12, abstol=1e-12)
+    assert np.all(got["status"] == 0)
+    yf = got["y_final"]
+    en = lambda y: 0.5 * (y[:, 2] ** 2 + y[:, 3] ** 2) - 1 / np.hypot(y[:, 0], y[:, 1])
+    am = lambda y: y[:, 0] * y[:, 3] - y[:, 1] * y[:, 2]
+    assert np.max(np.abs(en(yf) - en(y0))) < 1e-9
+    assert np.max(np.abs(am(yf) - am(y0))) < 1e-9
+    assert np.max(np.hypot(yf[:, 0] - y0[:, 0], yf[:, 1] - y0[:, 1])) < 2e-7  # 10 closed orbits
+    k = np.array([0.04, 3e7, 1e4]) * 10 ** rng.uniform(-0.5, 0.5, (n, 3))
+    y0 = np.tile([1.0, 0.0, 0.0], (n, 1))
+    got = m.solve_ensemble("ode23s", m.DeviceRHS("robertson", 0.04, 3e7, 1e4), y0, [0.0, 1e5], params=k,
+                           reltol=1e-8, abstol=1e-8)
+    assert np.all(got["status"] == 0) and np.all(got["t_final"] == 1e5)
+    assert np.max(np.abs(got["y_final"].sum(1) - 1.0)) < 1e-7 and got["y_final"].min() > -1e-9

@@ -117,6 +117,20 @@ def run_reference(args, rank):
     """--impl reference: the reference's CPU implementation of the path = the oracle port."""
     if rank != 0:
         return
+    if args.workload == "large":
+        from bench_large import cpu_baseline_large
+        cb = cpu_baseline_large()
+        v = cb["attempts_per_s_at_2^26"]
+        print(json.dumps({"impl": "reference", "metric": "rk_step_attempts_per_s", "value": v, "unit": "steps/s",
+                          "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": None,
+                          "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
+                          "data": "synthetic",
+                          "config": {"workload": "reaction_diffusion_ode45_dp_large", "n_per_gpu": 1 << 26,
+                                     "note": "attempts/s of a 2^26-point system extrapolated linearly from 2^22 points"},
+                          "cpu_baseline": cb,
+                          "e2e": {"value": v, "unit": "steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+                          "gpu_launches": 0}))
+        return
     sample = args.cpu_sample
     cb, per, att = cpu_baseline_lorenz(sample, steps=args.steps, warmup=args.warmup)
     line = {"impl": "reference", "metric": "rk_step_attempts_per_s", "value": cb["value"], "unit": "steps/s",

@@ -28,6 +28,23 @@ def u0_slab(lo, hi, n_global):
     return 0.5 + 0.4 * np.sin(2 * np.pi * 8 * i / n_global)
 
 
+def cpu_baseline_large(n=1 << 22, attempts=12):
+    """CPU restatement of ODE.jl (oracle, OpenMP over grid points) on a bounded sample: the first
+    `attempts` step attempts of the same problem at N = 2^22."""
+    from oracle import oracle as O
+    y0 = u0_slab(0, n, n)
+    threads = O.lib().oracle_max_threads()
+    O.solve("ode45", "reaction_diffusion", y0[:1 << 16], [0.0, 20.0], [1.0, 1.0], points="final", max_steps=2)  # warm-up
+    t0 = time.perf_counter()
+    s = O.solve("ode45", "reaction_diffusion", y0, [0.0, 20.0], [1.0, 1.0], points="final", max_steps=attempts)
+    dt = time.perf_counter() - t0
+    done = s.n_accept + s.n_reject
+    return {"value": done * n / dt, "unit": "point-updates/s", "cores": threads, "kind": "port",
+            "attempts_per_s_at_2^26": done * n / dt / (1 << 26),
+            "sample": "first %d step attempts (hinit included) of the same problem at N = 2^22, %.2f s; C++ restatement "
+                      "of ODE.jl (oracle/), OpenMP over grid points; Julia is not installed" % (done, dt)}
+
+
 def run_large(args, rank, local_rank, world):
     import torch
     import ode_jl_b200 as m
@@ -124,6 +141,8 @@ def run_large(args, rank, local_rank, world):
                              "fp64_issue_frac": FLOPS_PER_POINT * n_local / (per_attempt_ms * 1e-3) / dmix,
                              "note": "all stages of an attempt are fused in one kernel, so HBM traffic is 32 B/point "
                                      "instead of the 264 B/point of one kernel per stage; the kernel is FP64-issue bound"}}
+        if world == 1 and not getattr(args, "no_cpu_baseline", False):
+            line["cpu_baseline"] = cpu_baseline_large()
         print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()

@@ -119,6 +119,18 @@ inline double norm2(const double* x, int64_t n) {
   }
 }
 
+// Elementwise loop, OpenMP-parallel only for long vectors (the large-system CPU baseline).  A plain
+// branch, not an `if` clause: entering a (serialised) parallel region per small loop costs microseconds.
+template <class Fn>
+inline void par_for(int64_t n, Fn&& f) {
+  if (n >= 65536) {
+#pragma omp parallel for schedule(static)
+    for (int64_t i = 0; i < n; i++) f(i);
+  } else {
+    for (int64_t i = 0; i < n; i++) f(i);
+  }
+}
+
 // ------------------------------------------------------------------ tableaus
 // src/runge_kutta.jl:66-157, entries as reduced rationals; converted as
 // Float64(num)/Float64(den) (Rational -> Float64, src/ODE.jl:163).
@@ -288,10 +300,10 @@ struct Rhs {
       case ODE_B200_RHS_REACTION_DIFFUSION: {
         const double kap = p[0], r = p[1];
         const int64_t n = dof;
-        for (int64_t i = 0; i < n; i++) {
+        par_for(n, [&](int64_t i) {
           double um = y[i == 0 ? n - 1 : i - 1], u = y[i], up = y[i == n - 1 ? 0 : i + 1];
           f[i] = kap * ((um - 2.0 * u) + up) + (r * u) * (1.0 - u);
-        }
+        });
       } break;
       default:
         break;
@@ -410,9 +422,12 @@ inline void calc_next_k(std::vector<Vec>& ks, Vec& ytmp, const Vec& y, int s /*0
                         double dt, const Tab& bt) {
   const int64_t n = (int64_t)y.size();
   const int S = bt.S;
-  for (int64_t d = 0; d < n; d++) ytmp[d] = y[d];  // :452
-  for (int ss = 0; ss < s; ss++)                   // :453
-    for (int64_t d = 0; d < n; d++) ytmp[d] += dt * ks[ss][d] * bt.a[s * S + ss];  // :454 (dt*k)*a
+  // (loop order swapped to d-outer for long vectors: per component the additions stay in ss order, :453-455)
+  par_for(n, [&](int64_t d) {
+    double v = y[d];                                                        // :452
+    for (int ss = 0; ss < s; ss++) v += dt * ks[ss][d] * bt.a[s * S + ss];  // :454 (dt*k)*a
+    ytmp[d] = v;
+  });
   ks[s].resize(n);
   F(t + bt.c[s] * dt, ytmp.data(), ks[s].data());  // :456
 }
@@ -477,23 +492,23 @@ void oderk_adapt(const Rhs& F, const MathCtx& M, const Tab& bt, const Vec& y0, c
     }
     attempts++;
     // ---- rk_embedded_step! :371-399
-    for (int64_t d = 0; d < dof; d++) {  // :382-387
+    par_for(dof, [&](int64_t d) {  // :382-387
       ytrial[d] = 0.0;
       yerr[d] = 0.0;
       ytrial[d] += bt.b[0 * S + 0] * ks[0][d];
       yerr[d] += bt.b[1 * S + 0] * ks[0][d];
-    }
+    });
     for (int s = 1; s < S; s++) {  // :388-394
       calc_next_k(ks, ytmp, y, s, F, t, dt, bt);
-      for (int64_t d = 0; d < dof; d++) {
+      par_for(dof, [&](int64_t d) {
         ytrial[d] += bt.b[0 * S + s] * ks[s][d];
         yerr[d] += bt.b[1 * S + s] * ks[s][d];
-      }
+      });
     }
-    for (int64_t d = 0; d < dof; d++) {  // :395-398
+    par_for(dof, [&](int64_t d) {  // :395-398
       yerr[d] = dt * (ytrial[d] - yerr[d]);
       ytrial[d] = y[d] + dt * ytrial[d];
-    }
+    });
     // ---- stepsize_hw92! :401-442
     double err, newdt;
     bool nanout = false;

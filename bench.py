@@ -39,6 +39,9 @@ sys.path.insert(0, ROOT)
 
 LORENZ = (10.0, 28.0, 8.0 / 3.0)
 FLOPS_PER_ATTEMPT = 297  # dopri5 / Lorenz, SURVEY.md section 8d
+# dram__bytes_read.sum + dram__bytes_write.sum of one 2^20-trajectory launch, from the committed ncu capture
+# (profiles/ensemble_lorenz_r1.md: 27.72 MB + 3.86 MB); the kernel is register resident, traffic is I/O only
+NCU_TRAFFIC_BYTES_PER_LAUNCH = 31.58e6
 SEED = 20261019
 
 
@@ -288,7 +291,8 @@ def main():
         achieved = attempts * FLOPS_PER_ATTEMPT / (dev_ms * 1e-3) / 1e12
         peak = 2.0 * dfma / 1e12
         roofline = {"bound": "fp64", "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
-                    "frac_of_issue_peak": achieved / (max(dfma, dmix) / 1e12), "traffic": None,
+                    "frac_of_issue_peak": achieved / (max(dfma, dmix) / 1e12),
+                    "traffic": NCU_TRAFFIC_BYTES_PER_LAUNCH if n == (1 << 20) else None,
                     "peak_source": "measured live: ode_b200_fp64_peak DFMA chains x2 flops (no FP64 entry in "
                                    "MEASURED_PEAKS.json); issue peak = max(DFMA, DADD+DMUL) instr/s = %.3g" % max(dfma, dmix),
                     "note": "strict no-FMA arithmetic (reference parity) caps flops at 50% of the FMA peak; "

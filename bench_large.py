@@ -21,6 +21,9 @@ sys.path.insert(0, ROOT)
 FUSED_BYTES_PER_POINT = 32      # read y, k1; write ytrial, k7 (large-system kernel)
 STAGEWISE_BYTES_PER_POINT = 264  # SURVEY.md section 8d figure for one kernel per stage
 FLOPS_PER_POINT = 143
+# dram__bytes_read.sum + dram__bytes_write.sum of one attempt at N = 2^26 from the committed ncu capture
+# (profiles/large_rd_r1.md: 1.075 GB + 1.034 GB) -- equal to the algorithmic 32 B/point, i.e. no re-reads
+NCU_TRAFFIC_BYTES_PER_ATTEMPT_2_26 = 2.108e9
 
 
 def u0_slab(lo, hi, n_global):
@@ -132,7 +135,7 @@ def run_large(args, rank, local_rank, world):
                            "parallelism": "slab x%d, one all-gather of %d doubles per attempt" % (world, m._lib.XCHG_DOUBLES)},
                 "e2e": e2e, "gpu_launches": launches, "clocks": clocks,
                 "roofline": {"bound": "hbm", "achieved": gbs, "peak": hbm, "unit": "GB/s", "frac": gbs / hbm,
-                             "traffic": None,
+                             "traffic": NCU_TRAFFIC_BYTES_PER_ATTEMPT_2_26 if n_local == (1 << 26) else None,
                              "peak_source": "MEASURED_PEAKS.json hbm_gbs" if peaks else "fallback 6650 GB/s",
                              "algorithmic_bytes_per_point": FUSED_BYTES_PER_POINT,
                              "stagewise_equivalent": {"bytes_per_point": STAGEWISE_BYTES_PER_POINT,

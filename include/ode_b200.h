@@ -211,6 +211,15 @@ int ode_b200_solve_large_points(const ode_b200_opts* opts, int64_t n, const doub
                                 const double* tspan, int32_t n_tspan, double* pts_y, ode_b200_large_stats* stats,
                                 double* trace, int64_t trace_cap, int64_t* trace_n);
 
+/* Same with points = :all (src/runge_kutta.jl:327-340): every accepted step's state, preceded by the Hermite
+ * values at interior tspan points, capped at cap_rows rows: pts_t[cap_rows], pts_y[cap_rows][n].  *n_rows is
+ * the number of rows the reference would return; if it exceeds cap_rows, stats->status is
+ * ODE_B200_ST_OVERFLOW and the caller reruns with *n_rows rows (the integration is deterministic). */
+int ode_b200_solve_large_all(const ode_b200_opts* opts, int64_t n, const double* y0, const double* params,
+                             const double* tspan, int32_t n_tspan, int64_t cap_rows, double* pts_t, double* pts_y,
+                             int64_t* n_rows, ode_b200_large_stats* stats, double* trace, int64_t trace_cap,
+                             int64_t* trace_n);
+
 /* Slab session for the domain-decomposed path: every rank owns n_local
  * contiguous points of an n_global periodic grid plus ghost cells; between the
  * two halves of an attempt the host exchanges `xchg_send` (ODE_B200_XCHG_DOUBLES
@@ -228,6 +237,10 @@ int ode_b200_slab_reset(ode_b200_slab* s, double t0, double tend);
 /* points = :specified output: tspan (host, n_tspan entries) and a device buffer [n_tspan][n_local];
  * call before set_state (which writes row 0 = y0).  NULL disables. */
 int ode_b200_slab_set_output(ode_b200_slab* s, const double* tspan_host, int32_t n_tspan, double* out_dev);
+/* points = :all output: rows (t, y) for every accepted step plus interior tspan points, capped at cap_rows;
+ * out_dev [cap_rows][n_local], out_times_dev [cap_rows]; ctl_out[12] of poll is the row count needed. */
+int ode_b200_slab_set_output_all(ode_b200_slab* s, const double* tspan_host, int32_t n_tspan, double* out_dev,
+                                 double* out_times_dev, int64_t cap_rows);
 /* optional attempt trace on the device: rows (t, dt, err, accepted) */
 int ode_b200_slab_set_trace(ode_b200_slab* s, double* trace_dev, int64_t trace_cap);
 int ode_b200_slab_get_state(ode_b200_slab* s, double* y_local_dev);
@@ -239,8 +252,9 @@ int ode_b200_slab_attempt(ode_b200_slab* s, double* xchg_send);
 /* controller: reduce gathered partials, accept/reject, new dt, ghost refresh */
 int ode_b200_slab_control(ode_b200_slab* s, const double* xchg_recv);
 /* copy the control block to the host (synchronises the stream): ctl_out[12] =
- * {done, status, n_accept, n_reject, t, dt, err, t_final, n_rhs, attempts, trace_n, ghost width H} */
-int ode_b200_slab_poll(ode_b200_slab* s, double* ctl_out /*[12]*/);
+ * {done, status, n_accept, n_reject, t, dt, err, t_final, n_rhs, attempts, trace_n, ghost width H,
+ *  points=:all rows, 0, 0, 0} */
+int ode_b200_slab_poll(ode_b200_slab* s, double* ctl_out /*[16]*/);
 void ode_b200_slab_free(ode_b200_slab* s);
 
 /* ---- measurement hooks ---------------------------------------------------- */

@@ -95,6 +95,15 @@ class Solver:
 
 
 def _solve_single(name, F, y0, tspan, _stats=False, **kw):
+    if isinstance(F, DeviceRHS) and F.name == "reaction_diffusion":
+        # a dof = N method-of-lines state goes to the fused large-system kernels; same (tout, yout) contract
+        from .large import solve_large
+        kw.setdefault("points", "all")
+        r = solve_large(name, F, y0, tspan, **kw)
+        if r["status"] == 1:
+            print("Warning: dt < minstep.  Stopping.")  # src/runge_kutta.jl:359
+        st = dict(n_accept=r["n_accept"], n_reject=r["n_reject"], n_rhs=r["n_rhs"], status=r["status"])
+        return (r["t"], r["y"], st) if _stats else (r["t"], r["y"])
     scalar = np.ndim(y0) == 0
     y = np.ascontiguousarray(np.atleast_1d(np.asarray(y0, dtype=np.float64)))
     ts = np.ascontiguousarray(np.asarray(tspan, dtype=np.float64))

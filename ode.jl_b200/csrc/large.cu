@@ -72,13 +72,30 @@ __global__ void large_control_kernel(const ControlArgs C) {
     ctl->out_lo = ctl->out_hi = 0;
     if (accept) {
       ctl->nacc += 1;
-      if (C.tq) {  // :321-326  output at all new times which are < t+dt (all remaining ones on the last step)
+      if (C.tq && !C.out_times) {  // :321-326  output at all new times which are < t+dt (all remaining ones on the last step)
         int it = ctl->out_iter;  // 1-based index into tspan, like the reference's `iter`
         const int lo = it - 1;
         while (it - 1 < C.n_tq && (tdir * C.tq[it - 1] < tdir * (t + dt) || ctl->islast)) it++;
         ctl->out_lo = lo;
         ctl->out_hi = it - 1;
         ctl->out_iter = it;
+        ctl->out_end = 0;
+      } else if (C.tq) {  // :327-340  points = :all: interior tspan points strictly inside (t, t+dt), then the step end
+        int itf = ctl->out_iter;  // the reference's iter_fixed (1-based)
+        const int lo = itf - 1;
+        while (itf - 1 < C.n_tq && tdir * t < tdir * C.tq[itf - 1] && tdir * C.tq[itf - 1] < tdir * (t + dt)) itf++;
+        ctl->out_lo = lo;
+        ctl->out_hi = itf - 1;
+        ctl->out_iter = itf;
+        ctl->out_end = 1;
+        ctl->out_row0 = ctl->out_rows;
+        long long r = ctl->out_rows;
+        for (int q = lo; q < itf - 1; q++, r++)
+          if (r < C.out_cap) C.out_times[r] = C.tq[q];
+        if (r < C.out_cap) C.out_times[r] = t + dt;
+        ctl->out_rows = r + 1;
+      }
+      if (C.tq) {
         ctl->out_t = t;
         ctl->out_dt = dt;
         ctl->out_par = ctl->par;  // y, k1 of the step start live in Y/K[out_par]; ytrial, f1 in the other pair
@@ -141,23 +158,35 @@ __global__ void large_control_kernel(const ControlArgs C) {
 // hermite_interp! (src/runge_kutta.jl:479-492) for the tspan rows the control kernel selected.
 __global__ void __launch_bounds__(256) large_hermite_kernel(double* const Y0, double* const Y1, double* const K0,
                                                             double* const K1, const LargeCtl* ctl, const double* tq,
-                                                            double* out, long long n, int H) {
+                                                            double* out, long long n, int H, long long out_cap,
+                                                            int all_mode) {
   const int lo = ctl->out_lo, hi = ctl->out_hi;
-  if (hi <= lo) return;
+  const int end_row = all_mode ? ctl->out_end : 0;
+  if (hi <= lo && !end_row) return;
   const int par = ctl->out_par;
   const double* y0 = (par ? Y1 : Y0) + H;
   const double* y1 = (par ? Y0 : Y1) + H;
   const double* f0 = (par ? K1 : K0) + H;
   const double* f1 = (par ? K0 : K1) + H;
   const double t = ctl->out_t, dt = ctl->out_dt;
+  const long long row0 = all_mode ? ctl->out_row0 : (long long)lo;
   for (int q = lo; q < hi; q++) {
+    const long long row = row0 + (q - lo);
+    if (all_mode && row >= out_cap) continue;
     const double theta = (tq[q] - t) / dt;  // :486
-    double* o = out + (long long)q * n;
+    double* o = out + row * n;
     for (long long i = blockIdx.x * 256LL + threadIdx.x; i < n; i += (long long)gridDim.x * 256) {
       const double a = y0[i], b = y1[i];
       o[i] = ((1.0 - theta) * a + theta * b) +
              (theta * (theta - 1.0)) *
                  (((1.0 - 2.0 * theta) * (b - a) + ((theta - 1.0) * dt) * f0[i]) + (theta * dt) * f1[i]);  // :488-489
+    }
+  }
+  if (end_row) {  // index_or_push!(ys, iter, deepcopy(ytrial)) :337
+    const long long row = row0 + (hi - lo);
+    if (row < out_cap) {
+      double* o = out + row * n;
+      for (long long i = blockIdx.x * 256LL + threadIdx.x; i < n; i += (long long)gridDim.x * 256) o[i] = y1[i];
     }
   }
 }
@@ -278,8 +307,11 @@ __global__ void hinit_control_kernel(LargeCtl* ctl, const double* xrecv, int wor
     ctl->timeout = 0;
     ctl->nrhs = 2;
     ctl->t_final = ctl->tstart;
-    ctl->out_iter = 2;  // :304
+    ctl->out_iter = 2;  // :286,:304
     ctl->out_lo = ctl->out_hi = 0;
+    ctl->out_end = 0;
+    ctl->out_rows = 1;  // ys[1] = y0, tspan = [tstart] (:280,:285)
+    ctl->out_row0 = 0;
   }
 }
 
@@ -339,7 +371,9 @@ struct ode_b200_slab {
   long long trace_cap = 0;
   double* tq = nullptr;   // device copy of tspan for points = :specified
   int n_tq = 0;
-  double* out = nullptr;  // [n_tq][n] device, caller owned
+  double* out = nullptr;  // [n_tq][n] (:specified) or [out_cap][n] (:all) device, caller owned
+  double* out_times = nullptr;  // [out_cap] device (:all only)
+  long long out_cap = 0;
   double p0 = 0, p1 = 0;
   int init_blocks = 0;
   LargeCtl host_ctl;
@@ -527,8 +561,10 @@ int ode_b200_slab_set_state(ode_b200_slab* s, const double* y_local_dev) {
   int rc = slab_check(s);
   if (rc) return rc;
   ODEB200_CUDA(cudaMemcpyAsync(s->Y[0] + s->mi.H, y_local_dev, (size_t)s->n * 8, cudaMemcpyDeviceToDevice, s->stream));
-  if (s->out)  // ys[1] = y0, src/runge_kutta.jl:280
+  if (s->out && (!s->out_times || s->out_cap > 0))  // ys[1] = y0, src/runge_kutta.jl:280
     ODEB200_CUDA(cudaMemcpyAsync(s->out, y_local_dev, (size_t)s->n * 8, cudaMemcpyDeviceToDevice, s->stream));
+  if (s->out_times && s->out_cap > 0)  // tspan = [tstart] :285
+    ODEB200_CUDA(cudaMemcpyAsync(s->out_times, &s->host_ctl.tstart, 8, cudaMemcpyHostToDevice, s->stream));
   return 0;
 }
 
@@ -541,12 +577,24 @@ int ode_b200_slab_set_output(ode_b200_slab* s, const double* tspan_host, int32_t
   }
   s->n_tq = 0;
   s->out = nullptr;
+  s->out_times = nullptr;
+  s->out_cap = 0;
   if (!tspan_host || n_tspan < 2 || !out_dev) return 0;  // output disabled
   ODEB200_CUDA(cudaMalloc(&s->tq, (size_t)n_tspan * 8));
   ODEB200_CUDA(cudaMemcpyAsync(s->tq, tspan_host, (size_t)n_tspan * 8, cudaMemcpyHostToDevice, s->stream));
   ODEB200_CUDA(cudaStreamSynchronize(s->stream));
   s->n_tq = n_tspan;
   s->out = out_dev;
+  return 0;
+}
+
+int ode_b200_slab_set_output_all(ode_b200_slab* s, const double* tspan_host, int32_t n_tspan, double* out_dev,
+                                 double* out_times_dev, int64_t cap_rows) {
+  if (!out_times_dev || cap_rows < 1) return set_err(ODE_B200_E_INVALID, "points=:all output needs a times buffer and cap_rows >= 1");
+  int rc = ode_b200_slab_set_output(s, tspan_host, n_tspan, out_dev);
+  if (rc) return rc;
+  s->out_times = out_times_dev;
+  s->out_cap = cap_rows;
   return 0;
 }
 int ode_b200_slab_get_state(ode_b200_slab* s, double* y_local_dev) {
@@ -637,18 +685,21 @@ int ode_b200_slab_control(ode_b200_slab* s, const double* xrecv) {
   C.order = s->mi.order;
   C.tq = s->out ? s->tq : nullptr;
   C.n_tq = s->n_tq;
+  C.out_times = s->out ? s->out_times : nullptr;
+  C.out_cap = s->out_cap;
   large_control_kernel<<<1, 32, 0, s->stream>>>(C);
   note_launch();
   if (s->out) {  // before the next attempt overwrites the step-start arrays
     large_hermite_kernel<<<s->init_blocks, 256, 0, s->stream>>>(s->Y[0], s->Y[1], s->K[0], s->K[1], s->ctl, s->tq,
-                                                                 s->out, s->n, s->mi.H);
+                                                                 s->out, s->n, s->mi.H, s->out_cap,
+                                                                 s->out_times ? 1 : 0);
     note_launch();
   }
   ODEB200_CUDA(cudaGetLastError());
   return 0;
 }
 
-// ctl_out: {done, status, n_accept, n_reject, t, dt, err, t_final, n_rhs, attempts, trace_n, ghost H}
+// ctl_out[16]: {done, status, n_accept, n_reject, t, dt, err, t_final, n_rhs, attempts, trace_n, ghost H, out_rows, -, -, -}
 int ode_b200_slab_poll(ode_b200_slab* s, double* ctl_out) {
   int rc = slab_check(s);
   if (rc) return rc;
@@ -669,6 +720,7 @@ int ode_b200_slab_poll(ode_b200_slab* s, double* ctl_out) {
     ctl_out[9] = (double)c.attempts;
     ctl_out[10] = (double)c.trace_n;
     ctl_out[11] = (double)s->mi.H;
+    ctl_out[12] = (double)c.out_rows;
   }
   return 0;
 }
@@ -689,7 +741,8 @@ void ode_b200_slab_free(ode_b200_slab* s) {
 
 static int solve_large_impl(const ode_b200_opts* o, int64_t n, const double* y0, const double* params,
                             const double* tspan, int32_t n_tspan, double* y_out, double* pts_out,
-                            ode_b200_large_stats* stats, double* trace, int64_t trace_cap, int64_t* trace_n);
+                            ode_b200_large_stats* stats, double* trace, int64_t trace_cap, int64_t* trace_n,
+                            double* all_t = nullptr, int64_t all_cap = 0, int64_t* all_rows = nullptr);
 
 void ode_b200_trim(void) { large_cache_release(); }
 
@@ -707,9 +760,20 @@ int ode_b200_solve_large_points(const ode_b200_opts* o, int64_t n, const double*
   return solve_large_impl(o, n, y0, params, tspan, n_tspan, nullptr, pts_y, stats, trace, trace_cap, trace_n);
 }
 
+int ode_b200_solve_large_all(const ode_b200_opts* o, int64_t n, const double* y0, const double* params,
+                             const double* tspan, int32_t n_tspan, int64_t cap_rows, double* pts_t, double* pts_y,
+                             int64_t* n_rows, ode_b200_large_stats* stats, double* trace, int64_t trace_cap,
+                             int64_t* trace_n) {
+  if (!tspan || n_tspan < 2 || !pts_y || !pts_t || cap_rows < 1 || !n_rows)
+    return set_err(ODE_B200_E_INVALID, "tspan, pts_t, pts_y, n_rows and cap_rows >= 1 are required");
+  return solve_large_impl(o, n, y0, params, tspan, n_tspan, nullptr, pts_y, stats, trace, trace_cap, trace_n, pts_t,
+                          cap_rows, n_rows);
+}
+
 static int solve_large_impl(const ode_b200_opts* o, int64_t n, const double* y0, const double* params,
                             const double* tspan, int32_t n_tspan, double* y_out, double* pts_out,
-                            ode_b200_large_stats* stats, double* trace, int64_t trace_cap, int64_t* trace_n) {
+                            ode_b200_large_stats* stats, double* trace, int64_t trace_cap, int64_t* trace_n,
+                            double* all_t, int64_t all_cap, int64_t* all_rows) {
   if (!o || !y0) return set_err(ODE_B200_E_INVALID, "null argument");
   const double t0 = tspan[0], tend = tspan[n_tspan - 1];
   int cnt = 0;
@@ -753,7 +817,7 @@ static int solve_large_impl(const ode_b200_opts* o, int64_t n, const double* y0,
   cudaStream_t st = cc.st;
   double *dy = cc.dy, *xs = cc.xs, *xr = cc.xr, *dtrace = nullptr, *dpts = nullptr;
   cudaEvent_t e0 = nullptr, e1 = nullptr;
-  double poll[12] = {0};
+  double poll[16] = {0};
 #define LARGE_TRY(x)  \
   do {                \
     if (!rc) rc = (x); \
@@ -771,7 +835,12 @@ static int solve_large_impl(const ode_b200_opts* o, int64_t n, const double* y0,
     LARGE_CUDA(cudaMalloc(&dtrace, (size_t)trace_cap * 32));
     LARGE_TRY(ode_b200_slab_set_trace(s, dtrace, trace_cap));
   }
-  if (pts_out) {
+  double* dtimes = nullptr;
+  if (pts_out && all_t) {  // points = :all, capped at all_cap rows
+    LARGE_CUDA(cudaMalloc(&dpts, (size_t)all_cap * n * 8));
+    LARGE_CUDA(cudaMalloc(&dtimes, (size_t)all_cap * 8));
+    LARGE_TRY(ode_b200_slab_set_output_all(s, tspan, n_tspan, dpts, dtimes, all_cap));
+  } else if (pts_out) {
     LARGE_CUDA(cudaMalloc(&dpts, (size_t)n_tspan * n * 8));
     LARGE_TRY(ode_b200_slab_set_output(s, tspan, n_tspan, dpts));
   }
@@ -796,7 +865,15 @@ static int solve_large_impl(const ode_b200_opts* o, int64_t n, const double* y0,
   LARGE_CUDA(cudaEventRecord(e1, st));
   LARGE_TRY(ode_b200_slab_get_state(s, dy));
   if (y_out) LARGE_CUDA(cudaMemcpyAsync(y_out, dy, (size_t)n * 8, cudaMemcpyDeviceToHost, st));
-  if (pts_out && dpts) LARGE_CUDA(cudaMemcpyAsync(pts_out, dpts, (size_t)n_tspan * n * 8, cudaMemcpyDeviceToHost, st));
+  if (pts_out && dpts && all_t) {
+    const long long rows = (long long)poll[12];
+    const long long m = rows < all_cap ? rows : all_cap;
+    LARGE_CUDA(cudaMemcpyAsync(pts_out, dpts, (size_t)m * n * 8, cudaMemcpyDeviceToHost, st));
+    LARGE_CUDA(cudaMemcpyAsync(all_t, dtimes, (size_t)m * 8, cudaMemcpyDeviceToHost, st));
+    if (all_rows) *all_rows = rows;
+  } else if (pts_out && dpts) {
+    LARGE_CUDA(cudaMemcpyAsync(pts_out, dpts, (size_t)n_tspan * n * 8, cudaMemcpyDeviceToHost, st));
+  }
   if (trace && dtrace) {
     long long tn = (long long)poll[10];
     long long m = tn < trace_cap ? tn : trace_cap;
@@ -823,6 +900,8 @@ static int solve_large_impl(const ode_b200_opts* o, int64_t n, const double* y0,
   }
   if (dtrace) cudaFree(dtrace);
   if (dpts) cudaFree(dpts);
+  if (dtimes) cudaFree(dtimes);
+  if (!rc && stats && all_t && poll[12] > (double)all_cap) stats->status = ODE_B200_ST_OVERFLOW;
   if (rc) large_cache_release();
   return rc;
 #undef LARGE_TRY

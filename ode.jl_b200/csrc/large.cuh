@@ -71,6 +71,10 @@ struct LargeCtl {
   // Hermite-interpolated over the step (out_t, out_t + out_dt) that was just accepted
   int out_iter, out_lo, out_hi, out_par;
   double out_t, out_dt;
+  // points = :all (:327-340): rows [out_row0, out_row0 + (out_hi - out_lo)) get the Hermite values at
+  // tspan[out_lo..out_hi), the next row gets ytrial at t + dt; out_rows counts every row the reference emits
+  long long out_rows, out_row0;
+  int out_end;
 };
 
 struct LargeArgs {
@@ -418,6 +422,8 @@ struct ControlArgs {
   const double* xrecv;
   double* trace;
   const double* tq;  // output times (the reference's tspan), device; nullptr = no points output
+  double* out_times;  // points = :all: tout rows (device), nullptr for :specified
+  long long out_cap;  // rows available in the output buffer (:all)
   long long n;
   int rank, world, H, order, n_tq;
 };

@@ -51,8 +51,27 @@ def solve_large(alg, F, y0, tspan, *, trace=False, trace_cap=65536, out=None, **
     tn = C.c_int64(0)
     dp = _lib.dp
     specified = o.points == _lib.POINTS["specified"]
+    all_points = o.points == _lib.POINTS["all"]
     try:
-        if specified:  # tout = tspan, yout[i] = Hermite value at tspan[i] (src/runge_kutta.jl:321-326)
+        if all_points:  # every accepted step (+ interior tspan points), src/runge_kutta.jl:327-340
+            ts = np.ascontiguousarray(ts)
+            cap = ts.size + 64
+            rows = C.c_int64(0)
+            while True:
+                pt = np.empty(cap)
+                pts = np.empty((cap, y0.size))
+                check(lib().ode_b200_solve_large_all(C.byref(o), y0.size, y0.ctypes.data_as(dp), p.ctypes.data_as(dp),
+                                                     ts.ctypes.data_as(dp), ts.size, cap, pt.ctypes.data_as(dp),
+                                                     pts.ctypes.data_as(dp), C.byref(rows), C.byref(st),
+                                                     tr.ctypes.data_as(dp) if trace else None,
+                                                     trace_cap if trace else 0, C.byref(tn)))
+                if rows.value <= cap:
+                    break
+                cap = rows.value  # deterministic: rerun with the reported size
+            out = pts[:rows.value]
+            ts = pt[:rows.value]
+            specified = True
+        elif specified:  # tout = tspan, yout[i] = Hermite value at tspan[i] (src/runge_kutta.jl:321-326)
             ts = np.ascontiguousarray(ts)
             pts = np.empty((ts.size, y0.size))
             check(lib().ode_b200_solve_large_points(C.byref(o), y0.size, y0.ctypes.data_as(dp), p.ctypes.data_as(dp),
@@ -118,10 +137,11 @@ class CudaSlabEngine:
         check(self.L.ode_b200_slab_control(self.h, C.c_void_p(recv_ptr)))
 
     def poll(self):
-        a = np.zeros(12)
+        a = np.zeros(16)
         check(self.L.ode_b200_slab_poll(self.h, a.ctypes.data_as(_lib.dp)))
         return dict(done=bool(a[0]), status=int(a[1]), n_accept=int(a[2]), n_reject=int(a[3]), t=a[4], dt=a[5],
-                    err=a[6], t_final=a[7], n_rhs=int(a[8]), attempts=int(a[9]), trace_n=int(a[10]), ghost=int(a[11]))
+                    err=a[6], t_final=a[7], n_rhs=int(a[8]), attempts=int(a[9]), trace_n=int(a[10]), ghost=int(a[11]),
+                    out_rows=int(a[12]))
 
     def close(self):
         if self.h:

@@ -193,3 +193,24 @@ def test_large_nan_state_and_backward_direction():
     got = m.solve_large("ode45", m.DeviceRHS("reaction_diffusion", 1e-3, 1.0), y0, [0.5, 0.0], trace=True)
     ref = O.solve("ode45", "reaction_diffusion", y0, [0.5, 0.0], [1e-3, 1.0], trace=True, points="final")
     assert np.array_equal(got["trace"], ref.trace) and np.array_equal(got["y"], ref.y[-1]) and got["t_final"] == 0.0
+
+
+@pytest.mark.parametrize("method", ["ode45", "ode23"])
+def test_large_points_all_through_the_front_end(method):
+    """odeXX(F, u0, tspan) with the default points=:all on a dof = N state: every accepted step plus the
+    Hermite values at interior tspan points (src/runge_kutta.jl:327-340), bit for bit."""
+    n = 3000
+    y0 = u0(n)
+    ts = [0.0, 0.013, 0.5, 3.0, 4.0]
+    F = m.DeviceRHS("reaction_diffusion", *RD)
+    t, y, st = getattr(m, method).stats(F, y0, ts)
+    ref = O.solve(method, "reaction_diffusion", y0, ts, RD, points="all")
+    assert np.array_equal(t, ref.t) and np.array_equal(y, ref.y)
+    assert (st["n_accept"], st["n_reject"], st["n_rhs"]) == (ref.n_accept, ref.n_reject, ref.n_rhs)
+    # long integration: more rows than the first guess -> deterministic rerun with the reported size
+    t2, y2 = getattr(m, method)(F, y0, [0.0, 20.0], reltol=1e-7)
+    ref2 = O.solve(method, "reaction_diffusion", y0, [0.0, 20.0], RD, points="all", reltol=1e-7)
+    assert len(t2) == len(ref2.t) > 66 and np.array_equal(t2, ref2.t) and np.array_equal(y2, ref2.y)
+    t3, y3 = getattr(m, method)(F, y0, ts, points="specified")
+    ref3 = O.solve(method, "reaction_diffusion", y0, ts, RD, points="specified")
+    assert np.array_equal(t3, ref3.t) and np.array_equal(y3, ref3.y)

@@ -12,5 +12,6 @@ from .api import (ode1, ode2_midpoint, ode2_heun, ode4, ode21, ode23, ode45_fe, 
 from .common import ODEProblem, ODESolution, solve  # noqa: F401
 from .large import (solve_large, solve_large_distributed, shard_bounds, integrate_slab,  # noqa: F401
                     CudaSlabEngine)
+from .sharding import solve_ensemble_distributed  # noqa: F401
 
 lib()  # fail loudly at import if the CUDA library is missing

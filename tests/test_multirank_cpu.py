@@ -79,3 +79,51 @@ def test_shard_bounds_cover_the_grid():
         assert b[0][0] == 0 and b[-1][1] == n
         assert all(b[i][1] == b[i + 1][0] for i in range(w - 1))
         assert max(h - l for l, h in b) - min(h - l for l, h in b) <= 1
+
+
+def _ens_worker(rank, world, port, n, q):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    import ode_jl_b200 as m
+    from oracle import oracle as O
+    rng = np.random.default_rng(3)
+    y0 = np.stack([rng.uniform(-10, 10, n), rng.uniform(-10, 10, n), rng.uniform(5, 35, n)], 1)
+    mu = rng.uniform(0.5, 2.0, (n, 3)) * np.array([10.0, 28.0, 8 / 3])
+
+    def cpu_solve(alg, F, y, tspan, params=None, **kw):  # stand-in for the CUDA shard solve (tests only)
+        return O.solve_ensemble(alg, F.name, y, tspan, params, threads=1, **kw)
+
+    F = m.DeviceRHS("lorenz", 10.0, 28.0, 8 / 3)
+    full = m.solve_ensemble_distributed("ode45", F, y0, [0.0, 0.5], params=mu, _local_solve=cpu_solve)
+    part = m.solve_ensemble_distributed("ode45", F, y0, [0.0, 0.5], params=mu, gather=False, _local_solve=cpu_solve)
+    q.put((rank, full, part))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world", [2, 3])
+def test_gloo_ensemble_shards_and_final_gather(world):
+    """Trajectory shards + the final gather (the only communication of the ensemble regime)."""
+    from oracle import oracle as O
+    n = 101
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 29700 + (os.getpid() % 200) + world
+    ps = [ctx.Process(target=_ens_worker, args=(r, world, port, n, q)) for r in range(world)]
+    for p in ps:
+        p.start()
+    res = sorted([q.get(timeout=180) for _ in ps], key=lambda x: x[0])
+    for p in ps:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    rng = np.random.default_rng(3)
+    y0 = np.stack([rng.uniform(-10, 10, n), rng.uniform(-10, 10, n), rng.uniform(5, 35, n)], 1)
+    mu = rng.uniform(0.5, 2.0, (n, 3)) * np.array([10.0, 28.0, 8 / 3])
+    ref = O.solve_ensemble("ode45", "lorenz", y0, [0.0, 0.5], mu)
+    for rank, full, part in res:
+        for k in ("t_final", "y_final", "n_accept", "n_reject", "n_rhs", "status"):
+            assert np.array_equal(full[k], ref[k]), (rank, k)
+            lo, hi = part["rows"]
+            assert np.array_equal(part[k], ref[k][lo:hi])
+    assert [r[2]["rows"] for r in res][0][0] == 0 and res[-1][2]["rows"][1] == n

@@ -100,7 +100,7 @@ def cpu_baseline_lorenz(sample, steps=1, warmup=0):
     """CPU restatement of ODE.jl (oracle, OpenMP over trajectories) on `sample` trajectories."""
     from oracle import oracle as O
     y0 = lorenz_ics(sample)
-    threads = O.lib().oracle_max_threads()
+    threads = O.use_all_cores()
     best = None
     for it in range(warmup + steps):
         t0 = time.perf_counter()

@@ -36,7 +36,7 @@ def cpu_baseline_large(n=1 << 22, attempts=12):
     `attempts` step attempts of the same problem at N = 2^22."""
     from oracle import oracle as O
     y0 = u0_slab(0, n, n)
-    threads = O.lib().oracle_max_threads()
+    threads = O.use_all_cores()
     O.solve("ode45", "reaction_diffusion", y0[:1 << 16], [0.0, 20.0], [1.0, 1.0], points="final", max_steps=2)  # warm-up
     t0 = time.perf_counter()
     s = O.solve("ode45", "reaction_diffusion", y0, [0.0, 20.0], [1.0, 1.0], points="final", max_steps=attempts)

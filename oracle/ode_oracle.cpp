@@ -1051,6 +1051,11 @@ void oracle_rhs(int rhs, int64_t dof, const double* params, double t, const doub
   F(t, y, f);
 }
 double oracle_norm2(const double* x, int64_t n) { return norm2(x, n); }
+void oracle_set_threads(int n) {
+#ifdef _OPENMP
+  if (n > 0) omp_set_num_threads(n);
+#endif
+}
 int oracle_max_threads(void) {
 #ifdef _OPENMP
   return omp_get_max_threads();

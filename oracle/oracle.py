@@ -81,6 +81,8 @@ def lib():
         L.oracle_norm2.argtypes = [dp, C.c_int64]
         L.oracle_norm2.restype = C.c_double
         L.oracle_max_threads.restype = C.c_int
+        L.oracle_set_threads.argtypes = [C.c_int]
+        L.oracle_set_threads.restype = None
         _lib = L
     return _lib
 
@@ -197,3 +199,17 @@ def rhs_eval(rhs, t, y, params):
     f = np.empty_like(y)
     L.oracle_rhs(RHS[rhs] if isinstance(rhs, str) else rhs, y.size, _dp(p), float(t), _dp(y), _dp(f))
     return f
+
+
+def host_cores():
+    """Cores this process may run on (torchrun exports OMP_NUM_THREADS=1, which would hide them)."""
+    try:
+        return len(os.sched_getaffinity(0))
+    except Exception:
+        return os.cpu_count() or 1
+
+
+def use_all_cores():
+    n = host_cores()
+    lib().oracle_set_threads(n)
+    return n

@@ -1,6 +1,7 @@
 #!/usr/bin/env python3
-"""Run under torchrun on N GPUs: checks the two sharded paths on real hardware (NCCL).
-   python -m torch.distributed.run --nproc-per-node 2 --master-addr 127.0.0.1 tools/multigpu_check.py"""
+"""(Not collected by pytest: needs torchrun and >= 2 GPUs.)  Checks the two sharded paths on real hardware
+(NCCL) against the CPU oracle.
+   python -m torch.distributed.run --nproc-per-node 2 --master-addr 127.0.0.1 tests/multigpu_check.py"""
 import os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np

@@ -41,6 +41,44 @@ class ODESolution:
         return len(self.u)
 
 
+def _frange(a, step, b):
+    """collect(a:step:b) for floats: a + k*step, k = 0..n, with Julia's habit of landing exactly on b when the
+    range is meant to hit it (Julia computes float ranges in twice precision; this is the plain-float analogue,
+    so an interior element may differ from Julia's by an ulp)."""
+    if step == 0 or (b - a) / step < -1e-12:
+        return []
+    n = int(np.floor((b - a) / step * (1 + 1e-14) + 1e-12))
+    out = [a + k * step for k in range(n + 1)]
+    if out and abs(out[-1] - b) <= 4e-16 * max(abs(a), abs(b), abs(step)) * max(1, n):
+        out[-1] = b
+    return out
+
+
+def build_ts(tspan, saveat):
+    """`Ts` of src/common.jl:50-70: the time grid handed to the solver for a given `saveat`.
+
+    saveat a number: tspan[1]+saveat : saveat : tspan[end] (or up to tspan[end]-saveat when the range does not
+    land on tspan[end]); a collection: as given.  A trailing tspan[2] is dropped and re-appended, a leading
+    tspan[1] is kept once; duplicates are removed in order (`unique`)."""
+    t0, t1 = float(tspan[0]), float(tspan[1])
+    if np.ndim(saveat) == 0:  # :52-57
+        step = float(saveat)
+        full = _frange(t0, step, t1)
+        if full and full[-1] == t1:  # (tspan[1]:saveat:tspan[end])[end] == tspan[end]
+            saveat_vec = _frange(t0 + step, step, t1)
+        else:
+            saveat_vec = _frange(t0 + step, step, t1 - step)
+    else:
+        saveat_vec = [float(x) for x in saveat]  # :59
+    if saveat_vec and saveat_vec[-1] == t1:  # :62-64
+        saveat_vec.pop()
+    if saveat_vec and saveat_vec[0] == t0:   # :66-70
+        Ts = saveat_vec + [t1]
+    else:
+        Ts = [t0] + saveat_vec + [t1]
+    return list(dict.fromkeys(Ts))  # unique, order kept
+
+
 def solve(prob, alg, *, verbose=True, save_timeseries=None, saveat=(), reltol=1e-5, abstol=1e-8,
           save_everystep=None, dense=None, save_start=None, callback=None, dtmin=None, dtmax=None,
           timeseries_errors=True, dense_errors=False, dt=0.0, norm=None, **kwargs):
@@ -74,23 +112,7 @@ def solve(prob, alg, *, verbose=True, save_timeseries=None, saveat=(), reltol=1e
     if callback is not None or prob.callback is not None:  # :46-48
         raise ValueError("ODE is not compatible with callbacks.")
 
-    if saveat_is_number:  # :52-57
-        step = float(saveat)
-        nsteps = int(np.floor((tspan[1] - tspan[0]) / step + 1e-12))
-        grid_end = tspan[0] + nsteps * step
-        pts = [tspan[0] + k * step for k in range(1, nsteps + 1)]
-        if grid_end != tspan[1]:
-            pts = [x for x in pts if x <= tspan[1] - step + 1e-15 * max(1.0, abs(tspan[1]))]
-        saveat_vec = pts
-    else:
-        saveat_vec = [float(x) for x in saveat]  # :59
-    if saveat_vec and saveat_vec[-1] == tspan[1]:  # :62-64
-        saveat_vec.pop()
-    if saveat_vec and saveat_vec[0] == tspan[0]:   # :66-70
-        Ts = saveat_vec + [tspan[1]]
-    else:
-        Ts = [tspan[0]] + saveat_vec + [tspan[1]]
-    Ts = list(dict.fromkeys(Ts))  # unique, order kept
+    Ts = build_ts(tspan, saveat)
     points = "all" if save_everystep else "specified"  # :72-76
 
     u0 = np.asarray(prob.u0, dtype=np.float64)

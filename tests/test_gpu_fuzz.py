@@ -92,3 +92,57 @@ def test_random_configurations_match_oracle(seed):
         o = O.solve(method, name, np.atleast_1d(y0[i]), ts, p if p else None, max_steps=0, **okw2)
         yy = y if np.ndim(y) == 2 else y[:, None]
         assert np.array_equal(t, o.t) and np.array_equal(yy, o.y, equal_nan=True), desc + " :: front-end " + str(skw)
+
+
+@pytest.mark.parametrize("seed", range(8))
+def test_random_large_system_configurations_match_oracle(seed):
+    """Random N, tableau, stencil parameters, tolerances, spans, output mode; and for a third of the cases a random
+    slab decomposition (ranks emulated as sequential sessions on one GPU) that must give the single-slab bits."""
+    import torch
+    from test_gpu_large import lockstep
+    r = np.random.default_rng(5000 + seed)
+    for it in range(5):
+        n = int(r.integers(200, 20000))
+        method = str(r.choice(["ode23", "ode45_fe", "ode45", "ode78"]))
+        kappa, rr = float(r.uniform(0.05, 1.5)), float(r.uniform(0.0, 2.0))
+        i = np.arange(n)
+        y0 = 0.5 + 0.4 * np.sin(2 * np.pi * int(r.integers(1, 9)) * i / n) + 0.05 * r.uniform(-1, 1, n)
+        span = float(10 ** r.uniform(-1, 0.7))
+        kw = dict(reltol=float(10 ** r.uniform(-8, -3)), abstol=float(10 ** r.uniform(-10, -6)))
+        mode = str(r.choice(["final", "specified", "all"]))
+        ts = [0.0, span] if mode == "final" else [0.0] + sorted(r.uniform(0, span, int(r.integers(1, 4))).tolist()) + [span]
+        F = m.DeviceRHS("reaction_diffusion", kappa, rr)
+        desc = "seed %d case %d: %s n=%d kappa=%g r=%g ts=%s kw=%s mode=%s" % (seed, it, method, n, kappa, rr, ts, kw, mode)
+        got = m.solve_large(method, F, y0, ts, trace=True, points=mode, **kw)
+        ref = O.solve(method, "reaction_diffusion", y0, ts, [kappa, rr], trace=True, points=mode, **kw)
+        assert np.array_equal(got["trace"], ref.trace), desc
+        if mode == "final":
+            assert np.array_equal(got["y"], ref.y[-1]), desc
+        else:
+            assert np.array_equal(got["t"], ref.t) and np.array_equal(got["y"], ref.y), desc
+        if it % 3 == 0:
+            world = int(r.integers(2, 6))
+            dev = torch.device("cuda", 0)
+            st = torch.cuda.current_stream(dev).cuda_stream
+            engines, sends, recvs, parts = [], [], [], []
+            for k in range(world):
+                lo, hi = m.shard_bounds(n, world, k)
+                e = m.CudaSlabEngine(method, F, hi - lo, n, k, world, [0.0, span], st, **kw)
+                yl = torch.tensor(y0[lo:hi], dtype=torch.float64, device=dev)
+                e.set_state(yl.data_ptr())
+                engines.append(e)
+                parts.append(yl)
+                sends.append(torch.zeros(m._lib.XCHG_DOUBLES, dtype=torch.float64, device=dev))
+                recvs.append(torch.zeros(world, m._lib.XCHG_DOUBLES, dtype=torch.float64, device=dev))
+            ctls = lockstep(engines, sends, recvs)
+            outs = []
+            for e, yl in zip(engines, parts):
+                o = torch.empty_like(yl)
+                e.get_state(o.data_ptr())
+                outs.append(o)
+            torch.cuda.synchronize()
+            fin = O.solve(method, "reaction_diffusion", y0, [0.0, span], [kappa, rr], points="final", **kw)
+            assert np.array_equal(torch.cat(outs).cpu().numpy(), fin.y[-1]), desc + " world=%d" % world
+            assert ctls[0]["n_accept"] == fin.n_accept and ctls[0]["n_reject"] == fin.n_reject
+            for e in engines:
+                e.close()

@@ -26,7 +26,14 @@
 #ifndef ODE_B200_H
 #define ODE_B200_H
 
+#ifdef __CUDACC_RTC__ /* NVRTC has no <stdint.h>; the run-time RHS compiler includes this header */
+typedef int int32_t;
+typedef unsigned int uint32_t;
+typedef long long int64_t;
+typedef unsigned long long uint64_t;
+#else
 #include <stdint.h>
+#endif
 
 #ifdef __cplusplus
 extern "C" {
@@ -65,6 +72,8 @@ typedef enum {
   ODE_B200_RHS_REACTION_DIFFUSION = 8, /* dof N: kappa*((u[i-1]-2u[i])+u[i+1]) + (r*u[i])*(1-u[i]), periodic; params {kappa, r} */
   ODE_B200_RHS_COUNT = 9
 } ode_b200_rhs;
+/* ids returned by ode_b200_register_rhs start here */
+#define ODE_B200_RHS_USER_BASE 1000
 
 /* `points` keyword (src/runge_kutta.jl:238,283-290); FINAL is an ensemble-only
  * extension that skips all intermediate output. */
@@ -143,6 +152,7 @@ typedef struct {
   int64_t* trace_n;     /* attempts recorded */
 } ode_b200_ensemble_io;
 
+#ifndef __CUDACC_RTC__ /* host entry points: not visible to the run-time (NVRTC) compilation of kernels */
 /* ---- library info --------------------------------------------------------- */
 int ode_b200_version(void);                 /* ODE_B200_ABI_VERSION */
 const char* ode_b200_last_error(void);      /* thread-local, never NULL */
@@ -157,6 +167,18 @@ int ode_b200_method_is_fsal(int method);    /* isFSAL, src/runge_kutta.jl:62 */
 /* Tableau entry as the reference converts it (Rational -> Float64, src/ODE.jl:163).
  * which: 0 = a[i][j], 1 = b[i][j] (i = 0 stepping row, 1 error row), 2 = c[i]. */
 double ode_b200_tableau(int method, int which, int i, int j);
+
+/* ---- right-hand sides registered at run time ------------------------------- */
+/* The reference accepts any Julia function F(t, y).  The equivalent here: register the BODY of the device
+ * functor as CUDA C++ source.  `eval_body` is the body of
+ *     void eval(double t, const double (&y)[dof], double (&f)[dof], const double (&p)[max(n_params,1)])
+ * and `jac_body` (optional, NULL = none) the body of
+ *     void jac (double t, const double (&y)[dof], double (&J)[dof][dof], const double (&p)[...])
+ * (row-major dF/dy, used when opts.jacobian = 1).  On first use the library compiles its own kernel templates
+ * for this functor with NVRTC (same arithmetic rules: no FMA contraction) and caches the result.
+ * Returns the rhs id (>= ODE_B200_RHS_USER_BASE) to put in opts.rhs, or a negative error code.
+ * Available for the ensemble / single-system entry points (every method). */
+int ode_b200_register_rhs(const char* name, int32_t dof, int32_t n_params, const char* eval_body, const char* jac_body);
 
 /* ---- ensembles of small systems (one trajectory per thread) -------------- */
 /* Replaces n_traj independent calls of oderk_adapt / oderk_fixed / ode23s.
@@ -268,6 +290,8 @@ double ode_b200_fp64_peak(int device, int kind);
  * GPU produces the same bits as the host build of the same header. */
 int ode_b200_selftest_detmath(int device, const double* x, const double* y, double* out_pow, double* out_log10,
                               int64_t n);
+
+#endif /* !__CUDACC_RTC__ */
 
 #ifdef __cplusplus
 }

@@ -25,9 +25,24 @@
 #ifndef ODE_B200_DETMATH_H
 #define ODE_B200_DETMATH_H
 
+#ifdef __CUDACC_RTC__ /* NVRTC: no host headers; device code only */
+#ifndef ODE_B200_H
+typedef int int32_t;
+typedef unsigned int uint32_t;
+typedef long long int64_t;
+typedef unsigned long long uint64_t;
+#endif
+#ifndef INFINITY
+#define INFINITY __longlong_as_double(0x7ff0000000000000LL)
+#endif
+#ifndef NAN
+#define NAN __longlong_as_double(0x7ff8000000000000LL)
+#endif
+#else
 #include <stdint.h>
 #include <string.h>
 #include <math.h>
+#endif
 
 #include "ode_b200_detmath_tables.h"
 
@@ -40,8 +55,10 @@
 /* ---- tables: one host copy, one device copy (same bits) ------------------ */
 #define DM_X3(a, b, c) a, b, c,
 #define DM_X2(a, b) a, b,
+#ifndef __CUDACC_RTC__
 static const double dm_logtab_h[128 * 3] = {DM_LOG_TABLE(DM_X3)};
 static const double dm_exptab_h[128 * 2] = {DM_EXP_TABLE(DM_X2)};
+#endif
 #if defined(__CUDACC__)
 static __device__ const double dm_logtab_d[128 * 3] = {DM_LOG_TABLE(DM_X3)};
 static __device__ const double dm_exptab_d[128 * 2] = {DM_EXP_TABLE(DM_X2)};

@@ -48,6 +48,20 @@ function (f::DeviceRHS{:kepler})(t, y)
     [y[3]; y[4]; -y[1]/r3; -y[2]/r3]
 end
 
+# ---- right-hand sides registered at run time (CUDA C++ body, compiled by NVRTC inside the library) ------
+struct UserRHS
+    id::Int32
+    params::Vector{Float64}
+end
+rhs_id(f::UserRHS) = f.id
+"""register_rhs("brusselator", 2, 2, "f[0] = ...; f[1] = ...;"; jac = nothing, params = [1.0, 3.0])"""
+function register_rhs(name::String, dof::Integer, n_params::Integer, eval_body::String; jac = nothing, params = Float64[])
+    id = ccall((:ode_b200_register_rhs, LIB[]), Cint, (Cstring, Int32, Int32, Cstring, Cstring),
+               name, dof, n_params, eval_body, jac === nothing ? C_NULL : jac)
+    id < 0 && error("libode_b200: " * last_error())
+    UserRHS(id, Float64[params...])
+end
+
 # ---- ode_b200_opts (field order and types as in the header) -----------------------------------------
 struct Opts
     method::Int32; rhs::Int32; dof::Int32; n_params::Int32
@@ -69,7 +83,7 @@ function check(rc::Integer)
     error("libode_b200 error $rc: $msg")
 end
 
-function _solve(method::Symbol, F::DeviceRHS, y0, tspan;
+function _solve(method::Symbol, F::Union{DeviceRHS,UserRHS}, y0, tspan;
                 reltol = 1.0e-5, abstol = 1.0e-8,
                 minstep = abs(tspan[end] - tspan[1])/1e18,     # src/runge_kutta.jl:235
                 maxstep = abs(tspan[end] - tspan[1])/2.5,      # :236
@@ -101,12 +115,12 @@ end
 
 for name in (:ode1, :ode2_midpoint, :ode2_heun, :ode4, :ode21, :ode23, :ode45_fe, :ode45_dp, :ode45, :ode78, :ode23s,
              :ode4s, :ode4s_s, :ode4s_kr, :ode4ms)
-    @eval $name(F::DeviceRHS, y0, tspan; kw...) = _solve($(QuoteNode(name)), F, y0, tspan; kw...)
+    @eval $name(F::Union{DeviceRHS,UserRHS}, y0, tspan; kw...) = _solve($(QuoteNode(name)), F, y0, tspan; kw...)
     @eval $name(F, y0, tspan; kw...) =
         error("libode_b200 takes a registered DeviceRHS; a Julia closure cannot run on the device (no CPU fallback)")
     @eval export $name
 end
-export DeviceRHS
+export DeviceRHS, UserRHS, register_rhs
 
 # ---- ensembles: n independent odeXX calls in one launch --------------------------------------------
 struct EnsembleIO

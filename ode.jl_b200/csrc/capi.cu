@@ -15,6 +15,7 @@
 
 #include "dispatch.cuh"
 #include "host_util.cuh"
+#include "rtc.cuh"
 #include "tableaus.cuh"
 
 namespace odeb200 {
@@ -124,6 +125,17 @@ static double tab_get(int which, int i, int j) {
     default: break;                               \
   }
 
+// dof / parameter count of a built-in or run-time registered rhs
+static bool rhs_shape(int rhs, int* dof, int* np, bool* has_jac) {
+  if (rhs >= 0 && rhs < ODE_B200_RHS_COUNT) {
+    *dof = kRhsDof[rhs];
+    *np = kRhsNp[rhs];
+    if (has_jac) *has_jac = true;
+    return true;
+  }
+  return user_rhs_info(rhs, dof, np, has_jac);
+}
+
 static bool is_fixed_step(int method) {
   return method <= ODE_B200_M_RK4 || method == ODE_B200_M_ODE4S_S || method == ODE_B200_M_ODE4S_KR ||
          method == ODE_B200_M_ODE4MS;
@@ -145,13 +157,16 @@ static int device_ok(int dev) {
 static int validate(const ode_b200_opts* o, const ode_b200_ensemble_io* io, double t0, double tend) {
   if (!o || !io) return set_err(ODE_B200_E_INVALID, "null opts/io");
   if (o->method < 0 || o->method >= ODE_B200_M_COUNT) return set_err(ODE_B200_E_INVALID, "unknown method %d", o->method);
-  if (o->rhs < 0 || o->rhs >= ODE_B200_RHS_COUNT) return set_err(ODE_B200_E_INVALID, "unknown rhs %d", o->rhs);
+  int rdof = 0, rnp = 0;
+  bool has_jac = true;
+  if (!rhs_shape(o->rhs, &rdof, &rnp, &has_jac)) return set_err(ODE_B200_E_INVALID, "unknown rhs %d", o->rhs);
   if (o->rhs == ODE_B200_RHS_REACTION_DIFFUSION)
     return set_err(ODE_B200_E_UNSUPPORTED, "reaction_diffusion is a large-system RHS: use ode_b200_solve_large");
-  if (o->dof != kRhsDof[o->rhs]) return set_err(ODE_B200_E_INVALID, "rhs %d has dof %d, got %d", o->rhs, kRhsDof[o->rhs], o->dof);
-  if (o->n_params < kRhsNp[o->rhs]) return set_err(ODE_B200_E_INVALID, "rhs %d needs %d params, got %d", o->rhs, kRhsNp[o->rhs], o->n_params);
-  if (kRhsNp[o->rhs] > 0 && !io->params) return set_err(ODE_B200_E_INVALID, "params is NULL");
-  if (o->params_stride != 0 && o->params_stride < kRhsNp[o->rhs]) return set_err(ODE_B200_E_INVALID, "params_stride < n_params");
+  if (o->dof != rdof) return set_err(ODE_B200_E_INVALID, "rhs %d has dof %d, got %d", o->rhs, rdof, o->dof);
+  if (o->n_params < rnp) return set_err(ODE_B200_E_INVALID, "rhs %d needs %d params, got %d", o->rhs, rnp, o->n_params);
+  if (rnp > 0 && !io->params) return set_err(ODE_B200_E_INVALID, "params is NULL");
+  if (o->params_stride != 0 && o->params_stride < rnp) return set_err(ODE_B200_E_INVALID, "params_stride < n_params");
+  if (o->jacobian == 1 && !has_jac) return set_err(ODE_B200_E_INVALID, "rhs %d was registered without a Jacobian body", o->rhs);
   if (io->n_traj < 0 || (io->n_traj > 0 && !io->y0)) return set_err(ODE_B200_E_INVALID, "bad n_traj / y0");
   if (io->n_tspan < 2 || !io->tspan) return set_err(ODE_B200_E_INVALID, "tspan needs at least 2 entries");
   if (o->points != ODE_B200_POINTS_ALL && o->points != ODE_B200_POINTS_SPECIFIED && o->points != ODE_B200_POINTS_FINAL)
@@ -176,8 +191,21 @@ static int validate(const ode_b200_opts* o, const ode_b200_ensemble_io* io, doub
 }
 
 static bool is_adaptive_rk(int method) { return method >= ODE_B200_M_RK21 && method <= ODE_B200_M_FEH78; }
+static EnsembleKernel pick_kernel_fn(const ode_b200_opts* o, int mode, int literal);
 
-static EnsembleKernel pick_kernel(const ode_b200_opts* o, int mode, int literal = 0) {
+static const void* pick_kernel_builtin(const ode_b200_opts* o, int mode, int literal);
+
+// kernel handle: a __global__ function pointer for the built-in functors, a cudaKernel_t for run-time ones
+static const void* pick_kernel(const ode_b200_opts* o, int mode, int literal = 0) {
+  if (o->rhs >= ODE_B200_RHS_USER_BASE) return user_kernel(o->rhs, o->method, mode, literal, o->jacobian);
+  return pick_kernel_builtin(o, mode, literal);
+}
+
+static const void* pick_kernel_builtin(const ode_b200_opts* o, int mode, int literal) {
+  return (const void*)pick_kernel_fn(o, mode, literal);
+}
+
+static EnsembleKernel pick_kernel_fn(const ode_b200_opts* o, int mode, int literal) {
   switch (o->method) {
     case ODE_B200_M_RK21: return adapt_kernel_rk21(o->rhs, mode, literal);
     case ODE_B200_M_RK23: return adapt_kernel_rk23(o->rhs, mode, literal);
@@ -199,8 +227,11 @@ static int launch_ensemble(const ode_b200_opts* o, const ode_b200_ensemble_io* i
                            cudaStream_t stream, bool time_it) {
   const bool want_points = io->pts_y != nullptr || io->trace != nullptr;
   const int mode = (want_points && o->points != ODE_B200_POINTS_FINAL) || io->trace ? 1 : 0;
-  EnsembleKernel k = pick_kernel(o, mode);
-  if (!k) return set_err(ODE_B200_E_UNSUPPORTED, "no kernel for method %d / rhs %d", o->method, o->rhs);
+  const void* k = pick_kernel(o, mode);
+  if (!k) {
+    if (o->rhs >= ODE_B200_RHS_USER_BASE) return ODE_B200_E_INVALID;  // last_error set by the run-time compiler
+    return set_err(ODE_B200_E_UNSUPPORTED, "no kernel for method %d / rhs %d", o->method, o->rhs);
+  }
   EnsembleArgs A;
   memset(&A, 0, sizeof(A));
   A.n_traj = io->n_traj;
@@ -238,8 +269,10 @@ static int launch_ensemble(const ode_b200_opts* o, const ode_b200_ensemble_io* i
   int dev = 0, sms = 0, per_sm = 0;
   ODEB200_CUDA(cudaGetDevice(&dev));
   ODEB200_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
-  ODEB200_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k, ENS_BLOCK, 0));
-  if (per_sm < 1) per_sm = 1;
+  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k, ENS_BLOCK, 0) != cudaSuccess || per_sm < 1) {
+    cudaGetLastError();
+    per_sm = 4;
+  }
   long long need = (io->n_traj + ENS_BLOCK - 1) / ENS_BLOCK;
   long long grid = (long long)sms * per_sm;  // persistent: every lane pulls work until the counter runs out
   if (need < grid) grid = need;
@@ -257,23 +290,28 @@ static int launch_ensemble(const ode_b200_opts* o, const ode_b200_ensemble_io* i
     }
     ODEB200_CUDA(cudaEventRecord(g_ev0, stream));
   }
-  k<<<(unsigned)grid, ENS_BLOCK, 0, stream>>>(A);
+  void* kargs[] = {(void*)&A};
+  ODEB200_CUDA(cudaLaunchKernel(k, dim3((unsigned)grid), dim3(ENS_BLOCK), kargs, 0, stream));
   note_launch();
-  ODEB200_CUDA(cudaGetLastError());
   if (two_pass) {
     // literal pass: re-integrates the trajectories the fast pass marked ODE_B200_ST_REDO (non-finite trial
     // state or error), multiplying every tableau coefficient like the reference; returns at once if none.
-    EnsembleKernel kl = pick_kernel(o, mode, 1);
-    if (!kl) return set_err(ODE_B200_E_UNSUPPORTED, "no literal kernel for method %d / rhs %d", o->method, o->rhs);
+    const void* kl = pick_kernel(o, mode, 1);
+    if (!kl) {
+      if (o->rhs >= ODE_B200_RHS_USER_BASE) return ODE_B200_E_INVALID;
+      return set_err(ODE_B200_E_UNSUPPORTED, "no literal kernel for method %d / rhs %d", o->method, o->rhs);
+    }
     int per_sm_l = 1;
-    ODEB200_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm_l, kl, ENS_BLOCK, 0));
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm_l, kl, ENS_BLOCK, 0) != cudaSuccess) {
+      cudaGetLastError();
+      per_sm_l = 2;
+    }
     long long grid_l = (long long)sms * (per_sm_l < 1 ? 1 : per_sm_l);
     if (need < grid_l) grid_l = need;
     if (grid_l < 1) grid_l = 1;
     A.work_counter = counter + 2;
-    kl<<<(unsigned)grid_l, ENS_BLOCK, 0, stream>>>(A);
+    ODEB200_CUDA(cudaLaunchKernel(kl, dim3((unsigned)grid_l), dim3(ENS_BLOCK), kargs, 0, stream));
     note_launch();
-    ODEB200_CUDA(cudaGetLastError());
   }
   if (time_it) {
     ODEB200_CUDA(cudaEventRecord(g_ev1, stream));
@@ -310,8 +348,14 @@ int ode_b200_method_id(const char* name) {
       if (!strcmp(e.name, name)) return e.id;
   return ODE_B200_E_INVALID;
 }
-int ode_b200_rhs_dof(int rhs) { return (rhs >= 0 && rhs < ODE_B200_RHS_COUNT) ? kRhsDof[rhs] : ODE_B200_E_INVALID; }
-int ode_b200_rhs_nparams(int rhs) { return (rhs >= 0 && rhs < ODE_B200_RHS_COUNT) ? kRhsNp[rhs] : ODE_B200_E_INVALID; }
+int ode_b200_rhs_dof(int rhs) {
+  int d = 0, n = 0;
+  return rhs_shape(rhs, &d, &n, nullptr) ? d : ODE_B200_E_INVALID;
+}
+int ode_b200_rhs_nparams(int rhs) {
+  int d = 0, n = 0;
+  return rhs_shape(rhs, &d, &n, nullptr) ? n : ODE_B200_E_INVALID;
+}
 int ode_b200_method_stages(int method) {
   if (method == ODE_B200_M_ODE23S) return 3;
   if (method == ODE_B200_M_ODE4S_S || method == ODE_B200_M_ODE4S_KR || method == ODE_B200_M_ODE4MS) return 4;
@@ -409,7 +453,8 @@ int ode_b200_solve_ensemble(const ode_b200_opts* opts, const ode_b200_ensemble_i
   const long long n = io->n_traj;
   if (n == 0) return 0;
   const int D = opts->dof;
-  const int np = kRhsNp[opts->rhs];
+  int np = 0, dof_unused = 0;
+  rhs_shape(opts->rhs, &dof_unused, &np, nullptr);
   const size_t n_par = np ? (opts->params_stride ? (size_t)n * opts->params_stride : (size_t)np) : 0;
   const bool pts = io->pts_y != nullptr;
   size_t bytes = 256 + pad256(n * D * 8) + pad256(n_par * 8) + pad256((size_t)io->n_tspan * 8) + pad256(n * 8) +

@@ -1,0 +1,230 @@
+// rtc.cu -- right-hand sides registered at run time.
+//
+// The reference takes any Julia function as `F`.  A closure cannot cross the C ABI, so the built-in
+// functors of rhs.cuh are compiled in; for everything else a caller registers the BODY of the device
+// functor as CUDA C++ source (ode_b200_register_rhs).  On first use with a given method the library
+// compiles, with NVRTC, the very same kernel templates (ensemble_*.cuh) instantiated for that functor --
+// same arithmetic rules (-fmad=false), same controller, same bits -- and caches the loaded kernel.
+// NVRTC is opened with dlopen, so the library itself does not depend on it.
+#include <cuda_runtime.h>
+#include <dlfcn.h>
+#include <nvrtc.h>
+
+#include <cstdio>
+#include <cstring>
+#include <map>
+#include <mutex>
+#include <string>
+#include <vector>
+
+#include "../../include/ode_b200.h"
+#include "host_util.cuh"
+#include "rtc.cuh"
+
+namespace odeb200 {
+
+struct UserRhs {
+  std::string name, eval_body, jac_body;
+  int dof, np;
+};
+static std::vector<UserRhs> g_user;
+static std::map<std::string, const void*> g_kernels;  // key -> cudaKernel_t
+static std::mutex g_mu;
+
+struct Nvrtc {
+  void* h = nullptr;
+  nvrtcResult (*CreateProgram)(nvrtcProgram*, const char*, const char*, int, const char* const*, const char* const*);
+  nvrtcResult (*CompileProgram)(nvrtcProgram, int, const char* const*);
+  nvrtcResult (*GetProgramLogSize)(nvrtcProgram, size_t*);
+  nvrtcResult (*GetProgramLog)(nvrtcProgram, char*);
+  nvrtcResult (*GetCUBINSize)(nvrtcProgram, size_t*);
+  nvrtcResult (*GetCUBIN)(nvrtcProgram, char*);
+  nvrtcResult (*AddNameExpression)(nvrtcProgram, const char*);
+  nvrtcResult (*GetLoweredName)(nvrtcProgram, const char*, const char**);
+  nvrtcResult (*DestroyProgram)(nvrtcProgram*);
+  const char* (*GetErrorString)(nvrtcResult);
+};
+static Nvrtc g_nvrtc;
+
+static int load_nvrtc() {
+  if (g_nvrtc.h) return 0;
+  const char* names[] = {"libnvrtc.so.12", "libnvrtc.so", "/usr/local/cuda/lib64/libnvrtc.so.12"};
+  void* h = nullptr;
+  for (const char* n : names)
+    if ((h = dlopen(n, RTLD_NOW | RTLD_LOCAL))) break;
+  if (!h) return set_err(ODE_B200_E_UNSUPPORTED, "NVRTC (libnvrtc.so.12) not found: run-time RHS registration unavailable");
+#define LOAD(sym)                                                                   \
+  *(void**)(&g_nvrtc.sym) = dlsym(h, "nvrtc" #sym);                                 \
+  if (!g_nvrtc.sym) return set_err(ODE_B200_E_UNSUPPORTED, "nvrtc" #sym " missing")
+  LOAD(CreateProgram);
+  LOAD(CompileProgram);
+  LOAD(GetProgramLogSize);
+  LOAD(GetProgramLog);
+  LOAD(GetCUBINSize);
+  LOAD(GetCUBIN);
+  LOAD(AddNameExpression);
+  LOAD(GetLoweredName);
+  LOAD(DestroyProgram);
+  LOAD(GetErrorString);
+#undef LOAD
+  g_nvrtc.h = h;
+  return 0;
+}
+
+static std::string library_dir() {
+  Dl_info info;
+  if (dladdr((void*)&ode_b200_version, &info) && info.dli_fname) {
+    std::string p(info.dli_fname);
+    size_t k = p.find_last_of('/');
+    return k == std::string::npos ? std::string(".") : p.substr(0, k);
+  }
+  return ".";
+}
+
+bool user_rhs_info(int rhs, int* dof, int* np, bool* has_jac) {
+  std::lock_guard<std::mutex> lk(g_mu);
+  int i = rhs - ODE_B200_RHS_USER_BASE;
+  if (i < 0 || i >= (int)g_user.size()) return false;
+  if (dof) *dof = g_user[i].dof;
+  if (np) *np = g_user[i].np;
+  if (has_jac) *has_jac = !g_user[i].jac_body.empty();
+  return true;
+}
+
+static const char* tab_name(int method) {
+  switch (method) {
+    case ODE_B200_M_FEULER: return "odeb200::TabFEuler";
+    case ODE_B200_M_MIDPOINT: return "odeb200::TabMidpoint";
+    case ODE_B200_M_HEUN: return "odeb200::TabHeun";
+    case ODE_B200_M_RK4: return "odeb200::TabRK4";
+    case ODE_B200_M_RK21: return "odeb200::TabRK21";
+    case ODE_B200_M_RK23: return "odeb200::TabRK23";
+    case ODE_B200_M_RK45_FE: return "odeb200::TabRK45";
+    case ODE_B200_M_DOPRI5: return "odeb200::TabDopri5";
+    case ODE_B200_M_FEH78: return "odeb200::TabFeh78";
+    default: return nullptr;
+  }
+}
+
+// Kernel of `method` instantiated for the registered RHS; nullptr + last_error on failure.
+const void* user_kernel(int rhs, int method, int mode, int literal, int jac) {
+  UserRhs u;
+  {
+    std::lock_guard<std::mutex> lk(g_mu);
+    int i = rhs - ODE_B200_RHS_USER_BASE;
+    if (i < 0 || i >= (int)g_user.size()) {
+      set_err(ODE_B200_E_INVALID, "unknown user rhs %d", rhs);
+      return nullptr;
+    }
+    u = g_user[i];
+  }
+  char expr[512];
+  const char* header = "ensemble_adapt.cuh";
+  if (method >= ODE_B200_M_RK21 && method <= ODE_B200_M_FEH78) {
+    snprintf(expr, sizeof(expr), "odeb200::ens_adapt_kernel<%s, odeb200::RhsUser, %d, %s>", tab_name(method), mode ? 1 : 0,
+             literal ? "true" : "false");
+  } else if (method <= ODE_B200_M_RK4) {
+    header = "ensemble_fixed.cuh";
+    snprintf(expr, sizeof(expr), "odeb200::ens_fixed_kernel<%s, odeb200::RhsUser>", tab_name(method));
+  } else if (method == ODE_B200_M_ODE23S) {
+    header = "ensemble_ode23s.cuh";
+    snprintf(expr, sizeof(expr), "odeb200::ens_ode23s_kernel<odeb200::RhsUser, %d, %d>", mode ? 1 : 0, jac ? 1 : 0);
+  } else if (method == ODE_B200_M_ODE4S_S || method == ODE_B200_M_ODE4S_KR) {
+    header = "ensemble_ros.cuh";
+    snprintf(expr, sizeof(expr), "odeb200::ens_rosenbrock_kernel<odeb200::RhsUser, odeb200::%s, %d>",
+             method == ODE_B200_M_ODE4S_KR ? "RosKapsRentrop" : "RosShampine", jac ? 1 : 0);
+  } else if (method == ODE_B200_M_ODE4MS) {
+    header = "ensemble_ros.cuh";
+    snprintf(expr, sizeof(expr), "odeb200::ens_ms4_kernel<odeb200::RhsUser>");
+  } else {
+    set_err(ODE_B200_E_UNSUPPORTED, "method %d has no kernel for a run-time RHS", method);
+    return nullptr;
+  }
+  int dev = 0;
+  cudaGetDevice(&dev);
+  char keyb[640];
+  snprintf(keyb, sizeof(keyb), "%d|%d|%s", dev, rhs, expr);
+  const std::string key(keyb);
+  {
+    std::lock_guard<std::mutex> lk(g_mu);
+    auto it = g_kernels.find(key);
+    if (it != g_kernels.end()) return it->second;
+  }
+  if (load_nvrtc()) return nullptr;
+  const int npa = u.np > 0 ? u.np : 1;
+  std::string src = "#include \"" + std::string(header) + "\"\nnamespace odeb200 {\nstruct RhsUser {\n";
+  char buf[512];
+  snprintf(buf, sizeof(buf), "  static constexpr int DOF = %d, NP = %d, ID = %d;\n", u.dof, u.np, rhs);
+  src += buf;
+  snprintf(buf, sizeof(buf),
+           "  __device__ __forceinline__ static void eval(double t, const double (&y)[%d], double (&f)[%d], const double (&p)[%d]) {\n",
+           u.dof, u.dof, npa);
+  src += buf;
+  src += u.eval_body + "\n  }\n";
+  snprintf(buf, sizeof(buf),
+           "  __device__ __forceinline__ static void jac(double t, const double (&y)[%d], double (&J)[%d][%d], const double (&p)[%d]) {\n",
+           u.dof, u.dof, u.dof, npa);
+  src += buf;
+  src += u.jac_body + "\n  }\n};\n}  // namespace odeb200\n";
+
+  nvrtcProgram prog;
+  nvrtcResult r = g_nvrtc.CreateProgram(&prog, src.c_str(), "user_rhs.cu", 0, nullptr, nullptr);
+  if (r != NVRTC_SUCCESS) {
+    set_err(ODE_B200_E_CUDA, "nvrtcCreateProgram: %s", g_nvrtc.GetErrorString(r));
+    return nullptr;
+  }
+  g_nvrtc.AddNameExpression(prog, expr);
+  const std::string dir = library_dir();
+  const std::string i1 = "-I" + dir + "/csrc", i2 = "-I" + dir + "/../include";
+  // -fmad=false: the reference never fuses multiply-add; -default-device: lambdas inside the kernels
+  const char* opts[] = {"--gpu-architecture=sm_100a", "-std=c++17", "-fmad=false", "-lineinfo", "-default-device",
+                        i1.c_str(), i2.c_str()};
+  r = g_nvrtc.CompileProgram(prog, 7, opts);
+  if (r != NVRTC_SUCCESS) {
+    size_t n = 0;
+    g_nvrtc.GetProgramLogSize(prog, &n);
+    std::string log(n + 1, '\0');
+    if (n) g_nvrtc.GetProgramLog(prog, &log[0]);
+    set_err(ODE_B200_E_INVALID, "NVRTC compilation of rhs '%s' failed: %.380s", u.name.c_str(), log.c_str());
+    g_nvrtc.DestroyProgram(&prog);
+    return nullptr;
+  }
+  const char* lowered = nullptr;
+  size_t nb = 0;
+  g_nvrtc.GetLoweredName(prog, expr, &lowered);
+  g_nvrtc.GetCUBINSize(prog, &nb);
+  std::vector<char> cubin(nb);
+  g_nvrtc.GetCUBIN(prog, cubin.data());
+  cudaLibrary_t lib = nullptr;
+  cudaKernel_t kern = nullptr;
+  cudaError_t e = cudaLibraryLoadData(&lib, cubin.data(), nullptr, nullptr, 0, nullptr, nullptr, 0);
+  if (e == cudaSuccess) e = cudaLibraryGetKernel(&kern, lib, lowered ? lowered : "");
+  g_nvrtc.DestroyProgram(&prog);
+  if (e != cudaSuccess) {
+    cudaGetLastError();
+    set_err(ODE_B200_E_CUDA, "loading the compiled rhs '%s' failed: %s", u.name.c_str(), cudaGetErrorString(e));
+    return nullptr;
+  }
+  std::lock_guard<std::mutex> lk(g_mu);
+  g_kernels[key] = (const void*)kern;
+  return (const void*)kern;
+}
+
+}  // namespace odeb200
+
+using namespace odeb200;
+
+extern "C" int ode_b200_register_rhs(const char* name, int32_t dof, int32_t n_params, const char* eval_body,
+                                     const char* jac_body) {
+  if (!name || !eval_body || dof < 1 || dof > 16 || n_params < 0 || n_params > 64)
+    return set_err(ODE_B200_E_INVALID, "register_rhs: need a name, an eval body, 1 <= dof <= 16, 0 <= n_params <= 64");
+  std::lock_guard<std::mutex> lk(g_mu);
+  UserRhs u;
+  u.name = name;
+  u.eval_body = eval_body;
+  u.jac_body = jac_body ? jac_body : "";
+  u.dof = dof;
+  u.np = n_params;
+  g_user.push_back(u);
+  return ODE_B200_RHS_USER_BASE + (int)g_user.size() - 1;
+}

@@ -16,6 +16,25 @@ _DOF = dict(linear=1, const=1, timelin=1, rotation=2, lorenz=3, vdp=2, robertson
 _NP = dict(linear=1, const=1, timelin=1, rotation=0, lorenz=3, vdp=1, robertson=3, kepler=0, reaction_diffusion=2)
 
 
+def register_rhs(name, dof, n_params, eval_body, jac_body=None, host=None, params=()):
+    """Register a right-hand side from CUDA C++ source at run time and return its DeviceRHS token.
+
+    eval_body : body of  void eval(double t, const double (&y)[dof], double (&f)[dof], const double (&p)[max(n_params,1)])
+    jac_body  : optional body of  void jac(double t, const double (&y)[dof], double (&J)[dof][dof], const double (&p)[..])
+    host      : optional python callable host(t, y, p) evaluating the same expression (for DeviceRHS.__call__)
+    The library compiles its own kernel templates for this functor with NVRTC on first use (no FMA contraction)."""
+    from ._lib import lib
+    rid = lib().ode_b200_register_rhs(name.encode(), int(dof), int(n_params), eval_body.encode(),
+                                      jac_body.encode() if jac_body else None)
+    if rid < 0:
+        from ._lib import check
+        check(rid)
+    tok = DeviceRHS.__new__(DeviceRHS)
+    tok.name, tok.id, tok.dof, tok.n_params, tok.params = name, rid, int(dof), int(n_params), tuple(params)
+    tok._host = host
+    return tok
+
+
 class DeviceRHS:
     """`DeviceRHS("lorenz", 10.0, 28.0, 8/3)`; calling it evaluates F(t, y) on the host."""
 
@@ -34,7 +53,13 @@ class DeviceRHS:
     def with_params(self, p):
         if p is None:
             return self
-        return DeviceRHS(self.name, *np.atleast_1d(np.asarray(p, dtype=np.float64)).tolist())
+        vals = np.atleast_1d(np.asarray(p, dtype=np.float64)).tolist()
+        if self.id >= 1000:  # run-time registered: same functor, new parameter values
+            tok = DeviceRHS.__new__(DeviceRHS)
+            tok.__dict__.update(self.__dict__)
+            tok.params = tuple(vals)
+            return tok
+        return DeviceRHS(self.name, *vals)
 
     def param_array(self):
         if self.n_params == 0:
@@ -48,6 +73,10 @@ class DeviceRHS:
         return a
 
     def __call__(self, t, y):
+        if self.id >= 1000:
+            if getattr(self, "_host", None) is None:
+                raise TypeError("run-time RHS %r was registered without a host evaluator" % self.name)
+            return self._host(t, y, self.params)
         p = self.params
         n = self.name
         scalar = np.ndim(y) == 0

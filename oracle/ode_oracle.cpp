@@ -249,13 +249,21 @@ Tab make_tab(int method) {
 // ---------------------------------------------------------- right-hand sides
 // F(t, y) -> f.  Association is written out explicitly; the CUDA functors and
 // the Python restatement state the same expressions independently.
+typedef void (*UserRhsFn)(double t, const double* y, double* f, const double* p, int dof);
+typedef void (*UserJacFn)(double t, const double* y, double* J, const double* p, int dof);
 struct Rhs {
   int id;
   int64_t dof;
   const double* p;
+  UserRhsFn user = nullptr;  // run-time RHS (tests pass a ctypes callback evaluating the same expression)
+  UserJacFn user_jac = nullptr;
   mutable int64_t calls = 0;
   void operator()(double t, const double* y, double* f) const {
     calls++;
+    if (user) {
+      user(t, y, f, p, (int)dof);
+      return;
+    }
     switch (id) {
       case ODE_B200_RHS_LINEAR:  // README.md:19  f(u,p,t) = 1.01*u
         f[0] = p[0] * y[0];
@@ -316,6 +324,10 @@ struct Rhs {
 // repo's definition; the CUDA functors state the same expressions.
 bool rhs_jacobian(const Rhs& F, double t, const double* y, double* J) {
   const double* p = F.p;
+  if (F.user_jac) {
+    F.user_jac(t, y, J, p, (int)F.dof);
+    return true;
+  }
   switch (F.id) {
     case ODE_B200_RHS_LINEAR: J[0] = p[0]; return true;
     case ODE_B200_RHS_CONST: J[0] = 0.0; return true;
@@ -932,9 +944,16 @@ void ode4ms(const Rhs& F, const Vec& x0, const Vec& tspan, Result& R) {
     for (int64_t d = 0; d < n; d++) R.y[i * n + d] = x[i][d];
 }
 
+thread_local UserRhsFn g_user_rhs = nullptr;
+thread_local UserJacFn g_user_jac = nullptr;
+
 void solve_one(const ode_b200_opts* op, const double* y0, const double* params, const double* tspan, int n_tspan,
                bool want_trace, Result& R) {
   Rhs F{op->rhs, op->dof, params};
+  if (op->rhs >= ODE_B200_RHS_USER_BASE) {
+    F.user = g_user_rhs;
+    F.user_jac = g_user_jac;
+  }
   MathCtx M{op->mathmode};
   Opt o{op->reltol, op->abstol, op->minstep, op->maxstep, op->initstep, op->points,
         op->max_steps > 0 ? op->max_steps : 100000000, want_trace, op->jacobian};
@@ -966,6 +985,12 @@ extern "C" {
 struct oracle_result {
   Result r;
 };
+
+// run-time RHS for opts.rhs >= ODE_B200_RHS_USER_BASE (single-trajectory solves of the calling thread)
+void oracle_set_user_rhs(UserRhsFn f, UserJacFn j) {
+  g_user_rhs = f;
+  g_user_jac = j;
+}
 
 int oracle_solve(const ode_b200_opts* op, const double* y0, const double* params, const double* tspan, int n_tspan,
                  int want_trace, oracle_result** out) {

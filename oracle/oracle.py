@@ -81,6 +81,8 @@ def lib():
         L.oracle_norm2.argtypes = [dp, C.c_int64]
         L.oracle_norm2.restype = C.c_double
         L.oracle_max_threads.restype = C.c_int
+        L.oracle_set_user_rhs.argtypes = [C.c_void_p, C.c_void_p]
+        L.oracle_set_user_rhs.restype = None
         L.oracle_set_threads.argtypes = [C.c_int]
         L.oracle_set_threads.restype = None
         _lib = L
@@ -213,3 +215,38 @@ def use_all_cores():
     n = host_cores()
     lib().oracle_set_threads(n)
     return n
+
+
+USER_RHS_BASE = 1000
+_RHSFN = C.CFUNCTYPE(None, C.c_double, C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(C.c_double), C.c_int)
+
+
+def solve_user(method, f, y0, tspan, params=None, jac=None, **kw):
+    """One trajectory with a python right-hand side f(t, y, p) -> list (evaluated with python floats, i.e.
+    binary64 without FMA), run through the C++ restatement.  Used to check run-time registered CUDA functors."""
+    L = lib()
+    y0a = np.ascontiguousarray(np.atleast_1d(np.asarray(y0, dtype=np.float64)))
+    dof = y0a.size
+    npar = 0 if params is None else len(params)
+
+    def cb(t, yp, fp, pp, n):
+        out = f(t, [yp[i] for i in range(n)], [pp[i] for i in range(npar)])
+        for i in range(n):
+            fp[i] = out[i]
+
+    def cbj(t, yp, Jp, pp, n):
+        out = jac(t, [yp[i] for i in range(n)], [pp[i] for i in range(npar)])
+        for i in range(n):
+            for j in range(n):
+                Jp[i * n + j] = out[i][j]
+
+    c1 = _RHSFN(cb)
+    c2 = _RHSFN(cbj) if jac is not None else None
+    L.oracle_set_user_rhs(C.cast(c1, C.c_void_p), C.cast(c2, C.c_void_p) if c2 else None)
+    try:
+        kw2 = dict(kw)
+        if jac is not None:
+            kw2["jacobian"] = 1
+        return solve(method, USER_RHS_BASE, y0a, tspan, params, **kw2)
+    finally:
+        L.oracle_set_user_rhs(None, None)

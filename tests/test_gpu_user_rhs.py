@@ -1,0 +1,106 @@
+"""Right-hand sides registered at run time (NVRTC): the library compiles its own kernel templates for a
+functor given as CUDA C++ source.  Checked (a) against the built-in functor of the same expression, bit for
+bit, and (b) for a functor that is NOT built in, against the C++ oracle driven by a python callback that
+evaluates the same expression in binary64 without FMA."""
+import numpy as np
+import pytest
+
+import ode_jl_b200 as m
+from oracle import oracle as O
+
+pytestmark = pytest.mark.gpu
+
+LORENZ_SRC = """
+    f[0] = p[0] * (y[1] - y[0]);
+    f[1] = y[0] * (p[1] - y[2]) - y[1];
+    f[2] = y[0] * y[1] - p[2] * y[2];
+"""
+LORENZ_JAC = """
+    J[0][0] = -p[0];       J[0][1] = p[0];  J[0][2] = 0.0;
+    J[1][0] = p[1] - y[2]; J[1][1] = -1.0;  J[1][2] = -y[0];
+    J[2][0] = y[1];        J[2][1] = y[0];  J[2][2] = -p[2];
+"""
+# Brusselator: not a built-in
+BRUSS_SRC = """
+    const double x = y[0], z = y[1];
+    f[0] = p[0] + (x * x) * z - (p[1] + 1.0) * x;
+    f[1] = p[1] * x - (x * x) * z;
+"""
+BRUSS_JAC = """
+    const double x = y[0], z = y[1];
+    J[0][0] = (2.0 * x) * z - (p[1] + 1.0);  J[0][1] = x * x;
+    J[1][0] = p[1] - (2.0 * x) * z;          J[1][1] = -(x * x);
+"""
+
+
+def bruss(t, y, p):
+    x, z = y
+    return [p[0] + (x * x) * z - (p[1] + 1.0) * x, p[1] * x - (x * x) * z]
+
+
+def bruss_jac(t, y, p):
+    x, z = y
+    return [[(2.0 * x) * z - (p[1] + 1.0), x * x], [p[1] - (2.0 * x) * z, -(x * x)]]
+
+
+@pytest.fixture(scope="module")
+def user_lorenz():
+    return m.register_rhs("user_lorenz", 3, 3, LORENZ_SRC, LORENZ_JAC, params=(10.0, 28.0, 8 / 3))
+
+
+@pytest.fixture(scope="module")
+def user_bruss():
+    return m.register_rhs("brusselator", 2, 2, BRUSS_SRC, BRUSS_JAC, host=bruss, params=(1.0, 3.0))
+
+
+@pytest.mark.parametrize("method", ["ode21", "ode23", "ode45_fe", "ode45", "ode78", "ode23s", "ode4", "ode1",
+                                    "ode4s_s", "ode4s_kr", "ode4ms"])
+def test_user_rhs_equals_builtin_functor(method, user_lorenz):
+    rng = np.random.default_rng(3)
+    y0 = np.stack([rng.uniform(-10, 10, 200), rng.uniform(-10, 10, 200), rng.uniform(5, 35, 200)], 1)
+    ts = np.linspace(0.0, 0.5, 26) if m.lib().ode_b200_method_is_adaptive(m._lib.METHODS[method]) == 0 else [0.0, 1.0]
+    a = m.solve_ensemble(method, user_lorenz, y0, ts)
+    b = m.solve_ensemble(method, m.DeviceRHS("lorenz", 10.0, 28.0, 8 / 3), y0, ts)
+    for k in ("y_final", "t_final", "n_accept", "n_reject", "n_rhs", "status"):
+        assert np.array_equal(a[k], b[k]), k
+    if method in ("ode23s", "ode4s_s"):
+        a = m.solve_ensemble(method, user_lorenz, y0, ts, jacobian=True)
+        b = m.solve_ensemble(method, m.DeviceRHS("lorenz", 10.0, 28.0, 8 / 3), y0, ts, jacobian=True)
+        assert np.array_equal(a["y_final"], b["y_final"]) and np.array_equal(a["n_rhs"], b["n_rhs"])
+
+
+@pytest.mark.parametrize("method", ["ode23", "ode45", "ode78", "ode23s"])
+def test_user_rhs_not_builtin_matches_oracle_callback(method, user_bruss):
+    ts = [0.0, 2.5, 10.0]
+    for y0 in ([1.5, 3.0], [0.2, 0.1]):
+        t, y, st = getattr(m, method).stats(user_bruss, y0, ts)
+        o = O.solve_user(method, bruss, y0, ts, [1.0, 3.0])
+        assert np.array_equal(t, o.t) and np.array_equal(y, o.y)
+        assert (st["n_accept"], st["n_reject"], st["n_rhs"]) == (o.n_accept, o.n_reject, o.n_rhs)
+    if method == "ode23s":
+        t, y = m.ode23s(user_bruss, [1.5, 3.0], ts, jacobian=True)
+        o = O.solve_user("ode23s", bruss, [1.5, 3.0], ts, [1.0, 3.0], jac=bruss_jac)
+        assert np.array_equal(t, o.t) and np.array_equal(y, o.y)
+    # per-trajectory parameters through the ensemble entry point, final states vs the oracle
+    rng = np.random.default_rng(8)
+    n = 64
+    par = np.stack([rng.uniform(0.5, 1.5, n), rng.uniform(1.0, 3.5, n)], 1)
+    y0 = rng.uniform(0.5, 3.0, (n, 2))
+    got = m.solve_ensemble(method, user_bruss, y0, [0.0, 5.0], params=par)
+    for i in (0, 17, 63):
+        o = O.solve_user(method, bruss, y0[i], [0.0, 5.0], list(par[i]), points="final")
+        assert np.array_equal(got["y_final"][i], o.y[-1]) and got["n_accept"][i] == o.n_accept
+    assert np.allclose(user_bruss(0.0, [1.5, 3.0]), bruss(0.0, [1.5, 3.0], [1.0, 3.0]))  # host evaluator
+
+
+def test_user_rhs_errors():
+    bad = m.register_rhs("broken", 2, 0, "f[0] = y[1]; f[1] = undefined_symbol;")
+    with pytest.raises(m.OdeB200Error, match="NVRTC compilation"):
+        m.ode45(bad, [1.0, 0.0], [0.0, 1.0])
+    with pytest.raises(m.OdeB200Error):
+        m.register_rhs("toolarge", 64, 0, "f[0] = 0.0;")
+    nojac = m.register_rhs("nojac", 1, 1, "f[0] = p[0] * y[0];", params=(1.0,))
+    with pytest.raises(m.OdeB200Error, match="without a Jacobian"):
+        m.ode23s(nojac, [1.0], [0.0, 1.0], jacobian=True)
+    t, y = m.ode45(nojac, 1.0, [0.0, 1.0])
+    assert abs(y[-1] - np.e) < 1e-4

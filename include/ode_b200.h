@@ -222,8 +222,8 @@ int ode_b200_solve_large(const ode_b200_opts* opts, int64_t n, const double* y0,
                          double t0, double tend, double* y_out, ode_b200_large_stats* stats,
                          double* trace, int64_t trace_cap, int64_t* trace_n);
 
-/* ode_b200_solve_large keeps the device buffers of the calling thread's last call for reuse;
- * this releases them. */
+/* The host-buffer entry points keep device memory of the calling thread's last call for reuse (the ensemble
+ * arena, the large-system session); this releases it. */
 void ode_b200_trim(void);
 
 /* Same with the reference's points = :specified contract (src/runge_kutta.jl:321-326): pts_y is

@@ -75,6 +75,15 @@ struct Arena {
   }
 };
 thread_local Arena g_arena;
+void arena_release() {  // ode_b200_trim
+  if (g_arena.base) {
+    cudaSetDevice(g_arena.dev);
+    cudaFree(g_arena.base);
+    g_arena.base = nullptr;
+    g_arena.cap = 0;
+    g_arena.dev = -1;
+  }
+}
 static size_t pad256(size_t b) { return (b + 255) & ~(size_t)255; }
 
 // ---- names -------------------------------------------------------------------

@@ -387,6 +387,9 @@ struct LargeCache {
   long long n = 0;
 };
 static thread_local LargeCache g_large_cache;
+namespace odeb200 {
+void arena_release();  // capi.cu
+}
 static void large_cache_release();
 
 static int slab_check(ode_b200_slab* s) {
@@ -744,7 +747,10 @@ static int solve_large_impl(const ode_b200_opts* o, int64_t n, const double* y0,
                             ode_b200_large_stats* stats, double* trace, int64_t trace_cap, int64_t* trace_n,
                             double* all_t = nullptr, int64_t all_cap = 0, int64_t* all_rows = nullptr);
 
-void ode_b200_trim(void) { large_cache_release(); }
+void ode_b200_trim(void) {
+  large_cache_release();
+  arena_release();
+}
 
 int ode_b200_solve_large(const ode_b200_opts* o, int64_t n, const double* y0, const double* params, double t0,
                          double tend, double* y_out, ode_b200_large_stats* stats, double* trace, int64_t trace_cap,

@@ -51,6 +51,15 @@ struct Arena {
         base = nullptr;
         cap = 0;
       }
+      if (dev != device && stream) {  // streams and events belong to the device they were created on
+        cudaSetDevice(dev);
+        cudaStreamDestroy(stream);
+        cudaStreamDestroy(stream2);
+        cudaEventDestroy(ev_in);
+        cudaEventDestroy(ev_done2);
+        stream = stream2 = nullptr;
+        ev_in = ev_done2 = nullptr;
+      }
       ODEB200_CUDA(cudaSetDevice(device));
       size_t want = bytes + (bytes >> 3) + (1 << 20);
       ODEB200_CUDA(cudaMalloc(&base, want));

@@ -40,6 +40,8 @@ extern "C" {
 #endif
 
 #define ODE_B200_ABI_VERSION 1
+/* doubles per rank in the exchange buffer of the slab sessions (see ode_b200_slab_*) */
+#define ODE_B200_XCHG_DOUBLES 96
 
 /* ---- methods: one per reference tableau / driver ------------------------- */
 typedef enum {
@@ -72,8 +74,9 @@ typedef enum {
   ODE_B200_RHS_REACTION_DIFFUSION = 8, /* dof N: kappa*((u[i-1]-2u[i])+u[i+1]) + (r*u[i])*(1-u[i]), periodic; params {kappa, r} */
   ODE_B200_RHS_COUNT = 9
 } ode_b200_rhs;
-/* ids returned by ode_b200_register_rhs start here */
+/* ids returned by ode_b200_register_rhs / ode_b200_register_stencil start here */
 #define ODE_B200_RHS_USER_BASE 1000
+#define ODE_B200_STENCIL_USER_BASE 2000
 
 /* `points` keyword (src/runge_kutta.jl:238,283-290); FINAL is an ensemble-only
  * extension that skips all intermediate output. */
@@ -179,6 +182,11 @@ double ode_b200_tableau(int method, int which, int i, int j);
  * Returns the rhs id (>= ODE_B200_RHS_USER_BASE) to put in opts.rhs, or a negative error code.
  * Available for the ensemble / single-system entry points (every method). */
 int ode_b200_register_rhs(const char* name, int32_t dof, int32_t n_params, const char* eval_body, const char* jac_body);
+/* Same for the large-system regime: a 3-point stencil F_i = point(u[i-1], u[i], u[i+1]; p0, p1) on a periodic
+ * grid.  `point_body` is the body of   double point(double um, double u, double up, double p0, double p1)
+ * (must `return` the value).  Returns an rhs id >= ODE_B200_STENCIL_USER_BASE for ode_b200_solve_large* and the
+ * slab sessions. */
+int ode_b200_register_stencil(const char* name, const char* point_body);
 
 /* ---- ensembles of small systems (one trajectory per thread) -------------- */
 /* Replaces n_traj independent calls of oderk_adapt / oderk_fixed / ode23s.
@@ -247,7 +255,6 @@ int ode_b200_solve_large_all(const ode_b200_opts* opts, int64_t n, const double*
  * two halves of an attempt the host exchanges `xchg_send` (ODE_B200_XCHG_DOUBLES
  * doubles per rank) with an all-gather into `xchg_recv` ([world][XCHG]).
  * All pointers are device pointers; work is enqueued on `stream`. */
-#define ODE_B200_XCHG_DOUBLES 96
 typedef struct ode_b200_slab ode_b200_slab;
 int ode_b200_slab_create(const ode_b200_opts* opts, int64_t n_local, int64_t n_global, int32_t rank,
                          int32_t world, const double* params, double t0, double tend, void* stream,

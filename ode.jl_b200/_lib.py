@@ -108,6 +108,7 @@ def lib():
     L.ode_b200_solve_large_all.argtypes = [C.POINTER(Opts), C.c_int64, dp, dp, dp, C.c_int32, C.c_int64, dp, dp, lp,
                                            C.POINTER(LargeStats), dp, C.c_int64, lp]
     L.ode_b200_trim.restype = None
+    L.ode_b200_register_stencil.argtypes = [C.c_char_p, C.c_char_p]
     L.ode_b200_register_rhs.argtypes = [C.c_char_p, C.c_int32, C.c_int32, C.c_char_p, C.c_char_p]
     L.ode_b200_slab_create.argtypes = [C.POINTER(Opts), C.c_int64, C.c_int64, C.c_int32, C.c_int32, dp, C.c_double,
                                        C.c_double, C.c_void_p, C.POINTER(C.c_void_p)]

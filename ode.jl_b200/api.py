@@ -95,7 +95,7 @@ class Solver:
 
 
 def _solve_single(name, F, y0, tspan, _stats=False, **kw):
-    if isinstance(F, DeviceRHS) and F.name == "reaction_diffusion":
+    if isinstance(F, DeviceRHS) and getattr(F, "is_stencil", False):
         # a dof = N method-of-lines state goes to the fused large-system kernels; same (tout, yout) contract
         from .large import solve_large
         kw.setdefault("points", "all")

@@ -10,6 +10,7 @@
 
 #include "host_util.cuh"
 #include "large.cuh"
+#include "rtc.cuh"
 
 namespace odeb200 {
 
@@ -211,58 +212,6 @@ __global__ void large_ghost_kernel(double* a, const double* xrecv, long long n, 
   }
 }
 
-template <int T>
-__device__ __forceinline__ double block_max_nanprop(double v, double* sh) {
-#pragma unroll
-  for (int o = 16; o > 0; o >>= 1) v = normInf_step(v, __shfl_down_sync(0xffffffffu, v, o));
-  if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = v;
-  __syncthreads();
-  double r = 0.0;
-  if (threadIdx.x == 0) {
-    r = sh[0];
-    for (int w = 1; w < T / 32; w++) r = normInf_step(r, sh[w]);
-  }
-  __syncthreads();
-  return r;
-}
-
-// phase 1: f0 = F(t0, y) on the interior -> K[par]; partial max|y|, max|f0|
-template <class Rhs>
-__global__ void __launch_bounds__(256) hinit_f0_kernel(const double* y, double* f0, double* part, long long n, int H,
-                                                       double p0, double p1) {
-  __shared__ double sh[8];
-  double my = 0.0, mf = 0.0;
-  for (long long i = blockIdx.x * 256LL + threadIdx.x; i < n; i += (long long)gridDim.x * 256) {
-    const double um = y[H + i - 1], u = y[H + i], up = y[H + i + 1];
-    const double f = Rhs::point(um, u, up, p0, p1);
-    f0[H + i] = f;
-    my = normInf_step(my, fabs(u));
-    mf = normInf_step(mf, fabs(f));
-  }
-  double a = block_max_nanprop<256>(my, sh);
-  double b = block_max_nanprop<256>(mf, sh);
-  if (threadIdx.x == 0) {
-    part[blockIdx.x * 2] = a;
-    part[blockIdx.x * 2 + 1] = b;
-  }
-}
-// phase 2: x1 = y + (tdir*h0)*f0, f1 = F(t0 + tdir*h0, x1); partial max|f1 - f0|
-template <class Rhs>
-__global__ void __launch_bounds__(256) hinit_f1_kernel(const double* y, const double* f0, const LargeCtl* ctl,
-                                                       double* part, long long n, int H, double p0, double p1) {
-  __shared__ double sh[8];
-  const double th = ctl->tdir * ctl->h0;
-  double md = 0.0;
-  for (long long i = blockIdx.x * 256LL + threadIdx.x; i < n; i += (long long)gridDim.x * 256) {
-    const double xm = y[H + i - 1] + th * f0[H + i - 1];
-    const double x = y[H + i] + th * f0[H + i];
-    const double xp = y[H + i + 1] + th * f0[H + i + 1];
-    const double f1 = Rhs::point(xm, x, xp, p0, p1);
-    md = normInf_step(md, fabs(f1 - f0[H + i]));
-  }
-  double a = block_max_nanprop<256>(md, sh);
-  if (threadIdx.x == 0) part[blockIdx.x * 2] = a;
-}
 __global__ void reduce_max_kernel(const double* part, int nblocks, int ncol, double* xsend) {
   // one warp; NaN-propagating max of each column
   for (int c = 0; c < ncol; c++) {
@@ -315,32 +264,39 @@ __global__ void hinit_control_kernel(LargeCtl* ctl, const double* xrecv, int wor
   }
 }
 
-typedef void (*AttemptKernel)(LargeArgs);
+// Kernel handles are `const void*`: a __global__ function pointer for the compiled-in stencil, a
+// cudaKernel_t for a stencil registered at run time (rtc.cu).
 struct MethodInfo {
-  AttemptKernel kernel;
+  const void *attempt, *hinit_f0, *hinit_f1;
   int H, VAL, order, S, fsal;
 };
-static int persistent_grid(AttemptKernel k, int device, long long tiles) {
+static int persistent_grid(const void* k, int device, long long tiles) {
   int sms = 0, per_sm = 0;
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device);
   if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k, LARGE_THREADS, 0) != cudaSuccess || per_sm < 1) {
     cudaGetLastError();
-    per_sm = 1;
+    per_sm = 4;
   }
   long long g = (long long)sms * per_sm;  // one wave of resident CTAs, each loops over its tiles
   if (g > tiles) g = tiles;
   return (int)(g < 1 ? 1 : g);
 }
 template <class Tab>
+static void geometry(MethodInfo* m) {
+  using Geo = LargeGeom<Tab, RhsReactionDiffusion>;  // geometry depends on the tableau only
+  m->H = Geo::H;
+  m->VAL = Geo::VAL;
+  m->order = Tab::ORDER;
+  m->S = Tab::S;
+  m->fsal = Geo::FSAL ? 1 : 0;
+}
+template <class Tab>
 static MethodInfo method_info() {
-  using Geo = LargeGeom<Tab, RhsReactionDiffusion>;
   MethodInfo m;
-  m.kernel = large_attempt_kernel<Tab, RhsReactionDiffusion>;
-  m.H = Geo::H;
-  m.VAL = Geo::VAL;
-  m.order = Tab::ORDER;
-  m.S = Tab::S;
-  m.fsal = Geo::FSAL ? 1 : 0;
+  geometry<Tab>(&m);
+  m.attempt = (const void*)large_attempt_kernel<Tab, RhsReactionDiffusion>;
+  m.hinit_f0 = (const void*)hinit_f0_kernel<RhsReactionDiffusion>;
+  m.hinit_f1 = (const void*)hinit_f1_kernel<RhsReactionDiffusion>;
   return m;
 }
 static bool pick_method(int method, MethodInfo* out) {
@@ -383,7 +339,7 @@ struct LargeCache {
   ode_b200_slab* s = nullptr;
   cudaStream_t st = nullptr;
   double *dy = nullptr, *xs = nullptr, *xr = nullptr;
-  int device = -1, method = -1;
+  int device = -1, method = -1, rhs = -1;
   long long n = 0;
 };
 static thread_local LargeCache g_large_cache;
@@ -410,15 +366,20 @@ int ode_b200_slab_create(const ode_b200_opts* o, int64_t n_local, int64_t n_glob
     return set_err(ODE_B200_E_NO_DEVICE, "no CUDA device available; libode_b200 has no CPU fallback");
   }
   if (o->device < 0 || o->device >= cnt) return set_err(ODE_B200_E_INVALID, "device %d out of range", o->device);
-  if (o->rhs != ODE_B200_RHS_REACTION_DIFFUSION)
-    return set_err(ODE_B200_E_UNSUPPORTED, "the large-system path takes a registered stencil RHS (reaction_diffusion)");
+  const bool user_stencil = o->rhs >= ODE_B200_STENCIL_USER_BASE;
+  if (o->rhs != ODE_B200_RHS_REACTION_DIFFUSION && !user_stencil)
+    return set_err(ODE_B200_E_UNSUPPORTED, "the large-system path takes a stencil RHS (reaction_diffusion or a registered stencil)");
   MethodInfo mi;
   if (!pick_method(o->method, &mi)) {
     if (o->method >= 0 && o->method <= ODE_B200_M_RK4)
       return set_err(ODE_B200_E_NOT_ADAPTIVE, "Can only use this solver with an adaptive RK Butcher table");
     return set_err(ODE_B200_E_UNSUPPORTED, "method %d has no large-system kernel", o->method);
   }
-  if (!params || o->n_params < 2) return set_err(ODE_B200_E_INVALID, "reaction_diffusion needs params {kappa, r}");
+  if (user_stencil) {  // same geometry, kernels compiled at run time for the registered point functor
+    ODEB200_CUDA(cudaSetDevice(o->device));
+    if (!user_stencil_kernels(o->rhs, o->method, &mi.attempt, &mi.hinit_f0, &mi.hinit_f1)) return ODE_B200_E_INVALID;
+  }
+  if (!params || o->n_params < 2) return set_err(ODE_B200_E_INVALID, "the stencil RHS needs two params (reaction_diffusion: {kappa, r})");
   if (world < 1 || rank < 0 || rank >= world) return set_err(ODE_B200_E_INVALID, "bad rank/world");
   if (n_local < 2 * mi.H || n_global < 32 || n_local > n_global)
     return set_err(ODE_B200_E_INVALID, "slab too small: n_local %lld (needs >= %d), n_global %lld (needs >= 32)",
@@ -441,7 +402,7 @@ int ode_b200_slab_create(const ode_b200_opts* o, int64_t n_local, int64_t n_glob
   s->mi = mi;
   s->stream = (cudaStream_t)stream;
   s->tiles = (n_local + mi.VAL - 1) / mi.VAL;
-  s->grid = persistent_grid(mi.kernel, o->device, s->tiles);
+  s->grid = persistent_grid(mi.attempt, o->device, s->tiles);
   s->p0 = params[0];
   s->p1 = params[1];
   const size_t padded = (size_t)(n_local + 2 * mi.H + 8) * sizeof(double);
@@ -626,7 +587,13 @@ int ode_b200_slab_init_phase(ode_b200_slab* s, int phase, double* xsend, const d
       break;
     case 1:
       large_ghost_kernel<<<1, 32, 0, st>>>(s->Y[0], xrecv, s->n, s->rank, s->world, H, 0);
-      hinit_f0_kernel<RhsReactionDiffusion><<<s->init_blocks, 256, 0, st>>>(s->Y[0], s->K[0], s->ipart, s->n, H, s->p0, s->p1);
+      {
+        const double* y = s->Y[0];
+        double* f0 = s->K[0];
+        int Hh = H;
+        void* a[] = {(void*)&y, (void*)&f0, (void*)&s->ipart, (void*)&s->n, (void*)&Hh, (void*)&s->p0, (void*)&s->p1};
+        ODEB200_CUDA(cudaLaunchKernel(s->mi.hinit_f0, dim3(s->init_blocks), dim3(256), a, 0, st));
+      }
       reduce_max_kernel<<<1, 32, 0, st>>>(s->ipart, s->init_blocks, 2, xsend);
       pack_edges_kernel<<<1, 32, 0, st>>>(s->K[0], xsend, s->n, H, 1);
       for (int i = 0; i < 4; i++) note_launch();
@@ -634,7 +601,14 @@ int ode_b200_slab_init_phase(ode_b200_slab* s, int phase, double* xsend, const d
     case 2:
       hinit_control_kernel<<<1, 32, 0, st>>>(s->ctl, xrecv, s->world, 0, s->mi.order);
       large_ghost_kernel<<<1, 32, 0, st>>>(s->K[0], xrecv, s->n, s->rank, s->world, H, 1);
-      hinit_f1_kernel<RhsReactionDiffusion><<<s->init_blocks, 256, 0, st>>>(s->Y[0], s->K[0], s->ctl, s->ipart, s->n, H, s->p0, s->p1);
+      {
+        const double* y = s->Y[0];
+        const double* f0 = s->K[0];
+        const LargeCtl* c = s->ctl;
+        int Hh = H;
+        void* a[] = {(void*)&y, (void*)&f0, (void*)&c, (void*)&s->ipart, (void*)&s->n, (void*)&Hh, (void*)&s->p0, (void*)&s->p1};
+        ODEB200_CUDA(cudaLaunchKernel(s->mi.hinit_f1, dim3(s->init_blocks), dim3(256), a, 0, st));
+      }
       reduce_max_kernel<<<1, 32, 0, st>>>(s->ipart, s->init_blocks, 1, xsend);
       for (int i = 0; i < 4; i++) note_launch();
       break;
@@ -664,9 +638,9 @@ int ode_b200_slab_attempt(ode_b200_slab* s, double* xsend) {
   A.tiles = s->tiles;
   A.p0 = s->p0;
   A.p1 = s->p1;
-  s->mi.kernel<<<(unsigned)s->grid, LARGE_THREADS, 0, s->stream>>>(A);
+  void* kargs[] = {(void*)&A};
+  ODEB200_CUDA(cudaLaunchKernel(s->mi.attempt, dim3((unsigned)s->grid), dim3(LARGE_THREADS), kargs, 0, s->stream));
   note_launch();
-  ODEB200_CUDA(cudaGetLastError());
   return 0;
 }
 
@@ -794,7 +768,7 @@ static int solve_large_impl(const ode_b200_opts* o, int64_t n, const double* y0,
   // 5 arrays of n doubles each time.  ode_b200_trim() releases them.
   LargeCache& cc = g_large_cache;
   int rc = 0;
-  if (cc.s && (cc.device != o->device || cc.method != o->method || cc.n != n)) large_cache_release();
+  if (cc.s && (cc.device != o->device || cc.method != o->method || cc.n != n || cc.rhs != o->rhs)) large_cache_release();
   if (!cc.s) {
     ODEB200_CUDA(cudaStreamCreateWithFlags(&cc.st, cudaStreamNonBlocking));
     rc = ode_b200_slab_create(o, n, n, 0, 1, params, t0, tend, cc.st, &cc.s);
@@ -808,10 +782,10 @@ static int solve_large_impl(const ode_b200_opts* o, int64_t n, const double* y0,
     }
     cc.device = o->device;
     cc.method = o->method;
+    cc.rhs = o->rhs;
     cc.n = n;
   } else {
-    if (o->rhs != ODE_B200_RHS_REACTION_DIFFUSION || !params || o->n_params < 2)
-      return set_err(ODE_B200_E_INVALID, "reaction_diffusion needs params {kappa, r}");
+    if (!params || o->n_params < 2) return set_err(ODE_B200_E_INVALID, "the stencil RHS needs two params");
     if (o->points != ODE_B200_POINTS_ALL && o->points != ODE_B200_POINTS_FINAL && o->points != ODE_B200_POINTS_SPECIFIED)
       return set_err(ODE_B200_E_POINTS, "Unrecognized option points==%d", o->points);
     cc.s->trace = nullptr;

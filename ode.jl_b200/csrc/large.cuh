@@ -412,6 +412,59 @@ __global__ void __launch_bounds__(LARGE_THREADS) large_attempt_kernel(const Larg
   }
 }
 
+// ---- hinit (src/ODE.jl:85-112) sweeps over the slab ---------------------------------------
+template <int T>
+__device__ __forceinline__ double block_max_nanprop(double v, double* sh) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = normInf_step(v, __shfl_down_sync(0xffffffffu, v, o));
+  if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = v;
+  __syncthreads();
+  double r = 0.0;
+  if (threadIdx.x == 0) {
+    r = sh[0];
+    for (int w = 1; w < T / 32; w++) r = normInf_step(r, sh[w]);
+  }
+  __syncthreads();
+  return r;
+}
+
+// phase 1: f0 = F(t0, y) on the interior -> K[par]; partial max|y|, max|f0|
+template <class Rhs>
+__global__ void __launch_bounds__(256) hinit_f0_kernel(const double* y, double* f0, double* part, long long n, int H,
+                                                       double p0, double p1) {
+  __shared__ double sh[8];
+  double my = 0.0, mf = 0.0;
+  for (long long i = blockIdx.x * 256LL + threadIdx.x; i < n; i += (long long)gridDim.x * 256) {
+    const double um = y[H + i - 1], u = y[H + i], up = y[H + i + 1];
+    const double f = Rhs::point(um, u, up, p0, p1);
+    f0[H + i] = f;
+    my = normInf_step(my, fabs(u));
+    mf = normInf_step(mf, fabs(f));
+  }
+  double a = block_max_nanprop<256>(my, sh);
+  double b = block_max_nanprop<256>(mf, sh);
+  if (threadIdx.x == 0) {
+    part[blockIdx.x * 2] = a;
+    part[blockIdx.x * 2 + 1] = b;
+  }
+}
+// phase 2: x1 = y + (tdir*h0)*f0, f1 = F(t0 + tdir*h0, x1); partial max|f1 - f0|
+template <class Rhs>
+__global__ void __launch_bounds__(256) hinit_f1_kernel(const double* y, const double* f0, const LargeCtl* ctl,
+                                                       double* part, long long n, int H, double p0, double p1) {
+  __shared__ double sh[8];
+  const double th = ctl->tdir * ctl->h0;
+  double md = 0.0;
+  for (long long i = blockIdx.x * 256LL + threadIdx.x; i < n; i += (long long)gridDim.x * 256) {
+    const double xm = y[H + i - 1] + th * f0[H + i - 1];
+    const double x = y[H + i] + th * f0[H + i];
+    const double xp = y[H + i + 1] + th * f0[H + i + 1];
+    const double f1 = Rhs::point(xm, x, xp, p0, p1);
+    md = normInf_step(md, fabs(f1 - f0[H + i]));
+  }
+  double a = block_max_nanprop<256>(md, sh);
+  if (threadIdx.x == 0) part[blockIdx.x * 2] = a;
+}
 // ---- control: global accept/reject from the gathered partials --------------------
 // One block.  xrecv is [world][XCHG]; every rank runs the same arithmetic on the
 // same data, so all ranks take the same decision and the same new dt.

@@ -28,6 +28,7 @@ struct UserRhs {
   int dof, np;
 };
 static std::vector<UserRhs> g_user;
+static std::vector<UserRhs> g_stencils;  // eval_body = body of point(um, u, up, p0, p1)
 static std::map<std::string, const void*> g_kernels;  // key -> cudaKernel_t
 static std::mutex g_mu;
 
@@ -106,6 +107,55 @@ static const char* tab_name(int method) {
   }
 }
 
+// NVRTC-compile `src` (which includes this library's kernel headers), load the cubin and resolve the kernels
+// named by the template-instantiation expressions `exprs`.
+static bool compile_and_load(const std::string& what, const std::string& src, const char* const* exprs, int n,
+                             const void** out) {
+  if (load_nvrtc()) return false;
+  nvrtcProgram prog;
+  nvrtcResult r = g_nvrtc.CreateProgram(&prog, src.c_str(), "user_rhs.cu", 0, nullptr, nullptr);
+  if (r != NVRTC_SUCCESS) {
+    set_err(ODE_B200_E_CUDA, "nvrtcCreateProgram: %s", g_nvrtc.GetErrorString(r));
+    return false;
+  }
+  for (int i = 0; i < n; i++) g_nvrtc.AddNameExpression(prog, exprs[i]);
+  const std::string dir = library_dir();
+  const std::string i1 = "-I" + dir + "/csrc", i2 = "-I" + dir + "/../include";
+  // -fmad=false: the reference never fuses multiply-add; -default-device: lambdas inside the kernels
+  const char* opts[] = {"--gpu-architecture=sm_100a", "-std=c++17", "-fmad=false", "-lineinfo", "-default-device",
+                        i1.c_str(), i2.c_str()};
+  r = g_nvrtc.CompileProgram(prog, 7, opts);
+  if (r != NVRTC_SUCCESS) {
+    size_t nl = 0;
+    g_nvrtc.GetProgramLogSize(prog, &nl);
+    std::string log(nl + 1, '\0');
+    if (nl) g_nvrtc.GetProgramLog(prog, &log[0]);
+    set_err(ODE_B200_E_INVALID, "NVRTC compilation of rhs '%s' failed: %.380s", what.c_str(), log.c_str());
+    g_nvrtc.DestroyProgram(&prog);
+    return false;
+  }
+  size_t nb = 0;
+  g_nvrtc.GetCUBINSize(prog, &nb);
+  std::vector<char> cubin(nb);
+  g_nvrtc.GetCUBIN(prog, cubin.data());
+  cudaLibrary_t lib = nullptr;
+  cudaError_t e = cudaLibraryLoadData(&lib, cubin.data(), nullptr, nullptr, 0, nullptr, nullptr, 0);
+  for (int i = 0; i < n && e == cudaSuccess; i++) {
+    const char* lowered = nullptr;
+    g_nvrtc.GetLoweredName(prog, exprs[i], &lowered);
+    cudaKernel_t kern = nullptr;
+    e = cudaLibraryGetKernel(&kern, lib, lowered ? lowered : "");
+    out[i] = (const void*)kern;
+  }
+  g_nvrtc.DestroyProgram(&prog);
+  if (e != cudaSuccess) {
+    cudaGetLastError();
+    set_err(ODE_B200_E_CUDA, "loading the compiled rhs '%s' failed: %s", what.c_str(), cudaGetErrorString(e));
+    return false;
+  }
+  return true;
+}
+
 // Kernel of `method` instantiated for the registered RHS; nullptr + last_error on failure.
 const void* user_kernel(int rhs, int method, int mode, int literal, int jac) {
   UserRhs u;
@@ -150,7 +200,6 @@ const void* user_kernel(int rhs, int method, int mode, int literal, int jac) {
     auto it = g_kernels.find(key);
     if (it != g_kernels.end()) return it->second;
   }
-  if (load_nvrtc()) return nullptr;
   const int npa = u.np > 0 ? u.np : 1;
   std::string src = "#include \"" + std::string(header) + "\"\nnamespace odeb200 {\nstruct RhsUser {\n";
   char buf[512];
@@ -166,48 +215,64 @@ const void* user_kernel(int rhs, int method, int mode, int literal, int jac) {
            u.dof, u.dof, u.dof, npa);
   src += buf;
   src += u.jac_body + "\n  }\n};\n}  // namespace odeb200\n";
-
-  nvrtcProgram prog;
-  nvrtcResult r = g_nvrtc.CreateProgram(&prog, src.c_str(), "user_rhs.cu", 0, nullptr, nullptr);
-  if (r != NVRTC_SUCCESS) {
-    set_err(ODE_B200_E_CUDA, "nvrtcCreateProgram: %s", g_nvrtc.GetErrorString(r));
-    return nullptr;
-  }
-  g_nvrtc.AddNameExpression(prog, expr);
-  const std::string dir = library_dir();
-  const std::string i1 = "-I" + dir + "/csrc", i2 = "-I" + dir + "/../include";
-  // -fmad=false: the reference never fuses multiply-add; -default-device: lambdas inside the kernels
-  const char* opts[] = {"--gpu-architecture=sm_100a", "-std=c++17", "-fmad=false", "-lineinfo", "-default-device",
-                        i1.c_str(), i2.c_str()};
-  r = g_nvrtc.CompileProgram(prog, 7, opts);
-  if (r != NVRTC_SUCCESS) {
-    size_t n = 0;
-    g_nvrtc.GetProgramLogSize(prog, &n);
-    std::string log(n + 1, '\0');
-    if (n) g_nvrtc.GetProgramLog(prog, &log[0]);
-    set_err(ODE_B200_E_INVALID, "NVRTC compilation of rhs '%s' failed: %.380s", u.name.c_str(), log.c_str());
-    g_nvrtc.DestroyProgram(&prog);
-    return nullptr;
-  }
-  const char* lowered = nullptr;
-  size_t nb = 0;
-  g_nvrtc.GetLoweredName(prog, expr, &lowered);
-  g_nvrtc.GetCUBINSize(prog, &nb);
-  std::vector<char> cubin(nb);
-  g_nvrtc.GetCUBIN(prog, cubin.data());
-  cudaLibrary_t lib = nullptr;
-  cudaKernel_t kern = nullptr;
-  cudaError_t e = cudaLibraryLoadData(&lib, cubin.data(), nullptr, nullptr, 0, nullptr, nullptr, 0);
-  if (e == cudaSuccess) e = cudaLibraryGetKernel(&kern, lib, lowered ? lowered : "");
-  g_nvrtc.DestroyProgram(&prog);
-  if (e != cudaSuccess) {
-    cudaGetLastError();
-    set_err(ODE_B200_E_CUDA, "loading the compiled rhs '%s' failed: %s", u.name.c_str(), cudaGetErrorString(e));
-    return nullptr;
-  }
+  const char* exprs[1] = {expr};
+  const void* out[1] = {nullptr};
+  if (!compile_and_load(u.name, src, exprs, 1, out)) return nullptr;
   std::lock_guard<std::mutex> lk(g_mu);
-  g_kernels[key] = (const void*)kern;
-  return (const void*)kern;
+  g_kernels[key] = out[0];
+  return out[0];
+}
+
+bool user_stencil_kernels(int rhs, int method, const void** attempt, const void** hinit_f0, const void** hinit_f1) {
+  UserRhs u;
+  {
+    std::lock_guard<std::mutex> lk(g_mu);
+    int i = rhs - ODE_B200_STENCIL_USER_BASE;
+    if (i < 0 || i >= (int)g_stencils.size()) {
+      set_err(ODE_B200_E_INVALID, "unknown user stencil %d", rhs);
+      return false;
+    }
+    u = g_stencils[i];
+  }
+  const char* tab = tab_name(method);
+  if (!tab || method < ODE_B200_M_RK21 || method > ODE_B200_M_FEH78) {
+    set_err(ODE_B200_E_NOT_ADAPTIVE, "Can only use this solver with an adaptive RK Butcher table");
+    return false;
+  }
+  int dev = 0;
+  cudaGetDevice(&dev);
+  char e0[256], e1[128], e2[128], keyb[512];
+  snprintf(e0, sizeof(e0), "odeb200::large_attempt_kernel<%s, odeb200::StencilUser>", tab);
+  snprintf(e1, sizeof(e1), "odeb200::hinit_f0_kernel<odeb200::StencilUser>");
+  snprintf(e2, sizeof(e2), "odeb200::hinit_f1_kernel<odeb200::StencilUser>");
+  snprintf(keyb, sizeof(keyb), "%d|%d|%s", dev, rhs, e0);
+  const std::string key(keyb);
+  {
+    std::lock_guard<std::mutex> lk(g_mu);
+    auto it = g_kernels.find(key);
+    if (it != g_kernels.end()) {
+      *attempt = it->second;
+      *hinit_f0 = g_kernels[key + "|f0"];
+      *hinit_f1 = g_kernels[key + "|f1"];
+      return true;
+    }
+  }
+  std::string src =
+      "#include \"large.cuh\"\nnamespace odeb200 {\nstruct StencilUser {\n"
+      "  static constexpr int NP = 2, RADIUS = 1, ID = 0;\n"
+      "  __device__ __forceinline__ static double point(double um, double u, double up, double p0, double p1) {\n" +
+      u.eval_body + "\n  }\n};\n}  // namespace odeb200\n";
+  const char* exprs[3] = {e0, e1, e2};
+  const void* out[3] = {nullptr, nullptr, nullptr};
+  if (!compile_and_load(u.name, src, exprs, 3, out)) return false;
+  std::lock_guard<std::mutex> lk(g_mu);
+  g_kernels[key] = out[0];
+  g_kernels[key + "|f0"] = out[1];
+  g_kernels[key + "|f1"] = out[2];
+  *attempt = out[0];
+  *hinit_f0 = out[1];
+  *hinit_f1 = out[2];
+  return true;
 }
 
 }  // namespace odeb200
@@ -227,4 +292,16 @@ extern "C" int ode_b200_register_rhs(const char* name, int32_t dof, int32_t n_pa
   u.np = n_params;
   g_user.push_back(u);
   return ODE_B200_RHS_USER_BASE + (int)g_user.size() - 1;
+}
+
+extern "C" int ode_b200_register_stencil(const char* name, const char* point_body) {
+  if (!name || !point_body) return set_err(ODE_B200_E_INVALID, "register_stencil: need a name and the body of point()");
+  std::lock_guard<std::mutex> lk(g_mu);
+  UserRhs u;
+  u.name = name;
+  u.eval_body = point_body;
+  u.dof = 0;
+  u.np = 2;
+  g_stencils.push_back(u);
+  return ODE_B200_STENCIL_USER_BASE + (int)g_stencils.size() - 1;
 }

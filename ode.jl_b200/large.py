@@ -35,8 +35,8 @@ def shard_bounds(n_global, world, rank):
 def solve_large(alg, F, y0, tspan, *, trace=False, trace_cap=65536, out=None, **kw):
     """One GPU, host buffers in and out.  Returns dict(y, t_final, n_accept, n_reject, n_rhs, status, kernel_ms[, trace]).
     `out` (optional) is a caller-owned float64 array for the final state, e.g. pinned memory."""
-    if not isinstance(F, DeviceRHS) or F.name != "reaction_diffusion":
-        raise TypeError("the large-system path takes DeviceRHS('reaction_diffusion', kappa, r)")
+    if not isinstance(F, DeviceRHS) or not getattr(F, "is_stencil", False):
+        raise TypeError("the large-system path takes DeviceRHS('reaction_diffusion', kappa, r) or a register_stencil token")
     y0 = np.ascontiguousarray(np.asarray(y0, dtype=np.float64))
     ts = np.asarray(tspan, dtype=np.float64)
     kw.setdefault("points", "final")

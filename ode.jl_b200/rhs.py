@@ -35,6 +35,22 @@ def register_rhs(name, dof, n_params, eval_body, jac_body=None, host=None, param
     return tok
 
 
+def register_stencil(name, point_body, host=None, params=(0.0, 0.0)):
+    """Register a 3-point periodic stencil for the large-system regime from CUDA C++ source.
+
+    point_body : body of  double point(double um, double u, double up, double p0, double p1)  (must `return`)
+    host       : optional python callable host(um, u, up, p0, p1) for DeviceRHS.__call__ on whole arrays"""
+    from ._lib import lib, check
+    rid = lib().ode_b200_register_stencil(name.encode(), point_body.encode())
+    if rid < 0:
+        check(rid)
+    tok = DeviceRHS.__new__(DeviceRHS)
+    tok.name, tok.id, tok.dof, tok.n_params, tok.params = name, rid, 0, 2, tuple(params)
+    tok._host = host
+    tok.is_stencil = True
+    return tok
+
+
 class DeviceRHS:
     """`DeviceRHS("lorenz", 10.0, 28.0, 8/3)`; calling it evaluates F(t, y) on the host."""
 
@@ -49,6 +65,7 @@ class DeviceRHS:
         self.dof = _DOF[name]
         self.n_params = _NP[name]
         self.params = params
+        self.is_stencil = name == "reaction_diffusion"
 
     def with_params(self, p):
         if p is None:
@@ -73,6 +90,11 @@ class DeviceRHS:
         return a
 
     def __call__(self, t, y):
+        if self.id >= 2000:
+            if getattr(self, "_host", None) is None:
+                raise TypeError("run-time stencil %r was registered without a host evaluator" % self.name)
+            u = np.asarray(y, dtype=np.float64)
+            return np.array([self._host(u[i - 1], u[i], u[(i + 1) % u.size], *self.params) for i in range(u.size)])
         if self.id >= 1000:
             if getattr(self, "_host", None) is None:
                 raise TypeError("run-time RHS %r was registered without a host evaluator" % self.name)

@@ -251,15 +251,23 @@ Tab make_tab(int method) {
 // the Python restatement state the same expressions independently.
 typedef void (*UserRhsFn)(double t, const double* y, double* f, const double* p, int dof);
 typedef void (*UserJacFn)(double t, const double* y, double* J, const double* p, int dof);
+typedef double (*UserPointFn)(double um, double u, double up, double p0, double p1);  // 3-point periodic stencil
 struct Rhs {
   int id;
   int64_t dof;
   const double* p;
   UserRhsFn user = nullptr;  // run-time RHS (tests pass a ctypes callback evaluating the same expression)
   UserJacFn user_jac = nullptr;
+  UserPointFn user_point = nullptr;  // run-time stencil of the large-system regime
   mutable int64_t calls = 0;
   void operator()(double t, const double* y, double* f) const {
     calls++;
+    if (user_point) {
+      const int64_t n = dof;
+      for (int64_t i = 0; i < n; i++)
+        f[i] = user_point(y[i == 0 ? n - 1 : i - 1], y[i], y[i == n - 1 ? 0 : i + 1], p[0], p[1]);
+      return;
+    }
     if (user) {
       user(t, y, f, p, (int)dof);
       return;
@@ -946,11 +954,14 @@ void ode4ms(const Rhs& F, const Vec& x0, const Vec& tspan, Result& R) {
 
 thread_local UserRhsFn g_user_rhs = nullptr;
 thread_local UserJacFn g_user_jac = nullptr;
+thread_local UserPointFn g_user_point = nullptr;
 
 void solve_one(const ode_b200_opts* op, const double* y0, const double* params, const double* tspan, int n_tspan,
                bool want_trace, Result& R) {
   Rhs F{op->rhs, op->dof, params};
-  if (op->rhs >= ODE_B200_RHS_USER_BASE) {
+  if (op->rhs >= ODE_B200_STENCIL_USER_BASE) {
+    F.user_point = g_user_point;
+  } else if (op->rhs >= ODE_B200_RHS_USER_BASE) {
     F.user = g_user_rhs;
     F.user_jac = g_user_jac;
   }
@@ -991,6 +1002,7 @@ void oracle_set_user_rhs(UserRhsFn f, UserJacFn j) {
   g_user_rhs = f;
   g_user_jac = j;
 }
+void oracle_set_user_stencil(UserPointFn f) { g_user_point = f; }
 
 int oracle_solve(const ode_b200_opts* op, const double* y0, const double* params, const double* tspan, int n_tspan,
                  int want_trace, oracle_result** out) {

@@ -83,6 +83,8 @@ def lib():
         L.oracle_max_threads.restype = C.c_int
         L.oracle_set_user_rhs.argtypes = [C.c_void_p, C.c_void_p]
         L.oracle_set_user_rhs.restype = None
+        L.oracle_set_user_stencil.argtypes = [C.c_void_p]
+        L.oracle_set_user_stencil.restype = None
         L.oracle_set_threads.argtypes = [C.c_int]
         L.oracle_set_threads.restype = None
         _lib = L
@@ -250,3 +252,18 @@ def solve_user(method, f, y0, tspan, params=None, jac=None, **kw):
         return solve(method, USER_RHS_BASE, y0a, tspan, params, **kw2)
     finally:
         L.oracle_set_user_rhs(None, None)
+
+
+STENCIL_BASE = 2000
+_POINTFN = C.CFUNCTYPE(C.c_double, C.c_double, C.c_double, C.c_double, C.c_double, C.c_double)
+
+
+def solve_user_stencil(method, point, y0, tspan, params, **kw):
+    """Large system with a python 3-point stencil point(um, u, up, p0, p1) -> float on a periodic grid."""
+    L = lib()
+    cb = _POINTFN(point)
+    L.oracle_set_user_stencil(C.cast(cb, C.c_void_p))
+    try:
+        return solve(method, STENCIL_BASE, y0, tspan, params, **kw)
+    finally:
+        L.oracle_set_user_stencil(None)

@@ -104,3 +104,36 @@ def test_user_rhs_errors():
         m.ode23s(nojac, [1.0], [0.0, 1.0], jacobian=True)
     t, y = m.ode45(nojac, 1.0, [0.0, 1.0])
     assert abs(y[-1] - np.e) < 1e-4
+
+
+RD_BODY = "return p0 * ((um - 2.0 * u) + up) + (p1 * u) * (1.0 - u);"
+NAGUMO_BODY = "return p0 * ((um - 2.0 * u) + up) + ((p1 * u) * (1.0 - u)) * (u - 0.25);"  # not built in
+
+
+def nagumo(um, u, up, p0, p1):
+    return p0 * ((um - 2.0 * u) + up) + ((p1 * u) * (1.0 - u)) * (u - 0.25)
+
+
+def test_user_stencil_large_system():
+    """Run-time registered 3-point stencils on the fused large-system kernels."""
+    n = 3000
+    i = np.arange(n)
+    u0 = 0.5 + 0.4 * np.sin(2 * np.pi * 3 * i / n)
+    rd = m.register_stencil("user_rd", RD_BODY, params=(1.0, 1.0))
+    for method in ("ode45", "ode23", "ode78"):
+        a = m.solve_large(method, rd, u0, [0.0, 3.0], trace=True)
+        b = m.solve_large(method, m.DeviceRHS("reaction_diffusion", 1.0, 1.0), u0, [0.0, 3.0], trace=True)
+        assert np.array_equal(a["y"], b["y"]) and np.array_equal(a["trace"], b["trace"])
+    ng = m.register_stencil("nagumo", NAGUMO_BODY, host=nagumo, params=(0.8, 2.0))
+    n = 600
+    u0 = 0.5 + 0.45 * np.sin(2 * np.pi * 2 * np.arange(n) / n)
+    ts = [0.0, 0.4, 2.0]
+    for method, points in (("ode45", "specified"), ("ode23", "all")):
+        t, y, st = getattr(m, method).stats(ng, u0, ts, points=points)
+        o = O.solve_user_stencil(method, nagumo, u0, ts, [0.8, 2.0], points=points)
+        assert np.array_equal(t, o.t) and np.array_equal(y, o.y)
+        assert (st["n_accept"], st["n_reject"], st["n_rhs"]) == (o.n_accept, o.n_reject, o.n_rhs)
+    w = u0[:5]
+    assert np.allclose(ng(0.0, w), [nagumo(w[k - 1], w[k], w[(k + 1) % 5], 0.8, 2.0) for k in range(5)])
+    with pytest.raises(m.OdeB200Error, match="NVRTC compilation"):
+        m.solve_large("ode45", m.register_stencil("bad", "return undefined_thing;"), u0, [0.0, 1.0])

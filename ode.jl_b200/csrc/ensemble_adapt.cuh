@@ -55,7 +55,7 @@ __device__ __forceinline__ void hermite_point(double* out, double tq, double t, 
 // 4 CTAs/SM) and tighter bounds that spill.  Larger state x stage products are left unconstrained.
 template <class Tab, class Rhs>
 constexpr int adapt_min_blocks() {
-  return (Rhs::DOF <= 3 && Rhs::DOF * Tab::S <= 21) ? 5 : 1;
+  return (Rhs::DOF <= 3 && Rhs::DOF * Tab::S <= 21) ? (5 * 128) / ENS_BLOCK : 1;  // 640 resident threads per SM
 }
 
 template <class Tab, class Rhs, int MODE, bool LITERAL>

@@ -45,10 +45,10 @@ __global__ void __launch_bounds__(ENS_BLOCK) ens_fixed_kernel(const EnsembleArgs
         static_for<s>([&](auto J) {
           constexpr int ss = decltype(J)::value;
           constexpr double a = Tab::a(s, ss);
-          if constexpr (a != 0.0) {
+          // every coefficient is multiplied, zeros included, exactly like the reference (Inf*0 = NaN);
+          // these kernels are not FP64-critical, so no second "literal" pass is needed here
 #pragma unroll
-            for (int d = 0; d < D; d++) ytmp[d] = ytmp[d] + dtk[ss][d] * a;  // (dt*k)*a :454
-          }
+          for (int d = 0; d < D; d++) ytmp[d] = ytmp[d] + dtk[ss][d] * a;  // (dt*k)*a :454
         });
         constexpr double c = Tab::c(s);
         Rhs::eval(ti + c * dt, ytmp, ks, p);  // :456
@@ -56,7 +56,7 @@ __global__ void __launch_bounds__(ENS_BLOCK) ens_fixed_kernel(const EnsembleArgs
 #pragma unroll
         for (int d = 0; d < D; d++) {
           dtk[s][d] = dt * ks[d];
-          if constexpr (b != 0.0) ynew[d] = ynew[d] + (dt * b) * ks[d];  // :207
+          ynew[d] = ynew[d] + (dt * b) * ks[d];  // :207
         }
       });
 #pragma unroll

@@ -382,3 +382,19 @@ def test_full_size_kepler_and_robertson_invariants():
                            reltol=1e-8, abstol=1e-8)
     assert np.all(got["status"] == 0) and np.all(got["t_final"] == 1e5)
     assert np.max(np.abs(got["y_final"].sum(1) - 1.0)) < 1e-7 and got["y_final"].min() > -1e-9
+
+
+@pytest.mark.parametrize("method", FIXED + ["ode4ms", "ode4s_s"])
+def test_fixed_step_blowup_matches_oracle(method):
+    """Fixed-step solvers on a trajectory that overflows: Inf/NaN pattern as in the reference (every tableau
+    coefficient is multiplied, so Inf*0 = NaN)."""
+    ts = np.linspace(0.0, 2.0, 41)
+    y0 = np.array([[1e150, -1e150, 1e150], [1.0, 1.0, 1.0]])
+    got = m.solve_ensemble(method, m.DeviceRHS("lorenz", *LORENZ), y0, ts, points="specified")
+    for i in range(2):
+        o = O.solve(method, "lorenz", y0[i], ts, LORENZ)
+        k = len(o.t)  # the Rosenbrock solvers stop at a singular W (Julia raises SingularException there)
+        assert got["pts_n"][i] == k and got["status"][i] == o.status, (method, i)
+        assert np.array_equal(got["pts_y"][i, :k], o.y, equal_nan=True), (method, i)
+    if method != "ode4s_s":  # the L-stable Rosenbrock step survives 1e150; the explicit ones overflow
+        assert not np.all(np.isfinite(got["pts_y"][0]))

@@ -241,8 +241,27 @@ static EnsembleKernel pick_kernel_fn(const ode_b200_opts* o, int mode, int liter
 // Launch on `stream` with device pointers.  `counter` points at 32 bytes of device scratch: the work
 // counter of the fast pass, the redo count, and the work counter of the literal pass.  io->status must
 // be non-null for the adaptive RK methods (the two passes communicate through it).
+static const void* pick_init_kernel(const ode_b200_opts* o) {
+  if (o->rhs >= ODE_B200_RHS_USER_BASE) return user_init_kernel(o->rhs, o->method);
+  switch (o->method) {
+    case ODE_B200_M_RK21: return (const void*)adapt_kernel_rk21_init(o->rhs);
+    case ODE_B200_M_RK23: return (const void*)adapt_kernel_rk23_init(o->rhs);
+    case ODE_B200_M_RK45_FE: return (const void*)adapt_kernel_rk45_init(o->rhs);
+    case ODE_B200_M_DOPRI5: return (const void*)adapt_kernel_dopri5_init(o->rhs);
+    case ODE_B200_M_FEH78: return (const void*)adapt_kernel_feh78_init(o->rhs);
+    default: return nullptr;
+  }
+}
+// doubles of pre-pass scratch launch_ensemble can use for this call (0: hinit stays inline)
+static size_t init_scratch_doubles(const ode_b200_opts* o, const ode_b200_ensemble_io* io) {
+  const bool want_points = io->pts_y != nullptr || io->trace != nullptr;
+  const bool mode1 = (want_points && o->points != ODE_B200_POINTS_FINAL) || io->trace;
+  if (mode1 || io->n_traj < 4096 || !pick_init_kernel(o)) return 0;
+  return (size_t)io->n_traj * (size_t)(o->dof + 1);
+}
+
 static int launch_ensemble(const ode_b200_opts* o, const ode_b200_ensemble_io* io, unsigned long long* counter,
-                           cudaStream_t stream, bool time_it) {
+                           cudaStream_t stream, bool time_it, double* init_scratch = nullptr) {
   const bool want_points = io->pts_y != nullptr || io->trace != nullptr;
   const int mode = (want_points && o->points != ODE_B200_POINTS_FINAL) || io->trace ? 1 : 0;
   const void* k = pick_kernel(o, mode);
@@ -309,6 +328,13 @@ static int launch_ensemble(const ode_b200_opts* o, const ode_b200_ensemble_io* i
     ODEB200_CUDA(cudaEventRecord(g_ev0, stream));
   }
   void* kargs[] = {(void*)&A};
+  if (init_scratch && init_scratch_doubles(o, io) > 0) {  // hinit of every trajectory with full warps
+    A.init = init_scratch;
+    long long gi = (long long)sms * 8;
+    if (need < gi) gi = need;
+    ODEB200_CUDA(cudaLaunchKernel(pick_init_kernel(o), dim3((unsigned)gi), dim3(ENS_BLOCK), kargs, 0, stream));
+    note_launch();
+  }
   ODEB200_CUDA(cudaLaunchKernel(k, dim3((unsigned)grid), dim3(ENS_BLOCK), kargs, 0, stream));
   note_launch();
   if (two_pass) {
@@ -458,7 +484,17 @@ int ode_b200_solve_ensemble_dev(const ode_b200_opts* opts, const ode_b200_ensemb
     }
     d.status = status_scratch;
   }
-  return launch_ensemble(opts, &d, counter, (cudaStream_t)stream, true);
+  static thread_local double* init_scratch = nullptr;
+  static thread_local size_t init_cap = 0;
+  static thread_local int init_dev = -1;
+  const size_t want = init_scratch_doubles(opts, &d);
+  if (want > 0 && (init_dev != opts->device || init_cap < want)) {
+    if (init_scratch && init_dev == opts->device) cudaFree(init_scratch);
+    ODEB200_CUDA(cudaMalloc(&init_scratch, want * sizeof(double)));
+    init_cap = want;
+    init_dev = opts->device;
+  }
+  return launch_ensemble(opts, &d, counter, (cudaStream_t)stream, true, want > 0 ? init_scratch : nullptr);
 }
 
 int ode_b200_solve_ensemble(const ode_b200_opts* opts, const ode_b200_ensemble_io* io) {
@@ -479,6 +515,8 @@ int ode_b200_solve_ensemble(const ode_b200_opts* opts, const ode_b200_ensemble_i
                  pad256(n * D * 8) + 4 * pad256(n * 4);
   if (pts) bytes += pad256((size_t)n * io->pts_cap * 8) + pad256((size_t)n * io->pts_cap * D * 8) + pad256(n * 4);
   if (io->trace) bytes += pad256((size_t)io->trace_cap * 32) + 256;
+  const size_t init_doubles = init_scratch_doubles(opts, io);  // hinit pre-pass scratch (0: inline)
+  bytes += pad256(init_doubles * 8);
   rc = g_arena.ensure(opts->device, bytes);
   if (rc) return rc;
   cudaStream_t st = g_arena.stream;
@@ -496,6 +534,7 @@ int ode_b200_solve_ensemble(const ode_b200_opts* opts, const ode_b200_ensemble_i
   d.n_reject = io->n_reject ? g_arena.take<int>(n) : nullptr;
   d.n_rhs = io->n_rhs ? g_arena.take<int>(n) : nullptr;
   d.status = g_arena.take<int>(n);  // always: the fast and literal adaptive-RK passes talk through it
+  double* dinit = init_doubles ? g_arena.take<double>(init_doubles) : nullptr;
   if (pts) {
     d.pts_t = g_arena.take<double>((size_t)n * io->pts_cap);
     d.pts_y = g_arena.take<double>((size_t)n * io->pts_cap * D);
@@ -563,7 +602,8 @@ int ode_b200_solve_ensemble(const ode_b200_opts* opts, const ode_b200_ensemble_i
       if (d.pts_n) dc.pts_n = d.pts_n + lo;
     }
     if (n_chunks == 1) ODEB200_CUDA(cudaEventRecord(g_ev0, cs));
-    rc = launch_ensemble(opts, &dc, n_chunks > 1 ? counters + 32 * c : counter, cs, false);
+    rc = launch_ensemble(opts, &dc, n_chunks > 1 ? counters + 32 * c : counter, cs, false,
+                         dinit ? dinit + lo * (D + 1) : nullptr);
     if (rc) return rc;
     if (n_chunks == 1) ODEB200_CUDA(cudaEventRecord(g_ev1, cs));
     if (io->t_final) ODEB200_CUDA(cudaMemcpyAsync(io->t_final + lo, dc.t_final, m * 8, cudaMemcpyDeviceToHost, cs));

@@ -12,6 +12,11 @@ EnsembleKernel adapt_kernel_rk23(int rhs, int mode, int literal);
 EnsembleKernel adapt_kernel_rk45(int rhs, int mode, int literal);
 EnsembleKernel adapt_kernel_dopri5(int rhs, int mode, int literal);
 EnsembleKernel adapt_kernel_feh78(int rhs, int mode, int literal);
+EnsembleKernel adapt_kernel_rk21_init(int rhs);  // hinit pre-pass (ens_adapt_init_kernel)
+EnsembleKernel adapt_kernel_rk23_init(int rhs);  // hinit pre-pass (ens_adapt_init_kernel)
+EnsembleKernel adapt_kernel_rk45_init(int rhs);  // hinit pre-pass (ens_adapt_init_kernel)
+EnsembleKernel adapt_kernel_dopri5_init(int rhs);  // hinit pre-pass (ens_adapt_init_kernel)
+EnsembleKernel adapt_kernel_feh78_init(int rhs);  // hinit pre-pass (ens_adapt_init_kernel)
 EnsembleKernel fixed_kernel(int method, int rhs);
 EnsembleKernel ode23s_kernel(int rhs, int mode, int jac);  // jac: 0 fdjacobian, 1 analytic functor
 EnsembleKernel rosenbrock_kernel(int method, int rhs, int jac);
@@ -44,6 +49,7 @@ EnsembleKernel ms4_kernel(int rhs);
     } else {                                                                                   \
       ODEB200_RHS_SWITCH(rhs, ODEB200_ADAPT_M0_##TAB)                                          \
     }                                                                                          \
-  }
+  }                                                                                            \
+  EnsembleKernel NAME##_init(int rhs) { ODEB200_RHS_SWITCH(rhs, ODEB200_ADAPT_INIT_##TAB) }
 
 }  // namespace odeb200

@@ -50,6 +50,67 @@ __device__ __forceinline__ void hermite_point(double* out, double tq, double t, 
   }
 }
 
+// hinit, src/ODE.jl:85-112 with p = min(order): returns the signed first step, leaves f0 in k1 (-> ks[1]).
+template <class Tab, class Rhs>
+__device__ __forceinline__ double hinit_rk(const EnsembleArgs& A, double tstart, double tend, double tdir,
+                                           const double (&y)[Rhs::DOF], const double (&p)[RhsNP<Rhs>::value],
+                                           double (&k1)[Rhs::DOF]) {
+  constexpr int D = Rhs::DOF;
+  double n0 = fabs(y[0]);
+#pragma unroll
+  for (int d = 1; d < D; d++) n0 = normInf_step(n0, fabs(y[d]));
+  double tau = jl_max(A.reltol * n0, A.abstol);  // :89
+  double d0 = n0 / tau;                          // :90
+  Rhs::eval(tstart, y, k1, p);                   // :91  f0
+  double n1 = fabs(k1[0]);
+#pragma unroll
+  for (int d = 1; d < D; d++) n1 = normInf_step(n1, fabs(k1[d]));
+  double d1 = n1 / tau;  // :92
+  double h0 = (d0 < 1e-5 || d1 < 1e-5) ? 1e-6 : 0.01 * (d0 / d1);  // :93-97
+  double x1[D], f1[D];
+  double th = tdir * h0;
+#pragma unroll
+  for (int d = 0; d < D; d++) x1[d] = y[d] + th * k1[d];  // :100
+  Rhs::eval(tstart + tdir * h0, x1, f1, p);               // :101
+  double n2 = fabs(f1[0] - k1[0]);
+#pragma unroll
+  for (int d = 1; d < D; d++) n2 = normInf_step(n2, fabs(f1[d] - k1[d]));
+  double d2 = n2 / (tau * h0);  // :103
+  double dm = jl_max(d1, d2);
+  double h1;
+  if (dm <= 1e-15) {
+    h1 = jl_max(1e-6, 1e-3 * h0);  // :105
+  } else {
+    double pw = -(2.0 + dm_log10(dm)) / (double)(Tab::ORDER + 1);  // :107
+    h1 = dm_pow(10.0, pw);                                         // :108
+  }
+  return tdir * jl_min(jl_min(100.0 * h0, h1), tdir * (tend - tstart));  // :111
+}
+
+// Initial step and f0 of every trajectory, one lane per trajectory with full warps.  Inside the
+// persistent kernel a lane that fetches a new trajectory would run these ~300 instructions alone
+// while its 31 neighbours wait (2.6 % of all issue slots on Lorenz/dopri5, profiles/ensemble_lorenz_r1.md);
+// here the same arithmetic costs 1/32 of that.  init[idx] = {dt, f0[0..D)}.
+template <class Tab, class Rhs>
+__global__ void __launch_bounds__(ENS_BLOCK) ens_adapt_init_kernel(const EnsembleArgs A) {
+  constexpr int D = Rhs::DOF, NPA = RhsNP<Rhs>::value;
+  const double tstart = A.tspan[0];
+  const double tend = A.tspan[A.n_tspan - 1];
+  const double tdir = jl_sign(tend - tstart);
+  for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < A.n_traj;
+       idx += (long long)gridDim.x * blockDim.x) {
+    double y[D], k1[D], p[NPA];
+#pragma unroll
+    for (int d = 0; d < D; d++) y[d] = A.y0[idx * D + d];
+#pragma unroll
+    for (int q = 0; q < NPA; q++) p[q] = (q < Rhs::NP) ? A.params[idx * A.params_stride + q] : 0.0;
+    double* out = A.init + idx * (D + 1);
+    out[0] = hinit_rk<Tab, Rhs>(A, tstart, tend, tdir, y, p, k1);
+#pragma unroll
+    for (int d = 0; d < D; d++) out[1 + d] = k1[d];
+  }
+}
+
 // Resident CTAs per SM asked of ptxas.  Measured on Lorenz/dopri5 (profiles/ensemble_lorenz_r1.md):
 // 5 CTAs/SM (<= 102 registers, no spill) beats both the unconstrained allocation (119 registers,
 // 4 CTAs/SM) and tighter bounds that spill.  Larger state x stage products are left unconstrained.
@@ -101,39 +162,15 @@ __global__ void __launch_bounds__(ENS_BLOCK, LITERAL ? 1 : adapt_min_blocks<Tab,
       iter = 2;
       iter_fixed = 2;
       ntrace = 0;
-      // hinit, src/ODE.jl:85-112 (p = order)
-      {
-        double n0 = fabs(y[0]);
+      if (MODE == 0 && !LITERAL && A.init != nullptr) {  // computed by ens_adapt_init_kernel with all lanes busy
+        const double* in = A.init + idx * (D + 1);
+        dt = in[0];
 #pragma unroll
-        for (int d = 1; d < D; d++) n0 = normInf_step(n0, fabs(y[d]));
-        double tau = jl_max(A.reltol * n0, A.abstol);  // :89
-        double d0 = n0 / tau;                          // :90
-        Rhs::eval(tstart, y, k1, p);                   // :91  f0 -> ks[1]
-        double n1 = fabs(k1[0]);
-#pragma unroll
-        for (int d = 1; d < D; d++) n1 = normInf_step(n1, fabs(k1[d]));
-        double d1 = n1 / tau;  // :92
-        double h0 = (d0 < 1e-5 || d1 < 1e-5) ? 1e-6 : 0.01 * (d0 / d1);  // :93-97
-        double x1[D], f1[D];
-        double th = tdir * h0;
-#pragma unroll
-        for (int d = 0; d < D; d++) x1[d] = y[d] + th * k1[d];  // :100
-        Rhs::eval(tstart + tdir * h0, x1, f1, p);               // :101
-        double n2 = fabs(f1[0] - k1[0]);
-#pragma unroll
-        for (int d = 1; d < D; d++) n2 = normInf_step(n2, fabs(f1[d] - k1[d]));
-        double d2 = n2 / (tau * h0);  // :103
-        double dm = jl_max(d1, d2);
-        double h1;
-        if (dm <= 1e-15) {
-          h1 = jl_max(1e-6, 1e-3 * h0);  // :105
-        } else {
-          double pw = -(2.0 + dm_log10(dm)) / (double)(Tab::ORDER + 1);  // :107
-          h1 = dm_pow(10.0, pw);                                         // :108
-        }
-        dt = tdir * jl_min(jl_min(100.0 * h0, h1), tdir * (tend - tstart));  // :111
-        nrhs = 2;
+        for (int d = 0; d < D; d++) k1[d] = in[1 + d];
+      } else {
+        dt = hinit_rk<Tab, Rhs>(A, tstart, tend, tdir, y, p, k1);
       }
+      nrhs = 2;
       if (A.initstep != 0.0) dt = A.initstep;            // :293-295 (sign checked on the host)
       islast = fabs(t + dt - tend) <= jl_eps(tend);      // :302
       if (MODE == 1) {

@@ -168,11 +168,13 @@ const void* user_kernel(int rhs, int method, int mode, int literal, int jac) {
     }
     u = g_user[i];
   }
-  char expr[512];
+  char expr[512], expr_init[256] = "";
   const char* header = "ensemble_adapt.cuh";
   if (method >= ODE_B200_M_RK21 && method <= ODE_B200_M_FEH78) {
     snprintf(expr, sizeof(expr), "odeb200::ens_adapt_kernel<%s, odeb200::RhsUser, %d, %s>", tab_name(method), mode ? 1 : 0,
              literal ? "true" : "false");
+    if (!mode && !literal)  // the hinit pre-pass travels with the mode-0 fast kernel
+      snprintf(expr_init, sizeof(expr_init), "odeb200::ens_adapt_init_kernel<%s, odeb200::RhsUser>", tab_name(method));
   } else if (method <= ODE_B200_M_RK4) {
     header = "ensemble_fixed.cuh";
     snprintf(expr, sizeof(expr), "odeb200::ens_fixed_kernel<%s, odeb200::RhsUser>", tab_name(method));
@@ -215,12 +217,26 @@ const void* user_kernel(int rhs, int method, int mode, int literal, int jac) {
            u.dof, u.dof, u.dof, npa);
   src += buf;
   src += u.jac_body + "\n  }\n};\n}  // namespace odeb200\n";
-  const char* exprs[1] = {expr};
-  const void* out[1] = {nullptr};
-  if (!compile_and_load(u.name, src, exprs, 1, out)) return nullptr;
+  const char* exprs[2] = {expr, expr_init};
+  const void* out[2] = {nullptr, nullptr};
+  if (!compile_and_load(u.name, src, exprs, expr_init[0] ? 2 : 1, out)) return nullptr;
   std::lock_guard<std::mutex> lk(g_mu);
   g_kernels[key] = out[0];
+  if (expr_init[0]) g_kernels[key + "|init"] = out[1];
   return out[0];
+}
+
+// hinit pre-pass kernel that was compiled together with the mode-0 fast kernel of (rhs, method); nullptr if none.
+const void* user_init_kernel(int rhs, int method) {
+  if (method < ODE_B200_M_RK21 || method > ODE_B200_M_FEH78) return nullptr;
+  if (!user_kernel(rhs, method, 0, 0, 0)) return nullptr;
+  int dev = 0;
+  cudaGetDevice(&dev);
+  char keyb[640];
+  snprintf(keyb, sizeof(keyb), "%d|%d|odeb200::ens_adapt_kernel<%s, odeb200::RhsUser, 0, false>|init", dev, rhs, tab_name(method));
+  std::lock_guard<std::mutex> lk(g_mu);
+  auto it = g_kernels.find(keyb);
+  return it == g_kernels.end() ? nullptr : it->second;
 }
 
 bool user_stencil_kernels(int rhs, int method, const void** attempt, const void** hinit_f0, const void** hinit_f1) {

@@ -398,3 +398,27 @@ def test_fixed_step_blowup_matches_oracle(method):
         assert np.array_equal(got["pts_y"][i, :k], o.y, equal_nan=True), (method, i)
     if method != "ode4s_s":  # the L-stable Rosenbrock step survives 1e150; the explicit ones overflow
         assert not np.all(np.isfinite(got["pts_y"][0]))
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("method", ["ode21", "ode23", "ode45_fe", "ode45", "ode78"])
+def test_hinit_prepass_equals_inline_hinit(method):
+    """Ensembles of >= 4096 trajectories take the initial step and f0 from ens_adapt_init_kernel; smaller
+    ones compute hinit inside the persistent kernel.  Same bits either way (forward and backward spans,
+    per-trajectory parameters), and the same as the oracle on a few trajectories."""
+    rng = np.random.default_rng(77)
+    n = 6000
+    y0 = np.stack([rng.uniform(-10, 10, n), rng.uniform(-10, 10, n), rng.uniform(5, 35, n)], 1)
+    par = np.stack([rng.uniform(8, 12, n), rng.uniform(20, 30, n), rng.uniform(2, 3, n)], 1)
+    F = m.DeviceRHS("lorenz", *LORENZ)
+    # backward spans can run away after a rejection (reference quirk, SURVEY Q6): bound the attempts
+    for ts in ([0.0, 0.7], [0.3, -0.2]):
+        kw = dict(params=par, max_steps=400)
+        big = m.solve_ensemble(method, F, y0, ts, **kw)
+        halves = [m.solve_ensemble(method, F, y0[s], ts, params=par[s], max_steps=400)
+                  for s in (slice(0, 3000), slice(3000, n))]
+        for k in ("y_final", "t_final", "n_accept", "n_reject", "n_rhs", "status"):
+            assert np.array_equal(big[k], np.concatenate([h[k] for h in halves])), (k, ts)
+        for i in (0, 2999, 5999):
+            o = O.solve(method, "lorenz", y0[i], ts, list(par[i]), points="final", max_steps=400)
+            assert np.array_equal(big["y_final"][i], o.y[-1]) and big["n_rhs"][i] == o.n_rhs and big["status"][i] == o.status

@@ -91,6 +91,14 @@ def test_user_rhs_not_builtin_matches_oracle_callback(method, user_bruss):
         o = O.solve_user(method, bruss, y0[i], [0.0, 5.0], list(par[i]), points="final")
         assert np.array_equal(got["y_final"][i], o.y[-1]) and got["n_accept"][i] == o.n_accept
     assert np.allclose(user_bruss(0.0, [1.5, 3.0]), bruss(0.0, [1.5, 3.0], [1.0, 3.0]))  # host evaluator
+    if method != "ode23s":  # >= 4096 trajectories: hinit comes from the NVRTC-compiled pre-pass kernel
+        n = 5000
+        par = np.stack([rng.uniform(0.5, 1.5, n), rng.uniform(1.0, 3.5, n)], 1)
+        y0 = rng.uniform(0.5, 3.0, (n, 2))
+        big = m.solve_ensemble(method, user_bruss, y0, [0.0, 2.0], params=par)
+        small = m.solve_ensemble(method, user_bruss, y0[:100], [0.0, 2.0], params=par[:100])
+        for k in ("y_final", "n_accept", "n_reject", "n_rhs"):
+            assert np.array_equal(big[k][:100], small[k]), k
 
 
 def test_user_rhs_errors():

@@ -261,10 +261,15 @@ static size_t init_scratch_doubles(const ode_b200_opts* o, const ode_b200_ensemb
 }
 
 static int launch_ensemble(const ode_b200_opts* o, const ode_b200_ensemble_io* io, unsigned long long* counter,
-                           cudaStream_t stream, bool time_it, double* init_scratch = nullptr) {
+                           cudaStream_t stream, bool time_it, double* init_scratch = nullptr,
+                           const double* uparams_host = nullptr) {
   const bool want_points = io->pts_y != nullptr || io->trace != nullptr;
   const int mode = (want_points && o->points != ODE_B200_POINTS_FINAL) || io->trace ? 1 : 0;
-  const void* k = pick_kernel(o, mode);
+  // one parameter vector for the whole ensemble: the mode-0 fast kernel reads it from the constant bank
+  int np_u = 0, dof_u = 0;
+  rhs_shape(o->rhs, &dof_u, &np_u, nullptr);
+  const bool uniform = mode == 0 && is_adaptive_rk(o->method) && o->params_stride == 0 && np_u <= 16 && (np_u == 0 || uparams_host);
+  const void* k = pick_kernel(o, mode, uniform ? 2 : 0);
   if (!k) {
     if (o->rhs >= ODE_B200_RHS_USER_BASE) return ODE_B200_E_INVALID;  // last_error set by the run-time compiler
     return set_err(ODE_B200_E_UNSUPPORTED, "no kernel for method %d / rhs %d", o->method, o->rhs);
@@ -300,6 +305,8 @@ static int launch_ensemble(const ode_b200_opts* o, const ode_b200_ensemble_io* i
   A.trace_n = (long long*)io->trace_n;
   A.work_counter = counter;
   A.redo_count = reinterpret_cast<int*>(counter + 1);
+  if (uniform)
+    for (int q = 0; q < np_u; q++) A.uparams[q] = uparams_host[q];
   const bool two_pass = is_adaptive_rk(o->method);
   if (two_pass && !A.status) return set_err(ODE_B200_E_INVALID, "internal: adaptive RK launch without a status buffer");
 
@@ -457,7 +464,13 @@ int ode_b200_solve_ensemble_dev(const ode_b200_opts* opts, const ode_b200_ensemb
   ODEB200_CUDA(cudaSetDevice(opts->device));
   // the span is needed on the host for the reference's argument errors
   double ends[2] = {0, 0};
+  double upar[16];
+  int np_dev = 0, dof_dev = 0;
+  const bool fetch_upar = rhs_shape(opts->rhs, &dof_dev, &np_dev, nullptr) && np_dev > 0 && np_dev <= 16 &&
+                          opts->params_stride == 0 && io->params != nullptr;
   if (io->n_tspan >= 2 && io->tspan) {
+    if (fetch_upar)
+      ODEB200_CUDA(cudaMemcpyAsync(upar, io->params, (size_t)np_dev * 8, cudaMemcpyDeviceToHost, (cudaStream_t)stream));
     ODEB200_CUDA(cudaMemcpyAsync(&ends[0], io->tspan, 8, cudaMemcpyDeviceToHost, (cudaStream_t)stream));
     ODEB200_CUDA(cudaMemcpyAsync(&ends[1], io->tspan + (io->n_tspan - 1), 8, cudaMemcpyDeviceToHost, (cudaStream_t)stream));
     ODEB200_CUDA(cudaStreamSynchronize((cudaStream_t)stream));
@@ -494,7 +507,8 @@ int ode_b200_solve_ensemble_dev(const ode_b200_opts* opts, const ode_b200_ensemb
     init_cap = want;
     init_dev = opts->device;
   }
-  return launch_ensemble(opts, &d, counter, (cudaStream_t)stream, true, want > 0 ? init_scratch : nullptr);
+  return launch_ensemble(opts, &d, counter, (cudaStream_t)stream, true, want > 0 ? init_scratch : nullptr,
+                         fetch_upar ? upar : nullptr);
 }
 
 int ode_b200_solve_ensemble(const ode_b200_opts* opts, const ode_b200_ensemble_io* io) {
@@ -603,7 +617,7 @@ int ode_b200_solve_ensemble(const ode_b200_opts* opts, const ode_b200_ensemble_i
     }
     if (n_chunks == 1) ODEB200_CUDA(cudaEventRecord(g_ev0, cs));
     rc = launch_ensemble(opts, &dc, n_chunks > 1 ? counters + 32 * c : counter, cs, false,
-                         dinit ? dinit + lo * (D + 1) : nullptr);
+                         dinit ? dinit + lo * (D + 1) : nullptr, opts->params_stride == 0 ? io->params : nullptr);
     if (rc) return rc;
     if (n_chunks == 1) ODEB200_CUDA(cudaEventRecord(g_ev1, cs));
     if (io->t_final) ODEB200_CUDA(cudaMemcpyAsync(io->t_final + lo, dc.t_final, m * 8, cudaMemcpyDeviceToHost, cs));

@@ -6,7 +6,8 @@
 namespace odeb200 {
 
 // mode: 0 = final state + counters only, 1 = tout/yout points + trace
-// literal: 0 = fast pass (zero coefficients dropped, marks non-finite trajectories), 1 = literal redo pass
+// literal: 0 = fast pass (zero coefficients dropped, marks non-finite trajectories), 1 = literal redo pass,
+//          2 = fast pass, mode 0, one parameter vector for the whole ensemble (read from the constant bank)
 EnsembleKernel adapt_kernel_rk21(int rhs, int mode, int literal);
 EnsembleKernel adapt_kernel_rk23(int rhs, int mode, int literal);
 EnsembleKernel adapt_kernel_rk45(int rhs, int mode, int literal);
@@ -37,6 +38,9 @@ EnsembleKernel ms4_kernel(int rhs);
 
 #define ODEB200_DEFINE_ADAPT(NAME, TAB)                                                        \
   EnsembleKernel NAME(int rhs, int mode, int literal) {                                        \
+    if (literal == 2) {                                                                        \
+      ODEB200_RHS_SWITCH(rhs, ODEB200_ADAPT_M0U_##TAB)                                         \
+    }                                                                                          \
     if (literal) {                                                                             \
       if (mode) {                                                                              \
         ODEB200_RHS_SWITCH(rhs, ODEB200_ADAPT_M1L_##TAB)                                       \

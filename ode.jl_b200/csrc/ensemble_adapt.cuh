@@ -119,8 +119,9 @@ constexpr int adapt_min_blocks() {
   return (Rhs::DOF <= 3 && Rhs::DOF * Tab::S <= 21) ? (5 * 128) / ENS_BLOCK : 1;  // 640 resident threads per SM
 }
 
-template <class Tab, class Rhs, int MODE, bool LITERAL>
-__global__ void __launch_bounds__(ENS_BLOCK, LITERAL ? 1 : adapt_min_blocks<Tab, Rhs>()) ens_adapt_kernel(const EnsembleArgs A) {
+template <class Tab, class Rhs, int MODE, bool LITERAL, bool PU = false>
+__global__ void __launch_bounds__(ENS_BLOCK, LITERAL ? 1 : adapt_min_blocks<Tab, Rhs>() + (PU ? ODEB200_PU_EXTRA : 0))
+    ens_adapt_kernel(const __grid_constant__ EnsembleArgs A) {
   if (LITERAL && *A.redo_count == 0) return;  // nothing was marked by the fast pass
   constexpr int D = Rhs::DOF, S = Tab::S, NPA = RhsNP<Rhs>::value;
   constexpr bool FSAL = Tab::fsal();
@@ -134,11 +135,12 @@ __global__ void __launch_bounds__(ENS_BLOCK, LITERAL ? 1 : adapt_min_blocks<Tab,
   const int nfixed = A.n_tspan;
 
   long long idx = -1;
-  double y[D], k1[D], p[NPA];
+  double y[D], k1[D], pl[NPA];
+  // PU: one parameter vector for the whole ensemble, read from the kernel-parameter constant bank
+  const double (&p)[NPA] = PU ? reinterpret_cast<const double (&)[NPA]>(A.uparams) : const_cast<const double (&)[NPA]>(pl);
   double t = 0.0, dt = 0.0;
-  int timeout = 0, nacc = 0, nrej = 0, nrhs = 0;
+  int timeout = 0, nacc = 0, nrej = 0;
   bool islast = false;
-  long long attempts = 0;
   int iter = 2, iter_fixed = 2, npts = 0;  // 1-based like the reference (:286,:304)
   long long ntrace = 0;
 
@@ -153,11 +155,12 @@ __global__ void __launch_bounds__(ENS_BLOCK, LITERAL ? 1 : adapt_min_blocks<Tab,
       // ---------------------------------------------------------- init :256-304
 #pragma unroll
       for (int d = 0; d < D; d++) y[d] = A.y0[idx * D + d];
+      if (!PU) {
 #pragma unroll
-      for (int q = 0; q < NPA; q++) p[q] = (q < Rhs::NP) ? A.params[idx * A.params_stride + q] : 0.0;
+        for (int q = 0; q < NPA; q++) pl[q] = (q < Rhs::NP) ? A.params[idx * A.params_stride + q] : 0.0;
+      }
       t = tstart;
       nacc = nrej = 0;
-      attempts = 0;
       timeout = 0;  // :303
       iter = 2;
       iter_fixed = 2;
@@ -170,7 +173,6 @@ __global__ void __launch_bounds__(ENS_BLOCK, LITERAL ? 1 : adapt_min_blocks<Tab,
       } else {
         dt = hinit_rk<Tab, Rhs>(A, tstart, tend, tdir, y, p, k1);
       }
-      nrhs = 2;
       if (A.initstep != 0.0) dt = A.initstep;            // :293-295 (sign checked on the host)
       islast = fabs(t + dt - tend) <= jl_eps(tend);      // :302
       if (MODE == 1) {
@@ -193,7 +195,6 @@ __global__ void __launch_bounds__(ENS_BLOCK, LITERAL ? 1 : adapt_min_blocks<Tab,
     }
 
     // ------------------------------------------------ rk_embedded_step! :371-399
-    attempts++;
     double ytrial[D], yerr[D], dtk[NK][D], klast[D];
     constexpr double b10 = Tab::b(0, 0), b20 = Tab::b(1, 0);
 #pragma unroll
@@ -227,7 +228,6 @@ __global__ void __launch_bounds__(ENS_BLOCK, LITERAL ? 1 : adapt_min_blocks<Tab,
         if constexpr (s == S - 1) klast[d] = ks[d];
       }
     });
-    nrhs += S - 1;
 #pragma unroll
     for (int d = 0; d < D; d++) {  // :395-398
       yerr[d] = dt * (ytrial[d] - yerr[d]);
@@ -291,7 +291,6 @@ __global__ void __launch_bounds__(ENS_BLOCK, LITERAL ? 1 : adapt_min_blocks<Tab,
         for (int d = 0; d < D; d++) f1[d] = klast[d];
       } else {
         Rhs::eval(t + dt, ytrial, f1, p);
-        nrhs++;
       }
       if (MODE == 1) {
         double* py = A.pts_y + (idx * A.pts_cap) * D;
@@ -329,10 +328,16 @@ __global__ void __launch_bounds__(ENS_BLOCK, LITERAL ? 1 : adapt_min_blocks<Tab,
         for (int d = 0; d < D; d++) y[d] = ytrial[d];  // :347
         t += dt;                                       // :350
         dt = newdt;                                    // :351
-        const double tl = t + dt + dt / 100;  // :354-357, tdir*a >= tdir*b as a signed compare
-        if (fwd ? (tl >= tend) : (tl <= tend)) {
-          dt = tend - t;
-          islast = true;
+        // :354-357  tdir*(t+dt+dt/100) >= tdir*tend, as a signed compare.  The division is skipped when the
+        // test cannot pass: dt/100 <= |dt|/16 and rounding is monotone, so (t+dt)+dt/100 <= (t+dt)+|dt|/16
+        // (mirror image backwards); a NaN dt fails the filter and takes the exact test.
+        const double sdt = t + dt, mdt = fabs(dt) * 0.0625;
+        if (!(fwd ? (sdt + mdt < tend) : (sdt - mdt > tend))) {
+          const double tl = sdt + dt / 100;
+          if (fwd ? (tl >= tend) : (tl <= tend)) {
+            dt = tend - t;
+            islast = true;
+          }
         }
       }
     } else if (fabs(newdt) < A.minstep) {  // :358-360
@@ -344,9 +349,12 @@ __global__ void __launch_bounds__(ENS_BLOCK, LITERAL ? 1 : adapt_min_blocks<Tab,
       timeout = 5;
       if (!is_finite(dt)) fin = ODE_B200_ST_NONFINITE;  // the reference would spin forever
     }
-    if (fin < 0 && attempts >= A.max_steps) fin = ODE_B200_ST_MAXSTEPS;
+    if (fin < 0 && nacc + nrej >= A.max_steps) fin = ODE_B200_ST_MAXSTEPS;  // every attempt so far was counted
 
     if (fin >= 0) {
+      // RHS calls: 2 in hinit, S-1 per attempt (a minstep stop is an attempt in neither counter), +1 per
+      // accepted step without FSAL
+      const int nrhs = 2 + (S - 1) * (nacc + nrej + (fin == ODE_B200_ST_MINSTEP ? 1 : 0)) + (FSAL ? 0 : nacc);
       if (MODE == 1 && npts > A.pts_cap && A.pts_y) fin = ODE_B200_ST_OVERFLOW;
       if (A.t_final) A.t_final[idx] = fin_trial ? t + dt : t;
       if (A.y_final) {

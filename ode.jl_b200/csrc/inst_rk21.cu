@@ -6,6 +6,7 @@ namespace odeb200 {
 #define ODEB200_ADAPT_M1_TabRK21(R) return ens_adapt_kernel<TabRK21, R, 1, false>
 #define ODEB200_ADAPT_M0L_TabRK21(R) return ens_adapt_kernel<TabRK21, R, 0, true>
 #define ODEB200_ADAPT_M1L_TabRK21(R) return ens_adapt_kernel<TabRK21, R, 1, true>
+#define ODEB200_ADAPT_M0U_TabRK21(R) return ens_adapt_kernel<TabRK21, R, 0, false, true>
 #define ODEB200_ADAPT_INIT_TabRK21(R) return ens_adapt_init_kernel<TabRK21, R>
 ODEB200_DEFINE_ADAPT(adapt_kernel_rk21, TabRK21)
 }  // namespace odeb200

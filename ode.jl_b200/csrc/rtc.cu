@@ -171,8 +171,8 @@ const void* user_kernel(int rhs, int method, int mode, int literal, int jac) {
   char expr[512], expr_init[256] = "";
   const char* header = "ensemble_adapt.cuh";
   if (method >= ODE_B200_M_RK21 && method <= ODE_B200_M_FEH78) {
-    snprintf(expr, sizeof(expr), "odeb200::ens_adapt_kernel<%s, odeb200::RhsUser, %d, %s>", tab_name(method), mode ? 1 : 0,
-             literal ? "true" : "false");
+    snprintf(expr, sizeof(expr), "odeb200::ens_adapt_kernel<%s, odeb200::RhsUser, %d, %s%s>", tab_name(method), mode ? 1 : 0,
+             literal == 1 ? "true" : "false", literal == 2 ? ", true" : "");  // 2: uniform-parameter fast kernel
     if (!mode && !literal)  // the hinit pre-pass travels with the mode-0 fast kernel
       snprintf(expr_init, sizeof(expr_init), "odeb200::ens_adapt_init_kernel<%s, odeb200::RhsUser>", tab_name(method));
   } else if (method <= ODE_B200_M_RK4) {

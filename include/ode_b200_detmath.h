@@ -15,7 +15,7 @@
  *
  * Technique (standard, table-driven): log via an exact fma reduction
  * r = z*invc - 1 with an 8-bit invc and a 128-entry log(c) table kept as
- * hi + lo, a degree-10 Taylor tail, result carried as a double-double; exp via
+ * hi + lo, a degree-10 Taylor tail (pairwise evaluation), result carried as a double-double; exp via
  * k = round(x*128/ln2), an exact hi reduction, a 128-entry 2^(j/128) table and a
  * final compensated `th + th*q + ...` so there is one effective rounding.
  *
@@ -133,19 +133,27 @@ DM_HD dm_dd dm_log_dd(double x) {
 
   double r = dm_fma(z, invc, -1.0);         /* exact */
   double t1 = dm_fma(kd, DM_LN2_HI, logc);  /* exact: both on the 2^-42 grid */
-  dm_dd a = dm_two_sum(t1, r);              /* t1 + r */
+  /* fast two-sums are exact here: t1 is 0 or |t1| >= 1.9 |r| (checked over the whole table; |r| < 2^-7),
+     and |t1 + r| >= r^2/2 */
+  dm_dd a;
+  a.hi = t1 + r;
+  a.lo = (t1 - a.hi) + r;
   double r2 = r * r;
   double r2e = dm_fma(r, r, -r2);           /* r*r = r2 + r2e */
-  dm_dd b = dm_two_sum(a.hi, -0.5 * r2);    /* ... - r^2/2 */
-  /* r^3/3 - r^4/4 + ... + r^9/9 - r^10/10 */
-  double p = -0.1;
-  p = dm_fma(p, r, 0x1.c71c71c71c71cp-4);   /* 1/9 */
-  p = dm_fma(p, r, -0.125);
-  p = dm_fma(p, r, 0x1.2492492492492p-3);   /* 1/7 */
-  p = dm_fma(p, r, -0x1.5555555555555p-3);  /* 1/6 */
-  p = dm_fma(p, r, 0.2);
-  p = dm_fma(p, r, -0.25);
-  p = dm_fma(p, r, 0x1.5555555555555p-2);   /* 1/3 */
+  double hr2 = -0.5 * r2;
+  dm_dd b;
+  b.hi = a.hi + hr2;                        /* ... - r^2/2 */
+  b.lo = (a.hi - b.hi) + hr2;
+  /* r^3/3 - r^4/4 + ... + r^9/9 - r^10/10 = r^3 * (c0 + c1 r + ... + c7 r^7), evaluated pairwise
+     (Estrin) so the dependency chain is 3 fma deep instead of 7; the tail is < 2^-24 of the result */
+  double p01 = dm_fma(-0.25, r, 0x1.5555555555555p-2);                  /* 1/3 - r/4 */
+  double p23 = dm_fma(-0x1.5555555555555p-3, r, 0.2);                   /* 1/5 - r/6 */
+  double p45 = dm_fma(-0.125, r, 0x1.2492492492492p-3);                 /* 1/7 - r/8 */
+  double p67 = dm_fma(-0.1, r, 0x1.c71c71c71c71cp-4);                   /* 1/9 - r/10 */
+  double r4 = r2 * r2;
+  double p03 = dm_fma(p23, r2, p01);
+  double p47 = dm_fma(p67, r2, p45);
+  double p = dm_fma(p47, r4, p03);
   p = p * (r * r2);
   double lo = ((a.lo + b.lo) + (-0.5 * r2e)) + dm_fma(kd, DM_LN2_LO, logct);
   lo = lo + p;
@@ -177,13 +185,14 @@ DM_HD double dm_exp_dd(double ehi, double elo) {
   int64_t e2 = (ki - j) / 128; /* exact: ki - j is a multiple of 128 */
   double th = DM_EXPTAB(2 * j), tl = DM_EXPTAB(2 * j + 1);
   /* exp(q) - 1 - q = q^2 (1/2 + q/6 + ... + q^5/5040) */
-  double p = 0x1.a01a01a01a01ap-13;            /* 1/5040 */
-  p = dm_fma(p, q, 0x1.6c16c16c16c17p-10);     /* 1/720 */
-  p = dm_fma(p, q, 0x1.1111111111111p-7);      /* 1/120 */
-  p = dm_fma(p, q, 0x1.5555555555555p-5);      /* 1/24 */
-  p = dm_fma(p, q, 0x1.5555555555555p-3);      /* 1/6 */
-  p = dm_fma(p, q, 0.5);
-  double rest = dm_fma(q * q, p, dm_fma(q, ql, ql));
+  /* pairwise (Estrin): 3 fma deep instead of 6 */
+  double q2 = q * q;
+  double e01 = dm_fma(0x1.5555555555555p-3, q, 0.5);                     /* 1/2 + q/6 */
+  double e23 = dm_fma(0x1.1111111111111p-7, q, 0x1.5555555555555p-5);    /* 1/24 + q/120 */
+  double e45 = dm_fma(0x1.a01a01a01a01ap-13, q, 0x1.6c16c16c16c17p-10);  /* 1/720 + q/5040 */
+  double q4 = q2 * q2;
+  double p = dm_fma(e45, q4, dm_fma(e23, q2, e01));
+  double rest = dm_fma(q2, p, dm_fma(q, ql, ql));
   double ph = th * q;
   double pl = dm_fma(th, q, -ph);
   double s = th + ph;

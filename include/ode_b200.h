@@ -32,6 +32,7 @@ typedef unsigned int uint32_t;
 typedef long long int64_t;
 typedef unsigned long long uint64_t;
 #else
+#include <stddef.h>
 #include <stdint.h>
 #endif
 
@@ -233,6 +234,14 @@ int ode_b200_solve_large(const ode_b200_opts* opts, int64_t n, const double* y0,
 /* The host-buffer entry points keep device memory of the calling thread's last call for reuse (the ensemble
  * arena, the large-system session); this releases it. */
 void ode_b200_trim(void);
+
+/* Page-locked, device-mapped host memory for the caller's buffers (cudaHostAlloc).  The reference has no
+ * counterpart (Julia's GC owns its arrays); a binding uses these for arrays it hands to the entry points
+ * above repeatedly: ode_b200_solve_ensemble lets the kernel write results straight into output buffers that
+ * live in such memory (no D2H phase after the integration), and copies from/to them at full PCIe rate.
+ * Buffers from any other allocator (malloc, a GC heap) work everywhere, staged through HBM. */
+void* ode_b200_host_alloc(size_t bytes);
+void ode_b200_host_free(void* p);
 
 /* Same with the reference's points = :specified contract (src/runge_kutta.jl:321-326): pts_y is
  * [n_tspan][n]; row 0 is y0, the other rows are 3rd-order Hermite values (hermite_interp!, :479-492)

@@ -122,6 +122,10 @@ def lib():
     L.ode_b200_slab_poll.argtypes = [C.c_void_p, dp]
     L.ode_b200_slab_free.argtypes = [C.c_void_p]
     L.ode_b200_slab_free.restype = None
+    L.ode_b200_host_alloc.argtypes = [C.c_size_t]
+    L.ode_b200_host_alloc.restype = C.c_void_p
+    L.ode_b200_host_free.argtypes = [C.c_void_p]
+    L.ode_b200_host_free.restype = None
     L.ode_b200_fp64_peak.argtypes = [C.c_int, C.c_int]
     L.ode_b200_fp64_peak.restype = C.c_double
     L.ode_b200_selftest_detmath.argtypes = [C.c_int, dp, dp, dp, dp, C.c_int64]

@@ -165,18 +165,37 @@ ode4s = Solver("ode4s")        # = ode4s_s with jacobian=nothing, src/ODE.jl:437
 ode4ms = Solver("ode4ms")      # Adams-Bashforth order 4, src/ODE.jl:212
 
 
+def pinned_empty(shape, dtype=np.float64):
+    """An uninitialised numpy array in page-locked, device-mapped host memory (ode_b200_host_alloc).
+    Results the library delivers into such arrays are written by the kernel as trajectories finish, so
+    there is no copy-back phase after the integration; use them for buffers that are reused across calls
+    (`solve_ensemble(..., out=...)`)."""
+    import weakref
+    dt = np.dtype(dtype)
+    n = int(np.prod(shape)) * dt.itemsize
+    L = lib()
+    p = L.ode_b200_host_alloc(n)
+    if not p:
+        raise MemoryError(L.ode_b200_last_error().decode())
+    buf = (C.c_char * max(n, 1)).from_address(p)
+    a = np.frombuffer(buf, dtype=dt, count=int(np.prod(shape))).reshape(shape)
+    weakref.finalize(buf, L.ode_b200_host_free, p)  # the array keeps `buf` alive through .base
+    return a
+
+
 def _alg_name(alg):
     return alg.name if isinstance(alg, Solver) else str(alg)
 
 
 def solve_ensemble(alg, F, y0, tspan, *, params=None, points="final", pts_cap=None, trace_traj=None,
-                   trace_cap=65536, **kw):
+                   trace_cap=65536, out=None, **kw):
     """n independent odeXX calls in one launch.
 
     y0: [n_traj, dof].  params: None (use F's bound parameters for every
     trajectory) or [n_traj, n_params].  Returns a dict with t_final, y_final,
     n_accept, n_reject, n_rhs, status (+ pts_t, pts_y, pts_n for points != "final",
-    + trace rows (t, dt, err, accepted) for trace_traj).
+    + trace rows (t, dt, err, accepted) for trace_traj).  `out`: a dict returned by an earlier call of
+    the same shape (or arrays from `pinned_empty`) whose t_final ... status arrays are filled in place.
     """
     name = _alg_name(alg)
     y0 = np.ascontiguousarray(np.asarray(y0, dtype=np.float64))
@@ -195,8 +214,17 @@ def solve_ensemble(alg, F, y0, tspan, *, params=None, points="final", pts_cap=No
     o = make_opts(name, F, ts, points=points, params_stride=stride, **kw)
     if dof != o.dof:
         raise ValueError("%r has %d components, y0 has %d" % (F, o.dof, dof))
-    out = dict(t_final=np.empty(n), y_final=np.empty((n, dof)), n_accept=np.empty(n, np.int32),
-               n_reject=np.empty(n, np.int32), n_rhs=np.empty(n, np.int32), status=np.empty(n, np.int32))
+    want = dict(t_final=((n,), np.float64), y_final=((n, dof), np.float64), n_accept=((n,), np.int32),
+                n_reject=((n,), np.int32), n_rhs=((n,), np.int32), status=((n,), np.int32))
+    given = out if out is not None else {}
+    out = {}
+    for k, (shape, dt) in want.items():
+        a = given.get(k)
+        if a is None:
+            a = np.empty(shape, dt)
+        elif a.shape != shape or a.dtype != dt or not a.flags.c_contiguous:
+            raise ValueError("out[%r] must be a C-contiguous %s array of shape %r" % (k, np.dtype(dt).name, shape))
+        out[k] = a
     io = EnsembleIO()
     io.n_traj = n
     io.y0 = _vp(y0)

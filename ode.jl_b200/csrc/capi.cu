@@ -442,6 +442,18 @@ double ode_b200_tableau(int method, int which, int i, int j) {
   return NAN;
 }
 
+void* ode_b200_host_alloc(size_t bytes) {
+  void* p = nullptr;
+  if (cudaHostAlloc(&p, bytes ? bytes : 1, cudaHostAllocPortable | cudaHostAllocMapped) != cudaSuccess) {
+    set_err(ODE_B200_E_NOMEM, "cudaHostAlloc(%zu) failed: %s", bytes, cudaGetErrorString(cudaGetLastError()));
+    return nullptr;
+  }
+  return p;
+}
+void ode_b200_host_free(void* p) {
+  if (p) cudaFreeHost(p);
+}
+
 double ode_b200_last_kernel_ms(void) {
   if (g_ev_pending) {
     float ms = 0.f;
@@ -542,11 +554,30 @@ int ode_b200_solve_ensemble(const ode_b200_opts* opts, const ode_b200_ensemble_i
   d.y0 = dy0;
   d.params = dpar;
   d.tspan = dts;
-  d.t_final = io->t_final ? g_arena.take<double>(n) : nullptr;
-  d.y_final = io->y_final ? g_arena.take<double>((size_t)n * D) : nullptr;
-  d.n_accept = io->n_accept ? g_arena.take<int>(n) : nullptr;
-  d.n_reject = io->n_reject ? g_arena.take<int>(n) : nullptr;
-  d.n_rhs = io->n_rhs ? g_arena.take<int>(n) : nullptr;
+  // Output buffers the caller keeps in pinned (page-locked, device-mapped) host memory are written by the
+  // kernel itself as each trajectory ends: the results cross PCIe while the integration is still running,
+  // instead of in a D2H phase after it.  Pageable buffers are staged in HBM and copied back as before.
+  // (`status` is always staged: the fast and literal passes talk through it.)  ODE_B200_ZEROCOPY=0 disables.
+  static const bool zc_on = [] { const char* e = getenv("ODE_B200_ZEROCOPY"); return !(e && atoi(e) == 0); }();
+  auto mapped = [&](const void* h) -> void* {
+    if (!zc_on || !h) return nullptr;
+    cudaPointerAttributes at;
+    if (cudaPointerGetAttributes(&at, h) != cudaSuccess) {
+      cudaGetLastError();
+      return nullptr;
+    }
+    return at.type == cudaMemoryTypeHost ? at.devicePointer : nullptr;
+  };
+  double* zc_t = (double*)mapped(io->t_final);
+  double* zc_y = (double*)mapped(io->y_final);
+  int* zc_na = (int*)mapped(io->n_accept);
+  int* zc_nr = (int*)mapped(io->n_reject);
+  int* zc_nf = (int*)mapped(io->n_rhs);
+  d.t_final = zc_t ? zc_t : (io->t_final ? g_arena.take<double>(n) : nullptr);
+  d.y_final = zc_y ? zc_y : (io->y_final ? g_arena.take<double>((size_t)n * D) : nullptr);
+  d.n_accept = zc_na ? zc_na : (io->n_accept ? g_arena.take<int>(n) : nullptr);
+  d.n_reject = zc_nr ? zc_nr : (io->n_reject ? g_arena.take<int>(n) : nullptr);
+  d.n_rhs = zc_nf ? zc_nf : (io->n_rhs ? g_arena.take<int>(n) : nullptr);
   d.status = g_arena.take<int>(n);  // always: the fast and literal adaptive-RK passes talk through it
   double* dinit = init_doubles ? g_arena.take<double>(init_doubles) : nullptr;
   if (pts) {
@@ -620,11 +651,11 @@ int ode_b200_solve_ensemble(const ode_b200_opts* opts, const ode_b200_ensemble_i
                          dinit ? dinit + lo * (D + 1) : nullptr, opts->params_stride == 0 ? io->params : nullptr);
     if (rc) return rc;
     if (n_chunks == 1) ODEB200_CUDA(cudaEventRecord(g_ev1, cs));
-    if (io->t_final) ODEB200_CUDA(cudaMemcpyAsync(io->t_final + lo, dc.t_final, m * 8, cudaMemcpyDeviceToHost, cs));
-    if (io->y_final) ODEB200_CUDA(cudaMemcpyAsync(io->y_final + lo * D, dc.y_final, (size_t)m * D * 8, cudaMemcpyDeviceToHost, cs));
-    if (io->n_accept) ODEB200_CUDA(cudaMemcpyAsync(io->n_accept + lo, dc.n_accept, m * 4, cudaMemcpyDeviceToHost, cs));
-    if (io->n_reject) ODEB200_CUDA(cudaMemcpyAsync(io->n_reject + lo, dc.n_reject, m * 4, cudaMemcpyDeviceToHost, cs));
-    if (io->n_rhs) ODEB200_CUDA(cudaMemcpyAsync(io->n_rhs + lo, dc.n_rhs, m * 4, cudaMemcpyDeviceToHost, cs));
+    if (io->t_final && !zc_t) ODEB200_CUDA(cudaMemcpyAsync(io->t_final + lo, dc.t_final, m * 8, cudaMemcpyDeviceToHost, cs));
+    if (io->y_final && !zc_y) ODEB200_CUDA(cudaMemcpyAsync(io->y_final + lo * D, dc.y_final, (size_t)m * D * 8, cudaMemcpyDeviceToHost, cs));
+    if (io->n_accept && !zc_na) ODEB200_CUDA(cudaMemcpyAsync(io->n_accept + lo, dc.n_accept, m * 4, cudaMemcpyDeviceToHost, cs));
+    if (io->n_reject && !zc_nr) ODEB200_CUDA(cudaMemcpyAsync(io->n_reject + lo, dc.n_reject, m * 4, cudaMemcpyDeviceToHost, cs));
+    if (io->n_rhs && !zc_nf) ODEB200_CUDA(cudaMemcpyAsync(io->n_rhs + lo, dc.n_rhs, m * 4, cudaMemcpyDeviceToHost, cs));
     if (io->status) ODEB200_CUDA(cudaMemcpyAsync(io->status + lo, dc.status, m * 4, cudaMemcpyDeviceToHost, cs));
   }
   ODEB200_CUDA(cudaEventRecord(g_arena.ev_done2, g_arena.stream2));

@@ -422,3 +422,29 @@ def test_hinit_prepass_equals_inline_hinit(method):
         for i in (0, 2999, 5999):
             o = O.solve(method, "lorenz", y0[i], ts, list(par[i]), points="final", max_steps=400)
             assert np.array_equal(big["y_final"][i], o.y[-1]) and big["n_rhs"][i] == o.n_rhs and big["status"][i] == o.status
+
+
+@pytest.mark.gpu
+def test_pinned_output_buffers_are_written_in_place():
+    """Outputs in page-locked memory (ode_b200_host_alloc) are written by the kernel itself; pageable ones are
+    staged and copied.  Same bits, and `out=` really reuses the arrays."""
+    rng = np.random.default_rng(5)
+    n = 5000
+    y0 = np.stack([rng.uniform(-10, 10, n), rng.uniform(-10, 10, n), rng.uniform(5, 35, n)], 1)
+    F = m.DeviceRHS("lorenz", *LORENZ)
+    ref = m.solve_ensemble("ode45", F, y0, [0.0, 1.0])
+    out = dict(y_final=m.pinned_empty((n, 3)), t_final=m.pinned_empty((n,)), n_accept=m.pinned_empty((n,), np.int32),
+               n_rhs=m.pinned_empty((n,), np.int32))
+    out["y_final"][:] = -1.0
+    got = m.solve_ensemble("ode45", F, y0, [0.0, 1.0], out=out)
+    assert got["y_final"] is out["y_final"] and got["n_accept"] is out["n_accept"]
+    for k in ("y_final", "t_final", "n_accept", "n_reject", "n_rhs", "status"):
+        assert np.array_equal(got[k], ref[k]), k
+    # a blow-up goes through the literal second pass, which also writes the mapped buffers
+    y0[7] = [1e200, -1e200, 1e200]
+    ref = m.solve_ensemble("ode45", F, y0, [0.0, 1.0])
+    got = m.solve_ensemble("ode45", F, y0, [0.0, 1.0], out=out)
+    for k in ("y_final", "t_final", "n_accept", "n_reject", "n_rhs", "status"):
+        assert np.array_equal(got[k], ref[k], equal_nan=True), k
+    with pytest.raises(ValueError):
+        m.solve_ensemble("ode45", F, y0, [0.0, 1.0], out=dict(y_final=np.empty((n, 2))))

@@ -306,6 +306,10 @@ double ode_b200_fp64_peak(int device, int kind);
  * GPU produces the same bits as the host build of the same header. */
 int ode_b200_selftest_detmath(int device, const double* x, const double* y, double* out_pow, double* out_log10,
                               int64_t n);
+/* Compares the shared-denominator division of the kernels (recip_prepare/div_by, csrc/common.cuh) with the
+ * compiler's IEEE a / b on about n_samples pseudo-random operand pairs (all exponent ranges, NaN, Inf, zeros,
+ * denormals, hard mantissas).  Returns the number of pairs whose bits differ (0 expected), <0 on error. */
+int64_t ode_b200_selftest_div(int device, int64_t n_samples, uint64_t seed);
 
 #endif /* !__CUDACC_RTC__ */
 

@@ -129,6 +129,8 @@ def lib():
     L.ode_b200_fp64_peak.argtypes = [C.c_int, C.c_int]
     L.ode_b200_fp64_peak.restype = C.c_double
     L.ode_b200_selftest_detmath.argtypes = [C.c_int, dp, dp, dp, dp, C.c_int64]
+    L.ode_b200_selftest_div.argtypes = [C.c_int, C.c_int64, C.c_uint64]
+    L.ode_b200_selftest_div.restype = C.c_int64
     if L.ode_b200_version() != 1:
         raise ImportError("libode_b200.so ABI version mismatch")
     _lib = L

@@ -18,6 +18,7 @@ namespace odeb200 {
 template <int D>
 struct LuReg {
   double a[D][D];
+  double rd[D];  // refined reciprocal of U[j][j] (recip_prepare), shared by 1/pivot and the back substitutions
   int piv[D];
   bool singular;
 
@@ -46,10 +47,13 @@ struct LuReg {
           a[i][c] = sw ? aj : ai;
         }
       }
+      rd[j] = 0.0;
       if (a[j][j] == 0.0) {
         singular = true;
       } else {
-        double rp = 1.0 / a[j][j];
+        Recip R = recip_prepare(a[j][j]);
+        rd[j] = R.r;
+        double rp = div_by(1.0, R);
 #pragma unroll
         for (int i = j + 1; i < D; i++) a[i][j] = a[i][j] * rp;
 #pragma unroll
@@ -78,7 +82,10 @@ struct LuReg {
     }
 #pragma unroll
     for (int j = D - 1; j >= 0; j--) {
-      b[j] = b[j] / a[j][j];
+      Recip R;
+      R.b = a[j][j];
+      R.r = rd[j];
+      b[j] = div_by<true>(b[j], R);
 #pragma unroll
       for (int i = 0; i < j; i++) b[i] = b[i] - b[j] * a[i][j];
     }
@@ -92,13 +99,14 @@ __device__ __forceinline__ void fd_jacobian(double t, const double (&x)[D], cons
   Rhs::eval(t, x, ftx, p);  // :233
 #pragma unroll
   for (int j = 0; j < D; j++) {  // :236
-    double dxj = (x[j] + ((x[j] == 0.0) ? 1.0 : 0.0)) / 100;  // :239
+    const double dxj = div_by(x[j] + ((x[j] == 0.0) ? 1.0 : 0.0), recip_prepare(100.0));  // :239
+    const Recip Rdx = recip_prepare(dxj);
     double xp[D], fp[D];
 #pragma unroll
     for (int i = 0; i < D; i++) xp[i] = x[i] + ((i == j) ? dxj : 0.0);
     Rhs::eval(t, xp, fp, p);
 #pragma unroll
-    for (int i = 0; i < D; i++) J[i][j] = (fp[i] - ftx[i]) / dxj;  // :240
+    for (int i = 0; i < D; i++) J[i][j] = div_by<true>(fp[i] - ftx[i], Rdx);  // :240
   }
 }
 
@@ -114,7 +122,7 @@ __device__ __forceinline__ int eval_jacobian(double t, const double (&x)[D], con
 }
 
 template <class Rhs, int MODE, int JAC>
-__global__ void __launch_bounds__(ENS_BLOCK) ens_ode23s_kernel(const EnsembleArgs A) {
+__global__ void __launch_bounds__(ENS_BLOCK, (Rhs::DOF <= 3) ? ODEB200_S23_MINB : 1) ens_ode23s_kernel(const EnsembleArgs A) {
   constexpr int D = Rhs::DOF, NPA = RhsNP<Rhs>::value;
   const double dd = 1.0 / (2.0 + sqrt(2.0));  // :270
   const double e32 = 6.0 + sqrt(2.0);         // :271
@@ -214,9 +222,11 @@ __global__ void __launch_bounds__(ENS_BLOCK) ens_ode23s_kernel(const EnsembleArg
         fin = ODE_B200_ST_SINGULAR;
       } else {
         double Fa[D], T[D], k1[D], k2[D], k3[D], F1[D], F2[D], ynew[D], tmp[D];
-        Rhs::eval(t + h / 100, y, Fa, p);  // :313
+        const double h100 = div_by(h, recip_prepare(100.0));
+        Rhs::eval(t + h100, y, Fa, p);  // :313
+        const Recip Rh100 = recip_prepare(h100);
 #pragma unroll
-        for (int i = 0; i < D; i++) T[i] = (hd * (Fa[i] - F0[i])) / (h / 100);
+        for (int i = 0; i < D; i++) T[i] = div_by<true>(hd * (Fa[i] - F0[i]), Rh100);
 #pragma unroll
         for (int i = 0; i < D; i++) k1[i] = F0[i] + T[i];  // :316
         W.solve(k1);
@@ -238,7 +248,7 @@ __global__ void __launch_bounds__(ENS_BLOCK) ens_ode23s_kernel(const EnsembleArg
         nrhs += 3;
 #pragma unroll
         for (int i = 0; i < D; i++) tmp[i] = (k1[i] - 2 * k2[i]) + k3[i];
-        const double err = (fabs(h) / 6) * norm2_small<D>(tmp);  // :323
+        const double err = div_by(fabs(h), recip_prepare(6.0)) * norm2_small<D>(tmp);  // :323
         const double delta = jl_max(A.reltol * jl_max(norm2_small<D>(y), norm2_small<D>(ynew)), A.abstol);  // :324
         const bool accept = err <= delta;  // :327
         if (MODE == 1 && idx == A.trace_traj) {

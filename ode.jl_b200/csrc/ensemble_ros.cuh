@@ -66,6 +66,7 @@ __global__ void __launch_bounds__(ENS_BLOCK) ens_rosenbrock_kernel(const Ensembl
         break;
       }
       double g[4][D], xn[D], f[D];
+      const Recip Rhs_ = recip_prepare(hs);  // dF/hs for three stages x D components
       constexpr double b0 = Coef::b[0];
       Rhs::eval(ts + b0 * hs, x, f, p);  // :388
 #pragma unroll
@@ -95,7 +96,7 @@ __global__ void __launch_bounds__(ENS_BLOCK) ens_rosenbrock_kernel(const Ensembl
         constexpr double bi = Coef::b[i];
         Rhs::eval(ts + bi * hs, arg, f, p);  // :398
 #pragma unroll
-        for (int d = 0; d < D; d++) g[i][d] = f[d] + dF[d] / hs;
+        for (int d = 0; d < D; d++) g[i][d] = f[d] + div_by<true>(dF[d], Rhs_);
         W.solve(g[i]);
 #pragma unroll
         for (int d = 0; d < D; d++) xn[d] = xn[d] + bi * g[i][d];  // :399

@@ -119,10 +119,11 @@ struct RhsKepler {
   __device__ __forceinline__ static void eval(double, const double (&y)[4], double (&f)[4], const double (&)[1]) {
     double r2 = y[0] * y[0] + y[1] * y[1];
     double r3 = r2 * sqrt(r2);
+    const Recip R3 = recip_prepare(r3);  // two numerators over one denominator (common.cuh)
     f[0] = y[2];
     f[1] = y[3];
-    f[2] = -y[0] / r3;
-    f[3] = -y[1] / r3;
+    f[2] = div_by(-y[0], R3);
+    f[3] = div_by(-y[1], R3);
   }
   __device__ __forceinline__ static void jac(double, const double (&y)[4], double (&J)[4][4], const double (&)[1]) {
     const double x = y[0], yy = y[1];

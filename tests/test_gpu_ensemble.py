@@ -448,3 +448,9 @@ def test_pinned_output_buffers_are_written_in_place():
         assert np.array_equal(got[k], ref[k], equal_nan=True), k
     with pytest.raises(ValueError):
         m.solve_ensemble("ode45", F, y0, [0.0, 1.0], out=dict(y_final=np.empty((n, 2))))
+
+
+@pytest.mark.gpu
+def test_shared_denominator_division_is_ieee_division():
+    """recip_prepare/div_by (csrc/common.cuh) against the compiler's a / b on 2^30 operand pairs."""
+    assert m.lib().ode_b200_selftest_div(0, 1 << 30, 20261019) == 0

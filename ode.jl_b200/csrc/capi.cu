@@ -84,6 +84,30 @@ struct Arena {
   }
 };
 thread_local Arena g_arena;
+// scratch of the device-pointer entry point (ode_b200_solve_ensemble_dev), per calling thread and device
+struct DevScratch {
+  int dev = -1;
+  unsigned long long* counter = nullptr;  // work counters of the fast and literal passes
+  int* status = nullptr;                  // when the caller passes no status buffer
+  long long status_cap = 0;
+  double* init = nullptr;                 // hinit pre-pass output
+  size_t init_cap = 0;
+  void release() {
+    if (dev >= 0) {
+      cudaSetDevice(dev);
+      if (counter) cudaFree(counter);
+      if (status) cudaFree(status);
+      if (init) cudaFree(init);
+    }
+    counter = nullptr;
+    status = nullptr;
+    init = nullptr;
+    status_cap = 0;
+    init_cap = 0;
+    dev = -1;
+  }
+};
+thread_local DevScratch g_dev_scratch;
 void arena_release() {  // ode_b200_trim
   if (g_arena.base) {
     cudaSetDevice(g_arena.dev);
@@ -92,6 +116,7 @@ void arena_release() {  // ode_b200_trim
     g_arena.cap = 0;
     g_arena.dev = -1;
   }
+  g_dev_scratch.release();
 }
 static size_t pad256(size_t b) { return (b + 255) & ~(size_t)255; }
 
@@ -490,35 +515,34 @@ int ode_b200_solve_ensemble_dev(const ode_b200_opts* opts, const ode_b200_ensemb
   rc = validate(opts, io, ends[0], ends[1]);
   if (rc) return rc;
   if (io->n_traj == 0) return 0;
-  static thread_local unsigned long long* counter = nullptr;
-  static thread_local int counter_dev = -1;
-  static thread_local int* status_scratch = nullptr;
-  static thread_local long long status_cap = 0;
-  if (counter_dev != opts->device) {
-    ODEB200_CUDA(cudaMalloc(&counter, 256));
-    counter_dev = opts->device;
-    status_scratch = nullptr;
-    status_cap = 0;
+  DevScratch& S = g_dev_scratch;
+  if (S.dev != opts->device) {
+    S.release();
+    ODEB200_CUDA(cudaSetDevice(opts->device));
+    ODEB200_CUDA(cudaMalloc(&S.counter, 256));
+    S.dev = opts->device;
   }
+  unsigned long long* counter = S.counter;
   ode_b200_ensemble_io d = *io;
   if (!d.status && is_adaptive_rk(opts->method)) {  // the fast and literal passes talk through `status`
-    if (status_cap < io->n_traj) {
-      if (status_scratch) cudaFree(status_scratch);
-      ODEB200_CUDA(cudaMalloc(&status_scratch, (size_t)io->n_traj * sizeof(int)));
-      status_cap = io->n_traj;
+    if (S.status_cap < io->n_traj) {
+      if (S.status) cudaFree(S.status);
+      S.status = nullptr;
+      S.status_cap = 0;
+      ODEB200_CUDA(cudaMalloc(&S.status, (size_t)io->n_traj * sizeof(int)));
+      S.status_cap = io->n_traj;
     }
-    d.status = status_scratch;
+    d.status = S.status;
   }
-  static thread_local double* init_scratch = nullptr;
-  static thread_local size_t init_cap = 0;
-  static thread_local int init_dev = -1;
   const size_t want = init_scratch_doubles(opts, &d);
-  if (want > 0 && (init_dev != opts->device || init_cap < want)) {
-    if (init_scratch && init_dev == opts->device) cudaFree(init_scratch);
-    ODEB200_CUDA(cudaMalloc(&init_scratch, want * sizeof(double)));
-    init_cap = want;
-    init_dev = opts->device;
+  if (want > S.init_cap) {
+    if (S.init) cudaFree(S.init);
+    S.init = nullptr;
+    S.init_cap = 0;
+    ODEB200_CUDA(cudaMalloc(&S.init, want * sizeof(double)));
+    S.init_cap = want;
   }
+  double* init_scratch = S.init;
   return launch_ensemble(opts, &d, counter, (cudaStream_t)stream, true, want > 0 ? init_scratch : nullptr,
                          fetch_upar ? upar : nullptr);
 }

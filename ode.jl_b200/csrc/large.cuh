@@ -135,7 +135,7 @@ struct LargeGeom {
 };
 
 template <class Tab, class Rhs>
-__global__ void __launch_bounds__(LARGE_THREADS) large_attempt_kernel(const LargeArgs A) {
+__global__ void __launch_bounds__(LARGE_THREADS, ODEB200_LARGE_MINB) large_attempt_kernel(const LargeArgs A) {
   using Geo = LargeGeom<Tab, Rhs>;
   constexpr int S = Geo::S, H = Geo::H, VAL = Geo::VAL, P = LARGE_P, T = LARGE_THREADS;
   constexpr bool FSAL = Geo::FSAL;

@@ -2,6 +2,8 @@
 functor given as CUDA C++ source.  Checked (a) against the built-in functor of the same expression, bit for
 bit, and (b) for a functor that is NOT built in, against the C++ oracle driven by a python callback that
 evaluates the same expression in binary64 without FMA."""
+import math
+
 import numpy as np
 import pytest
 
@@ -145,3 +147,27 @@ def test_user_stencil_large_system():
     assert np.allclose(ng(0.0, w), [nagumo(w[k - 1], w[k], w[(k + 1) % 5], 0.8, 2.0) for k in range(5)])
     with pytest.raises(m.OdeB200Error, match="NVRTC compilation"):
         m.solve_large("ode45", m.register_stencil("bad", "return undefined_thing;"), u0, [0.0, 1.0])
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("dof", [8, 16])
+def test_user_rhs_wider_state_matches_oracle(dof):
+    """A ring of `dof` cubic oscillators: the per-thread register design, the in-register LU of the Rosenbrock
+    solvers and the fixed-step kernels for a state wider than any built-in functor (register_rhs allows
+    dof <= 16).  Bit-exact against the oracle driven by the same expression in Python."""
+    D = dof
+    src = "\n".join("f[%d] = p[0]*((y[%d] - 2.0*y[%d]) + y[%d]) - p[1]*(y[%d]*y[%d])*y[%d];"
+                    % (i, (i - 1) % D, i, (i + 1) % D, i, i, i) for i in range(D))
+
+    def host(t, y, p):
+        return [p[0] * ((y[(i - 1) % D] - 2.0 * y[i]) + y[(i + 1) % D]) - p[1] * (y[i] * y[i]) * y[i] for i in range(D)]
+
+    F = m.register_rhs("ring%d" % D, D, 2, src, None, host=host, params=(1.5, 0.3))
+    y0 = [math.sin(1.0 + i) for i in range(D)]
+    methods = ("ode45", "ode78", "ode23s", "ode4", "ode4s_s", "ode4ms") if D == 8 else ("ode45", "ode23s")
+    for meth in methods:
+        ts = [0.0, 1.0, 3.0] if meth in ("ode45", "ode78", "ode23s") else list(np.linspace(0, 1, 21))
+        t, y, st = getattr(m, meth).stats(F, y0, ts)
+        o = O.solve_user(meth, host, y0, ts, [1.5, 0.3])
+        assert np.array_equal(t, o.t) and np.array_equal(y, o.y), meth
+        assert (st["n_accept"], st["n_rhs"]) == (o.n_accept, o.n_rhs), meth

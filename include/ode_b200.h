@@ -42,7 +42,10 @@ extern "C" {
 
 #define ODE_B200_ABI_VERSION 1
 /* doubles per rank in the exchange buffer of the slab sessions (see ode_b200_slab_*) */
-#define ODE_B200_XCHG_DOUBLES 96
+#define ODE_B200_XCHG_DOUBLES 264
+/* limits of a registered large-system stencil (ode_b200_register_stencil) */
+#define ODE_B200_STENCIL_MAX_RADIUS 4
+#define ODE_B200_STENCIL_MAX_NP 8
 
 /* ---- methods: one per reference tableau / driver ------------------------- */
 typedef enum {
@@ -183,11 +186,14 @@ double ode_b200_tableau(int method, int which, int i, int j);
  * Returns the rhs id (>= ODE_B200_RHS_USER_BASE) to put in opts.rhs, or a negative error code.
  * Available for the ensemble / single-system entry points (every method). */
 int ode_b200_register_rhs(const char* name, int32_t dof, int32_t n_params, const char* eval_body, const char* jac_body);
-/* Same for the large-system regime: a 3-point stencil F_i = point(u[i-1], u[i], u[i+1]; p0, p1) on a periodic
- * grid.  `point_body` is the body of   double point(double um, double u, double up, double p0, double p1)
- * (must `return` the value).  Returns an rhs id >= ODE_B200_STENCIL_USER_BASE for ode_b200_solve_large* and the
- * slab sessions. */
-int ode_b200_register_stencil(const char* name, const char* point_body);
+/* Same for the large-system regime: a stencil of radius 1..4 on a periodic 1-D grid,
+ *     F_i(t, u) = point(w, p, t, i, n),   w[k] = u[i - radius + k]  (k = 0 .. 2*radius),
+ * p the parameter vector (n_params <= 8), t the stage time, i the global grid index, n the ring length.
+ * `point_body` is the body of
+ *     double point(const double (&w)[2*radius+1], const double (&p)[8], double t, long long i, long long n)
+ * (must `return` the value; a 3-point stencil may also use the names um, u, up and p0, p1).  Returns an rhs id
+ * >= ODE_B200_STENCIL_USER_BASE for ode_b200_solve_large* and the slab sessions. */
+int ode_b200_register_stencil(const char* name, int32_t radius, int32_t n_params, const char* point_body);
 
 /* ---- ensembles of small systems (one trajectory per thread) -------------- */
 /* Replaces n_traj independent calls of oderk_adapt / oderk_fixed / ode23s.
@@ -279,6 +285,9 @@ int ode_b200_slab_set_output(ode_b200_slab* s, const double* tspan_host, int32_t
  * out_dev [cap_rows][n_local], out_times_dev [cap_rows]; ctl_out[12] of poll is the row count needed. */
 int ode_b200_slab_set_output_all(ode_b200_slab* s, const double* tspan_host, int32_t n_tspan, double* out_dev,
                                  double* out_times_dev, int64_t cap_rows);
+/* global grid index of this slab's first point (what a stencil's `i` argument counts from).  Default:
+ * contiguous slabs in rank order, the first n_global % world ranks one point longer. */
+int ode_b200_slab_set_offset(ode_b200_slab* s, int64_t first_global_index);
 /* optional attempt trace on the device: rows (t, dt, err, accepted) */
 int ode_b200_slab_set_trace(ode_b200_slab* s, double* trace_dev, int64_t trace_cap);
 int ode_b200_slab_get_state(ode_b200_slab* s, double* y_local_dev);

@@ -18,7 +18,7 @@ RHS = dict(linear=0, const=1, timelin=2, rotation=3, lorenz=4, vdp=5, robertson=
 POINTS = {"all": 0, "specified": 1, "final": 2}
 STATUS = {0: "OK", 1: "MINSTEP", 2: "MAXSTEPS", 3: "NONFINITE", 4: "SINGULAR", 5: "OVERFLOW"}
 E_ZERO_SPAN, E_INITSTEP, E_POINTS, E_NOT_ADAPTIVE, E_NO_DEVICE, E_UNSUPPORTED = -2, -3, -4, -5, -6, -8
-XCHG_DOUBLES = 96
+XCHG_DOUBLES = 264
 
 dp = C.POINTER(C.c_double)
 ip = C.POINTER(C.c_int32)
@@ -108,7 +108,7 @@ def lib():
     L.ode_b200_solve_large_all.argtypes = [C.POINTER(Opts), C.c_int64, dp, dp, dp, C.c_int32, C.c_int64, dp, dp, lp,
                                            C.POINTER(LargeStats), dp, C.c_int64, lp]
     L.ode_b200_trim.restype = None
-    L.ode_b200_register_stencil.argtypes = [C.c_char_p, C.c_char_p]
+    L.ode_b200_register_stencil.argtypes = [C.c_char_p, C.c_int32, C.c_int32, C.c_char_p]
     L.ode_b200_register_rhs.argtypes = [C.c_char_p, C.c_int32, C.c_int32, C.c_char_p, C.c_char_p]
     L.ode_b200_slab_create.argtypes = [C.POINTER(Opts), C.c_int64, C.c_int64, C.c_int32, C.c_int32, dp, C.c_double,
                                        C.c_double, C.c_void_p, C.POINTER(C.c_void_p)]
@@ -116,6 +116,7 @@ def lib():
     L.ode_b200_slab_get_state.argtypes = [C.c_void_p, C.c_void_p]
     L.ode_b200_slab_reset.argtypes = [C.c_void_p, C.c_double, C.c_double]
     L.ode_b200_slab_set_trace.argtypes = [C.c_void_p, C.c_void_p, C.c_int64]
+    L.ode_b200_slab_set_offset.argtypes = [C.c_void_p, C.c_int64]
     L.ode_b200_slab_init_phase.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]
     L.ode_b200_slab_attempt.argtypes = [C.c_void_p, C.c_void_p]
     L.ode_b200_slab_control.argtypes = [C.c_void_p, C.c_void_p]

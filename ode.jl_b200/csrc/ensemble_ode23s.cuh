@@ -122,7 +122,7 @@ __device__ __forceinline__ int eval_jacobian(double t, const double (&x)[D], con
 }
 
 template <class Rhs, int MODE, int JAC>
-__global__ void __launch_bounds__(ENS_BLOCK, (Rhs::DOF <= 3) ? ODEB200_S23_MINB : 1) ens_ode23s_kernel(const EnsembleArgs A) {
+__global__ void __launch_bounds__(ENS_BLOCK, (Rhs::DOF <= 3) ? ODEB200_S23_MINB : 0) ens_ode23s_kernel(const EnsembleArgs A) {
   constexpr int D = Rhs::DOF, NPA = RhsNP<Rhs>::value;
   const double dd = 1.0 / (2.0 + sqrt(2.0));  // :270
   const double e32 = 6.0 + sqrt(2.0);         // :271

@@ -281,31 +281,35 @@ static int persistent_grid(const void* k, int device, long long tiles) {
   if (g > tiles) g = tiles;
   return (int)(g < 1 ? 1 : g);
 }
+// Tile geometry of (tableau, stencil radius): the same arithmetic as LargeGeom, for radii known only at run
+// time (registered stencils).
 template <class Tab>
-static void geometry(MethodInfo* m) {
-  using Geo = LargeGeom<Tab, RhsReactionDiffusion>;  // geometry depends on the tableau only
-  m->H = Geo::H;
-  m->VAL = Geo::VAL;
+static void geometry(MethodInfo* m, int radius) {
+  constexpr bool fsal = Tab::fsal();
+  const int g = radius * (Tab::S - 1 + (fsal ? 0 : 1));
+  m->H = (g + 3) / 4 * 4;
+  m->VAL = LARGE_THREADS * LARGE_P - 2 * m->H;
   m->order = Tab::ORDER;
   m->S = Tab::S;
-  m->fsal = Geo::FSAL ? 1 : 0;
+  m->fsal = fsal ? 1 : 0;
 }
 template <class Tab>
-static MethodInfo method_info() {
+static MethodInfo method_info(int radius) {
   MethodInfo m;
-  geometry<Tab>(&m);
+  geometry<Tab>(&m, radius);
+  static_assert(LargeGeom<Tab, RhsReactionDiffusion>::H == (Tab::S - 1 + (Tab::fsal() ? 0 : 1) + 3) / 4 * 4, "geometry");
   m.attempt = (const void*)large_attempt_kernel<Tab, RhsReactionDiffusion>;
   m.hinit_f0 = (const void*)hinit_f0_kernel<RhsReactionDiffusion>;
   m.hinit_f1 = (const void*)hinit_f1_kernel<RhsReactionDiffusion>;
   return m;
 }
-static bool pick_method(int method, MethodInfo* out) {
+static bool pick_method(int method, int radius, MethodInfo* out) {
   switch (method) {
-    case ODE_B200_M_RK21: *out = method_info<TabRK21>(); return true;
-    case ODE_B200_M_RK23: *out = method_info<TabRK23>(); return true;
-    case ODE_B200_M_RK45_FE: *out = method_info<TabRK45>(); return true;
-    case ODE_B200_M_DOPRI5: *out = method_info<TabDopri5>(); return true;
-    case ODE_B200_M_FEH78: *out = method_info<TabFeh78>(); return true;
+    case ODE_B200_M_RK21: *out = method_info<TabRK21>(radius); return true;
+    case ODE_B200_M_RK23: *out = method_info<TabRK23>(radius); return true;
+    case ODE_B200_M_RK45_FE: *out = method_info<TabRK45>(radius); return true;
+    case ODE_B200_M_DOPRI5: *out = method_info<TabDopri5>(radius); return true;
+    case ODE_B200_M_FEH78: *out = method_info<TabFeh78>(radius); return true;
     default: return false;
   }
 }
@@ -330,7 +334,8 @@ struct ode_b200_slab {
   double* out = nullptr;  // [n_tq][n] (:specified) or [out_cap][n] (:all) device, caller owned
   double* out_times = nullptr;  // [out_cap] device (:all only)
   long long out_cap = 0;
-  double p0 = 0, p1 = 0;
+  StencilCtx sc;  // parameters, global index of the first interior point, ring length
+  int np = 2;     // parameters the stencil takes
   int init_blocks = 0;
   LargeCtl host_ctl;
 };
@@ -369,17 +374,23 @@ int ode_b200_slab_create(const ode_b200_opts* o, int64_t n_local, int64_t n_glob
   const bool user_stencil = o->rhs >= ODE_B200_STENCIL_USER_BASE;
   if (o->rhs != ODE_B200_RHS_REACTION_DIFFUSION && !user_stencil)
     return set_err(ODE_B200_E_UNSUPPORTED, "the large-system path takes a stencil RHS (reaction_diffusion or a registered stencil)");
+  int radius = 1, np = 2;  // reaction_diffusion
+  if (user_stencil && !user_stencil_info(o->rhs, &radius, &np)) return set_err(ODE_B200_E_INVALID, "unknown stencil %d", o->rhs);
   MethodInfo mi;
-  if (!pick_method(o->method, &mi)) {
+  if (!pick_method(o->method, radius, &mi)) {
     if (o->method >= 0 && o->method <= ODE_B200_M_RK4)
       return set_err(ODE_B200_E_NOT_ADAPTIVE, "Can only use this solver with an adaptive RK Butcher table");
     return set_err(ODE_B200_E_UNSUPPORTED, "method %d has no large-system kernel", o->method);
   }
+  if (XS_EDGE + 4 * mi.H > XCHG || mi.VAL < LARGE_THREADS * LARGE_P / 2)
+    return set_err(ODE_B200_E_UNSUPPORTED, "stencil radius %d with method %d needs %d ghost points per side: too wide for the tile",
+                   radius, o->method, mi.H);
   if (user_stencil) {  // same geometry, kernels compiled at run time for the registered point functor
     ODEB200_CUDA(cudaSetDevice(o->device));
     if (!user_stencil_kernels(o->rhs, o->method, &mi.attempt, &mi.hinit_f0, &mi.hinit_f1)) return ODE_B200_E_INVALID;
   }
-  if (!params || o->n_params < 2) return set_err(ODE_B200_E_INVALID, "the stencil RHS needs two params (reaction_diffusion: {kappa, r})");
+  if (np > 0 && (!params || o->n_params < np))
+    return set_err(ODE_B200_E_INVALID, "the stencil RHS needs %d params (reaction_diffusion: {kappa, r})", np);
   if (world < 1 || rank < 0 || rank >= world) return set_err(ODE_B200_E_INVALID, "bad rank/world");
   if (n_local < 2 * mi.H || n_global < 32 || n_local > n_global)
     return set_err(ODE_B200_E_INVALID, "slab too small: n_local %lld (needs >= %d), n_global %lld (needs >= 32)",
@@ -403,8 +414,15 @@ int ode_b200_slab_create(const ode_b200_opts* o, int64_t n_local, int64_t n_glob
   s->stream = (cudaStream_t)stream;
   s->tiles = (n_local + mi.VAL - 1) / mi.VAL;
   s->grid = persistent_grid(mi.attempt, o->device, s->tiles);
-  s->p0 = params[0];
-  s->p1 = params[1];
+  memset(&s->sc, 0, sizeof(s->sc));
+  s->np = np;
+  for (int q = 0; q < np; q++) s->sc.p[q] = params[q];
+  s->sc.n_global = n_global;
+  {  // contiguous slabs in rank order, the first n_global % world ranks one point longer (what shard_bounds of
+     // the host mirror does); ode_b200_slab_set_offset overrides
+    const long long base = n_global / world, rem = n_global % world;
+    s->sc.i0 = rank * base + (rank < rem ? rank : rem);
+  }
   const size_t padded = (size_t)(n_local + 2 * mi.H + 8) * sizeof(double);
   int sms = 0;
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, o->device);
@@ -457,8 +475,8 @@ static int slab_configure(ode_b200_slab* s, const ode_b200_opts* o, const double
   if (!(o->reltol == o->reltol) || !(o->abstol == o->abstol) || !(o->minstep == o->minstep) ||
       !(o->maxstep == o->maxstep) || !(o->initstep == o->initstep))
     return set_err(ODE_B200_E_INVALID, "NaN in reltol/abstol/minstep/maxstep/initstep");
-  s->p0 = params[0];
-  s->p1 = params[1];
+  if (s->np > 0 && (!params || o->n_params < s->np)) return set_err(ODE_B200_E_INVALID, "the stencil RHS needs %d params", s->np);
+  for (int q = 0; q < s->np; q++) s->sc.p[q] = params[q];
   LargeCtl c;
   memset(&c, 0, sizeof(c));
   c.tdir = tdir;
@@ -507,6 +525,14 @@ int ode_b200_slab_reset(ode_b200_slab* s, double t0, double tend) {
   s->host_ctl = z;
   ODEB200_CUDA(cudaMemcpyAsync(s->ctl, &s->host_ctl, sizeof(LargeCtl), cudaMemcpyHostToDevice, s->stream));
   ODEB200_CUDA(cudaStreamSynchronize(s->stream));  // host_ctl is reused by poll
+  return 0;
+}
+
+int ode_b200_slab_set_offset(ode_b200_slab* s, int64_t first_global_index) {
+  int rc = slab_check(s);
+  if (rc) return rc;
+  if (first_global_index < 0 || first_global_index >= s->n_global) return set_err(ODE_B200_E_INVALID, "offset outside the ring");
+  s->sc.i0 = first_global_index;
   return 0;
 }
 
@@ -591,7 +617,8 @@ int ode_b200_slab_init_phase(ode_b200_slab* s, int phase, double* xsend, const d
         const double* y = s->Y[0];
         double* f0 = s->K[0];
         int Hh = H;
-        void* a[] = {(void*)&y, (void*)&f0, (void*)&s->ipart, (void*)&s->n, (void*)&Hh, (void*)&s->p0, (void*)&s->p1};
+        const LargeCtl* c = s->ctl;
+        void* a[] = {(void*)&y, (void*)&f0, (void*)&c, (void*)&s->ipart, (void*)&s->n, (void*)&Hh, (void*)&s->sc};
         ODEB200_CUDA(cudaLaunchKernel(s->mi.hinit_f0, dim3(s->init_blocks), dim3(256), a, 0, st));
       }
       reduce_max_kernel<<<1, 32, 0, st>>>(s->ipart, s->init_blocks, 2, xsend);
@@ -606,7 +633,7 @@ int ode_b200_slab_init_phase(ode_b200_slab* s, int phase, double* xsend, const d
         const double* f0 = s->K[0];
         const LargeCtl* c = s->ctl;
         int Hh = H;
-        void* a[] = {(void*)&y, (void*)&f0, (void*)&c, (void*)&s->ipart, (void*)&s->n, (void*)&Hh, (void*)&s->p0, (void*)&s->p1};
+        void* a[] = {(void*)&y, (void*)&f0, (void*)&c, (void*)&s->ipart, (void*)&s->n, (void*)&Hh, (void*)&s->sc};
         ODEB200_CUDA(cudaLaunchKernel(s->mi.hinit_f1, dim3(s->init_blocks), dim3(256), a, 0, st));
       }
       reduce_max_kernel<<<1, 32, 0, st>>>(s->ipart, s->init_blocks, 1, xsend);
@@ -636,8 +663,7 @@ int ode_b200_slab_attempt(ode_b200_slab* s, double* xsend) {
   A.xsend = xsend;
   A.n = s->n;
   A.tiles = s->tiles;
-  A.p0 = s->p0;
-  A.p1 = s->p1;
+  A.sc = s->sc;
   void* kargs[] = {(void*)&A};
   ODEB200_CUDA(cudaLaunchKernel(s->mi.attempt, dim3((unsigned)s->grid), dim3(LARGE_THREADS), kargs, 0, s->stream));
   note_launch();

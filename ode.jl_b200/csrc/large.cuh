@@ -2,7 +2,7 @@
 // in one fused kernel.
 //
 // Replaces oderk_adapt (/root/reference src/runge_kutta.jl:232-369) on a
-// dof = N state with a registered 3-point stencil right-hand side, with the
+// dof = N state with a registered periodic stencil right-hand side (radius 1..4), with the
 // reference's arithmetic per grid point (rk_embedded_step! :371-399,
 // calc_next_k! :444-458, the scaling of stepsize_hw92! :430-434).
 //
@@ -16,11 +16,12 @@
 //     CTAs are persistent (grid = SMs x resident CTAs) and request the next
 //     tile's y, k1 before computing the current one, so the tile load latency
 //     hides behind a whole attempt of FP64 work;
-//   * a stage needs ytmp at i-1, i, i+1: inside a thread these are registers, the
-//     two chunk-edge values cross threads through a double-buffered shared-memory
-//     line (one __syncthreads per stage); the tile edge loses one point of
-//     validity per stage, which is what the H >= S-1 ghost points pay for
-//     (redundant work 2H/W ~ 1.6 %);
+//   * a stage needs ytmp at i-R .. i+R (R = stencil radius): inside a thread these
+//     are registers, the R chunk-edge values per side cross threads through a
+//     double-buffered shared-memory line (one __syncthreads per stage); the tile
+//     edge loses R points of validity per stage, which is what the
+//     H >= R*(S-1) ghost points pay for (redundant work 2H/W = 3.1 % for
+//     dopri5 with a 3-point stencil);
 //   * HBM traffic per attempt drops to: read y, k1; write ytrial, k_next
 //     = 4 passes = 32 B per point (8.25x less than stage-per-kernel), with
 //     256-bit aligned vector loads/stores; the kernel becomes FP64-issue bound.
@@ -77,6 +78,18 @@ struct LargeCtl {
   int out_end;
 };
 
+// What a stencil functor sees besides its window of 2R+1 values:
+//   point(w, p, t, i, n):  w[k] = u at grid index i-R+k (periodic), p = parameters, t = stage time,
+//                          i = global grid index, n = global ring length
+constexpr int STENCIL_MAX_NP = ODE_B200_STENCIL_MAX_NP;
+constexpr int STENCIL_MAX_RADIUS = ODE_B200_STENCIL_MAX_RADIUS;
+static_assert(STENCIL_MAX_RADIUS <= ODEB200_LARGE_P, "the edge exchange hands over at most one thread's chunk");
+struct StencilCtx {
+  double p[STENCIL_MAX_NP];
+  long long i0;        // global index of this slab's first interior point
+  long long n_global;  // length of the periodic ring
+};
+
 struct LargeArgs {
   double* Y[2];  // padded [n + 2H]
   double* K[2];
@@ -85,7 +98,7 @@ struct LargeArgs {
   double* xsend;  // [XCHG]
   long long n;    // interior points of this slab
   long long tiles;
-  double p0, p1;  // stencil parameters
+  StencilCtx sc;  // stencil parameters and index base
 };
 
 __device__ __forceinline__ dm_dd dd_add(dm_dd a, dm_dd b) {
@@ -123,26 +136,69 @@ __device__ __forceinline__ void load_chunk(const double* a, long long q, long lo
   }
 }
 
+// One RHS sweep over a thread's P consecutive points: the R edge values per side cross threads through one
+// shared-memory line (written here, read after the barrier); the first / last thread of the tile repeats its
+// own edge value (those points are inside the ghost zone and already invalid).  g0 = global grid index of v[0].
+template <class Rhs, int P, int T>
+__device__ __forceinline__ void stencil_sweep(const double (&v)[P], double (&out)[P], double* sL, double* sR, int tid,
+                                              const StencilCtx& sc, double tt, long long g0) {
+  constexpr int R = Rhs::RADIUS;
+  static_assert(R >= 1 && R <= P && R <= STENCIL_MAX_RADIUS, "stencil radius must fit one thread's chunk");
+#pragma unroll
+  for (int r = 0; r < R; r++) {
+    sL[tid * R + r] = v[r];
+    sR[tid * R + r] = v[P - R + r];
+  }
+  __syncthreads();
+  double left[R], right[R];
+  const int tl = (tid > 0) ? tid - 1 : 0, tr = (tid < T - 1) ? tid + 1 : T - 1;  // clamped: loads stay unconditional
+#pragma unroll
+  for (int r = 0; r < R; r++) {
+    const double l = sR[tl * R + r], q = sL[tr * R + r];
+    left[r] = (tid > 0) ? l : v[0];
+    right[r] = (tid < T - 1) ? q : v[P - 1];
+  }
+#pragma unroll
+  for (int p = 0; p < P; p++) {
+    double w[2 * R + 1];
+#pragma unroll
+    for (int k = 0; k < 2 * R + 1; k++) {
+      const int idx = p + k - R;  // compile-time after unrolling
+      w[k] = (idx < 0) ? left[(idx < 0) ? R + idx : 0] : ((idx >= P) ? right[(idx >= P) ? idx - P : 0] : v[(idx >= 0 && idx < P) ? idx : 0]);
+    }
+    long long gi = g0 + p;
+    if (gi >= sc.n_global) gi -= sc.n_global;
+    out[p] = Rhs::point(w, sc.p, tt, gi, sc.n_global);
+  }
+}
+
 // ---- the fused attempt ---------------------------------------------------------
 template <class Tab, class Rhs>
 struct LargeGeom {
   static constexpr int S = Tab::S;
   static constexpr bool FSAL = Tab::fsal();
-  static constexpr int G = S - 1 + (FSAL ? 0 : 1);  // stencil radius 1 per RHS evaluation
-  static constexpr int H = (G + 3) / 4 * 4;         // ghost width, multiple of 4 for 32-byte alignment
+  static constexpr int R = Rhs::RADIUS;
+  static constexpr int G = R * (S - 1 + (FSAL ? 0 : 1));  // R points of validity lost per RHS evaluation
+  static constexpr int H = (G + 3) / 4 * 4;               // ghost width, multiple of 4 for 32-byte alignment
   static constexpr int W = LARGE_THREADS * LARGE_P;
   static constexpr int VAL = W - 2 * H;
 };
 
 template <class Tab, class Rhs>
-__global__ void __launch_bounds__(LARGE_THREADS, ODEB200_LARGE_MINB) large_attempt_kernel(const LargeArgs A) {
+#ifdef ODEB200_LARGE_MINB
+__global__ void __launch_bounds__(LARGE_THREADS, ODEB200_LARGE_MINB) large_attempt_kernel(
+#else
+__global__ void __launch_bounds__(LARGE_THREADS) large_attempt_kernel(
+#endif
+    const LargeArgs A) {
   using Geo = LargeGeom<Tab, Rhs>;
   constexpr int S = Geo::S, H = Geo::H, VAL = Geo::VAL, P = LARGE_P, T = LARGE_THREADS;
   constexpr bool FSAL = Geo::FSAL;
   constexpr int NK = S > 1 ? S - 1 : 1;
   static_assert(P % 4 == 0, "256-bit vector accesses");
 
-  __shared__ double eL[2][T], eR[2][T];
+  constexpr int R = Geo::R;
+  __shared__ double eL[2][T * R], eR[2][T * R];
   __shared__ double red[T / 32][4];
   __shared__ bool is_last;
 
@@ -150,8 +206,9 @@ __global__ void __launch_bounds__(LARGE_THREADS, ODEB200_LARGE_MINB) large_attem
   if (ctl->done) return;
   const int tid = threadIdx.x;
   const int par = ctl->par;
-  const double dt = ctl->dt;
+  const double dt = ctl->dt, t = ctl->t;
   const double reltol = ctl->reltol, abstol = ctl->abstol;
+  const StencilCtx& sc = A.sc;
   // (ternaries, not A.Y[par]: a dynamically indexed kernel-parameter array is copied to local memory)
   const double* __restrict__ yA = par ? A.Y[1] : A.Y[0];
   const double* __restrict__ kA = par ? A.K[1] : A.K[0];
@@ -177,6 +234,9 @@ __global__ void __launch_bounds__(LARGE_THREADS, ODEB200_LARGE_MINB) large_attem
   }
   for (; tile < A.tiles; tile += gridDim.x) {
     const long long q0 = tile * VAL + off0;  // padded index of my first point
+    long long g0 = sc.i0 + (q0 - H);         // its global grid index on the periodic ring (H < n_global)
+    if (g0 < 0) g0 += sc.n_global;
+    else if (g0 >= sc.n_global) g0 -= sc.n_global;
     double y[P], k1[P];
 #pragma unroll
     for (int p = 0; p < P; p++) {
@@ -198,7 +258,6 @@ __global__ void __launch_bounds__(LARGE_THREADS, ODEB200_LARGE_MINB) large_attem
       dtk[0][p] = dt * k1[p];
       klast[p] = k1[p];
     }
-    // (the registered stencil RHS is autonomous; t + c*dt is not needed)
     static_for<S - 1>([&](auto I) {
       constexpr int s = decltype(I)::value + 1;
       double ytmp[P], ks[P];
@@ -214,17 +273,8 @@ __global__ void __launch_bounds__(LARGE_THREADS, ODEB200_LARGE_MINB) large_attem
       });
       const int buf = xc & 1;
       xc++;
-      eL[buf][tid] = ytmp[0];
-      eR[buf][tid] = ytmp[P - 1];
-      __syncthreads();
-      const double left = (tid > 0) ? eR[buf][tid - 1] : ytmp[0];
-      const double right = (tid < T - 1) ? eL[buf][tid + 1] : ytmp[P - 1];
-#pragma unroll
-      for (int p = 0; p < P; p++) {
-        const double um = (p == 0) ? left : ytmp[p - 1];
-        const double up = (p == P - 1) ? right : ytmp[p + 1];
-        ks[p] = Rhs::point(um, ytmp[p], up, A.p0, A.p1);
-      }
+      constexpr double c = Tab::c(s);
+      stencil_sweep<Rhs, P, T>(ytmp, ks, eL[buf], eR[buf], tid, sc, t + c * dt, g0);  // :456
       constexpr double b1 = Tab::b(0, s), b2 = Tab::b(1, s);
 #pragma unroll
       for (int p = 0; p < P; p++) {
@@ -246,17 +296,7 @@ __global__ void __launch_bounds__(LARGE_THREADS, ODEB200_LARGE_MINB) large_attem
     } else {  // f1 = F(t+dt, ytrial) :320, fused as one more stencil sweep
       const int buf = xc & 1;
       xc++;
-      eL[buf][tid] = ytrial[0];
-      eR[buf][tid] = ytrial[P - 1];
-      __syncthreads();
-      const double left = (tid > 0) ? eR[buf][tid - 1] : ytrial[0];
-      const double right = (tid < T - 1) ? eL[buf][tid + 1] : ytrial[P - 1];
-#pragma unroll
-      for (int p = 0; p < P; p++) {
-        const double um = (p == 0) ? left : ytrial[p - 1];
-        const double up = (p == P - 1) ? right : ytrial[p + 1];
-        knext[p] = Rhs::point(um, ytrial[p], up, A.p0, A.p1);
-      }
+      stencil_sweep<Rhs, P, T>(ytrial, knext, eL[buf], eR[buf], tid, sc, t + dt, g0);
     }
 
     // ---- scaled error (stepsize_hw92! :430-435), valid points only -------------
@@ -428,17 +468,26 @@ __device__ __forceinline__ double block_max_nanprop(double v, double* sh) {
   return r;
 }
 
+// global grid index of local interior point i (periodic ring; i0 + n <= n_global or a single slab)
+__device__ __forceinline__ long long ring_index(const StencilCtx& sc, long long i) {
+  long long g = sc.i0 + i;
+  return g >= sc.n_global ? g - sc.n_global : g;
+}
 // phase 1: f0 = F(t0, y) on the interior -> K[par]; partial max|y|, max|f0|
 template <class Rhs>
-__global__ void __launch_bounds__(256) hinit_f0_kernel(const double* y, double* f0, double* part, long long n, int H,
-                                                       double p0, double p1) {
+__global__ void __launch_bounds__(256) hinit_f0_kernel(const double* y, double* f0, const LargeCtl* ctl, double* part,
+                                                       long long n, int H, const __grid_constant__ StencilCtx sc) {
+  constexpr int R = Rhs::RADIUS;
   __shared__ double sh[8];
+  const double t0 = ctl->tstart;
   double my = 0.0, mf = 0.0;
   for (long long i = blockIdx.x * 256LL + threadIdx.x; i < n; i += (long long)gridDim.x * 256) {
-    const double um = y[H + i - 1], u = y[H + i], up = y[H + i + 1];
-    const double f = Rhs::point(um, u, up, p0, p1);
+    double w[2 * R + 1];
+#pragma unroll
+    for (int k = 0; k < 2 * R + 1; k++) w[k] = y[H + i + (k - R)];
+    const double f = Rhs::point(w, sc.p, t0, ring_index(sc, i), sc.n_global);
     f0[H + i] = f;
-    my = normInf_step(my, fabs(u));
+    my = normInf_step(my, fabs(w[R]));
     mf = normInf_step(mf, fabs(f));
   }
   double a = block_max_nanprop<256>(my, sh);
@@ -451,15 +500,17 @@ __global__ void __launch_bounds__(256) hinit_f0_kernel(const double* y, double* 
 // phase 2: x1 = y + (tdir*h0)*f0, f1 = F(t0 + tdir*h0, x1); partial max|f1 - f0|
 template <class Rhs>
 __global__ void __launch_bounds__(256) hinit_f1_kernel(const double* y, const double* f0, const LargeCtl* ctl,
-                                                       double* part, long long n, int H, double p0, double p1) {
+                                                       double* part, long long n, int H, const __grid_constant__ StencilCtx sc) {
+  constexpr int R = Rhs::RADIUS;
   __shared__ double sh[8];
   const double th = ctl->tdir * ctl->h0;
+  const double t1 = ctl->tstart + ctl->tdir * ctl->h0;  // src/ODE.jl:101
   double md = 0.0;
   for (long long i = blockIdx.x * 256LL + threadIdx.x; i < n; i += (long long)gridDim.x * 256) {
-    const double xm = y[H + i - 1] + th * f0[H + i - 1];
-    const double x = y[H + i] + th * f0[H + i];
-    const double xp = y[H + i + 1] + th * f0[H + i + 1];
-    const double f1 = Rhs::point(xm, x, xp, p0, p1);
+    double w[2 * R + 1];
+#pragma unroll
+    for (int k = 0; k < 2 * R + 1; k++) w[k] = y[H + i + (k - R)] + th * f0[H + i + (k - R)];  // :100
+    const double f1 = Rhs::point(w, sc.p, t1, ring_index(sc, i), sc.n_global);
     md = normInf_step(md, fabs(f1 - f0[H + i]));
   }
   double a = block_max_nanprop<256>(md, sh);

@@ -143,12 +143,13 @@ struct RhsKepler {
   }
 };
 
-// 1-D reaction-diffusion stencil (large-system regime): point value from the
-// three neighbours, kappa*((um - 2*u) + up) + (r*u)*(1 - u).
+// 1-D reaction-diffusion stencil (large-system regime): point value from the three neighbours,
+// kappa*((um - 2*u) + up) + (r*u)*(1 - u).  Stencil functors see a window w[k] = u(i-R+k), the parameter
+// vector, the stage time and the global grid index (csrc/large.cuh).
 struct RhsReactionDiffusion {
   static constexpr int NP = 2, RADIUS = 1, ID = ODE_B200_RHS_REACTION_DIFFUSION;
-  __device__ __forceinline__ static double point(double um, double u, double up, double kappa, double r) {
-    return kappa * ((um - 2.0 * u) + up) + (r * u) * (1.0 - u);
+  __device__ __forceinline__ static double point(const double (&w)[3], const double (&p)[8], double, long long, long long) {
+    return p[0] * ((w[0] - 2.0 * w[1]) + w[2]) + (p[1] * w[1]) * (1.0 - w[1]);
   }
 };
 

@@ -92,6 +92,15 @@ bool user_rhs_info(int rhs, int* dof, int* np, bool* has_jac) {
   return true;
 }
 
+bool user_stencil_info(int rhs, int* radius, int* np) {
+  std::lock_guard<std::mutex> lk(g_mu);
+  int i = rhs - ODE_B200_STENCIL_USER_BASE;
+  if (i < 0 || i >= (int)g_stencils.size()) return false;
+  if (radius) *radius = g_stencils[i].dof;  // (the dof slot of a stencil entry holds its radius)
+  if (np) *np = g_stencils[i].np;
+  return true;
+}
+
 static const char* tab_name(int method) {
   switch (method) {
     case ODE_B200_M_FEULER: return "odeb200::TabFEuler";
@@ -273,11 +282,18 @@ bool user_stencil_kernels(int rhs, int method, const void** attempt, const void*
       return true;
     }
   }
-  std::string src =
-      "#include \"large.cuh\"\nnamespace odeb200 {\nstruct StencilUser {\n"
-      "  static constexpr int NP = 2, RADIUS = 1, ID = 0;\n"
-      "  __device__ __forceinline__ static double point(double um, double u, double up, double p0, double p1) {\n" +
-      u.eval_body + "\n  }\n};\n}  // namespace odeb200\n";
+  // point(w, p, t, i, n): w[k] = u at grid index i-R+k.  For a 3-point stencil the body may also use the
+  // names um, u, up, and p0, p1 for the first two parameters.
+  char decl[512];
+  snprintf(decl, sizeof(decl),
+           "  static constexpr int NP = %d, RADIUS = %d, ID = 0;\n"
+           "  __device__ __forceinline__ static double point(const double (&w)[%d], const double (&p)[8], double t, "
+           "long long i, long long n) {\n",
+           u.np, u.dof, 2 * u.dof + 1);
+  std::string src = "#include \"large.cuh\"\nnamespace odeb200 {\nstruct StencilUser {\n" + std::string(decl);
+  if (u.dof == 1) src += "    const double um = w[0], u = w[1], up = w[2]; (void)um; (void)u; (void)up;\n";
+  src += "    const double p0 = p[0], p1 = p[1]; (void)p0; (void)p1; (void)t; (void)i; (void)n;\n";
+  src += u.eval_body + "\n  }\n};\n}  // namespace odeb200\n";
   const char* exprs[3] = {e0, e1, e2};
   const void* out[3] = {nullptr, nullptr, nullptr};
   if (!compile_and_load(u.name, src, exprs, 3, out)) return false;
@@ -310,14 +326,17 @@ extern "C" int ode_b200_register_rhs(const char* name, int32_t dof, int32_t n_pa
   return ODE_B200_RHS_USER_BASE + (int)g_user.size() - 1;
 }
 
-extern "C" int ode_b200_register_stencil(const char* name, const char* point_body) {
-  if (!name || !point_body) return set_err(ODE_B200_E_INVALID, "register_stencil: need a name and the body of point()");
+extern "C" int ode_b200_register_stencil(const char* name, int32_t radius, int32_t n_params, const char* point_body) {
+  if (!name || !point_body || radius < 1 || radius > ODE_B200_STENCIL_MAX_RADIUS || n_params < 0 ||
+      n_params > ODE_B200_STENCIL_MAX_NP)
+    return set_err(ODE_B200_E_INVALID, "register_stencil: need a name, the body of point(), 1 <= radius <= %d, 0 <= n_params <= %d",
+                   ODE_B200_STENCIL_MAX_RADIUS, ODE_B200_STENCIL_MAX_NP);
   std::lock_guard<std::mutex> lk(g_mu);
   UserRhs u;
   u.name = name;
   u.eval_body = point_body;
-  u.dof = 0;
-  u.np = 2;
+  u.dof = radius;  // a stencil entry keeps its radius here
+  u.np = n_params;
   g_stencils.push_back(u);
   return ODE_B200_STENCIL_USER_BASE + (int)g_stencils.size() - 1;
 }

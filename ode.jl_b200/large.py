@@ -42,6 +42,8 @@ def solve_large(alg, F, y0, tspan, *, trace=False, trace_cap=65536, out=None, **
     kw.setdefault("points", "final")
     o = make_opts(_alg_name(alg), F, ts, dof=min(y0.size, 2 ** 31 - 1), **kw)
     p = F.param_array()
+    if p is None:
+        p = np.zeros(1)  # a stencil without parameters
     if out is None:
         out = np.empty_like(y0)
     elif out.dtype != np.float64 or out.size != y0.size or not out.flags.c_contiguous:
@@ -101,6 +103,8 @@ class CudaSlabEngine:
         kw.setdefault("points", "final")
         self.opts = make_opts(_alg_name(alg), F, ts, dof=min(int(n_global), 2 ** 31 - 1), device=device, **kw)
         p = F.param_array()
+        if p is None:
+            p = np.zeros(1)
         self.h = C.c_void_p()
         self.L = lib()
         try:

@@ -35,19 +35,23 @@ def register_rhs(name, dof, n_params, eval_body, jac_body=None, host=None, param
     return tok
 
 
-def register_stencil(name, point_body, host=None, params=(0.0, 0.0)):
-    """Register a 3-point periodic stencil for the large-system regime from CUDA C++ source.
+def register_stencil(name, point_body, host=None, params=(0.0, 0.0), radius=1):
+    """Register a periodic 1-D stencil of radius 1..4 for the large-system regime from CUDA C++ source.
 
-    point_body : body of  double point(double um, double u, double up, double p0, double p1)  (must `return`)
-    host       : optional python callable host(um, u, up, p0, p1) for DeviceRHS.__call__ on whole arrays"""
+    point_body : body of  double point(const double (&w)[2*radius+1], const double (&p)[8], double t,
+                 long long i, long long n)  -- w[k] = u[i-radius+k], t the stage time, i the global grid index,
+                 n the ring length; must `return`.  A 3-point stencil may also use um, u, up and p0, p1.
+    host       : optional python callable host(w, p, t, i, n) for DeviceRHS.__call__ on whole arrays
+    params     : default parameter values (at most 8); their count is the stencil's n_params"""
     from ._lib import lib, check
-    rid = lib().ode_b200_register_stencil(name.encode(), point_body.encode())
+    rid = lib().ode_b200_register_stencil(name.encode(), int(radius), len(params), point_body.encode())
     if rid < 0:
         check(rid)
     tok = DeviceRHS.__new__(DeviceRHS)
-    tok.name, tok.id, tok.dof, tok.n_params, tok.params = name, rid, 0, 2, tuple(params)
+    tok.name, tok.id, tok.dof, tok.n_params, tok.params = name, rid, 0, len(params), tuple(params)
     tok._host = host
     tok.is_stencil = True
+    tok.radius = int(radius)
     return tok
 
 
@@ -94,7 +98,9 @@ class DeviceRHS:
             if getattr(self, "_host", None) is None:
                 raise TypeError("run-time stencil %r was registered without a host evaluator" % self.name)
             u = np.asarray(y, dtype=np.float64)
-            return np.array([self._host(u[i - 1], u[i], u[(i + 1) % u.size], *self.params) for i in range(u.size)])
+            n, R = u.size, self.radius
+            return np.array([self._host([u[(i + k - R) % n] for k in range(2 * R + 1)], list(self.params), t, i, n)
+                             for i in range(n)])
         if self.id >= 1000:
             if getattr(self, "_host", None) is None:
                 raise TypeError("run-time RHS %r was registered without a host evaluator" % self.name)

@@ -251,7 +251,8 @@ Tab make_tab(int method) {
 // the Python restatement state the same expressions independently.
 typedef void (*UserRhsFn)(double t, const double* y, double* f, const double* p, int dof);
 typedef void (*UserJacFn)(double t, const double* y, double* J, const double* p, int dof);
-typedef double (*UserPointFn)(double um, double u, double up, double p0, double p1);  // 3-point periodic stencil
+// periodic stencil of radius R: w[k] = y[i-R+k], parameters, stage time, grid index, ring length
+typedef double (*UserPointFn)(const double* w, const double* p, double t, int64_t i, int64_t n);
 struct Rhs {
   int id;
   int64_t dof;
@@ -259,13 +260,18 @@ struct Rhs {
   UserRhsFn user = nullptr;  // run-time RHS (tests pass a ctypes callback evaluating the same expression)
   UserJacFn user_jac = nullptr;
   UserPointFn user_point = nullptr;  // run-time stencil of the large-system regime
+  int user_radius = 1;
   mutable int64_t calls = 0;
   void operator()(double t, const double* y, double* f) const {
     calls++;
     if (user_point) {
       const int64_t n = dof;
-      for (int64_t i = 0; i < n; i++)
-        f[i] = user_point(y[i == 0 ? n - 1 : i - 1], y[i], y[i == n - 1 ? 0 : i + 1], p[0], p[1]);
+      const int R = user_radius;
+      double w[16];
+      for (int64_t i = 0; i < n; i++) {
+        for (int k = 0; k < 2 * R + 1; k++) w[k] = y[((i + k - R) % n + n) % n];
+        f[i] = user_point(w, p, t, i, n);
+      }
       return;
     }
     if (user) {
@@ -955,12 +961,14 @@ void ode4ms(const Rhs& F, const Vec& x0, const Vec& tspan, Result& R) {
 thread_local UserRhsFn g_user_rhs = nullptr;
 thread_local UserJacFn g_user_jac = nullptr;
 thread_local UserPointFn g_user_point = nullptr;
+thread_local int g_user_radius = 1;
 
 void solve_one(const ode_b200_opts* op, const double* y0, const double* params, const double* tspan, int n_tspan,
                bool want_trace, Result& R) {
   Rhs F{op->rhs, op->dof, params};
   if (op->rhs >= ODE_B200_STENCIL_USER_BASE) {
     F.user_point = g_user_point;
+    F.user_radius = g_user_radius;
   } else if (op->rhs >= ODE_B200_RHS_USER_BASE) {
     F.user = g_user_rhs;
     F.user_jac = g_user_jac;
@@ -1002,7 +1010,10 @@ void oracle_set_user_rhs(UserRhsFn f, UserJacFn j) {
   g_user_rhs = f;
   g_user_jac = j;
 }
-void oracle_set_user_stencil(UserPointFn f) { g_user_point = f; }
+void oracle_set_user_stencil(UserPointFn f, int radius) {
+  g_user_point = f;
+  g_user_radius = radius >= 1 && radius <= 7 ? radius : 1;
+}
 
 int oracle_solve(const ode_b200_opts* op, const double* y0, const double* params, const double* tspan, int n_tspan,
                  int want_trace, oracle_result** out) {

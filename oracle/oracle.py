@@ -83,7 +83,7 @@ def lib():
         L.oracle_max_threads.restype = C.c_int
         L.oracle_set_user_rhs.argtypes = [C.c_void_p, C.c_void_p]
         L.oracle_set_user_rhs.restype = None
-        L.oracle_set_user_stencil.argtypes = [C.c_void_p]
+        L.oracle_set_user_stencil.argtypes = [C.c_void_p, C.c_int]
         L.oracle_set_user_stencil.restype = None
         L.oracle_set_threads.argtypes = [C.c_int]
         L.oracle_set_threads.restype = None
@@ -255,15 +255,22 @@ def solve_user(method, f, y0, tspan, params=None, jac=None, **kw):
 
 
 STENCIL_BASE = 2000
-_POINTFN = C.CFUNCTYPE(C.c_double, C.c_double, C.c_double, C.c_double, C.c_double, C.c_double)
+_POINTFN = C.CFUNCTYPE(C.c_double, C.POINTER(C.c_double), C.POINTER(C.c_double), C.c_double, C.c_int64, C.c_int64)
 
 
-def solve_user_stencil(method, point, y0, tspan, params, **kw):
-    """Large system with a python 3-point stencil point(um, u, up, p0, p1) -> float on a periodic grid."""
+def solve_user_stencil(method, point, y0, tspan, params, radius=1, **kw):
+    """Large system with a python stencil point(w, p, t, i, n) -> float on a periodic grid: w[k] = u[i-radius+k],
+    p the parameter list, t the stage time, i the grid index, n the ring length."""
     L = lib()
-    cb = _POINTFN(point)
-    L.oracle_set_user_stencil(C.cast(cb, C.c_void_p))
+    npar = len(params)
+    width = 2 * radius + 1
+
+    def trampoline(w, p, t, i, n):
+        return float(point([w[k] for k in range(width)], [p[q] for q in range(npar)], t, i, n))
+
+    cb = _POINTFN(trampoline)
+    L.oracle_set_user_stencil(C.cast(cb, C.c_void_p), int(radius))
     try:
         return solve(method, STENCIL_BASE, y0, tspan, params, **kw)
     finally:
-        L.oracle_set_user_stencil(None)
+        L.oracle_set_user_stencil(None, 1)

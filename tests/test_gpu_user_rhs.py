@@ -120,8 +120,9 @@ RD_BODY = "return p0 * ((um - 2.0 * u) + up) + (p1 * u) * (1.0 - u);"
 NAGUMO_BODY = "return p0 * ((um - 2.0 * u) + up) + ((p1 * u) * (1.0 - u)) * (u - 0.25);"  # not built in
 
 
-def nagumo(um, u, up, p0, p1):
-    return p0 * ((um - 2.0 * u) + up) + ((p1 * u) * (1.0 - u)) * (u - 0.25)
+def nagumo(w, p, t, i, n):
+    um, u, up = w
+    return p[0] * ((um - 2.0 * u) + up) + ((p[1] * u) * (1.0 - u)) * (u - 0.25)
 
 
 def test_user_stencil_large_system():
@@ -144,9 +145,47 @@ def test_user_stencil_large_system():
         assert np.array_equal(t, o.t) and np.array_equal(y, o.y)
         assert (st["n_accept"], st["n_reject"], st["n_rhs"]) == (o.n_accept, o.n_reject, o.n_rhs)
     w = u0[:5]
-    assert np.allclose(ng(0.0, w), [nagumo(w[k - 1], w[k], w[(k + 1) % 5], 0.8, 2.0) for k in range(5)])
+    assert np.allclose(ng(0.0, w), [nagumo([w[k - 1], w[k], w[(k + 1) % 5]], [0.8, 2.0], 0.0, k, 5) for k in range(5)])
     with pytest.raises(m.OdeB200Error, match="NVRTC compilation"):
         m.solve_large("ode45", m.register_stencil("bad", "return undefined_thing;"), u0, [0.0, 1.0])
+
+
+# 4th-order 5-point Laplacian with a space-dependent diffusivity and a travelling time-dependent source:
+# uses the whole stencil interface (radius 2, three parameters, stage time, grid index, ring length)
+WIDE_BODY = """
+const double x = (double)i / (double)n;
+const double kap = p[0] * (1.0 + 0.5 * x);
+const double lap = (((-w[0] + 16.0 * w[1]) - 30.0 * w[2]) + 16.0 * w[3]) - w[4];
+const double s = x - p[2] * t;
+return kap * (lap / 12.0) + p[1] * (s * (1.0 - s));
+"""
+
+
+def wide(w, p, t, i, n):
+    x = float(i) / float(n)
+    kap = p[0] * (1.0 + 0.5 * x)
+    lap = (((-w[0] + 16.0 * w[1]) - 30.0 * w[2]) + 16.0 * w[3]) - w[4]
+    s = x - p[2] * t
+    return kap * (lap / 12.0) + p[1] * (s * (1.0 - s))
+
+
+@pytest.mark.gpu
+def test_user_stencil_radius2_time_and_index_dependent():
+    F = m.register_stencil("wide5", WIDE_BODY, host=wide, params=(0.6, 0.3, 0.1), radius=2)
+    n = 700
+    u0 = 0.2 + 0.1 * np.cos(2 * np.pi * 3 * np.arange(n) / n)
+    ts = [0.0, 0.3, 1.5]
+    for method, points in (("ode45", "specified"), ("ode23", "all"), ("ode78", "specified"), ("ode45", "all")):
+        t, y, st = getattr(m, method).stats(F, u0, ts, points=points)
+        o = O.solve_user_stencil(method, wide, u0, ts, [0.6, 0.3, 0.1], radius=2, points=points)
+        assert np.array_equal(t, o.t) and np.array_equal(y, o.y), (method, points)
+        assert (st["n_accept"], st["n_reject"], st["n_rhs"]) == (o.n_accept, o.n_reject, o.n_rhs)
+    # backward in time, and a radius the tile cannot hold for a 13-stage tableau
+    t, y = m.ode45(F, u0, [0.5, 0.0], points="specified")
+    o = O.solve_user_stencil("ode45", wide, u0, [0.5, 0.0], [0.6, 0.3, 0.1], radius=2, points="specified")
+    assert np.array_equal(y, o.y)
+    with pytest.raises(m.OdeB200Error):
+        m.register_stencil("toowide", "return w[0];", params=(), radius=5)
 
 
 @pytest.mark.gpu

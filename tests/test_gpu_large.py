@@ -113,6 +113,49 @@ def test_slab_decomposition_equals_single_slab(world):
         e.close()
 
 
+WIDE_BODY = """
+const double x = (double)i / (double)n;
+const double lap = (((-w[0] + 16.0 * w[1]) - 30.0 * w[2]) + 16.0 * w[3]) - w[4];
+return (p[0] * (1.0 + 0.5 * x)) * (lap / 12.0) + p[1] * ((x - p[2] * t) * w[2]);
+"""
+
+
+@pytest.mark.parametrize("world", [2, 3])
+def test_slab_decomposition_radius2_index_dependent_stencil(world):
+    """A registered 5-point stencil whose coefficients depend on the global grid index and on time: the slabs
+    must agree on the index base (uneven split: n % world != 0) and exchange 2-wide halos per RHS sweep."""
+    import torch
+    n = 20011
+    y0 = u0(n)
+    F = m.register_stencil("wide_slab_%d" % world, WIDE_BODY, params=(0.6, 0.3, 0.1), radius=2)
+    single = m.solve_large("ode45", F, y0, [0.0, 2.0], trace=True)
+    dev = torch.device("cuda", 0)
+    st = torch.cuda.current_stream(dev).cuda_stream
+    engines, sends, recvs, parts = [], [], [], []
+    for r in range(world):
+        lo, hi = m.shard_bounds(n, world, r)
+        e = m.CudaSlabEngine("ode45", F, hi - lo, n, r, world, [0.0, 2.0], st)
+        yl = torch.tensor(y0[lo:hi], dtype=torch.float64, device=dev)
+        e.set_state(yl.data_ptr())
+        engines.append(e)
+        parts.append(yl)
+        sends.append(torch.zeros(m._lib.XCHG_DOUBLES, dtype=torch.float64, device=dev))
+        recvs.append(torch.zeros(world, m._lib.XCHG_DOUBLES, dtype=torch.float64, device=dev))
+    ctls = lockstep(engines, sends, recvs)
+    out = []
+    for e, yl in zip(engines, parts):
+        o = torch.empty_like(yl)
+        e.get_state(o.data_ptr())
+        out.append(o)
+    torch.cuda.synchronize()
+    y = torch.cat(out).cpu().numpy()
+    assert all(c["status"] == 0 for c in ctls)
+    assert (ctls[0]["n_accept"], ctls[0]["n_reject"]) == (single["n_accept"], single["n_reject"])
+    assert np.array_equal(y, single["y"])
+    for e in engines:
+        e.close()
+
+
 def test_solve_large_distributed_world1():
     import torch
     n = 10000

@@ -116,7 +116,7 @@ __global__ void __launch_bounds__(ENS_BLOCK) ens_adapt_init_kernel(const Ensembl
 // 4 CTAs/SM) and tighter bounds that spill.  Larger state x stage products are left unconstrained.
 template <class Tab, class Rhs>
 constexpr int adapt_min_blocks() {
-  return (Rhs::DOF <= 3 && Rhs::DOF * Tab::S <= 21) ? (5 * 128) / ENS_BLOCK : 0;  // 640 resident threads per SM; 0 = leave it to ptxas
+  return (Rhs::DOF <= 3 && Rhs::DOF * Tab::S <= 21) ? (5 * 128) / ENS_BLOCK : ODEB200_WIDE_MINB;  // 640 resident threads per SM; 0 = leave it to ptxas
 }
 
 template <class Tab, class Rhs, int MODE, bool LITERAL, bool PU = false>

@@ -69,7 +69,8 @@ struct Opts
     max_steps::Int64
     reltol::Float64; abstol::Float64; minstep::Float64; maxstep::Float64; initstep::Float64
     mathmode::Int32
-    reserved::NTuple{7,Int32}
+    host_output::Int32
+    reserved::NTuple{6,Int32}
 end
 
 last_error() = unsafe_string(ccall((:ode_b200_last_error, LIB[]), Cstring, ()))
@@ -95,7 +96,7 @@ function _solve(method::Symbol, F::Union{DeviceRHS,UserRHS}, y0, tspan;
     # jacobian = true selects the registered analytic Jacobian of F (a closure cannot run on the device)
     o = Ref(Opts(METHODS[method], rhs_id(F), length(y), length(F.params), 0, POINTS[points],
                  jacobian === true ? 1 : 0, device, 0,
-                 reltol, abstol, minstep, maxstep, initstep, 0, ntuple(_ -> Int32(0), 7)))
+                 reltol, abstol, minstep, maxstep, initstep, 0, 0, ntuple(_ -> Int32(0), 6)))
     h = Ref{Ptr{Cvoid}}(C_NULL)
     GC.@preserve y ts F begin
         check(ccall((:ode_b200_solve_single, LIB[]), Cint,
@@ -139,7 +140,7 @@ function solve_ensemble(method::Symbol, F::DeviceRHS, Y0::Matrix{Float64}, tspan
     tf = Vector{Float64}(undef, n); yf = Matrix{Float64}(undef, dof, n)
     na = Vector{Int32}(undef, n); nr = similar(na); nf = similar(na); st = similar(na)
     o = Ref(Opts(METHODS[method], rhs_id(F), dof, length(F.params), 0, POINTS[:final], 0, device, 0,
-                 reltol, abstol, minstep, maxstep, initstep, 0, ntuple(_ -> Int32(0), 7)))
+                 reltol, abstol, minstep, maxstep, initstep, 0, 0, ntuple(_ -> Int32(0), 6)))
     GC.@preserve Y0 ts F tf yf na nr nf st begin
         io = Ref(EnsembleIO(n, pointer(Y0), pointer(F.params), pointer(ts), length(ts), 0,
                             pointer(tf), pointer(yf), pointer(na), pointer(nr), pointer(nf), pointer(st),

@@ -31,7 +31,7 @@ class Opts(C.Structure):
                 ("device", C.c_int32), ("max_steps", C.c_int64),
                 ("reltol", C.c_double), ("abstol", C.c_double), ("minstep", C.c_double),
                 ("maxstep", C.c_double), ("initstep", C.c_double),
-                ("mathmode", C.c_int32), ("reserved", C.c_int32 * 7)]
+                ("mathmode", C.c_int32), ("host_output", C.c_int32), ("reserved", C.c_int32 * 6)]
 
 
 class EnsembleIO(C.Structure):

@@ -30,7 +30,8 @@ def _points(points):
 
 
 def make_opts(method, F, tspan, *, reltol=1e-5, abstol=1e-8, minstep=None, maxstep=None, initstep=0.0,
-              points="all", norm=None, jacobian=None, device=0, max_steps=0, params_stride=0, dof=None):
+              points="all", norm=None, jacobian=None, device=0, max_steps=0, params_stride=0, dof=None,
+              direct_output=False):
     """ode_b200_opts with the reference's defaults (src/runge_kutta.jl:233-239, src/ODE.jl:253-259)."""
     if not isinstance(F, DeviceRHS):
         raise TypeError("F must be a registered DeviceRHS (a host closure cannot run on the device; "
@@ -60,6 +61,7 @@ def make_opts(method, F, tspan, *, reltol=1e-5, abstol=1e-8, minstep=None, maxst
     o.maxstep = span / 2.5 if maxstep is None else float(maxstep)   # :236
     o.initstep = float(initstep)
     o.mathmode = 0
+    o.host_output = 1 if direct_output else 0  # kernel writes results into pinned `out=` buffers itself
     return o
 
 
@@ -195,7 +197,9 @@ def solve_ensemble(alg, F, y0, tspan, *, params=None, points="final", pts_cap=No
     trajectory) or [n_traj, n_params].  Returns a dict with t_final, y_final,
     n_accept, n_reject, n_rhs, status (+ pts_t, pts_y, pts_n for points != "final",
     + trace rows (t, dt, err, accepted) for trace_traj).  `out`: a dict returned by an earlier call of
-    the same shape (or arrays from `pinned_empty`) whose t_final ... status arrays are filled in place.
+    the same shape (or arrays from `pinned_empty`) whose t_final ... status arrays are filled in place;
+    with `direct_output=True` the kernel writes into the pinned ones itself as trajectories finish (no copy-back
+    phase; meant for one GPU per host -- many GPUs writing small records into one host contend).
     """
     name = _alg_name(alg)
     y0 = np.ascontiguousarray(np.asarray(y0, dtype=np.float64))

@@ -578,11 +578,13 @@ int ode_b200_solve_ensemble(const ode_b200_opts* opts, const ode_b200_ensemble_i
   d.y0 = dy0;
   d.params = dpar;
   d.tspan = dts;
-  // Output buffers the caller keeps in pinned (page-locked, device-mapped) host memory are written by the
-  // kernel itself as each trajectory ends: the results cross PCIe while the integration is still running,
-  // instead of in a D2H phase after it.  Pageable buffers are staged in HBM and copied back as before.
-  // (`status` is always staged: the fast and literal passes talk through it.)  ODE_B200_ZEROCOPY=0 disables.
-  static const bool zc_on = [] { const char* e = getenv("ODE_B200_ZEROCOPY"); return !(e && atoi(e) == 0); }();
+  // opts.host_output = 1: output buffers the caller keeps in pinned (page-locked, device-mapped) host memory are
+  // written by the kernel itself as each trajectory ends, so the results cross PCIe while the integration is
+  // still running instead of in a D2H phase after it.  Pageable buffers are staged in HBM and copied back.
+  // (`status` is always staged: the fast and literal passes talk through it.)  The environment variable
+  // ODE_B200_ZEROCOPY=0/1 overrides the option, for A/B measurements.
+  bool zc_on = opts->host_output == 1;
+  if (const char* e = getenv("ODE_B200_ZEROCOPY")) zc_on = atoi(e) != 0;
   auto mapped = [&](const void* h) -> void* {
     if (!zc_on || !h) return nullptr;
     cudaPointerAttributes at;

@@ -436,14 +436,17 @@ def test_pinned_output_buffers_are_written_in_place():
     out = dict(y_final=m.pinned_empty((n, 3)), t_final=m.pinned_empty((n,)), n_accept=m.pinned_empty((n,), np.int32),
                n_rhs=m.pinned_empty((n,), np.int32))
     out["y_final"][:] = -1.0
-    got = m.solve_ensemble("ode45", F, y0, [0.0, 1.0], out=out)
+    got = m.solve_ensemble("ode45", F, y0, [0.0, 1.0], out=out, direct_output=True)
     assert got["y_final"] is out["y_final"] and got["n_accept"] is out["n_accept"]
     for k in ("y_final", "t_final", "n_accept", "n_reject", "n_rhs", "status"):
         assert np.array_equal(got[k], ref[k]), k
     # a blow-up goes through the literal second pass, which also writes the mapped buffers
     y0[7] = [1e200, -1e200, 1e200]
     ref = m.solve_ensemble("ode45", F, y0, [0.0, 1.0])
-    got = m.solve_ensemble("ode45", F, y0, [0.0, 1.0], out=out)
+    got = m.solve_ensemble("ode45", F, y0, [0.0, 1.0], out=out, direct_output=True)
+    for k in ("y_final", "t_final", "n_accept", "n_reject", "n_rhs", "status"):
+        assert np.array_equal(got[k], ref[k], equal_nan=True), k
+    got = m.solve_ensemble("ode45", F, y0, [0.0, 1.0], out=out)  # same buffers, staged copy
     for k in ("y_final", "t_final", "n_accept", "n_reject", "n_rhs", "status"):
         assert np.array_equal(got[k], ref[k], equal_nan=True), k
     with pytest.raises(ValueError):

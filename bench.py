@@ -258,8 +258,8 @@ def main():
     d2h = n * 8 + n * dof * 8 + 3 * n * 4
 
     # One GPU per host: let the kernel write the results into the pinned output buffers itself (host_output = 1,
-    # no copy-back phase).  Several ranks on one host: staged copies -- measured on 8 B200s, the small
-    # per-trajectory PCIe writes of 8 kernels contend in the host (15.1 vs 12.6 ms per step).
+    # no copy-back phase: 12.4 -> 11.65 ms).  Several ranks on one host: staged copies -- with 8 B200s moving
+    # 570 MB per step through one host the host side is the bottleneck either way (15.1 ms direct, 14.8 ms staged).
     opts_e2e = m.make_opts("ode45", F, tspan, points="final", device=local_rank, direct_output=(world == 1))
 
     def step_e2e():

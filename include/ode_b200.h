@@ -131,9 +131,9 @@ typedef struct {
   int32_t host_output; /* ode_b200_solve_ensemble with output buffers in page-locked, device-mapped host memory:
                           0 = stage results in HBM and copy them back after the integration (default);
                           1 = the kernel writes each trajectory's results straight into those buffers when it
-                              finishes (no copy-back phase: ~6 % less end-to-end time on one GPU; with many
-                              GPUs writing into one host at once the small PCIe writes contend, so leave it 0
-                              there).  Pageable buffers are always staged. */
+                              finishes (no copy-back phase: ~6 % less end-to-end time on one GPU; no gain
+                              when many GPUs move data through one host at once -- measured with 8).
+                              Pageable buffers are always staged. */
   int32_t reserved[6];
 } ode_b200_opts;
 

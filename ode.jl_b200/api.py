@@ -199,7 +199,7 @@ def solve_ensemble(alg, F, y0, tspan, *, params=None, points="final", pts_cap=No
     + trace rows (t, dt, err, accepted) for trace_traj).  `out`: a dict returned by an earlier call of
     the same shape (or arrays from `pinned_empty`) whose t_final ... status arrays are filled in place;
     with `direct_output=True` the kernel writes into the pinned ones itself as trajectories finish (no copy-back
-    phase; meant for one GPU per host -- many GPUs writing small records into one host contend).
+    phase; pays with one GPU per host, measured no gain with 8 GPUs sharing one host).
     """
     name = _alg_name(alg)
     y0 = np.ascontiguousarray(np.asarray(y0, dtype=np.float64))

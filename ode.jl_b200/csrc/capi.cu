@@ -108,6 +108,30 @@ struct DevScratch {
   }
 };
 thread_local DevScratch g_dev_scratch;
+// page-locked staging block of the small-call path (solve_ensemble_small)
+struct SmallStage {
+  char* host = nullptr;  // cudaHostAlloc, portable + mapped
+  char* dev = nullptr;   // the same block as the device sees it
+  size_t cap = 0;
+  int ensure(size_t bytes) {
+    if (cap >= bytes) return 0;
+    if (host) cudaFreeHost(host);
+    host = dev = nullptr;
+    cap = 0;
+    size_t want = bytes < (256u << 10) ? (256u << 10) : bytes;
+    ODEB200_CUDA(cudaHostAlloc((void**)&host, want, cudaHostAllocPortable | cudaHostAllocMapped));
+    ODEB200_CUDA(cudaHostGetDevicePointer((void**)&dev, host, 0));
+    cap = want;
+    return 0;
+  }
+  void release() {
+    if (host) cudaFreeHost(host);
+    host = dev = nullptr;
+    cap = 0;
+  }
+};
+thread_local SmallStage g_small;
+static const size_t kSmallCallBytes = 192u << 10;
 void arena_release() {  // ode_b200_trim
   if (g_arena.base) {
     cudaSetDevice(g_arena.dev);
@@ -117,6 +141,7 @@ void arena_release() {  // ode_b200_trim
     g_arena.dev = -1;
   }
   g_dev_scratch.release();
+  g_small.release();
 }
 static size_t pad256(size_t b) { return (b + 255) & ~(size_t)255; }
 
@@ -547,6 +572,83 @@ int ode_b200_solve_ensemble_dev(const ode_b200_opts* opts, const ode_b200_ensemb
                          fetch_upar ? upar : nullptr);
 }
 
+// ---- small calls (a single system, a handful of trajectories) -----------------------------------
+// A call that moves a few kilobytes is dominated by the number of driver calls, not by bytes: the general
+// path below issues ~15 (three uploads, a memset, the launches, up to nine downloads).  Here the inputs are
+// packed into one page-locked staging block and uploaded with a single copy, and the kernel writes every
+// output straight into the device-mapped half of the same block; after the stream synchronises the results
+// are copied out by the CPU.  One upload, one memset, the launches, one synchronise.
+
+static int solve_ensemble_small(const ode_b200_opts* opts, const ode_b200_ensemble_io* io, size_t n_par) {
+  const long long n = io->n_traj;
+  const int D = opts->dof;
+  const bool pts = io->pts_y != nullptr;
+  // layout of the staging block: inputs first (uploaded), then outputs (written by the kernel)
+  size_t off = 0;
+  auto place = [&](size_t bytes) {
+    size_t o = off;
+    off += pad256(bytes);
+    return o;
+  };
+  const size_t o_y0 = place((size_t)n * D * 8), o_par = place(n_par * 8), o_ts = place((size_t)io->n_tspan * 8);
+  const size_t in_bytes = off;
+  const size_t o_tf = place(n * 8), o_yf = place((size_t)n * D * 8), o_na = place(n * 4), o_nr = place(n * 4),
+               o_nf = place(n * 4), o_st = place(n * 4);
+  const size_t o_pt = pts ? place((size_t)n * io->pts_cap * 8) : 0, o_py = pts ? place((size_t)n * io->pts_cap * D * 8) : 0,
+               o_pn = pts ? place(n * 4) : 0;
+  const size_t o_tr = io->trace ? place((size_t)io->trace_cap * 32) : 0, o_tn = io->trace ? place(8) : 0;
+  int rc = g_arena.ensure(opts->device, 256 + pad256(in_bytes));  // (also makes opts->device current)
+  if (rc) return rc;
+  rc = g_small.ensure(off);
+  if (rc) return rc;
+  cudaStream_t st = g_arena.stream;
+  unsigned long long* counter = g_arena.take<unsigned long long>(1);
+  char* din = reinterpret_cast<char*>(g_arena.take<char>(in_bytes));
+  char* h = g_small.host;
+  char* dv = g_small.dev;
+  memcpy(h + o_y0, io->y0, (size_t)n * D * 8);
+  if (n_par) memcpy(h + o_par, io->params, n_par * 8);
+  memcpy(h + o_ts, io->tspan, (size_t)io->n_tspan * 8);
+  if (io->trace) memset(h + o_tn, 0, 8);
+  ODEB200_CUDA(cudaMemcpyAsync(din, h, in_bytes, cudaMemcpyHostToDevice, st));
+  ode_b200_ensemble_io d = *io;
+  d.y0 = reinterpret_cast<double*>(din + o_y0);
+  d.params = n_par ? reinterpret_cast<double*>(din + o_par) : nullptr;
+  d.tspan = reinterpret_cast<double*>(din + o_ts);
+  d.t_final = io->t_final ? reinterpret_cast<double*>(dv + o_tf) : nullptr;
+  d.y_final = io->y_final ? reinterpret_cast<double*>(dv + o_yf) : nullptr;
+  d.n_accept = io->n_accept ? reinterpret_cast<int*>(dv + o_na) : nullptr;
+  d.n_reject = io->n_reject ? reinterpret_cast<int*>(dv + o_nr) : nullptr;
+  d.n_rhs = io->n_rhs ? reinterpret_cast<int*>(dv + o_nf) : nullptr;
+  d.status = reinterpret_cast<int*>(dv + o_st);
+  d.pts_t = pts ? reinterpret_cast<double*>(dv + o_pt) : nullptr;
+  d.pts_y = pts ? reinterpret_cast<double*>(dv + o_py) : nullptr;
+  d.pts_n = (pts && io->pts_n) ? reinterpret_cast<int*>(dv + o_pn) : nullptr;
+  if (io->trace) {
+    d.trace = reinterpret_cast<double*>(dv + o_tr);
+    d.trace_n = reinterpret_cast<int64_t*>(dv + o_tn);
+  }
+  rc = launch_ensemble(opts, &d, counter, st, true, nullptr, opts->params_stride == 0 ? io->params : nullptr);
+  if (rc) return rc;
+  ODEB200_CUDA(cudaStreamSynchronize(st));
+  if (io->t_final) memcpy(io->t_final, h + o_tf, n * 8);
+  if (io->y_final) memcpy(io->y_final, h + o_yf, (size_t)n * D * 8);
+  if (io->n_accept) memcpy(io->n_accept, h + o_na, n * 4);
+  if (io->n_reject) memcpy(io->n_reject, h + o_nr, n * 4);
+  if (io->n_rhs) memcpy(io->n_rhs, h + o_nf, n * 4);
+  if (io->status) memcpy(io->status, h + o_st, n * 4);
+  if (pts) {
+    memcpy(io->pts_t, h + o_pt, (size_t)n * io->pts_cap * 8);
+    memcpy(io->pts_y, h + o_py, (size_t)n * io->pts_cap * D * 8);
+    if (io->pts_n) memcpy(io->pts_n, h + o_pn, n * 4);
+  }
+  if (io->trace) {
+    memcpy(io->trace, h + o_tr, (size_t)io->trace_cap * 32);
+    if (io->trace_n) memcpy(io->trace_n, h + o_tn, 8);
+  }
+  return 0;
+}
+
 int ode_b200_solve_ensemble(const ode_b200_opts* opts, const ode_b200_ensemble_io* io) {
   if (!opts || !io) return set_err(ODE_B200_E_INVALID, "null opts/io");
   int rc = device_ok(opts->device);
@@ -565,6 +667,7 @@ int ode_b200_solve_ensemble(const ode_b200_opts* opts, const ode_b200_ensemble_i
                  pad256(n * D * 8) + 4 * pad256(n * 4);
   if (pts) bytes += pad256((size_t)n * io->pts_cap * 8) + pad256((size_t)n * io->pts_cap * D * 8) + pad256(n * 4);
   if (io->trace) bytes += pad256((size_t)io->trace_cap * 32) + 256;
+  if (bytes <= kSmallCallBytes && !getenv("ODE_B200_NO_SMALL_PATH")) return solve_ensemble_small(opts, io, n_par);
   const size_t init_doubles = init_scratch_doubles(opts, io);  // hinit pre-pass scratch (0: inline)
   bytes += pad256(init_doubles * 8);
   rc = g_arena.ensure(opts->device, bytes);

@@ -36,6 +36,14 @@ __global__ void large_control_kernel(const ControlArgs C) {
       m = normInf_step(m, x[XS_MAX]);
       nf = fmax(nf, x[XS_NAN]);
     }
+    // A non-finite trial state or error: the fast kernel dropped zero coefficients, the reference would have
+    // formed Inf*0 = NaN.  Repeat the attempt with the literal kernel first (every rank sees the same gathered
+    // data and takes the same decision); its result is then processed like any other.
+    if (!ctl->redo && (nf > 0.0 || m != m || !is_finite(m))) {
+      ctl->redo = 1;
+      refresh = 0;
+    } else {
+    ctl->redo = 0;
     const double dt = ctl->dt, tdir = ctl->tdir, t = ctl->t;
     double err, newdt;
     int timeout = ctl->timeout;
@@ -138,6 +146,7 @@ __global__ void large_control_kernel(const ControlArgs C) {
       ctl->done = 1;
       ctl->status = ODE_B200_ST_MAXSTEPS;
     }
+    }  // (!redo requested)
   }
   __syncthreads();
   if (!refresh) return;
@@ -267,7 +276,7 @@ __global__ void hinit_control_kernel(LargeCtl* ctl, const double* xrecv, int wor
 // Kernel handles are `const void*`: a __global__ function pointer for the compiled-in stencil, a
 // cudaKernel_t for a stencil registered at run time (rtc.cu).
 struct MethodInfo {
-  const void *attempt, *hinit_f0, *hinit_f1;
+  const void *attempt, *attempt_literal, *hinit_f0, *hinit_f1;
   int H, VAL, order, S, fsal;
 };
 static int persistent_grid(const void* k, int device, long long tiles) {
@@ -298,7 +307,8 @@ static MethodInfo method_info(int radius) {
   MethodInfo m;
   geometry<Tab>(&m, radius);
   static_assert(LargeGeom<Tab, RhsReactionDiffusion>::H == (Tab::S - 1 + (Tab::fsal() ? 0 : 1) + 3) / 4 * 4, "geometry");
-  m.attempt = (const void*)large_attempt_kernel<Tab, RhsReactionDiffusion>;
+  m.attempt = (const void*)large_attempt_kernel<Tab, RhsReactionDiffusion, false>;
+  m.attempt_literal = (const void*)large_attempt_kernel<Tab, RhsReactionDiffusion, true>;
   m.hinit_f0 = (const void*)hinit_f0_kernel<RhsReactionDiffusion>;
   m.hinit_f1 = (const void*)hinit_f1_kernel<RhsReactionDiffusion>;
   return m;
@@ -321,7 +331,7 @@ using namespace odeb200;
 struct ode_b200_slab {
   int device = 0, rank = 0, world = 1;
   long long n = 0, n_global = 0, tiles = 0;
-  int grid = 1;
+  int grid = 1, grid_literal = 1;
   MethodInfo mi;
   cudaStream_t stream = nullptr;
   double *Y[2] = {nullptr, nullptr}, *K[2] = {nullptr, nullptr};
@@ -387,7 +397,8 @@ int ode_b200_slab_create(const ode_b200_opts* o, int64_t n_local, int64_t n_glob
                    radius, o->method, mi.H);
   if (user_stencil) {  // same geometry, kernels compiled at run time for the registered point functor
     ODEB200_CUDA(cudaSetDevice(o->device));
-    if (!user_stencil_kernels(o->rhs, o->method, &mi.attempt, &mi.hinit_f0, &mi.hinit_f1)) return ODE_B200_E_INVALID;
+    if (!user_stencil_kernels(o->rhs, o->method, &mi.attempt, &mi.attempt_literal, &mi.hinit_f0, &mi.hinit_f1))
+      return ODE_B200_E_INVALID;
   }
   if (np > 0 && (!params || o->n_params < np))
     return set_err(ODE_B200_E_INVALID, "the stencil RHS needs %d params (reaction_diffusion: {kappa, r})", np);
@@ -414,6 +425,7 @@ int ode_b200_slab_create(const ode_b200_opts* o, int64_t n_local, int64_t n_glob
   s->stream = (cudaStream_t)stream;
   s->tiles = (n_local + mi.VAL - 1) / mi.VAL;
   s->grid = persistent_grid(mi.attempt, o->device, s->tiles);
+  s->grid_literal = persistent_grid(mi.attempt_literal, o->device, s->tiles);
   memset(&s->sc, 0, sizeof(s->sc));
   s->np = np;
   for (int q = 0; q < np; q++) s->sc.p[q] = params[q];
@@ -666,6 +678,9 @@ int ode_b200_slab_attempt(ode_b200_slab* s, double* xsend) {
   A.sc = s->sc;
   void* kargs[] = {(void*)&A};
   ODEB200_CUDA(cudaLaunchKernel(s->mi.attempt, dim3((unsigned)s->grid), dim3(LARGE_THREADS), kargs, 0, s->stream));
+  // the literal repeat of an attempt that went non-finite (ctl->redo); returns at once otherwise
+  ODEB200_CUDA(cudaLaunchKernel(s->mi.attempt_literal, dim3((unsigned)s->grid_literal), dim3(LARGE_THREADS), kargs, 0, s->stream));
+  note_launch();
   note_launch();
   return 0;
 }

@@ -66,6 +66,7 @@ struct LargeCtl {
   long long trace_n, trace_cap;
   int par;      // y = Y[par], ytrial = Y[par^1]; k1 = K[par], k_next = K[par^1]
   int islast, timeout, done, status, accepted_last;
+  int redo;  // the attempt just computed saw a non-finite value: repeat it with the LITERAL kernel before deciding
   unsigned int blocks_done;  // last-CTA-done counter of the attempt kernel
   int order;
   // points = :specified (src/runge_kutta.jl:321-326): tspan rows [out_lo, out_hi) are to be
@@ -184,7 +185,11 @@ struct LargeGeom {
   static constexpr int VAL = W - 2 * H;
 };
 
-template <class Tab, class Rhs>
+// LITERAL = false: zero tableau coefficients are dropped (bit-identical to the reference while every stage is
+// finite).  LITERAL = true multiplies every coefficient like the reference (:385-392,454), so a non-finite
+// stage turns into NaN through Inf*0 exactly as it does there; the control kernel asks for it (ctl->redo) when
+// the fast attempt produced a non-finite trial state or error, and it is a no-op launch otherwise.
+template <class Tab, class Rhs, bool LITERAL = false>
 #ifdef ODEB200_LARGE_MINB
 __global__ void __launch_bounds__(LARGE_THREADS, ODEB200_LARGE_MINB) large_attempt_kernel(
 #else
@@ -204,6 +209,7 @@ __global__ void __launch_bounds__(LARGE_THREADS) large_attempt_kernel(
 
   LargeCtl* ctl = A.ctl;
   if (ctl->done) return;
+  if (LITERAL != (ctl->redo != 0)) return;
   const int tid = threadIdx.x;
   const int par = ctl->par;
   const double dt = ctl->dt, t = ctl->t;
@@ -253,8 +259,8 @@ __global__ void __launch_bounds__(LARGE_THREADS) large_attempt_kernel(
     constexpr double b10 = Tab::b(0, 0), b20 = Tab::b(1, 0);
 #pragma unroll
     for (int p = 0; p < P; p++) {
-      ytrial[p] = (b10 != 0.0) ? b10 * k1[p] : 0.0;
-      yerr[p] = (b20 != 0.0) ? b20 * k1[p] : 0.0;
+      ytrial[p] = LITERAL ? (0.0 + b10 * k1[p]) : ((b10 != 0.0) ? b10 * k1[p] : 0.0);
+      yerr[p] = LITERAL ? (0.0 + b20 * k1[p]) : ((b20 != 0.0) ? b20 * k1[p] : 0.0);
       dtk[0][p] = dt * k1[p];
       klast[p] = k1[p];
     }
@@ -266,7 +272,7 @@ __global__ void __launch_bounds__(LARGE_THREADS) large_attempt_kernel(
       static_for<s>([&](auto J) {
         constexpr int ss = decltype(J)::value;
         constexpr double a = Tab::a(s, ss);
-        if constexpr (a != 0.0) {
+        if constexpr (a != 0.0 || LITERAL) {
 #pragma unroll
           for (int p = 0; p < P; p++) ytmp[p] = ytmp[p] + dtk[ss][p] * a;  // (dt*k)*a :454
         }
@@ -278,8 +284,8 @@ __global__ void __launch_bounds__(LARGE_THREADS) large_attempt_kernel(
       constexpr double b1 = Tab::b(0, s), b2 = Tab::b(1, s);
 #pragma unroll
       for (int p = 0; p < P; p++) {
-        if constexpr (b1 != 0.0) ytrial[p] = ytrial[p] + b1 * ks[p];
-        if constexpr (b2 != 0.0) yerr[p] = yerr[p] + b2 * ks[p];
+        if constexpr (b1 != 0.0 || LITERAL) ytrial[p] = ytrial[p] + b1 * ks[p];
+        if constexpr (b2 != 0.0 || LITERAL) yerr[p] = yerr[p] + b2 * ks[p];
         if constexpr (s < S - 1) dtk[s][p] = dt * ks[p];
         if constexpr (s == S - 1) klast[p] = ks[p];
       }

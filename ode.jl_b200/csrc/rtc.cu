@@ -248,7 +248,8 @@ const void* user_init_kernel(int rhs, int method) {
   return it == g_kernels.end() ? nullptr : it->second;
 }
 
-bool user_stencil_kernels(int rhs, int method, const void** attempt, const void** hinit_f0, const void** hinit_f1) {
+bool user_stencil_kernels(int rhs, int method, const void** attempt, const void** attempt_literal, const void** hinit_f0,
+                          const void** hinit_f1) {
   UserRhs u;
   {
     std::lock_guard<std::mutex> lk(g_mu);
@@ -266,8 +267,9 @@ bool user_stencil_kernels(int rhs, int method, const void** attempt, const void*
   }
   int dev = 0;
   cudaGetDevice(&dev);
-  char e0[256], e1[128], e2[128], keyb[512];
-  snprintf(e0, sizeof(e0), "odeb200::large_attempt_kernel<%s, odeb200::StencilUser>", tab);
+  char e0[256], e1[128], e2[128], e3[256], keyb[512];
+  snprintf(e0, sizeof(e0), "odeb200::large_attempt_kernel<%s, odeb200::StencilUser, false>", tab);
+  snprintf(e3, sizeof(e3), "odeb200::large_attempt_kernel<%s, odeb200::StencilUser, true>", tab);
   snprintf(e1, sizeof(e1), "odeb200::hinit_f0_kernel<odeb200::StencilUser>");
   snprintf(e2, sizeof(e2), "odeb200::hinit_f1_kernel<odeb200::StencilUser>");
   snprintf(keyb, sizeof(keyb), "%d|%d|%s", dev, rhs, e0);
@@ -277,6 +279,7 @@ bool user_stencil_kernels(int rhs, int method, const void** attempt, const void*
     auto it = g_kernels.find(key);
     if (it != g_kernels.end()) {
       *attempt = it->second;
+      *attempt_literal = g_kernels[key + "|lit"];
       *hinit_f0 = g_kernels[key + "|f0"];
       *hinit_f1 = g_kernels[key + "|f1"];
       return true;
@@ -294,13 +297,15 @@ bool user_stencil_kernels(int rhs, int method, const void** attempt, const void*
   if (u.dof == 1) src += "    const double um = w[0], u = w[1], up = w[2]; (void)um; (void)u; (void)up;\n";
   src += "    const double p0 = p[0], p1 = p[1]; (void)p0; (void)p1; (void)t; (void)i; (void)n;\n";
   src += u.eval_body + "\n  }\n};\n}  // namespace odeb200\n";
-  const char* exprs[3] = {e0, e1, e2};
-  const void* out[3] = {nullptr, nullptr, nullptr};
-  if (!compile_and_load(u.name, src, exprs, 3, out)) return false;
+  const char* exprs[4] = {e0, e1, e2, e3};
+  const void* out[4] = {nullptr, nullptr, nullptr, nullptr};
+  if (!compile_and_load(u.name, src, exprs, 4, out)) return false;
   std::lock_guard<std::mutex> lk(g_mu);
   g_kernels[key] = out[0];
   g_kernels[key + "|f0"] = out[1];
   g_kernels[key + "|f1"] = out[2];
+  g_kernels[key + "|lit"] = out[3];
+  *attempt_literal = out[3];
   *attempt = out[0];
   *hinit_f0 = out[1];
   *hinit_f1 = out[2];

@@ -6,5 +6,6 @@ const void* user_kernel(int rhs, int method, int mode, int literal, int jac);
 const void* user_init_kernel(int rhs, int method);  // hinit pre-pass compiled with the mode-0 adaptive kernel
 bool user_stencil_info(int rhs, int* radius, int* np);
 // kernels of the large-system path for a registered stencil; false + last_error on failure
-bool user_stencil_kernels(int rhs, int method, const void** attempt, const void** hinit_f0, const void** hinit_f1);
+bool user_stencil_kernels(int rhs, int method, const void** attempt, const void** attempt_literal, const void** hinit_f0,
+                          const void** hinit_f1);
 }  // namespace odeb200

@@ -238,6 +238,54 @@ def test_large_nan_state_and_backward_direction():
     assert np.array_equal(got["trace"], ref.trace) and np.array_equal(got["y"], ref.y[-1]) and got["t_final"] == 0.0
 
 
+@pytest.mark.parametrize("method", ["ode45", "ode23", "ode45_fe", "ode78"])
+def test_large_overflowing_first_step_recovers_like_the_reference(method):
+    """A first step far too long overflows the stages to Inf.  The reference multiplies zero tableau coefficients,
+    so Inf*0 = NaN reaches the trial state, the NaN guard (:432) cuts dt by 5 and the integration recovers.  The
+    fused kernel drops zero coefficients, notices the non-finite result and repeats the attempt with its literal
+    instantiation: same trace, same final state, bit for bit -- single slab and two slabs."""
+    import torch
+    n = 6000
+    y0 = u0(n)
+    F = m.DeviceRHS("reaction_diffusion", *RD)
+    kw = dict(initstep=1e7)
+    got = m.solve_large(method, F, y0, [0.0, 1.0], trace=True, **kw)
+    ref = O.solve(method, "reaction_diffusion", y0, [0.0, 1.0], RD, trace=True, points="final", **kw)
+    if method in ("ode45", "ode78"):
+        assert ref.status == 0 and np.any(ref.trace[:, 2] == 10.0)  # the NaN guard fired and the run recovered
+    # (ode45_fe meets err = Inf -> dt = NaN, where the reference spins forever and both sides stop with status 3)
+    assert got["status"] == ref.status
+    assert (got["n_accept"], got["n_reject"], got["n_rhs"]) == (ref.n_accept, ref.n_reject, ref.n_rhs)
+    assert np.array_equal(got["trace"], ref.trace, equal_nan=True)
+    assert np.array_equal(got["y"], ref.y[-1])
+    if method != "ode45":
+        return
+    dev = torch.device("cuda", 0)
+    st = torch.cuda.current_stream(dev).cuda_stream
+    world = 2
+    engines, sends, recvs, parts = [], [], [], []
+    for r in range(world):
+        lo, hi = m.shard_bounds(n, world, r)
+        e = m.CudaSlabEngine(method, F, hi - lo, n, r, world, [0.0, 1.0], st, **kw)
+        yl = torch.tensor(y0[lo:hi], dtype=torch.float64, device=dev)
+        e.set_state(yl.data_ptr())
+        engines.append(e)
+        parts.append(yl)
+        sends.append(torch.zeros(m._lib.XCHG_DOUBLES, dtype=torch.float64, device=dev))
+        recvs.append(torch.zeros(world, m._lib.XCHG_DOUBLES, dtype=torch.float64, device=dev))
+    ctls = lockstep(engines, sends, recvs)
+    out = []
+    for e, yl in zip(engines, parts):
+        o = torch.empty_like(yl)
+        e.get_state(o.data_ptr())
+        out.append(o)
+    torch.cuda.synchronize()
+    assert (ctls[0]["n_accept"], ctls[0]["n_reject"]) == (ref.n_accept, ref.n_reject)
+    assert np.array_equal(torch.cat(out).cpu().numpy(), ref.y[-1])
+    for e in engines:
+        e.close()
+
+
 @pytest.mark.parametrize("method", ["ode45", "ode23"])
 def test_large_points_all_through_the_front_end(method):
     """odeXX(F, u0, tspan) with the default points=:all on a dof = N state: every accepted step plus the

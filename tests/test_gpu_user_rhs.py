@@ -210,3 +210,49 @@ def test_user_rhs_wider_state_matches_oracle(dof):
         o = O.solve_user(meth, host, y0, ts, [1.5, 0.3])
         assert np.array_equal(t, o.t) and np.array_equal(y, o.y), meth
         assert (st["n_accept"], st["n_rhs"]) == (o.n_accept, o.n_rhs), meth
+
+
+# Two interleaved species (X at even, Y at odd grid indices) with fixed (Dirichlet) ends, written as ONE radius-2
+# stencil that branches on the grid index: the registered-stencil interface covers multi-component and
+# non-periodic method-of-lines systems without a special code path (the periodic wrap only feeds points whose
+# value the functor ignores).
+BRUSS_MOL_BODY = """
+const long long cell = i >> 1, ncell = n >> 1;
+if (cell == 0 || cell == ncell - 1) return 0.0;           // boundary cells keep their value
+const double lap = (w[0] - 2.0 * w[2]) + w[4];            // same species two indices away
+if ((i & 1) == 0) {                                       // X: A + X^2 Y - (B+1) X + D lap
+  const double x = w[2], y = w[3];
+  return ((p[0] + (x * x) * y) - (p[1] + 1.0) * x) + p[2] * lap;
+}
+const double x = w[1], y = w[2];                          // Y: B X - X^2 Y + D lap
+return (p[1] * x - (x * x) * y) + p[2] * lap;
+"""
+
+
+def bruss_mol(w, p, t, i, n):
+    cell, ncell = i >> 1, n >> 1
+    if cell == 0 or cell == ncell - 1:
+        return 0.0
+    lap = (w[0] - 2.0 * w[2]) + w[4]
+    if (i & 1) == 0:
+        x, y = w[2], w[3]
+        return ((p[0] + (x * x) * y) - (p[1] + 1.0) * x) + p[2] * lap
+    x, y = w[1], w[2]
+    return (p[1] * x - (x * x) * y) + p[2] * lap
+
+
+@pytest.mark.gpu
+def test_user_stencil_two_species_dirichlet_ends():
+    F = m.register_stencil("bruss_mol", BRUSS_MOL_BODY, host=bruss_mol, params=(1.0, 3.0, 0.02), radius=2)
+    ncell = 300
+    xs = np.arange(ncell) / (ncell - 1)
+    u0 = np.empty(2 * ncell)
+    u0[0::2] = 1.0 + np.sin(2 * np.pi * xs)
+    u0[1::2] = 3.0
+    ts = [0.0, 0.5, 2.0]
+    for method, points in (("ode45", "specified"), ("ode23", "all")):
+        t, y, st = getattr(m, method).stats(F, u0, ts, points=points)
+        o = O.solve_user_stencil(method, bruss_mol, u0, ts, [1.0, 3.0, 0.02], radius=2, points=points)
+        assert np.array_equal(t, o.t) and np.array_equal(y, o.y), method
+        assert (st["n_accept"], st["n_reject"], st["n_rhs"]) == (o.n_accept, o.n_reject, o.n_rhs)
+        assert np.array_equal(y[-1][:2], u0[:2]) and np.array_equal(y[-1][-2:], u0[-2:])  # the ends did not move

@@ -76,11 +76,14 @@ typedef enum {
   ODE_B200_RHS_ROBERTSON = 6, /* dof 3: params {k1, k2, k3}           (test/runtests.jl:81-87) */
   ODE_B200_RHS_KEPLER = 7,    /* dof 4: planar two-body, mu = 1 */
   ODE_B200_RHS_REACTION_DIFFUSION = 8, /* dof N: kappa*((u[i-1]-2u[i])+u[i+1]) + (r*u[i])*(1-u[i]), periodic; params {kappa, r} */
-  ODE_B200_RHS_COUNT = 9
+  ODE_B200_RHS_RD_FIELD = 9,  /* dof N: the same reaction-diffusion system written as a general gather "field" (one
+                                  kernel per stage instead of the fused stencil kernel); params {kappa, r} */
+  ODE_B200_RHS_COUNT = 10
 } ode_b200_rhs;
 /* ids returned by ode_b200_register_rhs / ode_b200_register_stencil start here */
 #define ODE_B200_RHS_USER_BASE 1000
 #define ODE_B200_STENCIL_USER_BASE 2000
+#define ODE_B200_FIELD_USER_BASE 3000
 
 /* `points` keyword (src/runge_kutta.jl:238,283-290); FINAL is an ensemble-only
  * extension that skips all intermediate output. */
@@ -200,6 +203,13 @@ int ode_b200_register_rhs(const char* name, int32_t dof, int32_t n_params, const
  * (must `return` the value; a 3-point stencil may also use the names um, u, up and p0, p1).  Returns an rhs id
  * >= ODE_B200_STENCIL_USER_BASE for ode_b200_solve_large* and the slab sessions. */
 int ode_b200_register_stencil(const char* name, int32_t radius, int32_t n_params, const char* point_body);
+/* A GENERAL right-hand side for one large system: F_i(t, y) may read any component of y (non-local couplings,
+ * networks, N-body sums, 2-D grids flattened by the caller).  `rhs_body` is the body of
+ *     double rhs(long long i, long long n, const double* y, const double (&p)[8], double t)
+ * returning dy_i/dt (n_params <= 8).  Such a system runs one kernel per Runge-Kutta stage (the stage argument must be
+ * complete in memory before any component of F can be evaluated) on one GPU, through ode_b200_solve_large* and a
+ * single-slab session (world = 1).  Returns an rhs id >= ODE_B200_FIELD_USER_BASE. */
+int ode_b200_register_field(const char* name, int32_t n_params, const char* rhs_body);
 
 /* ---- ensembles of small systems (one trajectory per thread) -------------- */
 /* Replaces n_traj independent calls of oderk_adapt / oderk_fixed / ode23s.

@@ -14,7 +14,8 @@ LIB_PATH = os.environ.get("ODE_B200_LIB") or os.path.join(_HERE, "libode_b200.so
 # include/ode_b200.h enums
 METHODS = dict(ode1=0, ode2_midpoint=1, ode2_heun=2, ode4=3, ode21=4, ode23=5, ode45_fe=6, ode45_dp=7, ode45=7,
                ode78=8, ode23s=9, ode4s=10, ode4s_s=10, ode4s_kr=11, ode4ms=12)
-RHS = dict(linear=0, const=1, timelin=2, rotation=3, lorenz=4, vdp=5, robertson=6, kepler=7, reaction_diffusion=8)
+RHS = dict(linear=0, const=1, timelin=2, rotation=3, lorenz=4, vdp=5, robertson=6, kepler=7, reaction_diffusion=8,
+           reaction_diffusion_field=9)
 POINTS = {"all": 0, "specified": 1, "final": 2}
 STATUS = {0: "OK", 1: "MINSTEP", 2: "MAXSTEPS", 3: "NONFINITE", 4: "SINGULAR", 5: "OVERFLOW"}
 E_ZERO_SPAN, E_INITSTEP, E_POINTS, E_NOT_ADAPTIVE, E_NO_DEVICE, E_UNSUPPORTED = -2, -3, -4, -5, -6, -8
@@ -109,6 +110,7 @@ def lib():
                                            C.POINTER(LargeStats), dp, C.c_int64, lp]
     L.ode_b200_trim.restype = None
     L.ode_b200_register_stencil.argtypes = [C.c_char_p, C.c_int32, C.c_int32, C.c_char_p]
+    L.ode_b200_register_field.argtypes = [C.c_char_p, C.c_int32, C.c_char_p]
     L.ode_b200_register_rhs.argtypes = [C.c_char_p, C.c_int32, C.c_int32, C.c_char_p, C.c_char_p]
     L.ode_b200_slab_create.argtypes = [C.POINTER(Opts), C.c_int64, C.c_int64, C.c_int32, C.c_int32, dp, C.c_double,
                                        C.c_double, C.c_void_p, C.POINTER(C.c_void_p)]

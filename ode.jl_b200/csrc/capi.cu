@@ -167,9 +167,10 @@ static const NameId kRhs[] = {{"linear", ODE_B200_RHS_LINEAR},
                               {"vdp", ODE_B200_RHS_VDP},
                               {"robertson", ODE_B200_RHS_ROBERTSON},
                               {"kepler", ODE_B200_RHS_KEPLER},
-                              {"reaction_diffusion", ODE_B200_RHS_REACTION_DIFFUSION}};
-static const int kRhsDof[ODE_B200_RHS_COUNT] = {1, 1, 1, 2, 3, 2, 3, 4, 0};
-static const int kRhsNp[ODE_B200_RHS_COUNT] = {1, 1, 1, 0, 3, 1, 3, 0, 2};
+                              {"reaction_diffusion", ODE_B200_RHS_REACTION_DIFFUSION},
+                              {"reaction_diffusion_field", ODE_B200_RHS_RD_FIELD}};
+static const int kRhsDof[ODE_B200_RHS_COUNT] = {1, 1, 1, 2, 3, 2, 3, 4, 0, 0};
+static const int kRhsNp[ODE_B200_RHS_COUNT] = {1, 1, 1, 0, 3, 1, 3, 0, 2, 2};
 
 template <class T>
 static double tab_get(int which, int i, int j) {
@@ -228,7 +229,7 @@ static int validate(const ode_b200_opts* o, const ode_b200_ensemble_io* io, doub
   int rdof = 0, rnp = 0;
   bool has_jac = true;
   if (!rhs_shape(o->rhs, &rdof, &rnp, &has_jac)) return set_err(ODE_B200_E_INVALID, "unknown rhs %d", o->rhs);
-  if (o->rhs == ODE_B200_RHS_REACTION_DIFFUSION)
+  if (o->rhs == ODE_B200_RHS_REACTION_DIFFUSION || o->rhs == ODE_B200_RHS_RD_FIELD)
     return set_err(ODE_B200_E_UNSUPPORTED, "reaction_diffusion is a large-system RHS: use ode_b200_solve_large");
   if (o->dof != rdof) return set_err(ODE_B200_E_INVALID, "rhs %d has dof %d, got %d", o->rhs, rdof, o->dof);
   if (o->n_params < rnp) return set_err(ODE_B200_E_INVALID, "rhs %d needs %d params, got %d", o->rhs, rnp, o->n_params);

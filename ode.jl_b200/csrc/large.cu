@@ -9,7 +9,7 @@
 #include <vector>
 
 #include "host_util.cuh"
-#include "large.cuh"
+#include "field.cuh"
 #include "rtc.cuh"
 
 namespace odeb200 {
@@ -231,6 +231,11 @@ __global__ void reduce_max_kernel(const double* part, int nblocks, int ncol, dou
     if (threadIdx.x == 0) xsend[XS_AUX0 + c] = v;
   }
 }
+__global__ void __launch_bounds__(256) field_hinit_x1_kernel(const double* __restrict__ y, const double* __restrict__ f0,
+                                                             const LargeCtl* ctl, double* x1, long long n) {
+  const double th = ctl->tdir * ctl->h0;
+  for (long long i = blockIdx.x * 256LL + threadIdx.x; i < n; i += (long long)gridDim.x * 256) x1[i] = y[i] + th * f0[i];  // :100
+}
 // hinit scalar parts: stage 0 after the (max|y|, max|f0|) exchange, stage 1 after max|f1-f0|
 __global__ void hinit_control_kernel(LargeCtl* ctl, const double* xrecv, int world, int stage, int order) {
   if (threadIdx.x != 0) return;
@@ -278,6 +283,11 @@ __global__ void hinit_control_kernel(LargeCtl* ctl, const double* xrecv, int wor
 struct MethodInfo {
   const void *attempt, *attempt_literal, *hinit_f0, *hinit_f1;
   int H, VAL, order, S, fsal;
+  // general gather right-hand sides (field.cuh): one kernel per stage instead of `attempt`
+  bool field = false;
+  const void* f_first = nullptr;
+  const void* f_stage[FIELD_MAX_STAGES + 1] = {};  // [s], reference stage numbering 2 .. S
+  const void* f_f1 = nullptr;
 };
 static int persistent_grid(const void* k, int device, long long tiles) {
   int sms = 0, per_sm = 0;
@@ -313,6 +323,40 @@ static MethodInfo method_info(int radius) {
   m.hinit_f1 = (const void*)hinit_f1_kernel<RhsReactionDiffusion>;
   return m;
 }
+template <class Tab, class Rhs, int s>
+struct FillFieldStages {
+  static void run(MethodInfo* m) {
+    m->f_stage[s] = (const void*)field_stage_kernel<Tab, Rhs, s>;
+    FillFieldStages<Tab, Rhs, s - 1>::run(m);
+  }
+};
+template <class Tab, class Rhs>
+struct FillFieldStages<Tab, Rhs, 1> {
+  static void run(MethodInfo*) {}
+};
+template <class Tab>
+static MethodInfo field_method_info() {
+  MethodInfo m;
+  geometry<Tab>(&m, 0);  // no ghost cells
+  m.attempt = m.attempt_literal = nullptr;
+  m.field = true;
+  m.f_first = (const void*)field_first_kernel<Tab>;
+  FillFieldStages<Tab, FieldReactionDiffusion, Tab::S>::run(&m);
+  m.f_f1 = (const void*)field_f1_kernel<FieldReactionDiffusion>;
+  m.hinit_f0 = (const void*)field_hinit_f0_kernel<FieldReactionDiffusion>;
+  m.hinit_f1 = (const void*)field_hinit_f1_kernel<FieldReactionDiffusion>;
+  return m;
+}
+static bool pick_field_method(int method, MethodInfo* out) {
+  switch (method) {
+    case ODE_B200_M_RK21: *out = field_method_info<TabRK21>(); return true;
+    case ODE_B200_M_RK23: *out = field_method_info<TabRK23>(); return true;
+    case ODE_B200_M_RK45_FE: *out = field_method_info<TabRK45>(); return true;
+    case ODE_B200_M_DOPRI5: *out = field_method_info<TabDopri5>(); return true;
+    case ODE_B200_M_FEH78: *out = field_method_info<TabFeh78>(); return true;
+    default: return false;
+  }
+}
 static bool pick_method(int method, int radius, MethodInfo* out) {
   switch (method) {
     case ODE_B200_M_RK21: *out = method_info<TabRK21>(radius); return true;
@@ -346,6 +390,9 @@ struct ode_b200_slab {
   long long out_cap = 0;
   StencilCtx sc;  // parameters, global index of the first interior point, ring length
   int np = 2;     // parameters the stencil takes
+  double* KS[FIELD_MAX_STAGES] = {};  // field path: middle stages
+  double* T[2] = {nullptr, nullptr};  // field path: stage-argument ping-pong
+  int field_grid = 1;
   int init_blocks = 0;
   LargeCtl host_ctl;
 };
@@ -381,18 +428,22 @@ int ode_b200_slab_create(const ode_b200_opts* o, int64_t n_local, int64_t n_glob
     return set_err(ODE_B200_E_NO_DEVICE, "no CUDA device available; libode_b200 has no CPU fallback");
   }
   if (o->device < 0 || o->device >= cnt) return set_err(ODE_B200_E_INVALID, "device %d out of range", o->device);
-  const bool user_stencil = o->rhs >= ODE_B200_STENCIL_USER_BASE;
-  if (o->rhs != ODE_B200_RHS_REACTION_DIFFUSION && !user_stencil)
-    return set_err(ODE_B200_E_UNSUPPORTED, "the large-system path takes a stencil RHS (reaction_diffusion or a registered stencil)");
+  const bool user_field = o->rhs >= ODE_B200_FIELD_USER_BASE;
+  const bool field = user_field || o->rhs == ODE_B200_RHS_RD_FIELD;
+  const bool user_stencil = !field && o->rhs >= ODE_B200_STENCIL_USER_BASE;
+  if (o->rhs != ODE_B200_RHS_REACTION_DIFFUSION && !user_stencil && !field)
+    return set_err(ODE_B200_E_UNSUPPORTED, "the large-system path takes a stencil RHS (reaction_diffusion or a registered stencil) "
+                                           "or a registered field");
   int radius = 1, np = 2;  // reaction_diffusion
   if (user_stencil && !user_stencil_info(o->rhs, &radius, &np)) return set_err(ODE_B200_E_INVALID, "unknown stencil %d", o->rhs);
+  if (user_field && !user_field_info(o->rhs, &np)) return set_err(ODE_B200_E_INVALID, "unknown field %d", o->rhs);
   MethodInfo mi;
-  if (!pick_method(o->method, radius, &mi)) {
+  if (!(field ? pick_field_method(o->method, &mi) : pick_method(o->method, radius, &mi))) {
     if (o->method >= 0 && o->method <= ODE_B200_M_RK4)
       return set_err(ODE_B200_E_NOT_ADAPTIVE, "Can only use this solver with an adaptive RK Butcher table");
     return set_err(ODE_B200_E_UNSUPPORTED, "method %d has no large-system kernel", o->method);
   }
-  if (XS_EDGE + 4 * mi.H > XCHG || mi.VAL < LARGE_THREADS * LARGE_P / 2)
+  if (!field && (XS_EDGE + 4 * mi.H > XCHG || mi.VAL < LARGE_THREADS * LARGE_P / 2))
     return set_err(ODE_B200_E_UNSUPPORTED, "stencil radius %d with method %d needs %d ghost points per side: too wide for the tile",
                    radius, o->method, mi.H);
   if (user_stencil) {  // same geometry, kernels compiled at run time for the registered point functor
@@ -400,10 +451,24 @@ int ode_b200_slab_create(const ode_b200_opts* o, int64_t n_local, int64_t n_glob
     if (!user_stencil_kernels(o->rhs, o->method, &mi.attempt, &mi.attempt_literal, &mi.hinit_f0, &mi.hinit_f1))
       return ODE_B200_E_INVALID;
   }
+  if (user_field) {  // one kernel per stage, compiled at run time for the registered gather functor
+    ODEB200_CUDA(cudaSetDevice(o->device));
+    const void* k[FIELD_MAX_STAGES + 4] = {};
+    if (!user_field_kernels(o->rhs, o->method, mi.S, k)) return ODE_B200_E_INVALID;
+    mi.f_first = k[0];
+    for (int st = 2; st <= mi.S; st++) mi.f_stage[st] = k[st - 1];
+    mi.f_f1 = k[mi.S];
+    mi.hinit_f0 = k[mi.S + 1];
+    mi.hinit_f1 = k[mi.S + 2];
+  }
   if (np > 0 && (!params || o->n_params < np))
-    return set_err(ODE_B200_E_INVALID, "the stencil RHS needs %d params (reaction_diffusion: {kappa, r})", np);
+    return set_err(ODE_B200_E_INVALID, "the right-hand side needs %d params (reaction_diffusion: {kappa, r})", np);
   if (world < 1 || rank < 0 || rank >= world) return set_err(ODE_B200_E_INVALID, "bad rank/world");
-  if (n_local < 2 * mi.H || n_global < 32 || n_local > n_global)
+  if (field && world != 1)
+    return set_err(ODE_B200_E_UNSUPPORTED, "a general field right-hand side gathers from the whole state: one slab (world = 1) only");
+  // (below 32 components the reference's norm is a plain sequential sum, LinearAlgebra.generic_norm2; such
+  // systems belong to the ensemble path, which restates it)
+  if (n_local < 2 * mi.H || n_global < 32 || n_local > n_global || n_local < 1)
     return set_err(ODE_B200_E_INVALID, "slab too small: n_local %lld (needs >= %d), n_global %lld (needs >= 32)",
                    (long long)n_local, 2 * mi.H, (long long)n_global);
   if (o->points != ODE_B200_POINTS_ALL && o->points != ODE_B200_POINTS_FINAL && o->points != ODE_B200_POINTS_SPECIFIED)
@@ -424,8 +489,10 @@ int ode_b200_slab_create(const ode_b200_opts* o, int64_t n_local, int64_t n_glob
   s->mi = mi;
   s->stream = (cudaStream_t)stream;
   s->tiles = (n_local + mi.VAL - 1) / mi.VAL;
-  s->grid = persistent_grid(mi.attempt, o->device, s->tiles);
-  s->grid_literal = persistent_grid(mi.attempt_literal, o->device, s->tiles);
+  if (!mi.field) {
+    s->grid = persistent_grid(mi.attempt, o->device, s->tiles);
+    s->grid_literal = persistent_grid(mi.attempt_literal, o->device, s->tiles);
+  }
   memset(&s->sc, 0, sizeof(s->sc));
   s->np = np;
   for (int q = 0; q < np; q++) s->sc.p[q] = params[q];
@@ -443,6 +510,13 @@ int ode_b200_slab_create(const ode_b200_opts* o, int64_t n_local, int64_t n_glob
   for (int i = 0; i < 2 && ok; i++) {
     ok = ok && cudaMalloc(&s->Y[i], padded) == cudaSuccess;
     ok = ok && cudaMalloc(&s->K[i], padded) == cudaSuccess;
+  }
+  if (mi.field) {  // middle stages k_2 .. k_{S-1} and the two stage-argument buffers
+    long long fb = (n_local + FIELD_THREADS - 1) / FIELD_THREADS;
+    s->field_grid = (int)(fb < (long long)sms * 8 ? (fb < 1 ? 1 : fb) : (long long)sms * 8);
+    s->grid = s->field_grid;  // the error partials are written by the last stage kernel
+    for (int q = 1; q <= mi.S - 2 && ok; q++) ok = ok && cudaMalloc(&s->KS[q], padded) == cudaSuccess;
+    for (int q = 0; q < 2 && ok; q++) ok = ok && cudaMalloc(&s->T[q], padded) == cudaSuccess;
   }
   ok = ok && cudaMalloc(&s->ctl, sizeof(LargeCtl)) == cudaSuccess;
   ok = ok && cudaMalloc(&s->part, (size_t)s->grid * 4 * sizeof(double)) == cudaSuccess;
@@ -618,6 +692,29 @@ int ode_b200_slab_init_phase(ode_b200_slab* s, int phase, double* xsend, const d
   if (rc) return rc;
   const int H = s->mi.H;
   cudaStream_t st = s->stream;
+  if (s->mi.field && phase >= 0 && phase <= 2) {  // gather right-hand side: no ghost cells, x1 is materialised
+    const double* y = s->Y[0];
+    double* f0 = s->K[0];
+    const LargeCtl* c = s->ctl;
+    if (phase == 1) {
+      void* a[] = {(void*)&y, (void*)&f0, (void*)&c, (void*)&s->ipart, (void*)&s->n, (void*)&s->sc};
+      ODEB200_CUDA(cudaLaunchKernel(s->mi.hinit_f0, dim3(s->init_blocks), dim3(256), a, 0, st));
+      reduce_max_kernel<<<1, 32, 0, st>>>(s->ipart, s->init_blocks, 2, xsend);
+      note_launch();
+      note_launch();
+    } else if (phase == 2) {
+      hinit_control_kernel<<<1, 32, 0, st>>>(s->ctl, xrecv, s->world, 0, s->mi.order);
+      field_hinit_x1_kernel<<<s->init_blocks, 256, 0, st>>>(y, f0, c, s->T[0], s->n);
+      const double* x1 = s->T[0];
+      const double* f0c = f0;
+      void* a[] = {(void*)&x1, (void*)&f0c, (void*)&c, (void*)&s->ipart, (void*)&s->n, (void*)&s->sc};
+      ODEB200_CUDA(cudaLaunchKernel(s->mi.hinit_f1, dim3(s->init_blocks), dim3(256), a, 0, st));
+      reduce_max_kernel<<<1, 32, 0, st>>>(s->ipart, s->init_blocks, 1, xsend);
+      for (int i = 0; i < 4; i++) note_launch();
+    }
+    ODEB200_CUDA(cudaGetLastError());
+    return 0;
+  }
   switch (phase) {
     case 0:
       pack_edges_kernel<<<1, 32, 0, st>>>(s->Y[0], xsend, s->n, H, 0);
@@ -665,6 +762,34 @@ int ode_b200_slab_init_phase(ode_b200_slab* s, int phase, double* xsend, const d
 int ode_b200_slab_attempt(ode_b200_slab* s, double* xsend) {
   int rc = slab_check(s);
   if (rc) return rc;
+  if (s->mi.field) {  // one kernel per stage (field.cuh)
+    FieldArgs F;
+    memset(&F, 0, sizeof(F));
+    for (int q = 0; q < 2; q++) {
+      F.Y[q] = s->Y[q];
+      F.K[q] = s->K[q];
+      F.T[q] = s->T[q];
+    }
+    for (int q = 0; q < FIELD_MAX_STAGES; q++) F.KS[q] = s->KS[q];
+    F.ctl = s->ctl;
+    F.part = s->part;
+    F.xsend = xsend;
+    F.n = s->n;
+    F.sc = s->sc;
+    void* kargs[] = {(void*)&F};
+    const dim3 g((unsigned)s->field_grid), b(FIELD_THREADS);
+    ODEB200_CUDA(cudaLaunchKernel(s->mi.f_first, g, b, kargs, 0, s->stream));
+    note_launch();
+    for (int st = 2; st <= s->mi.S; st++) {
+      ODEB200_CUDA(cudaLaunchKernel(s->mi.f_stage[st], g, b, kargs, 0, s->stream));
+      note_launch();
+    }
+    if (!s->mi.fsal) {
+      ODEB200_CUDA(cudaLaunchKernel(s->mi.f_f1, g, b, kargs, 0, s->stream));
+      note_launch();
+    }
+    return 0;
+  }
   LargeArgs A;
   A.Y[0] = s->Y[0];
   A.Y[1] = s->Y[1];
@@ -750,6 +875,10 @@ void ode_b200_slab_free(ode_b200_slab* s) {
     if (s->Y[i]) cudaFree(s->Y[i]);
     if (s->K[i]) cudaFree(s->K[i]);
   }
+  for (int q = 0; q < FIELD_MAX_STAGES; q++)
+    if (s->KS[q]) cudaFree(s->KS[q]);
+  for (int q = 0; q < 2; q++)
+    if (s->T[q]) cudaFree(s->T[q]);
   if (s->ctl) cudaFree(s->ctl);
   if (s->part) cudaFree(s->part);
   if (s->ipart) cudaFree(s->ipart);
@@ -826,7 +955,6 @@ static int solve_large_impl(const ode_b200_opts* o, int64_t n, const double* y0,
     cc.rhs = o->rhs;
     cc.n = n;
   } else {
-    if (!params || o->n_params < 2) return set_err(ODE_B200_E_INVALID, "the stencil RHS needs two params");
     if (o->points != ODE_B200_POINTS_ALL && o->points != ODE_B200_POINTS_FINAL && o->points != ODE_B200_POINTS_SPECIFIED)
       return set_err(ODE_B200_E_POINTS, "Unrecognized option points==%d", o->points);
     cc.s->trace = nullptr;

@@ -137,6 +137,114 @@ __device__ __forceinline__ void load_chunk(const double* a, long long q, long lo
   }
 }
 
+// ---- error partials of one attempt: per-thread double-double sums -> one value per CTA -> last CTA -> xsend ----
+// Every thread brings its running sum of squared scaled errors (double-double), max |e| and NaN flag; warp
+// shuffles and shared memory reduce them per CTA, and the last CTA to arrive reduces the per-CTA partials in a
+// fixed order, so the result does not depend on scheduling.  Shared by the fused stencil kernel and the
+// stage-per-kernel field path (field.cuh).
+template <int T>
+__device__ __forceinline__ void reduce_error_partials(dm_dd acc, double mx, bool anynan, double* part, LargeCtl* ctl,
+                                                      double* xsend) {
+  __shared__ double red[T / 32][4];
+  __shared__ bool is_last;
+  const int tid = threadIdx.x;
+  // ---- one block reduction per CTA: warp shuffles, then shared memory --------------
+  double nanf = anynan ? 1.0 : 0.0;
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    dm_dd other;
+    other.hi = __shfl_down_sync(0xffffffffu, acc.hi, o);
+    other.lo = __shfl_down_sync(0xffffffffu, acc.lo, o);
+    acc = dd_add(acc, other);
+    mx = normInf_step(mx, __shfl_down_sync(0xffffffffu, mx, o));
+    nanf = fmax(nanf, __shfl_down_sync(0xffffffffu, nanf, o));
+  }
+  __syncthreads();  // all exchanges of the tile loop are complete before `red` is reused
+  if ((tid & 31) == 0) {
+    red[tid >> 5][0] = acc.hi;
+    red[tid >> 5][1] = acc.lo;
+    red[tid >> 5][2] = mx;
+    red[tid >> 5][3] = nanf;
+  }
+  __syncthreads();
+  if (tid == 0) {
+    dm_dd tot;
+    tot.hi = red[0][0];
+    tot.lo = red[0][1];
+    double m = red[0][2], nf = red[0][3];
+    for (int w = 1; w < T / 32; w++) {
+      dm_dd o;
+      o.hi = red[w][0];
+      o.lo = red[w][1];
+      tot = dd_add(tot, o);
+      m = normInf_step(m, red[w][2]);
+      nf = fmax(nf, red[w][3]);
+    }
+    double* pp = part + (long long)blockIdx.x * 4;
+    pp[0] = tot.hi;
+    pp[1] = tot.lo;
+    pp[2] = m;
+    pp[3] = nf;
+    __threadfence();
+    unsigned int done = atomicAdd(&ctl->blocks_done, 1u);
+    is_last = (done == (unsigned int)(gridDim.x - 1));
+  }
+  __syncthreads();
+  if (!is_last) return;
+  // ---- last CTA: reduce the per-CTA partials in a fixed order -> xsend[0..3] ----------
+  __threadfence();
+  dm_dd a2;
+  a2.hi = 0.0;
+  a2.lo = 0.0;
+  double m2 = 0.0, n2 = 0.0;
+  for (int b = tid; b < (int)gridDim.x; b += T) {
+    const double2 lo2 = __ldcg(reinterpret_cast<const double2*>(part + (long long)b * 4));
+    const double2 hi2 = __ldcg(reinterpret_cast<const double2*>(part + (long long)b * 4 + 2));
+    dm_dd o;
+    o.hi = lo2.x;
+    o.lo = lo2.y;
+    a2 = dd_add(a2, o);
+    m2 = normInf_step(m2, hi2.x);
+    n2 = fmax(n2, hi2.y);
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    dm_dd other;
+    other.hi = __shfl_down_sync(0xffffffffu, a2.hi, o);
+    other.lo = __shfl_down_sync(0xffffffffu, a2.lo, o);
+    a2 = dd_add(a2, other);
+    m2 = normInf_step(m2, __shfl_down_sync(0xffffffffu, m2, o));
+    n2 = fmax(n2, __shfl_down_sync(0xffffffffu, n2, o));
+  }
+  __syncthreads();
+  if ((tid & 31) == 0) {
+    red[tid >> 5][0] = a2.hi;
+    red[tid >> 5][1] = a2.lo;
+    red[tid >> 5][2] = m2;
+    red[tid >> 5][3] = n2;
+  }
+  __syncthreads();
+  if (tid == 0) {
+    dm_dd tot;
+    tot.hi = red[0][0];
+    tot.lo = red[0][1];
+    double m = red[0][2], nf = red[0][3];
+    for (int w = 1; w < T / 32; w++) {
+      dm_dd o;
+      o.hi = red[w][0];
+      o.lo = red[w][1];
+      tot = dd_add(tot, o);
+      m = normInf_step(m, red[w][2]);
+      nf = fmax(nf, red[w][3]);
+    }
+    xsend[XS_HI] = tot.hi;
+    xsend[XS_LO] = tot.lo;
+    xsend[XS_MAX] = m;
+    xsend[XS_NAN] = nf;
+    ctl->blocks_done = 0;
+  }
+}
+
 // One RHS sweep over a thread's P consecutive points: the R edge values per side cross threads through one
 // shared-memory line (written here, read after the barrier); the first / last thread of the tile repeats its
 // own edge value (those points are inside the ghost zone and already invalid).  g0 = global grid index of v[0].
@@ -204,9 +312,6 @@ __global__ void __launch_bounds__(LARGE_THREADS) large_attempt_kernel(
 
   constexpr int R = Geo::R;
   __shared__ double eL[2][T * R], eR[2][T * R];
-  __shared__ double red[T / 32][4];
-  __shared__ bool is_last;
-
   LargeCtl* ctl = A.ctl;
   if (ctl->done) return;
   if (LITERAL != (ctl->redo != 0)) return;
@@ -361,101 +466,7 @@ __global__ void __launch_bounds__(LARGE_THREADS) large_attempt_kernel(
     }
   }
 
-  // ---- one block reduction per CTA: warp shuffles, then shared memory --------------
-  double nanf = anynan ? 1.0 : 0.0;
-#pragma unroll
-  for (int o = 16; o > 0; o >>= 1) {
-    dm_dd other;
-    other.hi = __shfl_down_sync(0xffffffffu, acc.hi, o);
-    other.lo = __shfl_down_sync(0xffffffffu, acc.lo, o);
-    acc = dd_add(acc, other);
-    mx = normInf_step(mx, __shfl_down_sync(0xffffffffu, mx, o));
-    nanf = fmax(nanf, __shfl_down_sync(0xffffffffu, nanf, o));
-  }
-  __syncthreads();  // all exchanges of the tile loop are complete before `red` is reused
-  if ((tid & 31) == 0) {
-    red[tid >> 5][0] = acc.hi;
-    red[tid >> 5][1] = acc.lo;
-    red[tid >> 5][2] = mx;
-    red[tid >> 5][3] = nanf;
-  }
-  __syncthreads();
-  if (tid == 0) {
-    dm_dd tot;
-    tot.hi = red[0][0];
-    tot.lo = red[0][1];
-    double m = red[0][2], nf = red[0][3];
-    for (int w = 1; w < T / 32; w++) {
-      dm_dd o;
-      o.hi = red[w][0];
-      o.lo = red[w][1];
-      tot = dd_add(tot, o);
-      m = normInf_step(m, red[w][2]);
-      nf = fmax(nf, red[w][3]);
-    }
-    double* pp = A.part + (long long)blockIdx.x * 4;
-    pp[0] = tot.hi;
-    pp[1] = tot.lo;
-    pp[2] = m;
-    pp[3] = nf;
-    __threadfence();
-    unsigned int done = atomicAdd(&ctl->blocks_done, 1u);
-    is_last = (done == (unsigned int)(gridDim.x - 1));
-  }
-  __syncthreads();
-  if (!is_last) return;
-  // ---- last CTA: reduce the per-CTA partials in a fixed order -> xsend[0..3] ----------
-  __threadfence();
-  dm_dd a2;
-  a2.hi = 0.0;
-  a2.lo = 0.0;
-  double m2 = 0.0, n2 = 0.0;
-  for (int b = tid; b < (int)gridDim.x; b += T) {
-    const double2 lo2 = __ldcg(reinterpret_cast<const double2*>(A.part + (long long)b * 4));
-    const double2 hi2 = __ldcg(reinterpret_cast<const double2*>(A.part + (long long)b * 4 + 2));
-    dm_dd o;
-    o.hi = lo2.x;
-    o.lo = lo2.y;
-    a2 = dd_add(a2, o);
-    m2 = normInf_step(m2, hi2.x);
-    n2 = fmax(n2, hi2.y);
-  }
-#pragma unroll
-  for (int o = 16; o > 0; o >>= 1) {
-    dm_dd other;
-    other.hi = __shfl_down_sync(0xffffffffu, a2.hi, o);
-    other.lo = __shfl_down_sync(0xffffffffu, a2.lo, o);
-    a2 = dd_add(a2, other);
-    m2 = normInf_step(m2, __shfl_down_sync(0xffffffffu, m2, o));
-    n2 = fmax(n2, __shfl_down_sync(0xffffffffu, n2, o));
-  }
-  __syncthreads();
-  if ((tid & 31) == 0) {
-    red[tid >> 5][0] = a2.hi;
-    red[tid >> 5][1] = a2.lo;
-    red[tid >> 5][2] = m2;
-    red[tid >> 5][3] = n2;
-  }
-  __syncthreads();
-  if (tid == 0) {
-    dm_dd tot;
-    tot.hi = red[0][0];
-    tot.lo = red[0][1];
-    double m = red[0][2], nf = red[0][3];
-    for (int w = 1; w < T / 32; w++) {
-      dm_dd o;
-      o.hi = red[w][0];
-      o.lo = red[w][1];
-      tot = dd_add(tot, o);
-      m = normInf_step(m, red[w][2]);
-      nf = fmax(nf, red[w][3]);
-    }
-    A.xsend[XS_HI] = tot.hi;
-    A.xsend[XS_LO] = tot.lo;
-    A.xsend[XS_MAX] = m;
-    A.xsend[XS_NAN] = nf;
-    ctl->blocks_done = 0;
-  }
+  reduce_error_partials<T>(acc, mx, anynan, A.part, ctl, A.xsend);
 }
 
 // ---- hinit (src/ODE.jl:85-112) sweeps over the slab ---------------------------------------

@@ -28,6 +28,7 @@ struct UserRhs {
   int dof, np;
 };
 static std::vector<UserRhs> g_user;
+static std::vector<UserRhs> g_fields;    // eval_body = body of rhs(i, n, y, p, t); large-system gather regime
 static std::vector<UserRhs> g_stencils;  // eval_body = body of point(um, u, up, p0, p1)
 static std::map<std::string, const void*> g_kernels;  // key -> cudaKernel_t
 static std::mutex g_mu;
@@ -312,6 +313,79 @@ bool user_stencil_kernels(int rhs, int method, const void** attempt, const void*
   return true;
 }
 
+
+bool user_field_info(int rhs, int* np) {
+  std::lock_guard<std::mutex> lk(g_mu);
+  int i = rhs - ODE_B200_FIELD_USER_BASE;
+  if (i < 0 || i >= (int)g_fields.size()) return false;
+  if (np) *np = g_fields[i].np;
+  return true;
+}
+
+// Kernels of the stage-per-kernel path (field.cuh) for a registered field functor and one tableau:
+// out[0] = field_first_kernel, out[1 .. S-1] = field_stage_kernel<s = 2 .. S>, then field_f1_kernel,
+// field_hinit_f0_kernel, field_hinit_f1_kernel (n_stages = S).
+bool user_field_kernels(int rhs, int method, int n_stages, const void** out) {
+  UserRhs u;
+  {
+    std::lock_guard<std::mutex> lk(g_mu);
+    int i = rhs - ODE_B200_FIELD_USER_BASE;
+    if (i < 0 || i >= (int)g_fields.size()) {
+      set_err(ODE_B200_E_INVALID, "unknown user field %d", rhs);
+      return false;
+    }
+    u = g_fields[i];
+  }
+  const char* tab = tab_name(method);
+  if (!tab || method < ODE_B200_M_RK21 || method > ODE_B200_M_FEH78) {
+    set_err(ODE_B200_E_NOT_ADAPTIVE, "Can only use this solver with an adaptive RK Butcher table");
+    return false;
+  }
+  const int nk = n_stages + 3;
+  int dev = 0;
+  cudaGetDevice(&dev);
+  char keyb[256];
+  snprintf(keyb, sizeof(keyb), "%d|%d|field|%s", dev, rhs, tab);
+  const std::string key(keyb);
+  {
+    std::lock_guard<std::mutex> lk(g_mu);
+    auto it = g_kernels.find(key + "|0");
+    if (it != g_kernels.end()) {
+      for (int k = 0; k < nk; k++) out[k] = g_kernels[key + "|" + std::to_string(k)];
+      return true;
+    }
+  }
+  std::vector<std::string> names;
+  char e[256];
+  snprintf(e, sizeof(e), "odeb200::field_first_kernel<%s>", tab);
+  names.push_back(e);
+  for (int s = 2; s <= n_stages; s++) {
+    snprintf(e, sizeof(e), "odeb200::field_stage_kernel<%s, odeb200::FieldUser, %d>", tab, s);
+    names.push_back(e);
+  }
+  names.push_back("odeb200::field_f1_kernel<odeb200::FieldUser>");
+  names.push_back("odeb200::field_hinit_f0_kernel<odeb200::FieldUser>");
+  names.push_back("odeb200::field_hinit_f1_kernel<odeb200::FieldUser>");
+  char decl[512];
+  snprintf(decl, sizeof(decl),
+           "  static constexpr int NP = %d, ID = 0;\n"
+           "  __device__ __forceinline__ static double rhs(long long i, long long n, const double* __restrict__ y, "
+           "const double (&p)[8], double t) {\n    (void)i; (void)n; (void)y; (void)p; (void)t;\n",
+           u.np);
+  const std::string src = "#include \"field.cuh\"\nnamespace odeb200 {\nstruct FieldUser {\n" + std::string(decl) + u.eval_body +
+                          "\n  }\n};\n}  // namespace odeb200\n";
+  std::vector<const char*> exprs;
+  for (const std::string& nme : names) exprs.push_back(nme.c_str());
+  std::vector<const void*> got(names.size(), nullptr);
+  if (!compile_and_load(u.name, src, exprs.data(), (int)exprs.size(), got.data())) return false;
+  std::lock_guard<std::mutex> lk(g_mu);
+  for (int k = 0; k < nk; k++) {
+    g_kernels[key + "|" + std::to_string(k)] = got[k];
+    out[k] = got[k];
+  }
+  return true;
+}
+
 }  // namespace odeb200
 
 using namespace odeb200;
@@ -344,4 +418,18 @@ extern "C" int ode_b200_register_stencil(const char* name, int32_t radius, int32
   u.np = n_params;
   g_stencils.push_back(u);
   return ODE_B200_STENCIL_USER_BASE + (int)g_stencils.size() - 1;
+}
+
+extern "C" int ode_b200_register_field(const char* name, int32_t n_params, const char* rhs_body) {
+  if (!name || !rhs_body || n_params < 0 || n_params > ODE_B200_STENCIL_MAX_NP)
+    return set_err(ODE_B200_E_INVALID, "register_field: need a name, the body of rhs(), 0 <= n_params <= %d",
+                   ODE_B200_STENCIL_MAX_NP);
+  std::lock_guard<std::mutex> lk(g_mu);
+  UserRhs u;
+  u.name = name;
+  u.eval_body = rhs_body;
+  u.dof = 0;
+  u.np = n_params;
+  g_fields.push_back(u);
+  return ODE_B200_FIELD_USER_BASE + (int)g_fields.size() - 1;
 }

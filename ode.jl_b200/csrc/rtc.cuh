@@ -8,4 +8,7 @@ bool user_stencil_info(int rhs, int* radius, int* np);
 // kernels of the large-system path for a registered stencil; false + last_error on failure
 bool user_stencil_kernels(int rhs, int method, const void** attempt, const void** attempt_literal, const void** hinit_f0,
                           const void** hinit_f1);
+// registered general large-system right-hand sides (field.cuh): parameter count; kernels for one tableau
+bool user_field_info(int rhs, int* np);
+bool user_field_kernels(int rhs, int method, int n_stages, const void** out);
 }  // namespace odeb200

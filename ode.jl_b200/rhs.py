@@ -12,8 +12,10 @@ import numpy as np
 
 from ._lib import RHS
 
-_DOF = dict(linear=1, const=1, timelin=1, rotation=2, lorenz=3, vdp=2, robertson=3, kepler=4, reaction_diffusion=0)
-_NP = dict(linear=1, const=1, timelin=1, rotation=0, lorenz=3, vdp=1, robertson=3, kepler=0, reaction_diffusion=2)
+_DOF = dict(linear=1, const=1, timelin=1, rotation=2, lorenz=3, vdp=2, robertson=3, kepler=4, reaction_diffusion=0,
+            reaction_diffusion_field=0)
+_NP = dict(linear=1, const=1, timelin=1, rotation=0, lorenz=3, vdp=1, robertson=3, kepler=0, reaction_diffusion=2,
+           reaction_diffusion_field=2)
 
 
 def register_rhs(name, dof, n_params, eval_body, jac_body=None, host=None, params=()):
@@ -55,6 +57,27 @@ def register_stencil(name, point_body, host=None, params=(0.0, 0.0), radius=1):
     return tok
 
 
+def register_field(name, rhs_body, host=None, params=()):
+    """Register a GENERAL right-hand side for one large system (dof = N) from CUDA C++ source: F_i(t, y) may read
+    any component of y (non-local couplings, networks, N-body sums, flattened 2-D grids).
+
+    rhs_body : body of  double rhs(long long i, long long n, const double* y, const double (&p)[8], double t)
+               returning dy_i/dt
+    host     : optional python callable host(t, y, p) -> array, for DeviceRHS.__call__
+    params   : default parameter values (at most 8)
+    Runs one kernel per Runge-Kutta stage on one GPU (`solve_large`, or the odeXX front-ends on a dof = N state)."""
+    from ._lib import lib, check
+    rid = lib().ode_b200_register_field(name.encode(), len(params), rhs_body.encode())
+    if rid < 0:
+        check(rid)
+    tok = DeviceRHS.__new__(DeviceRHS)
+    tok.name, tok.id, tok.dof, tok.n_params, tok.params = name, rid, 0, len(params), tuple(params)
+    tok._host = host
+    tok.is_stencil = True  # routed to the large-system entry points
+    tok.is_field = True
+    return tok
+
+
 class DeviceRHS:
     """`DeviceRHS("lorenz", 10.0, 28.0, 8/3)`; calling it evaluates F(t, y) on the host."""
 
@@ -69,7 +92,7 @@ class DeviceRHS:
         self.dof = _DOF[name]
         self.n_params = _NP[name]
         self.params = params
-        self.is_stencil = name == "reaction_diffusion"
+        self.is_stencil = name in ("reaction_diffusion", "reaction_diffusion_field")  # a dof = N large-system RHS
 
     def with_params(self, p):
         if p is None:
@@ -94,6 +117,10 @@ class DeviceRHS:
         return a
 
     def __call__(self, t, y):
+        if self.id >= 3000:
+            if getattr(self, "_host", None) is None:
+                raise TypeError("run-time field %r was registered without a host evaluator" % self.name)
+            return np.asarray(self._host(t, np.asarray(y, dtype=np.float64), list(self.params)), dtype=np.float64)
         if self.id >= 2000:
             if getattr(self, "_host", None) is None:
                 raise TypeError("run-time stencil %r was registered without a host evaluator" % self.name)

@@ -305,3 +305,62 @@ def test_large_points_all_through_the_front_end(method):
     t3, y3 = getattr(m, method)(F, y0, ts, points="specified")
     ref3 = O.solve(method, "reaction_diffusion", y0, ts, RD, points="specified")
     assert np.array_equal(t3, ref3.t) and np.array_equal(y3, ref3.y)
+
+
+# ---- general gather right-hand sides ("fields"): one kernel per stage (csrc/field.cuh) -------------------------
+@pytest.mark.parametrize("method", ["ode21", "ode23", "ode45_fe", "ode45", "ode78"])
+def test_field_path_equals_fused_stencil_path_and_oracle(method):
+    """The built-in reaction_diffusion_field is the reaction-diffusion system written as a gather over the global
+    state: the stage-per-kernel path must give the fused kernel's bits, and the oracle's."""
+    n = 5000
+    y0 = u0(n)
+    ts = [0.0, 0.7, 3.0]
+    a = m.solve_large(method, m.DeviceRHS("reaction_diffusion_field", *RD), y0, [0.0, 3.0], trace=True)
+    b = m.solve_large(method, m.DeviceRHS("reaction_diffusion", *RD), y0, [0.0, 3.0], trace=True)
+    assert np.array_equal(a["y"], b["y"]) and np.array_equal(a["trace"], b["trace"])
+    assert (a["n_accept"], a["n_reject"], a["n_rhs"]) == (b["n_accept"], b["n_reject"], b["n_rhs"])
+    for points in ("specified", "all"):
+        t, y, st = getattr(m, method).stats(m.DeviceRHS("reaction_diffusion_field", *RD), y0, ts, points=points)
+        o = O.solve(method, "reaction_diffusion", y0, ts, RD, points=points)
+        assert np.array_equal(t, o.t) and np.array_equal(y, o.y), points
+        assert (st["n_accept"], st["n_reject"], st["n_rhs"]) == (o.n_accept, o.n_reject, o.n_rhs)
+
+
+NONLOCAL_BODY = """
+const long long j = (i * 7 + 3) % n;            // a long-range partner
+const double mirror = y[n - 1 - i];
+return (p[0] * (y[j] - y[i]) + p[1] * (mirror * y[i])) - (p[2] * t) * ((y[i] * y[i]) * y[i]);
+"""
+
+
+def nonlocal_host(t, y, p):
+    n = len(y)
+    return [(p[0] * (y[(i * 7 + 3) % n] - y[i]) + p[1] * (y[n - 1 - i] * y[i])) - (p[2] * t) * ((y[i] * y[i]) * y[i])
+            for i in range(n)]
+
+
+def test_user_field_nonlocal_coupling_matches_oracle():
+    F = m.register_field("nonlocal", NONLOCAL_BODY, host=nonlocal_host, params=(0.8, 0.3, 0.5))
+    n = 400
+    y0 = 0.5 + 0.4 * np.sin(2 * np.pi * 3 * np.arange(n) / n)
+    ts = [0.0, 0.4, 1.5]
+    for method, points in (("ode45", "specified"), ("ode23", "all"), ("ode78", "specified"), ("ode45_fe", "all")):
+        t, y, st = getattr(m, method).stats(F, y0, ts, points=points)
+        o = O.solve_user(method, nonlocal_host, y0, ts, [0.8, 0.3, 0.5], points=points)
+        assert np.array_equal(t, o.t) and np.array_equal(y, o.y), (method, points)
+        assert (st["n_accept"], st["n_reject"], st["n_rhs"]) == (o.n_accept, o.n_reject, o.n_rhs)
+    # below 32 components the ensemble path (register_rhs) is the one that restates the reference's small-vector norm
+    with pytest.raises(m.OdeB200Error):
+        m.ode45(F, y0[:3], [0.0, 1.0])
+    assert np.allclose(F(0.3, y0[:5]), nonlocal_host(0.3, list(y0[:5]), [0.8, 0.3, 0.5]))
+
+
+def test_field_overflowing_first_step_recovers_like_the_reference():
+    n = 3000
+    y0 = u0(n)
+    kw = dict(initstep=1e7)
+    got = m.solve_large("ode45", m.DeviceRHS("reaction_diffusion_field", *RD), y0, [0.0, 1.0], trace=True, **kw)
+    ref = O.solve("ode45", "reaction_diffusion", y0, [0.0, 1.0], RD, trace=True, points="final", **kw)
+    assert ref.status == 0 and np.any(ref.trace[:, 2] == 10.0)
+    assert got["status"] == 0 and (got["n_accept"], got["n_reject"], got["n_rhs"]) == (ref.n_accept, ref.n_reject, ref.n_rhs)
+    assert np.array_equal(got["trace"], ref.trace, equal_nan=True) and np.array_equal(got["y"], ref.y[-1])

@@ -108,6 +108,7 @@ def lib():
     L.ode_b200_slab_set_output_all.argtypes = [C.c_void_p, dp, C.c_int32, C.c_void_p, C.c_void_p, C.c_int64]
     L.ode_b200_solve_large_all.argtypes = [C.POINTER(Opts), C.c_int64, dp, dp, dp, C.c_int32, C.c_int64, dp, dp, lp,
                                            C.POINTER(LargeStats), dp, C.c_int64, lp]
+    L.ode_b200_solve_large_fixed.argtypes = [C.POINTER(Opts), C.c_int64, dp, dp, dp, C.c_int32, dp, dp, C.POINTER(LargeStats)]
     L.ode_b200_trim.restype = None
     L.ode_b200_register_stencil.argtypes = [C.c_char_p, C.c_int32, C.c_int32, C.c_char_p]
     L.ode_b200_register_field.argtypes = [C.c_char_p, C.c_int32, C.c_char_p]

@@ -156,6 +156,73 @@ __global__ void __launch_bounds__(FIELD_THREADS) field_f1_kernel(const __grid_co
     kn[i] = Rhs::rhs(i, A.n, ytrial, A.sc.p, tt);
 }
 
+// ---- fixed-step explicit Runge-Kutta on a dof = N state (oderk_fixed, src/runge_kutta.jl:176-212) ---------------
+// A stencil functor seen as a field functor (periodic gather of its window), so that the stage-per-kernel
+// drivers below also serve registered stencils.
+template <class St>
+struct FieldFromStencil {
+  static constexpr int NP = St::NP, ID = St::ID;
+  __device__ __forceinline__ static double rhs(long long i, long long n, const double* __restrict__ y, const double (&p)[8],
+                                               double t) {
+    constexpr int R = St::RADIUS;
+    double w[2 * R + 1];
+#pragma unroll
+    for (int k = 0; k < 2 * R + 1; k++) {
+      long long j = i + (k - R);
+      if (j < 0) j += n;
+      else if (j >= n) j -= n;
+      w[k] = y[j];
+    }
+    return St::point(w, p, t, i, n);
+  }
+};
+
+struct FixedArgs {
+  const double* y;               // state at tspan[i]
+  double* ynew;                  // state at tspan[i+1]
+  double* KS[FIELD_MAX_STAGES];  // KS[s] = k_{s+1}, s = 0 .. S-2
+  double* T[2];                  // stage-argument ping-pong
+  long long n;
+  double t, dt;                  // tspan[i], tspan[i+1] - tspan[i] (:202)
+  StencilCtx sc;
+};
+
+// Stage s (1-based, 1 <= s <= S): k_s = F(t + c_s*dt, ytmp_s) -- every stage calls F, the first included (:205) --
+// then ytmp_{s+1} (every coefficient multiplied, zeros too, like the reference), or for s = S the update
+// ys[i+1] = y + sum (dt*b[s])*k_s (:207).
+template <class Tab, class Rhs, int s>
+__global__ void __launch_bounds__(FIELD_THREADS) field_fixed_stage_kernel(const __grid_constant__ FixedArgs A) {
+  constexpr int S = Tab::S;
+  const double dt = A.dt;
+  const double* __restrict__ tin = (s == 1) ? A.y : A.T[s & 1];
+  double* __restrict__ tout = A.T[(s + 1) & 1];
+  constexpr double c = Tab::c(s - 1);
+  const double tt = A.t + c * dt;  // :456
+  for (long long i = (long long)blockIdx.x * FIELD_THREADS + threadIdx.x; i < A.n; i += (long long)gridDim.x * FIELD_THREADS) {
+    const double ks = Rhs::rhs(i, A.n, tin, A.sc.p, tt);
+    if constexpr (s < S) {
+      A.KS[s - 1][i] = ks;
+      double v = A.y[i];
+      static_for<s>([&](auto J) {
+        constexpr int ss = decltype(J)::value;
+        constexpr double a = Tab::a(s, ss);
+        const double kv = (ss == s - 1) ? ks : A.KS[ss][i];
+        v = v + (dt * kv) * a;  // (dt*k)*a :454
+      });
+      tout[i] = v;
+    } else {
+      double yn = A.y[i];  // :203
+      static_for<S>([&](auto J) {
+        constexpr int ss = decltype(J)::value;
+        constexpr double b = Tab::b(0, ss);
+        const double kv = (ss == S - 1) ? ks : A.KS[ss][i];
+        yn = yn + (dt * b) * kv;  // :207
+      });
+      A.ynew[i] = yn;
+    }
+  }
+}
+
 // ---- hinit (src/ODE.jl:85-112) ---------------------------------------------------------------------
 // f0 = F(t0, y) -> K[0]; partial max|y|, max|f0|
 template <class Rhs>

@@ -368,6 +368,38 @@ static bool pick_method(int method, int radius, MethodInfo* out) {
   }
 }
 
+
+template <class Tab, class Rhs, int s>
+struct FillFixedStages {
+  static void run(const void** k) {
+    k[s - 1] = (const void*)field_fixed_stage_kernel<Tab, Rhs, s>;
+    FillFixedStages<Tab, Rhs, s - 1>::run(k);
+  }
+};
+template <class Tab, class Rhs>
+struct FillFixedStages<Tab, Rhs, 0> {
+  static void run(const void**) {}
+};
+// stage kernels of a fixed-step tableau for the built-in reaction-diffusion system; returns the stage count
+static int builtin_fixed_kernels(int method, const void** k) {
+  switch (method) {
+    case ODE_B200_M_FEULER: FillFixedStages<TabFEuler, FieldReactionDiffusion, TabFEuler::S>::run(k); return TabFEuler::S;
+    case ODE_B200_M_MIDPOINT: FillFixedStages<TabMidpoint, FieldReactionDiffusion, TabMidpoint::S>::run(k); return TabMidpoint::S;
+    case ODE_B200_M_HEUN: FillFixedStages<TabHeun, FieldReactionDiffusion, TabHeun::S>::run(k); return TabHeun::S;
+    case ODE_B200_M_RK4: FillFixedStages<TabRK4, FieldReactionDiffusion, TabRK4::S>::run(k); return TabRK4::S;
+    default: return 0;
+  }
+}
+static int fixed_stage_count(int method) {
+  switch (method) {
+    case ODE_B200_M_FEULER: return TabFEuler::S;
+    case ODE_B200_M_MIDPOINT: return TabMidpoint::S;
+    case ODE_B200_M_HEUN: return TabHeun::S;
+    case ODE_B200_M_RK4: return TabRK4::S;
+    default: return 0;
+  }
+}
+
 }  // namespace odeb200
 
 using namespace odeb200;
@@ -890,6 +922,113 @@ static int solve_large_impl(const ode_b200_opts* o, int64_t n, const double* y0,
                             const double* tspan, int32_t n_tspan, double* y_out, double* pts_out,
                             ode_b200_large_stats* stats, double* trace, int64_t trace_cap, int64_t* trace_n,
                             double* all_t = nullptr, int64_t all_cap = 0, int64_t* all_rows = nullptr);
+
+// oderk_fixed (src/runge_kutta.jl:176-212) on a dof = N state: ode1 / ode2_midpoint / ode2_heun / ode4 with a
+// stencil or field right-hand side, one kernel per stage per step on the tspan grid.
+int ode_b200_solve_large_fixed(const ode_b200_opts* o, int64_t n, const double* y0, const double* params,
+                               const double* tspan, int32_t n_tspan, double* pts_y, double* y_final,
+                               ode_b200_large_stats* stats) {
+  if (!o || !y0 || !tspan) return set_err(ODE_B200_E_INVALID, "null argument");
+  if (n_tspan < 2) return set_err(ODE_B200_E_INVALID, "tspan needs at least 2 entries");
+  int cnt = 0;
+  if (cudaGetDeviceCount(&cnt) != cudaSuccess || cnt <= 0) {
+    cudaGetLastError();
+    return set_err(ODE_B200_E_NO_DEVICE, "no CUDA device available; libode_b200 has no CPU fallback");
+  }
+  if (o->device < 0 || o->device >= cnt) return set_err(ODE_B200_E_INVALID, "device %d out of range", o->device);
+  const int S = fixed_stage_count(o->method);
+  if (S == 0) return set_err(ODE_B200_E_UNSUPPORTED, "method %d is not a fixed-step explicit RK tableau", o->method);
+  if (n < 32) return set_err(ODE_B200_E_INVALID, "large-system path: n %lld (needs >= 32; smaller systems take the ensemble path)", (long long)n);
+  ODEB200_CUDA(cudaSetDevice(o->device));
+  const void* k[FIELD_MAX_STAGES] = {};
+  int np = 2;
+  if (o->rhs == ODE_B200_RHS_REACTION_DIFFUSION || o->rhs == ODE_B200_RHS_RD_FIELD) {
+    builtin_fixed_kernels(o->method, k);
+  } else if (o->rhs >= ODE_B200_FIELD_USER_BASE) {
+    if (!user_field_info(o->rhs, &np)) return set_err(ODE_B200_E_INVALID, "unknown field %d", o->rhs);
+    if (!user_fixed_kernels(o->rhs, o->method, S, k)) return ODE_B200_E_INVALID;
+  } else if (o->rhs >= ODE_B200_STENCIL_USER_BASE) {
+    int radius = 1;
+    if (!user_stencil_info(o->rhs, &radius, &np)) return set_err(ODE_B200_E_INVALID, "unknown stencil %d", o->rhs);
+    if (!user_fixed_kernels(o->rhs, o->method, S, k)) return ODE_B200_E_INVALID;
+  } else {
+    return set_err(ODE_B200_E_UNSUPPORTED, "the large-system path takes a stencil or field right-hand side");
+  }
+  if (np > 0 && (!params || o->n_params < np)) return set_err(ODE_B200_E_INVALID, "the right-hand side needs %d params", np);
+  // device buffers: two states, S-1 stages, two stage arguments
+  std::vector<double*> bufs;
+  auto release = [&]() {
+    for (double* b : bufs) cudaFree(b);
+  };
+  auto alloc = [&](double** p) {
+    if (cudaMalloc(p, (size_t)n * sizeof(double)) != cudaSuccess) return false;
+    bufs.push_back(*p);
+    return true;
+  };
+  FixedArgs A;
+  memset(&A, 0, sizeof(A));
+  double *ya = nullptr, *yb = nullptr;
+  bool ok = alloc(&ya) && alloc(&yb) && alloc(&A.T[0]) && alloc(&A.T[1]);
+  for (int q = 0; q < S - 1 && ok; q++) ok = alloc(&A.KS[q]);
+  if (!ok) {
+    cudaGetLastError();
+    release();
+    return set_err(ODE_B200_E_NOMEM, "cudaMalloc failed for a fixed-step system of %lld components", (long long)n);
+  }
+  cudaStream_t st = nullptr;
+  cudaEvent_t e0 = nullptr, e1 = nullptr;
+  cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking);
+  cudaEventCreate(&e0);
+  cudaEventCreate(&e1);
+  A.n = n;
+  for (int q = 0; q < np; q++) A.sc.p[q] = params[q];
+  A.sc.n_global = n;
+  A.sc.i0 = 0;
+  int sms = 0;
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, o->device);
+  long long fb = (n + FIELD_THREADS - 1) / FIELD_THREADS;
+  const unsigned grid = (unsigned)(fb < (long long)sms * 8 ? fb : (long long)sms * 8);
+  cudaError_t ce = cudaMemcpyAsync(ya, y0, (size_t)n * 8, cudaMemcpyHostToDevice, st);
+  if (pts_y) memcpy(pts_y, y0, (size_t)n * 8);  // ys[1] = deepcopy(y0) :193
+  cudaEventRecord(e0, st);
+  for (int i = 0; i + 1 < n_tspan && ce == cudaSuccess; i++) {  // :201
+    A.y = ya;
+    A.ynew = yb;
+    A.t = tspan[i];
+    A.dt = tspan[i + 1] - tspan[i];  // :202
+    void* kargs[] = {(void*)&A};
+    for (int s = 1; s <= S && ce == cudaSuccess; s++) {
+      ce = cudaLaunchKernel(k[s - 1], dim3(grid), dim3(FIELD_THREADS), kargs, 0, st);
+      note_launch();
+    }
+    if (pts_y && ce == cudaSuccess)
+      ce = cudaMemcpyAsync(pts_y + (size_t)(i + 1) * n, yb, (size_t)n * 8, cudaMemcpyDeviceToHost, st);
+    double* tmp = ya;
+    ya = yb;
+    yb = tmp;
+  }
+  cudaEventRecord(e1, st);
+  if (y_final && ce == cudaSuccess) ce = cudaMemcpyAsync(y_final, ya, (size_t)n * 8, cudaMemcpyDeviceToHost, st);
+  if (ce == cudaSuccess) ce = cudaStreamSynchronize(st);
+  float ms = 0.f;
+  if (ce == cudaSuccess) cudaEventElapsedTime(&ms, e0, e1);
+  cudaEventDestroy(e0);
+  cudaEventDestroy(e1);
+  cudaStreamDestroy(st);
+  release();
+  if (ce != cudaSuccess) {
+    cudaGetLastError();
+    return set_err(ODE_B200_E_CUDA, "fixed-step large-system solve failed: %s", cudaGetErrorString(ce));
+  }
+  if (stats) {
+    memset(stats, 0, sizeof(*stats));
+    stats->t_final = tspan[n_tspan - 1];
+    stats->n_accept = n_tspan - 1;
+    stats->n_rhs = (int64_t)(n_tspan - 1) * S;
+    stats->kernel_ms = ms;
+  }
+  return 0;
+}
 
 void ode_b200_trim(void) {
   large_cache_release();

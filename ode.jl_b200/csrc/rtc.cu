@@ -386,6 +386,82 @@ bool user_field_kernels(int rhs, int method, int n_stages, const void** out) {
   return true;
 }
 
+
+// Fixed-step stage kernels (field_fixed_stage_kernel<Tab, F, s>, s = 1 .. S) for a registered field, or for a
+// registered stencil through the FieldFromStencil adapter.  out[s - 1] = stage s.
+bool user_fixed_kernels(int rhs, int method, int n_stages, const void** out) {
+  const bool is_field = rhs >= ODE_B200_FIELD_USER_BASE;
+  UserRhs u;
+  {
+    std::lock_guard<std::mutex> lk(g_mu);
+    std::vector<UserRhs>& reg = is_field ? g_fields : g_stencils;
+    int i = rhs - (is_field ? ODE_B200_FIELD_USER_BASE : ODE_B200_STENCIL_USER_BASE);
+    if (i < 0 || i >= (int)reg.size()) {
+      set_err(ODE_B200_E_INVALID, "unknown large-system right-hand side %d", rhs);
+      return false;
+    }
+    u = reg[i];
+  }
+  const char* tab = tab_name(method);
+  if (!tab || method > ODE_B200_M_RK4) {
+    set_err(ODE_B200_E_UNSUPPORTED, "method %d is not a fixed-step explicit RK tableau", method);
+    return false;
+  }
+  int dev = 0;
+  cudaGetDevice(&dev);
+  char keyb[256];
+  snprintf(keyb, sizeof(keyb), "%d|%d|fixed|%s", dev, rhs, tab);
+  const std::string key(keyb);
+  {
+    std::lock_guard<std::mutex> lk(g_mu);
+    auto it = g_kernels.find(key + "|0");
+    if (it != g_kernels.end()) {
+      for (int k = 0; k < n_stages; k++) out[k] = g_kernels[key + "|" + std::to_string(k)];
+      return true;
+    }
+  }
+  std::string src = "#include \"field.cuh\"\nnamespace odeb200 {\n";
+  const char* functor;
+  char decl[512];
+  if (is_field) {
+    snprintf(decl, sizeof(decl),
+             "struct FieldUser {\n  static constexpr int NP = %d, ID = 0;\n"
+             "  __device__ __forceinline__ static double rhs(long long i, long long n, const double* __restrict__ y, "
+             "const double (&p)[8], double t) {\n    (void)i; (void)n; (void)y; (void)p; (void)t;\n",
+             u.np);
+    src += std::string(decl) + u.eval_body + "\n  }\n};\n";
+    functor = "odeb200::FieldUser";
+  } else {
+    snprintf(decl, sizeof(decl),
+             "struct StencilUser {\n  static constexpr int NP = %d, RADIUS = %d, ID = 0;\n"
+             "  __device__ __forceinline__ static double point(const double (&w)[%d], const double (&p)[8], double t, "
+             "long long i, long long n) {\n",
+             u.np, u.dof, 2 * u.dof + 1);
+    src += decl;
+    if (u.dof == 1) src += "    const double um = w[0], u = w[1], up = w[2]; (void)um; (void)u; (void)up;\n";
+    src += "    const double p0 = p[0], p1 = p[1]; (void)p0; (void)p1; (void)t; (void)i; (void)n;\n";
+    src += u.eval_body + "\n  }\n};\n";
+    functor = "odeb200::FieldFromStencil<odeb200::StencilUser>";
+  }
+  src += "}  // namespace odeb200\n";
+  std::vector<std::string> names;
+  for (int st = 1; st <= n_stages; st++) {
+    char e[256];
+    snprintf(e, sizeof(e), "odeb200::field_fixed_stage_kernel<%s, %s, %d>", tab, functor, st);
+    names.push_back(e);
+  }
+  std::vector<const char*> exprs;
+  for (const std::string& nme : names) exprs.push_back(nme.c_str());
+  std::vector<const void*> got(names.size(), nullptr);
+  if (!compile_and_load(u.name, src, exprs.data(), (int)exprs.size(), got.data())) return false;
+  std::lock_guard<std::mutex> lk(g_mu);
+  for (int k = 0; k < n_stages; k++) {
+    g_kernels[key + "|" + std::to_string(k)] = got[k];
+    out[k] = got[k];
+  }
+  return true;
+}
+
 }  // namespace odeb200
 
 using namespace odeb200;

@@ -11,4 +11,6 @@ bool user_stencil_kernels(int rhs, int method, const void** attempt, const void*
 // registered general large-system right-hand sides (field.cuh): parameter count; kernels for one tableau
 bool user_field_info(int rhs, int* np);
 bool user_field_kernels(int rhs, int method, int n_stages, const void** out);
+// fixed-step stage kernels for a registered field or stencil (out[s-1] = stage s)
+bool user_fixed_kernels(int rhs, int method, int n_stages, const void** out);
 }  // namespace odeb200

@@ -32,6 +32,29 @@ def shard_bounds(n_global, world, rank):
     return lo, lo + base + (1 if rank < rem else 0)
 
 
+_FIXED_RK = ("ode1", "ode2_midpoint", "ode2_heun", "ode4")
+
+
+def _solve_large_fixed(name, F, y0, ts, points, device):
+    """ode1 / ode2_midpoint / ode2_heun / ode4 on a dof = N state (src/runge_kutta.jl:176-212)."""
+    ts = np.ascontiguousarray(ts)
+    o = make_opts(name, F, ts, dof=min(y0.size, 2 ** 31 - 1), device=device, points="all")
+    p = F.param_array()
+    if p is None:
+        p = np.zeros(1)
+    st = LargeStats()
+    dp = _lib.dp
+    rows = None if points == "final" else np.empty((ts.size, y0.size))
+    yf = np.empty_like(y0)
+    check(lib().ode_b200_solve_large_fixed(C.byref(o), y0.size, y0.ctypes.data_as(dp), p.ctypes.data_as(dp),
+                                           ts.ctypes.data_as(dp), ts.size,
+                                           None if rows is None else rows.ctypes.data_as(dp), yf.ctypes.data_as(dp),
+                                           C.byref(st)))
+    r = dict(y=yf if rows is None else rows, t=ts.copy(), t_final=st.t_final, n_accept=st.n_accept, n_reject=0,
+             n_rhs=st.n_rhs, status=st.status, kernel_ms=st.kernel_ms)
+    return r
+
+
 def solve_large(alg, F, y0, tspan, *, trace=False, trace_cap=65536, out=None, **kw):
     """One GPU, host buffers in and out.  Returns dict(y, t_final, n_accept, n_reject, n_rhs, status, kernel_ms[, trace]).
     `out` (optional) is a caller-owned float64 array for the final state, e.g. pinned memory."""
@@ -40,6 +63,8 @@ def solve_large(alg, F, y0, tspan, *, trace=False, trace_cap=65536, out=None, **
     y0 = np.ascontiguousarray(np.asarray(y0, dtype=np.float64))
     ts = np.asarray(tspan, dtype=np.float64)
     kw.setdefault("points", "final")
+    if _alg_name(alg) in _FIXED_RK:  # oderk_fixed on the tspan grid: one state per tspan entry, no keywords
+        return _solve_large_fixed(_alg_name(alg), F, y0, ts, kw.get("points"), kw.get("device", 0))
     o = make_opts(_alg_name(alg), F, ts, dof=min(y0.size, 2 ** 31 - 1), **kw)
     p = F.param_array()
     if p is None:

@@ -187,8 +187,11 @@ def test_large_error_paths():
     F = m.DeviceRHS("reaction_diffusion", *RD)
     with pytest.raises(ValueError, match="Zero time span"):
         m.solve_large("ode45", F, u0(4096), [1.0, 1.0])
-    with pytest.raises(ValueError, match="adaptive RK Butcher table"):
-        m.solve_large("ode4", F, u0(4096), [0.0, 1.0])
+    import torch
+    with pytest.raises(ValueError, match="adaptive RK Butcher table"):  # the adaptive driver with a fixed-step tableau
+        m.CudaSlabEngine("ode4", F, 4096, 4096, 0, 1, [0.0, 1.0], torch.cuda.current_stream().cuda_stream)
+    with pytest.raises(m.OdeB200Error):  # the Rosenbrock solvers need a dense N x N Jacobian: ensemble path only
+        m.solve_large("ode23s", F, u0(4096), [0.0, 1.0])
     with pytest.raises(m.OdeB200Error):
         m.solve_large("ode45", F, u0(8), [0.0, 1.0])
     got = m.solve_large("ode45", F, u0(4096), [0.0, 20.0], max_steps=7)
@@ -364,3 +367,34 @@ def test_field_overflowing_first_step_recovers_like_the_reference():
     assert ref.status == 0 and np.any(ref.trace[:, 2] == 10.0)
     assert got["status"] == 0 and (got["n_accept"], got["n_reject"], got["n_rhs"]) == (ref.n_accept, ref.n_reject, ref.n_rhs)
     assert np.array_equal(got["trace"], ref.trace, equal_nan=True) and np.array_equal(got["y"], ref.y[-1])
+
+
+@pytest.mark.parametrize("method", ["ode1", "ode2_midpoint", "ode2_heun", "ode4"])
+def test_fixed_step_rk_on_a_large_state(method):
+    """oderk_fixed (src/runge_kutta.jl:176-212) on a dof = N state: one state per tspan entry, bit for bit, for
+    the built-in system (stencil and gather ids), a registered radius-2 stencil and a registered field."""
+    n = 3000
+    y0 = u0(n)
+    ts = np.linspace(0.0, 0.5, 11)
+    o = O.solve(method, "reaction_diffusion", y0, ts, RD)
+    for name in ("reaction_diffusion", "reaction_diffusion_field"):
+        t, y = getattr(m, method)(m.DeviceRHS(name, *RD), y0, ts)
+        assert np.array_equal(t, o.t) and np.array_equal(y, o.y), name
+    r = m.solve_large(method, m.DeviceRHS("reaction_diffusion", *RD), y0, ts)  # points = final
+    assert np.array_equal(r["y"], o.y[-1]) and r["n_rhs"] == o.n_rhs
+    n = 400
+    y0 = 0.5 + 0.4 * np.sin(2 * np.pi * 3 * np.arange(n) / n)
+    W = m.register_stencil("wide_fixed_" + method, WIDE_BODY, params=(0.6, 0.3, 0.1), radius=2)
+
+    def wide_host(w, p, t, i, nn):
+        x = float(i) / float(nn)
+        lap = (((-w[0] + 16.0 * w[1]) - 30.0 * w[2]) + 16.0 * w[3]) - w[4]
+        return (p[0] * (1.0 + 0.5 * x)) * (lap / 12.0) + p[1] * ((x - p[2] * t) * w[2])
+
+    t, y = getattr(m, method)(W, y0, ts)
+    o = O.solve_user_stencil(method, wide_host, y0, ts, [0.6, 0.3, 0.1], radius=2)
+    assert np.array_equal(t, o.t) and np.array_equal(y, o.y)
+    F = m.register_field("nonlocal_fixed_" + method, NONLOCAL_BODY, params=(0.8, 0.3, 0.5))
+    t, y = getattr(m, method)(F, y0, ts)
+    o = O.solve_user(method, nonlocal_host, y0, ts, [0.8, 0.3, 0.5])
+    assert np.array_equal(t, o.t) and np.array_equal(y, o.y)

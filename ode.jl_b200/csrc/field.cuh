@@ -223,6 +223,48 @@ __global__ void __launch_bounds__(FIELD_THREADS) field_fixed_stage_kernel(const 
   }
 }
 
+// ---- ode4ms: Adams-Bashforth, order ramping up to 4 (ode_ms, src/ODE.jl:175-212) on a dof = N state ------------
+struct Ms4Args {
+  const double* y;        // x[i]
+  double* ynew;           // x[i+1]
+  const double* hold[3];  // xdot[i-3], xdot[i-2], xdot[i-1] (oldest first; unused ones may be anything)
+  double* hnew;           // xdot[i] = F(t_i, x[i]) is written here
+  long long n;
+  double t, h;            // tspan[i], tspan[i+1] - tspan[i]
+  int so;                 // min(i, 4), 1-based step number
+  StencilCtx sc;
+};
+template <class Rhs>
+__global__ void __launch_bounds__(FIELD_THREADS) field_ms4_kernel(const __grid_constant__ Ms4Args A) {
+  constexpr double B[4][4] = {{1, 0, 0, 0},
+                              {-1.0 / 2, 3.0 / 2, 0, 0},
+                              {5.0 / 12, -4.0 / 3, 23.0 / 12, 0},
+                              {-9.0 / 24, 37.0 / 24, -59.0 / 24, 55.0 / 24}};  // ms_coefficients4 :440-443
+  const double h = A.h;
+  const int so = A.so;
+  for (long long i = (long long)blockIdx.x * FIELD_THREADS + threadIdx.x; i < A.n; i += (long long)gridDim.x * FIELD_THREADS) {
+    const double h3 = Rhs::rhs(i, A.n, A.y, A.sc.p, A.t);  // :201
+    A.hnew[i] = h3;
+    double v = A.y[i];  // :203-206, oldest derivative first
+    if (so == 1) {
+      v = v + (h * B[0][0]) * h3;
+    } else if (so == 2) {
+      v = v + (h * B[1][0]) * A.hold[2][i];
+      v = v + (h * B[1][1]) * h3;
+    } else if (so == 3) {
+      v = v + (h * B[2][0]) * A.hold[1][i];
+      v = v + (h * B[2][1]) * A.hold[2][i];
+      v = v + (h * B[2][2]) * h3;
+    } else {
+      v = v + (h * B[3][0]) * A.hold[0][i];
+      v = v + (h * B[3][1]) * A.hold[1][i];
+      v = v + (h * B[3][2]) * A.hold[2][i];
+      v = v + (h * B[3][3]) * h3;
+    }
+    A.ynew[i] = v;
+  }
+}
+
 // ---- hinit (src/ODE.jl:85-112) ---------------------------------------------------------------------
 // f0 = F(t0, y) -> K[0]; partial max|y|, max|f0|
 template <class Rhs>

@@ -936,14 +936,20 @@ int ode_b200_solve_large_fixed(const ode_b200_opts* o, int64_t n, const double* 
     return set_err(ODE_B200_E_NO_DEVICE, "no CUDA device available; libode_b200 has no CPU fallback");
   }
   if (o->device < 0 || o->device >= cnt) return set_err(ODE_B200_E_INVALID, "device %d out of range", o->device);
-  const int S = fixed_stage_count(o->method);
-  if (S == 0) return set_err(ODE_B200_E_UNSUPPORTED, "method %d is not a fixed-step explicit RK tableau", o->method);
+  const bool ms4 = o->method == ODE_B200_M_ODE4MS;  // Adams-Bashforth: one kernel per step, four derivative arrays
+  const int S = ms4 ? 1 : fixed_stage_count(o->method);
+  if (S == 0)
+    return set_err(ODE_B200_E_UNSUPPORTED, "method %d is not a fixed-step explicit method with a large-system kernel "
+                                           "(the Rosenbrock solvers need a dense N x N Jacobian)", o->method);
   if (n < 32) return set_err(ODE_B200_E_INVALID, "large-system path: n %lld (needs >= 32; smaller systems take the ensemble path)", (long long)n);
   ODEB200_CUDA(cudaSetDevice(o->device));
   const void* k[FIELD_MAX_STAGES] = {};
   int np = 2;
   if (o->rhs == ODE_B200_RHS_REACTION_DIFFUSION || o->rhs == ODE_B200_RHS_RD_FIELD) {
-    builtin_fixed_kernels(o->method, k);
+    if (ms4)
+      k[0] = (const void*)field_ms4_kernel<FieldReactionDiffusion>;
+    else
+      builtin_fixed_kernels(o->method, k);
   } else if (o->rhs >= ODE_B200_FIELD_USER_BASE) {
     if (!user_field_info(o->rhs, &np)) return set_err(ODE_B200_E_INVALID, "unknown field %d", o->rhs);
     if (!user_fixed_kernels(o->rhs, o->method, S, k)) return ODE_B200_E_INVALID;
@@ -968,8 +974,14 @@ int ode_b200_solve_large_fixed(const ode_b200_opts* o, int64_t n, const double* 
   FixedArgs A;
   memset(&A, 0, sizeof(A));
   double *ya = nullptr, *yb = nullptr;
-  bool ok = alloc(&ya) && alloc(&yb) && alloc(&A.T[0]) && alloc(&A.T[1]);
-  for (int q = 0; q < S - 1 && ok; q++) ok = alloc(&A.KS[q]);
+  double* hist[4] = {nullptr, nullptr, nullptr, nullptr};  // ode4ms: ring of the last four derivatives
+  bool ok = alloc(&ya) && alloc(&yb);
+  if (ms4) {
+    for (int q = 0; q < 4 && ok; q++) ok = alloc(&hist[q]);
+  } else {
+    ok = ok && alloc(&A.T[0]) && alloc(&A.T[1]);
+    for (int q = 0; q < S - 1 && ok; q++) ok = alloc(&A.KS[q]);
+  }
   if (!ok) {
     cudaGetLastError();
     release();
@@ -996,10 +1008,27 @@ int ode_b200_solve_large_fixed(const ode_b200_opts* o, int64_t n, const double* 
     A.ynew = yb;
     A.t = tspan[i];
     A.dt = tspan[i + 1] - tspan[i];  // :202
-    void* kargs[] = {(void*)&A};
-    for (int s = 1; s <= S && ce == cudaSuccess; s++) {
-      ce = cudaLaunchKernel(k[s - 1], dim3(grid), dim3(FIELD_THREADS), kargs, 0, st);
+    if (ms4) {  // xdot[i] goes to ring slot i % 4; the three older ones are slots i-3 .. i-1
+      Ms4Args M;
+      memset(&M, 0, sizeof(M));
+      M.y = ya;
+      M.ynew = yb;
+      for (int q = 0; q < 3; q++) M.hold[q] = hist[(i + 1 + q) % 4];
+      M.hnew = hist[i % 4];
+      M.n = n;
+      M.t = A.t;
+      M.h = A.dt;
+      M.so = (i + 1 < 4) ? i + 1 : 4;
+      M.sc = A.sc;
+      void* margs[] = {(void*)&M};
+      ce = cudaLaunchKernel(k[0], dim3(grid), dim3(FIELD_THREADS), margs, 0, st);
       note_launch();
+    } else {
+      void* kargs[] = {(void*)&A};
+      for (int s = 1; s <= S && ce == cudaSuccess; s++) {
+        ce = cudaLaunchKernel(k[s - 1], dim3(grid), dim3(FIELD_THREADS), kargs, 0, st);
+        note_launch();
+      }
     }
     if (pts_y && ce == cudaSuccess)
       ce = cudaMemcpyAsync(pts_y + (size_t)(i + 1) * n, yb, (size_t)n * 8, cudaMemcpyDeviceToHost, st);

@@ -402,8 +402,9 @@ bool user_fixed_kernels(int rhs, int method, int n_stages, const void** out) {
     }
     u = reg[i];
   }
-  const char* tab = tab_name(method);
-  if (!tab || method > ODE_B200_M_RK4) {
+  const bool ms4 = method == ODE_B200_M_ODE4MS;  // one kernel per step (field_ms4_kernel)
+  const char* tab = ms4 ? "ms4" : tab_name(method);
+  if (!tab || (!ms4 && method > ODE_B200_M_RK4)) {
     set_err(ODE_B200_E_UNSUPPORTED, "method %d is not a fixed-step explicit RK tableau", method);
     return false;
   }
@@ -447,7 +448,10 @@ bool user_fixed_kernels(int rhs, int method, int n_stages, const void** out) {
   std::vector<std::string> names;
   for (int st = 1; st <= n_stages; st++) {
     char e[256];
-    snprintf(e, sizeof(e), "odeb200::field_fixed_stage_kernel<%s, %s, %d>", tab, functor, st);
+    if (ms4)
+      snprintf(e, sizeof(e), "odeb200::field_ms4_kernel<%s>", functor);
+    else
+      snprintf(e, sizeof(e), "odeb200::field_fixed_stage_kernel<%s, %s, %d>", tab, functor, st);
     names.push_back(e);
   }
   std::vector<const char*> exprs;

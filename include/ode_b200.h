@@ -254,8 +254,8 @@ int ode_b200_solve_large(const ode_b200_opts* opts, int64_t n, const double* y0,
                          double* trace, int64_t trace_cap, int64_t* trace_n);
 
 /* oderk_fixed (src/runge_kutta.jl:176-212: ode1, ode2_midpoint, ode2_heun, ode4) and ode4ms (src/ODE.jl:175-212) on a
- * dof = N state with a stencil or
- field right-hand side: one step per tspan interval, one kernel per stage.  pts_y (optional) is [n_tspan][n] and
+ * dof = N state with a stencil or field right-hand side: one step per tspan interval, one kernel per stage.
+ * pts_y (optional) is [n_tspan][n] and
  * receives one state per tspan entry like the reference's yout; y_final (optional) the last one. */
 int ode_b200_solve_large_fixed(const ode_b200_opts* opts, int64_t n, const double* y0, const double* params,
                                const double* tspan, int32_t n_tspan, double* pts_y, double* y_final,

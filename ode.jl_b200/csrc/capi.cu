@@ -611,6 +611,10 @@ static int solve_ensemble_small(const ode_b200_opts* opts, const ode_b200_ensemb
   if (n_par) memcpy(h + o_par, io->params, n_par * 8);
   memcpy(h + o_ts, io->tspan, (size_t)io->n_tspan * 8);
   if (io->trace) memset(h + o_tn, 0, 8);
+  if (pts) {  // rows a truncated integration never reaches (minstep stop with points = :specified) read as zeros
+    memset(h + o_pt, 0, (size_t)n * io->pts_cap * 8);
+    memset(h + o_py, 0, (size_t)n * io->pts_cap * D * 8);
+  }
   ODEB200_CUDA(cudaMemcpyAsync(din, h, in_bytes, cudaMemcpyHostToDevice, st));
   ode_b200_ensemble_io d = *io;
   d.y0 = reinterpret_cast<double*>(din + o_y0);
@@ -714,6 +718,9 @@ int ode_b200_solve_ensemble(const ode_b200_opts* opts, const ode_b200_ensemble_i
     d.pts_t = g_arena.take<double>((size_t)n * io->pts_cap);
     d.pts_y = g_arena.take<double>((size_t)n * io->pts_cap * D);
     d.pts_n = io->pts_n ? g_arena.take<int>(n) : nullptr;
+    // rows a truncated integration never reaches (minstep stop with points = :specified) read as zeros
+    ODEB200_CUDA(cudaMemsetAsync(d.pts_t, 0, (size_t)n * io->pts_cap * 8, st));
+    ODEB200_CUDA(cudaMemsetAsync(d.pts_y, 0, (size_t)n * io->pts_cap * D * 8, st));
   } else {
     d.pts_t = d.pts_y = nullptr;
     d.pts_n = nullptr;

@@ -236,6 +236,7 @@ __global__ void __launch_bounds__(ENS_BLOCK, LITERAL ? 1 : adapt_min_blocks<Tab,
 
     // ---------------------------------------------------- stepsize_hw92! :401-442
     bool nanout = false, weird = false;
+    unsigned int expo_or = 0u;  // fast pass: OR of the high words of every trial component and scaled error
 #pragma unroll
     for (int d = 0; d < D; d++) {  // :430-434
       double ay = fabs(y[d]), at = fabs(ytrial[d]);
@@ -243,11 +244,19 @@ __global__ void __launch_bounds__(ENS_BLOCK, LITERAL ? 1 : adapt_min_blocks<Tab,
         nanout = nanout || (ytrial[d] != ytrial[d]);  // isoutofdomain, src/ODE.jl:116
         yerr[d] = yerr[d] / (A.abstol + jl_max(ay, at) * A.reltol);  // :433
       } else {
-        weird = weird || !is_finite(ytrial[d]);
-        yerr[d] = yerr[d] / (A.abstol + ((ay > at) ? ay : at) * A.reltol);  // :433
-        weird = weird || !is_finite(yerr[d]);
+        // max(|y|, |ytrial|) as an integer compare of the magnitudes' bit patterns (order-preserving for
+        // non-NaN values; a NaN trial state sends the trajectory to the literal pass whatever is picked here)
+        const bool ygt = (unsigned long long)__double_as_longlong(ay) > (unsigned long long)__double_as_longlong(at);
+        yerr[d] = yerr[d] / (A.abstol + (ygt ? ay : at) * A.reltol);  // :433
+        // non-finite <=> exponent field all ones; testing max(exponent fields) keeps these 2*D tests off the
+        // FP64 pipe (written on the high words so that nvcc does not turn them back into DSETP)
+        const unsigned int ht = (unsigned int)__double2hiint(ytrial[d]) & 0x7ff00000u;
+        const unsigned int he = (unsigned int)__double2hiint(yerr[d]) & 0x7ff00000u;
+        expo_or = expo_or > ht ? expo_or : ht;
+        expo_or = expo_or > he ? expo_or : he;
       }
     }
+    if (!LITERAL) weird = expo_or == 0x7ff00000u;
     if (!LITERAL && weird) {  // hand the trajectory to the literal pass (see header)
       A.status[idx] = ODE_B200_ST_REDO;
       atomicAdd(A.redo_count, 1);

@@ -113,10 +113,16 @@ __device__ __forceinline__ dm_dd dd_add(dm_dd a, dm_dd b) {
 __device__ __forceinline__ dm_dd dd_add_sq(dm_dd acc, double e) {  // acc + e*e, error-free product
   double p = e * e;
   double pe = dm_fma(e, e, -p);
-  dm_dd s = dm_two_sum(acc.hi, p);
+  // error-free sum of two non-negative numbers: fast two-sum with the larger operand first (3 additions instead
+  // of Knuth's 6); which one is larger is decided on the bit patterns, off the FP64 pipe.  Same s and same exact
+  // error term as dm_two_sum, hence the same bits.  (NaN/Inf operands give NaN either way.)
+  const bool abig = (unsigned long long)__double_as_longlong(acc.hi) >= (unsigned long long)__double_as_longlong(p);
+  const double big = abig ? acc.hi : p, small = abig ? p : acc.hi;
+  const double sum = big + small;
+  const double err = small - (sum - big);
   dm_dd r;
-  r.hi = s.hi;
-  r.lo = acc.lo + (s.lo + pe);
+  r.hi = sum;
+  r.lo = acc.lo + (err + pe);
   return r;
 }
 

@@ -131,7 +131,7 @@ __global__ void __launch_bounds__(ENS_BLOCK, LITERAL ? 1 : adapt_min_blocks<Tab,
   const double tstart = A.tspan[0];
   const double tend = A.tspan[A.n_tspan - 1];
   const double tdir = jl_sign(tend - tstart);  // src/ODE.jl:87 (zero span rejected on the host)
-  const bool fwd = tdir > 0.0;                  // x*tdir == (fwd ? x : -x) exactly
+  const bool fwd = __double2hiint(tdir) > 0;    // tdir = +-1: x*tdir == (fwd ? x : -x) exactly (sign test off the FP64 pipe)
   const int nfixed = A.n_tspan;
 
   long long idx = -1;
@@ -273,13 +273,17 @@ __global__ void __launch_bounds__(ENS_BLOCK, LITERAL ? 1 : adapt_min_blocks<Tab,
       // :436  min(maxstep, tdir*dt*max(facmin, fac*(1/err)^(1/(order+1)))); tdir = +-1 is applied as a
       // sign (exact), min/max keep Julia's NaN propagation (maxstep, facmin and dt are never NaN here)
       const double g = 0.8 * dm_pow(1.0 / err, EXPO);
-      double nd = jl_min_nn(A.maxstep, (fwd ? dt : -dt) * jl_max_nn(0.2, g));
+      // max(facmin, g) with g >= +0 or NaN: unsigned compare of the bit patterns (NaN sorts above every number and is
+      // propagated, like Julia's max), again off the FP64 pipe
+      const double gmax = ((unsigned long long)__double_as_longlong(g) > 0x3FC999999999999AULL) ? g : 0.2;
+      double nd = jl_min_nn(A.maxstep, (fwd ? dt : -dt) * gmax);
       const double ndt = jl_min_nn(dt, nd);  // :437-440 (signed dt), branch-free
       nd = (timeout > 0) ? ndt : nd;
       timeout = (timeout > 0) ? timeout - 1 : 0;
       newdt = fwd ? nd : -nd;  // :441
     }
-    const bool accept = err <= 1.0;  // :312
+    // :312  err <= 1 for err >= +0 or NaN, as an unsigned compare of bit patterns (NaN compares false either way)
+    const bool accept = (unsigned long long)__double_as_longlong(err) <= 0x3FF0000000000000ULL;
     if (MODE == 1 && idx == A.trace_traj) {
       if (ntrace < A.trace_cap) {
         A.trace[ntrace * 4 + 0] = t;

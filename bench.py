@@ -40,9 +40,9 @@ sys.path.insert(0, ROOT)
 LORENZ = (10.0, 28.0, 8.0 / 3.0)
 FLOPS_PER_ATTEMPT = 297  # dopri5 / Lorenz, SURVEY.md section 8d
 # dram__bytes_read.sum + dram__bytes_write.sum of one 2^20-trajectory launch, from the committed ncu capture
-# (profiles/ensemble_lorenz_r1.md, capture prof_lorenz_r1_c: 61.06 MB + 15.61 MB; y0 25 MB + the pre-pass's
+# (profiles/ensemble_lorenz_r1.md, capture prof_lorenz_r1_d: 60.71 MB + 14.20 MB; y0 25 MB + the pre-pass's
 # {dt0, f0} 34 MB in, results out, most of which stay in L2); the kernel is register resident, traffic is I/O only
-NCU_TRAFFIC_BYTES_PER_LAUNCH = 76.67e6
+NCU_TRAFFIC_BYTES_PER_LAUNCH = 74.91e6
 SEED = 20261019
 
 

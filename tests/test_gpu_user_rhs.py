@@ -256,3 +256,24 @@ def test_user_stencil_two_species_dirichlet_ends():
         assert np.array_equal(t, o.t) and np.array_equal(y, o.y), method
         assert (st["n_accept"], st["n_reject"], st["n_rhs"]) == (o.n_accept, o.n_reject, o.n_rhs)
         assert np.array_equal(y[-1][:2], u0[:2]) and np.array_equal(y[-1][-2:], u0[-2:])  # the ends did not move
+
+
+@pytest.mark.gpu
+def test_user_field_and_stencil_error_paths():
+    u0 = 0.5 + 0.1 * np.sin(2 * np.pi * np.arange(256) / 256)
+    with pytest.raises(m.OdeB200Error, match="NVRTC compilation"):
+        m.solve_large("ode45", m.register_field("bad_field", "return undefined_thing;"), u0, [0.0, 1.0])
+    with pytest.raises(m.OdeB200Error):
+        m.register_field("too_many_params", "return 0.0;", params=tuple(range(9)))
+    with pytest.raises(ValueError, match="takes 3 parameters"):  # fewer parameters than the functor was registered with
+        F = m.register_stencil("three_params", "return p[2] * w[1];", params=(1.0, 2.0, 3.0))
+        m.solve_large("ode45", F.with_params([1.0]), u0, [0.0, 1.0])
+    with pytest.raises(m.OdeB200Error):  # fields gather from the whole state: single slab only
+        import torch
+        G = m.register_field("mirror_err", "return p[0] * (y[n - 1 - i] - y[i]);", params=(0.5,))
+        m.CudaSlabEngine("ode45", G, 128, 256, 0, 2, [0.0, 1.0], torch.cuda.current_stream().cuda_stream)
+    # a stencil and a field without parameters
+    t, y = m.ode45(m.register_stencil("no_params", "return (um - 2.0 * u) + up;", params=()), u0, [0.0, 0.1], points="specified")
+    t2, y2 = m.ode45(m.register_field("no_params_f", "return (y[i == 0 ? n - 1 : i - 1] - 2.0 * y[i]) + y[i == n - 1 ? 0 : i + 1];"),
+                     u0, [0.0, 0.1], points="specified")
+    assert np.array_equal(y, y2)

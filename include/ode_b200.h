@@ -312,6 +312,11 @@ int ode_b200_slab_set_output_all(ode_b200_slab* s, const double* tspan_host, int
 /* global grid index of this slab's first point (what a stencil's `i` argument counts from).  Default:
  * contiguous slabs in rank order, the first n_global % world ranks one point longer. */
 int ode_b200_slab_set_offset(ode_b200_slab* s, int64_t first_global_index);
+/* Single slab (world = 1, stencil right-hand side): let the last thread block of the attempt kernel run the step
+ * controller itself.  `attempt` then needs no exchange after it and `control` only produces the requested output
+ * rows -- one copy and one dependent launch less per attempt.  Off by default (the decomposed path needs the
+ * all-gather between the two). */
+int ode_b200_slab_set_fused(ode_b200_slab* s, int32_t on);
 /* optional attempt trace on the device: rows (t, dt, err, accepted) */
 int ode_b200_slab_set_trace(ode_b200_slab* s, double* trace_dev, int64_t trace_cap);
 int ode_b200_slab_get_state(ode_b200_slab* s, double* y_local_dev);

@@ -120,6 +120,7 @@ def lib():
     L.ode_b200_slab_reset.argtypes = [C.c_void_p, C.c_double, C.c_double]
     L.ode_b200_slab_set_trace.argtypes = [C.c_void_p, C.c_void_p, C.c_int64]
     L.ode_b200_slab_set_offset.argtypes = [C.c_void_p, C.c_int64]
+    L.ode_b200_slab_set_fused.argtypes = [C.c_void_p, C.c_int32]
     L.ode_b200_slab_init_phase.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]
     L.ode_b200_slab_attempt.argtypes = [C.c_void_p, C.c_void_p]
     L.ode_b200_slab_control.argtypes = [C.c_void_p, C.c_void_p]

@@ -14,156 +14,7 @@
 
 namespace odeb200 {
 
-// ---- control kernel -------------------------------------------------------------
-// stepsize_hw92! :435-441 on the globally reduced sum, the accept/reject branch of
-// oderk_adapt :312-366, and the ghost refresh for the next step.
-__global__ void large_control_kernel(const ControlArgs C) {
-  LargeCtl* ctl = C.ctl;
-  __shared__ int refresh;
-  if (ctl->done) return;
-  if (threadIdx.x == 0) {
-    refresh = 0;
-    dm_dd tot;
-    tot.hi = 0.0;
-    tot.lo = 0.0;
-    double m = 0.0, nf = 0.0;
-    for (int r = 0; r < C.world; r++) {  // fixed rank order on every rank
-      const double* x = C.xrecv + (long long)r * XCHG;
-      dm_dd o;
-      o.hi = x[XS_HI];
-      o.lo = x[XS_LO];
-      tot = dd_add(tot, o);
-      m = normInf_step(m, x[XS_MAX]);
-      nf = fmax(nf, x[XS_NAN]);
-    }
-    // A non-finite trial state or error: the fast kernel dropped zero coefficients, the reference would have
-    // formed Inf*0 = NaN.  Repeat the attempt with the literal kernel first (every rank sees the same gathered
-    // data and takes the same decision); its result is then processed like any other.
-    if (!ctl->redo && (nf > 0.0 || m != m || !is_finite(m))) {
-      ctl->redo = 1;
-      refresh = 0;
-    } else {
-    ctl->redo = 0;
-    const double dt = ctl->dt, tdir = ctl->tdir, t = ctl->t;
-    double err, newdt;
-    int timeout = ctl->timeout;
-    if (nf > 0.0) {  // :432
-      err = 10.0;
-      newdt = dt * 0.2;
-      timeout = 5;
-    } else {
-      // norm(xerr, 2) for a long vector: maxabs shortcut, else sqrt of the exact sum
-      if (m == 0.0 || m != m || !is_finite(m))
-        err = m;
-      else
-        err = sqrt(tot.hi + tot.lo);
-      double nd = jl_min(ctl->maxstep,
-                         (tdir * dt) * jl_max(0.2, 0.8 * dm_pow(1.0 / err, 1.0 / (double)(C.order + 1))));  // :436
-      if (timeout > 0) {
-        nd = jl_min(nd, dt);
-        timeout -= 1;
-      }
-      newdt = tdir * nd;
-    }
-    ctl->attempts += 1;
-    ctl->err = err;
-    ctl->newdt = newdt;
-    const bool accept = err <= 1.0;
-    if (C.trace && ctl->trace_n < ctl->trace_cap) {
-      double* row = C.trace + ctl->trace_n * 4;
-      row[0] = t;
-      row[1] = dt;
-      row[2] = err;
-      row[3] = accept ? 1.0 : 0.0;
-    }
-    ctl->trace_n += 1;
-    ctl->accepted_last = accept ? 1 : 0;
-    ctl->out_lo = ctl->out_hi = 0;
-    if (accept) {
-      ctl->nacc += 1;
-      if (C.tq && !C.out_times) {  // :321-326  output at all new times which are < t+dt (all remaining ones on the last step)
-        int it = ctl->out_iter;  // 1-based index into tspan, like the reference's `iter`
-        const int lo = it - 1;
-        while (it - 1 < C.n_tq && (tdir * C.tq[it - 1] < tdir * (t + dt) || ctl->islast)) it++;
-        ctl->out_lo = lo;
-        ctl->out_hi = it - 1;
-        ctl->out_iter = it;
-        ctl->out_end = 0;
-      } else if (C.tq) {  // :327-340  points = :all: interior tspan points strictly inside (t, t+dt), then the step end
-        int itf = ctl->out_iter;  // the reference's iter_fixed (1-based)
-        const int lo = itf - 1;
-        while (itf - 1 < C.n_tq && tdir * t < tdir * C.tq[itf - 1] && tdir * C.tq[itf - 1] < tdir * (t + dt)) itf++;
-        ctl->out_lo = lo;
-        ctl->out_hi = itf - 1;
-        ctl->out_iter = itf;
-        ctl->out_end = 1;
-        ctl->out_row0 = ctl->out_rows;
-        long long r = ctl->out_rows;
-        for (int q = lo; q < itf - 1; q++, r++)
-          if (r < C.out_cap) C.out_times[r] = C.tq[q];
-        if (r < C.out_cap) C.out_times[r] = t + dt;
-        ctl->out_rows = r + 1;
-      }
-      if (C.tq) {
-        ctl->out_t = t;
-        ctl->out_dt = dt;
-        ctl->out_par = ctl->par;  // y, k1 of the step start live in Y/K[out_par]; ytrial, f1 in the other pair
-      }
-      ctl->par ^= 1;  // y <-> ytrial, k1 <-> k_next  (:341,:347)
-      if (ctl->islast) {
-        ctl->t_final = t + dt;
-        ctl->done = 1;
-        ctl->status = ODE_B200_ST_OK;
-      } else {
-        double tn = t + dt;  // :350
-        double dn = newdt;   // :351
-        int islast = 0;
-        if (tdir * (tn + dn + dn / 100) >= tdir * ctl->tend) {  // :354-357
-          dn = ctl->tend - tn;
-          islast = 1;
-        }
-        ctl->t = tn;
-        ctl->dt = dn;
-        ctl->islast = islast;
-        ctl->t_final = tn;
-        refresh = 1;
-      }
-    } else if (fabs(newdt) < ctl->minstep) {  // :358-360
-      ctl->done = 1;
-      ctl->status = ODE_B200_ST_MINSTEP;
-    } else {  // :361-366
-      ctl->islast = 0;
-      ctl->nrej += 1;
-      ctl->dt = newdt;
-      timeout = 5;
-      if (!is_finite(newdt)) {
-        ctl->done = 1;
-        ctl->status = ODE_B200_ST_NONFINITE;
-      }
-    }
-    ctl->timeout = timeout;
-    if (!ctl->done && ctl->attempts >= ctl->max_steps) {
-      ctl->done = 1;
-      ctl->status = ODE_B200_ST_MAXSTEPS;
-    }
-    }  // (!redo requested)
-  }
-  __syncthreads();
-  if (!refresh) return;
-  // ghost cells of the new y and k1 from the neighbours' edges (periodic ring)
-  const int par = ctl->par, H = C.H;
-  double* Yp = par ? C.Y[1] : C.Y[0];
-  double* Kp = par ? C.K[1] : C.K[0];
-  const int lr = (C.rank + C.world - 1) % C.world, rr = (C.rank + 1) % C.world;
-  const double* xl = C.xrecv + (long long)lr * XCHG + XS_EDGE;
-  const double* xr = C.xrecv + (long long)rr * XCHG + XS_EDGE;
-  for (int j = threadIdx.x; j < H; j += blockDim.x) {
-    Yp[j] = xl[H + j];
-    Yp[C.n + H + j] = xr[j];
-    Kp[j] = xl[3 * H + j];
-    Kp[C.n + H + j] = xr[2 * H + j];
-  }
-}
+__global__ void large_control_kernel(const ControlArgs C) { large_control_body(C); }
 
 // hermite_interp! (src/runge_kutta.jl:479-492) for the tspan rows the control kernel selected.
 __global__ void __launch_bounds__(256) large_hermite_kernel(double* const Y0, double* const Y1, double* const K0,
@@ -425,6 +276,7 @@ struct ode_b200_slab {
   double* KS[FIELD_MAX_STAGES] = {};  // field path: middle stages
   double* T[2] = {nullptr, nullptr};  // field path: stage-argument ping-pong
   int field_grid = 1;
+  bool fused = false;  // single slab, stencil path: the attempt kernel's last CTA runs the step controller
   int init_blocks = 0;
   LargeCtl host_ctl;
 };
@@ -654,6 +506,15 @@ int ode_b200_slab_set_offset(ode_b200_slab* s, int64_t first_global_index) {
   return 0;
 }
 
+int ode_b200_slab_set_fused(ode_b200_slab* s, int32_t on) {
+  int rc = slab_check(s);
+  if (rc) return rc;
+  if (on && (s->world != 1 || s->mi.field))
+    return set_err(ODE_B200_E_UNSUPPORTED, "the step controller can run inside the attempt kernel for a single stencil slab only");
+  s->fused = on != 0;
+  return 0;
+}
+
 int ode_b200_slab_set_trace(ode_b200_slab* s, double* trace_dev, int64_t trace_cap) {
   int rc = slab_check(s);
   if (rc) return rc;
@@ -791,6 +652,27 @@ int ode_b200_slab_init_phase(ode_b200_slab* s, int phase, double* xsend, const d
   return 0;
 }
 
+static ControlArgs control_args(const ode_b200_slab* s, const double* xrecv) {
+  ControlArgs C;
+  C.Y[0] = s->Y[0];
+  C.Y[1] = s->Y[1];
+  C.K[0] = s->K[0];
+  C.K[1] = s->K[1];
+  C.ctl = s->ctl;
+  C.xrecv = xrecv;
+  C.trace = s->trace;
+  C.n = s->n;
+  C.rank = s->rank;
+  C.world = s->world;
+  C.H = s->mi.H;
+  C.order = s->mi.order;
+  C.tq = s->out ? s->tq : nullptr;
+  C.n_tq = s->n_tq;
+  C.out_times = s->out ? s->out_times : nullptr;
+  C.out_cap = s->out_cap;
+  return C;
+}
+
 int ode_b200_slab_attempt(ode_b200_slab* s, double* xsend) {
   int rc = slab_check(s);
   if (rc) return rc;
@@ -833,6 +715,8 @@ int ode_b200_slab_attempt(ode_b200_slab* s, double* xsend) {
   A.n = s->n;
   A.tiles = s->tiles;
   A.sc = s->sc;
+  A.fused = s->fused ? 1 : 0;
+  A.ctl_args = control_args(s, xsend);  // fused mode: the partials are read where the last CTA wrote them
   void* kargs[] = {(void*)&A};
   ODEB200_CUDA(cudaLaunchKernel(s->mi.attempt, dim3((unsigned)s->grid), dim3(LARGE_THREADS), kargs, 0, s->stream));
   // the literal repeat of an attempt that went non-finite (ctl->redo); returns at once otherwise
@@ -845,25 +729,11 @@ int ode_b200_slab_attempt(ode_b200_slab* s, double* xsend) {
 int ode_b200_slab_control(ode_b200_slab* s, const double* xrecv) {
   int rc = slab_check(s);
   if (rc) return rc;
-  ControlArgs C;
-  C.Y[0] = s->Y[0];
-  C.Y[1] = s->Y[1];
-  C.K[0] = s->K[0];
-  C.K[1] = s->K[1];
-  C.ctl = s->ctl;
-  C.xrecv = xrecv;
-  C.trace = s->trace;
-  C.n = s->n;
-  C.rank = s->rank;
-  C.world = s->world;
-  C.H = s->mi.H;
-  C.order = s->mi.order;
-  C.tq = s->out ? s->tq : nullptr;
-  C.n_tq = s->n_tq;
-  C.out_times = s->out ? s->out_times : nullptr;
-  C.out_cap = s->out_cap;
-  large_control_kernel<<<1, 32, 0, s->stream>>>(C);
-  note_launch();
+  if (!s->fused) {
+    const ControlArgs C = control_args(s, xrecv);
+    large_control_kernel<<<1, 32, 0, s->stream>>>(C);
+    note_launch();
+  }
   if (s->out) {  // before the next attempt overwrites the step-start arrays
     large_hermite_kernel<<<s->init_blocks, 256, 0, s->stream>>>(s->Y[0], s->Y[1], s->K[0], s->K[1], s->ctl, s->tq,
                                                                  s->out, s->n, s->mi.H, s->out_cap,
@@ -1170,10 +1040,11 @@ static int solve_large_impl(const ode_b200_opts* o, int64_t n, const double* y0,
     LARGE_TRY(ode_b200_slab_init_phase(s, ph, xs, xr));
     if (ph < 3) LARGE_CUDA(cudaMemcpyAsync(xr, xs, XCHG * 8, cudaMemcpyDeviceToDevice, st));  // world = 1 "all-gather"
   }
+  s->fused = !s->mi.field;  // one slab: accept/reject runs inside the attempt kernel (no exchange, no control launch)
   while (!rc) {
     for (int q = 0; q < 4 && !rc; q++) {  // poll the done flag every 4 attempts; extra launches are no-ops
       LARGE_TRY(ode_b200_slab_attempt(s, xs));
-      LARGE_CUDA(cudaMemcpyAsync(xr, xs, XCHG * 8, cudaMemcpyDeviceToDevice, st));
+      if (!s->fused) LARGE_CUDA(cudaMemcpyAsync(xr, xs, XCHG * 8, cudaMemcpyDeviceToDevice, st));
       LARGE_TRY(ode_b200_slab_control(s, xr));
     }
     LARGE_TRY(ode_b200_slab_poll(s, poll));

@@ -79,6 +79,23 @@ struct LargeCtl {
   int out_end;
 };
 
+// ---- control: global accept/reject from the gathered partials --------------------
+// One block.  xrecv is [world][XCHG]; every rank runs the same arithmetic on the
+// same data, so all ranks take the same decision and the same new dt.
+struct ControlArgs {
+  double* Y[2];
+  double* K[2];
+  LargeCtl* ctl;
+  const double* xrecv;
+  double* trace;
+  const double* tq;  // output times (the reference's tspan), device; nullptr = no points output
+  double* out_times;  // points = :all: tout rows (device), nullptr for :specified
+  long long out_cap;  // rows available in the output buffer (:all)
+  long long n;
+  int rank, world, H, order, n_tq;
+};
+
+
 // What a stencil functor sees besides its window of 2R+1 values:
 //   point(w, p, t, i, n):  w[k] = u at grid index i-R+k (periodic), p = parameters, t = stage time,
 //                          i = global grid index, n = global ring length
@@ -100,6 +117,8 @@ struct LargeArgs {
   long long n;    // interior points of this slab
   long long tiles;
   StencilCtx sc;  // stencil parameters and index base
+  int fused;      // single slab: the last CTA runs the step controller itself (large_control_body)
+  ControlArgs ctl_args;
 };
 
 __device__ __forceinline__ dm_dd dd_add(dm_dd a, dm_dd b) {
@@ -126,6 +145,161 @@ __device__ __forceinline__ dm_dd dd_add_sq(dm_dd acc, double e) {  // acc + e*e,
   return r;
 }
 
+// ---- control kernel -------------------------------------------------------------
+// stepsize_hw92! :435-441 on the globally reduced sum, the accept/reject branch of
+// oderk_adapt :312-366, and the ghost refresh for the next step.
+// Runs in one block of >= 32 threads: thread 0 decides, then all threads refresh the ghost cells.  Called by
+// large_control_kernel (slab sessions: after the all-gather) and, for a single slab, by the last CTA of the fused
+// attempt kernel itself (LargeArgs::fused), which saves the exchange copy and one dependent launch per attempt.
+__device__ __forceinline__ void large_control_body(const ControlArgs& C) {
+  LargeCtl* ctl = C.ctl;
+  __shared__ int refresh;
+  if (ctl->done) return;
+  if (threadIdx.x == 0) {
+    refresh = 0;
+    dm_dd tot;
+    tot.hi = 0.0;
+    tot.lo = 0.0;
+    double m = 0.0, nf = 0.0;
+    for (int r = 0; r < C.world; r++) {  // fixed rank order on every rank
+      const double* x = C.xrecv + (long long)r * XCHG;
+      dm_dd o;
+      o.hi = x[XS_HI];
+      o.lo = x[XS_LO];
+      tot = dd_add(tot, o);
+      m = normInf_step(m, x[XS_MAX]);
+      nf = fmax(nf, x[XS_NAN]);
+    }
+    // A non-finite trial state or error: the fast kernel dropped zero coefficients, the reference would have
+    // formed Inf*0 = NaN.  Repeat the attempt with the literal kernel first (every rank sees the same gathered
+    // data and takes the same decision); its result is then processed like any other.
+    if (!ctl->redo && (nf > 0.0 || m != m || !is_finite(m))) {
+      ctl->redo = 1;
+      refresh = 0;
+    } else {
+    ctl->redo = 0;
+    const double dt = ctl->dt, tdir = ctl->tdir, t = ctl->t;
+    double err, newdt;
+    int timeout = ctl->timeout;
+    if (nf > 0.0) {  // :432
+      err = 10.0;
+      newdt = dt * 0.2;
+      timeout = 5;
+    } else {
+      // norm(xerr, 2) for a long vector: maxabs shortcut, else sqrt of the exact sum
+      if (m == 0.0 || m != m || !is_finite(m))
+        err = m;
+      else
+        err = sqrt(tot.hi + tot.lo);
+      double nd = jl_min(ctl->maxstep,
+                         (tdir * dt) * jl_max(0.2, 0.8 * dm_pow(1.0 / err, 1.0 / (double)(C.order + 1))));  // :436
+      if (timeout > 0) {
+        nd = jl_min(nd, dt);
+        timeout -= 1;
+      }
+      newdt = tdir * nd;
+    }
+    ctl->attempts += 1;
+    ctl->err = err;
+    ctl->newdt = newdt;
+    const bool accept = err <= 1.0;
+    if (C.trace && ctl->trace_n < ctl->trace_cap) {
+      double* row = C.trace + ctl->trace_n * 4;
+      row[0] = t;
+      row[1] = dt;
+      row[2] = err;
+      row[3] = accept ? 1.0 : 0.0;
+    }
+    ctl->trace_n += 1;
+    ctl->accepted_last = accept ? 1 : 0;
+    ctl->out_lo = ctl->out_hi = 0;
+    if (accept) {
+      ctl->nacc += 1;
+      if (C.tq && !C.out_times) {  // :321-326  output at all new times which are < t+dt (all remaining ones on the last step)
+        int it = ctl->out_iter;  // 1-based index into tspan, like the reference's `iter`
+        const int lo = it - 1;
+        while (it - 1 < C.n_tq && (tdir * C.tq[it - 1] < tdir * (t + dt) || ctl->islast)) it++;
+        ctl->out_lo = lo;
+        ctl->out_hi = it - 1;
+        ctl->out_iter = it;
+        ctl->out_end = 0;
+      } else if (C.tq) {  // :327-340  points = :all: interior tspan points strictly inside (t, t+dt), then the step end
+        int itf = ctl->out_iter;  // the reference's iter_fixed (1-based)
+        const int lo = itf - 1;
+        while (itf - 1 < C.n_tq && tdir * t < tdir * C.tq[itf - 1] && tdir * C.tq[itf - 1] < tdir * (t + dt)) itf++;
+        ctl->out_lo = lo;
+        ctl->out_hi = itf - 1;
+        ctl->out_iter = itf;
+        ctl->out_end = 1;
+        ctl->out_row0 = ctl->out_rows;
+        long long r = ctl->out_rows;
+        for (int q = lo; q < itf - 1; q++, r++)
+          if (r < C.out_cap) C.out_times[r] = C.tq[q];
+        if (r < C.out_cap) C.out_times[r] = t + dt;
+        ctl->out_rows = r + 1;
+      }
+      if (C.tq) {
+        ctl->out_t = t;
+        ctl->out_dt = dt;
+        ctl->out_par = ctl->par;  // y, k1 of the step start live in Y/K[out_par]; ytrial, f1 in the other pair
+      }
+      ctl->par ^= 1;  // y <-> ytrial, k1 <-> k_next  (:341,:347)
+      if (ctl->islast) {
+        ctl->t_final = t + dt;
+        ctl->done = 1;
+        ctl->status = ODE_B200_ST_OK;
+      } else {
+        double tn = t + dt;  // :350
+        double dn = newdt;   // :351
+        int islast = 0;
+        if (tdir * (tn + dn + dn / 100) >= tdir * ctl->tend) {  // :354-357
+          dn = ctl->tend - tn;
+          islast = 1;
+        }
+        ctl->t = tn;
+        ctl->dt = dn;
+        ctl->islast = islast;
+        ctl->t_final = tn;
+        refresh = 1;
+      }
+    } else if (fabs(newdt) < ctl->minstep) {  // :358-360
+      ctl->done = 1;
+      ctl->status = ODE_B200_ST_MINSTEP;
+    } else {  // :361-366
+      ctl->islast = 0;
+      ctl->nrej += 1;
+      ctl->dt = newdt;
+      timeout = 5;
+      if (!is_finite(newdt)) {
+        ctl->done = 1;
+        ctl->status = ODE_B200_ST_NONFINITE;
+      }
+    }
+    ctl->timeout = timeout;
+    if (!ctl->done && ctl->attempts >= ctl->max_steps) {
+      ctl->done = 1;
+      ctl->status = ODE_B200_ST_MAXSTEPS;
+    }
+    }  // (!redo requested)
+  }
+  __syncthreads();
+  if (!refresh) return;
+  // ghost cells of the new y and k1 from the neighbours' edges (periodic ring)
+  const int par = ctl->par, H = C.H;
+  double* Yp = par ? C.Y[1] : C.Y[0];
+  double* Kp = par ? C.K[1] : C.K[0];
+  const int lr = (C.rank + C.world - 1) % C.world, rr = (C.rank + 1) % C.world;
+  const double* xl = C.xrecv + (long long)lr * XCHG + XS_EDGE;
+  const double* xr = C.xrecv + (long long)rr * XCHG + XS_EDGE;
+  for (int j = threadIdx.x; j < H; j += blockDim.x) {
+    Yp[j] = xl[H + j];
+    Yp[C.n + H + j] = xr[j];
+    Kp[j] = xl[3 * H + j];
+    Kp[C.n + H + j] = xr[2 * H + j];
+  }
+}
+
+
 template <int P>
 __device__ __forceinline__ void load_chunk(const double* a, long long q, long long lim, double (&v)[P]) {
   if (q + P <= lim) {
@@ -149,7 +323,7 @@ __device__ __forceinline__ void load_chunk(const double* a, long long q, long lo
 // fixed order, so the result does not depend on scheduling.  Shared by the fused stencil kernel and the
 // stage-per-kernel field path (field.cuh).
 template <int T>
-__device__ __forceinline__ void reduce_error_partials(dm_dd acc, double mx, bool anynan, double* part, LargeCtl* ctl,
+__device__ __forceinline__ bool reduce_error_partials(dm_dd acc, double mx, bool anynan, double* part, LargeCtl* ctl,
                                                       double* xsend) {
   __shared__ double red[T / 32][4];
   __shared__ bool is_last;
@@ -196,7 +370,7 @@ __device__ __forceinline__ void reduce_error_partials(dm_dd acc, double mx, bool
     is_last = (done == (unsigned int)(gridDim.x - 1));
   }
   __syncthreads();
-  if (!is_last) return;
+  if (!is_last) return false;
   // ---- last CTA: reduce the per-CTA partials in a fixed order -> xsend[0..3] ----------
   __threadfence();
   dm_dd a2;
@@ -249,6 +423,7 @@ __device__ __forceinline__ void reduce_error_partials(dm_dd acc, double mx, bool
     xsend[XS_NAN] = nf;
     ctl->blocks_done = 0;
   }
+  return true;
 }
 
 // One RHS sweep over a thread's P consecutive points: the R edge values per side cross threads through one
@@ -487,7 +662,11 @@ __global__ void __launch_bounds__(LARGE_THREADS) large_attempt_kernel(
   }
 
   if (!LITERAL) mx = __longlong_as_double((long long)mxb);
-  reduce_error_partials<T>(acc, mx, anynan, A.part, ctl, A.xsend);
+  const bool last_cta = reduce_error_partials<T>(acc, mx, anynan, A.part, ctl, A.xsend);
+  if (A.fused && last_cta) {  // single slab: accept/reject, new dt and the ghost refresh right here
+    __syncthreads();          // the reduced partials (thread 0) are visible to the block
+    large_control_body(A.ctl_args);
+  }
 }
 
 // ---- hinit (src/ODE.jl:85-112) sweeps over the slab ---------------------------------------
@@ -554,22 +733,6 @@ __global__ void __launch_bounds__(256) hinit_f1_kernel(const double* y, const do
   double a = block_max_nanprop<256>(md, sh);
   if (threadIdx.x == 0) part[blockIdx.x * 2] = a;
 }
-// ---- control: global accept/reject from the gathered partials --------------------
-// One block.  xrecv is [world][XCHG]; every rank runs the same arithmetic on the
-// same data, so all ranks take the same decision and the same new dt.
-struct ControlArgs {
-  double* Y[2];
-  double* K[2];
-  LargeCtl* ctl;
-  const double* xrecv;
-  double* trace;
-  const double* tq;  // output times (the reference's tspan), device; nullptr = no points output
-  double* out_times;  // points = :all: tout rows (device), nullptr for :specified
-  long long out_cap;  // rows available in the output buffer (:all)
-  long long n;
-  int rank, world, H, order, n_tq;
-};
-
 __global__ void large_control_kernel(const ControlArgs C);
 __global__ void large_ghost_kernel(double* a, const double* xrecv, long long n, int rank, int world, int H, int slot);
 

@@ -142,6 +142,12 @@ class CudaSlabEngine:
     def reset(self, t0, tend):
         check(self.L.ode_b200_slab_reset(self.h, float(t0), float(tend)))
 
+    def set_fused(self, on=True):
+        """Single stencil slab: the attempt kernel's last thread block runs the step controller (no exchange needed
+        between attempt() and control())."""
+        check(self.L.ode_b200_slab_set_fused(self.h, 1 if on else 0))
+        self.fused = bool(on)
+
     def set_state(self, dev_ptr):
         check(self.L.ode_b200_slab_set_state(self.h, C.c_void_p(dev_ptr)))
 
@@ -201,10 +207,12 @@ def integrate_slab(engine, send, recv, exchange, poll_every=4, max_polls=10 ** 9
         if phase < 3:
             exchange()
     polls = 0
+    fused = getattr(engine, "fused", False)  # single slab: the controller already ran inside attempt()
     while True:
         for _ in range(poll_every):
             engine.attempt(sp)
-            exchange()
+            if not fused:
+                exchange()
             engine.control(rp)
         ctl = engine.poll()
         polls += 1
@@ -241,6 +249,8 @@ def solve_large_distributed(alg, F, y_local, n_global, tspan, *, group=None, pol
     else:
         def exchange():
             recv.view(-1).copy_(send)
+    if world == 1 and not getattr(F, "is_field", False) and F.name != "reaction_diffusion_field":
+        eng.set_fused(True)
     y_local = y_local.contiguous()
     eng.set_state(y_local.data_ptr())
     ctl = integrate_slab(eng, send, recv, exchange, poll_every=poll_every)

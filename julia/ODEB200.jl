@@ -21,7 +21,7 @@ const METHODS = Dict(:ode1=>0, :ode2_midpoint=>1, :ode2_heun=>2, :ode4=>3, :ode2
                      :ode45_fe=>6, :ode45_dp=>7, :ode45=>7, :ode78=>8, :ode23s=>9,
                      :ode4s=>10, :ode4s_s=>10, :ode4s_kr=>11, :ode4ms=>12)
 const RHS = Dict(:linear=>0, :const=>1, :timelin=>2, :rotation=>3, :lorenz=>4, :vdp=>5,
-                 :robertson=>6, :kepler=>7, :reaction_diffusion=>8)
+                 :robertson=>6, :kepler=>7, :reaction_diffusion=>8, :reaction_diffusion_field=>9)
 const POINTS = Dict(:all=>0, :specified=>1, :final=>2)
 
 struct DeviceRHS{Name}
@@ -164,5 +164,60 @@ function solve_b200(f::DeviceRHS, u0, tspan::Tuple, alg::Symbol; saveat = Float6
                     maxstep = dtmax, minstep = dtmin, initstep = dt, points = points)
     return (t = ts, u = us, retcode = :Succss)   # src/common.jl:122
 end
+
+# ---- one large system (dof = N): registered stencils / fields, include/ode_b200.h -----------------------
+struct LargeStats
+    n_accept::Int64; n_reject::Int64; n_rhs::Int64; status::Int32; pad::Int32; t_final::Float64; kernel_ms::Float64
+end
+"""register_stencil("lap4", "return p[0]*((((-w[0]+16.0*w[1])-30.0*w[2])+16.0*w[3])-w[4])/12.0;"; radius = 2, params = [0.1])
+`point(w, p, t, i, n)`: w[k] = u[i-radius+k] on a periodic ring."""
+function register_stencil(name::String, body::String; radius::Integer = 1, params = Float64[])
+    id = ccall((:ode_b200_register_stencil, LIB[]), Cint, (Cstring, Int32, Int32, Cstring), name, radius, length(params), body)
+    id < 0 && error("libode_b200: " * last_error())
+    UserRHS(id, Float64[params...])
+end
+"""register_field("mirror", "return p[0]*(y[n-1-i] - y[i]);"; params = [0.5]): a general rhs(i, n, y, p, t)."""
+function register_field(name::String, body::String; params = Float64[])
+    id = ccall((:ode_b200_register_field, LIB[]), Cint, (Cstring, Int32, Cstring), name, length(params), body)
+    id < 0 && error("libode_b200: " * last_error())
+    UserRHS(id, Float64[params...])
+end
+"""solve_large(:ode45, F, u0, (t0, tend); kw...) -> (t_final, u_final, stats): oderk_adapt on a dof = N state with the
+built-in DeviceRHS(:reaction_diffusion, kappa, r), a registered stencil (fused kernel) or field (kernel per stage)."""
+function solve_large(method::Symbol, F::Union{DeviceRHS,UserRHS}, u0::Vector{Float64}, tspan;
+                     reltol = 1.0e-5, abstol = 1.0e-8, minstep = abs(tspan[end]-tspan[1])/1e18,
+                     maxstep = abs(tspan[end]-tspan[1])/2.5, initstep = 0.0, device = 0)
+    n = length(u0)
+    out = similar(u0)
+    p = isempty(F.params) ? Float64[0.0] : F.params
+    st = Ref(LargeStats(0, 0, 0, 0, 0, 0.0, 0.0))
+    o = Ref(Opts(METHODS[method], rhs_id(F), min(n, typemax(Int32)), length(F.params), 0, POINTS[:final], 0, device, 0,
+                 reltol, abstol, minstep, maxstep, initstep, 0, 0, ntuple(_ -> Int32(0), 6)))
+    GC.@preserve u0 out p begin
+        check(ccall((:ode_b200_solve_large, LIB[]), Cint,
+                    (Ref{Opts}, Int64, Ptr{Float64}, Ptr{Float64}, Float64, Float64, Ptr{Float64}, Ref{LargeStats},
+                     Ptr{Float64}, Int64, Ptr{Int64}),
+                    o, n, u0, p, Float64(tspan[1]), Float64(tspan[end]), out, st, C_NULL, 0, C_NULL))
+    end
+    st[].status == 1 && println("Warning: dt < minstep.  Stopping.")   # src/runge_kutta.jl:359
+    return st[].t_final, out, st[]
+end
+"""solve_large_fixed(:ode4, F, u0, tspan) -> (tspan, [u(t) for t in tspan]): oderk_fixed / ode4ms on a dof = N state."""
+function solve_large_fixed(method::Symbol, F::Union{DeviceRHS,UserRHS}, u0::Vector{Float64}, tspan; device = 0)
+    n = length(u0)
+    ts = convert(Vector{Float64}, collect(tspan))
+    rows = Matrix{Float64}(undef, n, length(ts))      # column = one state (row-major [n_tspan][n] in C)
+    p = isempty(F.params) ? Float64[0.0] : F.params
+    st = Ref(LargeStats(0, 0, 0, 0, 0, 0.0, 0.0))
+    o = Ref(Opts(METHODS[method], rhs_id(F), min(n, typemax(Int32)), length(F.params), 0, POINTS[:all], 0, device, 0,
+                 1.0e-5, 1.0e-8, 0.0, 0.0, 0.0, 0, 0, ntuple(_ -> Int32(0), 6)))
+    GC.@preserve u0 ts rows p begin
+        check(ccall((:ode_b200_solve_large_fixed, LIB[]), Cint,
+                    (Ref{Opts}, Int64, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Int32, Ptr{Float64}, Ptr{Float64}, Ref{LargeStats}),
+                    o, n, u0, p, ts, length(ts), rows, C_NULL, st))
+    end
+    return ts, [rows[:, i] for i in 1:length(ts)]
+end
+export register_stencil, register_field, solve_large, solve_large_fixed
 
 end # module

@@ -132,7 +132,13 @@ __global__ void __launch_bounds__(ENS_BLOCK, (Rhs::DOF <= 3) ? ODEB200_S23_MINB 
   const int nfixed = A.n_tspan;
 
   long long idx = -1;
-  double y[D], F0[D], J[D][D], p[NPA];
+  double y[D], F0[D], p[NPA];
+  // The Jacobian lives across attempts (it is rebuilt only after an accepted step) but is read once per attempt:
+  // for small systems it is parked in shared memory, [entry][thread] so that a warp's accesses are conflict free,
+  // which frees 2*D*D registers for occupancy.
+  constexpr bool JS = (D <= ODEB200_S23_JSHARED_MAXD);
+  __shared__ double Jsh[JS ? D * D : 1][JS ? ENS_BLOCK : 1];
+  double Jreg[JS ? 1 : D][JS ? 1 : D];
   double t = 0.0, h = 0.0, last_tout = 0.0;
   int nacc = 0, nrej = 0, nrhs = 0, npts = 0;
   long long attempts = 0, ntrace = 0;
@@ -195,7 +201,18 @@ __global__ void __launch_bounds__(ENS_BLOCK, (Rhs::DOF <= 3) ? ODEB200_S23_MINB 
         npts = 1;
         last_tout = tstart;
       }
-      nrhs += eval_jacobian<Rhs, JAC, D, NPA>(t, y, p, J);  // :294
+      {
+        double Jt[D][D];
+        nrhs += eval_jacobian<Rhs, JAC, D, NPA>(t, y, p, Jt);  // :294
+#pragma unroll
+        for (int i = 0; i < D; i++) {
+#pragma unroll
+          for (int j = 0; j < D; j++) {
+            if constexpr (JS) Jsh[i * D + j][threadIdx.x] = Jt[i][j];
+            else Jreg[i][j] = Jt[i][j];
+          }
+        }
+      }
     }
 
     int fin = -1;
@@ -213,7 +230,10 @@ __global__ void __launch_bounds__(ENS_BLOCK, (Rhs::DOF <= 3) ? ODEB200_S23_MINB 
       for (int i = 0; i < D; i++) {
 #pragma unroll
         for (int j = 0; j < D; j++) {
-          double m = -(hd * J[i][j]);
+          double Jij;
+          if constexpr (JS) Jij = Jsh[i * D + j][threadIdx.x];
+          else Jij = Jreg[i][j];
+          double m = -(hd * Jij);
           W.a[i][j] = (i == j) ? (m + 1.0) : m;
         }
       }
@@ -297,7 +317,18 @@ __global__ void __launch_bounds__(ENS_BLOCK, (Rhs::DOF <= 3) ? ODEB200_S23_MINB 
             y[i] = ynew[i];  // :349
             F0[i] = F2[i];   // :351
           }
-          nrhs += eval_jacobian<Rhs, JAC, D, NPA>(t, y, p, J);  // :352
+          {
+            double Jt[D][D];
+            nrhs += eval_jacobian<Rhs, JAC, D, NPA>(t, y, p, Jt);  // :352
+#pragma unroll
+            for (int i = 0; i < D; i++) {
+#pragma unroll
+              for (int j = 0; j < D; j++) {
+                if constexpr (JS) Jsh[i * D + j][threadIdx.x] = Jt[i][j];
+                else Jreg[i][j] = Jt[i][j];
+              }
+            }
+          }
         } else {
           nrej++;
         }

@@ -457,3 +457,26 @@ def test_pinned_output_buffers_are_written_in_place():
 def test_shared_denominator_division_is_ieee_division():
     """recip_prepare/div_by (csrc/common.cuh) against the compiler's a / b on 2^30 operand pairs."""
     assert m.lib().ode_b200_selftest_div(0, 1 << 30, 20261019) == 0
+
+
+@pytest.mark.gpu
+def test_cuda_path_against_committed_golden_runs():
+    """The CUDA path against tests/golden/oracle_runs.json directly (no live oracle in the loop): step counts and the
+    final state, as exact hex floats, of every committed run."""
+    import json
+    import os
+    gold = json.load(open(os.path.join(os.path.dirname(__file__), "golden", "oracle_runs.json")))
+    for entry in gold:
+        c, want = entry["case"], entry["result"]
+        F = m.DeviceRHS(c["rhs"], *(c["params"] or []))
+        kw = dict(c["kw"])
+        if "jacobian" in kw:
+            kw["jacobian"] = True
+        y0 = c["y0"] if len(c["y0"]) > 1 else c["y0"][0]
+        fixed = c["method"] in ("ode1", "ode2_midpoint", "ode2_heun", "ode4", "ode4s_s", "ode4s_kr", "ode4ms")
+        if fixed and (len(c["y0"]) > 1 or c["rhs"] == "reaction_diffusion"):
+            kw = {k: v for k, v in kw.items() if k == "jacobian"}
+        t, y, st = getattr(m, c["method"]).stats(F, y0, c["tspan"], **kw)
+        got = dict(n_accept=int(st["n_accept"]), n_reject=int(st["n_reject"]), n_rhs=int(st["n_rhs"]), status=int(st["status"]),
+                   n_out=len(t), t_final=float(t[-1]).hex(), y_final=[float(v).hex() for v in np.atleast_1d(y[-1])])
+        assert got == want, c["name"]

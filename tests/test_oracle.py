@@ -230,3 +230,19 @@ def test_analytic_jacobians_match_finite_differences():
             e[j] = 1e-6 * max(1.0, abs(y[j]))
             fd = (np.array(F(0.0, list(y + e))) - np.array(F(0.0, list(y - e)))) / (2 * e[j])
             assert np.allclose(J[:, j], fd, rtol=1e-5, atol=1e-4 * max(1.0, np.abs(J).max()))
+
+
+def test_oracle_against_golden_runs():
+    """The oracle's own bits are pinned: step counts and final states (exact hex floats) of a fixed set of problems
+    (tests/golden/oracle_runs.json, made by tools/gen_golden_oracle.py).  A change to oracle/ or to the shared
+    deterministic pow/log10 that moves a bit has to regenerate the fixture on purpose."""
+    import json
+    sys_path_tools = os.path.join(os.path.dirname(__file__), "..", "tools")
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("gen_golden_oracle", os.path.join(sys_path_tools, "gen_golden_oracle.py"))
+    gen = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(gen)
+    gold = json.load(open(os.path.join(GOLD, "oracle_runs.json")))
+    assert len(gold) >= 25
+    for entry in gold:
+        assert gen.run(entry["case"]) == entry["result"], entry["case"]["name"]

@@ -121,7 +121,7 @@ def run_reference(args, rank):
     """--impl reference: the reference's CPU implementation of the path = the oracle port."""
     if rank != 0:
         return
-    if args.workload == "large":
+    if args.workload in ("large", "field"):
         from bench_large import cpu_baseline_large
         cb = cpu_baseline_large()
         v = cb["attempts_per_s_at_2^26"]
@@ -154,7 +154,7 @@ def main():
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--workload", default="lorenz", choices=["lorenz", "large"])
+    ap.add_argument("--workload", default="lorenz", choices=["lorenz", "large", "field"])
     ap.add_argument("--n-traj", type=int, default=1 << 20)
     ap.add_argument("--cpu-sample", type=int, default=1 << 18)
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -168,7 +168,7 @@ def main():
     if args.impl == "reference":
         run_reference(args, rank)
         return
-    if args.workload == "large":
+    if args.workload in ("large", "field"):
         from bench_large import run_large  # noqa: E402
         run_large(args, rank, local_rank, world)
         return

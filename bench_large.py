@@ -19,6 +19,7 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
 FUSED_BYTES_PER_POINT = 32      # read y, k1; write ytrial, k7 (large-system kernel)
+FIELD_BYTES_PER_POINT = 368     # one kernel per stage: 46 array passes for dopri5
 STAGEWISE_BYTES_PER_POINT = 264  # SURVEY.md section 8d figure for one kernel per stage
 FLOPS_PER_POINT = 143
 # dram__bytes_read.sum + dram__bytes_write.sum of one attempt at N = 2^26 from the committed ncu capture
@@ -62,7 +63,11 @@ def run_large(args, rank, local_rank, world):
     n_local = int(os.environ.get("ODE_B200_LARGE_N", 1 << 26))
     n_global = n_local * world
     lo, hi = m.shard_bounds(n_global, world, rank)
-    F = m.DeviceRHS("reaction_diffusion", 1.0, 1.0)
+    field = getattr(args, "workload", "large") == "field"  # the same system through the stage-per-kernel path
+    if field and world > 1:
+        raise SystemExit("--workload field is a single-GPU path (a gather cannot be slab-decomposed)")
+    F = m.DeviceRHS("reaction_diffusion_field" if field else "reaction_diffusion", 1.0, 1.0)
+    bytes_per_point = FIELD_BYTES_PER_POINT if field else FUSED_BYTES_PER_POINT
     tspan = [0.0, 20.0]
     y0 = torch.from_numpy(u0_slab(lo, hi, n_global)).to(dev)
 
@@ -149,11 +154,11 @@ def run_large(args, rank, local_rank, world):
             pass
         hbm = float(peaks.get("hbm_gbs", 6650.0))
         dmix = L.ode_b200_fp64_peak(local_rank, 1)
-        gbs = FUSED_BYTES_PER_POINT * n_local / (per_attempt_ms * 1e-3) / 1e9
+        gbs = bytes_per_point * n_local / (per_attempt_ms * 1e-3) / 1e9
         line = {"metric": "rk_step_attempts_per_s", "value": attempts / (ms * 1e-3), "unit": "steps/s",
                 "n_gpus": world, "steps": steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True,
                 "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-                "config": {"workload": "reaction_diffusion_ode45_dp_large", "n_per_gpu": n_local, "n_global": n_global,
+                "config": {"workload": "reaction_diffusion_ode45_dp_field" if field else "reaction_diffusion_ode45_dp_large", "n_per_gpu": n_local, "n_global": n_global,
                            "tspan": tspan, "reltol": 1e-5, "abstol": 1e-8, "attempts_per_step": attempts,
                            "accepted": ctl["n_accept"], "rejected": ctl["n_reject"],
                            "ms_per_attempt": per_attempt_ms, "point_updates_per_s": attempts * n_global / (ms * 1e-3),
@@ -161,15 +166,17 @@ def run_large(args, rank, local_rank, world):
                            "parallelism": "slab x%d, one all-gather of %d doubles per attempt" % (world, m._lib.XCHG_DOUBLES)},
                 "e2e": e2e, "gpu_launches": launches, "clocks": clocks,
                 "roofline": {"bound": "hbm", "achieved": gbs, "peak": hbm, "unit": "GB/s", "frac": gbs / hbm,
-                             "traffic": NCU_TRAFFIC_BYTES_PER_ATTEMPT_2_26 if n_local == (1 << 26) else None,
+                             "traffic": NCU_TRAFFIC_BYTES_PER_ATTEMPT_2_26 if (n_local == (1 << 26) and not field) else None,
                              "peak_source": "MEASURED_PEAKS.json hbm_gbs" if peaks else "fallback 6650 GB/s",
-                             "algorithmic_bytes_per_point": FUSED_BYTES_PER_POINT,
+                             "algorithmic_bytes_per_point": bytes_per_point,
                              "stagewise_equivalent": {"bytes_per_point": STAGEWISE_BYTES_PER_POINT,
                                                       "gbs": STAGEWISE_BYTES_PER_POINT * n_local / (per_attempt_ms * 1e-3) / 1e9,
                                                       "frac": STAGEWISE_BYTES_PER_POINT * n_local / (per_attempt_ms * 1e-3) / 1e9 / hbm},
                              "fp64_issue_frac": FLOPS_PER_POINT * n_local / (per_attempt_ms * 1e-3) / dmix,
-                             "note": "all stages of an attempt are fused in one kernel, so HBM traffic is 32 B/point "
-                                     "instead of the 264 B/point of one kernel per stage; the kernel is FP64-issue bound"}}
+                             "note": ("general gather right-hand side: one kernel per stage, every stage argument "
+                                      "materialised; HBM bound") if field else
+                                     ("all stages of an attempt are fused in one kernel, so HBM traffic is 32 B/point "
+                                      "instead of the 264 B/point of one kernel per stage; the kernel is FP64-issue bound")}}
         if world == 1 and not getattr(args, "no_cpu_baseline", False):
             line["cpu_baseline"] = cpu_baseline_large()
         print(json.dumps(line))

@@ -1041,15 +1041,51 @@ static int solve_large_impl(const ode_b200_opts* o, int64_t n, const double* y0,
     if (ph < 3) LARGE_CUDA(cudaMemcpyAsync(xr, xs, XCHG * 8, cudaMemcpyDeviceToDevice, st));  // world = 1 "all-gather"
   }
   s->fused = !s->mi.field;  // one slab: accept/reject runs inside the attempt kernel (no exchange, no control launch)
-  while (!rc) {
-    for (int q = 0; q < 4 && !rc; q++) {  // poll the done flag every 4 attempts; extra launches are no-ops
+  // A batch of 4 attempts (the done flag is polled after each batch; attempts issued after the end are no-ops;
+  // batches of 16 were slower: the graph costs more to instantiate than the fewer polls save) is
+  // captured once into a CUDA graph and replayed: the launch-bound small and mid-size systems pay one graph launch
+  // per batch instead of 8-40 kernel launches.  ODE_B200_NO_GRAPH=1 (or a failed capture) issues the launches directly.
+  const int batch = 4;
+  auto enqueue_batch = [&]() {
+    for (int q = 0; q < batch && !rc; q++) {
       LARGE_TRY(ode_b200_slab_attempt(s, xs));
       if (!s->fused) LARGE_CUDA(cudaMemcpyAsync(xr, xs, XCHG * 8, cudaMemcpyDeviceToDevice, st));
       LARGE_TRY(ode_b200_slab_control(s, xr));
     }
+  };
+  cudaGraphExec_t gexec = nullptr;
+  long long batch_launches = 0;
+  if (!rc && !getenv("ODE_B200_NO_GRAPH")) {
+    cudaGraph_t graph = nullptr;
+    const long long before = ode_b200_launch_count(0);
+    if (cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal) == cudaSuccess) {
+      enqueue_batch();
+      const cudaError_t ce = cudaStreamEndCapture(st, &graph);
+      if (ce != cudaSuccess || rc || !graph || cudaGraphInstantiate(&gexec, graph, 0) != cudaSuccess) gexec = nullptr;
+      if (graph) cudaGraphDestroy(graph);
+      if (!gexec) {  // fall back to direct launches
+        cudaGetLastError();
+        rc = 0;
+      }
+    } else {
+      cudaGetLastError();
+    }
+    batch_launches = ode_b200_launch_count(0) - before;  // counted once at capture; added per replay below
+  }
+  bool first_batch = true;
+  while (!rc) {
+    if (gexec) {
+      LARGE_CUDA(cudaGraphLaunch(gexec, st));
+      if (!first_batch)
+        for (long long q = 0; q < batch_launches; q++) note_launch();
+      first_batch = false;
+    } else {
+      enqueue_batch();
+    }
     LARGE_TRY(ode_b200_slab_poll(s, poll));
     if (poll[0] != 0.0) break;
   }
+  if (gexec) cudaGraphExecDestroy(gexec);
   LARGE_CUDA(cudaEventRecord(e1, st));
   LARGE_TRY(ode_b200_slab_get_state(s, dy));
   if (y_out) LARGE_CUDA(cudaMemcpyAsync(y_out, dy, (size_t)n * 8, cudaMemcpyDeviceToHost, st));

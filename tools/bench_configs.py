@@ -15,6 +15,12 @@ rng = np.random.default_rng(20261019)
 n = int(sys.argv[1]) if len(sys.argv) > 1 else 1 << 18
 
 
+RESULTS = []
+# algorithmic FP64 operations per attempt, where they were counted
+FLOPS = {"C3 kepler ode78 tol1e-12": 753, "C4 robertson ode23s tol1e-8": 250, "lorenz ode45": 297, "lorenz ode45_fe": 250,
+         "lorenz ode23": 152}
+
+
 def run(name, alg, F, y0, tspan, **kw):
     best = None
     for _ in range(3):
@@ -24,6 +30,9 @@ def run(name, alg, F, y0, tspan, **kw):
     print("%-34s n=%d attempts=%d (%.1f/traj, rej %.2f%%) kernel %.3f ms  %.3e attempts/s  status!=0: %d"
           % (name, len(y0), att, att / len(y0), 100.0 * r["n_reject"].sum() / att, best, att / best * 1e3,
              int((r["status"] != 0).sum())))
+    RESULTS.append({"config": name, "method": alg, "n_traj": int(len(y0)), "attempts": att, "kernel_ms": best,
+                    "attempts_per_s": att / best * 1e3,
+                    "algorithmic_tflops": (FLOPS[name] * att / best * 1e3 / 1e12) if name in FLOPS else None})
     return r
 
 
@@ -43,3 +52,8 @@ for alg in ("ode23", "ode45_fe", "ode45", "ode78"):
 y0 = np.stack([rng.uniform(-2, 2, n), rng.uniform(-2, 2, n)], 1)
 run("vdp mu=5 ode45", "ode45", m.DeviceRHS("vdp", 5.0), y0, [0.0, 20.0])
 run("vdp mu=50 ode23s", "ode23s", m.DeviceRHS("vdp", 50.0), y0, [0.0, 20.0])
+
+if os.environ.get("ODE_B200_BENCH_CONFIGS_JSON"):
+    import json
+    with open(os.environ["ODE_B200_BENCH_CONFIGS_JSON"], "w") as f:
+        json.dump(RESULTS, f, indent=1)

@@ -179,12 +179,8 @@ DM_HD double dm_exp_dd(double ehi, double elo) {
   int64_t ki = (int64_t)kd;
   double rh = dm_fma(kd, -DM_LN2N_HI, ehi); /* exact (see header comment) */
   double rl = dm_fma(kd, -DM_LN2N_LO, elo);
-  /* error-free rh + rl as a fast two-sum with the larger magnitude first (3 additions instead of 6; the operand
-     order is decided on bit patterns, so no floating-point compare is spent): same hi, same exact lo */
-  const uint64_t arh = dm_bits(rh) & 0x7fffffffffffffffULL, arl = dm_bits(rl) & 0x7fffffffffffffffULL;
-  const double big = arh >= arl ? rh : rl, sml = arh >= arl ? rl : rh;
-  double q = big + sml;
-  double ql = sml - (q - big);
+  dm_dd qq = dm_two_sum(rh, rl);
+  double q = qq.hi, ql = qq.lo;
   int j = (int)(ki & 127);
   int64_t e2 = (ki - j) / 128; /* exact: ki - j is a multiple of 128 */
   double th = DM_EXPTAB(2 * j), tl = DM_EXPTAB(2 * j + 1);

@@ -67,3 +67,25 @@ def test_solve_argument_errors_before_the_device():
     with pytest.raises(TypeError, match="no keyword arguments"):
         m.ode4(m.DeviceRHS("rotation"), [1.0, 2.0], [0.0, 1.0], reltol=1e-3)  # oderk_fixed on vectors
     assert m.shard_bounds(10, 4, 3) == (8, 10)
+
+
+def test_registered_tokens_evaluate_on_the_host_without_a_gpu():
+    """register_rhs / register_stencil / register_field only record source text (compilation happens at first use on
+    the device); the tokens carry ids, shapes and an optional host evaluator, like DeviceRHS."""
+    import ode_jl_b200 as m
+    S = m.register_stencil("cpu_lap4", "return p[0] * (w[0] + w[4]);", host=lambda w, p, t, i, n: p[0] * (w[0] + w[4]),
+                           params=(2.0,), radius=2)
+    assert S.id >= 2000 and S.is_stencil and S.radius == 2 and S.n_params == 1
+    u = np.arange(6.0)
+    assert np.array_equal(S(0.0, u), [2.0 * (u[(i - 2) % 6] + u[(i + 2) % 6]) for i in range(6)])
+    F = m.register_field("cpu_mirror", "return p[0] * (y[n - 1 - i] - y[i]);", params=(0.5,),
+                         host=lambda t, y, p: p[0] * (y[::-1] - y))
+    assert F.id >= 3000 and F.is_stencil and F.is_field and F.n_params == 1
+    assert np.array_equal(F(0.0, u), 0.5 * (u[::-1] - u))
+    R = m.register_rhs("cpu_decay", 1, 1, "f[0] = -p[0] * y[0];", params=(3.0,), host=lambda t, y, p: [-p[0] * y[0]])
+    assert 1000 <= R.id < 2000 and R.dof == 1
+    assert R(0.0, [2.0]) == [-6.0]
+    with pytest.raises(m.OdeB200Error):
+        m.register_stencil("cpu_too_wide", "return w[0];", params=(), radius=9)
+    with pytest.raises(m.OdeB200Error):
+        m.register_field("cpu_too_many", "return 0.0;", params=tuple(range(9)))

@@ -217,7 +217,9 @@ int ode_b200_register_field(const char* name, int32_t n_params, const char* rhs_
 int ode_b200_solve_ensemble(const ode_b200_opts* opts, const ode_b200_ensemble_io* io);
 /* Same, but every pointer in `io` is a device pointer on opts->device (tspan
  * included); work is enqueued on `stream` (a cudaStream_t, NULL = default
- * stream) and the call returns without synchronising. */
+ * stream) and the call returns without waiting for the kernels.  Scratch memory is
+ * taken per call from the device's stream-ordered pool, so several calls may be in
+ * flight on different streams (from one thread or many). */
 int ode_b200_solve_ensemble_dev(const ode_b200_opts* opts, const ode_b200_ensemble_io* io, void* stream);
 /* Milliseconds the last ensemble kernel of this thread took (CUDA events on its stream). */
 double ode_b200_last_kernel_ms(void);

@@ -84,30 +84,21 @@ struct Arena {
   }
 };
 thread_local Arena g_arena;
-// scratch of the device-pointer entry point (ode_b200_solve_ensemble_dev), per calling thread and device
-struct DevScratch {
-  int dev = -1;
-  unsigned long long* counter = nullptr;  // work counters of the fast and literal passes
-  int* status = nullptr;                  // when the caller passes no status buffer
-  long long status_cap = 0;
-  double* init = nullptr;                 // hinit pre-pass output
-  size_t init_cap = 0;
-  void release() {
-    if (dev >= 0) {
-      cudaSetDevice(dev);
-      if (counter) cudaFree(counter);
-      if (status) cudaFree(status);
-      if (init) cudaFree(init);
-    }
-    counter = nullptr;
-    status = nullptr;
-    init = nullptr;
-    status_cap = 0;
-    init_cap = 0;
-    dev = -1;
-  }
-};
-thread_local DevScratch g_dev_scratch;
+// Scratch of the device-pointer entry point (ode_b200_solve_ensemble_dev) -- work counters, the status buffer the two
+// passes talk through, the hinit pre-pass output -- is allocated PER CALL from the device's stream-ordered memory
+// pool (cudaMallocAsync on the caller's stream, freed in stream order after the last kernel), so any number of
+// calls may be in flight on different streams.  The pool keeps freed blocks (release threshold = max), so a
+// repeated call costs no driver allocation.
+static int pool_keep(int device) {
+  static bool done[64] = {};
+  if (device < 0 || device >= 64 || done[device]) return 0;
+  cudaMemPool_t pool = nullptr;
+  ODEB200_CUDA(cudaDeviceGetDefaultMemPool(&pool, device));
+  unsigned long long keep = ~0ULL;
+  ODEB200_CUDA(cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep));
+  done[device] = true;
+  return 0;
+}
 // page-locked staging block of the small-call path (solve_ensemble_small)
 struct SmallStage {
   char* host = nullptr;  // cudaHostAlloc, portable + mapped
@@ -140,7 +131,6 @@ void arena_release() {  // ode_b200_trim
     g_arena.cap = 0;
     g_arena.dev = -1;
   }
-  g_dev_scratch.release();
   g_small.release();
 }
 static size_t pad256(size_t b) { return (b + 255) & ~(size_t)255; }
@@ -541,36 +531,21 @@ int ode_b200_solve_ensemble_dev(const ode_b200_opts* opts, const ode_b200_ensemb
   rc = validate(opts, io, ends[0], ends[1]);
   if (rc) return rc;
   if (io->n_traj == 0) return 0;
-  DevScratch& S = g_dev_scratch;
-  if (S.dev != opts->device) {
-    S.release();
-    ODEB200_CUDA(cudaSetDevice(opts->device));
-    ODEB200_CUDA(cudaMalloc(&S.counter, 256));
-    S.dev = opts->device;
-  }
-  unsigned long long* counter = S.counter;
+  rc = pool_keep(opts->device);
+  if (rc) return rc;
+  cudaStream_t st = (cudaStream_t)stream;
   ode_b200_ensemble_io d = *io;
-  if (!d.status && is_adaptive_rk(opts->method)) {  // the fast and literal passes talk through `status`
-    if (S.status_cap < io->n_traj) {
-      if (S.status) cudaFree(S.status);
-      S.status = nullptr;
-      S.status_cap = 0;
-      ODEB200_CUDA(cudaMalloc(&S.status, (size_t)io->n_traj * sizeof(int)));
-      S.status_cap = io->n_traj;
-    }
-    d.status = S.status;
-  }
+  const bool need_status = !d.status && is_adaptive_rk(opts->method);  // the fast and literal passes talk through `status`
+  const size_t status_bytes = need_status ? pad256((size_t)io->n_traj * sizeof(int)) : 0;
   const size_t want = init_scratch_doubles(opts, &d);
-  if (want > S.init_cap) {
-    if (S.init) cudaFree(S.init);
-    S.init = nullptr;
-    S.init_cap = 0;
-    ODEB200_CUDA(cudaMalloc(&S.init, want * sizeof(double)));
-    S.init_cap = want;
-  }
-  double* init_scratch = S.init;
-  return launch_ensemble(opts, &d, counter, (cudaStream_t)stream, true, want > 0 ? init_scratch : nullptr,
-                         fetch_upar ? upar : nullptr);
+  char* blk = nullptr;
+  ODEB200_CUDA(cudaMallocAsync((void**)&blk, 256 + status_bytes + pad256(want * sizeof(double)), st));
+  unsigned long long* counter = reinterpret_cast<unsigned long long*>(blk);
+  if (need_status) d.status = reinterpret_cast<int*>(blk + 256);
+  double* init_scratch = want > 0 ? reinterpret_cast<double*>(blk + 256 + status_bytes) : nullptr;
+  rc = launch_ensemble(opts, &d, counter, st, true, init_scratch, fetch_upar ? upar : nullptr);
+  cudaFreeAsync(blk, st);  // stream-ordered: after the kernels above
+  return rc;
 }
 
 // ---- small calls (a single system, a handful of trajectories) -----------------------------------

@@ -54,9 +54,9 @@ __global__ void __launch_bounds__(256) large_hermite_kernel(double* const Y0, do
 
 // ---- hinit (src/ODE.jl:85-112) in phases ------------------------------------------
 // pack the H edge values of an interior array into slot `slot` (0: A, 1: B)
+// (H can exceed the 32 threads of the launch: ode78 with a radius-3/4 stencil has H = 40 / 52)
 __global__ void pack_edges_kernel(const double* a, double* xsend, long long n, int H, int slot) {
-  int j = threadIdx.x;
-  if (j < H) {
+  for (int j = threadIdx.x; j < H; j += blockDim.x) {
     xsend[XS_EDGE + 2 * H * slot + j] = a[H + j];
     xsend[XS_EDGE + 2 * H * slot + H + j] = a[H + (n - H) + j];
   }
@@ -65,8 +65,7 @@ __global__ void large_ghost_kernel(double* a, const double* xrecv, long long n, 
   const int lr = (rank + world - 1) % world, rr = (rank + 1) % world;
   const double* xl = xrecv + (long long)lr * XCHG + XS_EDGE + 2 * H * slot;
   const double* xr = xrecv + (long long)rr * XCHG + XS_EDGE + 2 * H * slot;
-  int j = threadIdx.x;
-  if (j < H) {
+  for (int j = threadIdx.x; j < H; j += blockDim.x) {
     a[j] = xl[H + j];
     a[n + H + j] = xr[j];
   }
@@ -403,7 +402,8 @@ int ode_b200_slab_create(const ode_b200_opts* o, int64_t n_local, int64_t n_glob
     for (int q = 0; q < 2 && ok; q++) ok = ok && cudaMalloc(&s->T[q], padded) == cudaSuccess;
   }
   ok = ok && cudaMalloc(&s->ctl, sizeof(LargeCtl)) == cudaSuccess;
-  ok = ok && cudaMalloc(&s->part, (size_t)s->grid * 4 * sizeof(double)) == cudaSuccess;
+  // per-CTA error partials: the fast and the literal attempt kernels may get different occupancies
+  ok = ok && cudaMalloc(&s->part, (size_t)(s->grid > s->grid_literal ? s->grid : s->grid_literal) * 4 * sizeof(double)) == cudaSuccess;
   ok = ok && cudaMalloc(&s->ipart, (size_t)s->init_blocks * 2 * sizeof(double)) == cudaSuccess;
   if (!ok) {
     cudaGetLastError();

@@ -157,6 +157,11 @@ __device__ __forceinline__ void large_control_body(const ControlArgs& C) {
   if (ctl->done) return;
   if (threadIdx.x == 0) {
     refresh = 0;
+    // No output rows unless THIS invocation accepts a step: large_hermite_kernel runs after every control
+    // invocation (rejected attempts and literal-repeat requests included) and must then find nothing to do --
+    // the step-start arrays it would read have been overwritten by the rejected / non-finite trial state.
+    ctl->out_lo = ctl->out_hi = 0;
+    ctl->out_end = 0;
     dm_dd tot;
     tot.hi = 0.0;
     tot.lo = 0.0;
@@ -212,7 +217,6 @@ __device__ __forceinline__ void large_control_body(const ControlArgs& C) {
     }
     ctl->trace_n += 1;
     ctl->accepted_last = accept ? 1 : 0;
-    ctl->out_lo = ctl->out_hi = 0;
     if (accept) {
       ctl->nacc += 1;
       if (C.tq && !C.out_times) {  // :321-326  output at all new times which are < t+dt (all remaining ones on the last step)

@@ -398,3 +398,147 @@ def test_fixed_step_rk_on_a_large_state(method):
     t, y = getattr(m, method)(F, y0, ts)
     o = O.solve_user(method, nonlocal_host, y0, ts, [0.8, 0.3, 0.5])
     assert np.array_equal(t, o.t) and np.array_equal(y, o.y)
+
+
+# ---- C5 at its stated sizes ("N = 2^16 ... 2^20 full span and N = 2^26 for the first 5 attempts")
+def test_reaction_diffusion_2_20_full_span_bit_exact():
+    n = 1 << 20
+    y0 = u0(n)
+    got = m.solve_large("ode45", m.DeviceRHS("reaction_diffusion", *RD), y0, [0.0, 20.0], trace=True)
+    O.use_all_cores()
+    ref = oracle_rd("ode45", y0, [0.0, 20.0])
+    assert got["status"] == 0 and got["t_final"] == ref.t[-1]
+    assert (got["n_accept"], got["n_reject"], got["n_rhs"]) == (ref.n_accept, ref.n_reject, ref.n_rhs)
+    assert np.array_equal(got["trace"], ref.trace)
+    assert np.array_equal(got["y"], ref.y[-1])
+
+
+def test_reaction_diffusion_2_26_first_five_attempts_bit_exact():
+    """BASELINE.json configs[4] at its full size N = 2^26: the first five step attempts (t, dt, err, accept) and the
+    state they lead to, bit for bit against the oracle (which takes ~20 s for them on 8 cores)."""
+    n = 1 << 26
+    y0 = u0(n)
+    got = m.solve_large("ode45", m.DeviceRHS("reaction_diffusion", *RD), y0, [0.0, 20.0], trace=True, max_steps=5)
+    O.use_all_cores()
+    ref = oracle_rd("ode45", y0, [0.0, 20.0], max_steps=5)
+    assert got["status"] == ref.status == 2  # the max_steps guard
+    assert (got["n_accept"], got["n_reject"], got["n_rhs"]) == (ref.n_accept, ref.n_reject, ref.n_rhs)
+    assert got["n_accept"] + got["n_reject"] == 5
+    assert np.array_equal(got["trace"], ref.trace)
+    assert got["t_final"] == ref.t[-1]
+    assert np.array_equal(got["y"], ref.y[-1])
+    m.lib().ode_b200_trim()
+
+
+# ---- wide ghost zones: ode78 with a radius-3 / radius-4 stencil has H = 40 / 52 > one warp ------------------------
+def _wide_stencil(radius):
+    """A (2R+1)-point smoothing stencil with index- and time-dependent weights; CUDA body and host twin."""
+    terms = " + ".join("(%.17g * w[%d])" % (1.0 / (1 + abs(k - radius)), k) for k in range(2 * radius + 1))
+    norm = sum(1.0 / (1 + abs(k - radius)) for k in range(2 * radius + 1))
+    body = """
+const double x = (double)i / (double)n;
+const double avg = (%s) / %.17g;
+return (p[0] * (1.0 + 0.25 * x)) * (avg - w[%d]) + (p[1] * t) * (w[%d] * (1.0 - w[%d]));
+""" % (terms, norm, radius, radius, radius)
+
+    def host(w, p, t, i, nn):
+        x = float(i) / float(nn)
+        s = None
+        for k in range(2 * radius + 1):
+            term = (1.0 / (1 + abs(k - radius))) * w[k]
+            s = term if s is None else s + term
+        avg = s / norm
+        return (p[0] * (1.0 + 0.25 * x)) * (avg - w[radius]) + (p[1] * t) * (w[radius] * (1.0 - w[radius]))
+
+    return body, host
+
+
+@pytest.mark.parametrize("radius", [3, 4])
+def test_ode78_wide_stencil_ghost_zone_beyond_one_warp(radius):
+    """H = 40 (radius 3) and H = 52 (radius 4): the hinit edge packing / ghost fill must cover all H cells, on one
+    slab (periodic wrap) and across two slabs.  Oracle: the C++ restatement driven by the python twin of the stencil."""
+    import torch
+    n = 1500
+    y0 = u0(n) + 0.03 * np.cos(2 * np.pi * 5 * np.arange(n) / n)
+    body, host = _wide_stencil(radius)
+    F = m.register_stencil("wide_r%d_ode78" % radius, body, params=(0.9, 0.4), radius=radius)
+    ts = [0.0, 3.0]
+    got = m.solve_large("ode78", F, y0, ts, trace=True)
+    ref = O.solve_user_stencil("ode78", host, y0, ts, [0.9, 0.4], radius=radius, trace=True, points="final")
+    assert np.array_equal(got["trace"], ref.trace)
+    assert np.array_equal(got["y"], ref.y[-1])
+    assert (got["n_accept"], got["n_reject"], got["n_rhs"]) == (ref.n_accept, ref.n_reject, ref.n_rhs)
+    dev = torch.device("cuda", 0)
+    st = torch.cuda.current_stream(dev).cuda_stream
+    world = 2
+    engines, sends, recvs, parts = [], [], [], []
+    for r in range(world):
+        lo, hi = m.shard_bounds(n, world, r)
+        e = m.CudaSlabEngine("ode78", F, hi - lo, n, r, world, ts, st)
+        yl = torch.tensor(y0[lo:hi], dtype=torch.float64, device=dev)
+        e.set_state(yl.data_ptr())
+        engines.append(e)
+        parts.append(yl)
+        sends.append(torch.zeros(m._lib.XCHG_DOUBLES, dtype=torch.float64, device=dev))
+        recvs.append(torch.zeros(world, m._lib.XCHG_DOUBLES, dtype=torch.float64, device=dev))
+    ctls = lockstep(engines, sends, recvs)
+    assert ctls[0]["ghost"] == (40 if radius == 3 else 52)
+    out = []
+    for e, yl in zip(engines, parts):
+        o = torch.empty_like(yl)
+        e.get_state(o.data_ptr())
+        out.append(o)
+    torch.cuda.synchronize()
+    assert (ctls[0]["n_accept"], ctls[0]["n_reject"]) == (ref.n_accept, ref.n_reject)
+    assert np.array_equal(torch.cat(out).cpu().numpy(), ref.y[-1])
+    for e in engines:
+        e.close()
+
+
+# ---- output rows around rejected attempts ---------------------------------------------------------------------------
+@pytest.mark.parametrize("points", ["all", "specified"])
+def test_large_output_rows_survive_rejected_attempts(points):
+    """Dense tspan (almost every accepted step holds an interior output point) on a run with rejected attempts:
+    a rejection right after such a step must not touch the rows already written (the control kernel clears its
+    row selection on every invocation)."""
+    n = 1 << 14
+    y0 = u0(n)
+    ts = np.linspace(0.0, 20.0, 161)
+    F = m.DeviceRHS("reaction_diffusion", *RD)
+    r = m.solve_large("ode45", F, y0, ts, points=points, trace=True)
+    ref = O.solve("ode45", "reaction_diffusion", y0, ts, RD, points=points, trace=True)
+    assert ref.n_reject >= 1
+    assert np.array_equal(r["trace"], ref.trace)
+    assert np.array_equal(r["t"], ref.t) and np.array_equal(r["y"], ref.y)
+
+
+def test_slab_points_specified_with_rejections_two_ranks():
+    """The same through two slab sessions with the explicit exchange (the non-fused control kernel)."""
+    import torch
+    n = 1 << 14
+    y0 = u0(n)
+    ts = np.linspace(0.0, 20.0, 41)
+    F = m.DeviceRHS("reaction_diffusion", *RD)
+    ref = O.solve("ode45", "reaction_diffusion", y0, ts, RD, points="specified")
+    assert ref.n_reject >= 1
+    dev = torch.device("cuda", 0)
+    st = torch.cuda.current_stream(dev).cuda_stream
+    world = 2
+    engines, sends, recvs, outs = [], [], [], []
+    for r in range(world):
+        lo, hi = m.shard_bounds(n, world, r)
+        e = m.CudaSlabEngine("ode45", F, hi - lo, n, r, world, [0.0, 20.0], st, points="specified")
+        o = torch.zeros(len(ts), hi - lo, dtype=torch.float64, device=dev)
+        e.set_output(ts, o.data_ptr())
+        yl = torch.tensor(y0[lo:hi], dtype=torch.float64, device=dev)
+        e.set_state(yl.data_ptr())
+        engines.append(e)
+        outs.append(o)
+        sends.append(torch.zeros(m._lib.XCHG_DOUBLES, dtype=torch.float64, device=dev))
+        recvs.append(torch.zeros(world, m._lib.XCHG_DOUBLES, dtype=torch.float64, device=dev))
+    ctls = lockstep(engines, sends, recvs)
+    torch.cuda.synchronize()
+    assert (ctls[0]["n_accept"], ctls[0]["n_reject"]) == (ref.n_accept, ref.n_reject)
+    assert np.array_equal(torch.cat(outs, 1).cpu().numpy(), ref.y)
+    for e in engines:
+        e.close()

@@ -43,6 +43,10 @@ extern "C" {
 #define ODE_B200_ABI_VERSION 1
 /* doubles per rank in the exchange buffer of the slab sessions (see ode_b200_slab_*) */
 #define ODE_B200_XCHG_DOUBLES 264
+/* most slabs (GPUs of one node) that can exchange their records over peer memory (ode_b200_slab_peer_*) */
+#define ODE_B200_MAX_PEERS 16
+/* bytes of the opaque handle ode_b200_slab_peer_alloc exports for the other processes (a cudaIpcMemHandle_t) */
+#define ODE_B200_PEER_HANDLE_BYTES 64
 /* limits of a registered large-system stencil (ode_b200_register_stencil) */
 #define ODE_B200_STENCIL_MAX_RADIUS 4
 #define ODE_B200_STENCIL_MAX_NP 8
@@ -100,7 +104,8 @@ typedef enum {
   ODE_B200_ST_MAXSTEPS = 2,  /* max_steps guard hit (the reference would keep looping) */
   ODE_B200_ST_NONFINITE = 3, /* dt became NaN/Inf (the reference would loop forever) */
   ODE_B200_ST_SINGULAR = 4,  /* ode23s: zero pivot in W = I - h*d*J (Julia raises SingularException) */
-  ODE_B200_ST_OVERFLOW = 5   /* points buffer too small; n_points holds the required count */
+  ODE_B200_ST_OVERFLOW = 5,  /* points buffer too small; n_points holds the required count */
+  ODE_B200_ST_EXCHANGE = 6   /* domain-decomposed system: a peer's exchange record did not arrive in time */
 } ode_b200_status;
 
 /* error codes */
@@ -137,8 +142,20 @@ typedef struct {
                               finishes (no copy-back phase: ~6 % less end-to-end time on one GPU; no gain
                               when many GPUs move data through one host at once -- measured with 8).
                               Pageable buffers are always staged. */
-  int32_t reserved[6];
+  int32_t n_gpus;    /* multi-GPU fan-out inside the library: 0 or 1 = the one device `device`;
+                        N > 1 = devices device .. device+N-1 of this node.  ode_b200_solve_ensemble shards the
+                        trajectories (contiguous blocks, one host thread per GPU, results into disjoint slices of the
+                        caller's buffers, no collective); ode_b200_solve_large splits the grid into N slabs that exchange
+                        their per-attempt records over NVLink peer memory (see ode_b200_solve_large_multi). */
+  int32_t fp_mode;   /* the `strict_fp` switch of SURVEY.md section 8b.  ODE_B200_FP_STRICT (0, default): no fused
+                        multiply-add, reference association order -- the parity mode, bit-identical to the oracle.
+                        ODE_B200_FP_FMA (1): the same kernels compiled with FMA contraction (fewer FP64 instructions,
+                        results differ from the reference in the last bits; step counts can differ).  Opt-in, ensemble
+                        ode45 family only; anything without an FMA build fails with ODE_B200_E_UNSUPPORTED. */
+  int32_t reserved[4];
 } ode_b200_opts;
+#define ODE_B200_FP_STRICT 0
+#define ODE_B200_FP_FMA 1
 
 /* Ensemble I/O.  Host arrays are row-major [trajectory][...]; NULL outputs are
  * skipped.  `tspan` is shared by all trajectories (tspan[0] = start,
@@ -255,6 +272,19 @@ int ode_b200_solve_large(const ode_b200_opts* opts, int64_t n, const double* y0,
                          double t0, double tend, double* y_out, ode_b200_large_stats* stats,
                          double* trace, int64_t trace_cap, int64_t* trace_n);
 
+/* The same call fanned out over n_gpus devices of this process (devices[] = CUDA ordinals, NULL = opts->device ..
+ * opts->device + n_gpus - 1; n_gpus <= ODE_B200_MAX_PEERS, every pair needs peer access, i.e. NVLink/NVSwitch or
+ * PCIe P2P).  The reference has one Vector in one process (oderk_adapt, src/runge_kutta.jl:232-369); here the
+ * periodic grid is cut into n_gpus contiguous slabs (the first n % n_gpus one point longer).  Per step attempt every
+ * device runs one kernel whose last thread block writes the slab's record (exactly accumulated error partial, NaN
+ * flag, slab-edge values) into every peer's HBM, waits for theirs and runs the step controller on the gathered
+ * data, so all devices take the same decision and the result is the single-GPU result bit for bit.  y0 / y_out
+ * are host arrays of n doubles (each device reads and writes its own slice).  ode_b200_solve_large with
+ * opts->n_gpus > 1 calls this. */
+int ode_b200_solve_large_multi(const ode_b200_opts* opts, int32_t n_gpus, const int32_t* devices, int64_t n,
+                               const double* y0, const double* params, double t0, double tend, double* y_out,
+                               ode_b200_large_stats* stats, double* trace, int64_t trace_cap, int64_t* trace_n);
+
 /* oderk_fixed (src/runge_kutta.jl:176-212: ode1, ode2_midpoint, ode2_heun, ode4) and ode4ms (src/ODE.jl:175-212) on a
  * dof = N state with a stencil or field right-hand side: one step per tspan interval, one kernel per stage.
  * pts_y (optional) is [n_tspan][n] and
@@ -319,6 +349,24 @@ int ode_b200_slab_set_offset(ode_b200_slab* s, int64_t first_global_index);
  * rows -- one copy and one dependent launch less per attempt.  Off by default (the decomposed path needs the
  * all-gather between the two). */
 int ode_b200_slab_set_fused(ode_b200_slab* s, int32_t on);
+/* Exchange over peer memory instead of a caller-side all-gather: the slabs of one node (one process with several
+ * devices, or one process per device) write their records straight into each other's HBM from inside the attempt
+ * kernel (NVLink peer stores + a flag per record), and the kernel's last thread block goes on to run the step
+ * controller -- no collective library call, no host round trip per attempt.
+ *   1. every rank: ode_b200_slab_peer_alloc -> its receive block; `ipc_handle_out` (ODE_B200_PEER_HANDLE_BYTES bytes,
+ *      may be NULL) is what the OTHER PROCESSES need to map it, `local_ptr_out` (may be NULL) what other devices of
+ *      THIS process need (after cudaDeviceEnablePeerAccess);
+ *   2. the caller passes the handles / pointers around (once per session), all ranks reach a barrier;
+ *   3. every rank: ode_b200_slab_peer_connect with either `ipc_handles` [world][ODE_B200_PEER_HANDLE_BYTES] or
+ *      `ptrs` [world] (entry `rank` is ignored); then another barrier before the first ode_b200_slab_run.
+ * A peer that stops answering ends the integration with ODE_B200_ST_EXCHANGE after ODE_B200_PEER_TIMEOUT_MS
+ * (environment, default 5000). */
+int ode_b200_slab_peer_alloc(ode_b200_slab* s, void* ipc_handle_out, void** local_ptr_out);
+int ode_b200_slab_peer_connect(ode_b200_slab* s, const void* ipc_handles, void* const* ptrs);
+/* The whole integration of this rank's slab in one call: hinit, then batches of attempts replayed from a CUDA graph
+ * until the device-side done flag is set.  For a single slab (world = 1) or slabs connected over peer memory; all
+ * ranks call it at the same time.  ctl_out[16] as ode_b200_slab_poll; kernel_ms (optional) = device time. */
+int ode_b200_slab_run(ode_b200_slab* s, double* ctl_out /*[16]*/, double* kernel_ms);
 /* optional attempt trace on the device: rows (t, dt, err, accepted) */
 int ode_b200_slab_set_trace(ode_b200_slab* s, double* trace_dev, int64_t trace_cap);
 int ode_b200_slab_get_state(ode_b200_slab* s, double* y_local_dev);

@@ -17,9 +17,12 @@ METHODS = dict(ode1=0, ode2_midpoint=1, ode2_heun=2, ode4=3, ode21=4, ode23=5, o
 RHS = dict(linear=0, const=1, timelin=2, rotation=3, lorenz=4, vdp=5, robertson=6, kepler=7, reaction_diffusion=8,
            reaction_diffusion_field=9)
 POINTS = {"all": 0, "specified": 1, "final": 2}
-STATUS = {0: "OK", 1: "MINSTEP", 2: "MAXSTEPS", 3: "NONFINITE", 4: "SINGULAR", 5: "OVERFLOW"}
+STATUS = {0: "OK", 1: "MINSTEP", 2: "MAXSTEPS", 3: "NONFINITE", 4: "SINGULAR", 5: "OVERFLOW", 6: "EXCHANGE"}
 E_ZERO_SPAN, E_INITSTEP, E_POINTS, E_NOT_ADAPTIVE, E_NO_DEVICE, E_UNSUPPORTED = -2, -3, -4, -5, -6, -8
 XCHG_DOUBLES = 264
+PEER_HANDLE_BYTES = 64
+MAX_PEERS = 16
+FP_STRICT, FP_FMA = 0, 1
 
 dp = C.POINTER(C.c_double)
 ip = C.POINTER(C.c_int32)
@@ -32,7 +35,8 @@ class Opts(C.Structure):
                 ("device", C.c_int32), ("max_steps", C.c_int64),
                 ("reltol", C.c_double), ("abstol", C.c_double), ("minstep", C.c_double),
                 ("maxstep", C.c_double), ("initstep", C.c_double),
-                ("mathmode", C.c_int32), ("host_output", C.c_int32), ("reserved", C.c_int32 * 6)]
+                ("mathmode", C.c_int32), ("host_output", C.c_int32), ("n_gpus", C.c_int32), ("fp_mode", C.c_int32),
+                ("reserved", C.c_int32 * 4)]
 
 
 class EnsembleIO(C.Structure):
@@ -125,6 +129,11 @@ def lib():
     L.ode_b200_slab_attempt.argtypes = [C.c_void_p, C.c_void_p]
     L.ode_b200_slab_control.argtypes = [C.c_void_p, C.c_void_p]
     L.ode_b200_slab_poll.argtypes = [C.c_void_p, dp]
+    L.ode_b200_solve_large_multi.argtypes = [C.POINTER(Opts), C.c_int32, ip, C.c_int64, dp, dp, C.c_double, C.c_double, dp,
+                                             C.POINTER(LargeStats), dp, C.c_int64, lp]
+    L.ode_b200_slab_peer_alloc.argtypes = [C.c_void_p, C.c_void_p, C.POINTER(C.c_void_p)]
+    L.ode_b200_slab_peer_connect.argtypes = [C.c_void_p, C.c_void_p, C.POINTER(C.c_void_p)]
+    L.ode_b200_slab_run.argtypes = [C.c_void_p, dp, dp]
     L.ode_b200_slab_free.argtypes = [C.c_void_p]
     L.ode_b200_slab_free.restype = None
     L.ode_b200_host_alloc.argtypes = [C.c_size_t]

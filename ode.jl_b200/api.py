@@ -31,7 +31,7 @@ def _points(points):
 
 def make_opts(method, F, tspan, *, reltol=1e-5, abstol=1e-8, minstep=None, maxstep=None, initstep=0.0,
               points="all", norm=None, jacobian=None, device=0, max_steps=0, params_stride=0, dof=None,
-              direct_output=False):
+              direct_output=False, n_gpus=1, strict_fp=True):
     """ode_b200_opts with the reference's defaults (src/runge_kutta.jl:233-239, src/ODE.jl:253-259)."""
     if not isinstance(F, DeviceRHS):
         raise TypeError("F must be a registered DeviceRHS (a host closure cannot run on the device; "
@@ -62,6 +62,8 @@ def make_opts(method, F, tspan, *, reltol=1e-5, abstol=1e-8, minstep=None, maxst
     o.initstep = float(initstep)
     o.mathmode = 0
     o.host_output = 1 if direct_output else 0  # kernel writes results into pinned `out=` buffers itself
+    o.n_gpus = int(n_gpus)  # fan-out inside the library over devices device .. device + n_gpus - 1
+    o.fp_mode = _lib.FP_STRICT if strict_fp else _lib.FP_FMA  # strict_fp=False: opt-in FMA contraction, not bit-exact
     return o
 
 

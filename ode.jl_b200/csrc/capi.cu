@@ -10,7 +10,12 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <condition_variable>
+#include <functional>
+#include <mutex>
 #include <new>
+#include <string>
+#include <thread>
 #include <vector>
 
 #include "dispatch.cuh"
@@ -52,7 +57,7 @@ struct Arena {
         cap = 0;
       }
       if (dev != device && stream) {  // streams and events belong to the device they were created on
-        cudaSetDevice(dev);
+        if (dev >= 0) cudaSetDevice(dev);
         cudaStreamDestroy(stream);
         cudaStreamDestroy(stream2);
         cudaEventDestroy(ev_in);
@@ -124,12 +129,16 @@ struct SmallStage {
 thread_local SmallStage g_small;
 static const size_t kSmallCallBytes = 192u << 10;
 void arena_release() {  // ode_b200_trim
-  if (g_arena.base) {
+  if (g_arena.dev >= 0) {
     cudaSetDevice(g_arena.dev);
-    cudaFree(g_arena.base);
-    g_arena.base = nullptr;
-    g_arena.cap = 0;
-    g_arena.dev = -1;
+    if (g_arena.base) cudaFree(g_arena.base);
+    if (g_arena.stream) {
+      cudaStreamDestroy(g_arena.stream);
+      cudaStreamDestroy(g_arena.stream2);
+      cudaEventDestroy(g_arena.ev_in);
+      cudaEventDestroy(g_arena.ev_done2);
+    }
+    g_arena = Arena();
   }
   g_small.release();
 }
@@ -629,8 +638,130 @@ static int solve_ensemble_small(const ode_b200_opts* opts, const ode_b200_ensemb
   return 0;
 }
 
+// ---- ensembles on several GPUs of this process (opts->n_gpus > 1) ---------------------------------------------------
+// Trajectories are independent (the reference has no cross-trajectory state), so the ensemble is cut into n_gpus
+// contiguous blocks; one persistent host thread per device runs the single-GPU path on its block, reading its
+// slice of the caller's inputs and writing its slice of the caller's outputs.  No collective, no gather step:
+// when the call returns the caller's buffers hold the whole ensemble.
+namespace {
+struct FanWorker {
+  std::thread th;
+  std::mutex mu;
+  std::condition_variable cv;
+  std::function<void()> job;
+  bool has_job = false, stop = false;
+  void loop() {
+    std::unique_lock<std::mutex> lk(mu);
+    while (true) {
+      cv.wait(lk, [&] { return has_job || stop; });
+      if (stop) return;
+      std::function<void()> j = std::move(job);
+      lk.unlock();
+      j();
+      lk.lock();
+      has_job = false;
+      cv.notify_all();
+    }
+  }
+  void submit(std::function<void()> j) {
+    std::unique_lock<std::mutex> lk(mu);
+    job = std::move(j);
+    has_job = true;
+    cv.notify_all();
+  }
+  void wait() {
+    std::unique_lock<std::mutex> lk(mu);
+    cv.wait(lk, [&] { return !has_job; });
+  }
+};
+std::mutex g_fan_mu;                      // one fan-out at a time per process (the workers' arenas are per device)
+std::vector<FanWorker*> g_fan_workers;    // index = device ordinal; threads live until the process ends
+FanWorker* fan_worker(int device) {
+  if ((int)g_fan_workers.size() <= device) g_fan_workers.resize(device + 1, nullptr);
+  if (!g_fan_workers[device]) {
+    FanWorker* w = new FanWorker();
+    w->th = std::thread([w] { w->loop(); });
+    w->th.detach();
+    g_fan_workers[device] = w;
+  }
+  return g_fan_workers[device];
+}
+}  // namespace
+
+static int solve_ensemble_fanout(const ode_b200_opts* opts, const ode_b200_ensemble_io* io) {
+  const int G = opts->n_gpus;
+  int cnt = 0;
+  if (cudaGetDeviceCount(&cnt) != cudaSuccess || cnt <= 0) {
+    cudaGetLastError();
+    return set_err(ODE_B200_E_NO_DEVICE, "no CUDA device available; libode_b200 has no CPU fallback");
+  }
+  if (opts->device < 0 || opts->device + G > cnt)
+    return set_err(ODE_B200_E_INVALID, "n_gpus %d from device %d: only %d devices visible", G, opts->device, cnt);
+  if (io->n_tspan < 2 || !io->tspan) return set_err(ODE_B200_E_INVALID, "tspan needs at least 2 entries");
+  int rc = validate(opts, io, io->tspan[0], io->tspan[io->n_tspan - 1]);
+  if (rc) return rc;
+  const long long n = io->n_traj;
+  const int D = opts->dof;
+  std::lock_guard<std::mutex> fan_lock(g_fan_mu);
+  std::vector<int> rcs(G, 0);
+  std::vector<std::string> errs(G);
+  std::vector<double> kms(G, 0.0);
+  std::vector<long long> launches(G, 0);
+  for (int g = 0; g < G; g++) {
+    const long long lo = n * g / G, hi = n * (g + 1) / G;
+    ode_b200_opts og = *opts;
+    og.device = opts->device + g;
+    og.n_gpus = 1;
+    ode_b200_ensemble_io ig = *io;
+    ig.n_traj = hi - lo;
+    ig.y0 = io->y0 + lo * D;
+    if (io->params && opts->params_stride) ig.params = io->params + lo * opts->params_stride;
+    if (io->t_final) ig.t_final = io->t_final + lo;
+    if (io->y_final) ig.y_final = io->y_final + lo * D;
+    if (io->n_accept) ig.n_accept = io->n_accept + lo;
+    if (io->n_reject) ig.n_reject = io->n_reject + lo;
+    if (io->n_rhs) ig.n_rhs = io->n_rhs + lo;
+    if (io->status) ig.status = io->status + lo;
+    if (io->pts_y) {
+      ig.pts_t = io->pts_t + lo * io->pts_cap;
+      ig.pts_y = io->pts_y + lo * io->pts_cap * D;
+      if (io->pts_n) ig.pts_n = io->pts_n + lo;
+    }
+    if (io->trace && io->trace_traj >= lo && io->trace_traj < hi) {
+      ig.trace_traj = io->trace_traj - lo;
+    } else {
+      ig.trace = nullptr;
+      ig.trace_n = nullptr;
+      ig.trace_traj = -1;
+    }
+    FanWorker* w = fan_worker(og.device);
+    int* prc = &rcs[g];
+    std::string* perr = &errs[g];
+    double* pk = &kms[g];
+    long long* pl = &launches[g];
+    w->submit([og, ig, prc, perr, pk, pl]() {
+      ode_b200_launch_count(1);
+      *prc = ig.n_traj > 0 ? ode_b200_solve_ensemble(&og, &ig) : 0;
+      if (*prc) *perr = ode_b200_last_error();
+      *pk = ig.n_traj > 0 ? ode_b200_last_kernel_ms() : 0.0;
+      *pl = ode_b200_launch_count(1);
+    });
+  }
+  for (int g = 0; g < G; g++) fan_worker(opts->device + g)->wait();
+  double km = 0.0;
+  for (int g = 0; g < G; g++) {
+    km = kms[g] > km ? kms[g] : km;
+    g_launches += launches[g];
+    if (rcs[g] && !rc) rc = set_err(rcs[g], "device %d: %s", opts->device + g, errs[g].c_str());
+  }
+  g_last_kernel_ms = km;  // the slowest device's kernel
+  g_ev_pending = false;
+  return rc;
+}
+
 int ode_b200_solve_ensemble(const ode_b200_opts* opts, const ode_b200_ensemble_io* io) {
   if (!opts || !io) return set_err(ODE_B200_E_INVALID, "null opts/io");
+  if (opts->n_gpus > 1) return solve_ensemble_fanout(opts, io);
   int rc = device_ok(opts->device);
   if (rc) return rc;
   if (io->n_tspan < 2 || !io->tspan) return set_err(ODE_B200_E_INVALID, "tspan needs at least 2 entries");
@@ -802,6 +933,7 @@ int ode_b200_solve_single(const ode_b200_opts* opts, const double* y0, const dou
   if (opts->points == ODE_B200_POINTS_FINAL) return set_err(ODE_B200_E_POINTS, "Unrecognized option points==final");
   ode_b200_opts o = *opts;
   o.params_stride = 0;
+  o.n_gpus = 1;  // one trajectory lives on one device
   long long cap = n_tspan + 1024;
   const bool fixed = is_fixed_step(o.method);
   if (fixed || o.points == ODE_B200_POINTS_SPECIFIED) cap = n_tspan;

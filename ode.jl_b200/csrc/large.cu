@@ -71,6 +71,22 @@ __global__ void large_ghost_kernel(double* a, const double* xrecv, long long n, 
   }
 }
 
+// The all-gather of the slabs' records as its own launch: the hinit phases, and the attempts when the step
+// controller is not fused into the attempt kernel (ODE_B200_PEER_FUSED=0).  Leaves a copy of the gathered records
+// where the kernels launched after it expect them (P.gathered = the session's xr buffer).
+__global__ void __launch_bounds__(128) peer_exchange_kernel(const PeerXchg P, const double* xsend, int len, LargeCtl* ctl) {
+  if (ctl->done) return;
+  const double* g = peer_all_gather(P, xsend, len);
+  if (!g) {
+    if (threadIdx.x == 0) {
+      ctl->status = ODE_B200_ST_EXCHANGE;
+      ctl->done = 1;
+    }
+    return;
+  }
+  for (int j = threadIdx.x; j < P.world * XCHG; j += blockDim.x) P.gathered[j] = g[j];
+}
+
 __global__ void reduce_max_kernel(const double* part, int nblocks, int ncol, double* xsend) {
   // one warp; NaN-propagating max of each column
   for (int c = 0; c < ncol; c++) {
@@ -275,15 +291,23 @@ struct ode_b200_slab {
   double* KS[FIELD_MAX_STAGES] = {};  // field path: middle stages
   double* T[2] = {nullptr, nullptr};  // field path: stage-argument ping-pong
   int field_grid = 1;
-  bool fused = false;  // single slab, stencil path: the attempt kernel's last CTA runs the step controller
+  bool fused = false;  // stencil path: the attempt kernel's last CTA runs the step controller (single slab, or peers)
   int init_blocks = 0;
   LargeCtl host_ctl;
+  // exchange buffers owned by the session (ode_b200_slab_run; the step-wise API takes the caller's)
+  double *xs = nullptr, *xr = nullptr;
+  // exchange over peer memory (ode_b200_slab_peer_*)
+  bool peer_on = false;
+  double* peer_block = nullptr;              // this rank's receive block (cudaMalloc: exportable with CUDA IPC)
+  unsigned long long* peer_epoch = nullptr;  // inside peer_block, after the flags
+  void* peer_ipc[PEER_MAX] = {};             // blocks opened with cudaIpcOpenMemHandle (closed on free)
+  PeerXchg px;
 };
 
 struct LargeCache {
   ode_b200_slab* s = nullptr;
   cudaStream_t st = nullptr;
-  double *dy = nullptr, *xs = nullptr, *xr = nullptr;
+  double* dy = nullptr;
   int device = -1, method = -1, rhs = -1;
   long long n = 0;
 };
@@ -509,8 +533,9 @@ int ode_b200_slab_set_offset(ode_b200_slab* s, int64_t first_global_index) {
 int ode_b200_slab_set_fused(ode_b200_slab* s, int32_t on) {
   int rc = slab_check(s);
   if (rc) return rc;
-  if (on && (s->world != 1 || s->mi.field))
-    return set_err(ODE_B200_E_UNSUPPORTED, "the step controller can run inside the attempt kernel for a single stencil slab only");
+  if (on && ((s->world != 1 && !s->peer_on) || s->mi.field))
+    return set_err(ODE_B200_E_UNSUPPORTED, "the step controller can run inside the attempt kernel for a single stencil slab, or "
+                                           "for slabs connected over peer memory (ode_b200_slab_peer_connect)");
   s->fused = on != 0;
   return 0;
 }
@@ -717,6 +742,8 @@ int ode_b200_slab_attempt(ode_b200_slab* s, double* xsend) {
   A.sc = s->sc;
   A.fused = s->fused ? 1 : 0;
   A.ctl_args = control_args(s, xsend);  // fused mode: the partials are read where the last CTA wrote them
+  memset(&A.peer, 0, sizeof(A.peer));
+  if (s->fused && s->peer_on) A.peer = s->px;  // world > 1: the last CTA all-gathers the records over peer memory
   void* kargs[] = {(void*)&A};
   ODEB200_CUDA(cudaLaunchKernel(s->mi.attempt, dim3((unsigned)s->grid), dim3(LARGE_THREADS), kargs, 0, s->stream));
   // the literal repeat of an attempt that went non-finite (ctl->redo); returns at once otherwise
@@ -785,7 +812,227 @@ void ode_b200_slab_free(ode_b200_slab* s) {
   if (s->part) cudaFree(s->part);
   if (s->ipart) cudaFree(s->ipart);
   if (s->tq) cudaFree(s->tq);
+  if (s->xs) cudaFree(s->xs);
+  if (s->xr) cudaFree(s->xr);
+  for (int r = 0; r < PEER_MAX; r++)
+    if (s->peer_ipc[r]) cudaIpcCloseMemHandle(s->peer_ipc[r]);
+  if (s->peer_block) cudaFree(s->peer_block);
   delete s;
+}
+
+// ---- exchange over peer memory ---------------------------------------------------------------------------------
+static size_t peer_block_bytes(int world) { return ((size_t)2 * world * XCHG + 2 * world + 8) * sizeof(double); }
+
+int ode_b200_slab_peer_alloc(ode_b200_slab* s, void* ipc_handle_out, void** local_ptr_out) {
+  int rc = slab_check(s);
+  if (rc) return rc;
+  if (s->world > PEER_MAX) return set_err(ODE_B200_E_UNSUPPORTED, "at most %d slabs can exchange over peer memory", PEER_MAX);
+  if (s->mi.field) return set_err(ODE_B200_E_UNSUPPORTED, "a general field right-hand side runs on one slab");
+  if (!s->peer_block) {
+    ODEB200_CUDA(cudaMalloc(&s->peer_block, peer_block_bytes(s->world)));
+    ODEB200_CUDA(cudaMemset(s->peer_block, 0, peer_block_bytes(s->world)));  // flags and exchange counter start at 0
+    ODEB200_CUDA(cudaDeviceSynchronize());
+    s->peer_epoch = reinterpret_cast<unsigned long long*>(s->peer_block + 2LL * s->world * XCHG) + 2 * s->world;
+  }
+  if (ipc_handle_out) {
+    static_assert(sizeof(cudaIpcMemHandle_t) == ODE_B200_PEER_HANDLE_BYTES, "handle size");
+    cudaIpcMemHandle_t h;
+    ODEB200_CUDA(cudaIpcGetMemHandle(&h, s->peer_block));
+    memcpy(ipc_handle_out, &h, sizeof(h));
+  }
+  if (local_ptr_out) *local_ptr_out = s->peer_block;
+  return 0;
+}
+
+int ode_b200_slab_peer_connect(ode_b200_slab* s, const void* ipc_handles, void* const* ptrs) {
+  int rc = slab_check(s);
+  if (rc) return rc;
+  if (!s->peer_block) return set_err(ODE_B200_E_INVALID, "ode_b200_slab_peer_alloc comes first");
+  if (!ipc_handles && !ptrs) return set_err(ODE_B200_E_INVALID, "peer handles or peer pointers are required");
+  memset(&s->px, 0, sizeof(s->px));
+  for (int r = 0; r < s->world; r++) {
+    if (r == s->rank) {
+      s->px.block[r] = s->peer_block;
+    } else if (ptrs) {  // same process: the caller enabled peer access between the devices
+      if (!ptrs[r]) return set_err(ODE_B200_E_INVALID, "peer pointer %d is null", r);
+      s->px.block[r] = (double*)ptrs[r];
+    } else {
+      if (s->peer_ipc[r]) {
+        cudaIpcCloseMemHandle(s->peer_ipc[r]);
+        s->peer_ipc[r] = nullptr;
+      }
+      cudaIpcMemHandle_t h;
+      memcpy(&h, (const char*)ipc_handles + (size_t)r * ODE_B200_PEER_HANDLE_BYTES, sizeof(h));
+      void* p = nullptr;
+      ODEB200_CUDA(cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess));
+      s->peer_ipc[r] = p;
+      s->px.block[r] = (double*)p;
+    }
+  }
+  s->px.mine = s->peer_block;
+  s->px.epoch = s->peer_epoch;
+  s->px.world = s->world;
+  s->px.rank = s->rank;
+  long long ms = 5000;
+  if (const char* e = getenv("ODE_B200_PEER_TIMEOUT_MS")) ms = atoll(e) > 0 ? atoll(e) : ms;
+  s->px.timeout_ns = ms * 1000000LL;
+  s->peer_on = true;
+  s->fused = true;
+  if (const char* e = getenv("ODE_B200_PEER_FUSED")) s->fused = atoi(e) != 0;
+  return 0;
+}
+
+// recv <- all_gather(send) in stream order, for the exchanges the session can do itself
+static int slab_exchange(ode_b200_slab* s, double* xsend, double* xrecv) {
+  if (s->world == 1) {
+    ODEB200_CUDA(cudaMemcpyAsync(xrecv, xsend, XCHG * 8, cudaMemcpyDeviceToDevice, s->stream));
+    return 0;
+  }
+  if (!s->peer_on)
+    return set_err(ODE_B200_E_INVALID, "slabs of a decomposed grid that are not connected over peer memory are driven step by step "
+                                       "(ode_b200_slab_attempt / _control) with the caller's all-gather");
+  PeerXchg P = s->px;
+  P.gathered = xrecv;
+  peer_exchange_kernel<<<1, 128, 0, s->stream>>>(P, xsend, XS_EDGE + 4 * s->mi.H, s->ctl);
+  note_launch();
+  ODEB200_CUDA(cudaGetLastError());
+  return 0;
+}
+
+// The whole integration loop of `count` sessions of THIS process, in lockstep: hinit phases, then batches of 4
+// attempts (captured once per session into a CUDA graph and replayed; the done flag is polled after each batch and
+// attempts issued after the end are no-ops).  count = 1: one slab (world = 1), or this process's slab of a grid
+// decomposed across processes that are connected over peer memory.  count > 1: all slabs live in this process, one
+// per GPU; every launch is asynchronous, so one host thread keeps all devices busy, and nothing here blocks on a
+// device before the matching work of every other device has been enqueued.
+static int slabs_run(ode_b200_slab* const* ss, int count, double (*polls)[16], float* ms_out) {
+  int rc = 0;
+  for (int g = 0; g < count && !rc; g++) {
+    ode_b200_slab* s = ss[g];
+    rc = slab_check(s);
+    if (!rc && !s->xs) {
+      ODEB200_CUDA(cudaMalloc(&s->xs, XCHG * 8));
+      ODEB200_CUDA(cudaMalloc(&s->xr, (size_t)s->world * XCHG * 8));
+    }
+    if (!rc && s->world > 1 && !s->peer_on) rc = slab_exchange(s, nullptr, nullptr);  // (sets the error)
+  }
+  if (rc) return rc;
+  std::vector<cudaEvent_t> e0(count, nullptr), e1(count, nullptr);
+  std::vector<cudaGraphExec_t> gexec(count, nullptr);
+  std::vector<long long> batch_launches(count, 0);
+  auto cleanup = [&]() {
+    for (int g = 0; g < count; g++) {
+      cudaSetDevice(ss[g]->device);
+      if (gexec[g]) cudaGraphExecDestroy(gexec[g]);
+      if (e0[g]) cudaEventDestroy(e0[g]);
+      if (e1[g]) cudaEventDestroy(e1[g]);
+    }
+  };
+#define RUN_TRY(x)      \
+  do {                  \
+    if (!rc) rc = (x);  \
+  } while (0)
+#define RUN_CUDA(x)                                                                                  \
+  do {                                                                                               \
+    if (!rc) {                                                                                       \
+      cudaError_t e__ = (x);                                                                         \
+      if (e__ != cudaSuccess) rc = set_err(ODE_B200_E_CUDA, "%s: %s", #x, cudaGetErrorString(e__));  \
+    }                                                                                                \
+  } while (0)
+  for (int g = 0; g < count && !rc; g++) {
+    ode_b200_slab* s = ss[g];
+    RUN_CUDA(cudaSetDevice(s->device));
+    RUN_CUDA(cudaMemsetAsync(s->xs, 0, XCHG * 8, s->stream));
+    RUN_CUDA(cudaEventCreate(&e0[g]));
+    RUN_CUDA(cudaEventCreate(&e1[g]));
+    RUN_CUDA(cudaEventRecord(e0[g], s->stream));
+  }
+  for (int ph = 0; ph < 4 && !rc; ph++) {
+    for (int g = 0; g < count && !rc; g++) {
+      ode_b200_slab* s = ss[g];
+      RUN_CUDA(cudaSetDevice(s->device));
+      RUN_TRY(ode_b200_slab_init_phase(s, ph, s->xs, s->xr));
+      if (ph < 3) RUN_TRY(slab_exchange(s, s->xs, s->xr));
+    }
+  }
+  const int batch = 4;  // (batches of 16 were slower: the graph costs more to instantiate than the fewer polls save)
+  auto enqueue_batch = [&](ode_b200_slab* s) {
+    for (int q = 0; q < batch && !rc; q++) {
+      RUN_TRY(ode_b200_slab_attempt(s, s->xs));
+      if (!s->fused) RUN_TRY(slab_exchange(s, s->xs, s->xr));
+      RUN_TRY(ode_b200_slab_control(s, s->xr));
+    }
+  };
+  // ODE_B200_NO_GRAPH=1 (or a failed capture) issues the launches directly
+  if (!rc && !getenv("ODE_B200_NO_GRAPH")) {
+    for (int g = 0; g < count && !rc; g++) {
+      ode_b200_slab* s = ss[g];
+      RUN_CUDA(cudaSetDevice(s->device));
+      cudaGraph_t graph = nullptr;
+      const long long before = ode_b200_launch_count(0);
+      if (cudaStreamBeginCapture(s->stream, cudaStreamCaptureModeThreadLocal) == cudaSuccess) {
+        enqueue_batch(s);
+        const cudaError_t ce = cudaStreamEndCapture(s->stream, &graph);
+        if (ce != cudaSuccess || rc || !graph || cudaGraphInstantiate(&gexec[g], graph, 0) != cudaSuccess) gexec[g] = nullptr;
+        if (graph) cudaGraphDestroy(graph);
+        if (!gexec[g]) {  // fall back to direct launches
+          cudaGetLastError();
+          rc = 0;
+        }
+      } else {
+        cudaGetLastError();
+      }
+      batch_launches[g] = ode_b200_launch_count(0) - before;  // counted once at capture; added per replay below
+    }
+  }
+  bool first_batch = true;
+  while (!rc) {
+    for (int g = 0; g < count && !rc; g++) {
+      ode_b200_slab* s = ss[g];
+      RUN_CUDA(cudaSetDevice(s->device));
+      if (gexec[g]) {
+        RUN_CUDA(cudaGraphLaunch(gexec[g], s->stream));
+        if (!first_batch)
+          for (long long q = 0; q < batch_launches[g]; q++) note_launch();
+      } else {
+        enqueue_batch(s);
+      }
+    }
+    first_batch = false;
+    bool all_done = true;
+    for (int g = 0; g < count && !rc; g++) {
+      RUN_TRY(ode_b200_slab_poll(ss[g], polls[g]));
+      all_done = all_done && polls[g][0] != 0.0;
+    }
+    if (all_done) break;
+  }
+  float ms = 0.f;
+  for (int g = 0; g < count && !rc; g++) {
+    ode_b200_slab* s = ss[g];
+    RUN_CUDA(cudaSetDevice(s->device));
+    RUN_CUDA(cudaEventRecord(e1[g], s->stream));
+    RUN_CUDA(cudaEventSynchronize(e1[g]));
+    float m = 0.f;
+    if (!rc) cudaEventElapsedTime(&m, e0[g], e1[g]);
+    ms = m > ms ? m : ms;
+  }
+  if (ms_out) *ms_out = ms;
+  cleanup();
+  return rc;
+#undef RUN_TRY
+#undef RUN_CUDA
+}
+
+int ode_b200_slab_run(ode_b200_slab* s, double* ctl_out, double* kernel_ms) {
+  int rc = slab_check(s);
+  if (rc) return rc;
+  double poll[1][16] = {{0}};
+  float ms = 0.f;
+  if (s->world == 1 && !s->mi.field) s->fused = true;
+  rc = slabs_run(&s, 1, poll, &ms);
+  if (ctl_out) memcpy(ctl_out, poll[0], sizeof(poll[0]));
+  if (kernel_ms) *kernel_ms = ms;
+  return rc;
 }
 
 static int solve_large_impl(const ode_b200_opts* o, int64_t n, const double* y0, const double* params,
@@ -937,6 +1184,8 @@ void ode_b200_trim(void) {
 int ode_b200_solve_large(const ode_b200_opts* o, int64_t n, const double* y0, const double* params, double t0,
                          double tend, double* y_out, ode_b200_large_stats* stats, double* trace, int64_t trace_cap,
                          int64_t* trace_n) {
+  if (o && o->n_gpus > 1)  // fan-out inside the library: devices o->device .. o->device + n_gpus - 1
+    return ode_b200_solve_large_multi(o, o->n_gpus, nullptr, n, y0, params, t0, tend, y_out, stats, trace, trace_cap, trace_n);
   const double ts[2] = {t0, tend};
   return solve_large_impl(o, n, y0, params, ts, 2, y_out, nullptr, stats, trace, trace_cap, trace_n);
 }
@@ -981,8 +1230,6 @@ static int solve_large_impl(const ode_b200_opts* o, int64_t n, const double* y0,
     ODEB200_CUDA(cudaStreamCreateWithFlags(&cc.st, cudaStreamNonBlocking));
     rc = ode_b200_slab_create(o, n, n, 0, 1, params, t0, tend, cc.st, &cc.s);
     if (!rc && cudaMalloc(&cc.dy, (size_t)n * 8) != cudaSuccess) rc = set_err(ODE_B200_E_NOMEM, "cudaMalloc failed");
-    if (!rc && cudaMalloc(&cc.xs, XCHG * 8) != cudaSuccess) rc = set_err(ODE_B200_E_NOMEM, "cudaMalloc failed");
-    if (!rc && cudaMalloc(&cc.xr, XCHG * 8) != cudaSuccess) rc = set_err(ODE_B200_E_NOMEM, "cudaMalloc failed");
     if (rc) {
       cudaGetLastError();
       large_cache_release();
@@ -1002,8 +1249,7 @@ static int solve_large_impl(const ode_b200_opts* o, int64_t n, const double* y0,
   }
   ode_b200_slab* s = cc.s;
   cudaStream_t st = cc.st;
-  double *dy = cc.dy, *xs = cc.xs, *xr = cc.xr, *dtrace = nullptr, *dpts = nullptr;
-  cudaEvent_t e0 = nullptr, e1 = nullptr;
+  double *dy = cc.dy, *dtrace = nullptr, *dpts = nullptr;
   double poll[16] = {0};
 #define LARGE_TRY(x)  \
   do {                \
@@ -1016,7 +1262,6 @@ static int solve_large_impl(const ode_b200_opts* o, int64_t n, const double* y0,
       if (e__ != cudaSuccess) rc = set_err(ODE_B200_E_CUDA, "%s: %s", #x, cudaGetErrorString(e__)); \
     }                                                                                          \
   } while (0)
-  LARGE_CUDA(cudaMemsetAsync(xs, 0, XCHG * 8, st));
   LARGE_TRY(ode_b200_slab_set_output(s, nullptr, 0, nullptr));
   if (trace && trace_cap > 0) {
     LARGE_CUDA(cudaMalloc(&dtrace, (size_t)trace_cap * 32));
@@ -1033,60 +1278,11 @@ static int solve_large_impl(const ode_b200_opts* o, int64_t n, const double* y0,
   }
   LARGE_CUDA(cudaMemcpyAsync(dy, y0, (size_t)n * 8, cudaMemcpyHostToDevice, st));
   LARGE_TRY(ode_b200_slab_set_state(s, dy));
-  LARGE_CUDA(cudaEventCreate(&e0));
-  LARGE_CUDA(cudaEventCreate(&e1));
-  LARGE_CUDA(cudaEventRecord(e0, st));
-  for (int ph = 0; ph < 4 && !rc; ph++) {
-    LARGE_TRY(ode_b200_slab_init_phase(s, ph, xs, xr));
-    if (ph < 3) LARGE_CUDA(cudaMemcpyAsync(xr, xs, XCHG * 8, cudaMemcpyDeviceToDevice, st));  // world = 1 "all-gather"
-  }
   s->fused = !s->mi.field;  // one slab: accept/reject runs inside the attempt kernel (no exchange, no control launch)
-  // A batch of 4 attempts (the done flag is polled after each batch; attempts issued after the end are no-ops;
-  // batches of 16 were slower: the graph costs more to instantiate than the fewer polls save) is
-  // captured once into a CUDA graph and replayed: the launch-bound small and mid-size systems pay one graph launch
-  // per batch instead of 8-40 kernel launches.  ODE_B200_NO_GRAPH=1 (or a failed capture) issues the launches directly.
-  const int batch = 4;
-  auto enqueue_batch = [&]() {
-    for (int q = 0; q < batch && !rc; q++) {
-      LARGE_TRY(ode_b200_slab_attempt(s, xs));
-      if (!s->fused) LARGE_CUDA(cudaMemcpyAsync(xr, xs, XCHG * 8, cudaMemcpyDeviceToDevice, st));
-      LARGE_TRY(ode_b200_slab_control(s, xr));
-    }
-  };
-  cudaGraphExec_t gexec = nullptr;
-  long long batch_launches = 0;
-  if (!rc && !getenv("ODE_B200_NO_GRAPH")) {
-    cudaGraph_t graph = nullptr;
-    const long long before = ode_b200_launch_count(0);
-    if (cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal) == cudaSuccess) {
-      enqueue_batch();
-      const cudaError_t ce = cudaStreamEndCapture(st, &graph);
-      if (ce != cudaSuccess || rc || !graph || cudaGraphInstantiate(&gexec, graph, 0) != cudaSuccess) gexec = nullptr;
-      if (graph) cudaGraphDestroy(graph);
-      if (!gexec) {  // fall back to direct launches
-        cudaGetLastError();
-        rc = 0;
-      }
-    } else {
-      cudaGetLastError();
-    }
-    batch_launches = ode_b200_launch_count(0) - before;  // counted once at capture; added per replay below
-  }
-  bool first_batch = true;
-  while (!rc) {
-    if (gexec) {
-      LARGE_CUDA(cudaGraphLaunch(gexec, st));
-      if (!first_batch)
-        for (long long q = 0; q < batch_launches; q++) note_launch();
-      first_batch = false;
-    } else {
-      enqueue_batch();
-    }
-    LARGE_TRY(ode_b200_slab_poll(s, poll));
-    if (poll[0] != 0.0) break;
-  }
-  if (gexec) cudaGraphExecDestroy(gexec);
-  LARGE_CUDA(cudaEventRecord(e1, st));
+  float run_ms = 0.f;
+  double polls[1][16] = {{0}};
+  LARGE_TRY(slabs_run(&s, 1, polls, &run_ms));  // hinit phases + graph-replayed attempt batches until done
+  memcpy(poll, polls[0], sizeof(poll));
   LARGE_TRY(ode_b200_slab_get_state(s, dy));
   if (y_out) LARGE_CUDA(cudaMemcpyAsync(y_out, dy, (size_t)n * 8, cudaMemcpyDeviceToHost, st));
   if (pts_out && dpts && all_t) {
@@ -1106,8 +1302,7 @@ static int solve_large_impl(const ode_b200_opts* o, int64_t n, const double* y0,
   }
   LARGE_CUDA(cudaStreamSynchronize(st));
   if (!rc && stats) {
-    float ms = 0.f;
-    cudaEventElapsedTime(&ms, e0, e1);
+    const float ms = run_ms;
     stats->n_accept = (int64_t)poll[2];
     stats->n_reject = (int64_t)poll[3];
     stats->n_rhs = (int64_t)poll[8];
@@ -1115,8 +1310,6 @@ static int solve_large_impl(const ode_b200_opts* o, int64_t n, const double* y0,
     stats->t_final = poll[7];
     stats->kernel_ms = ms;
   }
-  if (e0) cudaEventDestroy(e0);
-  if (e1) cudaEventDestroy(e1);
   if (s) {  // per-call buffers go, the session stays cached
     s->trace = nullptr;
     s->trace_cap = 0;
@@ -1132,14 +1325,183 @@ static int solve_large_impl(const ode_b200_opts* o, int64_t n, const double* y0,
 #undef LARGE_CUDA
 }
 
+// ---- one large system on several GPUs of this process ------------------------------------------------------------
+// The reference integrates the whole state as one Vector in one process (oderk_adapt, src/runge_kutta.jl:232-369).
+// Here the periodic grid is cut into n_gpus contiguous slabs (the first n % n_gpus one point longer), one per device;
+// per step ATTEMPT every slab runs ONE kernel whose last thread block writes the slab's record (double-double error
+// partial, max, NaN flag, edge values of ytrial / k_next) into every peer's HBM over NVLink, waits for the peers'
+// records and runs the step controller on the gathered data -- every device takes the same decision from the same
+// bits, and the result equals the single-GPU result bit for bit.  One host thread replays one CUDA graph per device.
+struct MultiCache {
+  std::vector<ode_b200_slab*> s;
+  std::vector<cudaStream_t> st;
+  std::vector<double*> dy;
+  std::vector<int> dev;
+  int method = -1, rhs = -1;
+  long long n = 0;
+};
+static thread_local MultiCache g_multi;
+static void multi_release() {
+  MultiCache& M = g_multi;
+  for (size_t g = 0; g < M.s.size(); g++) {
+    cudaSetDevice(M.dev[g]);
+    cudaDeviceSynchronize();
+    if (M.dy[g]) cudaFree(M.dy[g]);
+    if (M.s[g]) ode_b200_slab_free(M.s[g]);
+    if (M.st[g]) cudaStreamDestroy(M.st[g]);
+  }
+  M = MultiCache();
+}
+
+int ode_b200_solve_large_multi(const ode_b200_opts* o, int32_t n_gpus, const int32_t* devices, int64_t n,
+                               const double* y0, const double* params, double t0, double tend, double* y_out,
+                               ode_b200_large_stats* stats, double* trace, int64_t trace_cap, int64_t* trace_n) {
+  if (!o || !y0) return set_err(ODE_B200_E_INVALID, "null argument");
+  int cnt = 0;
+  if (cudaGetDeviceCount(&cnt) != cudaSuccess || cnt <= 0) {
+    cudaGetLastError();
+    return set_err(ODE_B200_E_NO_DEVICE, "no CUDA device available; libode_b200 has no CPU fallback");
+  }
+  if (n_gpus < 1 || n_gpus > PEER_MAX) return set_err(ODE_B200_E_INVALID, "n_gpus must be 1..%d", PEER_MAX);
+  std::vector<int> dev(n_gpus);
+  for (int g = 0; g < n_gpus; g++) {
+    dev[g] = devices ? devices[g] : o->device + g;
+    if (dev[g] < 0 || dev[g] >= cnt) return set_err(ODE_B200_E_INVALID, "device %d out of range (0..%d)", dev[g], cnt - 1);
+    for (int q = 0; q < g; q++)
+      if (dev[q] == dev[g]) return set_err(ODE_B200_E_INVALID, "device %d listed twice", dev[g]);
+  }
+  if (n_gpus == 1) {
+    ode_b200_opts o1 = *o;
+    o1.device = dev[0];
+    o1.n_gpus = 1;
+    return ode_b200_solve_large(&o1, n, y0, params, t0, tend, y_out, stats, trace, trace_cap, trace_n);
+  }
+  MultiCache& M = g_multi;
+  int rc = 0;
+  if (!M.s.empty() && (M.dev != dev || M.method != o->method || M.rhs != o->rhs || M.n != n)) multi_release();
+  const long long base = n / n_gpus, rem = n % n_gpus;
+  auto lo_of = [&](int g) { return g * base + (g < rem ? g : rem); };
+  if (M.s.empty()) {
+    M.s.assign(n_gpus, nullptr);
+    M.st.assign(n_gpus, nullptr);
+    M.dy.assign(n_gpus, nullptr);
+    M.dev = dev;
+    for (int g = 0; g < n_gpus && !rc; g++) {  // NVLink peer access, every pair
+      if (cudaSetDevice(dev[g]) != cudaSuccess) rc = set_err(ODE_B200_E_CUDA, "cudaSetDevice(%d) failed", dev[g]);
+      for (int q = 0; q < n_gpus && !rc; q++) {
+        if (q == g) continue;
+        int can = 0;
+        cudaDeviceCanAccessPeer(&can, dev[g], dev[q]);
+        if (!can) rc = set_err(ODE_B200_E_UNSUPPORTED, "device %d cannot address the memory of device %d (no peer access)", dev[g], dev[q]);
+        if (!rc) {
+          const cudaError_t e = cudaDeviceEnablePeerAccess(dev[q], 0);
+          if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled) rc = set_err(ODE_B200_E_CUDA, "cudaDeviceEnablePeerAccess: %s", cudaGetErrorString(e));
+          cudaGetLastError();
+        }
+      }
+    }
+    std::vector<void*> blocks(n_gpus, nullptr);
+    for (int g = 0; g < n_gpus && !rc; g++) {
+      cudaSetDevice(dev[g]);
+      if (cudaStreamCreateWithFlags(&M.st[g], cudaStreamNonBlocking) != cudaSuccess) rc = set_err(ODE_B200_E_CUDA, "cudaStreamCreate failed");
+      ode_b200_opts og = *o;
+      og.device = dev[g];
+      const long long nl = lo_of(g + 1) - lo_of(g);
+      if (!rc) rc = ode_b200_slab_create(&og, nl, n, g, n_gpus, params, t0, tend, M.st[g], &M.s[g]);
+      if (!rc && cudaMalloc(&M.dy[g], (size_t)nl * 8) != cudaSuccess) rc = set_err(ODE_B200_E_NOMEM, "cudaMalloc failed");
+      if (!rc) rc = ode_b200_slab_peer_alloc(M.s[g], nullptr, &blocks[g]);
+    }
+    for (int g = 0; g < n_gpus && !rc; g++) rc = ode_b200_slab_peer_connect(M.s[g], nullptr, blocks.data());
+    if (rc) {
+      cudaGetLastError();
+      multi_release();
+      return rc;
+    }
+    M.method = o->method;
+    M.rhs = o->rhs;
+    M.n = n;
+  } else {
+    if (o->points != ODE_B200_POINTS_ALL && o->points != ODE_B200_POINTS_FINAL && o->points != ODE_B200_POINTS_SPECIFIED)
+      return set_err(ODE_B200_E_POINTS, "Unrecognized option points==%d", o->points);
+    for (int g = 0; g < n_gpus && !rc; g++) {
+      M.s[g]->trace = nullptr;
+      M.s[g]->trace_cap = 0;
+      rc = slab_configure(M.s[g], o, params, t0, tend);
+    }
+    if (rc) return rc;
+  }
+  double* dtrace = nullptr;
+#define MULTI_CUDA(x)                                                                                \
+  do {                                                                                               \
+    if (!rc) {                                                                                       \
+      cudaError_t e__ = (x);                                                                         \
+      if (e__ != cudaSuccess) rc = set_err(ODE_B200_E_CUDA, "%s: %s", #x, cudaGetErrorString(e__));  \
+    }                                                                                                \
+  } while (0)
+  for (int g = 0; g < n_gpus && !rc; g++) {
+    MULTI_CUDA(cudaSetDevice(dev[g]));
+    if (!rc) rc = ode_b200_slab_set_output(M.s[g], nullptr, 0, nullptr);
+    if (g == 0 && trace && trace_cap > 0) {  // every slab records the same rows: take rank 0's
+      MULTI_CUDA(cudaMalloc(&dtrace, (size_t)trace_cap * 32));
+      if (!rc) rc = ode_b200_slab_set_trace(M.s[0], dtrace, trace_cap);
+    }
+    const long long lo = lo_of(g), nl = lo_of(g + 1) - lo;
+    MULTI_CUDA(cudaMemcpyAsync(M.dy[g], y0 + lo, (size_t)nl * 8, cudaMemcpyHostToDevice, M.st[g]));
+    if (!rc) rc = ode_b200_slab_set_state(M.s[g], M.dy[g]);
+  }
+  for (int g = 0; g < n_gpus && !rc; g++) {  // all uploads done before any kernel may wait for a peer
+    MULTI_CUDA(cudaSetDevice(dev[g]));
+    MULTI_CUDA(cudaStreamSynchronize(M.st[g]));
+  }
+  std::vector<double> polls((size_t)n_gpus * 16, 0.0);
+  float ms = 0.f;
+  if (!rc) rc = slabs_run(M.s.data(), n_gpus, reinterpret_cast<double(*)[16]>(polls.data()), &ms);
+  for (int g = 0; g < n_gpus && !rc; g++) {
+    MULTI_CUDA(cudaSetDevice(dev[g]));
+    if (!rc) rc = ode_b200_slab_get_state(M.s[g], M.dy[g]);
+    const long long lo = lo_of(g), nl = lo_of(g + 1) - lo;
+    if (y_out) MULTI_CUDA(cudaMemcpyAsync(y_out + lo, M.dy[g], (size_t)nl * 8, cudaMemcpyDeviceToHost, M.st[g]));  // disjoint slices
+  }
+  if (trace && dtrace && !rc) {
+    MULTI_CUDA(cudaSetDevice(dev[0]));
+    const long long tn = (long long)polls[10];
+    const long long m = tn < trace_cap ? tn : trace_cap;
+    MULTI_CUDA(cudaMemcpyAsync(trace, dtrace, (size_t)m * 32, cudaMemcpyDeviceToHost, M.st[0]));
+    if (trace_n) *trace_n = tn;
+  }
+  for (int g = 0; g < n_gpus && !rc; g++) {
+    MULTI_CUDA(cudaSetDevice(dev[g]));
+    MULTI_CUDA(cudaStreamSynchronize(M.st[g]));
+  }
+  if (!rc && stats) {
+    const double* p0 = polls.data();
+    stats->n_accept = (int64_t)p0[2];
+    stats->n_reject = (int64_t)p0[3];
+    stats->n_rhs = (int64_t)p0[8];
+    stats->status = (int32_t)p0[1];
+    stats->t_final = p0[7];
+    stats->kernel_ms = ms;
+    for (int g = 1; g < n_gpus; g++)  // a slab that lost its peers stops with its own status
+      if ((int32_t)polls[(size_t)g * 16 + 1] != stats->status) stats->status = ODE_B200_ST_EXCHANGE;
+  }
+  if (dtrace) {
+    cudaSetDevice(dev[0]);
+    M.s[0]->trace = nullptr;
+    M.s[0]->trace_cap = 0;
+    cudaFree(dtrace);
+  }
+  if (rc) multi_release();
+  return rc;
+#undef MULTI_CUDA
+}
+
 }  // extern "C"
 
 static void large_cache_release() {
+  multi_release();
   LargeCache& cc = g_large_cache;
   if (cc.device >= 0) cudaSetDevice(cc.device);
   if (cc.dy) cudaFree(cc.dy);
-  if (cc.xs) cudaFree(cc.xs);
-  if (cc.xr) cudaFree(cc.xr);
   if (cc.s) ode_b200_slab_free(cc.s);
   if (cc.st) cudaStreamDestroy(cc.st);
   cc = LargeCache();

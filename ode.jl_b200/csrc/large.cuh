@@ -108,6 +108,79 @@ struct StencilCtx {
   long long n_global;  // length of the periodic ring
 };
 
+// ---- the exchange between slabs, done by the kernels themselves over peer memory --------------------------
+// Every rank owns a receive block in its HBM, mapped into the address space of all the others (NVLink peer
+// access inside one process, CUDA IPC between the processes of one node):
+//     double             slot[2][world][XCHG]   records, double-buffered by the parity of the exchange number
+//     unsigned long long flag[2][world]         exchange number whose record is complete in the slot
+// An all-gather is: write my record into slot[e&1][rank] of EVERY block, fence, raise flag[e&1][rank] = e in every
+// block, then wait until my own block shows flag[e&1][r] >= e for all r.  One NVLink store latency, no host, no
+// library kernel, and the waiting thread block goes on to run the step controller on the gathered records.
+// Double buffering is enough: a rank can send exchange e+2 only after it has completed e+1, i.e. after every
+// rank has sent e+1, which each does only after it has consumed the records of e.
+constexpr int PEER_MAX = ODE_B200_MAX_PEERS;
+struct PeerXchg {
+  double* block[PEER_MAX];      // block[r]: rank r's receive block as THIS device addresses it
+  double* mine;                 // = block[rank]
+  unsigned long long* epoch;    // exchanges completed so far (device word, survives ode_b200_slab_reset)
+  double* gathered;             // exchange kernel only: copy of the gathered records [world][XCHG], or nullptr
+  long long timeout_ns;         // a peer that never answers ends the integration with ODE_B200_ST_EXCHANGE
+  int world, rank;
+};
+__device__ __forceinline__ unsigned long long* peer_flags(double* block, int world) {
+  return reinterpret_cast<unsigned long long*>(block + 2LL * world * XCHG);
+}
+__device__ __forceinline__ unsigned long long global_timer_ns() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+  return t;
+}
+// Called by every thread of ONE thread block (>= 32 threads) once `xsend[0..len)` is complete and visible to it.
+// Returns the gathered records [world][XCHG] (in this rank's own block), or nullptr when a peer timed out.
+__device__ __forceinline__ const double* peer_all_gather(const PeerXchg& P, const double* xsend, int len) {
+  __shared__ unsigned long long sh_e;
+  __shared__ int sh_ok;
+  if (threadIdx.x == 0) {
+    sh_e = *P.epoch + 1ULL;
+    sh_ok = 1;
+  }
+  __syncthreads();
+  const unsigned long long e = sh_e;
+  const int par = (int)(e & 1ULL);
+  const long long slot = ((long long)par * P.world + P.rank) * XCHG;
+#pragma unroll
+  for (int r = 0; r < PEER_MAX; r++) {  // (unrolled with a predicate: a dynamically indexed kernel-parameter array
+    if (r < P.world) {                  //  would be copied to local memory)
+      double* dst = P.block[r] + slot;
+      for (int j = threadIdx.x; j < len; j += blockDim.x) dst[j] = __ldcg(xsend + j);
+    }
+  }
+  __threadfence_system();
+  __syncthreads();
+#pragma unroll
+  for (int r = 0; r < PEER_MAX; r++) {
+    if (r < P.world && (int)threadIdx.x == r) {
+      __threadfence_system();  // cumulative: orders the records the other threads wrote before the barrier
+      *reinterpret_cast<volatile unsigned long long*>(peer_flags(P.block[r], P.world) + par * P.world + P.rank) = e;
+    }
+  }
+  if ((int)threadIdx.x < P.world) {  // lane r waits for rank r's record
+    const volatile unsigned long long* f = peer_flags(P.mine, P.world) + par * P.world + threadIdx.x;
+    const unsigned long long t0 = global_timer_ns();
+    unsigned int spins = 0;
+    while (*f < e) {
+      if ((++spins & 1023u) == 0u && global_timer_ns() - t0 > (unsigned long long)P.timeout_ns) {
+        sh_ok = 0;
+        break;
+      }
+    }
+    __threadfence_system();
+  }
+  __syncthreads();
+  if (threadIdx.x == 0 && sh_ok) *P.epoch = e;
+  return sh_ok ? P.mine + (long long)par * P.world * XCHG : nullptr;
+}
+
 struct LargeArgs {
   double* Y[2];  // padded [n + 2H]
   double* K[2];
@@ -117,8 +190,10 @@ struct LargeArgs {
   long long n;    // interior points of this slab
   long long tiles;
   StencilCtx sc;  // stencil parameters and index base
-  int fused;      // single slab: the last CTA runs the step controller itself (large_control_body)
+  int fused;      // the last CTA runs the step controller itself (large_control_body): a single slab, or slabs
+                  // that exchange their records over peer memory (peer.world > 1)
   ControlArgs ctl_args;
+  PeerXchg peer;
 };
 
 __device__ __forceinline__ dm_dd dd_add(dm_dd a, dm_dd b) {
@@ -667,9 +742,23 @@ __global__ void __launch_bounds__(LARGE_THREADS) large_attempt_kernel(
 
   if (!LITERAL) mx = __longlong_as_double((long long)mxb);
   const bool last_cta = reduce_error_partials<T>(acc, mx, anynan, A.part, ctl, A.xsend);
-  if (A.fused && last_cta) {  // single slab: accept/reject, new dt and the ghost refresh right here
+  if (A.fused && last_cta) {  // accept/reject, new dt and the ghost refresh right here
     __syncthreads();          // the reduced partials (thread 0) are visible to the block
-    large_control_body(A.ctl_args);
+    if (A.peer.world > 1) {   // slabs: all-gather of the records over peer memory, then every rank decides alike
+      const double* g = peer_all_gather(A.peer, A.xsend, XS_EDGE + 4 * H);
+      if (!g) {
+        if (tid == 0) {
+          ctl->status = ODE_B200_ST_EXCHANGE;
+          ctl->done = 1;
+        }
+        return;
+      }
+      ControlArgs C = A.ctl_args;
+      C.xrecv = g;
+      large_control_body(C);
+    } else {
+      large_control_body(A.ctl_args);
+    }
   }
 }
 

@@ -1,19 +1,30 @@
 """The large-system regime: one method-of-lines ODE system of N unknowns.
 
-`solve_large` is the single-GPU call with host buffers (ode_b200_solve_large).
-`solve_large_distributed` is the domain-decomposed path: every rank owns a
-contiguous slab of the periodic grid plus ghost cells; per step ATTEMPT there is
-exactly one small all-gather (ODE_B200_XCHG_DOUBLES doubles per rank) that
-carries the double-double error partials, the NaN flag and the slab-edge values
-used to refresh the ghosts when the step is accepted.  Every rank then runs the
-same controller arithmetic on the same gathered data, so the accept/reject
-decision and the new dt are identical everywhere without a broadcast
+`solve_large` is the call with host buffers (ode_b200_solve_large); with
+`n_gpus=N` the library itself splits the grid over N devices of this process
+(ode_b200_solve_large_multi).
+`solve_large_distributed` is the domain-decomposed path with one process per GPU:
+every rank owns a contiguous slab of the periodic grid plus ghost cells; per step
+ATTEMPT there is exactly one small all-gather (ODE_B200_XCHG_DOUBLES doubles per
+rank) that carries the double-double error partials, the NaN flag and the
+slab-edge values used to refresh the ghosts when the step is accepted.  Every rank
+then runs the same controller arithmetic on the same gathered data, so the
+accept/reject decision and the new dt are identical everywhere without a broadcast
 (reference semantics: oderk_adapt, /root/reference src/runge_kutta.jl:232-369,
 where the whole state is one Vector in one process).
 
-The host loop (`integrate_slab`) is engine-agnostic: the CUDA engine below is the
-product; the CPU tests inject a stand-in engine to exercise the collective
-plumbing with gloo.
+Two ways to do that all-gather:
+  exchange="peer"  the attempt kernel itself writes the record into every peer's
+                   HBM (CUDA IPC mappings over NVLink) and its last thread block
+                   runs the controller; the whole integration is ONE C call per
+                   rank (ode_b200_slab_run), no Python in the loop.  Ranks of one
+                   node only.
+  exchange="nccl"  torch.distributed.all_gather_into_tensor between the attempt
+                   and the control kernel, driven by `integrate_slab` below.
+"auto" tries "peer" and falls back to "nccl".
+
+`integrate_slab` is engine-agnostic: the CUDA engine below is the product; the
+CPU tests inject a stand-in engine to exercise the collective plumbing with gloo.
 """
 import ctypes as C
 
@@ -106,7 +117,7 @@ def solve_large(alg, F, y0, tspan, *, trace=False, trace_cap=65536, out=None, **
                                                     C.byref(st), tr.ctypes.data_as(dp) if trace else None,
                                                     trace_cap if trace else 0, C.byref(tn)))
             out = pts
-        else:
+        else:  # (opts.n_gpus > 1: the library splits the grid over that many devices)
             check(lib().ode_b200_solve_large(C.byref(o), y0.size, y0.ctypes.data_as(dp), p.ctypes.data_as(dp),
                                              float(ts[0]), float(ts[-1]), out.ctypes.data_as(dp), C.byref(st),
                                              tr.ctypes.data_as(dp) if trace else None, trace_cap if trace else 0,
@@ -171,12 +182,40 @@ class CudaSlabEngine:
     def control(self, recv_ptr):
         check(self.L.ode_b200_slab_control(self.h, C.c_void_p(recv_ptr)))
 
-    def poll(self):
-        a = np.zeros(16)
-        check(self.L.ode_b200_slab_poll(self.h, a.ctypes.data_as(_lib.dp)))
+    @staticmethod
+    def _ctl(a):
         return dict(done=bool(a[0]), status=int(a[1]), n_accept=int(a[2]), n_reject=int(a[3]), t=a[4], dt=a[5],
                     err=a[6], t_final=a[7], n_rhs=int(a[8]), attempts=int(a[9]), trace_n=int(a[10]), ghost=int(a[11]),
                     out_rows=int(a[12]))
+
+    def poll(self):
+        a = np.zeros(16)
+        check(self.L.ode_b200_slab_poll(self.h, a.ctypes.data_as(_lib.dp)))
+        return self._ctl(a)
+
+    def peer_alloc(self):
+        """This rank's receive block for the exchange over peer memory: returns the CUDA IPC handle (bytes) the
+        other processes of the node map it with."""
+        h = C.create_string_buffer(_lib.PEER_HANDLE_BYTES)
+        check(self.L.ode_b200_slab_peer_alloc(self.h, h, None))
+        return h.raw
+
+    def peer_connect(self, handles):
+        """handles: the IPC handles of all ranks in rank order (this rank's own entry is ignored)."""
+        blob = b"".join(handles)
+        check(self.L.ode_b200_slab_peer_connect(self.h, blob, None))
+        self.fused = True
+        self.peer = True
+
+    def run(self):
+        """The whole integration in one C call (hinit, graph-replayed attempt batches, device-side controller):
+        for a single slab or slabs connected over peer memory.  Returns the control block like poll()."""
+        a = np.zeros(16)
+        ms = C.c_double(0.0)
+        check(self.L.ode_b200_slab_run(self.h, a.ctypes.data_as(_lib.dp), C.byref(ms)))
+        ctl = self._ctl(a)
+        ctl["kernel_ms"] = ms.value
+        return ctl
 
     def close(self):
         if self.h:
@@ -220,10 +259,36 @@ def integrate_slab(engine, send, recv, exchange, poll_every=4, max_polls=10 ** 9
             return ctl
 
 
+def connect_peers(eng, group=None):
+    """Collective over `group`: map every rank's receive block into every other rank (CUDA IPC) so the slabs
+    exchange their records from inside the attempt kernel.  Raises on every rank if any rank failed."""
+    import torch.distributed as dist
+    world = dist.get_world_size(group)
+    err, handle = None, b""
+    try:
+        handle = eng.peer_alloc()
+    except Exception as e:  # noqa: BLE001 -- reported collectively below
+        err = repr(e)
+    got = [None] * world
+    dist.all_gather_object(got, (handle, err), group=group)
+    if any(g[1] for g in got):
+        raise RuntimeError("peer exchange unavailable: %s" % [g[1] for g in got if g[1]][0])
+    try:
+        eng.peer_connect([g[0] for g in got])
+    except Exception as e:  # noqa: BLE001
+        err = repr(e)
+    got2 = [None] * world
+    dist.all_gather_object(got2, err, group=group)  # also the barrier before the first run
+    if any(got2):
+        eng.peer = False
+        raise RuntimeError("peer exchange unavailable: %s" % [g for g in got2 if g][0])
+
+
 def solve_large_distributed(alg, F, y_local, n_global, tspan, *, group=None, poll_every=4, trace=False,
-                            trace_cap=65536, engine=None, keep_engine=False, **kw):
+                            trace_cap=65536, engine=None, keep_engine=False, exchange="auto", **kw):
     """Domain-decomposed solve.  y_local: CUDA float64 torch tensor holding this rank's slab
-    (shard_bounds(n_global, world, rank)); returns (y_local_final tensor, ctl dict[, trace tensor])."""
+    (shard_bounds(n_global, world, rank)); returns (y_local_final tensor, ctl dict[, trace tensor]).
+    exchange: "peer" | "nccl" | "auto" (see the module docstring); ctl["exchange"] says which one ran."""
     import torch
     import torch.distributed as dist
 
@@ -234,26 +299,53 @@ def solve_large_distributed(alg, F, y_local, n_global, tspan, *, group=None, pol
     if engine is None:
         eng = CudaSlabEngine(alg, F, y_local.numel(), n_global, rank, world, tspan, stream.cuda_stream,
                              device=dev.index or 0, **kw)
+        eng.peer = False
+        if world > 1 and exchange in ("peer", "auto") and world <= _lib.MAX_PEERS:
+            try:
+                connect_peers(eng, group)
+            except RuntimeError:
+                if exchange == "peer":
+                    raise
     else:  # reuse the device buffers of an earlier call (same slab size, options and stream)
         eng = engine
         eng.reset(tspan[0], tspan[-1])
+    if world == 1 or getattr(eng, "peer", False):
+        # one slab, or peers: one C call per rank runs the whole integration (CUDA-graph batches of attempts, the
+        # controller on the device); peers exchange their records from inside the kernels
+        tr = None
+        if trace:
+            tr = torch.zeros(trace_cap, 4, dtype=torch.float64, device=dev)
+            eng.set_trace(tr.data_ptr(), trace_cap)
+        y_local = y_local.contiguous()
+        eng.set_state(y_local.data_ptr())
+        ctl = eng.run()
+        ctl["exchange"] = "peer" if world > 1 else "none"
+        out = torch.empty_like(y_local)
+        eng.get_state(out.data_ptr())
+        torch.cuda.current_stream(dev).synchronize()
+        if keep_engine:
+            ctl["engine"] = eng
+        else:
+            if world > 1:
+                dist.barrier(group)  # no rank unmaps its block while a peer may still look at it
+            eng.close()
+        if trace:
+            return out, ctl, tr[:min(ctl["trace_n"], trace_cap)]
+        return out, ctl
     send = torch.zeros(XCHG_DOUBLES, dtype=torch.float64, device=dev)
     recv = torch.zeros(world, XCHG_DOUBLES, dtype=torch.float64, device=dev)
     tr = None
     if trace:
         tr = torch.zeros(trace_cap, 4, dtype=torch.float64, device=dev)
         eng.set_trace(tr.data_ptr(), trace_cap)
-    if world > 1:
-        def exchange():
-            dist.all_gather_into_tensor(recv.view(-1), send, group=group)
-    else:
-        def exchange():
-            recv.view(-1).copy_(send)
-    if world == 1 and not getattr(F, "is_field", False) and F.name != "reaction_diffusion_field":
-        eng.set_fused(True)
+
+    def do_exchange():
+        dist.all_gather_into_tensor(recv.view(-1), send, group=group)
+
     y_local = y_local.contiguous()
     eng.set_state(y_local.data_ptr())
-    ctl = integrate_slab(eng, send, recv, exchange, poll_every=poll_every)
+    ctl = integrate_slab(eng, send, recv, do_exchange, poll_every=poll_every)
+    ctl["exchange"] = "nccl"
     out = torch.empty_like(y_local)
     eng.get_state(out.data_ptr())
     torch.cuda.current_stream(dev).synchronize()

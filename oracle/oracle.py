@@ -28,7 +28,8 @@ class Opts(C.Structure):
                 ("device", C.c_int32), ("max_steps", C.c_int64),
                 ("reltol", C.c_double), ("abstol", C.c_double), ("minstep", C.c_double),
                 ("maxstep", C.c_double), ("initstep", C.c_double),
-                ("mathmode", C.c_int32), ("host_output", C.c_int32), ("reserved", C.c_int32 * 6)]
+                ("mathmode", C.c_int32), ("host_output", C.c_int32), ("n_gpus", C.c_int32), ("fp_mode", C.c_int32),
+                ("reserved", C.c_int32 * 4)]
 
 
 def build(force=False):

@@ -11,7 +11,7 @@ from .api import (ode1, ode2_midpoint, ode2_heun, ode4, ode21, ode23, ode45_fe, 
                   ode4s, ode4s_s, ode4s_kr, ode4ms, solve_ensemble, make_opts, Solver, pinned_empty)
 from .common import ODEProblem, ODESolution, solve  # noqa: F401
 from .large import (solve_large, solve_large_distributed, shard_bounds, integrate_slab,  # noqa: F401
-                    CudaSlabEngine)
-from .sharding import solve_ensemble_distributed  # noqa: F401
+                    CudaSlabEngine, connect_peers)
+from .sharding import solve_ensemble_distributed, SharedEnsembleResult  # noqa: F401
 
 lib()  # fail loudly at import if the CUDA library is missing

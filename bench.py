@@ -1,12 +1,21 @@
 #!/usr/bin/env python3
 """bench.py -- headline benchmark: RK step attempts per second.
 
-Workload (BASELINE.json configs[1]): Lorenz, ode45 (Dormand-Prince), 2^20
+Headline workload (BASELINE.json configs[1]): Lorenz, ode45 (Dormand-Prince), 2^20
 trajectories with randomised initial conditions, FP64, t in [0, 10], reference
 default tolerances (reltol 1e-5, abstol 1e-8).  A "step" of this benchmark is
 one pass of the hot path over the batch, i.e. the whole ensemble solve; the
 metric counts RK step attempts (accepted + rejected, one attempt = one
 rk_embedded_step! + stepsize_hw92!, /root/reference src/runge_kutta.jl:305-310).
+
+The ONE JSON line of the default run (`--workload all`) is that headline record plus
+  "large"  : the second north-star regime measured the same way -- reaction-diffusion, N = 2^26 per GPU,
+             ode45, one fused kernel per step attempt (bench_large.py) -- with its own value, e2e,
+             roofline and cpu_baseline; on N > 1 ranks the grid is cut into slabs that exchange one
+             record per attempt over NVLink peer memory (checked against the single-slab bits first);
+  "strong" : N > 1 only: the same two workloads at FIXED total size (2^20 trajectories, N = 2^26)
+             split over the ranks, next to the weak-scaling numbers above.
+`--workload lorenz | large | field` runs one of them alone.
 
   value : attempts/s with y0 already resident in HBM (ode_b200_solve_ensemble_dev
           on torch's current stream, CUDA events around every step)
@@ -19,10 +28,10 @@ rk_embedded_step! + stepsize_hw92!, /root/reference src/runge_kutta.jl:305-310).
                trajectories) on a bounded sample, on rank 0 at N=1 only
 
 `--impl reference` times that CPU restatement instead (the reference itself is
-Julia, which is not installed here or on the GPU box).  `--workload large`
-benchmarks the single large reaction-diffusion system (configs[4]) instead.
-Multi-GPU (torchrun): trajectories shard across ranks with no data-path
-collective (weak scaling: 2^20 trajectories per GPU).
+Julia, which is not installed here or on the GPU box).
+Multi-GPU (torchrun, one process per GPU): trajectories shard across ranks with no
+data-path collective (weak scaling: 2^20 trajectories per GPU); the final gather is
+every rank's D2H into its slice of one node-shared pinned host buffer, inside e2e.
 """
 import argparse
 import json
@@ -39,10 +48,7 @@ sys.path.insert(0, ROOT)
 
 LORENZ = (10.0, 28.0, 8.0 / 3.0)
 FLOPS_PER_ATTEMPT = 297  # dopri5 / Lorenz, SURVEY.md section 8d
-# dram__bytes_read.sum + dram__bytes_write.sum of one 2^20-trajectory launch, from the committed ncu capture
-# (profiles/ensemble_lorenz_r1.md, capture prof_lorenz_r1_d: 60.71 MB + 14.20 MB; y0 25 MB + the pre-pass's
-# {dt0, f0} 34 MB in, results out, most of which stay in L2); the kernel is register resident, traffic is I/O only
-NCU_TRAFFIC_BYTES_PER_LAUNCH = 74.91e6
+FP64_NOMINAL_TFLOPS = 148 * 64 * 2 * 1.965e9 / 1e12  # 148 SMs x 64 FP64 FMA lanes x 2 flops x 1.965 GHz = 37.2
 SEED = 20261019
 
 
@@ -117,6 +123,30 @@ def cpu_baseline_lorenz(sample, steps=1, warmup=0):
                        % (sample, att, per)), per, att
 
 
+def bind_to_gpu_numa(local_rank):
+    """Several ranks on one host: run this rank (and so first-touch its pinned buffers) on the NUMA node its GPU
+    hangs off.  Returns a short description for the bench record; never fails."""
+    try:
+        bus = subprocess.run(["nvidia-smi", "-i", str(local_rank), "--query-gpu=pci.bus_id", "--format=csv,noheader"],
+                             capture_output=True, text=True, timeout=20).stdout.strip().lower()
+        if bus.startswith("0000"):
+            bus = bus[4:]  # nvidia-smi prints an 8-digit domain, sysfs a 4-digit one
+        node = int(open("/sys/bus/pci/devices/%s/numa_node" % bus).read())
+        if node < 0:
+            return "numa_node unknown"
+        cpus = set()
+        for part in open("/sys/devices/system/node/node%d/cpulist" % node).read().strip().split(","):
+            a, _, b = part.partition("-")
+            cpus.update(range(int(a), int(b or a) + 1))
+        cpus &= os.sched_getaffinity(0)
+        if not cpus:
+            return "numa node %d has no allowed cpu" % node
+        os.sched_setaffinity(0, cpus)
+        return "bound to numa node %d (%d cpus)" % (node, len(cpus))
+    except Exception as e:  # noqa: BLE001
+        return "not bound (%s)" % type(e).__name__
+
+
 def run_reference(args, rank):
     """--impl reference: the reference's CPU implementation of the path = the oracle port."""
     if rank != 0:
@@ -124,7 +154,7 @@ def run_reference(args, rank):
     if args.workload in ("large", "field"):
         from bench_large import cpu_baseline_large
         cb = cpu_baseline_large()
-        v = cb["attempts_per_s_at_2^26"]
+        v = cb["value"]
         print(json.dumps({"impl": "reference", "metric": "rk_step_attempts_per_s", "value": v, "unit": "steps/s",
                           "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": None,
                           "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
@@ -145,54 +175,29 @@ def run_reference(args, rank):
             "cpu_baseline": cb,
             "e2e": {"value": cb["value"], "unit": "steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
+    if args.workload == "all":  # the second regime's CPU number rides along, like the `large` record of our arm
+        from bench_large import cpu_baseline_large
+        cbl = cpu_baseline_large()
+        line["large"] = {"impl": "reference", "metric": "rk_step_attempts_per_s", "value": cbl["value"], "unit": "steps/s",
+                         "higher_is_better": True, "config": {"workload": "reaction_diffusion_ode45_dp_large", "n_per_gpu": 1 << 26},
+                         "cpu_baseline": cbl,
+                         "e2e": {"value": cbl["value"], "unit": "steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line))
 
 
-def main():
-    ap = argparse.ArgumentParser()
-    ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=5)
-    ap.add_argument("--warmup", type=int, default=3)
-    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--workload", default="lorenz", choices=["lorenz", "large", "field"])
-    ap.add_argument("--n-traj", type=int, default=1 << 20)
-    ap.add_argument("--cpu-sample", type=int, default=1 << 18)
-    ap.add_argument("--no-cpu-baseline", action="store_true")
-    args = ap.parse_args()
-    args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
-
-    rank = int(os.environ.get("RANK", "0"))
-    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-
-    if args.impl == "reference":
-        run_reference(args, rank)
-        return
-    if args.workload in ("large", "field"):
-        from bench_large import run_large  # noqa: E402
-        run_large(args, rank, local_rank, world)
-        return
-
+def measure_lorenz(ctx, n, y0_np, steps, warmup, *, scaling, peaks, with_cpu, cpu_sample, strict_fp=True):
+    """`steps` passes of the ode45 hot path over this rank's n Lorenz trajectories; record complete on rank 0."""
     import ctypes as C
-    import torch
-    import ode_jl_b200 as m
+    torch, m, L = ctx.torch, ctx.m, ctx.L
     from ode_jl_b200 import _lib
-
-    L = m.lib()
-    if not torch.cuda.is_available() or L.ode_b200_device_count() < 1:
-        raise SystemExit("bench.py needs a CUDA device: the hot path has no CPU fallback")
-    torch.cuda.set_device(local_rank)
-    dev = torch.device("cuda", local_rank)
-    if world > 1:
-        import torch.distributed as dist
-        dist.init_process_group("nccl", device_id=dev)
-
-    n = args.n_traj
+    from bench_large import measured_traffic
+    rank, world, dev, local_rank = ctx.rank, ctx.world, ctx.dev, ctx.local_rank
+    dist = ctx.dist
     dof = 3
-    y0_host = torch.from_numpy(lorenz_ics(n, SEED + rank)).pin_memory()
+    y0_host = torch.from_numpy(np.ascontiguousarray(y0_np)).pin_memory()
     F = m.DeviceRHS("lorenz", *LORENZ)
     tspan = np.array([0.0, 10.0])
-    opts = m.make_opts("ode45", F, tspan, points="final", device=local_rank)
+    opts = m.make_opts("ode45", F, tspan, points="final", device=local_rank, strict_fp=strict_fp)
 
     # ---- device-resident arm ------------------------------------------------------
     d_y0 = y0_host.to(dev)
@@ -215,14 +220,9 @@ def main():
     def step_dev():
         _lib.check(L.ode_b200_solve_ensemble_dev(C.byref(opts), C.byref(io), C.c_void_p(stream.cuda_stream)))
 
-    def barrier():
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
-
-    for _ in range(args.warmup):
+    for _ in range(warmup):
         step_dev()
-    barrier()
+    ctx.barrier()
     attempts = int((d_na.sum() + d_nr.sum()).item())
     assert int(d_st.max().item()) == 0, "a trajectory did not finish"
 
@@ -230,64 +230,77 @@ def main():
     if rank == 0:
         sampler.start()
     L.ode_b200_launch_count(1)
-    evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
-    barrier()
+    evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(steps)]
+    ctx.barrier()
     for e0, e1 in evs:
         flush.fill_(1)  # L2 flush between timed iterations (not timed)
         e0.record(stream)
         step_dev()
         e1.record(stream)
-    barrier()
+    ctx.barrier()
     launches = int(L.ode_b200_launch_count(0))
     clocks = sampler.stop() if rank == 0 else None
-    dev_ms = sum(a.elapsed_time(b) for a, b in evs) / args.steps
+    dev_ms = sum(a.elapsed_time(b) for a, b in evs) / steps
 
     # ---- end-to-end arm: host buffers through the C ABI ----------------------------
-    out = dict(t_final=torch.empty(n, dtype=torch.float64).pin_memory(),
-               y_final=torch.empty(n, dof, dtype=torch.float64).pin_memory(),
-               n_accept=torch.empty(n, dtype=torch.int32).pin_memory(),
-               n_reject=torch.empty(n, dtype=torch.int32).pin_memory(),
-               status=torch.empty(n, dtype=torch.int32).pin_memory())
+    # One rank: caller-owned pinned output buffers.  Several ranks: the outputs ARE the final gather -- every rank's
+    # library call copies its results device -> host into its slice of one node-shared page-locked buffer, and a
+    # barrier per step closes the gather (north star: "no collectives beyond the final gather").
+    shared = None
+    if world == 1:
+        out = dict(t_final=torch.empty(n, dtype=torch.float64).pin_memory().numpy(),
+                   y_final=torch.empty(n, dof, dtype=torch.float64).pin_memory().numpy(),
+                   n_accept=torch.empty(n, dtype=torch.int32).pin_memory().numpy(),
+                   n_reject=torch.empty(n, dtype=torch.int32).pin_memory().numpy(),
+                   status=torch.empty(n, dtype=torch.int32).pin_memory().numpy())
+    else:
+        (n_max,) = ctx.max_over_ranks(n)
+        assert int(n_max) == n, "equal shards expected"
+        shared = m.SharedEnsembleResult(n * world, dof, None)
+        out = shared.mine
     par_h = np.array(LORENZ)
     io2 = _lib.EnsembleIO()
     io2.n_traj, io2.n_tspan, io2.trace_traj = n, 2, -1
     io2.y0, io2.params, io2.tspan = y0_host.data_ptr(), par_h.ctypes.data, tspan.ctypes.data
-    io2.t_final, io2.y_final = out["t_final"].data_ptr(), out["y_final"].data_ptr()
-    io2.n_accept, io2.n_reject, io2.status = out["n_accept"].data_ptr(), out["n_reject"].data_ptr(), out["status"].data_ptr()
+    io2.t_final, io2.y_final = out["t_final"].ctypes.data, out["y_final"].ctypes.data
+    io2.n_accept, io2.n_reject, io2.status = out["n_accept"].ctypes.data, out["n_reject"].ctypes.data, out["status"].ctypes.data
     h2d = y0_host.numel() * 8 + 3 * 8 + 2 * 8
     d2h = n * 8 + n * dof * 8 + 3 * n * 4
-
-    # One GPU per host: let the kernel write the results into the pinned output buffers itself (host_output = 1,
-    # no copy-back phase: 12.4 -> 11.65 ms).  Several ranks on one host: staged copies -- with 8 B200s moving
-    # 570 MB per step through one host the host side is the bottleneck either way (15.1 ms direct, 14.8 ms staged).
-    opts_e2e = m.make_opts("ode45", F, tspan, points="final", device=local_rank, direct_output=(world == 1))
+    # direct = the kernel writes the results into the pinned output buffers itself (host_output = 1, no copy-back
+    # phase).  Default: on for one rank; for several ranks per host staged copies measured no slower (8 x B200).
+    direct = world == 1
+    if os.environ.get("ODE_B200_BENCH_DIRECT"):
+        direct = os.environ["ODE_B200_BENCH_DIRECT"] != "0"
+    opts_e2e = m.make_opts("ode45", F, tspan, points="final", device=local_rank, direct_output=direct, strict_fp=strict_fp)
 
     def step_e2e():
         _lib.check(L.ode_b200_solve_ensemble(C.byref(opts_e2e), C.byref(io2)))
+        if dist is not None:
+            dist.barrier()  # every rank's slice is in the shared buffer
 
     for _ in range(2):
         step_e2e()
-    barrier()
+    ctx.barrier()
     t0 = time.perf_counter()
-    for _ in range(args.steps):
+    for _ in range(steps):
         step_e2e()
-    barrier()
-    e2e_s = (time.perf_counter() - t0) / args.steps
-    att2 = int(out["n_accept"].sum().item() + out["n_reject"].sum().item())
+    ctx.barrier()
+    e2e_s = (time.perf_counter() - t0) / steps
+    att2 = int(out["n_accept"].sum() + out["n_reject"].sum())
     assert att2 == attempts
-    same = torch.equal(out["y_final"], d_yf.cpu())
-    assert same, "host-buffer and device-resident arms disagree"
-
-    # ---- reduce over ranks (max time, sum of work) ----------------------------------
+    assert np.array_equal(out["y_final"], d_yf.cpu().numpy()), "host-buffer and device-resident arms disagree"
     tot_attempts = attempts
     if world > 1:
-        t = torch.tensor([dev_ms, e2e_s], dtype=torch.float64, device=dev)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        dev_ms, e2e_s = float(t[0]), float(t[1])
+        if rank == 0:  # the gathered ensemble is complete on rank 0 (and everywhere else)
+            assert int(shared.arrays["n_accept"].sum() + shared.arrays["n_reject"].sum()) > attempts
+            assert int(shared.arrays["status"].max()) == 0
+        dev_ms, e2e_s = ctx.max_over_ranks(dev_ms, e2e_s)
         a = torch.tensor([attempts], dtype=torch.float64, device=dev)
         dist.all_reduce(a, op=dist.ReduceOp.SUM)
         tot_attempts = int(a.item())
+        shared.close()
 
+    line = None
     if rank == 0:
         value = tot_attempts / (dev_ms * 1e-3)
         e2e_v = tot_attempts / e2e_s
@@ -296,27 +309,113 @@ def main():
         dmix = L.ode_b200_fp64_peak(local_rank, 1)   # DADD+DMUL instr/s, measured now
         achieved = attempts * FLOPS_PER_ATTEMPT / (dev_ms * 1e-3) / 1e12
         peak = 2.0 * dfma / 1e12
+        traffic, tsrc = measured_traffic("lorenz", n)
         roofline = {"bound": "fp64", "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
                     "frac_of_issue_peak": achieved / (max(dfma, dmix) / 1e12),
-                    "traffic": NCU_TRAFFIC_BYTES_PER_LAUNCH if n == (1 << 20) else None,
+                    "peak_nominal": FP64_NOMINAL_TFLOPS, "frac_of_nominal": achieved / FP64_NOMINAL_TFLOPS,
+                    "traffic": traffic, "traffic_source": tsrc,
                     "peak_source": "measured live: ode_b200_fp64_peak DFMA chains x2 flops (no FP64 entry in "
-                                   "MEASURED_PEAKS.json); issue peak = max(DFMA, DADD+DMUL) instr/s = %.3g" % max(dfma, dmix),
-                    "note": "strict no-FMA arithmetic (reference parity) caps flops at 50% of the FMA peak; "
-                            "frac_of_issue_peak counts algorithmic FP64 ops against FP64 instruction slots"}
+                                   "MEASURED_PEAKS.json; ncu of the microbenchmark: profiles/); issue peak = "
+                                   "max(DFMA, DADD+DMUL) instr/s = %.3g; nominal = 148 SM x 64 lanes x 2 x 1.965 GHz" % max(dfma, dmix),
+                    "note": ("strict no-FMA arithmetic (reference parity) caps flops at 50% of the FMA peak; "
+                             "frac_of_issue_peak counts algorithmic FP64 ops against FP64 instruction slots") if strict_fp else
+                            "fp_mode = FMA: contracted multiply-adds, NOT the parity path (flops counted as in strict mode)"}
         line = {"metric": "rk_step_attempts_per_s", "value": value, "unit": "steps/s", "n_gpus": world,
-                "steps": args.steps, "warmup": args.warmup, "ms_per_step": dev_ms, "higher_is_better": True,
-                "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+                "steps": steps, "warmup": warmup, "ms_per_step": dev_ms, "higher_is_better": True,
+                "scaling": scaling, "vs_baseline": None, "dtype": "f64", "data": "synthetic",
                 "config": {"workload": "lorenz_ode45_dp_ensemble", "n_traj_per_gpu": n, "tspan": [0.0, 10.0],
                            "reltol": 1e-5, "abstol": 1e-8, "attempts_per_step_per_gpu": attempts,
+                           "fp_mode": "strict (no FMA, reference parity)" if strict_fp else "fma (opt-in, not bit-exact)",
                            "l2": "256 MiB flush write between timed iterations", "parallelism": "traj-shard x%d" % world},
-                "e2e": {"output_path": "kernel writes pinned host buffers" if world == 1 else "staged D2H copies", "value": e2e_v, "unit": "steps/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                "e2e": {"output_path": ("kernel writes pinned host buffers" if direct else "staged D2H copies") +
+                                       ("" if world == 1 else "; final gather = every rank's results land in its slice "
+                                                              "of one node-shared pinned host buffer, barrier per step"),
+                        "value": e2e_v, "unit": "steps/s", "h2d_bytes_per_step": h2d * world, "d2h_bytes_per_step": d2h * world,
                         "ms_per_step": e2e_s * 1e3},
                 "gpu_launches": launches, "clocks": clocks, "roofline": roofline}
-        if world == 1 and not args.no_cpu_baseline:
-            line["cpu_baseline"] = cpu_baseline_lorenz(args.cpu_sample)[0]
+        if with_cpu and world == 1:
+            line["cpu_baseline"] = cpu_baseline_lorenz(cpu_sample)[0]
+    del flush
+    torch.cuda.empty_cache()
+    return line
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="all", choices=["all", "lorenz", "large", "field"])
+    ap.add_argument("--n-traj", type=int, default=1 << 20)
+    ap.add_argument("--large-n", type=int, default=int(os.environ.get("ODE_B200_LARGE_N", 1 << 26)))
+    ap.add_argument("--cpu-sample", type=int, default=1 << 18)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--exchange", default="auto", choices=["auto", "peer", "nccl"])
+    ap.add_argument("--relaxed-fp", action="store_true", help="opt-in FMA-contracted kernels (not the parity path)")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
+
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+
+    if args.impl == "reference":
+        run_reference(args, rank)
+        return
+
+    numa = bind_to_gpu_numa(local_rank) if world > 1 else "one rank: not bound"
+    import torch
+    from bench_large import Ctx, measure_large, check_slabs_against_single_slab
+    ctx = Ctx(rank, local_rank, world)
+    if not torch.cuda.is_available() or ctx.L.ode_b200_device_count() < 1:
+        raise SystemExit("bench.py needs a CUDA device: the hot path has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        ctx.dist.init_process_group("nccl", device_id=ctx.dev)
+    peaks = None
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:  # noqa: BLE001
+        pass
+    with_cpu = not args.no_cpu_baseline
+    strict = not args.relaxed_fp
+    line = None
+    if args.workload in ("large", "field"):
+        line = measure_large(ctx, args.large_n * world, args.steps, args.warmup, field=args.workload == "field",
+                             exchange=args.exchange, with_cpu=with_cpu, peaks=peaks)
+    else:
+        n = args.n_traj
+        line = measure_lorenz(ctx, n, lorenz_ics(n, SEED + rank), args.steps, args.warmup, scaling="weak", peaks=peaks,
+                              with_cpu=with_cpu, cpu_sample=args.cpu_sample, strict_fp=strict)
+        if args.workload == "all":
+            parity = None
+            if world > 1:  # real multi-rank parity on this hardware, before the decomposed path is timed
+                ok, how = check_slabs_against_single_slab(ctx, exchange=args.exchange)
+                parity = {"slabs_equal_single_slab_bits_at_N_2^20": ok, "exchange": how}
+                assert ok, "decomposed integration differs from the single-slab result"
+            large = measure_large(ctx, args.large_n * world, args.steps, args.warmup, exchange=args.exchange,
+                                  with_cpu=with_cpu, peaks=peaks)
+            strong = None
+            if world > 1:  # fixed total work split over the ranks, next to the weak numbers
+                n_s = n // world
+                ics = lorenz_ics(n, SEED)[rank * n_s:(rank + 1) * n_s]
+                s_l = measure_lorenz(ctx, n_s, ics, args.steps, args.warmup, scaling="strong", peaks=peaks,
+                                     with_cpu=False, cpu_sample=0)
+                s_g = measure_large(ctx, args.large_n, args.steps, args.warmup, exchange=args.exchange, with_cpu=False,
+                                    scaling="strong", peaks=peaks)
+                strong = {"lorenz": s_l, "large": s_g}
+            if rank == 0:
+                if parity:
+                    large["parity_check"] = parity
+                line["large"] = large
+                if strong:
+                    line["strong"] = strong
+    if rank == 0:
+        line["host"] = {"numa": numa, "ranks": world}
         print(json.dumps(line))
     if world > 1:
-        dist.destroy_process_group()
+        ctx.dist.destroy_process_group()
 
 
 if __name__ == "__main__":

@@ -221,6 +221,7 @@ static int device_ok(int dev) {
   return 0;
 }
 
+static bool fma_kernel_available(const ode_b200_opts* o);
 // Checks shared by every ensemble entry point; mirrors the reference's errors.
 static int validate(const ode_b200_opts* o, const ode_b200_ensemble_io* io, double t0, double tend) {
   if (!o || !io) return set_err(ODE_B200_E_INVALID, "null opts/io");
@@ -240,6 +241,10 @@ static int validate(const ode_b200_opts* o, const ode_b200_ensemble_io* io, doub
   if (o->points != ODE_B200_POINTS_ALL && o->points != ODE_B200_POINTS_SPECIFIED && o->points != ODE_B200_POINTS_FINAL)
     return set_err(ODE_B200_E_POINTS, "Unrecognized option points==%d", o->points);  // src/runge_kutta.jl:289
   if (o->jacobian != 0 && o->jacobian != 1) return set_err(ODE_B200_E_INVALID, "jacobian must be 0 (fdjacobian) or 1 (analytic)");
+  if (o->fp_mode != ODE_B200_FP_STRICT && o->fp_mode != ODE_B200_FP_FMA) return set_err(ODE_B200_E_INVALID, "fp_mode must be 0 (strict) or 1 (FMA)");
+  if (o->fp_mode == ODE_B200_FP_FMA && !fma_kernel_available(o))
+    return set_err(ODE_B200_E_UNSUPPORTED, "fp_mode = FMA is built for the ensemble ode45 (Dormand-Prince) kernels with a built-in "
+                                           "right-hand side and points = final only; everything else runs in strict mode");
   if (!(o->reltol == o->reltol) || !(o->abstol == o->abstol) || !(o->minstep == o->minstep) ||
       !(o->maxstep == o->maxstep) || !(o->initstep == o->initstep))
     return set_err(ODE_B200_E_INVALID, "NaN in reltol/abstol/minstep/maxstep/initstep");
@@ -259,6 +264,7 @@ static int validate(const ode_b200_opts* o, const ode_b200_ensemble_io* io, doub
 }
 
 static bool is_adaptive_rk(int method) { return method >= ODE_B200_M_RK21 && method <= ODE_B200_M_FEH78; }
+static bool fma_kernel_available(const ode_b200_opts* o) { return false; }  // (no FMA build yet)
 static EnsembleKernel pick_kernel_fn(const ode_b200_opts* o, int mode, int literal);
 
 static const void* pick_kernel_builtin(const ode_b200_opts* o, int mode, int literal);

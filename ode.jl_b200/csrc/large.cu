@@ -335,6 +335,8 @@ int ode_b200_slab_create(const ode_b200_opts* o, int64_t n_local, int64_t n_glob
     return set_err(ODE_B200_E_NO_DEVICE, "no CUDA device available; libode_b200 has no CPU fallback");
   }
   if (o->device < 0 || o->device >= cnt) return set_err(ODE_B200_E_INVALID, "device %d out of range", o->device);
+  if (o->fp_mode != ODE_B200_FP_STRICT)
+    return set_err(ODE_B200_E_UNSUPPORTED, "the large-system kernels are built in strict mode only (fp_mode = 0)");
   const bool user_field = o->rhs >= ODE_B200_FIELD_USER_BASE;
   const bool field = user_field || o->rhs == ODE_B200_RHS_RD_FIELD;
   const bool user_stencil = !field && o->rhs >= ODE_B200_STENCIL_USER_BASE;

@@ -8,7 +8,9 @@ rank's library call copies its results device -> host straight into its slice, a
 sees the whole ensemble.  No device all-gather, no padding, nothing crosses NVLink or the network.  Ranks on
 different hosts fall back to an all_gather of the shards."""
 import os
+import shutil
 import socket
+import tempfile
 
 import numpy as np
 
@@ -20,56 +22,56 @@ _KEYS = (("t_final", np.float64, 0), ("y_final", np.float64, 1), ("n_accept", np
 _counter = [0]
 
 
-class SharedEnsembleResult:
-    """Result arrays of a whole ensemble [n_traj] in host memory shared by the ranks of one node.
-    Collective constructor and `close()`.  `arrays[k]` is the full array, `mine[k]` this rank's slice (what the
-    rank's solve writes); reusable across solves of the same shape."""
+class SharedHostBlock:
+    """`nbytes` of host memory shared by the ranks of one node (a file in /dev/shm mapped by every rank).
+    Collective constructor and `close()`; `pin(array)` page-locks a slice for this rank's device copies."""
 
-    def __init__(self, n_traj, dof, group=None, pin=True):
+    def __init__(self, nbytes, group=None):
         import torch.distributed as dist
-        self.group, self.n, self.dof = group, int(n_traj), int(dof)
+        self.group = group
         self.world = dist.get_world_size(group)
         self.rank = dist.get_rank(group)
         hosts = [None] * self.world
         dist.all_gather_object(hosts, socket.gethostname(), group=group)
         if len(set(hosts)) != 1:
             raise RuntimeError("ranks on different hosts cannot share a host buffer")
-        offs, total = {}, 0
-        for k, dt, vec in _KEYS:
-            offs[k] = total
-            total += self.n * (self.dof if vec else 1) * np.dtype(dt).itemsize
-            total = (total + 4095) & ~4095
+        nbytes = max(int(nbytes), 4096)
         name = [None]
         if self.rank == 0:
             _counter[0] += 1
-            name[0] = "/dev/shm/ode_b200_%d_%d" % (os.getpid(), _counter[0])
-            with open(name[0], "wb") as f:
-                f.truncate(max(total, 4096))
+            for d in ("/dev/shm", tempfile.gettempdir()):  # memory-backed if it fits (containers may keep /dev/shm tiny)
+                try:
+                    if shutil.disk_usage(d).free < nbytes + (64 << 20):
+                        continue
+                    name[0] = os.path.join(d, "ode_b200_%d_%d" % (os.getpid(), _counter[0]))
+                    with open(name[0], "wb") as f:
+                        f.truncate(nbytes)
+                    break
+                except OSError:
+                    name[0] = None
         dist.broadcast_object_list(name, src=dist.get_global_rank(group, 0) if group is not None else 0, group=group)
         self.path = name[0]
-        self.map = np.memmap(self.path, dtype=np.uint8, mode="r+", shape=(max(total, 4096),))
-        lo, hi = shard_bounds(self.n, self.world, self.rank)
-        self.rows = (lo, hi)
-        self.arrays, self.mine = {}, {}
-        for k, dt, vec in _KEYS:
-            shape = (self.n, self.dof) if vec else (self.n,)
-            cnt = int(np.prod(shape))
-            a = self.map[offs[k]:offs[k] + cnt * np.dtype(dt).itemsize].view(dt).reshape(shape)
-            self.arrays[k] = a
-            self.mine[k] = a[lo:hi]
+        if self.path is None:
+            raise RuntimeError("no room for a %d-byte shared host buffer" % nbytes)
+        self.map = np.memmap(self.path, dtype=np.uint8, mode="r+", shape=(nbytes,))
         self._pinned = []
-        if pin:  # page-lock this rank's slices so the device -> host copies run at full PCIe rate, asynchronously
-            try:
-                import torch
-                if torch.cuda.is_available():
-                    rt = torch.cuda.cudart()
-                    for k in self.mine:
-                        a = self.mine[k]
-                        if a.nbytes and int(rt.cudaHostRegister(a.ctypes.data, a.nbytes, 0)) == 0:
-                            self._pinned.append(a.ctypes.data)
-            except Exception:  # noqa: BLE001 -- pageable memory works too, staged
-                pass
         dist.barrier(group)
+
+    def view(self, dtype, shape, offset=0):
+        cnt = int(np.prod(shape)) * np.dtype(dtype).itemsize
+        return self.map[offset:offset + cnt].view(dtype).reshape(shape)
+
+    def pin(self, a):
+        """Page-lock the memory of array `a` (a view of this block) so device copies run at full PCIe rate."""
+        try:
+            import torch
+            if a.nbytes and torch.cuda.is_available():
+                if int(torch.cuda.cudart().cudaHostRegister(a.ctypes.data, a.nbytes, 0)) == 0:
+                    self._pinned.append(a.ctypes.data)
+                    return True
+        except Exception:  # noqa: BLE001 -- pageable memory works too, staged
+            pass
+        return False
 
     def close(self):
         import torch.distributed as dist
@@ -77,18 +79,45 @@ class SharedEnsembleResult:
             return
         if self._pinned:
             import torch
-            rt = torch.cuda.cudart()
             for p in self._pinned:
-                rt.cudaHostUnregister(p)
+                torch.cuda.cudart().cudaHostUnregister(p)
             self._pinned = []
         dist.barrier(self.group)
-        self.arrays, self.mine = {}, {}
         self.map = None
         if self.rank == 0:
             try:
                 os.unlink(self.path)
             except OSError:
                 pass
+
+
+class SharedEnsembleResult:
+    """Result arrays of a whole ensemble [n_traj] in host memory shared by the ranks of one node.
+    Collective constructor and `close()`.  `arrays[k]` is the full array, `mine[k]` this rank's slice (what the
+    rank's solve writes); reusable across solves of the same shape."""
+
+    def __init__(self, n_traj, dof, group=None, pin=True):
+        self.n, self.dof = int(n_traj), int(dof)
+        offs, total = {}, 0
+        for k, dt, vec in _KEYS:
+            offs[k] = total
+            total += self.n * (self.dof if vec else 1) * np.dtype(dt).itemsize
+            total = (total + 4095) & ~4095
+        self.block = SharedHostBlock(total, group)
+        self.group, self.world, self.rank = group, self.block.world, self.block.rank
+        lo, hi = shard_bounds(self.n, self.world, self.rank)
+        self.rows = (lo, hi)
+        self.arrays, self.mine = {}, {}
+        for k, dt, vec in _KEYS:
+            a = self.block.view(dt, (self.n, self.dof) if vec else (self.n,), offs[k])
+            self.arrays[k] = a
+            self.mine[k] = a[lo:hi]
+            if pin:  # this rank's slices: device -> host copies at full PCIe rate, asynchronously
+                self.block.pin(self.mine[k])
+
+    def close(self):
+        self.arrays, self.mine = {}, {}
+        self.block.close()
 
 
 def _gather_collective(loc, n, lo, hi, world, group, device):

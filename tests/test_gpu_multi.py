@@ -108,5 +108,7 @@ def test_multi_error_paths():
     F = m.DeviceRHS("reaction_diffusion", *RD)
     with pytest.raises(m.OdeB200Error):
         m.solve_large("ode45", F, u0(4096), [0.0, 1.0], n_gpus=n_dev() + 1)
-    with pytest.raises(m.OdeB200Error):  # slabs too short for the ghost zone
-        m.solve_large("ode45", F, u0(40), [0.0, 1.0], n_gpus=2)
+    with pytest.raises(m.OdeB200Error):  # slabs shorter than two ghost zones (ode78: H = 12)
+        m.solve_large("ode78", F, u0(40), [0.0, 1.0], n_gpus=2)
+    ok = m.solve_large("ode45", F, u0(40), [0.0, 1.0], n_gpus=2)  # 20 points per slab, H = 8: fine
+    assert np.array_equal(ok["y"], m.solve_large("ode45", F, u0(40), [0.0, 1.0])["y"])

@@ -9,10 +9,30 @@
 #
 # NOTE: written against the C ABI but NOT executed in the build container (Julia is not
 # installed there, SURVEY.md F2).  The Python mirror ode.jl_b200/api.py is the tested twin; the
-# two files marshal the same structs in the same order.
+# two files marshal the same structs in the same order (tests/test_abi.py checks the Julia struct
+# declarations below against the C header field by field).
+#
+# Like the reference (src/algorithm_types.jl), every solver name is a TYPE whose constructor-call
+# with arguments is the solver function and whose instance is the algorithm marker:
+#     tout, yout = ode45(F, y0, tspan; kw...)          # src/runge_kutta.jl:218-224
+#     sol = solve(ODEProblem(F, u0, tspan), ode45())   # src/common.jl:1-123, when DiffEqBase is loaded
 module ODEB200
 
 using Libdl
+
+# DiffEqBase is optional: with it the algorithm types join its hierarchy and `DiffEqBase.solve(prob, alg)`
+# gets a method for them (the end of this file); without it only the odeXX / solve_b200 surface exists.
+const HAVE_DIFFEQBASE = try
+    @eval import DiffEqBase
+    true
+catch
+    false
+end
+@static if HAVE_DIFFEQBASE
+    abstract type ODEB200Algorithm <: DiffEqBase.AbstractODEAlgorithm end
+else
+    abstract type ODEB200Algorithm end
+end
 
 const LIB = Ref{String}(get(ENV, "ODE_B200_LIB", joinpath(@__DIR__, "..", "ode.jl_b200", "libode_b200.so")))
 
@@ -48,6 +68,11 @@ function (f::DeviceRHS{:kepler})(t, y)
     [y[3]; y[4]; -y[1]/r3; -y[2]/r3]
 end
 
+# DiffEq-style signatures, so that ODEProblem(DeviceRHS(:lorenz, 10.0, 28.0, 8/3), u0, tspan) works with the stock
+# CPU solvers too: f(u, p, t) and f(du, u, p, t) (the problem's `p` is ignored: the token carries its parameters)
+(f::DeviceRHS)(u, p, t) = f(t, u)
+(f::DeviceRHS)(du, u, p, t) = (du .= f(t, u); nothing)
+
 # ---- right-hand sides registered at run time (CUDA C++ body, compiled by NVRTC inside the library) ------
 struct UserRHS
     id::Int32
@@ -70,8 +95,15 @@ struct Opts
     reltol::Float64; abstol::Float64; minstep::Float64; maxstep::Float64; initstep::Float64
     mathmode::Int32
     host_output::Int32
-    reserved::NTuple{6,Int32}
+    n_gpus::Int32      # fan-out inside the library over devices device .. device + n_gpus - 1
+    fp_mode::Int32     # 0 = strict (reference parity), 1 = FMA contraction (opt-in)
+    reserved::NTuple{4,Int32}
 end
+"""Opts with the tail fields spelled once (mathmode = 0, host_output = 0)."""
+make_opts(method, rhs, dof, n_params, params_stride, points, jacobian, device, max_steps, reltol, abstol, minstep,
+          maxstep, initstep; n_gpus = 1, strict_fp = true) =
+    Opts(method, rhs, dof, n_params, params_stride, points, jacobian, device, max_steps, reltol, abstol, minstep,
+         maxstep, initstep, 0, 0, n_gpus, strict_fp ? 0 : 1, ntuple(_ -> Int32(0), 4))
 
 last_error() = unsafe_string(ccall((:ode_b200_last_error, LIB[]), Cstring, ()))
 
@@ -94,9 +126,8 @@ function _solve(method::Symbol, F::Union{DeviceRHS,UserRHS}, y0, tspan;
     y = scalar ? Float64[y0] : convert(Vector{Float64}, y0)
     ts = convert(Vector{Float64}, collect(tspan))
     # jacobian = true selects the registered analytic Jacobian of F (a closure cannot run on the device)
-    o = Ref(Opts(METHODS[method], rhs_id(F), length(y), length(F.params), 0, POINTS[points],
-                 jacobian === true ? 1 : 0, device, 0,
-                 reltol, abstol, minstep, maxstep, initstep, 0, 0, ntuple(_ -> Int32(0), 6)))
+    o = Ref(make_opts(METHODS[method], rhs_id(F), length(y), length(F.params), 0, POINTS[points],
+                      jacobian === true ? 1 : 0, device, 0, reltol, abstol, minstep, maxstep, initstep))
     h = Ref{Ptr{Cvoid}}(C_NULL)
     GC.@preserve y ts F begin
         check(ccall((:ode_b200_solve_single, LIB[]), Cint,
@@ -116,9 +147,13 @@ end
 
 for name in (:ode1, :ode2_midpoint, :ode2_heun, :ode4, :ode21, :ode23, :ode45_fe, :ode45_dp, :ode45, :ode78, :ode23s,
              :ode4s, :ode4s_s, :ode4s_kr, :ode4ms)
+    # the solver name is a type (its instance is the algorithm marker, src/algorithm_types.jl); calling the type with
+    # (F, y0, tspan) is the solver function, exactly the reference's `AlgType(f, u0, Ts; ...)` at src/common.jl:93
+    @eval struct $name <: ODEB200Algorithm end
     @eval $name(F::Union{DeviceRHS,UserRHS}, y0, tspan; kw...) = _solve($(QuoteNode(name)), F, y0, tspan; kw...)
     @eval $name(F, y0, tspan; kw...) =
         error("libode_b200 takes a registered DeviceRHS; a Julia closure cannot run on the device (no CPU fallback)")
+    @eval alg_symbol(::$name) = $(QuoteNode(name))
     @eval export $name
 end
 export DeviceRHS, UserRHS, register_rhs
@@ -134,13 +169,14 @@ end
 """solve_ensemble(:ode45, F, Y0, tspan; kw...) with Y0 a dof x n_traj matrix (one trajectory per column)."""
 function solve_ensemble(method::Symbol, F::DeviceRHS, Y0::Matrix{Float64}, tspan;
                         reltol = 1.0e-5, abstol = 1.0e-8, minstep = abs(tspan[end]-tspan[1])/1e18,
-                        maxstep = abs(tspan[end]-tspan[1])/2.5, initstep = 0.0, device = 0)
+                        maxstep = abs(tspan[end]-tspan[1])/2.5, initstep = 0.0, device = 0, n_gpus = 1, strict_fp = true)
     dof, n = size(Y0)
     ts = convert(Vector{Float64}, collect(tspan))
     tf = Vector{Float64}(undef, n); yf = Matrix{Float64}(undef, dof, n)
     na = Vector{Int32}(undef, n); nr = similar(na); nf = similar(na); st = similar(na)
-    o = Ref(Opts(METHODS[method], rhs_id(F), dof, length(F.params), 0, POINTS[:final], 0, device, 0,
-                 reltol, abstol, minstep, maxstep, initstep, 0, 0, ntuple(_ -> Int32(0), 6)))
+    # n_gpus > 1: the library shards the trajectories over that many devices (one host thread each, no collective)
+    o = Ref(make_opts(METHODS[method], rhs_id(F), dof, length(F.params), 0, POINTS[:final], 0, device, 0,
+                      reltol, abstol, minstep, maxstep, initstep; n_gpus = n_gpus, strict_fp = strict_fp))
     GC.@preserve Y0 ts F tf yf na nr nf st begin
         io = Ref(EnsembleIO(n, pointer(Y0), pointer(F.params), pointer(ts), length(ts), 0,
                             pointer(tf), pointer(yf), pointer(na), pointer(nr), pointer(nf), pointer(st),
@@ -186,13 +222,15 @@ end
 built-in DeviceRHS(:reaction_diffusion, kappa, r), a registered stencil (fused kernel) or field (kernel per stage)."""
 function solve_large(method::Symbol, F::Union{DeviceRHS,UserRHS}, u0::Vector{Float64}, tspan;
                      reltol = 1.0e-5, abstol = 1.0e-8, minstep = abs(tspan[end]-tspan[1])/1e18,
-                     maxstep = abs(tspan[end]-tspan[1])/2.5, initstep = 0.0, device = 0)
+                     maxstep = abs(tspan[end]-tspan[1])/2.5, initstep = 0.0, device = 0, n_gpus = 1)
     n = length(u0)
     out = similar(u0)
     p = isempty(F.params) ? Float64[0.0] : F.params
     st = Ref(LargeStats(0, 0, 0, 0, 0, 0.0, 0.0))
-    o = Ref(Opts(METHODS[method], rhs_id(F), min(n, typemax(Int32)), length(F.params), 0, POINTS[:final], 0, device, 0,
-                 reltol, abstol, minstep, maxstep, initstep, 0, 0, ntuple(_ -> Int32(0), 6)))
+    # n_gpus > 1: the grid is cut into that many slabs, one per device, which exchange one record per step attempt
+    # over NVLink peer memory from inside the attempt kernel (ode_b200_solve_large_multi); same bits as one GPU
+    o = Ref(make_opts(METHODS[method], rhs_id(F), min(n, typemax(Int32)), length(F.params), 0, POINTS[:final], 0, device, 0,
+                      reltol, abstol, minstep, maxstep, initstep; n_gpus = n_gpus))
     GC.@preserve u0 out p begin
         check(ccall((:ode_b200_solve_large, LIB[]), Cint,
                     (Ref{Opts}, Int64, Ptr{Float64}, Ptr{Float64}, Float64, Float64, Ptr{Float64}, Ref{LargeStats},
@@ -209,8 +247,8 @@ function solve_large_fixed(method::Symbol, F::Union{DeviceRHS,UserRHS}, u0::Vect
     rows = Matrix{Float64}(undef, n, length(ts))      # column = one state (row-major [n_tspan][n] in C)
     p = isempty(F.params) ? Float64[0.0] : F.params
     st = Ref(LargeStats(0, 0, 0, 0, 0, 0.0, 0.0))
-    o = Ref(Opts(METHODS[method], rhs_id(F), min(n, typemax(Int32)), length(F.params), 0, POINTS[:all], 0, device, 0,
-                 1.0e-5, 1.0e-8, 0.0, 0.0, 0.0, 0, 0, ntuple(_ -> Int32(0), 6)))
+    o = Ref(make_opts(METHODS[method], rhs_id(F), min(n, typemax(Int32)), length(F.params), 0, POINTS[:all], 0, device, 0,
+                      1.0e-5, 1.0e-8, 0.0, 0.0, 0.0))
     GC.@preserve u0 ts rows p begin
         check(ccall((:ode_b200_solve_large_fixed, LIB[]), Cint,
                     (Ref{Opts}, Int64, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Int32, Ptr{Float64}, Ptr{Float64}, Ref{LargeStats}),
@@ -219,5 +257,154 @@ function solve_large_fixed(method::Symbol, F::Union{DeviceRHS,UserRHS}, u0::Vect
     return ts, [rows[:, i] for i in 1:length(ts)]
 end
 export register_stencil, register_field, solve_large, solve_large_fixed
+
+"""solve_large_multi(:ode45, F, u0, (t0, tend), devices; kw...): the same on an explicit list of CUDA devices."""
+function solve_large_multi(method::Symbol, F::Union{DeviceRHS,UserRHS}, u0::Vector{Float64}, tspan, devices::Vector{<:Integer};
+                           reltol = 1.0e-5, abstol = 1.0e-8, minstep = abs(tspan[end]-tspan[1])/1e18,
+                           maxstep = abs(tspan[end]-tspan[1])/2.5, initstep = 0.0)
+    n = length(u0)
+    out = similar(u0)
+    p = isempty(F.params) ? Float64[0.0] : F.params
+    devs = convert(Vector{Int32}, devices)
+    st = Ref(LargeStats(0, 0, 0, 0, 0, 0.0, 0.0))
+    o = Ref(make_opts(METHODS[method], rhs_id(F), min(n, typemax(Int32)), length(F.params), 0, POINTS[:final], 0, devs[1], 0,
+                      reltol, abstol, minstep, maxstep, initstep))
+    GC.@preserve u0 out p devs begin
+        check(ccall((:ode_b200_solve_large_multi, LIB[]), Cint,
+                    (Ref{Opts}, Int32, Ptr{Int32}, Int64, Ptr{Float64}, Ptr{Float64}, Float64, Float64, Ptr{Float64},
+                     Ref{LargeStats}, Ptr{Float64}, Int64, Ptr{Int64}),
+                    o, length(devs), devs, n, u0, p, Float64(tspan[1]), Float64(tspan[end]), out, st, C_NULL, 0, C_NULL))
+    end
+    st[].status == 1 && println("Warning: dt < minstep.  Stopping.")
+    return st[].t_final, out, st[]
+end
+export solve_large_multi
+
+# ---- slab sessions (one process per GPU, e.g. under MPI.jl): device pointers, the caller's stream ----------------
+# The per-rank flow with the exchange over peer memory:
+#     s = slab_create(:ode45, F, n_local, n_global, rank, world, (t0, tend); device = local_rank)
+#     h = slab_peer_alloc(s)                      # 64-byte handle; allgather it across the ranks (MPI.Allgather)
+#     slab_peer_connect(s, all_handles)           # Vector{UInt8} of world*64 bytes, rank order; then MPI.Barrier
+#     slab_set_state(s, d_u_local); ctl = slab_run(s); slab_get_state(s, d_u_local); slab_free(s)
+# (d_u_local: a device pointer, e.g. pointer(::CuArray{Float64}) from CUDA.jl.)
+const PEER_HANDLE_BYTES = 64
+function slab_create(method::Symbol, F::Union{DeviceRHS,UserRHS}, n_local::Integer, n_global::Integer, rank::Integer,
+                     world::Integer, tspan; reltol = 1.0e-5, abstol = 1.0e-8, minstep = abs(tspan[end]-tspan[1])/1e18,
+                     maxstep = abs(tspan[end]-tspan[1])/2.5, initstep = 0.0, device = 0, stream = C_NULL)
+    p = isempty(F.params) ? Float64[0.0] : F.params
+    o = Ref(make_opts(METHODS[method], rhs_id(F), min(n_global, typemax(Int32)), length(F.params), 0, POINTS[:final], 0,
+                      device, 0, reltol, abstol, minstep, maxstep, initstep))
+    h = Ref{Ptr{Cvoid}}(C_NULL)
+    GC.@preserve p begin
+        check(ccall((:ode_b200_slab_create, LIB[]), Cint,
+                    (Ref{Opts}, Int64, Int64, Int32, Int32, Ptr{Float64}, Float64, Float64, Ptr{Cvoid}, Ref{Ptr{Cvoid}}),
+                    o, n_local, n_global, rank, world, p, Float64(tspan[1]), Float64(tspan[end]), stream, h))
+    end
+    h[]
+end
+function slab_peer_alloc(s::Ptr{Cvoid})
+    h = zeros(UInt8, PEER_HANDLE_BYTES)
+    check(ccall((:ode_b200_slab_peer_alloc, LIB[]), Cint, (Ptr{Cvoid}, Ptr{UInt8}, Ptr{Ptr{Cvoid}}), s, h, C_NULL))
+    h
+end
+slab_peer_connect(s::Ptr{Cvoid}, handles::Vector{UInt8}) =
+    check(ccall((:ode_b200_slab_peer_connect, LIB[]), Cint, (Ptr{Cvoid}, Ptr{UInt8}, Ptr{Ptr{Cvoid}}), s, handles, C_NULL))
+slab_set_state(s::Ptr{Cvoid}, d_u::Ptr) = check(ccall((:ode_b200_slab_set_state, LIB[]), Cint, (Ptr{Cvoid}, Ptr{Cvoid}), s, d_u))
+slab_get_state(s::Ptr{Cvoid}, d_u::Ptr) = check(ccall((:ode_b200_slab_get_state, LIB[]), Cint, (Ptr{Cvoid}, Ptr{Cvoid}), s, d_u))
+slab_reset(s::Ptr{Cvoid}, t0, tend) = check(ccall((:ode_b200_slab_reset, LIB[]), Cint, (Ptr{Cvoid}, Float64, Float64), s, t0, tend))
+"""slab_run(s) -> (done, status, n_accept, n_reject, t_final, attempts, kernel_ms): the whole integration in one call."""
+function slab_run(s::Ptr{Cvoid})
+    ctl = zeros(Float64, 16)
+    ms = Ref{Float64}(0.0)
+    check(ccall((:ode_b200_slab_run, LIB[]), Cint, (Ptr{Cvoid}, Ptr{Float64}, Ref{Float64}), s, ctl, ms))
+    (done = ctl[1] != 0, status = Int(ctl[2]), n_accept = Int(ctl[3]), n_reject = Int(ctl[4]), t_final = ctl[8],
+     attempts = Int(ctl[10]), kernel_ms = ms[])
+end
+slab_free(s::Ptr{Cvoid}) = ccall((:ode_b200_slab_free, LIB[]), Cvoid, (Ptr{Cvoid},), s)
+export slab_create, slab_peer_alloc, slab_peer_connect, slab_set_state, slab_get_state, slab_reset, slab_run, slab_free
+
+# ---- DiffEqBase.solve(prob, alg): the reference's common-interface method (src/common.jl:1-123) --------------------
+# Same signature, same keyword mapping (dtmin = span/1e-9 (sic, :13), dtmax = span/2.5, saveat -> Ts, save_everystep ->
+# points, save_start), same reshaping and the same build_solution call with retcode = :Succss (:119-122).  The only
+# difference: prob.f must wrap a DeviceRHS / UserRHS token (ODEProblem(DeviceRHS(:lorenz, ...), u0, tspan)); a plain
+# Julia function raises, because there is no CPU fallback.
+@static if HAVE_DIFFEQBASE
+function DiffEqBase.solve(
+    prob::DiffEqBase.AbstractODEProblem{uType,tupType,isinplace},
+    alg::AlgType,
+    timeseries=[], ts=[], ks=[];
+    verbose=true,
+    save_timeseries=nothing,
+    saveat=eltype(tupType)[], reltol = 1e-5, abstol = 1e-8,
+    save_everystep=isempty(saveat),
+    dense = save_everystep && isempty(saveat),
+    save_start = save_everystep || isempty(saveat) || saveat isa Number ?
+                 true : prob.tspan[1] in saveat,
+    callback=nothing,
+    dtmin = abs(prob.tspan[2]-prob.tspan[1])/1e-9,
+    dtmax = abs(prob.tspan[2]-prob.tspan[1])/2.5,
+    timeseries_errors=true, dense_errors=false,
+    dt = 0.0, norm = nothing,
+    kwargs...) where {uType,tupType,isinplace,AlgType<:ODEB200Algorithm}
+
+    tType = eltype(tupType)
+    F = prob.f isa DiffEqBase.AbstractDiffEqFunction && hasproperty(prob.f, :f) ? prob.f.f : prob.f
+    F isa Union{DeviceRHS,UserRHS} ||
+        error("ODEB200: the problem's function must be a registered DeviceRHS token (no CPU fallback)")
+    norm === nothing || error("ODEB200: only the default norm (LinearAlgebra.norm) is compiled into the kernels")
+    if save_timeseries !== nothing
+        verbose && @warn("save_timeseries is deprecated. Use save_everystep instead")
+        save_everystep = save_timeseries
+    end
+    if hasproperty(prob.f, :mass_matrix) && prob.f.mass_matrix != DiffEqBase.I
+        error("This solver is not able to use mass matrices.")            # src/common.jl:42-44
+    end
+    if callback !== nothing || :callback ∈ keys(prob.kwargs)
+        error("ODE is not compatible with callbacks.")                    # :46-48
+    end
+    tspan = prob.tspan
+    if saveat isa Number                                                   # :52-61
+        if (tspan[1]:saveat:tspan[end])[end] == tspan[end]
+            saveat_vec = convert(Vector{tType}, collect(tType, tspan[1]+saveat:saveat:tspan[end]))
+        else
+            saveat_vec = convert(Vector{tType}, collect(tType, tspan[1]+saveat:saveat:(tspan[end]-saveat)))
+        end
+    else
+        saveat_vec = convert(Vector{tType}, collect(saveat))
+    end
+    if !isempty(saveat_vec) && saveat_vec[end] == tspan[2]                 # :63-65
+        pop!(saveat_vec)
+    end
+    if !isempty(saveat_vec) && saveat_vec[1] == tspan[1]                   # :67-71
+        Ts = unique([saveat_vec; tspan[2]])
+    else
+        Ts = unique([tspan[1]; saveat_vec; tspan[2]])
+    end
+    points = save_everystep ? :all : :specified                            # :72-76
+    sizeu = size(prob.u0)
+    u0 = uType <: AbstractArray ? vec(prob.u0) : prob.u0
+    # AlgType(...) is ode45(...) etc., like :93-100; fixed-step / multistep front-ends take no keywords there either
+    ts, timeseries_tmp = AlgType(F, u0, Ts; abstol = abstol, reltol = reltol, maxstep = dtmax, minstep = dtmin,
+                                 initstep = dt, points = points)
+    if save_start                                                          # :102-107
+        start_idx = 1
+    else
+        start_idx = 2
+        ts = ts[2:end]
+    end
+    if uType <: AbstractArray                                              # :110-117
+        timeseries = Vector{uType}()
+        for i = start_idx:length(timeseries_tmp)
+            push!(timeseries, reshape(timeseries_tmp[i], sizeu))
+        end
+    else
+        timeseries = timeseries_tmp
+    end
+    DiffEqBase.build_solution(prob, alg, ts, timeseries,
+                              timeseries_errors = timeseries_errors,
+                              dense_errors = dense_errors,
+                              retcode = :Succss)                           # :119-122
+end
+end # HAVE_DIFFEQBASE
 
 end # module

@@ -363,6 +363,14 @@ static int launch_ensemble(const ode_b200_opts* o, const ode_b200_ensemble_io* i
   A.redo_count = reinterpret_cast<int*>(counter + 1);
   if (uniform)
     for (int q = 0; q < np_u; q++) A.uparams[q] = uparams_host[q];
+  if (is_adaptive_rk(o->method)) {  // the tableau for the kernel-parameter constant bank (common.cuh, EnsembleArgs::tab)
+    const int S = ode_b200_method_stages(o->method);
+    for (int s1 = 1; s1 < S; s1++)
+      for (int ss = 0; ss < s1; ss++) A.tab[tab_a_index(s1, ss)] = ode_b200_tableau(o->method, 0, s1, ss);
+    for (int r = 0; r < 2; r++)
+      for (int j = 0; j < S; j++) A.tab[tab_b_index(S, r, j)] = ode_b200_tableau(o->method, 1, r, j);
+    for (int i = 0; i < S; i++) A.tab[tab_c_index(S, i)] = ode_b200_tableau(o->method, 2, i, 0);
+  }
   const bool two_pass = is_adaptive_rk(o->method);
   if (two_pass && !A.status) return set_err(ODE_B200_E_INVALID, "internal: adaptive RK launch without a status buffer");
 

@@ -127,6 +127,7 @@ __global__ void __launch_bounds__(ENS_BLOCK, LITERAL ? 1 : adapt_min_blocks<Tab,
   constexpr bool FSAL = Tab::fsal();
   constexpr double EXPO = 1.0 / (double)(Tab::ORDER + 1);  // T(1/(order+1)) :436
   constexpr int NK = S > 1 ? S - 1 : 1;
+  constexpr bool BANK = ODEB200_TAB_BANK != 0;
 
   const double tstart = A.tspan[0];
   const double tend = A.tspan[A.n_tspan - 1];
@@ -197,10 +198,11 @@ __global__ void __launch_bounds__(ENS_BLOCK, LITERAL ? 1 : adapt_min_blocks<Tab,
     // ------------------------------------------------ rk_embedded_step! :371-399
     double ytrial[D], yerr[D], dtk[NK][D], klast[D];
     constexpr double b10 = Tab::b(0, 0), b20 = Tab::b(1, 0);
+    const double b10v = BANK ? A.tab[tab_b_index(S, 0, 0)] : b10, b20v = BANK ? A.tab[tab_b_index(S, 1, 0)] : b20;
 #pragma unroll
     for (int d = 0; d < D; d++) {  // :384-387
-      ytrial[d] = LITERAL ? (0.0 + b10 * k1[d]) : ((b10 != 0.0) ? b10 * k1[d] : 0.0);
-      yerr[d] = LITERAL ? (0.0 + b20 * k1[d]) : ((b20 != 0.0) ? b20 * k1[d] : 0.0);
+      ytrial[d] = LITERAL ? (0.0 + b10v * k1[d]) : ((b10 != 0.0) ? b10v * k1[d] : 0.0);
+      yerr[d] = LITERAL ? (0.0 + b20v * k1[d]) : ((b20 != 0.0) ? b20v * k1[d] : 0.0);
       dtk[0][d] = dt * k1[d];
       klast[d] = k1[d];
     }
@@ -213,17 +215,20 @@ __global__ void __launch_bounds__(ENS_BLOCK, LITERAL ? 1 : adapt_min_blocks<Tab,
         constexpr int ss = decltype(J)::value;
         constexpr double a = Tab::a(s, ss);
         if constexpr (a != 0.0 || LITERAL) {
+          const double av = BANK ? A.tab[tab_a_index(s, ss)] : a;  // same value: the host fills tab from this tableau
 #pragma unroll
-          for (int d = 0; d < D; d++) ytmp[d] = ytmp[d] + dtk[ss][d] * a;
+          for (int d = 0; d < D; d++) ytmp[d] = ytmp[d] + dtk[ss][d] * av;
         }
       });
       constexpr double c = Tab::c(s);
-      Rhs::eval(t + c * dt, ytmp, ks, p);  // :456
+      const double cv = BANK ? A.tab[tab_c_index(S, s)] : c;
+      Rhs::eval(t + cv * dt, ytmp, ks, p);  // :456
       constexpr double b1 = Tab::b(0, s), b2 = Tab::b(1, s);
+      const double b1v = BANK ? A.tab[tab_b_index(S, 0, s)] : b1, b2v = BANK ? A.tab[tab_b_index(S, 1, s)] : b2;
 #pragma unroll
       for (int d = 0; d < D; d++) {  // :390-393
-        if constexpr (b1 != 0.0 || LITERAL) ytrial[d] = ytrial[d] + b1 * ks[d];
-        if constexpr (b2 != 0.0 || LITERAL) yerr[d] = yerr[d] + b2 * ks[d];
+        if constexpr (b1 != 0.0 || LITERAL) ytrial[d] = ytrial[d] + b1v * ks[d];
+        if constexpr (b2 != 0.0 || LITERAL) yerr[d] = yerr[d] + b2v * ks[d];
         if constexpr (s < S - 1) dtk[s][d] = dt * ks[d];
         if constexpr (s == S - 1) klast[d] = ks[d];
       }

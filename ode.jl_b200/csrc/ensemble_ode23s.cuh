@@ -23,6 +23,18 @@ struct LuReg {
   bool singular;
 
   __device__ __forceinline__ void factor() {
+    bool unused = false;
+    factor_t<true>(unused);
+  }
+  __device__ __forceinline__ void solve(double (&b)[D]) const {
+    bool unused = false;
+    solve_t<true>(b, unused);
+  }
+  // EXACT = false: straight-line code, divisions with the deferred acceptance check (div_nb) and no zero-pivot
+  // branch -- a zero pivot makes the reciprocal non-finite, which sets `bad` like any other failed check, and the
+  // caller repeats the attempt with EXACT = true, where the zero pivot is reported as `singular`.
+  template <bool EXACT>
+  __device__ __forceinline__ void factor_t(bool& bad) {
     singular = false;
 #pragma unroll
     for (int j = 0; j < D; j++) {
@@ -48,12 +60,12 @@ struct LuReg {
         }
       }
       rd[j] = 0.0;
-      if (a[j][j] == 0.0) {
+      if (EXACT && a[j][j] == 0.0) {
         singular = true;
       } else {
         Recip R = recip_prepare(a[j][j]);
         rd[j] = R.r;
-        double rp = div_by(1.0, R);
+        double rp = div_sel<EXACT>(1.0, R, bad);
 #pragma unroll
         for (int i = j + 1; i < D; i++) a[i][j] = a[i][j] * rp;
 #pragma unroll
@@ -64,7 +76,8 @@ struct LuReg {
       }
     }
   }
-  __device__ __forceinline__ void solve(double (&b)[D]) const {
+  template <bool EXACT>
+  __device__ __forceinline__ void solve_t(double (&b)[D], bool& bad) const {
 #pragma unroll
     for (int j = 0; j < D; j++) {
 #pragma unroll
@@ -85,7 +98,7 @@ struct LuReg {
       Recip R;
       R.b = a[j][j];
       R.r = rd[j];
-      b[j] = div_by<true>(b[j], R);
+      b[j] = div_sel<EXACT, true>(b[j], R, bad);
 #pragma unroll
       for (int i = 0; i < j; i++) b[i] = b[i] - b[j] * a[i][j];
     }
@@ -93,32 +106,45 @@ struct LuReg {
 };
 
 // fdjacobian, src/ODE.jl:232-243 (recomputes F(t,x), D+1 RHS calls).
-template <class Rhs, int D, int NPA>
-__device__ __forceinline__ void fd_jacobian(double t, const double (&x)[D], const double (&p)[NPA], double (&J)[D][D]) {
+template <class Rhs, int D, int NPA, bool EXACT = true>
+__device__ __forceinline__ void fd_jacobian(double t, const double (&x)[D], const double (&p)[NPA], double (&J)[D][D],
+                                            bool& bad) {
   double ftx[D];
   Rhs::eval(t, x, ftx, p);  // :233
+  const Recip R100 = recip_prepare(100.0);
 #pragma unroll
   for (int j = 0; j < D; j++) {  // :236
-    const double dxj = div_by(x[j] + ((x[j] == 0.0) ? 1.0 : 0.0), recip_prepare(100.0));  // :239
+    const double dxj = div_sel<EXACT>(x[j] + ((x[j] == 0.0) ? 1.0 : 0.0), R100, bad);  // :239
     const Recip Rdx = recip_prepare(dxj);
     double xp[D], fp[D];
 #pragma unroll
     for (int i = 0; i < D; i++) xp[i] = x[i] + ((i == j) ? dxj : 0.0);
     Rhs::eval(t, xp, fp, p);
 #pragma unroll
-    for (int i = 0; i < D; i++) J[i][j] = div_by<true>(fp[i] - ftx[i], Rdx);  // :240
+    for (int i = 0; i < D; i++) J[i][j] = div_sel<EXACT, true>(fp[i] - ftx[i], Rdx, bad);  // :240
   }
+}
+template <class Rhs, int D, int NPA>
+__device__ __forceinline__ void fd_jacobian(double t, const double (&x)[D], const double (&p)[NPA], double (&J)[D][D]) {
+  bool unused = false;
+  fd_jacobian<Rhs, D, NPA, true>(t, x, p, J, unused);
 }
 
 // jac = jacobian(t, y): the registered analytic functor (JAC = 1) or fdjacobian (JAC = 0), :262-267
-template <class Rhs, int JAC, int D, int NPA>
-__device__ __forceinline__ int eval_jacobian(double t, const double (&x)[D], const double (&p)[NPA], double (&J)[D][D]) {
+template <class Rhs, int JAC, int D, int NPA, bool EXACT = true>
+__device__ __forceinline__ int eval_jacobian(double t, const double (&x)[D], const double (&p)[NPA], double (&J)[D][D],
+                                             bool& bad) {
   if (JAC) {
     Rhs::jac(t, x, J, p);
     return 0;
   }
-  fd_jacobian<Rhs, D, NPA>(t, x, p, J);
+  fd_jacobian<Rhs, D, NPA, EXACT>(t, x, p, J, bad);
   return D + 1;
+}
+template <class Rhs, int JAC, int D, int NPA>
+__device__ __forceinline__ int eval_jacobian(double t, const double (&x)[D], const double (&p)[NPA], double (&J)[D][D]) {
+  bool unused = false;
+  return eval_jacobian<Rhs, JAC, D, NPA, true>(t, x, p, J, unused);
 }
 
 template <class Rhs, int MODE, int JAC>
@@ -224,39 +250,50 @@ __global__ void __launch_bounds__(ENS_BLOCK, (Rhs::DOF <= 3) ? ODEB200_S23_MINB 
     } else {
       attempts++;
       if (fabs(t - tfinal) < fabs(h)) h = tfinal - t;  // :297-299
-      LuReg<D> W;                                     // :301-310
       const double hd = h * dd;
+      // One attempt (:301-324) as straight-line arithmetic.  EXACT = false: every division carries a deferred
+      // acceptance check (div_nb) and there is no zero-pivot branch; if any check failed (`bad`) the attempt is
+      // repeated with EXACT = true -- the branchy, always-correct divisions -- which produces the same bits whenever
+      // the fast pass would have been accepted, so the two passes never disagree.  With ODEB200_S23_SPECJ the
+      // Jacobian of the NEXT step, J(t + h, ynew) (:352), is part of the attempt and simply dropped on a rejection.
+      double k1[D], k2[D], ynew[D], F2[D], Jn[D][D];
+      double err = 0.0, delta = 0.0;
+      bool singular = false;
+      int jac_rhs = 0;
+      auto attempt = [&](auto EX, bool& bad) {
+        constexpr bool EXACT = decltype(EX)::value != 0;
+        LuReg<D> W;  // :301-310
 #pragma unroll
-      for (int i = 0; i < D; i++) {
+        for (int i = 0; i < D; i++) {
 #pragma unroll
-        for (int j = 0; j < D; j++) {
-          double Jij;
-          if constexpr (JS) Jij = Jsh[i * D + j][threadIdx.x];
-          else Jij = Jreg[i][j];
-          double m = -(hd * Jij);
-          W.a[i][j] = (i == j) ? (m + 1.0) : m;
+          for (int j = 0; j < D; j++) {
+            double Jij;
+            if constexpr (JS) Jij = Jsh[i * D + j][threadIdx.x];
+            else Jij = Jreg[i][j];
+            double m = -(hd * Jij);
+            W.a[i][j] = (i == j) ? (m + 1.0) : m;
+          }
         }
-      }
-      W.factor();
-      if (W.singular) {
-        fin = ODE_B200_ST_SINGULAR;
-      } else {
-        double Fa[D], T[D], k1[D], k2[D], k3[D], F1[D], F2[D], ynew[D], tmp[D];
-        const double h100 = div_by(h, recip_prepare(100.0));
+        W.template factor_t<EXACT>(bad);
+        singular = W.singular;
+        if (EXACT && singular) return;
+        double Fa[D], T[D], k3[D], F1[D], tmp[D];
+        const Recip R100 = recip_prepare(100.0);
+        const double h100 = div_sel<EXACT>(h, R100, bad);
         Rhs::eval(t + h100, y, Fa, p);  // :313
         const Recip Rh100 = recip_prepare(h100);
 #pragma unroll
-        for (int i = 0; i < D; i++) T[i] = div_by<true>(hd * (Fa[i] - F0[i]), Rh100);
+        for (int i = 0; i < D; i++) T[i] = div_sel<EXACT, true>(hd * (Fa[i] - F0[i]), Rh100, bad);
 #pragma unroll
         for (int i = 0; i < D; i++) k1[i] = F0[i] + T[i];  // :316
-        W.solve(k1);
+        W.template solve_t<EXACT>(k1, bad);
         const double hh = 0.5 * h;
 #pragma unroll
         for (int i = 0; i < D; i++) tmp[i] = y[i] + hh * k1[i];  // :317
         Rhs::eval(t + 0.5 * h, tmp, F1, p);
 #pragma unroll
         for (int i = 0; i < D; i++) k2[i] = F1[i] - k1[i];  // :318
-        W.solve(k2);
+        W.template solve_t<EXACT>(k2, bad);
 #pragma unroll
         for (int i = 0; i < D; i++) k2[i] = k2[i] + k1[i];
 #pragma unroll
@@ -264,12 +301,26 @@ __global__ void __launch_bounds__(ENS_BLOCK, (Rhs::DOF <= 3) ? ODEB200_S23_MINB 
         Rhs::eval(t + h, ynew, F2, p);                           // :320
 #pragma unroll
         for (int i = 0; i < D; i++) k3[i] = ((F2[i] - e32 * (k2[i] - F1[i])) - 2 * (k1[i] - F0[i])) + T[i];  // :321
-        W.solve(k3);
-        nrhs += 3;
+        W.template solve_t<EXACT>(k3, bad);
+        if (ODEB200_S23_SPECJ) jac_rhs = eval_jacobian<Rhs, JAC, D, NPA, EXACT>(t + h, ynew, p, Jn, bad);  // :352, ahead of time
 #pragma unroll
         for (int i = 0; i < D; i++) tmp[i] = (k1[i] - 2 * k2[i]) + k3[i];
-        const double err = div_by(fabs(h), recip_prepare(6.0)) * norm2_small<D>(tmp);  // :323
-        const double delta = jl_max(A.reltol * jl_max(norm2_small<D>(y), norm2_small<D>(ynew)), A.abstol);  // :324
+        err = div_sel<EXACT>(fabs(h), recip_prepare(6.0), bad) * norm2_sel<EXACT, D>(tmp, bad);  // :323
+        delta = jl_max(A.reltol * jl_max(norm2_sel<EXACT, D>(y, bad), norm2_sel<EXACT, D>(ynew, bad)), A.abstol);  // :324
+      };
+      bool bad = false;
+      if (ODEB200_S23_DEFER) {
+        attempt(iconst<0>{}, bad);
+#ifndef ODEB200_S23_NOEXACT
+        if (bad) attempt(iconst<1>{}, bad);
+#endif
+      } else {
+        attempt(iconst<1>{}, bad);
+      }
+      if (singular) {
+        fin = ODE_B200_ST_SINGULAR;
+      } else {
+        nrhs += 3;
         const bool accept = err <= delta;  // :327
         if (MODE == 1 && idx == A.trace_traj) {
           if (ntrace < A.trace_cap) {
@@ -317,16 +368,14 @@ __global__ void __launch_bounds__(ENS_BLOCK, (Rhs::DOF <= 3) ? ODEB200_S23_MINB 
             y[i] = ynew[i];  // :349
             F0[i] = F2[i];   // :351
           }
-          {
-            double Jt[D][D];
-            nrhs += eval_jacobian<Rhs, JAC, D, NPA>(t, y, p, Jt);  // :352
+          if (!ODEB200_S23_SPECJ) jac_rhs = eval_jacobian<Rhs, JAC, D, NPA>(t, y, p, Jn);  // :352
+          nrhs += jac_rhs;
 #pragma unroll
-            for (int i = 0; i < D; i++) {
+          for (int i = 0; i < D; i++) {
 #pragma unroll
-              for (int j = 0; j < D; j++) {
-                if constexpr (JS) Jsh[i * D + j][threadIdx.x] = Jt[i][j];
-                else Jreg[i][j] = Jt[i][j];
-              }
+            for (int j = 0; j < D; j++) {
+              if constexpr (JS) Jsh[i * D + j][threadIdx.x] = Jn[i][j];
+              else Jreg[i][j] = Jn[i][j];
             }
           }
         } else {

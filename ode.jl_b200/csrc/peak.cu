@@ -119,6 +119,14 @@ __global__ void div_selftest_kernel(unsigned long long seed, int per_thread, uns
     const unsigned long long ug = (unsigned long long)__double_as_longlong(got), uw = (unsigned long long)__double_as_longlong(want);
     const bool both_nan = (got != got) && (want != want);
     if (ug != uw && !both_nan) bad++;
+    // the branch-free variants: whenever their deferred check passes, the value must be the IEEE one
+    bool flag = false;
+    const double gnb = (it & 8) ? div_nb<true>(a, R, flag) : div_nb<false>(a, R, flag);
+    if (!flag && (unsigned long long)__double_as_longlong(gnb) != uw && !((gnb != gnb) && (want != want))) bad++;
+    flag = false;
+    const double snb = sqrt_nb(a, flag), swant = sqrt(a);
+    if (!flag && (unsigned long long)__double_as_longlong(snb) != (unsigned long long)__double_as_longlong(swant)) bad++;
+    if (kind == 1 && a > 0.0 && flag) bad++;  // mid-range positive arguments must take the fast path
   }
   if (bad) atomicAdd(mismatches, bad);
 }

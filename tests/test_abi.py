@@ -83,3 +83,85 @@ def test_host_rhs_tokens_match_oracle_rhs():
         a = np.atleast_1d(m.DeviceRHS(name, *p)(0.3, y))
         b = O.rhs_eval(name, 0.3, y, p if p else None)
         assert np.array_equal(a, b), name
+
+
+# ---- the header from plain C, and the struct declarations of the other bindings against it --------------------------
+def build_abi_smoke(tmp):
+    import subprocess
+    exe = os.path.join(str(tmp), "abi_smoke")
+    libdir = os.path.join(ROOT, "ode.jl_b200")
+    cc = "/usr/bin/gcc" if os.path.exists("/usr/bin/gcc") else "gcc"
+    subprocess.check_call([cc, "-std=c11", "-Wall", "-Wextra", "-Werror", "-I" + os.path.join(ROOT, "include"),
+                           os.path.join(ROOT, "tests", "abi_smoke.c"), "-o", exe, "-L" + libdir, "-lode_b200", "-lm",
+                           "-Wl,-rpath," + libdir])
+    return exe
+
+
+def test_header_compiles_as_c11_and_layouts_hold(tmp_path):
+    """tests/abi_smoke.c: static_asserts on sizeof/offsetof of the ABI structs; the program itself solves the README
+    problem on a GPU box and must get ODE_B200_E_NO_DEVICE here."""
+    import subprocess
+    exe = build_abi_smoke(tmp_path)
+    r = subprocess.run([exe], capture_output=True, text=True)
+    assert r.returncode == 0, r.stdout + r.stderr
+    if m.lib().ode_b200_device_count() < 1:
+        assert "ODE_B200_E_NO_DEVICE" in r.stdout
+
+
+def c_struct_fields(name):
+    """[(ctype, field, array_len)] of `typedef struct { ... } name;` in the header."""
+    src = re.sub(r"/\*.*?\*/", "", open(HEADER).read(), flags=re.S)
+    body = re.search(r"typedef struct\s*\{([^}]*)\}\s*%s\s*;" % name, src).group(1)
+    out = []
+    for decl in body.split(";"):
+        decl = " ".join(decl.split())
+        if not decl:
+            continue
+        mm = re.match(r"(const )?([a-z0-9_]+)\s*(\*?)\s*(.*)$", decl)
+        ctype, ptr, names = mm.group(2), mm.group(3), mm.group(4)
+        for nm in names.split(","):
+            nm = nm.strip()
+            p = ptr or ("*" if nm.startswith("*") else "")
+            nm = nm.lstrip("* ")
+            arr = re.match(r"([a-z0-9_]+)\[(\d+)\]", nm)
+            out.append((ctype + p, arr.group(1) if arr else nm, int(arr.group(2)) if arr else 0))
+    return out
+
+
+def test_python_and_julia_struct_declarations_match_the_header():
+    from ode_jl_b200 import _lib
+    ctype_of = {"int32_t": C.c_int32, "int64_t": C.c_int64, "double": C.c_double}
+    for cname, py in (("ode_b200_opts", _lib.Opts), ("ode_b200_ensemble_io", _lib.EnsembleIO),
+                      ("ode_b200_large_stats", _lib.LargeStats)):
+        want = c_struct_fields(cname)
+        assert [f for _, f, _ in want] == [f[0] for f in py._fields_], cname
+        for (ct, fname, arr), (pname, ptype) in zip(want, py._fields_):
+            if ct.endswith("*"):
+                assert ptype is C.c_void_p, (cname, fname)
+            elif arr:
+                assert ptype._length_ == arr and ptype._type_ is ctype_of[ct], (cname, fname)
+            else:
+                assert ptype is ctype_of[ct], (cname, fname)
+    from oracle import oracle as O
+    assert [f[0] for f in O.Opts._fields_] == [f for _, f, _ in c_struct_fields("ode_b200_opts")]
+    assert C.sizeof(_lib.Opts) == 112 and C.sizeof(O.Opts) == 112
+    # julia/ODEB200.jl: same fields, same order, same widths
+    jl = open(os.path.join(ROOT, "julia", "ODEB200.jl")).read()
+    jtype = {"int32_t": "Int32", "int64_t": "Int64", "double": "Float64"}
+    for cname, jname in (("ode_b200_opts", "Opts"), ("ode_b200_ensemble_io", "EnsembleIO"),
+                         ("ode_b200_large_stats", "LargeStats")):
+        body = re.search(r"^struct %s\n(.*?)^end" % jname, jl, flags=re.S | re.M).group(1)
+        body = re.sub(r"#.*", "", body)
+        fields = re.findall(r"([a-z0-9_]+)::([A-Za-z0-9{},]+)", body)
+        want = c_struct_fields(cname)
+        assert [f for f, _ in fields] == [f for _, f, _ in want], jname
+        for (ct, fname, arr), (_, jt) in zip(want, fields):
+            if ct.endswith("*"):
+                assert jt.startswith("Ptr{"), (jname, fname)
+            elif arr:
+                assert jt == "NTuple{%d,%s}" % (arr, jtype[ct]), (jname, fname)
+            else:
+                assert jt == jtype[ct], (jname, fname)
+    # every ccall in the shim names a symbol the header declares
+    for sym in set(re.findall(r"\(:(ode_b200_[a-z0-9_]+), LIB\[\]\)", jl)):
+        assert sym in declared_symbols(), sym

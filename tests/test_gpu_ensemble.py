@@ -480,3 +480,13 @@ def test_cuda_path_against_committed_golden_runs():
         got = dict(n_accept=int(st["n_accept"]), n_reject=int(st["n_reject"]), n_rhs=int(st["n_rhs"]), status=int(st["status"]),
                    n_out=len(t), t_final=float(t[-1]).hex(), y_final=[float(v).hex() for v in np.atleast_1d(y[-1])])
         assert got == want, c["name"]
+
+
+def test_plain_c_program_solves_the_readme_problem(tmp_path):
+    """tests/abi_smoke.c, built with gcc against include/ode_b200.h: the README problem (config 1) through
+    ode_b200_solve_single from plain C -- 11 accepted / 0 rejected steps, y(1) = 1.3728005108017367."""
+    import subprocess
+    from test_abi import build_abi_smoke
+    r = subprocess.run([build_abi_smoke(tmp_path)], capture_output=True, text=True)
+    assert r.returncode == 0, r.stdout + r.stderr
+    assert "11 accepted, 0 rejected" in r.stdout

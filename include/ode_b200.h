@@ -66,8 +66,15 @@ typedef enum {
   ODE_B200_M_ODE4S_S = 10, /* ode4s = ode4s_s  oderosenbrock with Shampine coefficients, src/ODE.jl:366-438 */
   ODE_B200_M_ODE4S_KR = 11,/* ode4s_kr         oderosenbrock with Kaps-Rentrop coefficients, src/ODE.jl:408-419 */
   ODE_B200_M_ODE4MS = 12,  /* ode4ms           Adams-Bashforth order 4, ode_ms src/ODE.jl:175-212 */
-  ODE_B200_M_COUNT = 13
+  ODE_B200_M_ODE5MS = 13,  /* ode5ms           ode_ms(F, x0, tspan, 5) src/ODE.jl:213; the order-5 row is computed in floating
+                              point the way the reference does it with Polynomials (:183-194) */
+  ODE_B200_M_ODE_MS1 = 14, /* ode_ms(F, x0, tspan, 1): the first row of ms_coefficients4 (src/ODE.jl:180-181,440) */
+  ODE_B200_M_ODE_MS2 = 15, /* ode_ms(F, x0, tspan, 2) */
+  ODE_B200_M_ODE_MS3 = 16, /* ode_ms(F, x0, tspan, 3) */
+  ODE_B200_M_COUNT = 17
 } ode_b200_method;
+/* order of an ode_ms method id (1..5), 0 for every other method */
+#define ODE_B200_MS_MAX_ORDER 5
 
 /* ---- registered right-hand sides F(t, y; params) ------------------------- */
 typedef enum {
@@ -197,6 +204,10 @@ int ode_b200_rhs_nparams(int rhs);
 int ode_b200_method_stages(int method);     /* S of the tableau (src/runge_kutta.jl:66-157), 3 for ode23s */
 int ode_b200_method_is_adaptive(int method);/* isadaptive, src/runge_kutta.jl:58 */
 int ode_b200_method_is_fsal(int method);    /* isFSAL, src/runge_kutta.jl:62 */
+int ode_b200_method_ms_order(int method);   /* order of ode_ms for ode4ms / ode5ms / ode_ms1..3, 0 for other methods */
+/* b[order][j] of ode_ms (src/ODE.jl:180-194): rows 1-4 are ms_coefficients4 (:440-443), row 5 the reference's
+ * floating-point evaluation; order, j 1-based, j <= order; NaN outside */
+double ode_b200_ms_coefficient(int order, int j);
 /* Tableau entry as the reference converts it (Rational -> Float64, src/ODE.jl:163).
  * which: 0 = a[i][j], 1 = b[i][j] (i = 0 stepping row, 1 error row), 2 = c[i]. */
 double ode_b200_tableau(int method, int which, int i, int j);
@@ -285,7 +296,7 @@ int ode_b200_solve_large_multi(const ode_b200_opts* opts, int32_t n_gpus, const 
                                const double* y0, const double* params, double t0, double tend, double* y_out,
                                ode_b200_large_stats* stats, double* trace, int64_t trace_cap, int64_t* trace_n);
 
-/* oderk_fixed (src/runge_kutta.jl:176-212: ode1, ode2_midpoint, ode2_heun, ode4) and ode4ms (src/ODE.jl:175-212) on a
+/* oderk_fixed (src/runge_kutta.jl:176-212: ode1, ode2_midpoint, ode2_heun, ode4) and ode_ms (src/ODE.jl:175-213: ode4ms, ode5ms, orders 1-3) on a
  * dof = N state with a stencil or field right-hand side: one step per tspan interval, one kernel per stage.
  * pts_y (optional) is [n_tspan][n] and
  * receives one state per tspan entry like the reference's yout; y_final (optional) the last one. */

@@ -15,6 +15,7 @@ from .rhs import DeviceRHS
 
 _FIXED = ("ode1", "ode2_midpoint", "ode2_heun", "ode4")
 _ROSENBROCK_FIXED = ("ode4s", "ode4s_s", "ode4s_kr")  # oderosenbrock(...; jacobian=nothing, kwargs...), src/ODE.jl:366
+_MULTISTEP = ("ode4ms", "ode5ms", "ode_ms1", "ode_ms2", "ode_ms3", "ode_ms4", "ode_ms5")  # ode_ms, src/ODE.jl:175-213
 
 
 def _vp(a):
@@ -121,8 +122,8 @@ def _solve_single(name, F, y0, tspan, _stats=False, **kw):
         kw = {"jacobian": kw.get("jacobian")}  # the other keywords are swallowed by kwargs... (src/ODE.jl:366)
         if name == "ode4s":
             kw = {}  # ode4s(F, x0, tspan; jacobian=nothing, kwargs...) passes jacobian=nothing on (src/ODE.jl:437-438)
-    elif name == "ode4ms":
-        kw = {}  # ode_ms(F, x0, tspan, order; kwargs...) ignores keywords (src/ODE.jl:175,212)
+    elif name in _MULTISTEP:
+        kw = {}  # ode_ms(F, x0, tspan, order; kwargs...) ignores keywords (src/ODE.jl:175,212-213)
     o = make_opts(name, F, ts, **kw)
     if y.size != o.dof:
         raise ValueError("%r has %d components, y0 has %d" % (F, o.dof, y.size))
@@ -167,6 +168,16 @@ ode4s_s = Solver("ode4s_s")    # Shampine coefficients, src/ODE.jl:433
 ode4s_kr = Solver("ode4s_kr")  # Kaps-Rentrop coefficients, src/ODE.jl:419
 ode4s = Solver("ode4s")        # = ode4s_s with jacobian=nothing, src/ODE.jl:437
 ode4ms = Solver("ode4ms")      # Adams-Bashforth order 4, src/ODE.jl:212
+ode5ms = Solver("ode5ms")      # order 5, src/ODE.jl:213 (not exported by the reference either: ODE.ode5ms)
+
+
+def ode_ms(F, x0, tspan, order, **kw):
+    """ode_ms(F, x0, tspan, order; kwargs...) (src/ODE.jl:175): fixed-step Adams-Bashforth of order 1..5 on the tspan
+    grid, the first steps at reduced order."""
+    if int(order) != order or not 1 <= int(order) <= 5:
+        raise ValueError("ode_ms is built for order 1..5 (the reference computes higher orders with Polynomials)")
+    return _solve_single("ode_ms%d" % int(order), F, x0, tspan, **kw)
+
 
 
 def pinned_empty(shape, dtype=np.float64):

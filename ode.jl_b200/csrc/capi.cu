@@ -157,7 +157,9 @@ static const NameId kMethods[] = {
     {"ode45_fe", ODE_B200_M_RK45_FE},  {"rk45", ODE_B200_M_RK45_FE},      {"ode45", ODE_B200_M_DOPRI5},
     {"ode45_dp", ODE_B200_M_DOPRI5},   {"dopri5", ODE_B200_M_DOPRI5},     {"ode78", ODE_B200_M_FEH78},
     {"feh78", ODE_B200_M_FEH78},       {"ode23s", ODE_B200_M_ODE23S},     {"ode4s", ODE_B200_M_ODE4S_S},
-    {"ode4s_s", ODE_B200_M_ODE4S_S},   {"ode4s_kr", ODE_B200_M_ODE4S_KR}, {"ode4ms", ODE_B200_M_ODE4MS}};
+    {"ode4s_s", ODE_B200_M_ODE4S_S},   {"ode4s_kr", ODE_B200_M_ODE4S_KR}, {"ode4ms", ODE_B200_M_ODE4MS},
+    {"ode5ms", ODE_B200_M_ODE5MS},     {"ode_ms1", ODE_B200_M_ODE_MS1},   {"ode_ms2", ODE_B200_M_ODE_MS2},
+    {"ode_ms3", ODE_B200_M_ODE_MS3},   {"ode_ms4", ODE_B200_M_ODE4MS},    {"ode_ms5", ODE_B200_M_ODE5MS}};
 static const NameId kRhs[] = {{"linear", ODE_B200_RHS_LINEAR},
                               {"const", ODE_B200_RHS_CONST},
                               {"timelin", ODE_B200_RHS_TIMELIN},
@@ -204,9 +206,55 @@ static bool rhs_shape(int rhs, int* dof, int* np, bool* has_jac) {
   return user_rhs_info(rhs, dof, np, has_jac);
 }
 
+// order of ode_ms for a method id (0: not a multistep method)
+int ms_order(int method) {
+  switch (method) {
+    case ODE_B200_M_ODE_MS1: return 1;
+    case ODE_B200_M_ODE_MS2: return 2;
+    case ODE_B200_M_ODE_MS3: return 3;
+    case ODE_B200_M_ODE4MS: return 4;
+    case ODE_B200_M_ODE5MS: return 5;
+    default: return 0;
+  }
+}
+// b[order][j] of ode_ms (0-based here).  Rows 1-4: ms_coefficients4 (src/ODE.jl:440-443) -- Julia evaluates the
+// literals -1/2, 5/12, ... as Float64 divisions, so do we.  Row 5 (src/ODE.jl:183-194): for j = 0..4
+//   p     = poly(roots -[0:j-1; j+1:4])          monic, from its roots by successive multiplication (exact: small integers)
+//   p_int = polyint(p)                           coefficient k -> a_k/(k+1)
+//   b[5, 5-j] = (-1)^j / factorial(j) / factorial(4-j) * polyval(p_int, 1)     left to right; polyval = Horner
+// The exact values are [251, -1274, 2616, -2774, 1901]/720; the bits below are the ones this evaluation order gives
+// (Polynomials.jl's own order cannot be checked here: no Julia -- parity of this row is unpinned).
+double ms_coefficient(int order, int j) {
+  static const double B4[4][4] = {{1, 0, 0, 0},
+                                  {-1.0 / 2, 3.0 / 2, 0, 0},
+                                  {5.0 / 12, -4.0 / 3, 23.0 / 12, 0},
+                                  {-9.0 / 24, 37.0 / 24, -59.0 / 24, 55.0 / 24}};
+  if (order < 1 || order > ODE_B200_MS_MAX_ORDER || j < 0 || j >= order) return NAN;
+  if (order <= 4) return B4[order - 1][j];
+  const int s = 5, jj = s - 1 - j;  // b[s, s - jj] (1-based) is column j (0-based)
+  double p[8] = {1.0};              // ascending coefficients of the monic polynomial
+  int deg = 0;
+  for (int r = 0; r <= s - 1; r++) {
+    if (r == jj) continue;
+    const double root = -(double)r;  // multiply by (x - root)
+    for (int k = deg + 1; k >= 1; k--) p[k] = p[k - 1] - root * p[k];
+    p[0] = -root * p[0];
+    deg++;
+  }
+  double pint[9] = {0.0};
+  for (int k = 0; k <= deg; k++) pint[k + 1] = p[k] / (double)(k + 1);
+  double v = pint[deg + 1];
+  for (int k = deg; k >= 0; k--) v = pint[k] + 1.0 * v;  // polyval(p_int, 1), Horner
+  double fj = 1.0, fs = 1.0;
+  for (int k = 2; k <= jj; k++) fj *= k;
+  for (int k = 2; k <= s - 1 - jj; k++) fs *= k;
+  const double sign = (jj % 2) ? -1.0 : 1.0;
+  return sign / fj / fs * v;
+}
+
 static bool is_fixed_step(int method) {
   return method <= ODE_B200_M_RK4 || method == ODE_B200_M_ODE4S_S || method == ODE_B200_M_ODE4S_KR ||
-         method == ODE_B200_M_ODE4MS;
+         ms_order(method) > 0;
 }
 
 static int device_ok(int dev) {
@@ -289,8 +337,7 @@ static EnsembleKernel pick_kernel_fn(const ode_b200_opts* o, int mode, int liter
     case ODE_B200_M_ODE23S: return ode23s_kernel(o->rhs, mode, o->jacobian);
     case ODE_B200_M_ODE4S_S:
     case ODE_B200_M_ODE4S_KR: return rosenbrock_kernel(o->method, o->rhs, o->jacobian);
-    case ODE_B200_M_ODE4MS: return ms4_kernel(o->rhs);
-    default: return fixed_kernel(o->method, o->rhs);
+    default: return ms_order(o->method) > 0 ? ms_kernel(o->rhs) : fixed_kernel(o->method, o->rhs);
   }
 }
 
@@ -363,6 +410,11 @@ static int launch_ensemble(const ode_b200_opts* o, const ode_b200_ensemble_io* i
   A.redo_count = reinterpret_cast<int*>(counter + 1);
   if (uniform)
     for (int q = 0; q < np_u; q++) A.uparams[q] = uparams_host[q];
+  if (ms_order(o->method) > 0) {  // ode_ms: order and b[so-1][j] for the kernel
+    A.ms_order = ms_order(o->method);
+    for (int so = 1; so <= A.ms_order; so++)
+      for (int j = 0; j < so; j++) A.tab[(so - 1) * ODE_B200_MS_MAX_ORDER + j] = ms_coefficient(so, j);
+  }
   if (is_adaptive_rk(o->method)) {  // the tableau for the kernel-parameter constant bank (common.cuh, EnsembleArgs::tab)
     const int S = ode_b200_method_stages(o->method);
     for (int s1 = 1; s1 < S; s1++)
@@ -473,7 +525,8 @@ int ode_b200_rhs_nparams(int rhs) {
 }
 int ode_b200_method_stages(int method) {
   if (method == ODE_B200_M_ODE23S) return 3;
-  if (method == ODE_B200_M_ODE4S_S || method == ODE_B200_M_ODE4S_KR || method == ODE_B200_M_ODE4MS) return 4;
+  if (method == ODE_B200_M_ODE4S_S || method == ODE_B200_M_ODE4S_KR) return 4;
+  if (ms_order(method) > 0) return ms_order(method);
 #define X(T) return T::S
   ODEB200_TAB_SWITCH(method, X)
 #undef X
@@ -481,14 +534,14 @@ int ode_b200_method_stages(int method) {
 }
 int ode_b200_method_is_adaptive(int method) {
   if (method == ODE_B200_M_ODE23S) return 1;
-  if (method == ODE_B200_M_ODE4S_S || method == ODE_B200_M_ODE4S_KR || method == ODE_B200_M_ODE4MS) return 0;
+  if (method == ODE_B200_M_ODE4S_S || method == ODE_B200_M_ODE4S_KR || ms_order(method) > 0) return 0;
 #define X(T) return T::NB == 2
   ODEB200_TAB_SWITCH(method, X)
 #undef X
   return ODE_B200_E_INVALID;
 }
 int ode_b200_method_is_fsal(int method) {
-  if (method == ODE_B200_M_ODE4S_S || method == ODE_B200_M_ODE4S_KR || method == ODE_B200_M_ODE4MS) return 0;
+  if (method == ODE_B200_M_ODE4S_S || method == ODE_B200_M_ODE4S_KR || ms_order(method) > 0) return 0;
   if (method == ODE_B200_M_ODE23S) return 1;  // F0 = F2, src/ODE.jl:351
 #define X(T)                       \
   {                                \
@@ -499,6 +552,8 @@ int ode_b200_method_is_fsal(int method) {
 #undef X
   return ODE_B200_E_INVALID;
 }
+int ode_b200_method_ms_order(int method) { return ms_order(method); }
+double ode_b200_ms_coefficient(int order, int j) { return ms_coefficient(order, j - 1); }
 double ode_b200_tableau(int method, int which, int i, int j) {
 #define X(T) return tab_get<T>(which, i, j)
   ODEB200_TAB_SWITCH(method, X)

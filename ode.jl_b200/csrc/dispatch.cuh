@@ -21,7 +21,7 @@ EnsembleKernel adapt_kernel_feh78_init(int rhs);  // hinit pre-pass (ens_adapt_i
 EnsembleKernel fixed_kernel(int method, int rhs);
 EnsembleKernel ode23s_kernel(int rhs, int mode, int jac);  // jac: 0 fdjacobian, 1 analytic functor
 EnsembleKernel rosenbrock_kernel(int method, int rhs, int jac);
-EnsembleKernel ms4_kernel(int rhs);
+EnsembleKernel ms_kernel(int rhs);  // ode_ms, orders 1..5
 
 #define ODEB200_RHS_SWITCH(rhs, X)                 \
   switch (rhs) {                                   \

@@ -127,21 +127,20 @@ __global__ void __launch_bounds__(ENS_BLOCK) ens_rosenbrock_kernel(const Ensembl
 
 // ode4ms: x[i+1] = x[i] + sum_j (h*b[so][j]) * xdot[i-(so-1)+j], so = min(i, 4) (1-based i), :198-207
 template <class Rhs>
-__global__ void __launch_bounds__(ENS_BLOCK) ens_ms4_kernel(const EnsembleArgs A) {
-  constexpr int D = Rhs::DOF, NPA = RhsNP<Rhs>::value;
-  constexpr double B[4][4] = {{1, 0, 0, 0},
-                              {-1.0 / 2, 3.0 / 2, 0, 0},
-                              {5.0 / 12, -4.0 / 3, 23.0 / 12, 0},
-                              {-9.0 / 24, 37.0 / 24, -59.0 / 24, 55.0 / 24}};  // ms_coefficients4 :440-443
-  const int nt = A.n_tspan;
+__global__ void __launch_bounds__(ENS_BLOCK) ens_ms_kernel(const __grid_constant__ EnsembleArgs A) {
+  constexpr int D = Rhs::DOF, NPA = RhsNP<Rhs>::value, MO = ODE_B200_MS_MAX_ORDER;
+  // b[so-1][j] = A.tab[(so-1)*MO + j]: rows 1-4 are ms_coefficients4 (:440-443), row 5 is filled by the host the way
+  // the reference computes it (:183-194)
+  const int nt = A.n_tspan, order = A.ms_order;
   while (true) {
     long long idx = (long long)atomicAdd(A.work_counter, 1ULL);
     if (idx >= A.n_traj) break;
-    double x[D], p[NPA], h0[D], h1[D], h2[D], h3[D];  // h3 = newest derivative
+    double x[D], p[NPA], hist[MO][D];  // hist[MO-1] = newest derivative
 #pragma unroll
     for (int d = 0; d < D; d++) {
       x[d] = A.y0[idx * D + d];
-      h0[d] = h1[d] = h2[d] = h3[d] = 0.0;
+#pragma unroll
+      for (int q = 0; q < MO; q++) hist[q][d] = 0.0;
     }
 #pragma unroll
     for (int q = 0; q < NPA; q++) p[q] = (q < Rhs::NP) ? A.params[idx * A.params_stride + q] : 0.0;
@@ -156,30 +155,23 @@ __global__ void __launch_bounds__(ENS_BLOCK) ens_ms4_kernel(const EnsembleArgs A
       const double ti = A.tspan[i], h = A.tspan[i + 1] - ti;
 #pragma unroll
       for (int d = 0; d < D; d++) {
-        h0[d] = h1[d];
-        h1[d] = h2[d];
-        h2[d] = h3[d];
+#pragma unroll
+        for (int q = 0; q + 1 < MO; q++) hist[q][d] = hist[q + 1][d];
       }
-      Rhs::eval(ti, x, h3, p);  // :201
-      const int so = (i + 1 < 4) ? i + 1 : 4;
+      Rhs::eval(ti, x, hist[MO - 1], p);  // :201
+      const int so = (i + 1 < order) ? i + 1 : order;  // :200  steporder = min(i, order)
+      double hb[MO];  // h[i]*b[steporder, j] for the derivative in hist[q]: j = q - (MO - so), oldest first
+#pragma unroll
+      for (int q = 0; q < MO; q++) {
+        const int j = q - (MO - so);
+        hb[q] = (j >= 0) ? h * A.tab[(so - 1) * MO + j] : 0.0;
+      }
 #pragma unroll
       for (int d = 0; d < D; d++) {  // :203-206, oldest derivative first
         double v = x[d];
-        if (so == 1) {
-          v = v + (h * B[0][0]) * h3[d];
-        } else if (so == 2) {
-          v = v + (h * B[1][0]) * h2[d];
-          v = v + (h * B[1][1]) * h3[d];
-        } else if (so == 3) {
-          v = v + (h * B[2][0]) * h1[d];
-          v = v + (h * B[2][1]) * h2[d];
-          v = v + (h * B[2][2]) * h3[d];
-        } else {
-          v = v + (h * B[3][0]) * h0[d];
-          v = v + (h * B[3][1]) * h1[d];
-          v = v + (h * B[3][2]) * h2[d];
-          v = v + (h * B[3][3]) * h3[d];
-        }
+#pragma unroll
+        for (int q = 0; q < MO; q++)
+          if (q >= MO - so) v = v + hb[q] * hist[q][d];
         x[d] = v;
       }
       if (py && i + 1 < A.pts_cap) {

@@ -223,44 +223,30 @@ __global__ void __launch_bounds__(FIELD_THREADS) field_fixed_stage_kernel(const 
   }
 }
 
-// ---- ode4ms: Adams-Bashforth, order ramping up to 4 (ode_ms, src/ODE.jl:175-212) on a dof = N state ------------
-struct Ms4Args {
+// ---- ode_ms: Adams-Bashforth, order ramping up to `order` <= 5 (src/ODE.jl:175-213) on a dof = N state ----------
+struct MsArgs {
   const double* y;        // x[i]
   double* ynew;           // x[i+1]
-  const double* hold[3];  // xdot[i-3], xdot[i-2], xdot[i-1] (oldest first; unused ones may be anything)
+  const double* hold[ODE_B200_MS_MAX_ORDER - 1];  // xdot[i-4] .. xdot[i-1] (oldest first; unused ones may be anything)
   double* hnew;           // xdot[i] = F(t_i, x[i]) is written here
   long long n;
   double t, h;            // tspan[i], tspan[i+1] - tspan[i]
-  int so;                 // min(i, 4), 1-based step number
+  int so;                 // steporder = min(i, order), 1-based step number i (:200)
+  double hb[ODE_B200_MS_MAX_ORDER];  // h[i]*b[steporder, j] for hold[0..3], hnew (zero where unused): (h*b)*xdot (:205)
   StencilCtx sc;
 };
 template <class Rhs>
-__global__ void __launch_bounds__(FIELD_THREADS) field_ms4_kernel(const __grid_constant__ Ms4Args A) {
-  constexpr double B[4][4] = {{1, 0, 0, 0},
-                              {-1.0 / 2, 3.0 / 2, 0, 0},
-                              {5.0 / 12, -4.0 / 3, 23.0 / 12, 0},
-                              {-9.0 / 24, 37.0 / 24, -59.0 / 24, 55.0 / 24}};  // ms_coefficients4 :440-443
-  const double h = A.h;
+__global__ void __launch_bounds__(FIELD_THREADS) field_ms_kernel(const __grid_constant__ MsArgs A) {
+  constexpr int MO = ODE_B200_MS_MAX_ORDER;
   const int so = A.so;
   for (long long i = (long long)blockIdx.x * FIELD_THREADS + threadIdx.x; i < A.n; i += (long long)gridDim.x * FIELD_THREADS) {
-    const double h3 = Rhs::rhs(i, A.n, A.y, A.sc.p, A.t);  // :201
-    A.hnew[i] = h3;
+    const double hn = Rhs::rhs(i, A.n, A.y, A.sc.p, A.t);  // :201
+    A.hnew[i] = hn;
     double v = A.y[i];  // :203-206, oldest derivative first
-    if (so == 1) {
-      v = v + (h * B[0][0]) * h3;
-    } else if (so == 2) {
-      v = v + (h * B[1][0]) * A.hold[2][i];
-      v = v + (h * B[1][1]) * h3;
-    } else if (so == 3) {
-      v = v + (h * B[2][0]) * A.hold[1][i];
-      v = v + (h * B[2][1]) * A.hold[2][i];
-      v = v + (h * B[2][2]) * h3;
-    } else {
-      v = v + (h * B[3][0]) * A.hold[0][i];
-      v = v + (h * B[3][1]) * A.hold[1][i];
-      v = v + (h * B[3][2]) * A.hold[2][i];
-      v = v + (h * B[3][3]) * h3;
-    }
+#pragma unroll
+    for (int q = 0; q < MO - 1; q++)
+      if (q >= MO - so) v = v + A.hb[q] * A.hold[q][i];
+    v = v + A.hb[MO - 1] * hn;
     A.ynew[i] = v;
   }
 }

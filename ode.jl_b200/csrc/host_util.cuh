@@ -5,6 +5,8 @@
 namespace odeb200 {
 int set_err(int code, const char* fmt, ...);  // fills the thread-local last_error, returns code
 void note_launch();                           // counts kernel launches (ode_b200_launch_count)
+int ms_order(int method);                     // order of ode_ms for a method id, 0 if it is not a multistep method
+double ms_coefficient(int order, int j);      // b[order][j] of ode_ms, j 0-based (capi.cu)
 }  // namespace odeb200
 
 #define ODEB200_CUDA(call)                                                                              \

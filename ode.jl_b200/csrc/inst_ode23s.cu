@@ -23,8 +23,8 @@ EnsembleKernel rosenbrock_kernel(int method, int rhs, int jac) {
   if (method == ODE_B200_M_ODE4S_KR) return jac ? ros_for<RosKapsRentrop, 1>(rhs) : ros_for<RosKapsRentrop, 0>(rhs);
   return jac ? ros_for<RosShampine, 1>(rhs) : ros_for<RosShampine, 0>(rhs);
 }
-EnsembleKernel ms4_kernel(int rhs) {
-#define X(R) return ens_ms4_kernel<R>
+EnsembleKernel ms_kernel(int rhs) {
+#define X(R) return ens_ms_kernel<R>
   ODEB200_RHS_SWITCH(rhs, X)
 #undef X
 }

@@ -1055,7 +1055,8 @@ int ode_b200_solve_large_fixed(const ode_b200_opts* o, int64_t n, const double* 
     return set_err(ODE_B200_E_NO_DEVICE, "no CUDA device available; libode_b200 has no CPU fallback");
   }
   if (o->device < 0 || o->device >= cnt) return set_err(ODE_B200_E_INVALID, "device %d out of range", o->device);
-  const bool ms4 = o->method == ODE_B200_M_ODE4MS;  // Adams-Bashforth: one kernel per step, four derivative arrays
+  const int msord = ms_order(o->method);  // ode_ms (Adams-Bashforth, order 1..5): one kernel per step, a ring of derivative arrays
+  const bool ms4 = msord > 0;
   const int S = ms4 ? 1 : fixed_stage_count(o->method);
   if (S == 0)
     return set_err(ODE_B200_E_UNSUPPORTED, "method %d is not a fixed-step explicit method with a large-system kernel "
@@ -1066,7 +1067,7 @@ int ode_b200_solve_large_fixed(const ode_b200_opts* o, int64_t n, const double* 
   int np = 2;
   if (o->rhs == ODE_B200_RHS_REACTION_DIFFUSION || o->rhs == ODE_B200_RHS_RD_FIELD) {
     if (ms4)
-      k[0] = (const void*)field_ms4_kernel<FieldReactionDiffusion>;
+      k[0] = (const void*)field_ms_kernel<FieldReactionDiffusion>;
     else
       builtin_fixed_kernels(o->method, k);
   } else if (o->rhs >= ODE_B200_FIELD_USER_BASE) {
@@ -1093,10 +1094,11 @@ int ode_b200_solve_large_fixed(const ode_b200_opts* o, int64_t n, const double* 
   FixedArgs A;
   memset(&A, 0, sizeof(A));
   double *ya = nullptr, *yb = nullptr;
-  double* hist[4] = {nullptr, nullptr, nullptr, nullptr};  // ode4ms: ring of the last four derivatives
+  constexpr int MO = ODE_B200_MS_MAX_ORDER;
+  double* hist[MO] = {};  // ode_ms: ring of the last MO derivatives
   bool ok = alloc(&ya) && alloc(&yb);
   if (ms4) {
-    for (int q = 0; q < 4 && ok; q++) ok = alloc(&hist[q]);
+    for (int q = 0; q < MO && ok; q++) ok = alloc(&hist[q]);
   } else {
     ok = ok && alloc(&A.T[0]) && alloc(&A.T[1]);
     for (int q = 0; q < S - 1 && ok; q++) ok = alloc(&A.KS[q]);
@@ -1127,17 +1129,21 @@ int ode_b200_solve_large_fixed(const ode_b200_opts* o, int64_t n, const double* 
     A.ynew = yb;
     A.t = tspan[i];
     A.dt = tspan[i + 1] - tspan[i];  // :202
-    if (ms4) {  // xdot[i] goes to ring slot i % 4; the three older ones are slots i-3 .. i-1
-      Ms4Args M;
+    if (ms4) {  // xdot[i] goes to ring slot i % MO; the older ones are slots i-4 .. i-1
+      MsArgs M;
       memset(&M, 0, sizeof(M));
       M.y = ya;
       M.ynew = yb;
-      for (int q = 0; q < 3; q++) M.hold[q] = hist[(i + 1 + q) % 4];
-      M.hnew = hist[i % 4];
+      for (int q = 0; q < MO - 1; q++) M.hold[q] = hist[(i + 1 + q) % MO];  // xdot[i-4+q]
+      M.hnew = hist[i % MO];
       M.n = n;
       M.t = A.t;
       M.h = A.dt;
-      M.so = (i + 1 < 4) ? i + 1 : 4;
+      M.so = (i + 1 < msord) ? i + 1 : msord;  // steporder = min(i, order), src/ODE.jl:200
+      for (int q = 0; q < MO; q++) {           // h[i]*b[steporder, j] (:205), j = q - (MO - so), oldest derivative first
+        const int j = q - (MO - M.so);
+        M.hb[q] = j >= 0 ? A.dt * ms_coefficient(M.so, j) : 0.0;
+      }
       M.sc = A.sc;
       void* margs[] = {(void*)&M};
       ce = cudaLaunchKernel(k[0], dim3(grid), dim3(FIELD_THREADS), margs, 0, st);

@@ -195,9 +195,9 @@ const void* user_kernel(int rhs, int method, int mode, int literal, int jac) {
     header = "ensemble_ros.cuh";
     snprintf(expr, sizeof(expr), "odeb200::ens_rosenbrock_kernel<odeb200::RhsUser, odeb200::%s, %d>",
              method == ODE_B200_M_ODE4S_KR ? "RosKapsRentrop" : "RosShampine", jac ? 1 : 0);
-  } else if (method == ODE_B200_M_ODE4MS) {
+  } else if (ms_order(method) > 0) {
     header = "ensemble_ros.cuh";
-    snprintf(expr, sizeof(expr), "odeb200::ens_ms4_kernel<odeb200::RhsUser>");
+    snprintf(expr, sizeof(expr), "odeb200::ens_ms_kernel<odeb200::RhsUser>");
   } else {
     set_err(ODE_B200_E_UNSUPPORTED, "method %d has no kernel for a run-time RHS", method);
     return nullptr;
@@ -402,8 +402,8 @@ bool user_fixed_kernels(int rhs, int method, int n_stages, const void** out) {
     }
     u = reg[i];
   }
-  const bool ms4 = method == ODE_B200_M_ODE4MS;  // one kernel per step (field_ms4_kernel)
-  const char* tab = ms4 ? "ms4" : tab_name(method);
+  const bool ms4 = ms_order(method) > 0;  // ode_ms, any order: one kernel per step (field_ms_kernel)
+  const char* tab = ms4 ? "ms" : tab_name(method);
   if (!tab || (!ms4 && method > ODE_B200_M_RK4)) {
     set_err(ODE_B200_E_UNSUPPORTED, "method %d is not a fixed-step explicit RK tableau", method);
     return false;
@@ -449,7 +449,7 @@ bool user_fixed_kernels(int rhs, int method, int n_stages, const void** out) {
   for (int st = 1; st <= n_stages; st++) {
     char e[256];
     if (ms4)
-      snprintf(e, sizeof(e), "odeb200::field_ms4_kernel<%s>", functor);
+      snprintf(e, sizeof(e), "odeb200::field_ms_kernel<%s>", functor);
     else
       snprintf(e, sizeof(e), "odeb200::field_fixed_stage_kernel<%s, %s, %d>", tab, functor, st);
     names.push_back(e);

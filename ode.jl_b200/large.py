@@ -43,7 +43,8 @@ def shard_bounds(n_global, world, rank):
     return lo, lo + base + (1 if rank < rem else 0)
 
 
-_FIXED_RK = ("ode1", "ode2_midpoint", "ode2_heun", "ode4", "ode4ms")  # fixed-step methods with a dof = N kernel
+_FIXED_RK = ("ode1", "ode2_midpoint", "ode2_heun", "ode4", "ode4ms", "ode5ms", "ode_ms1", "ode_ms2", "ode_ms3", "ode_ms4",
+             "ode_ms5")  # fixed-step methods with a dof = N kernel
 
 
 def _solve_large_fixed(name, F, y0, ts, points, device):

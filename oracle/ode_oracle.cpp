@@ -931,13 +931,56 @@ void oderosenbrock(const Rhs& F, int method, const Vec& x0, const Vec& tspan, co
     for (int64_t d = 0; d < n; d++) R.y[i * n + d] = x[i][d];
 }
 
-// ode_ms with order 4 (ode4ms), src/ODE.jl:175-212, coefficients :440-443.
-void ode4ms(const Rhs& F, const Vec& x0, const Vec& tspan, Result& R) {
-  static const double b[4][4] = {{1, 0, 0, 0},
-                                 {-1.0 / 2, 3.0 / 2, 0, 0},
-                                 {5.0 / 12, -4.0 / 3, 23.0 / 12, 0},
-                                 {-9.0 / 24, 37.0 / 24, -59.0 / 24, 55.0 / 24}};
-  const int order = 4;
+// ode_ms (src/ODE.jl:175-213): ode4ms = order 4, ode5ms = order 5, orders 1-3 through ODE.ode_ms.
+// b for order <= 4 is ms_coefficients4 (:440-443); for order 5 the reference fills b[5, :] in floating point (:183-194):
+//   p_int = polyint(poly(diagm(0 => -[0:j-1; j+1:s-1])));  b[s, s-j] = (-1)^j / factorial(j) / factorial(s-1-j) * polyval(p_int, 1)
+// restated with poly = product of (x - r) over the roots in the order listed (small integers: exact), polyint = a_k/(k+1),
+// polyval = Horner from the leading coefficient, the prefactor evaluated left to right.  Polynomials.jl is not vendored
+// and Julia is absent: the bits of this row are UNPINNED against the reference (exact values [251,-1274,2616,-2774,1901]/720).
+int ms_order_of(int method) {
+  switch (method) {
+    case ODE_B200_M_ODE_MS1: return 1;
+    case ODE_B200_M_ODE_MS2: return 2;
+    case ODE_B200_M_ODE_MS3: return 3;
+    case ODE_B200_M_ODE4MS: return 4;
+    case ODE_B200_M_ODE5MS: return 5;
+    default: return 0;
+  }
+}
+void ms_coefficients(int order, double (&b)[5][5]) {
+  static const double b4[4][4] = {{1, 0, 0, 0},
+                                  {-1.0 / 2, 3.0 / 2, 0, 0},
+                                  {5.0 / 12, -4.0 / 3, 23.0 / 12, 0},
+                                  {-9.0 / 24, 37.0 / 24, -59.0 / 24, 55.0 / 24}};
+  for (int i = 0; i < 5; i++)
+    for (int j = 0; j < 5; j++) b[i][j] = (i < 4 && j < 4) ? b4[i][j] : 0.0;
+  for (int s = 5; s <= order; s++) {
+    for (int j = 0; j <= s - 1; j++) {
+      std::vector<double> pc(1, 1.0);  // ascending coefficients
+      for (int r = 0; r <= s - 1; r++) {
+        if (r == j) continue;
+        const double root = -(double)r;
+        std::vector<double> q(pc.size() + 1, 0.0);
+        for (size_t k = 0; k < pc.size(); k++) {
+          q[k + 1] += pc[k];
+          q[k] += -root * pc[k];
+        }
+        pc = q;
+      }
+      std::vector<double> pi(pc.size() + 1, 0.0);
+      for (size_t k = 0; k < pc.size(); k++) pi[k + 1] = pc[k] / (double)(k + 1);
+      double v = pi.back();
+      for (int k = (int)pi.size() - 2; k >= 0; k--) v = pi[k] + 1.0 * v;
+      double fj = 1.0, fs = 1.0;
+      for (int k = 2; k <= j; k++) fj *= k;
+      for (int k = 2; k <= s - 1 - j; k++) fs *= k;
+      b[s - 1][s - j - 1] = ((j % 2) ? -1.0 : 1.0) / fj / fs * v;
+    }
+  }
+}
+void ode_ms(const Rhs& F, const Vec& x0, const Vec& tspan, int order, Result& R) {
+  double b[5][5];
+  ms_coefficients(order, b);
   const int64_t n = (int64_t)x0.size(), nt = (int64_t)tspan.size();
   R.dof = (int)n;
   std::vector<Vec> x(nt, Vec(n, 0.0)), xdot(nt, Vec(n, 0.0));
@@ -981,8 +1024,8 @@ void solve_one(const ode_b200_opts* op, const double* y0, const double* params, 
     ode23s(F, M, y, ts, o, R);
   } else if (op->method == ODE_B200_M_ODE4S_S || op->method == ODE_B200_M_ODE4S_KR) {
     oderosenbrock(F, op->method, y, ts, o, R);
-  } else if (op->method == ODE_B200_M_ODE4MS) {
-    ode4ms(F, y, ts, R);
+  } else if (ms_order_of(op->method) > 0) {
+    ode_ms(F, y, ts, ms_order_of(op->method), R);
   } else {
     Tab bt = make_tab(op->method);
     if (bt.S == 0) {
@@ -1005,6 +1048,12 @@ struct oracle_result {
   Result r;
 };
 
+double oracle_ms_coefficient(int order, int j) {  // 1-based like the reference's b[order, j]
+  double b[5][5];
+  if (order < 1 || order > 5 || j < 1 || j > order) return NAN;
+  ms_coefficients(order, b);
+  return b[order - 1][j - 1];
+}
 // run-time RHS for opts.rhs >= ODE_B200_RHS_USER_BASE (single-trajectory solves of the calling thread)
 void oracle_set_user_rhs(UserRhsFn f, UserJacFn j) {
   g_user_rhs = f;

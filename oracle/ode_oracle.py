@@ -588,16 +588,47 @@ def oderosenbrock(F, x0, tspan, method, jac=None):
     return dict(t=tspan, y=xs_all, n_rhs=F.n)
 
 
-def ode4ms(F, x0, tspan):
-    """ode_ms with order 4, src/ODE.jl:175-212."""
-    b = [[1, 0, 0, 0], [-1 / 2, 3 / 2, 0, 0], [5 / 12, -4 / 3, 23 / 12, 0], [-9 / 24, 37 / 24, -59 / 24, 55 / 24]]
+def ms_coefficients(order):
+    """b of ode_ms (src/ODE.jl:180-194): ms_coefficients4 (:440-443), and for order 5 the reference's floating-point
+    evaluation through poly / polyint / polyval (restated: product over the roots, a_k/(k+1), Horner)."""
+    from math import factorial
+    b4 = [[1, 0, 0, 0], [-1 / 2, 3 / 2, 0, 0], [5 / 12, -4 / 3, 23 / 12, 0], [-9 / 24, 37 / 24, -59 / 24, 55 / 24]]
+    if order <= 4:
+        return b4
+    b = [[0.0] * order for _ in range(order)]
+    for i in range(4):
+        for j in range(4):
+            b[i][j] = float(b4[i][j])
+    for s in range(5, order + 1):
+        for j in range(s):
+            pc = [1.0]
+            for r in range(s):
+                if r == j:
+                    continue
+                root = -float(r)
+                q = [0.0] * (len(pc) + 1)
+                for k, c in enumerate(pc):
+                    q[k + 1] += c
+                    q[k] += -root * c
+                pc = q
+            pi = [0.0] + [c / float(k + 1) for k, c in enumerate(pc)]
+            v = pi[-1]
+            for k in range(len(pi) - 2, -1, -1):
+                v = pi[k] + 1.0 * v
+            b[s - 1][s - j - 1] = (-1.0) ** j / factorial(j) / factorial(s - 1 - j) * v
+    return b
+
+
+def ode_ms(F, x0, tspan, order):
+    """ode_ms, src/ODE.jl:175-209."""
+    b = ms_coefficients(order)
     F = Counted(F)
     tspan = [float(v) for v in tspan]
     x = [[float(v) for v in x0]]
     xdot = []
     for i in range(len(tspan) - 1):
         h = tspan[i + 1] - tspan[i]
-        so = min(i + 1, 4)
+        so = min(i + 1, order)
         xdot.append(F(tspan[i], x[i]))
         xn = list(x[i])
         for j in range(so):
@@ -608,12 +639,19 @@ def ode4ms(F, x0, tspan):
     return dict(t=tspan, y=x, n_rhs=F.n)
 
 
+def ode4ms(F, x0, tspan):
+    return ode_ms(F, x0, tspan, 4)
+
+
+MS_ORDER = dict(ode4ms=4, ode5ms=5, ode_ms1=1, ode_ms2=2, ode_ms3=3, ode_ms4=4, ode_ms5=5)
+
+
 def solve(method, rhs, y0, tspan, params=None, jacobian=0, **kw):
     F = rhs_factory(rhs, params)
     if method in ROS:
         return oderosenbrock(F, y0, tspan, method, jac_factory(rhs, params) if jacobian else None)
-    if method == "ode4ms":
-        return ode4ms(F, y0, tspan)
+    if method in MS_ORDER:
+        return ode_ms(F, y0, tspan, MS_ORDER[method])
     if method == "ode23s":
         return ode23s(F, y0, tspan, jac=jac_factory(rhs, params) if jacobian else None, **kw)
     if Tab(method).adaptive:

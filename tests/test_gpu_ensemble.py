@@ -160,7 +160,8 @@ def test_fixed_step_bit_exact(method):
         assert np.array_equal(got["y_final"][i], oi.y[-1])
 
 
-ALL = FIXED + ["ode4ms"] + ADAPTIVE + ["ode4s_s", "ode4s_kr", "ode4s", "ode23s"]
+MULTISTEP = ["ode4ms", "ode5ms", "ode_ms1", "ode_ms2", "ode_ms3"]  # ode_ms, src/ODE.jl:175-213
+ALL = FIXED + MULTISTEP + ADAPTIVE + ["ode4s_s", "ode4s_kr", "ode4s", "ode23s"]
 
 
 @pytest.mark.parametrize("solver", ALL)
@@ -384,7 +385,7 @@ def test_full_size_kepler_and_robertson_invariants():
     assert np.max(np.abs(got["y_final"].sum(1) - 1.0)) < 1e-7 and got["y_final"].min() > -1e-9
 
 
-@pytest.mark.parametrize("method", FIXED + ["ode4ms", "ode4s_s"])
+@pytest.mark.parametrize("method", FIXED + MULTISTEP + ["ode4s_s"])
 def test_fixed_step_blowup_matches_oracle(method):
     """Fixed-step solvers on a trajectory that overflows: Inf/NaN pattern as in the reference (every tableau
     coefficient is multiplied, so Inf*0 = NaN)."""
@@ -490,3 +491,28 @@ def test_plain_c_program_solves_the_readme_problem(tmp_path):
     r = subprocess.run([build_abi_smoke(tmp_path)], capture_output=True, text=True)
     assert r.returncode == 0, r.stdout + r.stderr
     assert "11 accepted, 0 rejected" in r.stdout
+
+
+@pytest.mark.parametrize("order", [1, 2, 3, 4, 5])
+def test_ode_ms_all_orders_bit_exact(order):
+    """ode_ms(F, x0, tspan, order) (src/ODE.jl:175-209; ode4ms :212, ode5ms :213): every tspan point of a single
+    system and of an ensemble with per-trajectory parameters equals the oracle's, bit for bit."""
+    ts = np.linspace(0.0, 1.0, 201)
+    t, y = m.ode_ms(m.DeviceRHS("lorenz", 10.0, 28.0, 8 / 3), [1.0, 1.0, 1.0], ts, order)
+    ref = O.solve("ode_ms%d" % order, "lorenz", [1.0, 1.0, 1.0], ts, [10.0, 28.0, 8 / 3])
+    assert np.array_equal(t, ref.t) and np.array_equal(y, ref.y)
+    if order == 5:
+        t5, y5 = m.ode5ms(m.DeviceRHS("lorenz", 10.0, 28.0, 8 / 3), [1.0, 1.0, 1.0], ts)
+        assert np.array_equal(y5, ref.y)
+    rng = np.random.default_rng(order)
+    n = 777
+    y0 = rng.uniform(-2, 2, (n, 2))
+    mu = rng.uniform(0.5, 3.0, (n, 1))
+    got = m.solve_ensemble("ode_ms%d" % order, m.DeviceRHS("vdp", 1.0), y0, ts, params=mu, points="all", pts_cap=len(ts))
+    exp = O.solve_ensemble("ode_ms%d" % order, "vdp", y0, ts, mu)
+    assert np.array_equal(got["y_final"], exp["y_final"]) and np.all(got["pts_n"] == len(ts))
+    k = int(rng.integers(n))
+    one = O.solve("ode_ms%d" % order, "vdp", y0[k], ts, mu[k])
+    assert np.array_equal(got["pts_y"][k], one.y)
+    with pytest.raises(ValueError):
+        m.ode_ms(m.DeviceRHS("vdp", 1.0), [1.0, 0.0], ts, 6)

@@ -369,7 +369,8 @@ def test_field_overflowing_first_step_recovers_like_the_reference():
     assert np.array_equal(got["trace"], ref.trace, equal_nan=True) and np.array_equal(got["y"], ref.y[-1])
 
 
-@pytest.mark.parametrize("method", ["ode1", "ode2_midpoint", "ode2_heun", "ode4", "ode4ms"])
+@pytest.mark.parametrize("method", ["ode1", "ode2_midpoint", "ode2_heun", "ode4", "ode4ms", "ode5ms", "ode_ms1", "ode_ms2",
+                                    "ode_ms3"])
 def test_fixed_step_rk_on_a_large_state(method):
     """oderk_fixed (src/runge_kutta.jl:176-212) on a dof = N state: one state per tspan entry, bit for bit, for
     the built-in system (stencil and gather ids), a registered radius-2 stencil and a registered field."""

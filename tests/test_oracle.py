@@ -52,7 +52,7 @@ def test_tableau_matches_reference_source(name):
     assert pt.fsal == t["fsal"]
 
 
-ALL_SOLVERS = FIXED + ["ode4ms"] + ADAPTIVE + ["ode4s_s", "ode4s_kr", "ode23s"]  # test/runtests.jl:5-25 minus ode5ms
+ALL_SOLVERS = FIXED + ["ode4ms", "ode5ms"] + ADAPTIVE + ["ode4s_s", "ode4s_kr", "ode23s"]  # test/runtests.jl:5-25
 
 
 @pytest.mark.parametrize("solver", ALL_SOLVERS)
@@ -268,3 +268,40 @@ def test_oracle_against_real_julia_if_present():
         worst = max(worst, float(ulps))
         assert ulps <= 4096, (c["name"], ulps)   # same step sequence; trajectories may separate by rounding
     print("largest final-state difference to real ODE.jl: %.1f ulp" % worst)
+
+
+# ---- ode_ms, orders 1..5 (src/ODE.jl:175-213; ode5ms is in the reference's solver sweep, test/runtests.jl:13) ---------
+def test_ms_coefficients():
+    """Rows 1-4 are ms_coefficients4 (src/ODE.jl:440-443) as Julia evaluates the literals; row 5 is the float
+    evaluation of :183-194 -- within an ulp or two of the exact Adams-Bashforth weights, and the same bits in the C++
+    oracle, its Python twin and the library (host table the kernels read)."""
+    import ode_jl_b200 as m
+    b4 = [[1.0], [-1 / 2, 3 / 2], [5 / 12, -4 / 3, 23 / 12], [-9 / 24, 37 / 24, -59 / 24, 55 / 24]]
+    L, Lib = O.lib(), m.lib()
+    for order in range(1, 5):
+        for j in range(1, order + 1):
+            assert L.oracle_ms_coefficient(order, j) == b4[order - 1][j - 1] == Lib.ode_b200_ms_coefficient(order, j)
+    exact = [251 / 720, -1274 / 720, 2616 / 720, -2774 / 720, 1901 / 720]
+    row = [L.oracle_ms_coefficient(5, j) for j in range(1, 6)]
+    assert row == P.ms_coefficients(5)[4] == [Lib.ode_b200_ms_coefficient(5, j) for j in range(1, 6)]
+    assert all(abs(a - b) <= 2 * np.spacing(abs(b)) for a, b in zip(row, exact))
+    assert abs(sum(row) - 1.0) < 1e-15  # consistency of an Adams-Bashforth formula
+    assert math.isnan(L.oracle_ms_coefficient(6, 1)) and math.isnan(Lib.ode_b200_ms_coefficient(3, 4))
+
+
+@pytest.mark.parametrize("order", [1, 2, 3, 4, 5])
+def test_ode_ms_cpp_equals_python_twin(order):
+    name = "ode_ms%d" % order
+    ts = np.linspace(0.0, 1.0, 201)
+    for rhs, y0, p in (("lorenz", [1.0, 1.0, 1.0], [10.0, 28.0, 8 / 3]), ("vdp", [2.0, 0.0], [1.5])):
+        a = O.solve(name, rhs, y0, ts, p)
+        b = P.solve(name, rhs, y0, ts, p)
+        assert np.array_equal(a.y, np.array(b["y"])) and a.n_rhs == b["n_rhs"] == len(ts) - 1
+    assert np.array_equal(O.solve("ode4ms", "vdp", [2.0, 0.0], ts, [1.5]).y, O.solve("ode_ms4", "vdp", [2.0, 0.0], ts, [1.5]).y)
+    assert np.array_equal(O.solve("ode5ms", "vdp", [2.0, 0.0], ts, [1.5]).y, O.solve("ode_ms5", "vdp", [2.0, 0.0], ts, [1.5]).y)
+    # order of accuracy on y' = y: halving h divides the end error by about 2^order
+    errs = []
+    for n in (100, 200):
+        t = np.linspace(0.0, 1.0, n + 1)
+        errs.append(abs(O.solve(name, "linear", [1.0], t, [1.0]).y[-1, 0] - math.e))
+    assert 0.7 * 2 ** order < errs[0] / errs[1] < 1.4 * 2 ** order

@@ -299,9 +299,10 @@ def test_ode_ms_cpp_equals_python_twin(order):
         assert np.array_equal(a.y, np.array(b["y"])) and a.n_rhs == b["n_rhs"] == len(ts) - 1
     assert np.array_equal(O.solve("ode4ms", "vdp", [2.0, 0.0], ts, [1.5]).y, O.solve("ode_ms4", "vdp", [2.0, 0.0], ts, [1.5]).y)
     assert np.array_equal(O.solve("ode5ms", "vdp", [2.0, 0.0], ts, [1.5]).y, O.solve("ode_ms5", "vdp", [2.0, 0.0], ts, [1.5]).y)
-    # order of accuracy on y' = y: halving h divides the end error by about 2^order
+    # convergence on y' = y: the reference starts with reduced-order steps (src/ODE.jl:199-200; the first one is an
+    # Euler step with an O(h^2) error that is never repaired), so halving h divides the end error by 2^min(order, 2)
     errs = []
     for n in (100, 200):
         t = np.linspace(0.0, 1.0, n + 1)
         errs.append(abs(O.solve(name, "linear", [1.0], t, [1.0]).y[-1, 0] - math.e))
-    assert 0.7 * 2 ** order < errs[0] / errs[1] < 1.4 * 2 ** order
+    assert 0.9 * 2 ** min(order, 2) < errs[0] / errs[1] < 1.1 * 2 ** min(order, 2)

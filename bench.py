@@ -405,12 +405,22 @@ def main():
                 s_g = measure_large(ctx, args.large_n, args.steps, args.warmup, exchange=args.exchange, with_cpu=False,
                                     scaling="strong", peaks=peaks)
                 strong = {"lorenz": s_l, "large": s_g}
+            relaxed = None
+            if world == 1:  # what the same kernel reaches with FMA contraction: labelled, opt-in, never the headline
+                relaxed = measure_lorenz(ctx, n, lorenz_ics(n, SEED + rank), args.steps, args.warmup, scaling="weak",
+                                         peaks=peaks, with_cpu=False, cpu_sample=0, strict_fp=False)
             if rank == 0:
                 if parity:
                     large["parity_check"] = parity
                 line["large"] = large
                 if strong:
                     line["strong"] = strong
+                if relaxed:
+                    relaxed["note"] = ("opts.fp_mode = ODE_B200_FP_FMA: the same Dormand-Prince kernel compiled with FMA "
+                                       "contraction; NOT bit-identical to the reference (within 1e-10 relative on "
+                                       "non-chaotic problems, tests/test_gpu_ensemble.py), reported only to show the "
+                                       "fraction of the FP64 FMA peak the design reaches when fusing is allowed")
+                    line["relaxed_fp"] = relaxed
     if rank == 0:
         line["host"] = {"numa": numa, "ranks": world}
         print(json.dumps(line))

@@ -292,7 +292,7 @@ static int validate(const ode_b200_opts* o, const ode_b200_ensemble_io* io, doub
   if (o->fp_mode != ODE_B200_FP_STRICT && o->fp_mode != ODE_B200_FP_FMA) return set_err(ODE_B200_E_INVALID, "fp_mode must be 0 (strict) or 1 (FMA)");
   if (o->fp_mode == ODE_B200_FP_FMA && !fma_kernel_available(o))
     return set_err(ODE_B200_E_UNSUPPORTED, "fp_mode = FMA is built for the ensemble ode45 (Dormand-Prince) kernels with a built-in "
-                                           "right-hand side and points = final only; everything else runs in strict mode");
+                                           "right-hand side; everything else runs in strict mode only");
   if (!(o->reltol == o->reltol) || !(o->abstol == o->abstol) || !(o->minstep == o->minstep) ||
       !(o->maxstep == o->maxstep) || !(o->initstep == o->initstep))
     return set_err(ODE_B200_E_INVALID, "NaN in reltol/abstol/minstep/maxstep/initstep");
@@ -312,13 +312,19 @@ static int validate(const ode_b200_opts* o, const ode_b200_ensemble_io* io, doub
 }
 
 static bool is_adaptive_rk(int method) { return method >= ODE_B200_M_RK21 && method <= ODE_B200_M_FEH78; }
-static bool fma_kernel_available(const ode_b200_opts* o) { return false; }  // (no FMA build yet)
+// the opt-in FMA build (inst_dopri5_fma.cu): Dormand-Prince, built-in right-hand sides
+extern "C" const void* odeb200_fma_dopri5_kernel(int rhs, int mode, int literal);
+extern "C" const void* odeb200_fma_dopri5_init_kernel(int rhs);
+static bool fma_kernel_available(const ode_b200_opts* o) {
+  return o->method == ODE_B200_M_DOPRI5 && o->rhs >= 0 && o->rhs < ODE_B200_RHS_COUNT;
+}
 static EnsembleKernel pick_kernel_fn(const ode_b200_opts* o, int mode, int literal);
 
 static const void* pick_kernel_builtin(const ode_b200_opts* o, int mode, int literal);
 
 // kernel handle: a __global__ function pointer for the built-in functors, a cudaKernel_t for run-time ones
 static const void* pick_kernel(const ode_b200_opts* o, int mode, int literal = 0) {
+  if (o->fp_mode == ODE_B200_FP_FMA) return fma_kernel_available(o) ? odeb200_fma_dopri5_kernel(o->rhs, mode, literal) : nullptr;
   if (o->rhs >= ODE_B200_RHS_USER_BASE) return user_kernel(o->rhs, o->method, mode, literal, o->jacobian);
   return pick_kernel_builtin(o, mode, literal);
 }
@@ -345,6 +351,7 @@ static EnsembleKernel pick_kernel_fn(const ode_b200_opts* o, int mode, int liter
 // counter of the fast pass, the redo count, and the work counter of the literal pass.  io->status must
 // be non-null for the adaptive RK methods (the two passes communicate through it).
 static const void* pick_init_kernel(const ode_b200_opts* o) {
+  if (o->fp_mode == ODE_B200_FP_FMA) return fma_kernel_available(o) ? odeb200_fma_dopri5_init_kernel(o->rhs) : nullptr;
   if (o->rhs >= ODE_B200_RHS_USER_BASE) return user_init_kernel(o->rhs, o->method);
   switch (o->method) {
     case ODE_B200_M_RK21: return (const void*)adapt_kernel_rk21_init(o->rhs);

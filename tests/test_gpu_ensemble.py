@@ -516,3 +516,31 @@ def test_ode_ms_all_orders_bit_exact(order):
     assert np.array_equal(got["pts_y"][k], one.y)
     with pytest.raises(ValueError):
         m.ode_ms(m.DeviceRHS("vdp", 1.0), [1.0, 0.0], ts, 6)
+
+
+def test_relaxed_fp_mode_is_close_to_but_is_not_the_parity_path():
+    """opts.fp_mode = ODE_B200_FP_FMA (strict_fp=False): the Dormand-Prince kernels compiled with FMA contraction.
+    Opt-in, never the parity path: on non-chaotic problems (and Lorenz over a short horizon) the final states agree
+    with the strict / oracle result to 1e-10 relative (the north-star tolerance) and the step counts are the same
+    except where a decision sat within rounding of the threshold; the bits are NOT the oracle's."""
+    rng = np.random.default_rng(11)
+    n = 8192
+    cases = [("vdp", m.DeviceRHS("vdp", 1.0), rng.uniform(-2, 2, (n, 2)), [0.0, 5.0]),
+             ("lorenz", m.DeviceRHS("lorenz", 10.0, 28.0, 8 / 3),
+              np.stack([rng.uniform(-10, 10, n), rng.uniform(-10, 10, n), rng.uniform(5, 35, n)], 1), [0.0, 2.0])]
+    for name, F, y0, ts in cases:
+        strict = m.solve_ensemble("ode45", F, y0, ts)
+        fma = m.solve_ensemble("ode45", F, y0, ts, strict_fp=False)
+        assert np.all(fma["status"] == 0)
+        scale = np.maximum(np.abs(strict["y_final"]).max(axis=1), 1e-3)
+        rel = np.abs(fma["y_final"] - strict["y_final"]).max(axis=1) / scale
+        same_steps = (fma["n_accept"] == strict["n_accept"]) & (fma["n_reject"] == strict["n_reject"])
+        print("%s: max rel diff %.3e over %d trajectories, %d with different step counts, %d bit-identical"
+              % (name, rel[same_steps].max(), n, int((~same_steps).sum()), int((rel == 0).sum())))
+        assert rel[same_steps].max() < 1e-10
+        assert (~same_steps).sum() <= n // 1000  # a flipped accept/reject needs err within ~1e-15 of 1
+        assert (rel > 0).any()  # it really is different arithmetic
+    with pytest.raises(m.OdeB200Error):  # no FMA build of the other methods: refused, not silently strict
+        m.solve_ensemble("ode23", cases[0][1], cases[0][2], cases[0][3], strict_fp=False)
+    with pytest.raises(m.OdeB200Error):
+        m.solve_large("ode45", m.DeviceRHS("reaction_diffusion", 1.0, 1.0), np.linspace(0.1, 0.9, 4096), [0.0, 1.0], strict_fp=False)

@@ -171,6 +171,9 @@ ode4ms = Solver("ode4ms")      # Adams-Bashforth order 4, src/ODE.jl:212
 ode5ms = Solver("ode5ms")      # order 5, src/ODE.jl:213 (not exported by the reference either: ODE.ode5ms)
 
 
+ode_ms1, ode_ms2, ode_ms3 = Solver("ode_ms1"), Solver("ode_ms2"), Solver("ode_ms3")  # ODE.ode_ms(F, x0, tspan, 1..3)
+
+
 def ode_ms(F, x0, tspan, order, **kw):
     """ode_ms(F, x0, tspan, order; kwargs...) (src/ODE.jl:175): fixed-step Adams-Bashforth of order 1..5 on the tspan
     grid, the first steps at reduced order."""

@@ -436,11 +436,12 @@ static int launch_ensemble(const ode_b200_opts* o, const ode_b200_ensemble_io* i
   int dev = 0, sms = 0, per_sm = 0;
   ODEB200_CUDA(cudaGetDevice(&dev));
   ODEB200_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
-  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k, ENS_BLOCK, 0) != cudaSuccess || per_sm < 1) {
+  const int block = o->method == ODE_B200_M_ODE23S ? S23_BLOCK : ENS_BLOCK;  // threads per block of the main kernel
+  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k, block, 0) != cudaSuccess || per_sm < 1) {
     cudaGetLastError();
     per_sm = 4;
   }
-  long long need = (io->n_traj + ENS_BLOCK - 1) / ENS_BLOCK;
+  long long need = (io->n_traj + block - 1) / block;
   long long grid = (long long)sms * per_sm;  // persistent: every lane pulls work until the counter runs out
   if (need < grid) grid = need;
   if (grid < 1) grid = 1;
@@ -465,7 +466,7 @@ static int launch_ensemble(const ode_b200_opts* o, const ode_b200_ensemble_io* i
     ODEB200_CUDA(cudaLaunchKernel(pick_init_kernel(o), dim3((unsigned)gi), dim3(ENS_BLOCK), kargs, 0, stream));
     note_launch();
   }
-  ODEB200_CUDA(cudaLaunchKernel(k, dim3((unsigned)grid), dim3(ENS_BLOCK), kargs, 0, stream));
+  ODEB200_CUDA(cudaLaunchKernel(k, dim3((unsigned)grid), dim3(block), kargs, 0, stream));
   note_launch();
   if (two_pass) {
     // literal pass: re-integrates the trajectories the fast pass marked ODE_B200_ST_REDO (non-finite trial

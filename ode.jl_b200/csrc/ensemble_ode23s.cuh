@@ -148,7 +148,7 @@ __device__ __forceinline__ int eval_jacobian(double t, const double (&x)[D], con
 }
 
 template <class Rhs, int MODE, int JAC>
-__global__ void __launch_bounds__(ENS_BLOCK, (Rhs::DOF <= 3) ? ODEB200_S23_MINB : 0) ens_ode23s_kernel(const EnsembleArgs A) {
+__global__ void __launch_bounds__(S23_BLOCK, (Rhs::DOF <= 3) ? ODEB200_S23_MINB : 0) ens_ode23s_kernel(const EnsembleArgs A) {
   constexpr int D = Rhs::DOF, NPA = RhsNP<Rhs>::value;
   const double dd = 1.0 / (2.0 + sqrt(2.0));  // :270
   const double e32 = 6.0 + sqrt(2.0);         // :271
@@ -163,7 +163,7 @@ __global__ void __launch_bounds__(ENS_BLOCK, (Rhs::DOF <= 3) ? ODEB200_S23_MINB 
   // for small systems it is parked in shared memory, [entry][thread] so that a warp's accesses are conflict free,
   // which frees 2*D*D registers for occupancy.
   constexpr bool JS = (D <= ODEB200_S23_JSHARED_MAXD);
-  __shared__ double Jsh[JS ? D * D : 1][JS ? ENS_BLOCK : 1];
+  __shared__ double Jsh[JS ? D * D : 1][JS ? S23_BLOCK : 1];
   double Jreg[JS ? 1 : D][JS ? 1 : D];
   double t = 0.0, h = 0.0, last_tout = 0.0;
   int nacc = 0, nrej = 0, nrhs = 0, npts = 0;

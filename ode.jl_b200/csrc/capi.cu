@@ -359,20 +359,111 @@ static const void* pick_init_kernel(const ode_b200_opts* o) {
     case ODE_B200_M_RK45_FE: return (const void*)adapt_kernel_rk45_init(o->rhs);
     case ODE_B200_M_DOPRI5: return (const void*)adapt_kernel_dopri5_init(o->rhs);
     case ODE_B200_M_FEH78: return (const void*)adapt_kernel_feh78_init(o->rhs);
+    case ODE_B200_M_ODE23S: return (const void*)ode23s_init_kernel(o->rhs, o->jacobian);
     default: return nullptr;
   }
+}
+// doubles per trajectory the pre-pass writes: {dt0, f0[dof]} for adaptive RK, {h, F0[dof], J[dof][dof], rhs count} for ode23s
+static size_t init_width(const ode_b200_opts* o) {
+  return o->method == ODE_B200_M_ODE23S ? (size_t)(2 + o->dof + o->dof * o->dof) : (size_t)(o->dof + 1);
+}
+
+// ---- dispatch order: counting sort of the trajectories by the first step size (common.cuh, sched_key) -----------
+// scratch words: [0] min key, [1] max key (finite keys), [2 .. 2+BINS) histogram / running offsets
+__global__ void __launch_bounds__(256) sched_range_kernel(const double* init, int width, long long n, unsigned int* w) {
+  __shared__ unsigned int smin[8], smax[8];
+  unsigned int lo = 0xffffffffu, hi = 0u;
+  for (long long i = blockIdx.x * 256LL + threadIdx.x; i < n; i += (long long)gridDim.x * 256) {
+    const unsigned int k = sched_key(init[i * width]);
+    if (k < 0x7ff00000u) {
+      lo = k < lo ? k : lo;
+      hi = k > hi ? k : hi;
+    }
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    const unsigned int a = __shfl_down_sync(0xffffffffu, lo, o), b = __shfl_down_sync(0xffffffffu, hi, o);
+    lo = a < lo ? a : lo;
+    hi = b > hi ? b : hi;
+  }
+  if ((threadIdx.x & 31) == 0) {
+    smin[threadIdx.x >> 5] = lo;
+    smax[threadIdx.x >> 5] = hi;
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    for (int q = 1; q < 8; q++) {
+      lo = smin[q] < lo ? smin[q] : lo;
+      hi = smax[q] > hi ? smax[q] : hi;
+    }
+    atomicMin(&w[0], lo);
+    atomicMax(&w[1], hi);
+  }
+}
+// pass = 0: histogram; pass = 1: scatter.  Each block works on a contiguous chunk through a shared-memory histogram.
+__global__ void __launch_bounds__(256) sched_bin_kernel(const double* init, int width, long long n, unsigned int* w, int* order,
+                                                        int pass) {
+  __shared__ unsigned int cnt[SCHED_BINS], base[SCHED_BINS];
+  const unsigned int lo = w[0], hi = w[1];
+  unsigned int* hist = w + 2;
+  const long long per = (n + gridDim.x - 1) / gridDim.x, i0 = blockIdx.x * per, i1 = (i0 + per < n) ? i0 + per : n;
+  for (int q = threadIdx.x; q < SCHED_BINS; q += 256) cnt[q] = 0u;
+  __syncthreads();
+  for (long long i = i0 + threadIdx.x; i < i1; i += 256) atomicAdd(&cnt[sched_bin(sched_key(init[i * width]), lo, hi)], 1u);
+  __syncthreads();
+  for (int q = threadIdx.x; q < SCHED_BINS; q += 256) {
+    const unsigned int c = cnt[q];
+    if (c) base[q] = atomicAdd(&hist[q], c);  // pass 0: counts; pass 1: hist holds the exclusive scan, this reserves a range
+    cnt[q] = 0u;
+  }
+  if (pass == 0) return;
+  __syncthreads();
+  for (long long i = i0 + threadIdx.x; i < i1; i += 256) {
+    const int bn = sched_bin(sched_key(init[i * width]), lo, hi);
+    order[base[bn] + atomicAdd(&cnt[bn], 1u)] = (int)i;
+  }
+}
+__global__ void __launch_bounds__(SCHED_BINS) sched_scan_kernel(unsigned int* w) {  // exclusive scan of the histogram, in place
+  __shared__ unsigned int part[SCHED_BINS];
+  unsigned int* hist = w + 2;
+  const unsigned int mine = hist[threadIdx.x];
+  part[threadIdx.x] = mine;
+  __syncthreads();
+  for (int off = 1; off < SCHED_BINS; off <<= 1) {
+    const unsigned int v = threadIdx.x >= off ? part[threadIdx.x - off] : 0u;
+    __syncthreads();
+    part[threadIdx.x] += v;
+    __syncthreads();
+  }
+  hist[threadIdx.x] = part[threadIdx.x] - mine;
+}
+// bytes of scratch for the order (index array + histogram), after the pre-pass output; 0 = natural order
+static size_t order_scratch_bytes(const ode_b200_opts* o, const ode_b200_ensemble_io* io) {
+  if (io->n_traj >= (1LL << 31)) return 0;
+  // The tail the order removes is about half a trajectory per lane: it matters with a handful of trajectories per
+  // lane and is noise with many (2^20 Lorenz trajectories = 11 per lane: the sort costs more than it saves).
+  // ODE_B200_ORDER=0/1 overrides, for A/B measurements.
+  if (const char* e = getenv("ODE_B200_ORDER")) {
+    if (atoi(e) == 0) return 0;
+  } else {
+    int dev = 0, sms = 148;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    if (io->n_traj > 6LL * sms * 640) return 0;  // (~640 resident lanes per SM)
+  }
+  return pad256((size_t)io->n_traj * sizeof(int)) + pad256((size_t)(SCHED_BINS + 2) * sizeof(unsigned int));
 }
 // doubles of pre-pass scratch launch_ensemble can use for this call (0: hinit stays inline)
 static size_t init_scratch_doubles(const ode_b200_opts* o, const ode_b200_ensemble_io* io) {
   const bool want_points = io->pts_y != nullptr || io->trace != nullptr;
   const bool mode1 = (want_points && o->points != ODE_B200_POINTS_FINAL) || io->trace;
   if (mode1 || io->n_traj < 4096 || !pick_init_kernel(o)) return 0;
-  return (size_t)io->n_traj * (size_t)(o->dof + 1);
+  return (size_t)io->n_traj * init_width(o);
 }
 
 static int launch_ensemble(const ode_b200_opts* o, const ode_b200_ensemble_io* io, unsigned long long* counter,
                            cudaStream_t stream, bool time_it, double* init_scratch = nullptr,
-                           const double* uparams_host = nullptr) {
+                           const double* uparams_host = nullptr, void* order_scratch = nullptr) {
   const bool want_points = io->pts_y != nullptr || io->trace != nullptr;
   const int mode = (want_points && o->points != ODE_B200_POINTS_FINAL) || io->trace ? 1 : 0;
   // one parameter vector for the whole ensemble: the mode-0 fast kernel reads it from the constant bank
@@ -463,8 +554,26 @@ static int launch_ensemble(const ode_b200_opts* o, const ode_b200_ensemble_io* i
     A.init = init_scratch;
     long long gi = (long long)sms * 8;
     if (need < gi) gi = need;
-    ODEB200_CUDA(cudaLaunchKernel(pick_init_kernel(o), dim3((unsigned)gi), dim3(ENS_BLOCK), kargs, 0, stream));
+    ODEB200_CUDA(cudaLaunchKernel(pick_init_kernel(o), dim3((unsigned)gi), dim3(block), kargs, 0, stream));
     note_launch();
+    if (order_scratch && order_scratch_bytes(o, io) > 0) {  // longest expected trajectory first
+      int* order = reinterpret_cast<int*>(order_scratch);
+      unsigned int* hist = reinterpret_cast<unsigned int*>((char*)order_scratch + pad256((size_t)io->n_traj * sizeof(int)));
+      const unsigned int seed[2] = {0xffffffffu, 0u};
+      ODEB200_CUDA(cudaMemsetAsync(hist, 0, (size_t)(SCHED_BINS + 2) * sizeof(unsigned int), stream));
+      ODEB200_CUDA(cudaMemsetAsync(hist, 0xff, sizeof(unsigned int), stream));  // min key starts at the largest value
+      (void)seed;
+      const int w = (int)init_width(o);
+      const unsigned gs = (unsigned)(io->n_traj / 2048 + 1 < (long long)sms * 4 ? io->n_traj / 2048 + 1 : (long long)sms * 4);
+      sched_range_kernel<<<gs, 256, 0, stream>>>(init_scratch, w, io->n_traj, hist);
+      sched_bin_kernel<<<gs, 256, 0, stream>>>(init_scratch, w, io->n_traj, hist, order, 0);
+      sched_scan_kernel<<<1, SCHED_BINS, 0, stream>>>(hist);
+      sched_bin_kernel<<<gs, 256, 0, stream>>>(init_scratch, w, io->n_traj, hist, order, 1);
+      note_launch();
+      for (int q = 0; q < 3; q++) note_launch();
+      ODEB200_CUDA(cudaGetLastError());
+      A.order = order;
+    }
   }
   ODEB200_CUDA(cudaLaunchKernel(k, dim3((unsigned)grid), dim3(block), kargs, 0, stream));
   note_launch();
@@ -624,12 +733,14 @@ int ode_b200_solve_ensemble_dev(const ode_b200_opts* opts, const ode_b200_ensemb
   const bool need_status = !d.status && is_adaptive_rk(opts->method);  // the fast and literal passes talk through `status`
   const size_t status_bytes = need_status ? pad256((size_t)io->n_traj * sizeof(int)) : 0;
   const size_t want = init_scratch_doubles(opts, &d);
+  const size_t order_bytes = want > 0 ? order_scratch_bytes(opts, &d) : 0;
   char* blk = nullptr;
-  ODEB200_CUDA(cudaMallocAsync((void**)&blk, 256 + status_bytes + pad256(want * sizeof(double)), st));
+  ODEB200_CUDA(cudaMallocAsync((void**)&blk, 256 + status_bytes + pad256(want * sizeof(double)) + order_bytes, st));
   unsigned long long* counter = reinterpret_cast<unsigned long long*>(blk);
   if (need_status) d.status = reinterpret_cast<int*>(blk + 256);
   double* init_scratch = want > 0 ? reinterpret_cast<double*>(blk + 256 + status_bytes) : nullptr;
-  rc = launch_ensemble(opts, &d, counter, st, true, init_scratch, fetch_upar ? upar : nullptr);
+  void* order_scratch = order_bytes ? blk + 256 + status_bytes + pad256(want * sizeof(double)) : nullptr;
+  rc = launch_ensemble(opts, &d, counter, st, true, init_scratch, fetch_upar ? upar : nullptr, order_scratch);
   cudaFreeAsync(blk, st);  // stream-ordered: after the kernels above
   return rc;
 }
@@ -857,7 +968,8 @@ int ode_b200_solve_ensemble(const ode_b200_opts* opts, const ode_b200_ensemble_i
   if (io->trace) bytes += pad256((size_t)io->trace_cap * 32) + 256;
   if (bytes <= kSmallCallBytes && !getenv("ODE_B200_NO_SMALL_PATH")) return solve_ensemble_small(opts, io, n_par);
   const size_t init_doubles = init_scratch_doubles(opts, io);  // hinit pre-pass scratch (0: inline)
-  bytes += pad256(init_doubles * 8);
+  const size_t order_bytes = init_doubles ? order_scratch_bytes(opts, io) : 0;
+  bytes += pad256(init_doubles * 8) + order_bytes + 256;
   rc = g_arena.ensure(opts->device, bytes);
   if (rc) return rc;
   cudaStream_t st = g_arena.stream;
@@ -897,6 +1009,7 @@ int ode_b200_solve_ensemble(const ode_b200_opts* opts, const ode_b200_ensemble_i
   d.n_rhs = zc_nf ? zc_nf : (io->n_rhs ? g_arena.take<int>(n) : nullptr);
   d.status = g_arena.take<int>(n);  // always: the fast and literal adaptive-RK passes talk through it
   double* dinit = init_doubles ? g_arena.take<double>(init_doubles) : nullptr;
+  char* dorder = order_bytes ? g_arena.take<char>(order_bytes) : nullptr;
   if (pts) {
     d.pts_t = g_arena.take<double>((size_t)n * io->pts_cap);
     d.pts_y = g_arena.take<double>((size_t)n * io->pts_cap * D);
@@ -968,7 +1081,8 @@ int ode_b200_solve_ensemble(const ode_b200_opts* opts, const ode_b200_ensemble_i
     }
     if (n_chunks == 1) ODEB200_CUDA(cudaEventRecord(g_ev0, cs));
     rc = launch_ensemble(opts, &dc, n_chunks > 1 ? counters + 32 * c : counter, cs, false,
-                         dinit ? dinit + lo * (D + 1) : nullptr, opts->params_stride == 0 ? io->params : nullptr);
+                         dinit ? dinit + lo * init_width(opts) : nullptr, opts->params_stride == 0 ? io->params : nullptr,
+                         n_chunks == 1 ? (void*)dorder : nullptr);
     if (rc) return rc;
     if (n_chunks == 1) ODEB200_CUDA(cudaEventRecord(g_ev1, cs));
     if (io->t_final && !zc_t) ODEB200_CUDA(cudaMemcpyAsync(io->t_final + lo, dc.t_final, m * 8, cudaMemcpyDeviceToHost, cs));

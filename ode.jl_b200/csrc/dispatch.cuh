@@ -20,6 +20,7 @@ EnsembleKernel adapt_kernel_dopri5_init(int rhs);  // hinit pre-pass (ens_adapt_
 EnsembleKernel adapt_kernel_feh78_init(int rhs);  // hinit pre-pass (ens_adapt_init_kernel)
 EnsembleKernel fixed_kernel(int method, int rhs);
 EnsembleKernel ode23s_kernel(int rhs, int mode, int jac);  // jac: 0 fdjacobian, 1 analytic functor
+EnsembleKernel ode23s_init_kernel(int rhs, int jac);       // pre-pass: first step, F0, first Jacobian
 EnsembleKernel rosenbrock_kernel(int method, int rhs, int jac);
 EnsembleKernel ms_kernel(int rhs);  // ode_ms, orders 1..5
 

@@ -149,6 +149,7 @@ __global__ void __launch_bounds__(ENS_BLOCK, LITERAL ? 1 : adapt_min_blocks<Tab,
     if (idx < 0) {
       idx = (long long)atomicAdd(A.work_counter, 1ULL);
       if (idx >= A.n_traj) break;
+      if (!LITERAL && A.order != nullptr) idx = A.order[idx];  // longest expected trajectory first (common.cuh)
       if (LITERAL && A.status[idx] != ODE_B200_ST_REDO) {  // the literal pass redoes marked trajectories only
         idx = -1;
         continue;
@@ -197,6 +198,7 @@ __global__ void __launch_bounds__(ENS_BLOCK, LITERAL ? 1 : adapt_min_blocks<Tab,
 
     // ------------------------------------------------ rk_embedded_step! :371-399
     double ytrial[D], yerr[D], dtk[NK][D], klast[D];
+    bool rhs_bad = false;  // a deferred sqrt / division check of the right-hand side failed (rhs.cuh eval_nb)
     constexpr double b10 = Tab::b(0, 0), b20 = Tab::b(1, 0);
     const double b10v = BANK ? A.tab[tab_b_index(S, 0, 0)] : b10, b20v = BANK ? A.tab[tab_b_index(S, 1, 0)] : b20;
 #pragma unroll
@@ -222,7 +224,8 @@ __global__ void __launch_bounds__(ENS_BLOCK, LITERAL ? 1 : adapt_min_blocks<Tab,
       });
       constexpr double c = Tab::c(s);
       const double cv = BANK ? A.tab[tab_c_index(S, s)] : c;
-      Rhs::eval(t + cv * dt, ytmp, ks, p);  // :456
+      if constexpr (LITERAL) Rhs::eval(t + cv * dt, ytmp, ks, p);  // :456
+      else rhs_eval_fast<Rhs>(t + cv * dt, ytmp, ks, p, rhs_bad);  // same values; failed fast-path checks -> rhs_bad
       constexpr double b1 = Tab::b(0, s), b2 = Tab::b(1, s);
       const double b1v = BANK ? A.tab[tab_b_index(S, 0, s)] : b1, b2v = BANK ? A.tab[tab_b_index(S, 1, s)] : b2;
 #pragma unroll
@@ -261,7 +264,7 @@ __global__ void __launch_bounds__(ENS_BLOCK, LITERAL ? 1 : adapt_min_blocks<Tab,
         expo_or = expo_or > he ? expo_or : he;
       }
     }
-    if (!LITERAL) weird = expo_or == 0x7ff00000u;
+    if (!LITERAL) weird = (expo_or == 0x7ff00000u) || rhs_bad;
     if (!LITERAL && weird) {  // hand the trajectory to the literal pass (see header)
       A.status[idx] = ODE_B200_ST_REDO;
       atomicAdd(A.redo_count, 1);
@@ -308,7 +311,7 @@ __global__ void __launch_bounds__(ENS_BLOCK, LITERAL ? 1 : adapt_min_blocks<Tab,
 #pragma unroll
         for (int d = 0; d < D; d++) f1[d] = klast[d];
       } else {
-        Rhs::eval(t + dt, ytrial, f1, p);
+        Rhs::eval(t + dt, ytrial, f1, p);  // (exact: this branch is taken once per accepted step)
       }
       if (MODE == 1) {
         double* py = A.pts_y + (idx * A.pts_cap) * D;

@@ -147,6 +147,83 @@ __device__ __forceinline__ int eval_jacobian(double t, const double (&x)[D], con
   return eval_jacobian<Rhs, JAC, D, NPA, true>(t, x, p, J, unused);
 }
 
+// hinit with p = 3 (src/ODE.jl:279-287): returns the first step (before the maxstep clip of :287), F0 and the RHS count
+template <class Rhs, int D, int NPA>
+__device__ __forceinline__ double hinit_ode23s(const EnsembleArgs& A, double tstart, double tfinal, double tdir,
+                                               const double (&y)[D], const double (&p)[NPA], double (&F0)[D], int& nrhs) {
+  double h = A.initstep;  // :279
+  if (h == 0.0) {         // hinit, :282 (src/ODE.jl:85-112)
+    double n0 = fabs(y[0]);
+#pragma unroll
+    for (int d = 1; d < D; d++) n0 = normInf_step(n0, fabs(y[d]));
+    double tau = jl_max(A.reltol * n0, A.abstol);
+    double d0 = n0 / tau;
+    Rhs::eval(tstart, y, F0, p);
+    double n1 = fabs(F0[0]);
+#pragma unroll
+    for (int d = 1; d < D; d++) n1 = normInf_step(n1, fabs(F0[d]));
+    double d1 = n1 / tau;
+    double h0 = (d0 < 1e-5 || d1 < 1e-5) ? 1e-6 : 0.01 * (d0 / d1);
+    double x1[D], f1[D];
+    double th = tdir * h0;
+#pragma unroll
+    for (int d = 0; d < D; d++) x1[d] = y[d] + th * F0[d];
+    Rhs::eval(tstart + tdir * h0, x1, f1, p);
+    double n2 = fabs(f1[0] - F0[0]);
+#pragma unroll
+    for (int d = 1; d < D; d++) n2 = normInf_step(n2, fabs(f1[d] - F0[d]));
+    double d2 = n2 / (tau * h0);
+    double dm = jl_max(d1, d2);
+    double h1;
+    if (dm <= 1e-15) {
+      h1 = jl_max(1e-6, 1e-3 * h0);
+    } else {
+      double pw = -(2.0 + dm_log10(dm)) / 4.0;
+      h1 = dm_pow(10.0, pw);
+    }
+    h = tdir * jl_min(jl_min(100.0 * h0, h1), tdir * (tfinal - tstart));
+    nrhs = 2;
+  } else {  // :284-285
+    Rhs::eval(tstart, y, F0, p);
+    nrhs = 1;
+  }
+  return h;
+}
+
+// Pre-pass for large ensembles (like ens_adapt_init_kernel): the first step, F0 and the first Jacobian of every
+// trajectory with full warps -- inside the persistent kernel a lane that fetches a trajectory would run hinit and
+// D+2 more right-hand sides alone while its 31 neighbours wait.  init[idx] = {h, F0[D], J[D][D], rhs count}; h also
+// feeds the dispatch order.
+template <class Rhs, int JAC>
+__global__ void __launch_bounds__(S23_BLOCK) ens_ode23s_init_kernel(const EnsembleArgs A) {
+  constexpr int D = Rhs::DOF, NPA = RhsNP<Rhs>::value, W = 2 + D + D * D;
+  const double tstart = A.tspan[0];
+  const double tfinal = A.tspan[A.n_tspan - 1];
+  const double tdir = jl_sign(tfinal - tstart);
+  for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < A.n_traj;
+       idx += (long long)gridDim.x * blockDim.x) {
+    double y[D], F0[D], p[NPA], Jt[D][D];
+#pragma unroll
+    for (int d = 0; d < D; d++) y[d] = A.y0[idx * D + d];
+#pragma unroll
+    for (int q = 0; q < NPA; q++) p[q] = (q < Rhs::NP) ? A.params[idx * A.params_stride + q] : 0.0;
+    int nrhs = 0;
+    double h = hinit_ode23s<Rhs, D, NPA>(A, tstart, tfinal, tdir, y, p, F0, nrhs);
+    h = tdir * jl_min(fabs(h), A.maxstep);  // :287
+    nrhs += eval_jacobian<Rhs, JAC, D, NPA>(tstart, y, p, Jt);  // :294
+    double* out = A.init + idx * W;
+    out[0] = h;
+#pragma unroll
+    for (int d = 0; d < D; d++) out[1 + d] = F0[d];
+#pragma unroll
+    for (int i = 0; i < D; i++) {
+#pragma unroll
+      for (int j = 0; j < D; j++) out[1 + D + i * D + j] = Jt[i][j];
+    }
+    out[1 + D + D * D] = (double)nrhs;
+  }
+}
+
 template <class Rhs, int MODE, int JAC>
 __global__ void __launch_bounds__(S23_BLOCK, (Rhs::DOF <= 3) ? ODEB200_S23_MINB : 0) ens_ode23s_kernel(const EnsembleArgs A) {
   constexpr int D = Rhs::DOF, NPA = RhsNP<Rhs>::value;
@@ -173,6 +250,7 @@ __global__ void __launch_bounds__(S23_BLOCK, (Rhs::DOF <= 3) ? ODEB200_S23_MINB 
     if (idx < 0) {
       idx = (long long)atomicAdd(A.work_counter, 1ULL);
       if (idx >= A.n_traj) break;
+      if (A.order != nullptr) idx = A.order[idx];  // longest expected trajectory first (common.cuh)
 #pragma unroll
       for (int d = 0; d < D; d++) y[d] = A.y0[idx * D + d];
 #pragma unroll
@@ -181,44 +259,24 @@ __global__ void __launch_bounds__(S23_BLOCK, (Rhs::DOF <= 3) ? ODEB200_S23_MINB 
       nacc = nrej = nrhs = 0;
       attempts = 0;
       ntrace = 0;
-      h = A.initstep;  // :279
-      if (h == 0.0) {  // hinit with p = 3, :282 (src/ODE.jl:85-112)
-        double n0 = fabs(y[0]);
+      double Jt[D][D];
+      if (MODE == 0 && A.init != nullptr) {  // computed by ens_ode23s_init_kernel with all lanes busy
+        const double* in = A.init + idx * (2 + D + D * D);
+        h = in[0];
 #pragma unroll
-        for (int d = 1; d < D; d++) n0 = normInf_step(n0, fabs(y[d]));
-        double tau = jl_max(A.reltol * n0, A.abstol);
-        double d0 = n0 / tau;
-        Rhs::eval(tstart, y, F0, p);
-        double n1 = fabs(F0[0]);
+        for (int d = 0; d < D; d++) F0[d] = in[1 + d];
 #pragma unroll
-        for (int d = 1; d < D; d++) n1 = normInf_step(n1, fabs(F0[d]));
-        double d1 = n1 / tau;
-        double h0 = (d0 < 1e-5 || d1 < 1e-5) ? 1e-6 : 0.01 * (d0 / d1);
-        double x1[D], f1[D];
-        double th = tdir * h0;
+        for (int i = 0; i < D; i++) {
 #pragma unroll
-        for (int d = 0; d < D; d++) x1[d] = y[d] + th * F0[d];
-        Rhs::eval(tstart + tdir * h0, x1, f1, p);
-        double n2 = fabs(f1[0] - F0[0]);
-#pragma unroll
-        for (int d = 1; d < D; d++) n2 = normInf_step(n2, fabs(f1[d] - F0[d]));
-        double d2 = n2 / (tau * h0);
-        double dm = jl_max(d1, d2);
-        double h1;
-        if (dm <= 1e-15) {
-          h1 = jl_max(1e-6, 1e-3 * h0);
-        } else {
-          double pw = -(2.0 + dm_log10(dm)) / 4.0;
-          h1 = dm_pow(10.0, pw);
+          for (int j = 0; j < D; j++) Jt[i][j] = in[1 + D + i * D + j];
         }
-        h = tdir * jl_min(jl_min(100.0 * h0, h1), tdir * (tfinal - tstart));
-        nrhs = 2;
-      } else {  // :284-285
-        Rhs::eval(tstart, y, F0, p);
-        nrhs = 1;
+        nrhs = (int)in[1 + D + D * D];
+      } else {
+        h = hinit_ode23s<Rhs, D, NPA>(A, tstart, tfinal, tdir, y, p, F0, nrhs);
+        h = tdir * jl_min(fabs(h), A.maxstep);  // :287
+        nrhs += eval_jacobian<Rhs, JAC, D, NPA>(t, y, p, Jt);  // :294
       }
-      h = tdir * jl_min(fabs(h), A.maxstep);  // :287
-      if (MODE == 1) {                        // tout = [t], yout = [y0] :290-291
+      if (MODE == 1) {  // tout = [t], yout = [y0] :290-291
         if (A.pts_cap > 0 && A.pts_y) {
           A.pts_t[idx * A.pts_cap] = tstart;
 #pragma unroll
@@ -227,16 +285,12 @@ __global__ void __launch_bounds__(S23_BLOCK, (Rhs::DOF <= 3) ? ODEB200_S23_MINB 
         npts = 1;
         last_tout = tstart;
       }
-      {
-        double Jt[D][D];
-        nrhs += eval_jacobian<Rhs, JAC, D, NPA>(t, y, p, Jt);  // :294
 #pragma unroll
-        for (int i = 0; i < D; i++) {
+      for (int i = 0; i < D; i++) {
 #pragma unroll
-          for (int j = 0; j < D; j++) {
-            if constexpr (JS) Jsh[i * D + j][threadIdx.x] = Jt[i][j];
-            else Jreg[i][j] = Jt[i][j];
-          }
+        for (int j = 0; j < D; j++) {
+          if constexpr (JS) Jsh[i * D + j][threadIdx.x] = Jt[i][j];
+          else Jreg[i][j] = Jt[i][j];
         }
       }
     }

@@ -13,6 +13,13 @@ EnsembleKernel ode23s_kernel(int rhs, int mode, int jac) {
   if (mode) return jac ? ode23s_for<1, 1>(rhs) : ode23s_for<1, 0>(rhs);
   return jac ? ode23s_for<0, 1>(rhs) : ode23s_for<0, 0>(rhs);
 }
+template <int JAC>
+static EnsembleKernel ode23s_init_for(int rhs) {
+#define X(R) return ens_ode23s_init_kernel<R, JAC>
+  ODEB200_RHS_SWITCH(rhs, X)
+#undef X
+}
+EnsembleKernel ode23s_init_kernel(int rhs, int jac) { return jac ? ode23s_init_for<1>(rhs) : ode23s_init_for<0>(rhs); }
 template <class Coef, int JAC>
 static EnsembleKernel ros_for(int rhs) {
 #define X(R) return ens_rosenbrock_kernel<R, Coef, JAC>

@@ -411,7 +411,8 @@ int ode_b200_slab_create(const ode_b200_opts* o, int64_t n_local, int64_t n_glob
     const long long base = n_global / world, rem = n_global % world;
     s->sc.i0 = rank * base + (rank < rem ? rank : rem);
   }
-  const size_t padded = (size_t)(n_local + 2 * mi.H + 8) * sizeof(double);
+  // (one tile of zero padding behind the slab: the bulk-copy staging of large.cuh reads whole tile rows)
+  const size_t padded = (size_t)(n_local + 2 * mi.H + 8 + LARGE_THREADS * LARGE_P) * sizeof(double);
   int sms = 0;
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, o->device);
   s->init_blocks = sms * 8;

@@ -541,6 +541,37 @@ __device__ __forceinline__ void stencil_sweep(const double (&v)[P], double (&out
   }
 }
 
+// ---- bulk-copy (TMA engine) staging of the next tile, ODEB200_LARGE_BULK=1 ------------------------------------
+// Instead of prefetching the next tile's y and k1 into 16 registers per thread, one thread asks the copy engine for
+// the two 4 KB tile rows (cp.async.bulk global -> shared, completion counted on an mbarrier); the threads pick their
+// 4 points up from shared memory when they get there.  Frees the prefetch registers for occupancy at the price of
+// one more block barrier per tile.  Measured against the register prefetch in profiles/large_rd_r2.md.
+#ifndef ODEB200_LARGE_BULK
+#define ODEB200_LARGE_BULK 0
+#endif
+__device__ __forceinline__ unsigned int smem_addr(const void* p) { return (unsigned int)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(unsigned long long* bar, unsigned int arrivals) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_addr(bar)), "r"(arrivals) : "memory");
+  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(unsigned long long* bar, unsigned int bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_addr(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_copy_g2s(void* dst_smem, const void* src_gmem, unsigned int bytes, unsigned long long* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_addr(dst_smem)),
+               "l"(src_gmem), "r"(bytes), "r"(smem_addr(bar))
+               : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned long long* bar, unsigned int parity) {
+  unsigned int done = 0;
+  while (!done) {
+    asm volatile("{\n  .reg .pred p;\n  mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n  selp.u32 %0, 1, 0, p;\n}"
+                 : "=r"(done)
+                 : "r"(smem_addr(bar)), "r"(parity)
+                 : "memory");
+  }
+}
+
 // ---- the fused attempt ---------------------------------------------------------
 template <class Tab, class Rhs>
 struct LargeGeom {
@@ -597,29 +628,65 @@ __global__ void __launch_bounds__(LARGE_THREADS) large_attempt_kernel(
   bool anynan = false;
   int xc = 0;  // exchange counter: shared-memory line parity alternates across stages AND tiles
 
+  long long tile = blockIdx.x;
+#if ODEB200_LARGE_BULK
+  // the next tile's y, k1 rows are staged in shared memory by the copy engine (the arrays are padded by one tile, so a
+  // whole row can always be read; what lies beyond the slab is zero, like load_chunk's fill)
+  constexpr int WT = T * P;
+  __shared__ __align__(128) double tY[WT], tK[WT];
+  __shared__ unsigned long long tbar;
+  unsigned int tphase = 0;
+  if (tid == 0) mbar_init(&tbar, 1);
+  __syncthreads();
+  if (tid == 0 && tile < A.tiles) {
+    mbar_expect_tx(&tbar, 2u * WT * 8u);
+    bulk_copy_g2s(tY, yA + tile * VAL, WT * 8u, &tbar);
+    bulk_copy_g2s(tK, kA + tile * VAL, WT * 8u, &tbar);
+  }
+#else
   // software prefetch: the next tile's y, k1 are requested before the current tile is computed
   double yN[P], kN[P];
-  long long tile = blockIdx.x;
   if (tile < A.tiles) {
     load_chunk<P>(yA, tile * VAL + off0, lim, yN);
     load_chunk<P>(kA, tile * VAL + off0, lim, kN);
   }
+#endif
   for (; tile < A.tiles; tile += gridDim.x) {
     const long long q0 = tile * VAL + off0;  // padded index of my first point
     long long g0 = sc.i0 + (q0 - H);         // its global grid index on the periodic ring (H < n_global)
     if (g0 < 0) g0 += sc.n_global;
     else if (g0 >= sc.n_global) g0 -= sc.n_global;
     double y[P], k1[P];
+    const long long nxt = tile + gridDim.x;
+#if ODEB200_LARGE_BULK
+    mbar_wait(&tbar, tphase);
+    tphase ^= 1u;
+#pragma unroll
+    for (int c = 0; c < P / 2; c++) {
+      const double2 a = *reinterpret_cast<const double2*>(tY + off0 + 2 * c);
+      const double2 b = *reinterpret_cast<const double2*>(tK + off0 + 2 * c);
+      y[2 * c] = a.x;
+      y[2 * c + 1] = a.y;
+      k1[2 * c] = b.x;
+      k1[2 * c + 1] = b.y;
+    }
+    __syncthreads();  // every thread has its points: the rows can be overwritten
+    if (tid == 0 && nxt < A.tiles) {
+      mbar_expect_tx(&tbar, 2u * WT * 8u);
+      bulk_copy_g2s(tY, yA + nxt * VAL, WT * 8u, &tbar);
+      bulk_copy_g2s(tK, kA + nxt * VAL, WT * 8u, &tbar);
+    }
+#else
 #pragma unroll
     for (int p = 0; p < P; p++) {
       y[p] = yN[p];
       k1[p] = kN[p];
     }
-    const long long nxt = tile + gridDim.x;
     if (nxt < A.tiles) {
       load_chunk<P>(yA, nxt * VAL + off0, lim, yN);
       load_chunk<P>(kA, nxt * VAL + off0, lim, kN);
     }
+#endif
 
     double ytrial[P], yerr[P], dtk[NK][P], klast[P];
     constexpr double b10 = Tab::b(0, 0), b20 = Tab::b(1, 0);

@@ -125,6 +125,18 @@ struct RhsKepler {
     f[2] = div_by(-y[0], R3);
     f[3] = div_by(-y[1], R3);
   }
+  // The same values as straight-line code for the fast ensemble kernels: sqrt and the two divisions carry deferred
+  // acceptance checks (common.cuh sqrt_nb / div_nb) instead of a branch each; `bad` sends the trajectory to the
+  // literal pass, which uses eval().
+  __device__ __forceinline__ static void eval_nb(double, const double (&y)[4], double (&f)[4], const double (&)[1], bool& bad) {
+    double r2 = y[0] * y[0] + y[1] * y[1];
+    double r3 = r2 * sqrt_nb(r2, bad);
+    const Recip R3 = recip_prepare(r3);
+    f[0] = y[2];
+    f[1] = y[3];
+    f[2] = div_nb<true>(-y[0], R3, bad);
+    f[3] = div_nb<true>(-y[1], R3, bad);
+  }
   __device__ __forceinline__ static void jac(double, const double (&y)[4], double (&J)[4][4], const double (&)[1]) {
     const double x = y[0], yy = y[1];
     const double r2 = x * x + yy * yy;
@@ -157,5 +169,32 @@ template <class R>
 struct RhsNP {
   static constexpr int value = R::NP > 0 ? R::NP : 1;
 };
+
+// rhs_eval_fast: R::eval_nb (deferred checks ORed into `bad`) where a functor has one, else R::eval
+template <class R, int D, int NPA>
+__device__ __forceinline__ auto rhs_eval_fast_impl(double t, const double (&y)[D], double (&f)[D], const double (&p)[NPA],
+                                                   bool& bad, int) -> decltype(R::eval_nb(t, y, f, p, bad), void()) {
+  R::eval_nb(t, y, f, p, bad);
+}
+template <class R, int D, int NPA>
+__device__ __forceinline__ void rhs_eval_fast_impl(double t, const double (&y)[D], double (&f)[D], const double (&p)[NPA],
+                                                   bool&, long) {
+  R::eval(t, y, f, p);
+}
+#ifndef ODEB200_RHS_NB
+// 1: functors with an eval_nb use it in the fast adaptive kernels; 0: always R::eval (a branch per sqrt / division).
+// Measured on Kepler/feh78 (profiles/ensemble_kernels_r2.md): with the branches gone the scheduler interleaves so
+// much more that the kernel needs 214 registers instead of 150 (2 CTAs/SM): 22.3 ms vs 18.6 ms; capped at 168 / 128
+// registers it spills: 19.2 / 19.0 ms.  Off.
+#define ODEB200_RHS_NB 0
+#endif
+template <class R, int D, int NPA>
+__device__ __forceinline__ void rhs_eval_fast(double t, const double (&y)[D], double (&f)[D], const double (&p)[NPA], bool& bad) {
+#if ODEB200_RHS_NB
+  rhs_eval_fast_impl<R, D, NPA>(t, y, f, p, bad, 0);
+#else
+  R::eval(t, y, f, p);
+#endif
+}
 
 }  // namespace odeb200

@@ -245,12 +245,24 @@ __global__ void __launch_bounds__(ENS_BLOCK, LITERAL ? 1 : adapt_min_blocks<Tab,
     // ---------------------------------------------------- stepsize_hw92! :401-442
     bool nanout = false, weird = false;
     unsigned int expo_or = 0u;  // fast pass: OR of the high words of every trial component and scaled error
+    // ODEB200_CTRL_NB: the D divisions of :433, the square root of :435 and 1/err of :436 as straight-line code with
+    // deferred acceptance checks (common.cuh div_nb / sqrt_nb): one rarely taken branch that redoes them with the
+    // compiler's own operations instead of a slow-path branch (and a basic-block boundary) per operation
+    constexpr bool CNB = !LITERAL && (ODEB200_CTRL_NB != 0);
+    bool cbad = false;
+    double ynum[CNB ? D : 1];
 #pragma unroll
     for (int d = 0; d < D; d++) {  // :430-434
       double ay = fabs(y[d]), at = fabs(ytrial[d]);
       if (LITERAL) {
         nanout = nanout || (ytrial[d] != ytrial[d]);  // isoutofdomain, src/ODE.jl:116
         yerr[d] = yerr[d] / (A.abstol + jl_max(ay, at) * A.reltol);  // :433
+      } else if (CNB) {
+        const bool ygt = (unsigned long long)__double_as_longlong(ay) > (unsigned long long)__double_as_longlong(at);
+        ynum[d] = yerr[d];
+        yerr[d] = div_nb(yerr[d], recip_prepare(A.abstol + (ygt ? ay : at) * A.reltol), cbad);
+        const unsigned int ht = (unsigned int)__double2hiint(ytrial[d]) & 0x7ff00000u;
+        expo_or = expo_or > ht ? expo_or : ht;
       } else {
         // max(|y|, |ytrial|) as an integer compare of the magnitudes' bit patterns (order-preserving for
         // non-NaN values; a NaN trial state sends the trajectory to the literal pass whatever is picked here)
@@ -261,6 +273,26 @@ __global__ void __launch_bounds__(ENS_BLOCK, LITERAL ? 1 : adapt_min_blocks<Tab,
         const unsigned int ht = (unsigned int)__double2hiint(ytrial[d]) & 0x7ff00000u;
         const unsigned int he = (unsigned int)__double2hiint(yerr[d]) & 0x7ff00000u;
         expo_or = expo_or > ht ? expo_or : ht;
+        expo_or = expo_or > he ? expo_or : he;
+      }
+    }
+    double inv_err = 0.0, err_nb = 0.0;
+    if (CNB) {
+      err_nb = norm2_nb<D>(yerr, cbad);
+      inv_err = div_nb(1.0, recip_prepare(err_nb), cbad);
+      if (cbad) {  // some check failed: the same operations the slow way (bit-identical whenever the checks pass)
+#pragma unroll
+        for (int d = 0; d < D; d++) {
+          const double ay = fabs(y[d]), at = fabs(ytrial[d]);
+          const bool ygt = (unsigned long long)__double_as_longlong(ay) > (unsigned long long)__double_as_longlong(at);
+          yerr[d] = ynum[d] / (A.abstol + (ygt ? ay : at) * A.reltol);
+        }
+        err_nb = norm2_small<D>(yerr);
+        inv_err = 1.0 / err_nb;
+      }
+#pragma unroll
+      for (int d = 0; d < D; d++) {
+        const unsigned int he = (unsigned int)__double2hiint(yerr[d]) & 0x7ff00000u;
         expo_or = expo_or > he ? expo_or : he;
       }
     }
@@ -277,10 +309,10 @@ __global__ void __launch_bounds__(ENS_BLOCK, LITERAL ? 1 : adapt_min_blocks<Tab,
       newdt = dt * 0.2;
       timeout = 5;
     } else {
-      err = norm2_small<D>(yerr);  // :435
+      err = CNB ? err_nb : norm2_small<D>(yerr);  // :435
       // :436  min(maxstep, tdir*dt*max(facmin, fac*(1/err)^(1/(order+1)))); tdir = +-1 is applied as a
       // sign (exact), min/max keep Julia's NaN propagation (maxstep, facmin and dt are never NaN here)
-      const double g = 0.8 * dm_pow(1.0 / err, EXPO);
+      const double g = 0.8 * dm_pow(CNB ? inv_err : 1.0 / err, EXPO);
       // max(facmin, g) with g >= +0 or NaN: unsigned compare of the bit patterns (NaN sorts above every number and is
       // propagated, like Julia's max), again off the FP64 pipe
       const double gmax = ((unsigned long long)__double_as_longlong(g) > 0x3FC999999999999AULL) ? g : 0.2;

@@ -106,11 +106,20 @@ struct LuReg {
 };
 
 // fdjacobian, src/ODE.jl:232-243 (recomputes F(t,x), D+1 RHS calls).
+// `known`: F(t, x) as the caller already holds it.  The reference evaluates F(t, x) again (:233), with exactly the
+// arguments of a call it has just made -- F0 = F(t0, y0) of hinit (:91) for the first Jacobian (:294), F2 =
+// F(t + h, ynew) (:320) for the one after an accepted step (:352) -- and a functor is a deterministic function of its
+// arguments, so the stored values are the recomputed ones bit for bit.  The RHS-call counter still counts D + 1.
 template <class Rhs, int D, int NPA, bool EXACT = true>
 __device__ __forceinline__ void fd_jacobian(double t, const double (&x)[D], const double (&p)[NPA], double (&J)[D][D],
-                                            bool& bad) {
+                                            bool& bad, const double* known = nullptr) {
   double ftx[D];
-  Rhs::eval(t, x, ftx, p);  // :233
+  if (ODEB200_S23_REUSE && known != nullptr) {
+#pragma unroll
+    for (int i = 0; i < D; i++) ftx[i] = known[i];
+  } else {
+    Rhs::eval(t, x, ftx, p);  // :233
+  }
   const Recip R100 = recip_prepare(100.0);
 #pragma unroll
   for (int j = 0; j < D; j++) {  // :236
@@ -133,18 +142,19 @@ __device__ __forceinline__ void fd_jacobian(double t, const double (&x)[D], cons
 // jac = jacobian(t, y): the registered analytic functor (JAC = 1) or fdjacobian (JAC = 0), :262-267
 template <class Rhs, int JAC, int D, int NPA, bool EXACT = true>
 __device__ __forceinline__ int eval_jacobian(double t, const double (&x)[D], const double (&p)[NPA], double (&J)[D][D],
-                                             bool& bad) {
+                                             bool& bad, const double* known = nullptr) {
   if (JAC) {
     Rhs::jac(t, x, J, p);
     return 0;
   }
-  fd_jacobian<Rhs, D, NPA, EXACT>(t, x, p, J, bad);
+  fd_jacobian<Rhs, D, NPA, EXACT>(t, x, p, J, bad, known);
   return D + 1;
 }
 template <class Rhs, int JAC, int D, int NPA>
-__device__ __forceinline__ int eval_jacobian(double t, const double (&x)[D], const double (&p)[NPA], double (&J)[D][D]) {
+__device__ __forceinline__ int eval_jacobian(double t, const double (&x)[D], const double (&p)[NPA], double (&J)[D][D],
+                                             const double* known = nullptr) {
   bool unused = false;
-  return eval_jacobian<Rhs, JAC, D, NPA, true>(t, x, p, J, unused);
+  return eval_jacobian<Rhs, JAC, D, NPA, true>(t, x, p, J, unused, known);
 }
 
 // hinit with p = 3 (src/ODE.jl:279-287): returns the first step (before the maxstep clip of :287), F0 and the RHS count
@@ -210,7 +220,7 @@ __global__ void __launch_bounds__(S23_BLOCK) ens_ode23s_init_kernel(const Ensemb
     int nrhs = 0;
     double h = hinit_ode23s<Rhs, D, NPA>(A, tstart, tfinal, tdir, y, p, F0, nrhs);
     h = tdir * jl_min(fabs(h), A.maxstep);  // :287
-    nrhs += eval_jacobian<Rhs, JAC, D, NPA>(tstart, y, p, Jt);  // :294
+    nrhs += eval_jacobian<Rhs, JAC, D, NPA>(tstart, y, p, Jt, F0);  // :294 (F(tstart, y) = F0)
     double* out = A.init + idx * W;
     out[0] = h;
 #pragma unroll
@@ -243,6 +253,8 @@ __global__ void __launch_bounds__(S23_BLOCK, (Rhs::DOF <= 3) ? ODEB200_S23_MINB 
   __shared__ double Jsh[JS ? D * D : 1][JS ? S23_BLOCK : 1];
   double Jreg[JS ? 1 : D][JS ? 1 : D];
   double t = 0.0, h = 0.0, last_tout = 0.0;
+  double ny = 0.0;  // norm(y), :324: y is the ynew of the last accepted step, whose norm that attempt already took
+  constexpr bool AUTO = ODEB200_S23_AUTO && RhsAutonomous<Rhs>::value;
   int nacc = 0, nrej = 0, nrhs = 0, npts = 0;
   long long attempts = 0, ntrace = 0;
 
@@ -274,8 +286,9 @@ __global__ void __launch_bounds__(S23_BLOCK, (Rhs::DOF <= 3) ? ODEB200_S23_MINB 
       } else {
         h = hinit_ode23s<Rhs, D, NPA>(A, tstart, tfinal, tdir, y, p, F0, nrhs);
         h = tdir * jl_min(fabs(h), A.maxstep);  // :287
-        nrhs += eval_jacobian<Rhs, JAC, D, NPA>(t, y, p, Jt);  // :294
+        nrhs += eval_jacobian<Rhs, JAC, D, NPA>(t, y, p, Jt, F0);  // :294 (F(tstart, y) = F0)
       }
+      if (ODEB200_S23_NORMY) ny = norm2_small<D>(y);
       if (MODE == 1) {  // tout = [t], yout = [y0] :290-291
         if (A.pts_cap > 0 && A.pts_y) {
           A.pts_t[idx * A.pts_cap] = tstart;
@@ -311,7 +324,7 @@ __global__ void __launch_bounds__(S23_BLOCK, (Rhs::DOF <= 3) ? ODEB200_S23_MINB 
       // the fast pass would have been accepted, so the two passes never disagree.  With ODEB200_S23_SPECJ the
       // Jacobian of the NEXT step, J(t + h, ynew) (:352), is part of the attempt and simply dropped on a rejection.
       double k1[D], k2[D], ynew[D], F2[D], Jn[D][D];
-      double err = 0.0, delta = 0.0;
+      double err = 0.0, delta = 0.0, nyn = 0.0;
       bool singular = false;
       int jac_rhs = 0;
       auto attempt = [&](auto EX, bool& bad) {
@@ -331,13 +344,31 @@ __global__ void __launch_bounds__(S23_BLOCK, (Rhs::DOF <= 3) ? ODEB200_S23_MINB 
         W.template factor_t<EXACT>(bad);
         singular = W.singular;
         if (EXACT && singular) return;
-        double Fa[D], T[D], k3[D], F1[D], tmp[D];
-        const Recip R100 = recip_prepare(100.0);
-        const double h100 = div_sel<EXACT>(h, R100, bad);
-        Rhs::eval(t + h100, y, Fa, p);  // :313
-        const Recip Rh100 = recip_prepare(h100);
+        double T[D], k3[D], F1[D], tmp[D];
+        if constexpr (AUTO && !EXACT) {
+          // :313 for a functor that ignores t: F(t + h/100, y) is F(., y) again, and F0 IS F(., y) -- from hinit or,
+          // after an accepted step, F2 = F(t + h, ynew) with y = ynew -- so F(t + h/100, y) - F0 = +0 exactly and
+          // T = (hd * +0) / (h/100) = +0 (hd and h/100 carry the sign of h), provided F0 is finite and h/100 does not
+          // underflow to zero; otherwise the attempt is repeated literally (EXACT).  The additions of +0 stay: they
+          // turn a -0 into +0 like the reference's.
+          unsigned int ex = 0u;
 #pragma unroll
-        for (int i = 0; i < D; i++) T[i] = div_sel<EXACT, true>(hd * (Fa[i] - F0[i]), Rh100, bad);
+          for (int i = 0; i < D; i++) {
+            const unsigned int e = (unsigned int)__double2hiint(F0[i]) & 0x7ff00000u;
+            ex = ex > e ? ex : e;
+          }
+          bad = bad || (ex == 0x7ff00000u) || (((unsigned int)__double2hiint(h) & 0x7ff00000u) < 0x01000000u);
+#pragma unroll
+          for (int i = 0; i < D; i++) T[i] = 0.0;
+        } else {
+          double Fa[D];
+          const Recip R100 = recip_prepare(100.0);
+          const double h100 = div_sel<EXACT>(h, R100, bad);
+          Rhs::eval(t + h100, y, Fa, p);  // :313
+          const Recip Rh100 = recip_prepare(h100);
+#pragma unroll
+          for (int i = 0; i < D; i++) T[i] = div_sel<EXACT, true>(hd * (Fa[i] - F0[i]), Rh100, bad);
+        }
 #pragma unroll
         for (int i = 0; i < D; i++) k1[i] = F0[i] + T[i];  // :316
         W.template solve_t<EXACT>(k1, bad);
@@ -356,11 +387,13 @@ __global__ void __launch_bounds__(S23_BLOCK, (Rhs::DOF <= 3) ? ODEB200_S23_MINB 
 #pragma unroll
         for (int i = 0; i < D; i++) k3[i] = ((F2[i] - e32 * (k2[i] - F1[i])) - 2 * (k1[i] - F0[i])) + T[i];  // :321
         W.template solve_t<EXACT>(k3, bad);
-        if (ODEB200_S23_SPECJ) jac_rhs = eval_jacobian<Rhs, JAC, D, NPA, EXACT>(t + h, ynew, p, Jn, bad);  // :352, ahead of time
+        if (ODEB200_S23_SPECJ) jac_rhs = eval_jacobian<Rhs, JAC, D, NPA, EXACT>(t + h, ynew, p, Jn, bad, F2);  // :352, ahead of time (F(t + h, ynew) = F2)
 #pragma unroll
         for (int i = 0; i < D; i++) tmp[i] = (k1[i] - 2 * k2[i]) + k3[i];
         err = div_sel<EXACT>(fabs(h), recip_prepare(6.0), bad) * norm2_sel<EXACT, D>(tmp, bad);  // :323
-        delta = jl_max(A.reltol * jl_max(norm2_sel<EXACT, D>(y, bad), norm2_sel<EXACT, D>(ynew, bad)), A.abstol);  // :324
+        nyn = norm2_sel<EXACT, D>(ynew, bad);
+        const double nyv = (ODEB200_S23_NORMY && !EXACT) ? ny : norm2_sel<EXACT, D>(y, bad);
+        delta = jl_max(A.reltol * jl_max(nyv, nyn), A.abstol);  // :324
       };
       bool bad = false;
       if (ODEB200_S23_DEFER) {
@@ -422,7 +455,8 @@ __global__ void __launch_bounds__(S23_BLOCK, (Rhs::DOF <= 3) ? ODEB200_S23_MINB 
             y[i] = ynew[i];  // :349
             F0[i] = F2[i];   // :351
           }
-          if (!ODEB200_S23_SPECJ) jac_rhs = eval_jacobian<Rhs, JAC, D, NPA>(t, y, p, Jn);  // :352
+          ny = nyn;
+          if (!ODEB200_S23_SPECJ) jac_rhs = eval_jacobian<Rhs, JAC, D, NPA>(t, y, p, Jn, F0);  // :352
           nrhs += jac_rhs;
 #pragma unroll
           for (int i = 0; i < D; i++) {

@@ -15,6 +15,7 @@ namespace odeb200 {
 // f(u,p,t) = a*u            README.md:19 (a = 1.01), test/runtests.jl:54 (a = 1)
 struct RhsLinear {
   static constexpr int DOF = 1, NP = 1, ID = ODE_B200_RHS_LINEAR;
+  static constexpr bool AUTONOMOUS = true;  // F does not read t
   __device__ __forceinline__ static void eval(double, const double (&y)[1], double (&f)[1], const double (&p)[1]) {
     f[0] = p[0] * y[0];
   }
@@ -25,6 +26,7 @@ struct RhsLinear {
 // (t,y) -> T(6)             test/runtests.jl:40
 struct RhsConst {
   static constexpr int DOF = 1, NP = 1, ID = ODE_B200_RHS_CONST;
+  static constexpr bool AUTONOMOUS = true;  // F does not read t
   __device__ __forceinline__ static void eval(double, const double (&)[1], double (&f)[1], const double (&p)[1]) {
     f[0] = p[0];
   }
@@ -45,6 +47,7 @@ struct RhsTimeLin {
 // (t,y) -> [-y[2]; y[1]]    test/runtests.jl:67
 struct RhsRotation {
   static constexpr int DOF = 2, NP = 0, ID = ODE_B200_RHS_ROTATION;
+  static constexpr bool AUTONOMOUS = true;  // F does not read t
   __device__ __forceinline__ static void eval(double, const double (&y)[2], double (&f)[2], const double (&)[1]) {
     f[0] = -y[1];
     f[1] = y[0];
@@ -59,6 +62,7 @@ struct RhsRotation {
 // Lorenz, examples/Lorenz_Attractor.ipynb cell 4: [s*(y-x); x*(r-z)-y; x*y-b*z]
 struct RhsLorenz {
   static constexpr int DOF = 3, NP = 3, ID = ODE_B200_RHS_LORENZ;
+  static constexpr bool AUTONOMOUS = true;  // F does not read t
   __device__ __forceinline__ static void eval(double, const double (&y)[3], double (&f)[3], const double (&p)[3]) {
     f[0] = p[0] * (y[1] - y[0]);
     f[1] = y[0] * (p[1] - y[2]) - y[1];
@@ -79,6 +83,7 @@ struct RhsLorenz {
 // Van der Pol: [y2; mu*((1-y1*y1)*y2) - y1]
 struct RhsVdp {
   static constexpr int DOF = 2, NP = 1, ID = ODE_B200_RHS_VDP;
+  static constexpr bool AUTONOMOUS = true;  // F does not read t
   __device__ __forceinline__ static void eval(double, const double (&y)[2], double (&f)[2], const double (&p)[1]) {
     f[0] = y[1];
     f[1] = p[0] * ((1.0 - y[0] * y[0]) * y[1]) - y[0];
@@ -93,6 +98,7 @@ struct RhsVdp {
 // Robertson, test/runtests.jl:81-87 (ydot[1], then ydot[3], then ydot[2] = -ydot[1]-ydot[3])
 struct RhsRobertson {
   static constexpr int DOF = 3, NP = 3, ID = ODE_B200_RHS_ROBERTSON;
+  static constexpr bool AUTONOMOUS = true;  // F does not read t
   __device__ __forceinline__ static void eval(double, const double (&y)[3], double (&f)[3], const double (&p)[3]) {
     double d1 = -p[0] * y[0] + p[2] * y[1] * y[2];
     double d3 = p[1] * y[1] * y[1];
@@ -116,6 +122,7 @@ struct RhsRobertson {
 // planar Kepler, mu = 1: r2 = x*x+y*y; r3 = r2*sqrt(r2); [vx, vy, -x/r3, -y/r3]
 struct RhsKepler {
   static constexpr int DOF = 4, NP = 0, ID = ODE_B200_RHS_KEPLER;
+  static constexpr bool AUTONOMOUS = true;  // F does not read t
   __device__ __forceinline__ static void eval(double, const double (&y)[4], double (&f)[4], const double (&)[1]) {
     double r2 = y[0] * y[0] + y[1] * y[1];
     double r3 = r2 * sqrt(r2);
@@ -163,6 +170,17 @@ struct RhsReactionDiffusion {
   __device__ __forceinline__ static double point(const double (&w)[3], const double (&p)[8], double, long long, long long) {
     return p[0] * ((w[0] - 2.0 * w[1]) + w[2]) + (p[1] * w[1]) * (1.0 - w[1]);
   }
+};
+
+// R::AUTONOMOUS (optional member): the functor ignores its time argument, so F(t1, y) and F(t2, y) are the same
+// bits; absent = false (run-time registered functors unless they declare it).
+template <class R, class = void>
+struct RhsAutonomous {
+  static constexpr bool value = false;
+};
+template <class R>
+struct RhsAutonomous<R, decltype((void)R::AUTONOMOUS)> {
+  static constexpr bool value = R::AUTONOMOUS;
 };
 
 template <class R>

@@ -71,7 +71,10 @@ typedef enum {
   ODE_B200_M_ODE_MS1 = 14, /* ode_ms(F, x0, tspan, 1): the first row of ms_coefficients4 (src/ODE.jl:180-181,440) */
   ODE_B200_M_ODE_MS2 = 15, /* ode_ms(F, x0, tspan, 2) */
   ODE_B200_M_ODE_MS3 = 16, /* ode_ms(F, x0, tspan, 3) */
-  ODE_B200_M_COUNT = 17
+  ODE_B200_M_CK45 = 17,    /* ode45_ck: Cash-Karp 4(5), order (5,4).  EXTENSION: README.md:57 names the coefficients, the
+                              reference source has no such tableau; literature coefficients, driver =
+                              oderk_adapt src/runge_kutta.jl:232-369 */
+  ODE_B200_M_COUNT = 18
 } ode_b200_method;
 /* order of an ode_ms method id (1..5), 0 for every other method */
 #define ODE_B200_MS_MAX_ORDER 5

@@ -40,7 +40,8 @@ const LIB = Ref{String}(get(ENV, "ODE_B200_LIB", joinpath(@__DIR__, "..", "ode.j
 const METHODS = Dict(:ode1=>0, :ode2_midpoint=>1, :ode2_heun=>2, :ode4=>3, :ode21=>4, :ode23=>5,
                      :ode45_fe=>6, :ode45_dp=>7, :ode45=>7, :ode78=>8, :ode23s=>9,
                      :ode4s=>10, :ode4s_s=>10, :ode4s_kr=>11, :ode4ms=>12, :ode5ms=>13,
-                     :ode_ms1=>14, :ode_ms2=>15, :ode_ms3=>16, :ode_ms4=>12, :ode_ms5=>13)
+                     :ode_ms1=>14, :ode_ms2=>15, :ode_ms3=>16, :ode_ms4=>12, :ode_ms5=>13,
+                     :ode45_ck=>17)  # ode45_ck: Cash-Karp, an extension (README.md:57; no tableau in the reference source)
 const RHS = Dict(:linear=>0, :const=>1, :timelin=>2, :rotation=>3, :lorenz=>4, :vdp=>5,
                  :robertson=>6, :kepler=>7, :reaction_diffusion=>8, :reaction_diffusion_field=>9)
 const POINTS = Dict(:all=>0, :specified=>1, :final=>2)
@@ -146,7 +147,7 @@ function _solve(method::Symbol, F::Union{DeviceRHS,UserRHS}, y0, tspan;
     return tout, yout
 end
 
-for name in (:ode1, :ode2_midpoint, :ode2_heun, :ode4, :ode21, :ode23, :ode45_fe, :ode45_dp, :ode45, :ode78, :ode23s,
+for name in (:ode1, :ode2_midpoint, :ode2_heun, :ode4, :ode21, :ode23, :ode45_fe, :ode45_dp, :ode45, :ode45_ck, :ode78, :ode23s,
              :ode4s, :ode4s_s, :ode4s_kr, :ode4ms, :ode5ms)
     # the solver name is a type (its instance is the algorithm marker, src/algorithm_types.jl); calling the type with
     # (F, y0, tspan) is the solver function, exactly the reference's `AlgType(f, u0, Ts; ...)` at src/common.jl:93

@@ -14,7 +14,7 @@ LIB_PATH = os.environ.get("ODE_B200_LIB") or os.path.join(_HERE, "libode_b200.so
 # include/ode_b200.h enums
 METHODS = dict(ode1=0, ode2_midpoint=1, ode2_heun=2, ode4=3, ode21=4, ode23=5, ode45_fe=6, ode45_dp=7, ode45=7,
                ode78=8, ode23s=9, ode4s=10, ode4s_s=10, ode4s_kr=11, ode4ms=12, ode5ms=13, ode_ms1=14, ode_ms2=15,
-               ode_ms3=16, ode_ms4=12, ode_ms5=13)
+               ode_ms3=16, ode_ms4=12, ode_ms5=13, ode45_ck=17)
 RHS = dict(linear=0, const=1, timelin=2, rotation=3, lorenz=4, vdp=5, robertson=6, kepler=7, reaction_diffusion=8,
            reaction_diffusion_field=9)
 POINTS = {"all": 0, "specified": 1, "final": 2}

@@ -163,6 +163,9 @@ ode45_fe = Solver("ode45_fe")
 ode45_dp = Solver("ode45_dp")
 ode45 = Solver("ode45")  # Dormand-Prince by default, src/runge_kutta.jl:223
 ode78 = Solver("ode78")
+# EXTENSION: Cash-Karp 4(5).  README.md:57 of the reference says the coefficients "are also available"; its source has
+# no such tableau, so this one carries the published coefficients (Cash & Karp 1990) in bt_dopri5's layout, order (5,4).
+ode45_ck = Solver("ode45_ck")
 ode23s = Solver("ode23s")
 ode4s_s = Solver("ode4s_s")    # Shampine coefficients, src/ODE.jl:433
 ode4s_kr = Solver("ode4s_kr")  # Kaps-Rentrop coefficients, src/ODE.jl:419

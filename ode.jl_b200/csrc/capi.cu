@@ -159,7 +159,8 @@ static const NameId kMethods[] = {
     {"feh78", ODE_B200_M_FEH78},       {"ode23s", ODE_B200_M_ODE23S},     {"ode4s", ODE_B200_M_ODE4S_S},
     {"ode4s_s", ODE_B200_M_ODE4S_S},   {"ode4s_kr", ODE_B200_M_ODE4S_KR}, {"ode4ms", ODE_B200_M_ODE4MS},
     {"ode5ms", ODE_B200_M_ODE5MS},     {"ode_ms1", ODE_B200_M_ODE_MS1},   {"ode_ms2", ODE_B200_M_ODE_MS2},
-    {"ode_ms3", ODE_B200_M_ODE_MS3},   {"ode_ms4", ODE_B200_M_ODE4MS},    {"ode_ms5", ODE_B200_M_ODE5MS}};
+    {"ode_ms3", ODE_B200_M_ODE_MS3},   {"ode_ms4", ODE_B200_M_ODE4MS},    {"ode_ms5", ODE_B200_M_ODE5MS},
+    {"ode45_ck", ODE_B200_M_CK45},     {"ck45", ODE_B200_M_CK45}};
 static const NameId kRhs[] = {{"linear", ODE_B200_RHS_LINEAR},
                               {"const", ODE_B200_RHS_CONST},
                               {"timelin", ODE_B200_RHS_TIMELIN},
@@ -192,6 +193,7 @@ static double tab_get(int which, int i, int j) {
     case ODE_B200_M_RK45_FE: X(TabRK45);          \
     case ODE_B200_M_DOPRI5: X(TabDopri5);         \
     case ODE_B200_M_FEH78: X(TabFeh78);           \
+    case ODE_B200_M_CK45: X(TabCK45);             \
     default: break;                               \
   }
 
@@ -311,7 +313,7 @@ static int validate(const ode_b200_opts* o, const ode_b200_ensemble_io* io, doub
   return 0;
 }
 
-static bool is_adaptive_rk(int method) { return method >= ODE_B200_M_RK21 && method <= ODE_B200_M_FEH78; }
+static bool is_adaptive_rk(int method) { return method_is_adaptive_rk(method); }
 // the opt-in FMA build (inst_dopri5_fma.cu): Dormand-Prince, built-in right-hand sides
 extern "C" const void* odeb200_fma_dopri5_kernel(int rhs, int mode, int literal);
 extern "C" const void* odeb200_fma_dopri5_init_kernel(int rhs);
@@ -340,6 +342,7 @@ static EnsembleKernel pick_kernel_fn(const ode_b200_opts* o, int mode, int liter
     case ODE_B200_M_RK45_FE: return adapt_kernel_rk45(o->rhs, mode, literal);
     case ODE_B200_M_DOPRI5: return adapt_kernel_dopri5(o->rhs, mode, literal);
     case ODE_B200_M_FEH78: return adapt_kernel_feh78(o->rhs, mode, literal);
+    case ODE_B200_M_CK45: return adapt_kernel_ck45(o->rhs, mode, literal);
     case ODE_B200_M_ODE23S: return ode23s_kernel(o->rhs, mode, o->jacobian);
     case ODE_B200_M_ODE4S_S:
     case ODE_B200_M_ODE4S_KR: return rosenbrock_kernel(o->method, o->rhs, o->jacobian);
@@ -359,6 +362,7 @@ static const void* pick_init_kernel(const ode_b200_opts* o) {
     case ODE_B200_M_RK45_FE: return (const void*)adapt_kernel_rk45_init(o->rhs);
     case ODE_B200_M_DOPRI5: return (const void*)adapt_kernel_dopri5_init(o->rhs);
     case ODE_B200_M_FEH78: return (const void*)adapt_kernel_feh78_init(o->rhs);
+    case ODE_B200_M_CK45: return (const void*)adapt_kernel_ck45_init(o->rhs);
     case ODE_B200_M_ODE23S: return (const void*)ode23s_init_kernel(o->rhs, o->jacobian);
     default: return nullptr;
   }

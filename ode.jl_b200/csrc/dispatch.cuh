@@ -13,11 +13,13 @@ EnsembleKernel adapt_kernel_rk23(int rhs, int mode, int literal);
 EnsembleKernel adapt_kernel_rk45(int rhs, int mode, int literal);
 EnsembleKernel adapt_kernel_dopri5(int rhs, int mode, int literal);
 EnsembleKernel adapt_kernel_feh78(int rhs, int mode, int literal);
+EnsembleKernel adapt_kernel_ck45(int rhs, int mode, int literal);
 EnsembleKernel adapt_kernel_rk21_init(int rhs);  // hinit pre-pass (ens_adapt_init_kernel)
 EnsembleKernel adapt_kernel_rk23_init(int rhs);  // hinit pre-pass (ens_adapt_init_kernel)
 EnsembleKernel adapt_kernel_rk45_init(int rhs);  // hinit pre-pass (ens_adapt_init_kernel)
 EnsembleKernel adapt_kernel_dopri5_init(int rhs);  // hinit pre-pass (ens_adapt_init_kernel)
 EnsembleKernel adapt_kernel_feh78_init(int rhs);  // hinit pre-pass (ens_adapt_init_kernel)
+EnsembleKernel adapt_kernel_ck45_init(int rhs);   // hinit pre-pass (ens_adapt_init_kernel)
 EnsembleKernel fixed_kernel(int method, int rhs);
 EnsembleKernel ode23s_kernel(int rhs, int mode, int jac);  // jac: 0 fdjacobian, 1 analytic functor
 EnsembleKernel ode23s_init_kernel(int rhs, int jac);       // pre-pass: first step, F0, first Jacobian

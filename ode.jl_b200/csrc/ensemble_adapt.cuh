@@ -119,6 +119,15 @@ constexpr int adapt_min_blocks() {
   return (Rhs::DOF <= 3 && Rhs::DOF * Tab::S <= 21) ? (5 * 128) / ENS_BLOCK : ODEB200_WIDE_MINB;  // 640 resident threads per SM; 0 = leave it to ptxas
 }
 
+// Which (tableau, functor) pairs take the deferred-check controller (ODEB200_CTRL_NB = 2), from measurement
+// (profiles/ensemble_kernels_r2.md, 2^18 trajectories): Lorenz/dopri5 3.31 -> 3.03 ms, Kepler/feh78 18.22 -> 17.56 ms,
+// but Lorenz/feh78 2.08 -> 2.14 ms and Van der Pol/dopri5 1.73 -> 1.79 ms: it pays where there are at least three
+// divisions to straighten and the stage loop leaves registers for the kept numerators.
+template <class Tab, class Rhs>
+__host__ __device__ constexpr bool ctrl_nb_policy() {
+  return Rhs::DOF >= 3 && (Tab::S <= 7 || Rhs::DOF >= 4);
+}
+
 template <class Tab, class Rhs, int MODE, bool LITERAL, bool PU = false>
 __global__ void __launch_bounds__(ENS_BLOCK, LITERAL ? 1 : adapt_min_blocks<Tab, Rhs>() + (PU ? ODEB200_PU_EXTRA : 0))
     ens_adapt_kernel(const __grid_constant__ EnsembleArgs A) {
@@ -248,7 +257,7 @@ __global__ void __launch_bounds__(ENS_BLOCK, LITERAL ? 1 : adapt_min_blocks<Tab,
     // ODEB200_CTRL_NB: the D divisions of :433, the square root of :435 and 1/err of :436 as straight-line code with
     // deferred acceptance checks (common.cuh div_nb / sqrt_nb): one rarely taken branch that redoes them with the
     // compiler's own operations instead of a slow-path branch (and a basic-block boundary) per operation
-    constexpr bool CNB = !LITERAL && (ODEB200_CTRL_NB != 0);
+    constexpr bool CNB = !LITERAL && (ODEB200_CTRL_NB == 1 || (ODEB200_CTRL_NB == 2 && ctrl_nb_policy<Tab, Rhs>()));
     bool cbad = false;
     double ynum[CNB ? D : 1];
 #pragma unroll

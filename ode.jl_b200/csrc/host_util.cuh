@@ -7,6 +7,8 @@ int set_err(int code, const char* fmt, ...);  // fills the thread-local last_err
 void note_launch();                           // counts kernel launches (ode_b200_launch_count)
 int ms_order(int method);                     // order of ode_ms for a method id, 0 if it is not a multistep method
 double ms_coefficient(int order, int j);      // b[order][j] of ode_ms, j 0-based (capi.cu)
+// the embedded (adaptive) explicit RK tableaus: the reference's five (ids 4..8) and the Cash-Karp extension
+inline bool method_is_adaptive_rk(int method) { return (method >= 4 && method <= 8) || method == 17; }
 }  // namespace odeb200
 
 #define ODEB200_CUDA(call)                                                                              \

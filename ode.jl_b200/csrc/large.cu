@@ -220,6 +220,7 @@ static bool pick_field_method(int method, MethodInfo* out) {
     case ODE_B200_M_RK45_FE: *out = field_method_info<TabRK45>(); return true;
     case ODE_B200_M_DOPRI5: *out = field_method_info<TabDopri5>(); return true;
     case ODE_B200_M_FEH78: *out = field_method_info<TabFeh78>(); return true;
+    case ODE_B200_M_CK45: *out = field_method_info<TabCK45>(); return true;
     default: return false;
   }
 }
@@ -230,6 +231,7 @@ static bool pick_method(int method, int radius, MethodInfo* out) {
     case ODE_B200_M_RK45_FE: *out = method_info<TabRK45>(radius); return true;
     case ODE_B200_M_DOPRI5: *out = method_info<TabDopri5>(radius); return true;
     case ODE_B200_M_FEH78: *out = method_info<TabFeh78>(radius); return true;
+    case ODE_B200_M_CK45: *out = method_info<TabCK45>(radius); return true;
     default: return false;
   }
 }

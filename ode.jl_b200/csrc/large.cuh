@@ -631,17 +631,22 @@ __global__ void __launch_bounds__(LARGE_THREADS) large_attempt_kernel(
   long long tile = blockIdx.x;
 #if ODEB200_LARGE_BULK
   // the next tile's y, k1 rows are staged in shared memory by the copy engine (the arrays are padded by one tile, so a
-  // whole row can always be read; what lies beyond the slab is zero, like load_chunk's fill)
+  // whole row can always be read; what lies beyond the slab is zero, like load_chunk's fill).  Two slots, one mbarrier
+  // each: the slot refilled while tile i is computed is the one tile i-1 was read from.
   constexpr int WT = T * P;
-  __shared__ __align__(128) double tY[WT], tK[WT];
-  __shared__ unsigned long long tbar;
-  unsigned int tphase = 0;
-  if (tid == 0) mbar_init(&tbar, 1);
+  __shared__ __align__(128) double tY[2][WT], tK[2][WT];
+  __shared__ unsigned long long tbar[2];
+  unsigned int tphase = 0;  // bit b = parity to wait for on slot b
+  int tslot = 0;
+  if (tid == 0) {
+    mbar_init(&tbar[0], 1);
+    mbar_init(&tbar[1], 1);
+  }
   __syncthreads();
   if (tid == 0 && tile < A.tiles) {
-    mbar_expect_tx(&tbar, 2u * WT * 8u);
-    bulk_copy_g2s(tY, yA + tile * VAL, WT * 8u, &tbar);
-    bulk_copy_g2s(tK, kA + tile * VAL, WT * 8u, &tbar);
+    mbar_expect_tx(&tbar[0], 2u * WT * 8u);
+    bulk_copy_g2s(tY[0], yA + tile * VAL, WT * 8u, &tbar[0]);
+    bulk_copy_g2s(tK[0], kA + tile * VAL, WT * 8u, &tbar[0]);
   }
 #else
   // software prefetch: the next tile's y, k1 are requested before the current tile is computed
@@ -659,23 +664,25 @@ __global__ void __launch_bounds__(LARGE_THREADS) large_attempt_kernel(
     double y[P], k1[P];
     const long long nxt = tile + gridDim.x;
 #if ODEB200_LARGE_BULK
-    mbar_wait(&tbar, tphase);
-    tphase ^= 1u;
+    if (tid == 0 && nxt < A.tiles) {  // the other slot was last read one tile ago (a whole attempt of barriers back)
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+      const int o = tslot ^ 1;
+      mbar_expect_tx(&tbar[o], 2u * WT * 8u);
+      bulk_copy_g2s(tY[o], yA + nxt * VAL, WT * 8u, &tbar[o]);
+      bulk_copy_g2s(tK[o], kA + nxt * VAL, WT * 8u, &tbar[o]);
+    }
+    mbar_wait(&tbar[tslot], (tphase >> tslot) & 1u);
+    tphase ^= 1u << tslot;
 #pragma unroll
     for (int c = 0; c < P / 2; c++) {
-      const double2 a = *reinterpret_cast<const double2*>(tY + off0 + 2 * c);
-      const double2 b = *reinterpret_cast<const double2*>(tK + off0 + 2 * c);
+      const double2 a = *reinterpret_cast<const double2*>(&tY[tslot][off0 + 2 * c]);
+      const double2 b = *reinterpret_cast<const double2*>(&tK[tslot][off0 + 2 * c]);
       y[2 * c] = a.x;
       y[2 * c + 1] = a.y;
       k1[2 * c] = b.x;
       k1[2 * c + 1] = b.y;
     }
-    __syncthreads();  // every thread has its points: the rows can be overwritten
-    if (tid == 0 && nxt < A.tiles) {
-      mbar_expect_tx(&tbar, 2u * WT * 8u);
-      bulk_copy_g2s(tY, yA + nxt * VAL, WT * 8u, &tbar);
-      bulk_copy_g2s(tK, kA + nxt * VAL, WT * 8u, &tbar);
-    }
+    tslot ^= 1;
 #else
 #pragma unroll
     for (int p = 0; p < P; p++) {

@@ -113,6 +113,7 @@ static const char* tab_name(int method) {
     case ODE_B200_M_RK45_FE: return "odeb200::TabRK45";
     case ODE_B200_M_DOPRI5: return "odeb200::TabDopri5";
     case ODE_B200_M_FEH78: return "odeb200::TabFeh78";
+    case ODE_B200_M_CK45: return "odeb200::TabCK45";
     default: return nullptr;
   }
 }
@@ -180,7 +181,7 @@ const void* user_kernel(int rhs, int method, int mode, int literal, int jac) {
   }
   char expr[512], expr_init[256] = "";
   const char* header = "ensemble_adapt.cuh";
-  if (method >= ODE_B200_M_RK21 && method <= ODE_B200_M_FEH78) {
+  if (method_is_adaptive_rk(method)) {
     snprintf(expr, sizeof(expr), "odeb200::ens_adapt_kernel<%s, odeb200::RhsUser, %d, %s%s>", tab_name(method), mode ? 1 : 0,
              literal == 1 ? "true" : "false", literal == 2 ? ", true" : "");  // 2: uniform-parameter fast kernel
     if (!mode && !literal)  // the hinit pre-pass travels with the mode-0 fast kernel
@@ -238,7 +239,7 @@ const void* user_kernel(int rhs, int method, int mode, int literal, int jac) {
 
 // hinit pre-pass kernel that was compiled together with the mode-0 fast kernel of (rhs, method); nullptr if none.
 const void* user_init_kernel(int rhs, int method) {
-  if (method < ODE_B200_M_RK21 || method > ODE_B200_M_FEH78) return nullptr;
+  if (!method_is_adaptive_rk(method)) return nullptr;
   if (!user_kernel(rhs, method, 0, 0, 0)) return nullptr;
   int dev = 0;
   cudaGetDevice(&dev);
@@ -262,7 +263,7 @@ bool user_stencil_kernels(int rhs, int method, const void** attempt, const void*
     u = g_stencils[i];
   }
   const char* tab = tab_name(method);
-  if (!tab || method < ODE_B200_M_RK21 || method > ODE_B200_M_FEH78) {
+  if (!tab || !method_is_adaptive_rk(method)) {
     set_err(ODE_B200_E_NOT_ADAPTIVE, "Can only use this solver with an adaptive RK Butcher table");
     return false;
   }
@@ -337,7 +338,7 @@ bool user_field_kernels(int rhs, int method, int n_stages, const void** out) {
     u = g_fields[i];
   }
   const char* tab = tab_name(method);
-  if (!tab || method < ODE_B200_M_RK21 || method > ODE_B200_M_FEH78) {
+  if (!tab || !method_is_adaptive_rk(method)) {
     set_err(ODE_B200_E_NOT_ADAPTIVE, "Can only use this solver with an adaptive RK Butcher table");
     return false;
   }

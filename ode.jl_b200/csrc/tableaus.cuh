@@ -88,6 +88,23 @@ struct TabRK45 : TabOps<TabRK45> {  // bt_rk45 (Fehlberg) :112, order (4,5)
                                   {{16, 135}, ODEB200_Z, {6656, 12825}, {28561, 56430}, {-9, 50}, {2, 55}}};
   static constexpr Rat C[6] = {ODEB200_Z, {1, 4}, {3, 8}, {12, 13}, {1, 1}, {1, 2}};
 };
+// Cash-Karp 4(5).  The reference's README (README.md:57) says "Fehlberg and Cash-Karp coefficients are also available"
+// for ode45, but src/runge_kutta.jl defines no such tableau: this one is an EXTENSION with the
+// coefficients of Cash & Karp, ACM TOMS 16 (1990) 201-222, laid out like bt_dopri5 -- order (5,4), the solver advances
+// with the 5th-order row b[1,:] and the controller exponent is 1/(min(order)+1) = 1/5.  Not FSAL (c[end] = 7/8).
+struct TabCK45 : TabOps<TabCK45> {
+  static constexpr int S = 6, NB = 2, ORDER = 4;
+  static constexpr Rat A[6][6] = {
+      {ODEB200_Z, ODEB200_Z, ODEB200_Z, ODEB200_Z, ODEB200_Z, ODEB200_Z},
+      {{1, 5}, ODEB200_Z, ODEB200_Z, ODEB200_Z, ODEB200_Z, ODEB200_Z},
+      {{3, 40}, {9, 40}, ODEB200_Z, ODEB200_Z, ODEB200_Z, ODEB200_Z},
+      {{3, 10}, {-9, 10}, {6, 5}, ODEB200_Z, ODEB200_Z, ODEB200_Z},
+      {{-11, 54}, {5, 2}, {-70, 27}, {35, 27}, ODEB200_Z, ODEB200_Z},
+      {{1631, 55296}, {175, 512}, {575, 13824}, {44275, 110592}, {253, 4096}, ODEB200_Z}};
+  static constexpr Rat B[2][6] = {{{37, 378}, ODEB200_Z, {250, 621}, {125, 594}, ODEB200_Z, {512, 1771}},
+                                  {{2825, 27648}, ODEB200_Z, {18575, 48384}, {13525, 55296}, {277, 14336}, {1, 4}}};
+  static constexpr Rat C[6] = {ODEB200_Z, {1, 5}, {3, 10}, {3, 5}, {1, 1}, {7, 8}};
+};
 struct TabDopri5 : TabOps<TabDopri5> {  // bt_dopri5 :124, order (5,4)
   static constexpr int S = 7, NB = 2, ORDER = 4;
   static constexpr Rat A[7][7] = {

@@ -239,6 +239,18 @@ Tab make_tab(int method) {
       static const Q c[] = {Z, {2, 27}, {1, 9}, {1, 6}, {5, 12}, {1, 2}, {5, 6}, {1, 6}, {2, 3}, {1, 3}, {1, 1}, Z, {1, 1}};
       fill(13, 2, 7, 8, a, b, c);
     } break;
+    case ODE_B200_M_CK45: {  // EXTENSION (not in the reference source; README.md:57 names it): Cash & Karp 1990, order (5,4)
+      static const Q a[] = {Z, Z, Z, Z, Z, Z,
+                            {1, 5}, Z, Z, Z, Z, Z,
+                            {3, 40}, {9, 40}, Z, Z, Z, Z,
+                            {3, 10}, {-9, 10}, {6, 5}, Z, Z, Z,
+                            {-11, 54}, {5, 2}, {-70, 27}, {35, 27}, Z, Z,
+                            {1631, 55296}, {175, 512}, {575, 13824}, {44275, 110592}, {253, 4096}, Z};
+      static const Q b[] = {{37, 378}, Z, {250, 621}, {125, 594}, Z, {512, 1771},
+                            {2825, 27648}, Z, {18575, 48384}, {13525, 55296}, {277, 14336}, {1, 4}};
+      static const Q c[] = {Z, {1, 5}, {3, 10}, {3, 5}, {1, 1}, {7, 8}};
+      fill(6, 2, 5, 4, a, b, c);
+    } break;
     default:
       break;
   }

@@ -146,6 +146,18 @@ TABLEAUS = {
                      Fr(1, 3), Fr(1), Fr(0), Fr(1)]),
 }
 TABLEAUS["ode45_dp"] = TABLEAUS["ode45"]
+# EXTENSION, not in the reference source (README.md:57 names it): Cash & Karp, ACM TOMS 16 (1990); order (5,4) like
+# bt_dopri5 -- the solver advances with the 5th-order row
+TABLEAUS["ode45_ck"] = dict(order=(5, 4), a=_parse("""
+        0 0 0 0 0 0
+        1/5 0 0 0 0 0
+        3/40 9/40 0 0 0 0
+        3/10 -9/10 6/5 0 0 0
+        -11/54 5/2 -70/27 35/27 0 0
+        1631/55296 175/512 575/13824 44275/110592 253/4096 0"""),
+                            b=_parse("37/378 0 250/621 125/594 0 512/1771\n"
+                                     "2825/27648 0 18575/48384 13525/55296 277/14336 1/4"),
+                            c=[Fr(0), Fr(1, 5), Fr(3, 10), Fr(3, 5), Fr(1), Fr(7, 8)])
 
 
 def _f(fr):

@@ -17,7 +17,7 @@ _SO = os.path.join(_HERE, "libode_oracle.so")
 METHODS = dict(ode1=0, feuler=0, ode2_midpoint=1, midpoint=1, ode2_heun=2, heun=2, ode4=3, rk4=3,
                ode21=4, rk21=4, ode23=5, rk23=5, ode45_fe=6, rk45=6, ode45=7, ode45_dp=7, dopri5=7,
                ode78=8, feh78=8, ode23s=9, ode4s=10, ode4s_s=10, ode4s_kr=11, ode4ms=12, ode5ms=13, ode_ms1=14,
-               ode_ms2=15, ode_ms3=16, ode_ms4=12, ode_ms5=13)
+               ode_ms2=15, ode_ms3=16, ode_ms4=12, ode_ms5=13, ode45_ck=17, ck45=17)
 RHS = dict(linear=0, const=1, timelin=2, rotation=3, lorenz=4, vdp=5, robertson=6, kepler=7,
            reaction_diffusion=8)
 POINTS = dict(all=0, specified=1, final=2)

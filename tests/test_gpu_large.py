@@ -34,7 +34,7 @@ def test_reaction_diffusion_dopri5_bit_exact(n):
     assert np.array_equal(got["y"], ref.y[-1])
 
 
-@pytest.mark.parametrize("method", ["ode21", "ode23", "ode45_fe", "ode45", "ode78"])
+@pytest.mark.parametrize("method", ["ode21", "ode23", "ode45_fe", "ode45", "ode78", "ode45_ck"])
 def test_all_tableaus_large_bit_exact(method):
     n = 3000
     y0 = u0(n) + 0.05 * np.cos(2 * np.pi * 3 * np.arange(n) / n)
@@ -311,7 +311,7 @@ def test_large_points_all_through_the_front_end(method):
 
 
 # ---- general gather right-hand sides ("fields"): one kernel per stage (csrc/field.cuh) -------------------------
-@pytest.mark.parametrize("method", ["ode21", "ode23", "ode45_fe", "ode45", "ode78"])
+@pytest.mark.parametrize("method", ["ode21", "ode23", "ode45_fe", "ode45", "ode78", "ode45_ck"])
 def test_field_path_equals_fused_stencil_path_and_oracle(method):
     """The built-in reaction_diffusion_field is the reaction-diffusion system written as a gather over the global
     state: the stage-per-kernel path must give the fused kernel's bits, and the oracle's."""

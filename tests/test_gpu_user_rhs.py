@@ -55,7 +55,7 @@ def user_bruss():
     return m.register_rhs("brusselator", 2, 2, BRUSS_SRC, BRUSS_JAC, host=bruss, params=(1.0, 3.0))
 
 
-@pytest.mark.parametrize("method", ["ode21", "ode23", "ode45_fe", "ode45", "ode78", "ode23s", "ode4", "ode1",
+@pytest.mark.parametrize("method", ["ode21", "ode23", "ode45_fe", "ode45", "ode78", "ode45_ck", "ode23s", "ode4", "ode1",
                                     "ode4s_s", "ode4s_kr", "ode4ms"])
 def test_user_rhs_equals_builtin_functor(method, user_lorenz):
     rng = np.random.default_rng(3)

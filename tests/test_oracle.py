@@ -21,7 +21,7 @@ from oracle import ode_oracle as P
 GOLD = os.path.join(os.path.dirname(__file__), "golden")
 NAME2GOLD = dict(ode1="bt_feuler", ode2_midpoint="bt_midpoint", ode2_heun="bt_heun", ode4="bt_rk4", ode21="bt_rk21",
                  ode23="bt_rk23", ode45_fe="bt_rk45", ode45="bt_dopri5", ode78="bt_feh78")
-ADAPTIVE = ["ode21", "ode23", "ode45_fe", "ode45", "ode78"]
+ADAPTIVE = ["ode21", "ode23", "ode45_fe", "ode45", "ode78", "ode45_ck"]  # ode45_ck: the Cash-Karp extension
 FIXED = ["ode1", "ode2_midpoint", "ode2_heun", "ode4"]
 LORENZ = [10.0, 28.0, 8.0 / 3.0]
 
@@ -50,6 +50,40 @@ def test_tableau_matches_reference_source(name):
     pt = P.Tab(name)
     assert pt.a == t["a"].tolist() and pt.b == t["b"].tolist() and pt.c == t["c"].tolist()
     assert pt.fsal == t["fsal"]
+
+
+def test_cash_karp_extension_satisfies_its_order_conditions():
+    """ode45_ck is not in the reference source (README.md:57 only names it): its pin is the published tableau itself.
+    Exact rationals: row sums = c, all 17 order conditions up to order 5 for the advancing row b[1,:], all 8 up to
+    order 4 for the embedded row b[2,:] (and the embedded row is NOT of order 5), not FSAL, min(order) = 4."""
+    d = P.TABLEAUS["ode45_ck"]
+    a, c = d["a"], d["c"]
+    S = len(c)
+    for i in range(S):
+        assert sum(a[i]) == c[i]
+    mv = lambda v: [sum(a[i][j] * v[j] for j in range(S)) for i in range(S)]  # noqa: E731
+    had = lambda u, v: [x * y for x, y in zip(u, v)]  # noqa: E731
+    one = [Fraction(1)] * S
+    c2, c3, c4 = had(c, c), had(had(c, c), c), had(had(c, c), had(c, c))
+    ac, ac2, ac3 = mv(c), mv(c2), mv(c3)
+    aac, aac2, aaac = mv(ac), mv(ac2), mv(mv(ac))
+    conds = [(one, 1, 1), (c, 2, 2), (c2, 3, 3), (ac, 6, 3), (c3, 4, 4), (had(c, ac), 8, 4), (ac2, 12, 4), (aac, 24, 4),
+             (c4, 5, 5), (had(c2, ac), 10, 5), (had(c, ac2), 15, 5), (had(c, aac), 30, 5), (had(ac, ac), 20, 5),
+             (ac3, 20, 5), (mv(had(c, ac)), 40, 5), (aac2, 60, 5), (aaac, 120, 5)]
+    dot = lambda b, v: sum(x * y for x, y in zip(b, v))  # noqa: E731
+    for v, den, order in conds:
+        assert dot(d["b"][0], v) == Fraction(1, den)
+        if order <= 4:
+            assert dot(d["b"][1], v) == Fraction(1, den)
+    assert any(dot(d["b"][1], v) != Fraction(1, den) for v, den, order in conds if order == 5)
+    t = O.tableau("ode45_ck")
+    assert (t["S"], t["order"], t["fsal"], t["adaptive"]) == (6, 4, False, True)
+    pt = P.Tab("ode45_ck")
+    assert pt.a == t["a"].tolist() and pt.b == t["b"].tolist() and pt.c == t["c"].tolist()
+    # and it converges at the expected rate on y' = y: halving the tolerance-independent fixed grid is not available
+    # for the adaptive driver, so compare with the exact solution at a tight tolerance instead
+    s = O.solve("ode45_ck", "linear", [1.0], [0.0, 1.0], [1.0], reltol=1e-10, abstol=1e-10)
+    assert abs(s.y[-1, 0] - math.e) < 1e-9
 
 
 ALL_SOLVERS = FIXED + ["ode4ms", "ode5ms"] + ADAPTIVE + ["ode4s_s", "ode4s_kr", "ode23s"]  # test/runtests.jl:5-25

@@ -374,8 +374,11 @@ static size_t init_width(const ode_b200_opts* o) {
 
 // ---- dispatch order: counting sort of the trajectories by the first step size (common.cuh, sched_key) -----------
 // scratch words: [0] min key, [1] max key (finite keys), [2 .. 2+BINS) histogram / running offsets
-__global__ void __launch_bounds__(256) sched_range_kernel(const double* init, int width, long long n, unsigned int* w) {
+// (n_dev, when given, is the element count as a device-side word: the tail hand-off's record counter)
+__global__ void __launch_bounds__(256) sched_range_kernel(const double* init, int width, long long n, unsigned int* w,
+                                                          const unsigned int* n_dev = nullptr) {
   __shared__ unsigned int smin[8], smax[8];
+  if (n_dev) n = (long long)*n_dev;
   unsigned int lo = 0xffffffffu, hi = 0u;
   for (long long i = blockIdx.x * 256LL + threadIdx.x; i < n; i += (long long)gridDim.x * 256) {
     const unsigned int k = sched_key(init[i * width]);
@@ -406,8 +409,9 @@ __global__ void __launch_bounds__(256) sched_range_kernel(const double* init, in
 }
 // pass = 0: histogram; pass = 1: scatter.  Each block works on a contiguous chunk through a shared-memory histogram.
 __global__ void __launch_bounds__(256) sched_bin_kernel(const double* init, int width, long long n, unsigned int* w, int* order,
-                                                        int pass) {
+                                                        int pass, const unsigned int* n_dev = nullptr) {
   __shared__ unsigned int cnt[SCHED_BINS], base[SCHED_BINS];
+  if (n_dev) n = (long long)*n_dev;
   const unsigned int lo = w[0], hi = w[1];
   unsigned int* hist = w + 2;
   const long long per = (n + gridDim.x - 1) / gridDim.x, i0 = blockIdx.x * per, i1 = (i0 + per < n) ? i0 + per : n;
@@ -457,6 +461,28 @@ static size_t order_scratch_bytes(const ode_b200_opts* o, const ode_b200_ensembl
   }
   return pad256((size_t)io->n_traj * sizeof(int)) + pad256((size_t)(SCHED_BINS + 2) * sizeof(unsigned int));
 }
+// Tail hand-off of the adaptive RK fast kernels (ensemble_adapt.cuh): scratch for one record per resident lane, their
+// order and a histogram; 0 = not used for this call.  Worth it only when the lanes are kept busy by dynamic fetch
+// first (several trajectories per lane); ODE_B200_DRAIN=0/1 overrides, for A/B measurements.
+static size_t drain_lanes(const ode_b200_opts* o) {
+  int dev = 0, sms = 148;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  return (size_t)sms * 2048;  // upper bound of resident threads
+}
+static size_t drain_scratch_bytes(const ode_b200_opts* o, const ode_b200_ensemble_io* io) {
+  if (!ODEB200_DRAIN || !is_adaptive_rk(o->method) || o->fp_mode == ODE_B200_FP_FMA || o->rhs >= ODE_B200_RHS_USER_BASE) return 0;
+  const bool want_points = io->pts_y != nullptr || io->trace != nullptr;
+  if ((want_points && o->points != ODE_B200_POINTS_FINAL) || io->trace) return 0;
+  const size_t lanes = drain_lanes(o);
+  if (const char* e = getenv("ODE_B200_DRAIN")) {
+    if (atoi(e) == 0) return 0;
+  } else if ((size_t)io->n_traj < 2 * lanes / 3) {  // (~640 of the 2048 lanes per SM are resident: fewer than 2 trajectories per lane)
+    return 0;
+  }
+  return 256 + pad256(lanes * dump_width(o->dof) * sizeof(double)) + pad256(lanes * sizeof(int)) +
+         pad256((size_t)(SCHED_BINS + 2) * sizeof(unsigned int));
+}
 // doubles of pre-pass scratch launch_ensemble can use for this call (0: hinit stays inline)
 static size_t init_scratch_doubles(const ode_b200_opts* o, const ode_b200_ensemble_io* io) {
   const bool want_points = io->pts_y != nullptr || io->trace != nullptr;
@@ -467,7 +493,7 @@ static size_t init_scratch_doubles(const ode_b200_opts* o, const ode_b200_ensemb
 
 static int launch_ensemble(const ode_b200_opts* o, const ode_b200_ensemble_io* io, unsigned long long* counter,
                            cudaStream_t stream, bool time_it, double* init_scratch = nullptr,
-                           const double* uparams_host = nullptr, void* order_scratch = nullptr) {
+                           const double* uparams_host = nullptr, void* order_scratch = nullptr, void* drain_scratch = nullptr) {
   const bool want_points = io->pts_y != nullptr || io->trace != nullptr;
   const int mode = (want_points && o->points != ODE_B200_POINTS_FINAL) || io->trace ? 1 : 0;
   // one parameter vector for the whole ensemble: the mode-0 fast kernel reads it from the constant bank
@@ -579,8 +605,46 @@ static int launch_ensemble(const ode_b200_opts* o, const ode_b200_ensemble_io* i
       A.order = order;
     }
   }
+  const bool drain = drain_scratch != nullptr && two_pass && mode == 0 && drain_scratch_bytes(o, io) > 0 &&
+                     io->n_traj > grid * block;
+  unsigned int* dcount = nullptr;
+  int* dorder = nullptr;
+  unsigned int* dhist = nullptr;
+  if (drain) {  // phase A hands the tail over (ensemble_adapt.cuh)
+    const size_t lanes = drain_lanes(o);
+    char* b = reinterpret_cast<char*>(drain_scratch);
+    dcount = reinterpret_cast<unsigned int*>(b);
+    A.dump = reinterpret_cast<double*>(b + 256);
+    A.dump_count = dcount;
+    dorder = reinterpret_cast<int*>(b + 256 + pad256(lanes * dump_width(o->dof) * sizeof(double)));
+    dhist = reinterpret_cast<unsigned int*>(reinterpret_cast<char*>(dorder) + pad256(lanes * sizeof(int)));
+    ODEB200_CUDA(cudaMemsetAsync(dcount, 0, 256, stream));
+    ODEB200_CUDA(cudaMemsetAsync(dhist, 0, (size_t)(SCHED_BINS + 2) * sizeof(unsigned int), stream));
+    ODEB200_CUDA(cudaMemsetAsync(dhist, 0xff, sizeof(unsigned int), stream));
+  }
   ODEB200_CUDA(cudaLaunchKernel(k, dim3((unsigned)grid), dim3(block), kargs, 0, stream));
   note_launch();
+  if (drain) {  // phase B: the handed-over trajectories, least progress first, one warp = neighbours in progress
+    const int w = dump_width(o->dof);
+    const long long cap = grid * block;  // at most one record per lane of phase A
+    const unsigned gs = (unsigned)(cap / 2048 + 1 < (long long)sms * 4 ? cap / 2048 + 1 : (long long)sms * 4);
+    sched_range_kernel<<<gs, 256, 0, stream>>>(A.dump, w, cap, dhist, dcount);
+    sched_bin_kernel<<<gs, 256, 0, stream>>>(A.dump, w, cap, dhist, dorder, 0, dcount);
+    sched_scan_kernel<<<1, SCHED_BINS, 0, stream>>>(dhist);
+    sched_bin_kernel<<<gs, 256, 0, stream>>>(A.dump, w, cap, dhist, dorder, 1, dcount);
+    for (int q = 0; q < 4; q++) note_launch();
+    ODEB200_CUDA(cudaGetLastError());
+    A.resume = A.dump;
+    A.resume_order = dorder;
+    A.dump = nullptr;
+    A.work_counter = counter + 3;
+    ODEB200_CUDA(cudaLaunchKernel(k, dim3((unsigned)grid), dim3(block), kargs, 0, stream));
+    note_launch();
+    A.resume = nullptr;
+    A.resume_order = nullptr;
+    A.dump_count = nullptr;
+    A.work_counter = counter;
+  }
   if (two_pass) {
     // literal pass: re-integrates the trajectories the fast pass marked ODE_B200_ST_REDO (non-finite trial
     // state or error), multiplying every tableau coefficient like the reference; returns at once if none.
@@ -738,13 +802,15 @@ int ode_b200_solve_ensemble_dev(const ode_b200_opts* opts, const ode_b200_ensemb
   const size_t status_bytes = need_status ? pad256((size_t)io->n_traj * sizeof(int)) : 0;
   const size_t want = init_scratch_doubles(opts, &d);
   const size_t order_bytes = want > 0 ? order_scratch_bytes(opts, &d) : 0;
+  const size_t drain_bytes = drain_scratch_bytes(opts, &d);
   char* blk = nullptr;
-  ODEB200_CUDA(cudaMallocAsync((void**)&blk, 256 + status_bytes + pad256(want * sizeof(double)) + order_bytes, st));
+  ODEB200_CUDA(cudaMallocAsync((void**)&blk, 256 + status_bytes + pad256(want * sizeof(double)) + order_bytes + drain_bytes, st));
   unsigned long long* counter = reinterpret_cast<unsigned long long*>(blk);
   if (need_status) d.status = reinterpret_cast<int*>(blk + 256);
   double* init_scratch = want > 0 ? reinterpret_cast<double*>(blk + 256 + status_bytes) : nullptr;
   void* order_scratch = order_bytes ? blk + 256 + status_bytes + pad256(want * sizeof(double)) : nullptr;
-  rc = launch_ensemble(opts, &d, counter, st, true, init_scratch, fetch_upar ? upar : nullptr, order_scratch);
+  void* drain_scratch = drain_bytes ? blk + 256 + status_bytes + pad256(want * sizeof(double)) + order_bytes : nullptr;
+  rc = launch_ensemble(opts, &d, counter, st, true, init_scratch, fetch_upar ? upar : nullptr, order_scratch, drain_scratch);
   cudaFreeAsync(blk, st);  // stream-ordered: after the kernels above
   return rc;
 }
@@ -973,7 +1039,8 @@ int ode_b200_solve_ensemble(const ode_b200_opts* opts, const ode_b200_ensemble_i
   if (bytes <= kSmallCallBytes && !getenv("ODE_B200_NO_SMALL_PATH")) return solve_ensemble_small(opts, io, n_par);
   const size_t init_doubles = init_scratch_doubles(opts, io);  // hinit pre-pass scratch (0: inline)
   const size_t order_bytes = init_doubles ? order_scratch_bytes(opts, io) : 0;
-  bytes += pad256(init_doubles * 8) + order_bytes + 256;
+  const size_t drain_bytes = drain_scratch_bytes(opts, io);
+  bytes += pad256(init_doubles * 8) + order_bytes + 256 + drain_bytes + 256;
   rc = g_arena.ensure(opts->device, bytes);
   if (rc) return rc;
   cudaStream_t st = g_arena.stream;
@@ -1014,6 +1081,7 @@ int ode_b200_solve_ensemble(const ode_b200_opts* opts, const ode_b200_ensemble_i
   d.status = g_arena.take<int>(n);  // always: the fast and literal adaptive-RK passes talk through it
   double* dinit = init_doubles ? g_arena.take<double>(init_doubles) : nullptr;
   char* dorder = order_bytes ? g_arena.take<char>(order_bytes) : nullptr;
+  char* ddrain = drain_bytes ? g_arena.take<char>(drain_bytes) : nullptr;
   if (pts) {
     d.pts_t = g_arena.take<double>((size_t)n * io->pts_cap);
     d.pts_y = g_arena.take<double>((size_t)n * io->pts_cap * D);
@@ -1086,7 +1154,7 @@ int ode_b200_solve_ensemble(const ode_b200_opts* opts, const ode_b200_ensemble_i
     if (n_chunks == 1) ODEB200_CUDA(cudaEventRecord(g_ev0, cs));
     rc = launch_ensemble(opts, &dc, n_chunks > 1 ? counters + 32 * c : counter, cs, false,
                          dinit ? dinit + lo * init_width(opts) : nullptr, opts->params_stride == 0 ? io->params : nullptr,
-                         n_chunks == 1 ? (void*)dorder : nullptr);
+                         n_chunks == 1 ? (void*)dorder : nullptr, n_chunks == 1 ? (void*)ddrain : nullptr);
     if (rc) return rc;
     if (n_chunks == 1) ODEB200_CUDA(cudaEventRecord(g_ev1, cs));
     if (io->t_final && !zc_t) ODEB200_CUDA(cudaMemcpyAsync(io->t_final + lo, dc.t_final, m * 8, cudaMemcpyDeviceToHost, cs));

@@ -144,6 +144,20 @@ __global__ void __launch_bounds__(ENS_BLOCK, LITERAL ? 1 : adapt_min_blocks<Tab,
   const bool fwd = __double2hiint(tdir) > 0;    // tdir = +-1: x*tdir == (fwd ? x : -x) exactly (sign test off the FP64 pipe)
   const int nfixed = A.n_tspan;
 
+  // Tail hand-off.  When the work counter runs out every lane is busy with its last trajectory and the lanes of a
+  // warp finish at times spread over one trajectory duration: a warp would keep issuing for its slowest lane with
+  // ever fewer lanes active (4-5 % of all warp-iterations on 2^20 Lorenz trajectories, tools/tail_sim.py).  Instead the
+  // first lane of a warp that finds no work raises the warp's flag; its neighbours, at the end of their current
+  // attempt, write their state to A.dump and leave; a second launch of this kernel (A.resume) continues those
+  // trajectories, packed so that lanes of a warp have about the same distance to go.  The arithmetic of a trajectory
+  // does not change: its state crosses the launches as the very same doubles.
+  constexpr bool DRAIN = (ODEB200_DRAIN != 0) && MODE == 0 && !LITERAL;
+  __shared__ int warp_out[DRAIN ? ENS_BLOCK / 32 : 1];
+  if (DRAIN) {
+    if (threadIdx.x < ENS_BLOCK / 32) warp_out[threadIdx.x] = 0;
+    __syncthreads();
+  }
+
   long long idx = -1;
   double y[D], k1[D], pl[NPA];
   // PU: one parameter vector for the whole ensemble, read from the kernel-parameter constant bank
@@ -155,9 +169,35 @@ __global__ void __launch_bounds__(ENS_BLOCK, LITERAL ? 1 : adapt_min_blocks<Tab,
   long long ntrace = 0;
 
   while (true) {
+    if (DRAIN && idx < 0 && A.resume != nullptr) {  // second launch: continue a handed-over trajectory
+      const unsigned long long slot = atomicAdd(A.work_counter, 1ULL);
+      if (slot >= (unsigned long long)*A.dump_count) break;
+      const double* rec = A.resume + (long long)A.resume_order[slot] * dump_width(D);
+      t = rec[1];
+      dt = rec[2];
+      idx = __double_as_longlong(rec[3]);
+      const unsigned long long cnt = (unsigned long long)__double_as_longlong(rec[4]);
+      const unsigned long long fl = (unsigned long long)__double_as_longlong(rec[5]);
+      nacc = (int)(cnt & 0xffffffffULL);
+      nrej = (int)(cnt >> 32);
+      timeout = (int)(fl & 0xffULL);
+      islast = ((fl >> 8) & 1ULL) != 0;
+#pragma unroll
+      for (int d = 0; d < D; d++) {
+        y[d] = rec[6 + d];
+        k1[d] = rec[6 + D + d];
+      }
+      if (!PU) {
+#pragma unroll
+        for (int q = 0; q < NPA; q++) pl[q] = (q < Rhs::NP) ? A.params[idx * A.params_stride + q] : 0.0;
+      }
+    }
     if (idx < 0) {
       idx = (long long)atomicAdd(A.work_counter, 1ULL);
-      if (idx >= A.n_traj) break;
+      if (idx >= A.n_traj) {
+        if (DRAIN && A.dump != nullptr) *(volatile int*)&warp_out[threadIdx.x >> 5] = 1;
+        break;
+      }
       if (!LITERAL && A.order != nullptr) idx = A.order[idx];  // longest expected trajectory first (common.cuh)
       if (LITERAL && A.status[idx] != ODE_B200_ST_REDO) {  // the literal pass redoes marked trajectories only
         idx = -1;
@@ -432,6 +472,21 @@ __global__ void __launch_bounds__(ENS_BLOCK, LITERAL ? 1 : adapt_min_blocks<Tab,
         if (idx == A.trace_traj && A.trace_n) *A.trace_n = ntrace;
       }
       idx = -1;
+    }
+    if (DRAIN && A.dump != nullptr && idx >= 0 && *(volatile int*)&warp_out[threadIdx.x >> 5] != 0) {
+      double* rec = A.dump + (long long)atomicAdd(A.dump_count, 1u) * dump_width(D);
+      rec[0] = fabs(t - tstart);
+      rec[1] = t;
+      rec[2] = dt;
+      rec[3] = __longlong_as_double(idx);
+      rec[4] = __longlong_as_double((long long)((unsigned long long)(unsigned int)nacc | ((unsigned long long)(unsigned int)nrej << 32)));
+      rec[5] = __longlong_as_double((long long)((unsigned long long)(unsigned int)timeout | (islast ? 0x100ULL : 0ULL)));
+#pragma unroll
+      for (int d = 0; d < D; d++) {
+        rec[6 + d] = y[d];
+        rec[6 + D + d] = k1[d];
+      }
+      break;  // (the counter is exhausted: nothing else to fetch)
     }
   }
 }

@@ -286,6 +286,8 @@ def measure_lorenz(ctx, n, y0_np, steps, warmup, *, scaling, peaks, with_cpu, cp
         step_e2e()
     ctx.barrier()
     e2e_s = (time.perf_counter() - t0) / steps
+    L.ode_b200_last_kernel_ms.restype = C.c_double
+    e2e_kernel_ms = float(L.ode_b200_last_kernel_ms())  # device span of the last call's kernels (events inside the library)
     att2 = int(out["n_accept"].sum() + out["n_reject"].sum())
     assert att2 == attempts
     assert np.array_equal(out["y_final"], d_yf.cpu().numpy()), "host-buffer and device-resident arms disagree"
@@ -331,7 +333,7 @@ def measure_lorenz(ctx, n, y0_np, steps, warmup, *, scaling, peaks, with_cpu, cp
                                        ("" if world == 1 else "; final gather = every rank's results land in its slice "
                                                               "of one node-shared pinned host buffer, barrier per step"),
                         "value": e2e_v, "unit": "steps/s", "h2d_bytes_per_step": h2d * world, "d2h_bytes_per_step": d2h * world,
-                        "ms_per_step": e2e_s * 1e3},
+                        "ms_per_step": e2e_s * 1e3, "kernels_ms_inside_last_call": e2e_kernel_ms},
                 "gpu_launches": launches, "clocks": clocks, "roofline": roofline}
         if with_cpu and world == 1:
             line["cpu_baseline"] = cpu_baseline_lorenz(cpu_sample)[0]

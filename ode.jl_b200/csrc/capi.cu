@@ -367,6 +367,24 @@ static const void* pick_init_kernel(const ode_b200_opts* o) {
     default: return nullptr;
   }
 }
+// streaming pre-pass (ensemble_adapt.cuh): reads y0 from page-locked host memory while the persistent kernel runs
+static const void* pick_stream_init_kernel(const ode_b200_opts* o) {
+  if (o->fp_mode == ODE_B200_FP_FMA || o->rhs >= ODE_B200_RHS_USER_BASE) return nullptr;
+  switch (o->method) {
+    case ODE_B200_M_RK21: return adapt_kernel_rk21_stream_init(o->rhs);
+    case ODE_B200_M_RK23: return adapt_kernel_rk23_stream_init(o->rhs);
+    case ODE_B200_M_RK45_FE: return adapt_kernel_rk45_stream_init(o->rhs);
+    case ODE_B200_M_DOPRI5: return adapt_kernel_dopri5_stream_init(o->rhs);
+    case ODE_B200_M_FEH78: return adapt_kernel_feh78_stream_init(o->rhs);
+    case ODE_B200_M_CK45: return adapt_kernel_ck45_stream_init(o->rhs);
+    default: return nullptr;
+  }
+}
+struct StreamInit {        // what launch_ensemble needs for the streaming pre-pass
+  int* ready = nullptr;    // one flag per STREAM_CHUNK trajectories (device)
+  cudaStream_t side = nullptr;
+  cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
+};
 // doubles per trajectory the pre-pass writes: {dt0, f0[dof]} for adaptive RK, {h, F0[dof], J[dof][dof], rhs count} for ode23s
 static size_t init_width(const ode_b200_opts* o) {
   return o->method == ODE_B200_M_ODE23S ? (size_t)(2 + o->dof + o->dof * o->dof) : (size_t)(o->dof + 1);
@@ -493,7 +511,8 @@ static size_t init_scratch_doubles(const ode_b200_opts* o, const ode_b200_ensemb
 
 static int launch_ensemble(const ode_b200_opts* o, const ode_b200_ensemble_io* io, unsigned long long* counter,
                            cudaStream_t stream, bool time_it, double* init_scratch = nullptr,
-                           const double* uparams_host = nullptr, void* order_scratch = nullptr, void* drain_scratch = nullptr) {
+                           const double* uparams_host = nullptr, void* order_scratch = nullptr, void* drain_scratch = nullptr,
+                           const StreamInit* si = nullptr, int* status_out = nullptr) {
   const bool want_points = io->pts_y != nullptr || io->trace != nullptr;
   const int mode = (want_points && o->points != ODE_B200_POINTS_FINAL) || io->trace ? 1 : 0;
   // one parameter vector for the whole ensemble: the mode-0 fast kernel reads it from the constant bank
@@ -536,6 +555,7 @@ static int launch_ensemble(const ode_b200_opts* o, const ode_b200_ensemble_io* i
   A.trace_n = (long long*)io->trace_n;
   A.work_counter = counter;
   A.redo_count = reinterpret_cast<int*>(counter + 1);
+  A.status_out = status_out;
   if (uniform)
     for (int q = 0; q < np_u; q++) A.uparams[q] = uparams_host[q];
   if (ms_order(o->method) > 0) {  // ode_ms: order and b[so-1][j] for the kernel
@@ -580,7 +600,23 @@ static int launch_ensemble(const ode_b200_opts* o, const ode_b200_ensemble_io* i
     ODEB200_CUDA(cudaEventRecord(g_ev0, stream));
   }
   void* kargs[] = {(void*)&A};
-  if (init_scratch && init_scratch_doubles(o, io) > 0) {  // hinit of every trajectory with full warps
+  if (si && uniform && init_scratch) {
+    // streaming pre-pass: io->y0 is the caller's page-locked buffer as the device sees it; the side stream reads it
+    // chunk by chunk while the persistent kernel (launched right after, on `stream`) already integrates
+    const void* ks = pick_stream_init_kernel(o);
+    if (!ks) return set_err(ODE_B200_E_UNSUPPORTED, "no streaming pre-pass for method %d / rhs %d", o->method, o->rhs);
+    const long long chunks = (io->n_traj + STREAM_CHUNK - 1) / STREAM_CHUNK;
+    ODEB200_CUDA(cudaMemsetAsync(si->ready, 0, (size_t)chunks * sizeof(int), stream));
+    ODEB200_CUDA(cudaEventRecord(si->ev_fork, stream));
+    ODEB200_CUDA(cudaStreamWaitEvent(si->side, si->ev_fork, 0));
+    A.init = init_scratch;
+    int* ready = si->ready;
+    void* sargs[] = {(void*)&A, (void*)&ready};
+    ODEB200_CUDA(cudaLaunchKernel(ks, dim3((unsigned)(chunks < sms ? chunks : sms)), dim3(STREAM_CHUNK), sargs, 0, si->side));
+    note_launch();
+    ODEB200_CUDA(cudaEventRecord(si->ev_join, si->side));
+    A.ready = si->ready;
+  } else if (init_scratch && init_scratch_doubles(o, io) > 0) {  // hinit of every trajectory with full warps
     A.init = init_scratch;
     long long gi = (long long)sms * 8;
     if (need < gi) gi = need;
@@ -665,6 +701,7 @@ static int launch_ensemble(const ode_b200_opts* o, const ode_b200_ensemble_io* i
     ODEB200_CUDA(cudaLaunchKernel(kl, dim3((unsigned)grid_l), dim3(ENS_BLOCK), kargs, 0, stream));
     note_launch();
   }
+  if (A.ready) ODEB200_CUDA(cudaStreamWaitEvent(stream, si->ev_join, 0));
   if (time_it) {
     ODEB200_CUDA(cudaEventRecord(g_ev1, stream));
     g_ev_pending = true;
@@ -1037,10 +1074,31 @@ int ode_b200_solve_ensemble(const ode_b200_opts* opts, const ode_b200_ensemble_i
   if (pts) bytes += pad256((size_t)n * io->pts_cap * 8) + pad256((size_t)n * io->pts_cap * D * 8) + pad256(n * 4);
   if (io->trace) bytes += pad256((size_t)io->trace_cap * 32) + 256;
   if (bytes <= kSmallCallBytes && !getenv("ODE_B200_NO_SMALL_PATH")) return solve_ensemble_small(opts, io, n_par);
-  const size_t init_doubles = init_scratch_doubles(opts, io);  // hinit pre-pass scratch (0: inline)
+  size_t init_doubles = init_scratch_doubles(opts, io);  // hinit pre-pass scratch (0: inline)
   const size_t order_bytes = init_doubles ? order_scratch_bytes(opts, io) : 0;
   const size_t drain_bytes = drain_scratch_bytes(opts, io);
-  bytes += pad256(init_doubles * 8) + order_bytes + 256 + drain_bytes + 256;
+  // Streaming pre-pass: with y0 in page-locked (device-mapped) host memory and one parameter vector for the whole
+  // ensemble, the pre-pass reads y0 over PCIe chunk by chunk while the persistent kernel already integrates, instead
+  // of a host-to-device copy in front of everything (ensemble_adapt.cuh).  ODE_B200_STREAM_INIT=0/1 overrides.
+  const double* y0_mapped = nullptr;
+  {
+    bool want = n >= (1 << 17);
+    if (const char* e = getenv("ODE_B200_STREAM_INIT")) want = atoi(e) != 0;
+    cudaPointerAttributes at;
+    if (want && init_doubles > 0 && order_bytes == 0 && !getenv("ODE_B200_CHUNKS") && is_adaptive_rk(opts->method) &&
+        opts->params_stride == 0 && np <= 16 && !pts && !io->trace && pick_stream_init_kernel(opts) != nullptr) {
+      if (cudaPointerGetAttributes(&at, io->y0) == cudaSuccess && at.type == cudaMemoryTypeHost && at.devicePointer)
+        y0_mapped = (const double*)at.devicePointer;
+      else
+        cudaGetLastError();
+    }
+  }
+  size_t ready_bytes = 0;
+  if (y0_mapped) {
+    init_doubles = (size_t)n * (2 * D + 1);
+    ready_bytes = pad256(((size_t)n / STREAM_CHUNK + 1) * sizeof(int));
+  }
+  bytes += pad256(init_doubles * 8) + order_bytes + 256 + drain_bytes + 256 + ready_bytes;
   rc = g_arena.ensure(opts->device, bytes);
   if (rc) return rc;
   cudaStream_t st = g_arena.stream;
@@ -1078,10 +1136,22 @@ int ode_b200_solve_ensemble(const ode_b200_opts* opts, const ode_b200_ensemble_i
   d.n_accept = zc_na ? zc_na : (io->n_accept ? g_arena.take<int>(n) : nullptr);
   d.n_reject = zc_nr ? zc_nr : (io->n_reject ? g_arena.take<int>(n) : nullptr);
   d.n_rhs = zc_nf ? zc_nf : (io->n_rhs ? g_arena.take<int>(n) : nullptr);
-  d.status = g_arena.take<int>(n);  // always: the fast and literal adaptive-RK passes talk through it
+  // status: the fast and literal adaptive-RK passes talk through a device copy; a mapped caller buffer gets the final
+  // values from the kernels directly (adaptive RK: next to the device copy; other methods write status once)
+  int* zc_st = (int*)mapped(io->status);
+  const bool rk_two_pass = is_adaptive_rk(opts->method);
+  d.status = (zc_st && !rk_two_pass) ? zc_st : g_arena.take<int>(n);
   double* dinit = init_doubles ? g_arena.take<double>(init_doubles) : nullptr;
   char* dorder = order_bytes ? g_arena.take<char>(order_bytes) : nullptr;
   char* ddrain = drain_bytes ? g_arena.take<char>(drain_bytes) : nullptr;
+  StreamInit sinit;
+  if (y0_mapped) {
+    sinit.ready = reinterpret_cast<int*>(g_arena.take<char>(ready_bytes));
+    sinit.side = g_arena.stream2;
+    sinit.ev_fork = g_arena.ev_in;
+    sinit.ev_join = g_arena.ev_done2;
+    d.y0 = y0_mapped;  // nothing is uploaded: every reader takes y0 from the caller's buffer
+  }
   if (pts) {
     d.pts_t = g_arena.take<double>((size_t)n * io->pts_cap);
     d.pts_y = g_arena.take<double>((size_t)n * io->pts_cap * D);
@@ -1133,8 +1203,10 @@ int ode_b200_solve_ensemble(const ode_b200_opts* opts, const ode_b200_ensemble_i
     cudaStream_t cs = (c & 1) ? g_arena.stream2 : st;
     ode_b200_ensemble_io dc = d;
     dc.n_traj = m;
-    dc.y0 = dy0 + lo * D;
-    ODEB200_CUDA(cudaMemcpyAsync(dy0 + lo * D, io->y0 + lo * D, (size_t)m * D * 8, cudaMemcpyHostToDevice, cs));
+    if (!y0_mapped) {
+      dc.y0 = dy0 + lo * D;
+      ODEB200_CUDA(cudaMemcpyAsync(dy0 + lo * D, io->y0 + lo * D, (size_t)m * D * 8, cudaMemcpyHostToDevice, cs));
+    }
     if (n_par && opts->params_stride) {
       dc.params = dpar + lo * opts->params_stride;
       ODEB200_CUDA(cudaMemcpyAsync(dpar + lo * opts->params_stride, io->params + lo * opts->params_stride,
@@ -1154,7 +1226,8 @@ int ode_b200_solve_ensemble(const ode_b200_opts* opts, const ode_b200_ensemble_i
     if (n_chunks == 1) ODEB200_CUDA(cudaEventRecord(g_ev0, cs));
     rc = launch_ensemble(opts, &dc, n_chunks > 1 ? counters + 32 * c : counter, cs, false,
                          dinit ? dinit + lo * init_width(opts) : nullptr, opts->params_stride == 0 ? io->params : nullptr,
-                         n_chunks == 1 ? (void*)dorder : nullptr, n_chunks == 1 ? (void*)ddrain : nullptr);
+                         n_chunks == 1 ? (void*)dorder : nullptr, n_chunks == 1 ? (void*)ddrain : nullptr,
+                         y0_mapped ? &sinit : nullptr, (zc_st && rk_two_pass) ? zc_st + lo : nullptr);
     if (rc) return rc;
     if (n_chunks == 1) ODEB200_CUDA(cudaEventRecord(g_ev1, cs));
     if (io->t_final && !zc_t) ODEB200_CUDA(cudaMemcpyAsync(io->t_final + lo, dc.t_final, m * 8, cudaMemcpyDeviceToHost, cs));
@@ -1162,7 +1235,7 @@ int ode_b200_solve_ensemble(const ode_b200_opts* opts, const ode_b200_ensemble_i
     if (io->n_accept && !zc_na) ODEB200_CUDA(cudaMemcpyAsync(io->n_accept + lo, dc.n_accept, m * 4, cudaMemcpyDeviceToHost, cs));
     if (io->n_reject && !zc_nr) ODEB200_CUDA(cudaMemcpyAsync(io->n_reject + lo, dc.n_reject, m * 4, cudaMemcpyDeviceToHost, cs));
     if (io->n_rhs && !zc_nf) ODEB200_CUDA(cudaMemcpyAsync(io->n_rhs + lo, dc.n_rhs, m * 4, cudaMemcpyDeviceToHost, cs));
-    if (io->status) ODEB200_CUDA(cudaMemcpyAsync(io->status + lo, dc.status, m * 4, cudaMemcpyDeviceToHost, cs));
+    if (io->status && !zc_st) ODEB200_CUDA(cudaMemcpyAsync(io->status + lo, dc.status, m * 4, cudaMemcpyDeviceToHost, cs));
   }
   ODEB200_CUDA(cudaEventRecord(g_arena.ev_done2, g_arena.stream2));
   ODEB200_CUDA(cudaStreamWaitEvent(st, g_arena.ev_done2, 0));

@@ -14,12 +14,18 @@ EnsembleKernel adapt_kernel_rk45(int rhs, int mode, int literal);
 EnsembleKernel adapt_kernel_dopri5(int rhs, int mode, int literal);
 EnsembleKernel adapt_kernel_feh78(int rhs, int mode, int literal);
 EnsembleKernel adapt_kernel_ck45(int rhs, int mode, int literal);
-EnsembleKernel adapt_kernel_rk21_init(int rhs);  // hinit pre-pass (ens_adapt_init_kernel)
-EnsembleKernel adapt_kernel_rk23_init(int rhs);  // hinit pre-pass (ens_adapt_init_kernel)
-EnsembleKernel adapt_kernel_rk45_init(int rhs);  // hinit pre-pass (ens_adapt_init_kernel)
-EnsembleKernel adapt_kernel_dopri5_init(int rhs);  // hinit pre-pass (ens_adapt_init_kernel)
-EnsembleKernel adapt_kernel_feh78_init(int rhs);  // hinit pre-pass (ens_adapt_init_kernel)
-EnsembleKernel adapt_kernel_ck45_init(int rhs);   // hinit pre-pass (ens_adapt_init_kernel)
+EnsembleKernel adapt_kernel_rk21_init(int rhs);
+const void* adapt_kernel_rk21_stream_init(int rhs);  // hinit pre-pass (ens_adapt_init_kernel)
+EnsembleKernel adapt_kernel_rk23_init(int rhs);
+const void* adapt_kernel_rk23_stream_init(int rhs);  // hinit pre-pass (ens_adapt_init_kernel)
+EnsembleKernel adapt_kernel_rk45_init(int rhs);
+const void* adapt_kernel_rk45_stream_init(int rhs);  // hinit pre-pass (ens_adapt_init_kernel)
+EnsembleKernel adapt_kernel_dopri5_init(int rhs);
+const void* adapt_kernel_dopri5_stream_init(int rhs);  // hinit pre-pass (ens_adapt_init_kernel)
+EnsembleKernel adapt_kernel_feh78_init(int rhs);
+const void* adapt_kernel_feh78_stream_init(int rhs);  // hinit pre-pass (ens_adapt_init_kernel)
+EnsembleKernel adapt_kernel_ck45_init(int rhs);
+const void* adapt_kernel_ck45_stream_init(int rhs);   // hinit pre-pass (ens_adapt_init_kernel)
 EnsembleKernel fixed_kernel(int method, int rhs);
 EnsembleKernel ode23s_kernel(int rhs, int mode, int jac);  // jac: 0 fdjacobian, 1 analytic functor
 EnsembleKernel ode23s_init_kernel(int rhs, int jac);       // pre-pass: first step, F0, first Jacobian
@@ -57,6 +63,7 @@ EnsembleKernel ms_kernel(int rhs);  // ode_ms, orders 1..5
       ODEB200_RHS_SWITCH(rhs, ODEB200_ADAPT_M0_##TAB)                                          \
     }                                                                                          \
   }                                                                                            \
-  EnsembleKernel NAME##_init(int rhs) { ODEB200_RHS_SWITCH(rhs, ODEB200_ADAPT_INIT_##TAB) }
+  EnsembleKernel NAME##_init(int rhs) { ODEB200_RHS_SWITCH(rhs, ODEB200_ADAPT_INIT_##TAB) }                      \
+  const void* NAME##_stream_init(int rhs) { ODEB200_RHS_SWITCH(rhs, ODEB200_ADAPT_SINIT_##TAB) }
 
 }  // namespace odeb200

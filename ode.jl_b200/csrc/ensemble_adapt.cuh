@@ -111,6 +111,44 @@ __global__ void __launch_bounds__(ENS_BLOCK) ens_adapt_init_kernel(const Ensembl
   }
 }
 
+// The same pre-pass reading y0 straight from the caller's page-locked host buffer (device-mapped), in trajectory
+// order, WHILE the persistent kernel runs: the upload of y0 (25 MB = 0.45 ms of an 11.5 ms call for 2^20 Lorenz
+// trajectories) disappears behind the integration.  One 64-thread block per SM, launched before the persistent grid so
+// that it is resident first (it needs 4 K of the 65 K registers per SM); each block walks the chunks
+// blockIdx, blockIdx + gridDim, ... and raises ready[chunk] when the chunk's rows {dt0, f0, y0} are in HBM.  A lane of
+// the persistent kernel that fetches a trajectory whose chunk is not ready yet waits for the flag; the pre-pass never
+// waits for anything, so the pair cannot deadlock (and a lane that waited too long computes hinit itself from the
+// host copy).  Only one parameter vector for the whole ensemble (nothing else to stream).
+template <class Tab, class Rhs>
+__global__ void __launch_bounds__(STREAM_CHUNK, 16) ens_adapt_stream_init_kernel(const EnsembleArgs A, int* ready) {
+  constexpr int D = Rhs::DOF, NPA = RhsNP<Rhs>::value, W = 2 * D + 1;
+  const double tstart = A.tspan[0];
+  const double tend = A.tspan[A.n_tspan - 1];
+  const double tdir = jl_sign(tend - tstart);
+  double p[NPA];
+#pragma unroll
+  for (int q = 0; q < NPA; q++) p[q] = (q < Rhs::NP) ? A.uparams[q] : 0.0;
+  const long long chunks = (A.n_traj + STREAM_CHUNK - 1) / STREAM_CHUNK;
+  for (long long c = blockIdx.x; c < chunks; c += gridDim.x) {
+    const long long idx = c * STREAM_CHUNK + threadIdx.x;
+    if (idx < A.n_traj) {
+      double y[D], k1[D];
+#pragma unroll
+      for (int d = 0; d < D; d++) y[d] = A.y0[idx * D + d];  // over PCIe
+      double* out = A.init + idx * W;
+      out[0] = hinit_rk<Tab, Rhs>(A, tstart, tend, tdir, y, p, k1);
+#pragma unroll
+      for (int d = 0; d < D; d++) {
+        out[1 + d] = k1[d];
+        out[1 + D + d] = y[d];
+      }
+    }
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0) *(volatile int*)&ready[c] = 1;
+  }
+}
+
 // Resident CTAs per SM asked of ptxas.  Measured on Lorenz/dopri5 (profiles/ensemble_lorenz_r1.md):
 // 5 CTAs/SM (<= 102 registers, no spill) beats both the unconstrained allocation (119 registers,
 // 4 CTAs/SM) and tighter bounds that spill.  Larger state x stage products are left unconstrained.
@@ -204,8 +242,28 @@ __global__ void __launch_bounds__(ENS_BLOCK, LITERAL ? 1 : adapt_min_blocks<Tab,
         continue;
       }
       // ---------------------------------------------------------- init :256-304
+      bool have_row = false;
+      if (MODE == 0 && !LITERAL && PU && A.ready != nullptr) {  // streaming pre-pass: {dt0, f0, y0} when the chunk is ready
+        const volatile int* flag = A.ready + idx / STREAM_CHUNK;
+        for (int spin = 0; spin < (1 << 16) && !have_row; spin++) {
+          have_row = *flag != 0;
+          if (!have_row) __nanosleep(200);
+        }
+        if (have_row) {
+          __threadfence();
+          const double* in = A.init + idx * (2 * D + 1);
+          dt = __ldcg(in);
 #pragma unroll
-      for (int d = 0; d < D; d++) y[d] = A.y0[idx * D + d];
+          for (int d = 0; d < D; d++) {
+            k1[d] = __ldcg(in + 1 + d);
+            y[d] = __ldcg(in + 1 + D + d);
+          }
+        }
+      }
+      if (!have_row) {
+#pragma unroll
+        for (int d = 0; d < D; d++) y[d] = A.y0[idx * D + d];
+      }
       if (!PU) {
 #pragma unroll
         for (int q = 0; q < NPA; q++) pl[q] = (q < Rhs::NP) ? A.params[idx * A.params_stride + q] : 0.0;
@@ -216,7 +274,8 @@ __global__ void __launch_bounds__(ENS_BLOCK, LITERAL ? 1 : adapt_min_blocks<Tab,
       iter = 2;
       iter_fixed = 2;
       ntrace = 0;
-      if (MODE == 0 && !LITERAL && A.init != nullptr) {  // computed by ens_adapt_init_kernel with all lanes busy
+      if (have_row) {
+      } else if (MODE == 0 && !LITERAL && A.init != nullptr && A.ready == nullptr) {  // computed by ens_adapt_init_kernel with all lanes busy
         const double* in = A.init + idx * (D + 1);
         dt = in[0];
 #pragma unroll
@@ -467,6 +526,7 @@ __global__ void __launch_bounds__(ENS_BLOCK, LITERAL ? 1 : adapt_min_blocks<Tab,
       if (A.n_reject) A.n_reject[idx] = nrej;
       if (A.n_rhs) A.n_rhs[idx] = nrhs;
       if (A.status) A.status[idx] = fin;
+      if (A.status_out) A.status_out[idx] = fin;
       if (MODE == 1) {
         if (A.pts_n) A.pts_n[idx] = npts;
         if (idx == A.trace_traj && A.trace_n) *A.trace_n = ntrace;

@@ -235,7 +235,11 @@ __global__ void __launch_bounds__(S23_BLOCK) ens_ode23s_init_kernel(const Ensemb
 }
 
 template <class Rhs, int MODE, int JAC>
+#ifdef ODEB200_S23_MAXNREG
+__global__ void __maxnreg__(ODEB200_S23_MAXNREG) ens_ode23s_kernel(const EnsembleArgs A) {
+#else
 __global__ void __launch_bounds__(S23_BLOCK, (Rhs::DOF <= 3) ? ODEB200_S23_MINB : 0) ens_ode23s_kernel(const EnsembleArgs A) {
+#endif
   constexpr int D = Rhs::DOF, NPA = RhsNP<Rhs>::value;
   const double dd = 1.0 / (2.0 + sqrt(2.0));  // :270
   const double e32 = 6.0 + sqrt(2.0);         // :271

@@ -8,5 +8,6 @@ namespace odeb200 {
 #define ODEB200_ADAPT_M1L_TabCK45(R) return ens_adapt_kernel<TabCK45, R, 1, true>
 #define ODEB200_ADAPT_M0U_TabCK45(R) return ens_adapt_kernel<TabCK45, R, 0, false, true>
 #define ODEB200_ADAPT_INIT_TabCK45(R) return ens_adapt_init_kernel<TabCK45, R>
+#define ODEB200_ADAPT_SINIT_TabCK45(R) return (const void*)ens_adapt_stream_init_kernel<TabCK45, R>
 ODEB200_DEFINE_ADAPT(adapt_kernel_ck45, TabCK45)
 }  // namespace odeb200

@@ -8,5 +8,6 @@ namespace odeb200 {
 #define ODEB200_ADAPT_M1L_TabFeh78(R) return ens_adapt_kernel<TabFeh78, R, 1, true>
 #define ODEB200_ADAPT_M0U_TabFeh78(R) return ens_adapt_kernel<TabFeh78, R, 0, false, true>
 #define ODEB200_ADAPT_INIT_TabFeh78(R) return ens_adapt_init_kernel<TabFeh78, R>
+#define ODEB200_ADAPT_SINIT_TabFeh78(R) return (const void*)ens_adapt_stream_init_kernel<TabFeh78, R>
 ODEB200_DEFINE_ADAPT(adapt_kernel_feh78, TabFeh78)
 }  // namespace odeb200

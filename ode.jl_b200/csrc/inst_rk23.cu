@@ -8,5 +8,6 @@ namespace odeb200 {
 #define ODEB200_ADAPT_M1L_TabRK23(R) return ens_adapt_kernel<TabRK23, R, 1, true>
 #define ODEB200_ADAPT_M0U_TabRK23(R) return ens_adapt_kernel<TabRK23, R, 0, false, true>
 #define ODEB200_ADAPT_INIT_TabRK23(R) return ens_adapt_init_kernel<TabRK23, R>
+#define ODEB200_ADAPT_SINIT_TabRK23(R) return (const void*)ens_adapt_stream_init_kernel<TabRK23, R>
 ODEB200_DEFINE_ADAPT(adapt_kernel_rk23, TabRK23)
 }  // namespace odeb200

@@ -8,5 +8,6 @@ namespace odeb200 {
 #define ODEB200_ADAPT_M1L_TabRK45(R) return ens_adapt_kernel<TabRK45, R, 1, true>
 #define ODEB200_ADAPT_M0U_TabRK45(R) return ens_adapt_kernel<TabRK45, R, 0, false, true>
 #define ODEB200_ADAPT_INIT_TabRK45(R) return ens_adapt_init_kernel<TabRK45, R>
+#define ODEB200_ADAPT_SINIT_TabRK45(R) return (const void*)ens_adapt_stream_init_kernel<TabRK45, R>
 ODEB200_DEFINE_ADAPT(adapt_kernel_rk45, TabRK45)
 }  // namespace odeb200

@@ -587,3 +587,30 @@ def test_tail_handoff_second_launch_bit_exact(method, rhs, monkeypatch):
                            **{k: v for k, v in kw.items() if k != "params"})
     for k in ("y_final", "t_final", "n_accept", "n_reject", "n_rhs", "status"):
         assert np.array_equal(got[k][sub], ref[k]), k
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("method,n", [("ode45", 200000), ("ode45", 6000), ("ode78", 70001), ("ode23", 9999)])
+def test_streaming_prepass_from_pinned_y0_bit_exact(method, n, monkeypatch):
+    """y0 in page-locked host memory + one parameter vector: the pre-pass reads y0 over PCIe chunk by chunk while the
+    persistent kernel is already integrating (ens_adapt_stream_init_kernel) instead of an upload in front of
+    everything.  Same bits as the staged path and as the oracle; ragged sizes exercise the last partial chunk."""
+    rng = np.random.default_rng(11)
+    y0 = m.pinned_empty((n, 3))
+    y0[:] = np.stack([rng.uniform(-10, 10, n), rng.uniform(-10, 10, n), rng.uniform(5, 35, n)], 1)
+    F = m.DeviceRHS("lorenz", *LORENZ)
+    ts = [0.0, 0.5]
+    L = m.lib()
+    monkeypatch.setenv("ODE_B200_STREAM_INIT", "0")
+    plain = m.solve_ensemble(method, F, y0, ts)
+    monkeypatch.setenv("ODE_B200_STREAM_INIT", "1")
+    for direct in (False, True):
+        got = m.solve_ensemble(method, F, y0, ts, direct_output=direct)
+        assert_same(got, plain)
+    pageable = m.solve_ensemble(method, F, np.array(y0), ts)  # a pageable copy takes the staged path
+    assert_same(pageable, plain)
+    sub = slice(0, min(n, 20000))
+    O.use_all_cores()
+    ref = O.solve_ensemble(method, "lorenz", np.array(y0[sub]), ts, LORENZ)
+    for k in ("y_final", "t_final", "n_accept", "n_reject", "n_rhs", "status"):
+        assert np.array_equal(got[k][sub], ref[k]), k

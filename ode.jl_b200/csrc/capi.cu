@@ -384,6 +384,7 @@ struct StreamInit {        // what launch_ensemble needs for the streaming pre-p
   int* ready = nullptr;    // one flag per STREAM_CHUNK trajectories (device)
   cudaStream_t side = nullptr;
   cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
+
 };
 // doubles per trajectory the pre-pass writes: {dt0, f0[dof]} for adaptive RK, {h, F0[dof], J[dof][dof], rhs count} for ode23s
 static size_t init_width(const ode_b200_opts* o) {
@@ -601,18 +602,26 @@ static int launch_ensemble(const ode_b200_opts* o, const ode_b200_ensemble_io* i
   }
   void* kargs[] = {(void*)&A};
   if (si && uniform && init_scratch) {
-    // streaming pre-pass: io->y0 is the caller's page-locked buffer as the device sees it; the side stream reads it
-    // chunk by chunk while the persistent kernel (launched right after, on `stream`) already integrates
+    // streaming pre-pass: A.y0 is the caller's page-locked buffer as the device sees it; a few blocks on the side
+    // stream read it chunk by chunk while the persistent kernel (launched right after, on `stream`) already integrates
     const void* ks = pick_stream_init_kernel(o);
     if (!ks) return set_err(ODE_B200_E_UNSUPPORTED, "no streaming pre-pass for method %d / rhs %d", o->method, o->rhs);
-    const long long chunks = (io->n_traj + STREAM_CHUNK - 1) / STREAM_CHUNK;
-    ODEB200_CUDA(cudaMemsetAsync(si->ready, 0, (size_t)chunks * sizeof(int), stream));
+    long long cend = (io->n_traj + STREAM_CHUNK - 1) / STREAM_CHUNK;
+    ODEB200_CUDA(cudaMemsetAsync(si->ready, 0, (size_t)cend * sizeof(int), stream));
     ODEB200_CUDA(cudaEventRecord(si->ev_fork, stream));
     ODEB200_CUDA(cudaStreamWaitEvent(si->side, si->ev_fork, 0));
     A.init = init_scratch;
     int* ready = si->ready;
-    void* sargs[] = {(void*)&A, (void*)&ready};
-    ODEB200_CUDA(cudaLaunchKernel(ks, dim3((unsigned)(chunks < sms ? chunks : sms)), dim3(STREAM_CHUNK), sargs, 0, si->side));
+    // one block per chunk for the rows every resident lane starts with (all in flight at once, gone after one PCIe
+    // round trip); `nlong` of them stay for the rest: every SM hosting one gives up resident CTAs of the persistent grid
+    long long cfirst = (grid * block + STREAM_CHUNK - 1) / STREAM_CHUNK;
+    if (getenv("ODE_B200_STREAM_ONE")) cfirst = 0;
+    if (cfirst > cend) cfirst = cend;
+    int nlong = 16;
+    if (const char* e = getenv("ODE_B200_STREAM_GRID")) nlong = atoi(e) > 0 ? atoi(e) : nlong;
+    void* sargs[] = {(void*)&A, (void*)&ready, (void*)&cfirst, (void*)&cend, (void*)&nlong};
+    const long long sgrid = cfirst > nlong ? cfirst : nlong;
+    ODEB200_CUDA(cudaLaunchKernel(ks, dim3((unsigned)sgrid), dim3(STREAM_CHUNK), sargs, 0, si->side));
     note_launch();
     ODEB200_CUDA(cudaEventRecord(si->ev_join, si->side));
     A.ready = si->ready;
@@ -681,6 +690,7 @@ static int launch_ensemble(const ode_b200_opts* o, const ode_b200_ensemble_io* i
     A.dump_count = nullptr;
     A.work_counter = counter;
   }
+  if (A.ready) ODEB200_CUDA(cudaStreamWaitEvent(stream, si->ev_join, 0));  // (the pre-pass is long over)
   if (two_pass) {
     // literal pass: re-integrates the trajectories the fast pass marked ODE_B200_ST_REDO (non-finite trial
     // state or error), multiplying every tableau coefficient like the reference; returns at once if none.
@@ -701,7 +711,6 @@ static int launch_ensemble(const ode_b200_opts* o, const ode_b200_ensemble_io* i
     ODEB200_CUDA(cudaLaunchKernel(kl, dim3((unsigned)grid_l), dim3(ENS_BLOCK), kargs, 0, stream));
     note_launch();
   }
-  if (A.ready) ODEB200_CUDA(cudaStreamWaitEvent(stream, si->ev_join, 0));
   if (time_it) {
     ODEB200_CUDA(cudaEventRecord(g_ev1, stream));
     g_ev_pending = true;
@@ -1082,12 +1091,13 @@ int ode_b200_solve_ensemble(const ode_b200_opts* opts, const ode_b200_ensemble_i
   // of a host-to-device copy in front of everything (ensemble_adapt.cuh).  ODE_B200_STREAM_INIT=0/1 overrides.
   const double* y0_mapped = nullptr;
   {
-    bool want = n >= (1 << 17);
+    bool want = n >= (1 << 18);
     if (const char* e = getenv("ODE_B200_STREAM_INIT")) want = atoi(e) != 0;
     cudaPointerAttributes at;
     if (want && init_doubles > 0 && order_bytes == 0 && !getenv("ODE_B200_CHUNKS") && is_adaptive_rk(opts->method) &&
         opts->params_stride == 0 && np <= 16 && !pts && !io->trace && pick_stream_init_kernel(opts) != nullptr) {
-      if (cudaPointerGetAttributes(&at, io->y0) == cudaSuccess && at.type == cudaMemoryTypeHost && at.devicePointer)
+      if (cudaPointerGetAttributes(&at, io->y0) == cudaSuccess && at.type == cudaMemoryTypeHost && at.devicePointer &&
+          ((size_t)at.devicePointer & 15) == 0)  // (the pre-pass reads y0 in 16-byte pieces)
         y0_mapped = (const double*)at.devicePointer;
       else
         cudaGetLastError();

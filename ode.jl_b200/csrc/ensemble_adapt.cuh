@@ -112,29 +112,68 @@ __global__ void __launch_bounds__(ENS_BLOCK) ens_adapt_init_kernel(const Ensembl
 }
 
 // The same pre-pass reading y0 straight from the caller's page-locked host buffer (device-mapped), in trajectory
-// order, WHILE the persistent kernel runs: the upload of y0 (25 MB = 0.45 ms of an 11.5 ms call for 2^20 Lorenz
-// trajectories) disappears behind the integration.  One 64-thread block per SM, launched before the persistent grid so
-// that it is resident first (it needs 4 K of the 65 K registers per SM); each block walks the chunks
-// blockIdx, blockIdx + gridDim, ... and raises ready[chunk] when the chunk's rows {dt0, f0, y0} are in HBM.  A lane of
-// the persistent kernel that fetches a trajectory whose chunk is not ready yet waits for the flag; the pre-pass never
-// waits for anything, so the pair cannot deadlock (and a lane that waited too long computes hinit itself from the
-// host copy).  Only one parameter vector for the whole ensemble (nothing else to stream).
+// order, WHILE the persistent kernel runs: the upload of y0 (25 MB = 0.45 ms of an 11.3 ms call for 2^20 Lorenz
+// trajectories) disappears behind the integration.  A FEW fat blocks (STREAM_BLOCKS x 256 threads: enough loads in
+// flight to keep PCIe busy), launched before the persistent grid so that they are resident first; each walks the
+// chunks c0 + blockIdx, c0 + blockIdx + gridDim, ... < c1 and raises ready[chunk] when the chunk's rows {dt0, f0, y0}
+// are in HBM.  A lane of the persistent kernel that fetches a trajectory whose chunk is not ready yet waits for the
+// flag; the pre-pass never waits for anything, so the pair cannot deadlock (and a lane that waited too long computes
+// hinit itself from the caller's buffer).  Only for one parameter vector shared by the whole ensemble.
+// Measured alternatives (profiles/ensemble_kernels_r2.md): one 64-thread block on EVERY SM costs each SM a resident
+// CTA of the persistent grid for 0.5 ms (register files are per scheduler: a 64-register warp does not fit next to
+// five 96-register ones), 11.30 -> 11.16 ms only; pre-processing a DMA-copied remainder with a second launch cannot
+// become resident next to the full persistent grid at all (the lanes time out: 290 ms).
 template <class Tab, class Rhs>
-__global__ void __launch_bounds__(STREAM_CHUNK, 16) ens_adapt_stream_init_kernel(const EnsembleArgs A, int* ready) {
+__global__ void __launch_bounds__(STREAM_CHUNK, 2) ens_adapt_stream_init_kernel(const EnsembleArgs A, int* ready, long long cfirst, long long cend, int nlong) {
   constexpr int D = Rhs::DOF, NPA = RhsNP<Rhs>::value, W = 2 * D + 1;
+  constexpr int PAIRS = STREAM_CHUNK * D / 2;                          // 16-byte pieces of one chunk of y0
+  constexpr int PER = (PAIRS + STREAM_CHUNK - 1) / STREAM_CHUNK;       // pieces per thread
+  static_assert((STREAM_CHUNK * D) % 2 == 0, "a chunk of y0 is a whole number of 16-byte pieces");
+  __shared__ double2 sy[PAIRS];
   const double tstart = A.tspan[0];
   const double tend = A.tspan[A.n_tspan - 1];
   const double tdir = jl_sign(tend - tstart);
   double p[NPA];
 #pragma unroll
   for (int q = 0; q < NPA; q++) p[q] = (q < Rhs::NP) ? A.uparams[q] : 0.0;
-  const long long chunks = (A.n_traj + STREAM_CHUNK - 1) / STREAM_CHUNK;
-  for (long long c = blockIdx.x; c < chunks; c += gridDim.x) {
+  // Blocks 0 .. cfirst-1 take one chunk each first -- the rows every resident lane of the persistent grid starts with,
+  // all in flight at once -- and all but the first `nlong` blocks leave after that (making room for the persistent
+  // grid); the long-lived ones share the remaining chunks round-robin.
+  const long long total = A.n_traj * D;  // doubles in y0
+  auto next_chunk = [&](long long c) -> long long {
+    if (c < cfirst) return (blockIdx.x < nlong) ? cfirst + blockIdx.x : cend;
+    return c + nlong;
+  };
+  // The chunk's 64*D doubles are fetched over PCIe as coalesced 16-byte loads (a warp asks for 512 contiguous bytes),
+  // one chunk ahead of the arithmetic, and handed to their trajectories through shared memory.
+  double2 nx[PER];
+  auto fetch = [&](long long c) {
+    const long long base = c * (STREAM_CHUNK * D);
+#pragma unroll
+    for (int k = 0; k < PER; k++) {
+      const int i = threadIdx.x + k * STREAM_CHUNK;
+      const long long g = base + 2 * i;
+      nx[k] = make_double2(0.0, 0.0);
+      if (i < PAIRS && g + 1 < total) nx[k] = *reinterpret_cast<const double2*>(A.y0 + g);
+      else if (i < PAIRS && g < total) nx[k].x = A.y0[g];
+    }
+  };
+  long long c = (blockIdx.x < cfirst) ? (long long)blockIdx.x : ((blockIdx.x < nlong) ? cfirst + blockIdx.x : cend);
+  if (c < cend) fetch(c);
+  for (; c < cend; c = next_chunk(c)) {
+#pragma unroll
+    for (int k = 0; k < PER; k++) {
+      const int i = threadIdx.x + k * STREAM_CHUNK;
+      if (i < PAIRS) sy[i] = nx[k];
+    }
+    __syncthreads();
+    if (next_chunk(c) < cend) fetch(next_chunk(c));
     const long long idx = c * STREAM_CHUNK + threadIdx.x;
     if (idx < A.n_traj) {
       double y[D], k1[D];
+      const double* mine = reinterpret_cast<const double*>(sy) + threadIdx.x * D;
 #pragma unroll
-      for (int d = 0; d < D; d++) y[d] = A.y0[idx * D + d];  // over PCIe
+      for (int d = 0; d < D; d++) y[d] = mine[d];
       double* out = A.init + idx * W;
       out[0] = hinit_rk<Tab, Rhs>(A, tstart, tend, tdir, y, p, k1);
 #pragma unroll
@@ -144,7 +183,7 @@ __global__ void __launch_bounds__(STREAM_CHUNK, 16) ens_adapt_stream_init_kernel
       }
     }
     __threadfence();
-    __syncthreads();
+    __syncthreads();  // (also: everybody has read sy before the next chunk overwrites it)
     if (threadIdx.x == 0) *(volatile int*)&ready[c] = 1;
   }
 }

@@ -267,7 +267,9 @@ def measure_lorenz(ctx, n, y0_np, steps, warmup, *, scaling, peaks, with_cpu, cp
     h2d = y0_host.numel() * 8 + 3 * 8 + 2 * 8
     d2h = n * 8 + n * dof * 8 + 3 * n * 4
     # direct = the kernel writes the results into the pinned output buffers itself (host_output = 1, no copy-back
-    # phase).  Default: on for one rank; for several ranks per host staged copies measured no slower (8 x B200).
+    # phase).  Default: on for one rank (11.05 vs 11.25 ms); several ranks per host take the progressive copy-back of
+    # the staged path: the host cannot absorb eight kernels' small writes (8 x B200: 15.3 ms direct, 14.8 ms with a
+    # copy phase after the kernel, 11.46 ms progressive).
     direct = world == 1
     if os.environ.get("ODE_B200_BENCH_DIRECT"):
         direct = os.environ["ODE_B200_BENCH_DIRECT"] != "0"
@@ -275,8 +277,11 @@ def measure_lorenz(ctx, n, y0_np, steps, warmup, *, scaling, peaks, with_cpu, cp
 
     def step_e2e():
         _lib.check(L.ode_b200_solve_ensemble(C.byref(opts_e2e), C.byref(io2)))
-        if dist is not None:
-            dist.barrier()  # every rank's slice is in the shared buffer
+        if dist is not None:  # every rank's slice is in the shared buffer
+            if os.environ.get("ODE_B200_BENCH_BARRIER") == "nccl":
+                dist.barrier()
+            else:
+                shared.block.host_barrier()
 
     for _ in range(2):
         step_e2e()
@@ -329,7 +334,8 @@ def measure_lorenz(ctx, n, y0_np, steps, warmup, *, scaling, peaks, with_cpu, cp
                            "reltol": 1e-5, "abstol": 1e-8, "attempts_per_step_per_gpu": attempts,
                            "fp_mode": "strict (no FMA, reference parity)" if strict_fp else "fma (opt-in, not bit-exact)",
                            "l2": "256 MiB flush write between timed iterations", "parallelism": "traj-shard x%d" % world},
-                "e2e": {"output_path": ("kernel writes pinned host buffers" if direct else "staged D2H copies") +
+                "e2e": {"output_path": ("kernel writes pinned host buffers" if direct else
+                                        "results staged in HBM, copied back chunk by chunk while the kernel runs") +
                                        ("" if world == 1 else "; final gather = every rank's results land in its slice "
                                                               "of one node-shared pinned host buffer, barrier per step"),
                         "value": e2e_v, "unit": "steps/s", "h2d_bytes_per_step": h2d * world, "d2h_bytes_per_step": d2h * world,

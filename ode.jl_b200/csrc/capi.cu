@@ -380,6 +380,11 @@ static const void* pick_stream_init_kernel(const ode_b200_opts* o) {
     default: return nullptr;
   }
 }
+struct ChunkBack {         // progressive copy-back (common.cuh, EnsembleArgs::chunk_done)
+  int* done = nullptr;     // device counters, one per chunk
+  int* flag_dev = nullptr; // the host flags as the device sees them
+  int log2 = 14;           // trajectories per chunk = 2^log2
+};
 struct StreamInit {        // what launch_ensemble needs for the streaming pre-pass
   int* ready = nullptr;    // one flag per STREAM_CHUNK trajectories (device)
   cudaStream_t side = nullptr;
@@ -513,7 +518,7 @@ static size_t init_scratch_doubles(const ode_b200_opts* o, const ode_b200_ensemb
 static int launch_ensemble(const ode_b200_opts* o, const ode_b200_ensemble_io* io, unsigned long long* counter,
                            cudaStream_t stream, bool time_it, double* init_scratch = nullptr,
                            const double* uparams_host = nullptr, void* order_scratch = nullptr, void* drain_scratch = nullptr,
-                           const StreamInit* si = nullptr, int* status_out = nullptr) {
+                           const StreamInit* si = nullptr, int* status_out = nullptr, const ChunkBack* cb = nullptr) {
   const bool want_points = io->pts_y != nullptr || io->trace != nullptr;
   const int mode = (want_points && o->points != ODE_B200_POINTS_FINAL) || io->trace ? 1 : 0;
   // one parameter vector for the whole ensemble: the mode-0 fast kernel reads it from the constant bank
@@ -557,6 +562,11 @@ static int launch_ensemble(const ode_b200_opts* o, const ode_b200_ensemble_io* i
   A.work_counter = counter;
   A.redo_count = reinterpret_cast<int*>(counter + 1);
   A.status_out = status_out;
+  if (cb) {
+    A.chunk_done = cb->done;
+    A.chunk_flag = cb->flag_dev;
+    A.chunk_log2 = cb->log2;
+  }
   if (uniform)
     for (int q = 0; q < np_u; q++) A.uparams[q] = uparams_host[q];
   if (ms_order(o->method) > 0) {  // ode_ms: order and b[so-1][j] for the kernel
@@ -1103,6 +1113,17 @@ int ode_b200_solve_ensemble(const ode_b200_opts* opts, const ode_b200_ensemble_i
         cudaGetLastError();
     }
   }
+  // Progressive copy-back: staged (not kernel-written) outputs of a large adaptive-RK ensemble go back to the host in
+  // chunks while the kernel is still running; the host thread of this blocking call does the polling.  With many GPUs
+  // behind one host this beats both a copy phase after the kernel and the kernel's own small writes into host memory
+  // (profiles/ensemble_kernels_r2.md).  ODE_B200_PROGRESSIVE=0/1 overrides.
+  ChunkBack cback;
+  bool progressive = n >= (1 << 17) && opts->host_output != 1;
+  if (const char* e = getenv("ODE_B200_PROGRESSIVE")) progressive = atoi(e) != 0;
+  progressive = progressive && is_adaptive_rk(opts->method) && !pts && !io->trace && !getenv("ODE_B200_CHUNKS") &&
+                opts->fp_mode != ODE_B200_FP_FMA && opts->rhs < ODE_B200_RHS_USER_BASE;
+  const long long n_back = progressive ? ((n + (1LL << cback.log2) - 1) >> cback.log2) : 0;
+  if (progressive) bytes += pad256((size_t)n_back * sizeof(int));
   size_t ready_bytes = 0;
   if (y0_mapped) {
     init_doubles = (size_t)n * (2 * D + 1);
@@ -1154,6 +1175,16 @@ int ode_b200_solve_ensemble(const ode_b200_opts* opts, const ode_b200_ensemble_i
   double* dinit = init_doubles ? g_arena.take<double>(init_doubles) : nullptr;
   char* dorder = order_bytes ? g_arena.take<char>(order_bytes) : nullptr;
   char* ddrain = drain_bytes ? g_arena.take<char>(drain_bytes) : nullptr;
+  int* back_flags = nullptr;  // host side of the chunk flags
+  if (progressive) {
+    cback.done = g_arena.take<int>((size_t)n_back);
+    rc = g_small.ensure((size_t)n_back * sizeof(int));
+    if (rc) return rc;
+    back_flags = reinterpret_cast<int*>(g_small.host);
+    cback.flag_dev = reinterpret_cast<int*>(g_small.dev);
+    memset(back_flags, 0, (size_t)n_back * sizeof(int));
+    ODEB200_CUDA(cudaMemsetAsync(cback.done, 0, (size_t)n_back * sizeof(int), st));
+  }
   StreamInit sinit;
   if (y0_mapped) {
     sinit.ready = reinterpret_cast<int*>(g_arena.take<char>(ready_bytes));
@@ -1237,9 +1268,46 @@ int ode_b200_solve_ensemble(const ode_b200_opts* opts, const ode_b200_ensemble_i
     rc = launch_ensemble(opts, &dc, n_chunks > 1 ? counters + 32 * c : counter, cs, false,
                          dinit ? dinit + lo * init_width(opts) : nullptr, opts->params_stride == 0 ? io->params : nullptr,
                          n_chunks == 1 ? (void*)dorder : nullptr, n_chunks == 1 ? (void*)ddrain : nullptr,
-                         y0_mapped ? &sinit : nullptr, (zc_st && rk_two_pass) ? zc_st + lo : nullptr);
+                         y0_mapped ? &sinit : nullptr, (zc_st && rk_two_pass) ? zc_st + lo : nullptr,
+                         (progressive && n_chunks == 1) ? &cback : nullptr);
     if (rc) return rc;
     if (n_chunks == 1) ODEB200_CUDA(cudaEventRecord(g_ev1, cs));
+    if (progressive && n_chunks == 1) {
+      // copy every chunk whose flag is up (on the second stream: the data of a flagged chunk is final), until the
+      // kernels are done; then the rest
+      std::vector<char> copied((size_t)n_back, 0);
+      auto copy_chunk = [&](long long c) -> cudaError_t {
+        const long long a = c << cback.log2, b = (a + (1LL << cback.log2) < n) ? a + (1LL << cback.log2) : n, k = b - a;
+        cudaStream_t s2 = g_arena.stream2;
+        cudaError_t e = cudaSuccess;
+        if (io->t_final && !zc_t && e == cudaSuccess) e = cudaMemcpyAsync(io->t_final + a, dc.t_final + a, k * 8, cudaMemcpyDeviceToHost, s2);
+        if (io->y_final && !zc_y && e == cudaSuccess) e = cudaMemcpyAsync(io->y_final + a * D, dc.y_final + a * D, (size_t)k * D * 8, cudaMemcpyDeviceToHost, s2);
+        if (io->n_accept && !zc_na && e == cudaSuccess) e = cudaMemcpyAsync(io->n_accept + a, dc.n_accept + a, k * 4, cudaMemcpyDeviceToHost, s2);
+        if (io->n_reject && !zc_nr && e == cudaSuccess) e = cudaMemcpyAsync(io->n_reject + a, dc.n_reject + a, k * 4, cudaMemcpyDeviceToHost, s2);
+        if (io->n_rhs && !zc_nf && e == cudaSuccess) e = cudaMemcpyAsync(io->n_rhs + a, dc.n_rhs + a, k * 4, cudaMemcpyDeviceToHost, s2);
+        if (io->status && !zc_st && e == cudaSuccess) e = cudaMemcpyAsync(io->status + a, dc.status + a, k * 4, cudaMemcpyDeviceToHost, s2);
+        return e;
+      };
+      long long first = 0;
+      bool kernels_done = false;
+      while (!kernels_done) {
+        const cudaError_t q = cudaEventQuery(g_ev1);
+        if (q == cudaSuccess) kernels_done = true;
+        else if (q != cudaErrorNotReady) ODEB200_CUDA(q);
+        while (first < n_back && copied[first]) first++;
+        const long long last = first + 64 < n_back ? first + 64 : n_back;  // (chunks complete roughly in order)
+        for (long long c = first; c < last; c++) {
+          if (!copied[c] && *(volatile int*)&back_flags[c] != 0) {
+            ODEB200_CUDA(copy_chunk(c));
+            copied[c] = 1;
+          }
+        }
+      }
+      ODEB200_CUDA(cudaStreamWaitEvent(g_arena.stream2, g_ev1, 0));
+      for (long long c = 0; c < n_back; c++)
+        if (!copied[c]) ODEB200_CUDA(copy_chunk(c));
+      continue;  // (everything is on its way: skip the copy phase below)
+    }
     if (io->t_final && !zc_t) ODEB200_CUDA(cudaMemcpyAsync(io->t_final + lo, dc.t_final, m * 8, cudaMemcpyDeviceToHost, cs));
     if (io->y_final && !zc_y) ODEB200_CUDA(cudaMemcpyAsync(io->y_final + lo * D, dc.y_final, (size_t)m * D * 8, cudaMemcpyDeviceToHost, cs));
     if (io->n_accept && !zc_na) ODEB200_CUDA(cudaMemcpyAsync(io->n_accept + lo, dc.n_accept, m * 4, cudaMemcpyDeviceToHost, cs));

@@ -566,6 +566,15 @@ __global__ void __launch_bounds__(ENS_BLOCK, LITERAL ? 1 : adapt_min_blocks<Tab,
       if (A.n_rhs) A.n_rhs[idx] = nrhs;
       if (A.status) A.status[idx] = fin;
       if (A.status_out) A.status_out[idx] = fin;
+      if (A.chunk_done != nullptr) {  // progressive copy-back: the last finisher of a chunk tells the host
+        __threadfence();
+        const long long c = idx >> A.chunk_log2;
+        const long long c_lo = c << A.chunk_log2, c_hi = (c_lo + (1LL << A.chunk_log2) < A.n_traj) ? c_lo + (1LL << A.chunk_log2) : A.n_traj;
+        if (atomicAdd(&A.chunk_done[c], 1) == (int)(c_hi - c_lo) - 1) {
+          __threadfence_system();
+          *(volatile int*)&A.chunk_flag[c] = 1;
+        }
+      }
       if (MODE == 1) {
         if (A.pts_n) A.pts_n[idx] = npts;
         if (idx == A.trace_traj && A.trace_n) *A.trace_n = ntrace;

@@ -36,6 +36,9 @@ class SharedHostBlock:
         if len(set(hosts)) != 1:
             raise RuntimeError("ranks on different hosts cannot share a host buffer")
         nbytes = max(int(nbytes), 4096)
+        self._bar_off = (nbytes + 4095) & ~4095  # one cache line per rank behind the payload: host_barrier()
+        nbytes = self._bar_off + 64 * self.world
+        self._gen = 0
         name = [None]
         if self.rank == 0:
             _counter[0] += 1
@@ -56,6 +59,19 @@ class SharedHostBlock:
         self.map = np.memmap(self.path, dtype=np.uint8, mode="r+", shape=(nbytes,))
         self._pinned = []
         dist.barrier(group)
+
+    def host_barrier(self, timeout_s=60.0):
+        """Barrier of the node's ranks through the shared block itself (a generation counter per rank, spun on by the
+        CPU): the "every slice has landed" point of the final gather without a device collective -- a NCCL barrier
+        costs a kernel launch and a stream synchronise per rank."""
+        import time
+        self._gen += 1
+        flags = self.map[self._bar_off:self._bar_off + 64 * self.world].view(np.int64).reshape(self.world, 8)
+        flags[self.rank, 0] = self._gen
+        t0 = time.perf_counter()
+        while int(flags[:, 0].min()) < self._gen:
+            if time.perf_counter() - t0 > timeout_s:
+                raise RuntimeError("host barrier timed out (a rank left?)")
 
     def view(self, dtype, shape, offset=0):
         cnt = int(np.prod(shape)) * np.dtype(dtype).itemsize
@@ -189,7 +205,7 @@ def solve_ensemble_distributed(alg, F, y0, tspan, *, params=None, group=None, ga
         loc = _local_solve(alg, F, y0[lo:hi], tspan, params=p_loc, **kw)
         for k in keys:
             shared.mine[k][...] = loc[k]
-    dist.barrier(group)  # every slice is complete: this is the whole "gather"
+    shared.block.host_barrier()  # every slice is complete: this is the whole "gather" (no device collective)
     if own is None:
         out = dict(shared.arrays)
     else:

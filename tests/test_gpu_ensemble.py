@@ -614,3 +614,38 @@ def test_streaming_prepass_from_pinned_y0_bit_exact(method, n, monkeypatch):
     ref = O.solve_ensemble(method, "lorenz", np.array(y0[sub]), ts, LORENZ)
     for k in ("y_final", "t_final", "n_accept", "n_reject", "n_rhs", "status"):
         assert np.array_equal(got[k][sub], ref[k]), k
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("pinned_out", [False, True])
+def test_progressive_copy_back_bit_exact(pinned_out, monkeypatch):
+    """Staged outputs of a large ensemble go back to the host chunk by chunk while the kernel still runs (the lane that
+    finishes a chunk's last trajectory raises a host flag, the calling thread issues the copies).  Same bits as the
+    copy phase after the kernel, also for chunks completed by the literal pass (a blown-up trajectory) and a ragged
+    last chunk."""
+    rng = np.random.default_rng(21)
+    n = 150001
+    y0 = np.stack([rng.uniform(-10, 10, n), rng.uniform(-10, 10, n), rng.uniform(5, 35, n)], 1)
+    y0[40000] = [1e200, -1e200, 1e200]  # overflows in the first attempt: re-integrated by the literal pass
+    F = m.DeviceRHS("lorenz", *LORENZ)
+    ts = [0.0, 0.5]
+    keys = ("t_final", "y_final", "n_accept", "n_reject", "status")
+
+    def outputs():
+        if not pinned_out:
+            return None
+        return dict(t_final=m.pinned_empty(n), y_final=m.pinned_empty((n, 3)), n_accept=m.pinned_empty(n, np.int32),
+                    n_reject=m.pinned_empty(n, np.int32), status=m.pinned_empty(n, np.int32))
+
+    monkeypatch.setenv("ODE_B200_PROGRESSIVE", "0")
+    plain = m.solve_ensemble("ode45", F, y0, ts, max_steps=500, out=outputs())
+    monkeypatch.setenv("ODE_B200_PROGRESSIVE", "1")
+    got = m.solve_ensemble("ode45", F, y0, ts, max_steps=500, out=outputs())
+    for k in keys:
+        assert np.array_equal(got[k], plain[k], equal_nan=True), k
+    assert got["status"][40000] != 0 and int((got["status"] != 0).sum()) == 1
+    O.use_all_cores()
+    sub = slice(30000, 50000)
+    ref = O.solve_ensemble("ode45", "lorenz", y0[sub], ts, LORENZ, max_steps=500)
+    for k in keys:
+        assert np.array_equal(got[k][sub], ref[k], equal_nan=True), k

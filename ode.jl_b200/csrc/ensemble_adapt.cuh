@@ -400,11 +400,13 @@ __global__ void __launch_bounds__(ENS_BLOCK, LITERAL ? 1 : adapt_min_blocks<Tab,
     double ynum[CNB ? D : 1];
 #pragma unroll
     for (int d = 0; d < D; d++) {  // :430-434
-      double ay = fabs(y[d]), at = fabs(ytrial[d]);
       if (LITERAL) {
+        const double ay = fabs(y[d]), at = fabs(ytrial[d]);
         nanout = nanout || (ytrial[d] != ytrial[d]);  // isoutofdomain, src/ODE.jl:116
         yerr[d] = yerr[d] / (A.abstol + jl_max(ay, at) * A.reltol);  // :433
       } else if (CNB) {
+        // max(|y|, |ytrial|) as an integer compare of the magnitudes' bit patterns (order-preserving for non-NaN values)
+        const double ay = fabs(y[d]), at = fabs(ytrial[d]);
         const bool ygt = (unsigned long long)__double_as_longlong(ay) > (unsigned long long)__double_as_longlong(at);
         ynum[d] = yerr[d];
         yerr[d] = div_nb(yerr[d], recip_prepare(A.abstol + (ygt ? ay : at) * A.reltol), cbad);
@@ -413,6 +415,7 @@ __global__ void __launch_bounds__(ENS_BLOCK, LITERAL ? 1 : adapt_min_blocks<Tab,
       } else {
         // max(|y|, |ytrial|) as an integer compare of the magnitudes' bit patterns (order-preserving for
         // non-NaN values; a NaN trial state sends the trajectory to the literal pass whatever is picked here)
+        const double ay = fabs(y[d]), at = fabs(ytrial[d]);
         const bool ygt = (unsigned long long)__double_as_longlong(ay) > (unsigned long long)__double_as_longlong(at);
         yerr[d] = yerr[d] / (A.abstol + (ygt ? ay : at) * A.reltol);  // :433
         // non-finite <=> exponent field all ones; testing max(exponent fields) keeps these 2*D tests off the

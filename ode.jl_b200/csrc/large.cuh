@@ -754,8 +754,8 @@ __global__ void __launch_bounds__(LARGE_THREADS) large_attempt_kernel(
       const bool valid = (off >= H) && (off < H + VAL) && (li < A.n);
       allvalid = allvalid && valid;
       if (valid) {
-        const double ay = fabs(y[p]), at = fabs(ytrial[p]);
         if (LITERAL) {
+          const double ay = fabs(y[p]), at = fabs(ytrial[p]);
           anynan = anynan || (ytrial[p] != ytrial[p]);
           const double e = yerr[p] / (abstol + ((ay > at) ? ay : at) * reltol);  // :433
           acc = dd_add_sq(acc, e);
@@ -765,11 +765,10 @@ __global__ void __launch_bounds__(LARGE_THREADS) large_attempt_kernel(
           // (integer pipe) instead of the FP64 pipe this kernel is bound by.  Magnitudes compare like unsigned
           // integers; a non-finite trial state always gives a non-finite e (Inf/Inf or NaN), which ends up in
           // mxb and makes the control kernel call for the literal repeat with the reference's exact NaN guard.
-          const unsigned long long ub = (unsigned long long)__double_as_longlong(at);
-          const bool ygt = (unsigned long long)__double_as_longlong(ay) > ub;
-          const double e = yerr[p] / (abstol + (ygt ? ay : at) * reltol);  // :433
+          const double e = yerr[p] / (abstol + max_abs_bits(y[p], ytrial[p]) * reltol);  // :433
           acc = dd_add_sq(acc, e);
-          const unsigned long long eb = (unsigned long long)__double_as_longlong(fabs(e));
+          const unsigned long long eb = ((unsigned long long)((unsigned int)__double2hiint(e) & 0x7fffffffu) << 32) |
+                                        (unsigned long long)(unsigned int)__double2loint(e);
           mxb = mxb > eb ? mxb : eb;
         }
       }

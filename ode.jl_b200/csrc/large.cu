@@ -296,6 +296,8 @@ struct ode_b200_slab {
   bool fused = false;  // stencil path: the attempt kernel's last CTA runs the step controller (single slab, or peers)
   int init_blocks = 0;
   LargeCtl host_ctl;
+  LargeCtl* pin_ctl = nullptr;                // 2 page-locked copies of the control block: slabs_run's pipelined polls
+  cudaEvent_t ev_poll[2] = {nullptr, nullptr};
   // exchange buffers owned by the session (ode_b200_slab_run; the step-wise API takes the caller's)
   double *xs = nullptr, *xr = nullptr;
   // exchange over peer memory (ode_b200_slab_peer_*)
@@ -819,6 +821,9 @@ void ode_b200_slab_free(ode_b200_slab* s) {
   if (s->tq) cudaFree(s->tq);
   if (s->xs) cudaFree(s->xs);
   if (s->xr) cudaFree(s->xr);
+  if (s->pin_ctl) cudaFreeHost(s->pin_ctl);
+  for (int q = 0; q < 2; q++)
+    if (s->ev_poll[q]) cudaEventDestroy(s->ev_poll[q]);
   for (int r = 0; r < PEER_MAX; r++)
     if (s->peer_ipc[r]) cudaIpcCloseMemHandle(s->peer_ipc[r]);
   if (s->peer_block) cudaFree(s->peer_block);
@@ -905,8 +910,8 @@ static int slab_exchange(ode_b200_slab* s, double* xsend, double* xrecv) {
 }
 
 // The whole integration loop of `count` sessions of THIS process, in lockstep: hinit phases, then batches of 4
-// attempts (captured once per session into a CUDA graph and replayed; the done flag is polled after each batch and
-// attempts issued after the end are no-ops).  count = 1: one slab (world = 1), or this process's slab of a grid
+// attempts (captured once per session into a CUDA graph and replayed; the done flag of batch k is looked at while
+// batch k+1 is already queued, and attempts issued after the end are no-ops).  count = 1: one slab (world = 1), or this process's slab of a grid
 // decomposed across processes that are connected over peer memory.  count > 1: all slabs live in this process, one
 // per GPU; every launch is asynchronous, so one host thread keeps all devices busy, and nothing here blocks on a
 // device before the matching work of every other device has been enqueued.
@@ -990,8 +995,21 @@ static int slabs_run(ode_b200_slab* const* ss, int count, double (*polls)[16], f
       batch_launches[g] = ode_b200_launch_count(0) - before;  // counted once at capture; added per replay below
     }
   }
+  // Pipelined polling: batch k+1 is enqueued BEFORE the host looks at the control block batch k left behind (copied
+  // into page-locked memory behind batch k, with an event), so the device never waits for the host's round trip --
+  // 5-7 us per attempt that matter when an attempt is short (small systems, strong scaling), and, across processes,
+  // the ranks' host jitter no longer shows up as a wait for the slowest rank's record.  At most one batch of no-ops
+  // is enqueued past the end.
+  for (int g = 0; g < count && !rc; g++) {
+    ode_b200_slab* s = ss[g];
+    RUN_CUDA(cudaSetDevice(s->device));
+    if (!s->pin_ctl) {
+      RUN_CUDA(cudaHostAlloc((void**)&s->pin_ctl, 2 * sizeof(LargeCtl), cudaHostAllocDefault));
+      for (int q = 0; q < 2; q++) RUN_CUDA(cudaEventCreateWithFlags(&s->ev_poll[q], cudaEventDisableTiming));
+    }
+  }
   bool first_batch = true;
-  while (!rc) {
+  for (long long k = 0; !rc; k++) {
     for (int g = 0; g < count && !rc; g++) {
       ode_b200_slab* s = ss[g];
       RUN_CUDA(cudaSetDevice(s->device));
@@ -1002,15 +1020,21 @@ static int slabs_run(ode_b200_slab* const* ss, int count, double (*polls)[16], f
       } else {
         enqueue_batch(s);
       }
+      RUN_CUDA(cudaMemcpyAsync(&s->pin_ctl[k & 1], s->ctl, sizeof(LargeCtl), cudaMemcpyDeviceToHost, s->stream));
+      RUN_CUDA(cudaEventRecord(s->ev_poll[k & 1], s->stream));
     }
     first_batch = false;
+    if (k == 0) continue;  // keep one batch in flight ahead of the poll
     bool all_done = true;
     for (int g = 0; g < count && !rc; g++) {
-      RUN_TRY(ode_b200_slab_poll(ss[g], polls[g]));
-      all_done = all_done && polls[g][0] != 0.0;
+      ode_b200_slab* s = ss[g];
+      RUN_CUDA(cudaSetDevice(s->device));
+      RUN_CUDA(cudaEventSynchronize(s->ev_poll[(k - 1) & 1]));
+      all_done = all_done && s->pin_ctl[(k - 1) & 1].done != 0;
     }
     if (all_done) break;
   }
+  for (int g = 0; g < count && !rc; g++) RUN_TRY(ode_b200_slab_poll(ss[g], polls[g]));  // (waits for the batch in flight)
   float ms = 0.f;
   for (int g = 0; g < count && !rc; g++) {
     ode_b200_slab* s = ss[g];

@@ -193,7 +193,11 @@ __global__ void __launch_bounds__(STREAM_CHUNK, 2) ens_adapt_stream_init_kernel(
 // 4 CTAs/SM) and tighter bounds that spill.  Larger state x stage products are left unconstrained.
 template <class Tab, class Rhs>
 constexpr int adapt_min_blocks() {
+#ifdef ODEB200_NARROW_MINB
+  return (Rhs::DOF <= 3 && Rhs::DOF * Tab::S <= 21) ? ODEB200_NARROW_MINB : ODEB200_WIDE_MINB;
+#else
   return (Rhs::DOF <= 3 && Rhs::DOF * Tab::S <= 21) ? (5 * 128) / ENS_BLOCK : ODEB200_WIDE_MINB;  // 640 resident threads per SM; 0 = leave it to ptxas
+#endif
 }
 
 // Which (tableau, functor) pairs take the deferred-check controller (ODEB200_CTRL_NB = 2), from measurement

@@ -590,28 +590,42 @@ def test_tail_handoff_second_launch_bit_exact(method, rhs, monkeypatch):
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("method,n", [("ode45", 200000), ("ode45", 6000), ("ode78", 70001), ("ode23", 9999)])
-def test_streaming_prepass_from_pinned_y0_bit_exact(method, n, monkeypatch):
+@pytest.mark.parametrize("method,rhs,n", [("ode45", "lorenz", 200000), ("ode45", "lorenz", 6000), ("ode78", "lorenz", 70001),
+                                          ("ode23", "lorenz", 9999), ("ode78", "kepler", 30011), ("ode45", "vdp", 20000),
+                                          ("ode45_ck", "linear", 5001)])
+def test_streaming_prepass_from_pinned_y0_bit_exact(method, rhs, n, monkeypatch):
     """y0 in page-locked host memory + one parameter vector: the pre-pass reads y0 over PCIe chunk by chunk while the
     persistent kernel is already integrating (ens_adapt_stream_init_kernel) instead of an upload in front of
-    everything.  Same bits as the staged path and as the oracle; ragged sizes exercise the last partial chunk."""
+    everything.  Same bits as the staged path and as the oracle; ragged sizes exercise the last partial chunk, the
+    functors state sizes 1..4 (a chunk of y0 is fetched in 16-byte pieces)."""
     rng = np.random.default_rng(11)
-    y0 = m.pinned_empty((n, 3))
-    y0[:] = np.stack([rng.uniform(-10, 10, n), rng.uniform(-10, 10, n), rng.uniform(5, 35, n)], 1)
-    F = m.DeviceRHS("lorenz", *LORENZ)
-    ts = [0.0, 0.5]
-    L = m.lib()
+    kw = {}
+    if rhs == "lorenz":
+        src = np.stack([rng.uniform(-10, 10, n), rng.uniform(-10, 10, n), rng.uniform(5, 35, n)], 1)
+        F, par, ts = m.DeviceRHS("lorenz", *LORENZ), LORENZ, [0.0, 0.5]
+    elif rhs == "kepler":
+        e = rng.uniform(0, 0.9, n)
+        src = np.stack([1 - e, np.zeros(n), np.zeros(n), np.sqrt((1 + e) / (1 - e))], 1)
+        F, par, ts, kw = m.DeviceRHS("kepler"), None, [0.0, 1.5], dict(reltol=1e-10, abstol=1e-10)
+    elif rhs == "vdp":
+        src = np.stack([rng.uniform(-2, 2, n), rng.uniform(-2, 2, n)], 1)
+        F, par, ts = m.DeviceRHS("vdp", 5.0), [5.0], [0.0, 1.0]
+    else:
+        src = rng.uniform(0.5, 2.0, (n, 1))
+        F, par, ts = m.DeviceRHS("linear", 1.01), [1.01], [0.0, 1.0]
+    y0 = m.pinned_empty(src.shape)
+    y0[:] = src
     monkeypatch.setenv("ODE_B200_STREAM_INIT", "0")
-    plain = m.solve_ensemble(method, F, y0, ts)
+    plain = m.solve_ensemble(method, F, y0, ts, **kw)
     monkeypatch.setenv("ODE_B200_STREAM_INIT", "1")
     for direct in (False, True):
-        got = m.solve_ensemble(method, F, y0, ts, direct_output=direct)
+        got = m.solve_ensemble(method, F, y0, ts, direct_output=direct, **kw)
         assert_same(got, plain)
-    pageable = m.solve_ensemble(method, F, np.array(y0), ts)  # a pageable copy takes the staged path
+    pageable = m.solve_ensemble(method, F, np.array(y0), ts, **kw)  # a pageable copy takes the staged path
     assert_same(pageable, plain)
     sub = slice(0, min(n, 20000))
     O.use_all_cores()
-    ref = O.solve_ensemble(method, "lorenz", np.array(y0[sub]), ts, LORENZ)
+    ref = O.solve_ensemble(method, rhs, np.array(y0[sub]), ts, par, **kw)
     for k in ("y_final", "t_final", "n_accept", "n_reject", "n_rhs", "status"):
         assert np.array_equal(got[k][sub], ref[k]), k
 

@@ -1242,6 +1242,35 @@ int ode_b200_solve_large_all(const ode_b200_opts* o, int64_t n, const double* y0
                           cap_rows, n_rows);
 }
 
+// ODE_B200_GUARD_CHECK=1 (tests; compute-sanitizer is not available on every pool): every state / stage array of a
+// session is allocated with a zeroed tail behind the last ghost cell; no kernel may ever write there.  Counts the
+// doubles of those tails that are no longer +0.
+__global__ void guard_count_kernel(const double* a, long long lo, long long hi, unsigned int* count) {
+  for (long long i = lo + blockIdx.x * (long long)blockDim.x + threadIdx.x; i < hi; i += (long long)gridDim.x * blockDim.x)
+    if (__double_as_longlong(a[i]) != 0LL) atomicAdd(count, 1u);
+}
+static int slab_guard_violations(ode_b200_slab* s, long long* out) {
+  *out = 0;
+  unsigned int* d = nullptr;
+  ODEB200_CUDA(cudaMalloc(&d, sizeof(unsigned int)));
+  ODEB200_CUDA(cudaMemsetAsync(d, 0, sizeof(unsigned int), s->stream));
+  const long long lo = s->n + 2 * s->mi.H, hi = lo + 8 + LARGE_THREADS * LARGE_P;
+  const double* arrays[4 + FIELD_MAX_STAGES + 2] = {s->Y[0], s->Y[1], s->K[0], s->K[1]};
+  int na = 4;
+  for (int q = 0; q < FIELD_MAX_STAGES; q++)
+    if (s->KS[q]) arrays[na++] = s->KS[q];
+  for (int q = 0; q < 2; q++)
+    if (s->T[q]) arrays[na++] = s->T[q];
+  for (int q = 0; q < na; q++)
+    if (arrays[q]) guard_count_kernel<<<2, 256, 0, s->stream>>>(arrays[q], lo, hi, d);
+  unsigned int h = 0;
+  ODEB200_CUDA(cudaMemcpyAsync(&h, d, sizeof(h), cudaMemcpyDeviceToHost, s->stream));
+  ODEB200_CUDA(cudaStreamSynchronize(s->stream));
+  cudaFree(d);
+  *out = h;
+  return 0;
+}
+
 static int solve_large_impl(const ode_b200_opts* o, int64_t n, const double* y0, const double* params,
                             const double* tspan, int32_t n_tspan, double* y_out, double* pts_out,
                             ode_b200_large_stats* stats, double* trace, int64_t trace_cap, int64_t* trace_n,
@@ -1336,6 +1365,20 @@ static int solve_large_impl(const ode_b200_opts* o, int64_t n, const double* y0,
     if (trace_n) *trace_n = tn;
   }
   LARGE_CUDA(cudaStreamSynchronize(st));
+  if (!rc && s && getenv("ODE_B200_GUARD_CHECK")) {
+    long long bad = 0;
+    if (getenv("ODE_B200_GUARD_SELFTEST"))  // (the check checked: poke one double of a tail, the solve must fail)
+      LARGE_CUDA(cudaMemsetAsync(s->K[1] + s->n + 2 * s->mi.H + 3, 0x3f, 8, st));
+    LARGE_TRY(slab_guard_violations(s, &bad));
+    if (!rc && bad) {
+      rc = set_err(ODE_B200_E_INVALID, "guard check: %lld doubles behind the slab's ghost cells were written", bad);
+      for (int i = 0; i < 2; i++) {  // (leave the cached session clean)
+        cudaMemsetAsync(s->Y[i] + s->n + 2 * s->mi.H, 0, (8 + LARGE_THREADS * LARGE_P) * sizeof(double), st);
+        cudaMemsetAsync(s->K[i] + s->n + 2 * s->mi.H, 0, (8 + LARGE_THREADS * LARGE_P) * sizeof(double), st);
+      }
+      cudaStreamSynchronize(st);
+    }
+  }
   if (!rc && stats) {
     const float ms = run_ms;
     stats->n_accept = (int64_t)poll[2];

@@ -663,3 +663,60 @@ def test_progressive_copy_back_bit_exact(pinned_out, monkeypatch):
     ref = O.solve_ensemble("ode45", "lorenz", y0[sub], ts, LORENZ, max_steps=500)
     for k in keys:
         assert np.array_equal(got[k][sub], ref[k], equal_nan=True), k
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("method,rhs,n", [("ode45", "lorenz", 5001), ("ode45", "lorenz", 100003), ("ode78", "kepler", 4099),
+                                          ("ode23s", "robertson", 4097), ("ode23", "vdp", 333)])
+def test_device_entry_point_writes_nothing_outside_its_output_arrays(method, rhs, n):
+    """Own bounds check of the ensemble kernels (compute-sanitizer is not available on every pool): every output array
+    of ode_b200_solve_ensemble_dev sits between two canary margins in one device allocation; after the solve (pre-pass,
+    persistent kernel, literal pass) the margins must be intact and the payload complete."""
+    import ctypes as C
+    import torch
+    from ode_jl_b200 import _lib
+    dev = torch.device("cuda", 0)
+    rng = np.random.default_rng(9)
+    if rhs == "lorenz":
+        y0 = np.stack([rng.uniform(-10, 10, n), rng.uniform(-10, 10, n), rng.uniform(5, 35, n)], 1)
+        F, ts, kw = m.DeviceRHS("lorenz", *LORENZ), [0.0, 0.5], {}
+    elif rhs == "kepler":
+        e = rng.uniform(0, 0.9, n)
+        y0 = np.stack([1 - e, np.zeros(n), np.zeros(n), np.sqrt((1 + e) / (1 - e))], 1)
+        F, ts, kw = m.DeviceRHS("kepler"), [0.0, 1.0], dict(reltol=1e-10, abstol=1e-10)
+    elif rhs == "robertson":
+        y0 = np.tile([1.0, 0.0, 0.0], (n, 1))
+        F, ts, kw = m.DeviceRHS("robertson", 0.04, 3e7, 1e4), [0.0, 10.0], dict(reltol=1e-6, abstol=1e-8)
+    else:
+        y0 = np.stack([rng.uniform(-2, 2, n), rng.uniform(-2, 2, n)], 1)
+        F, ts, kw = m.DeviceRHS("vdp", 5.0), [0.0, 1.0], {}
+    dof = y0.shape[1]
+    M = 1024  # canary elements on either side
+    CAN64, CAN32 = float.fromhex("0x1.dead1p+700"), 0x5EADBEEF
+
+    def guarded(count, dtype):
+        t = torch.full((count + 2 * M,), CAN64 if dtype == torch.float64 else CAN32, dtype=dtype, device=dev)
+        return t, t[M:M + count]
+
+    bufs = {k: guarded(c, dt) for k, c, dt in (("t_final", n, torch.float64), ("y_final", n * dof, torch.float64),
+                                               ("n_accept", n, torch.int32), ("n_reject", n, torch.int32),
+                                               ("n_rhs", n, torch.int32), ("status", n, torch.int32))}
+    d_y0 = torch.from_numpy(np.ascontiguousarray(y0)).to(dev)
+    par = F.param_array()
+    d_par = torch.from_numpy(np.ascontiguousarray(par if par is not None else np.zeros(1))).to(dev)
+    d_ts = torch.tensor(ts, dtype=torch.float64, device=dev)
+    opts = m.make_opts(method, F, np.array(ts), points="final", **kw)
+    io = _lib.EnsembleIO()
+    io.n_traj, io.n_tspan, io.trace_traj = n, 2, -1
+    io.y0, io.params, io.tspan = d_y0.data_ptr(), d_par.data_ptr(), d_ts.data_ptr()
+    for k in bufs:
+        setattr(io, k, bufs[k][1].data_ptr())
+    _lib.check(m.lib().ode_b200_solve_ensemble_dev(C.byref(opts), C.byref(io), C.c_void_p(torch.cuda.current_stream().cuda_stream)))
+    torch.cuda.synchronize()
+    for k, (whole, view) in bufs.items():
+        can = CAN64 if whole.dtype == torch.float64 else CAN32
+        assert bool((whole[:M] == can).all()) and bool((whole[M + view.numel():] == can).all()), "canary of %s overwritten" % k
+        assert not bool((view == can).any()), "%s not completely written" % k
+    ref = m.solve_ensemble(method, F, y0, ts, **kw)
+    assert np.array_equal(bufs["y_final"][1].cpu().numpy().reshape(n, dof), ref["y_final"])
+    assert np.array_equal(bufs["status"][1].cpu().numpy(), ref["status"])

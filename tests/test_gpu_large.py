@@ -543,3 +543,38 @@ def test_slab_points_specified_with_rejections_two_ranks():
     assert np.array_equal(torch.cat(outs, 1).cpu().numpy(), ref.y)
     for e in engines:
         e.close()
+
+
+@pytest.mark.gpu
+def test_guard_zones_behind_the_slab_stay_untouched(monkeypatch):
+    """compute-sanitizer is not available on every pool, so the library carries its own bounds check for the arrays
+    the tile / ghost indexing writes: every state and stage array has a zeroed tail behind the last ghost cell, and
+    with ODE_B200_GUARD_CHECK=1 a solve fails if any kernel wrote there.  Ragged sizes (partial last tile, sizes
+    around tile multiples), every tableau (ghost widths 4 .. 24), wide registered stencils (ghost widths up to 52),
+    the stage-per-kernel field path, output modes."""
+    monkeypatch.setenv("ODE_B200_GUARD_CHECK", "1")
+    F = m.DeviceRHS("reaction_diffusion", 1.0, 1.0)
+    for n in (33, 495, 496, 497, 511, 512, 513, 700, 991, 992, 993, 4096, 5003, 65537, 300007):
+        r = m.solve_large("ode45", F, u0(n), [0.0, 0.6])
+        assert r["status"] == 0, n
+    for method in ("ode21", "ode23", "ode45_fe", "ode45", "ode45_ck", "ode78"):
+        for n in (481, 700, 5003):
+            assert m.solve_large(method, F, u0(n), [0.0, 0.5])["status"] == 0, (method, n)
+    for radius in (2, 3, 4):
+        body, _ = _wide_stencil(radius) if radius > 2 else ("return p[0] * ((((-w[0] + 16.0*w[1]) - 30.0*w[2]) + 16.0*w[3]) - w[4]) / 12.0;", None)
+        S = m.register_stencil("guard_r%d" % radius, body, params=(0.9, 0.4) if radius > 2 else (0.1,), radius=radius)
+        for method in ("ode45", "ode78"):
+            assert m.solve_large(method, S, u0(1500), [0.0, 0.4])["status"] == 0, (radius, method)
+    G = m.DeviceRHS("reaction_diffusion_field", 1.0, 1.0)
+    for n in (700, 5003):
+        assert m.solve_large("ode45", G, u0(n), [0.0, 0.5])["status"] == 0
+    r = m.solve_large("ode45", F, u0(5003), [0.0, 0.2, 0.5], points="specified")
+    assert r["status"] == 0
+    t, y = m.ode45(F, u0(700), [0.0, 0.3, 0.5])  # points = :all through the front end
+    assert t[-1] == 0.5
+    # the check itself: with one double of a tail poked on purpose the same solve must fail
+    monkeypatch.setenv("ODE_B200_GUARD_SELFTEST", "1")
+    with pytest.raises(Exception, match="guard check: 1 doubles"):
+        m.solve_large("ode45", F, u0(700), [0.0, 0.5])
+    monkeypatch.delenv("ODE_B200_GUARD_SELFTEST")
+    assert m.solve_large("ode45", F, u0(700), [0.0, 0.5])["status"] == 0

@@ -13,6 +13,11 @@
  * (|y*log(x)| < 64), i.e. they equal the correctly rounded result except in
  * rare near-tie cases (checked against mpmath in tests/test_detmath.py).
  *
+ * The exponents the step controllers actually use -- the doubles nearest 1/3, 1/5 and 1/8 -- take a K-th root path
+ * (dm_root3/5/8 below: the same argument reduction, a table of (2^s/invc)^(1/K), one short binomial series) that
+ * costs half the arithmetic of the general log/exp path at the same accuracy; every other exponent (hinit's
+ * 10^x, src/ODE.jl:108) takes the general path.
+ *
  * Technique (standard, table-driven): log via an exact fma reduction
  * r = z*invc - 1 with an 8-bit invc and a 128-entry log(c) table kept as
  * hi + lo, a degree-10 Taylor tail (pairwise evaluation), result carried as a double-double; exp via
@@ -58,18 +63,26 @@ typedef unsigned long long uint64_t;
 #ifndef __CUDACC_RTC__
 static const double dm_logtab_h[128 * 3] = {DM_LOG_TABLE(DM_X3)};
 static const double dm_exptab_h[128 * 2] = {DM_EXP_TABLE(DM_X2)};
+static const double dm_root3tab_h[3 * 128 * 2] = {DM_ROOT3_TABLE(DM_X2)};
+static const double dm_root5tab_h[5 * 128 * 2] = {DM_ROOT5_TABLE(DM_X2)};
+static const double dm_root8tab_h[8 * 128 * 2] = {DM_ROOT8_TABLE(DM_X2)};
 #endif
 #if defined(__CUDACC__)
 static __device__ const double dm_logtab_d[128 * 3] = {DM_LOG_TABLE(DM_X3)};
 static __device__ const double dm_exptab_d[128 * 2] = {DM_EXP_TABLE(DM_X2)};
+static __device__ const double dm_root3tab_d[3 * 128 * 2] = {DM_ROOT3_TABLE(DM_X2)};
+static __device__ const double dm_root5tab_d[5 * 128 * 2] = {DM_ROOT5_TABLE(DM_X2)};
+static __device__ const double dm_root8tab_d[8 * 128 * 2] = {DM_ROOT8_TABLE(DM_X2)};
 #endif
 
 #if defined(__CUDA_ARCH__)
 #define DM_LOGTAB(i) dm_logtab_d[(i)]
 #define DM_EXPTAB(i) dm_exptab_d[(i)]
+#define DM_ROOTTAB(K, i) ((K) == 3 ? dm_root3tab_d[(i)] : ((K) == 5 ? dm_root5tab_d[(i)] : dm_root8tab_d[(i)]))
 #else
 #define DM_LOGTAB(i) dm_logtab_h[(i)]
 #define DM_EXPTAB(i) dm_exptab_h[(i)]
+#define DM_ROOTTAB(K, i) ((K) == 3 ? dm_root3tab_h[(i)] : ((K) == 5 ? dm_root5tab_h[(i)] : dm_root8tab_h[(i)]))
 #endif
 
 DM_HD uint64_t dm_bits(double x) {
@@ -214,6 +227,63 @@ DM_HD double dm_exp_dd(double ehi, double elo) {
   }
 }
 
+/* x^y for the three exponents the step controllers use, y = the double nearest 1/K with K = 3, 5, 8
+ * ((1/err)^(1/(order+1)), src/runge_kutta.jl:436; (delta/err)^(1/3), src/ODE.jl:357), for positive finite x
+ * (normal or subnormal).  Half the arithmetic of the general path and the same accuracy (0.5 ulp + ~2^-15 ulp):
+ *     x = 2^k z,  z*invc_i = 1 + r exactly (the log table's reduction),  k = K q + s,  0 <= s < K
+ *     x^(1/K) = 2^q * R[s][i] * (1 + r)^(1/K)            R[s][i] = (2^s / invc_i)^(1/K) tabulated as hi + lo
+ *     (1 + r)^(1/K) = 1 + r/K + r^2 Q(r)                 |r| < 2^-7: binomial series to r^9, r/K with 1/K = AH + AL
+ *     x^y = x^(1/K) * exp((y - 1/K) ln x)                y - 1/K = DELTA ~ 1e-17: 1 + DELTA ln x, ln x to 2^-40
+ * with the sum R*(1 + ...) accumulated so that there is one effective rounding. */
+#define DM_ROOT_BODY(K, AH, AL, DELTA, C0, C1, C2, C3, C4, C5, C6, C7)                                              \
+  uint64_t ix = dm_bits(x);                                                                                         \
+  int64_t kadj = 0;                                                                                                 \
+  if (ix < 0x0010000000000000ULL) { /* subnormal: scale by 2^52 (exact) */                                          \
+    x = x * 4503599627370496.0;                                                                                     \
+    ix = dm_bits(x);                                                                                                \
+    kadj = -52;                                                                                                     \
+  }                                                                                                                 \
+  const uint64_t tmp = ix - 0x3FE6A00000000000ULL;                                                                  \
+  const int i = (int)((tmp >> 45) & 127);                                                                           \
+  const int64_t k = ((int64_t)tmp >> 52) + kadj;                                                                    \
+  const double z = dm_from_bits(ix - (tmp & 0xFFF0000000000000ULL));                                                \
+  int64_t sft = k % (K);                                                                                            \
+  if (sft < 0) sft += (K);                                                                                          \
+  const int64_t q = (k - sft) / (K);                                                                                \
+  const double invc = DM_LOGTAB(3 * i), logc = DM_LOGTAB(3 * i + 1);                                                \
+  const double rh = DM_ROOTTAB(K, 2 * ((int)sft * 128 + i)), rl = DM_ROOTTAB(K, 2 * ((int)sft * 128 + i) + 1);      \
+  const double r = dm_fma(z, invc, -1.0); /* exact */                                                               \
+  const double t1h = r * (AH);                                                                                      \
+  double plo = dm_fma(r, (AL), dm_fma(r, (AH), -t1h)); /* r/K = t1h + plo */                                        \
+  const double r2 = r * r;                                                                                          \
+  const double p01 = dm_fma((C1), r, (C0)), p23 = dm_fma((C3), r, (C2));                                            \
+  const double p45 = dm_fma((C5), r, (C4)), p67 = dm_fma((C7), r, (C6));                                            \
+  const double r4 = r2 * r2;                                                                                        \
+  const double qq = dm_fma(dm_fma(p67, r2, p45), r4, dm_fma(p23, r2, p01));                                         \
+  plo = dm_fma(r2, qq, plo);                                                                                        \
+  if ((DELTA) != 0.0) { /* (1 + t1h + plo)(1 + c) = 1 + t1h + (plo + c + c*t1h), c = DELTA ln x */                  \
+    const double c = (DELTA) * (dm_fma((double)k, DM_LN2_HI, logc) + r);                                            \
+    plo = dm_fma(c, t1h, plo) + c;                                                                                  \
+  }                                                                                                                 \
+  const double w = rh * t1h;                                                                                        \
+  const double v = dm_fma(rh, plo, dm_fma(rl, t1h, rl)) + dm_fma(rh, t1h, -w);                                      \
+  const double sm = rh + w;                                                                                         \
+  const double tail = ((rh - sm) + w) + v; /* fast two-sum: |rh| > |w| */                                           \
+  return (sm + tail) * dm_from_bits((uint64_t)(q + 1023) << 52);
+
+DM_HD double dm_root3(double x) {
+  DM_ROOT_BODY(3, DM_ROOT3_AH, DM_ROOT3_AL, DM_ROOT3_DELTA, DM_ROOT3_C0, DM_ROOT3_C1, DM_ROOT3_C2, DM_ROOT3_C3, DM_ROOT3_C4,
+               DM_ROOT3_C5, DM_ROOT3_C6, DM_ROOT3_C7)
+}
+DM_HD double dm_root5(double x) {
+  DM_ROOT_BODY(5, DM_ROOT5_AH, DM_ROOT5_AL, DM_ROOT5_DELTA, DM_ROOT5_C0, DM_ROOT5_C1, DM_ROOT5_C2, DM_ROOT5_C3, DM_ROOT5_C4,
+               DM_ROOT5_C5, DM_ROOT5_C6, DM_ROOT5_C7)
+}
+DM_HD double dm_root8(double x) {
+  DM_ROOT_BODY(8, DM_ROOT8_AH, DM_ROOT8_AL, DM_ROOT8_DELTA, DM_ROOT8_C0, DM_ROOT8_C1, DM_ROOT8_C2, DM_ROOT8_C3, DM_ROOT8_C4,
+               DM_ROOT8_C5, DM_ROOT8_C6, DM_ROOT8_C7)
+}
+
 /* x^y for x >= 0.  Negative x returns NaN (Julia raises DomainError there;
  * the solvers only ever pass norms and ratios of norms).  Positive normal
  * finite x with finite y -- every controller call -- is recognised with integer
@@ -233,6 +303,13 @@ DM_HD double dm_pow(double x, double y) {
     if (y == -(double)INFINITY) return x == 1.0 ? 1.0 : (x > 1.0 ? 0.0 : (double)INFINITY);
     /* positive subnormal x, finite y: falls through */
   }
+#ifndef DM_NO_ROOTS
+  /* the controllers' exponents (compile-time constants at every hot call site: the tests fold away) */
+  if (y == 0.5) return sqrt(x); /* IEEE square root on both sides: the correctly rounded x^(1/2) */
+  if (y == DM_ROOT5_AH) return dm_root5(x);
+  if (y == DM_ROOT3_AH) return dm_root3(x);
+  if (y == DM_ROOT8_AH) return dm_root8(x);
+#endif
   dm_dd l = dm_log_dd(x);
   double ehi = y * l.hi;
   double elo = dm_fma(y, l.lo, dm_fma(y, l.hi, -ehi));

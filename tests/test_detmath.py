@@ -31,6 +31,22 @@ def test_pow_correctly_rounded_on_controller_domain():
     assert bad == 0
 
 
+@pytest.mark.parametrize("y", [1.0 / 3, 0.2, 0.125])
+def test_controller_roots_correctly_rounded(y):
+    """The K-th root path of the controllers' exponents (dm_root3/5/8): correctly rounded on every sample over the whole
+    positive range (subnormal to 1.8e308), at exact powers, next to 1, and equal to the general path except where that
+    one misrounds (it never does on these samples either)."""
+    mp.mp.prec = 300
+    rng = np.random.default_rng(int(1 / y))
+    n = 20000
+    x = np.concatenate([np.exp(rng.uniform(-700, 700, n // 2)), np.exp(rng.uniform(-3, 3, n // 2)),
+                        [5e-324, 1e-310, 2.2250738585072014e-308, 2.0 ** -1022, 1.0, 2.0, 8.0, 32.0, 243.0, 256.0,
+                         1.0000000000000002, 0.9999999999999999, 1.7976931348623157e308]])
+    got = _powv(x, np.full(x.size, y))
+    bad = sum(1 for i in range(x.size) if float(mp.power(mp.mpf(float(x[i])), mp.mpf(y))) != got[i])
+    assert bad == 0
+
+
 def test_pow10_and_log10_correctly_rounded():
     mp.mp.prec = 200
     rng = np.random.default_rng(12)

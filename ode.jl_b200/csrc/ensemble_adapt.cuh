@@ -193,6 +193,9 @@ __global__ void __launch_bounds__(STREAM_CHUNK, 2) ens_adapt_stream_init_kernel(
 // 4 CTAs/SM) and tighter bounds that spill.  Larger state x stage products are left unconstrained.
 template <class Tab, class Rhs>
 constexpr int adapt_min_blocks() {
+  // 13 stages x 4 components: unconstrained ptxas takes 152 registers (3 CTAs/SM); 128 registers with a 96-byte spill
+  // (4 CTAs/SM) measured 2 % faster on Kepler/feh78 (17.66 -> 17.29 ms, profiles/ensemble_kernels_r2.md)
+  if (ODEB200_WIDE_MINB == 0 && Rhs::DOF >= 4 && Tab::S >= 13 && ENS_BLOCK == 128) return 4;
 #ifdef ODEB200_NARROW_MINB
   return (Rhs::DOF <= 3 && Rhs::DOF * Tab::S <= 21) ? ODEB200_NARROW_MINB : ODEB200_WIDE_MINB;
 #else

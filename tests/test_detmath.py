@@ -89,3 +89,18 @@ def test_detmath_close_to_libm():
     # both are within an ulp of each other, and they differ on well under 1% of inputs
     assert np.max(np.abs(a - b) / np.spacing(np.abs(a))) <= 1.0
     assert np.mean(a != b) < 0.01
+
+
+def test_tables_header_is_what_the_generator_writes():
+    """include/ode_b200_detmath_tables.h is generated (tools/gen_detmath_tables.py, mpmath): the committed file must be
+    byte for byte the generator's output, so a table can never drift from its documented construction."""
+    import io
+    import os
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    sys.path.insert(0, os.path.join(root, "tools"))
+    import gen_detmath_tables as G
+    buf = io.StringIO()
+    G.main(buf)
+    mp.mp.prec = 200  # (the generator raises the working precision; restore the tests' own)
+    assert buf.getvalue() == open(os.path.join(root, "include", "ode_b200_detmath_tables.h")).read()

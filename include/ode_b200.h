@@ -244,7 +244,11 @@ int ode_b200_register_field(const char* name, int32_t n_params, const char* rhs_
 
 /* ---- ensembles of small systems (one trajectory per thread) -------------- */
 /* Replaces n_traj independent calls of oderk_adapt / oderk_fixed / ode23s.
- * Host buffers; H2D, kernel and D2H happen inside the call. */
+ * Host buffers; every transfer happens inside the (blocking) call.  For large adaptive-RK ensembles the transfers
+ * run beside the one persistent kernel instead of around it: y0 in page-locked memory (one parameter vector) is read
+ * by the hinit pre-pass over PCIe while the persistent kernel already integrates; outputs in page-locked memory are
+ * written by the kernel as trajectories end (opts.host_output = 1), staged outputs are copied back chunk by chunk
+ * while it runs.  Pageable buffers work too (uploaded first / copied through the driver's staging). */
 int ode_b200_solve_ensemble(const ode_b200_opts* opts, const ode_b200_ensemble_io* io);
 /* Same, but every pointer in `io` is a device pointer on opts->device (tspan
  * included); work is enqueued on `stream` (a cudaStream_t, NULL = default
